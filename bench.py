@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py -- AF evals/s of the MetaBO hot path on B200 (see BASELINE.json).
+
+A "step" is one AF-optimisation round (what the reference runs per environment step,
+metabo_gym.py:195-217) for B parallel BO episodes: GP refit, then three dependent candidate phases
+(multistart grid -> k local Sobol grids -> xi_t), each = GP posterior + NeuralAF MLP + reduction,
+ending in the greedy action.  Workload = configs[1] of BASELINE.json: evaluate_metabo_hm3.py
+(Hartmann-3, D=3, F=7, 4x200 ReLU policy `weights_1988`, N_MS=1728, N_LS=2000, k=5 ->
+1728 + 10000 + 1733 = 13461 candidates per episode and round) at B=1024 episodes per GPU with
+n = T = 30 observations per episode (the most expensive round of an episode).
+
+  value   AF evals/s with the observations already resident in HBM
+  e2e     same metric through the public engine API with HOST buffers (H2D of X/Y/n/scalars and
+          D2H of the chosen actions inside the timed region)
+  --impl reference   the reference algorithm's CPU path (oracle port, all host cores)
+
+Multi-GPU: episodes are independent -> every rank runs its own B episodes (weak scaling, no
+data-path collective); rank 0 prints one JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HM3 = dict(D=3, T=30, N_MS=2000, N_LS=2000, k=5, kernel="RBF",
+           features=["posterior_mean", "posterior_std", "timestep", "budget", "x"],
+           lengthscale=[0.716, 0.298, 0.186], variance=0.83, noise=1.688e-11)
+MLP_FLOPS = 2 * (7 * 200 + 3 * 200 * 200 + 200)       # 243 200 per candidate
+
+
+def gp_flops(n, D):
+    return n * n + n * (3 * D + 8)
+
+
+def load_weights():
+    """shipped HM3 policy if the fixture is present, else N(0, 0.01) weights of the same shape."""
+    p = os.path.join(ROOT, "tests", "golden", "weights_hm3_1988.npz")
+    if os.path.exists(p):
+        z = np.load(p)
+        W = [z["policy_net.fc.%d.weight" % i] for i in range(5)]
+        b = [z["policy_net.fc.%d.bias" % i] for i in range(5)]
+        return W, b, "shipped iclr2020 hm3/M_50 weights_1988"
+    rng = np.random.RandomState(0)
+    dims = [7, 200, 200, 200, 200, 1]
+    W = [rng.normal(0, 0.01, (dims[i + 1], dims[i])).astype(np.float32) for i in range(5)]
+    b = [np.zeros(dims[i + 1], dtype=np.float32) for i in range(5)]
+    return W, b, "random N(0,0.01) init"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm on host cores (oracle port; the reference's GPy is not
+# installable).  One forked worker per core, torch pinned to 1 thread per worker,
+# exactly the reference's deployment (batchrecorder.py:24,162).
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    seed, rounds, n = args
+    import torch
+    torch.set_num_threads(1)
+    from oracle import metabo_oracle as O
+    pw = O.PolicyWeights.from_npz(os.path.join(ROOT, "tests", "golden", "weights_hm3_1988.npz"))
+    grids = O.Grids(HM3["D"], N_MS=HM3["N_MS"], N_LS=HM3["N_LS"], k=HM3["k"])
+    rng = np.random.RandomState(seed)
+    cands = 0
+    t0 = time.perf_counter()
+    for _ in range(rounds):
+        X = rng.rand(n, HM3["D"])
+        Y = O.hm3_var(X, rng.uniform(-0.1, 0.1, 3), rng.uniform(0.9, 1.1))[:, 0]
+        gp = O.EpisodeGP(HM3["D"], "RBF", HM3["variance"], HM3["lengthscale"], HM3["noise"])
+        gp.set_data(X, Y)
+        r = O.af_round(gp, grids, pw, HM3["features"], n, HM3["T"])
+        cands += grids.N_MS + grids.k * grids.N_LS + r["xi_t"].shape[0]
+    return cands, time.perf_counter() - t0
+
+
+def cpu_arm(rounds_per_core, n, cores=None):
+    import multiprocessing as mp
+    cores = cores or os.cpu_count()
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, [(1000 + i, rounds_per_core, n) for i in range(cores)])
+    wall = time.perf_counter() - t0
+    cands = sum(r[0] for r in res)
+    busy = max(r[1] for r in res)
+    return dict(value=cands / busy, unit="AF evals/s", cores=cores, kind="port",
+                sample="%d episodes-rounds (n=%d obs, 13461 candidates each) on %d forked workers, "
+                       "oracle port of GPy-route GP + torch-CPU NeuralAF, 1 thread/worker; %.1fs wall"
+                       % (rounds_per_core * cores, n, cores, wall)), cands, busy
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    per_step = []
+    total_c = 0
+    for i in range(args.warmup + args.steps):
+        cb, cands, busy = cpu_arm(1, args.n_obs)
+        if i >= args.warmup:
+            per_step.append(busy)
+            total_c += cands
+    t = sum(per_step)
+    v = total_c / t
+    line = {"metric": "AF evals/sec (GP posterior+NeuralAF per candidate)", "impl": "reference", "value": v,
+            "unit": "AF evals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64 GP + f32 MLP", "data": "synthetic",
+            "config": workload_config(args, cb["cores"], ref=True),
+            "cpu_baseline": dict(cb, value=v),
+            "e2e": {"value": v, "unit": "AF evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(args, B, ref=False):
+    c = {"workload": "evaluate_metabo_hm3.py AF-optimisation round (BASELINE configs[1]): D=3, F=7, 4x200 ReLU "
+                     "policy, candidates 1728+10000+1733 per episode, n=%d observations" % args.n_obs,
+         "episodes_per_gpu": B, "candidates_per_episode_round": 13461, "n_obs": args.n_obs}
+    if ref:
+        c["episodes_per_step"] = B
+    else:
+        c.update(gp_precision=args.gp, mlp_mode=args.mlp, l2="flushed between timed steps (256 MiB write)")
+    return c
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.f.read().splitlines():
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if sm:
+            # "under load" = samples in the upper half of the observed power/clock activity
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--B", type=int, default=1024, help="episodes per GPU")
+    ap.add_argument("--n-obs", dest="n_obs", type=int, default=30)
+    ap.add_argument("--gp", default="fp64", choices=["fp64", "fp32"])
+    ap.add_argument("--mlp", default="auto", choices=["auto", "fp32", "tf32", "bf16x3"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from metabo_b200 import _lib as L
+    from metabo_b200.engine import AFEngine
+    from metabo_b200.sobol import i4_sobol_generate
+    from metabo_b200 import objectives
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, D, T, n = args.B, HM3["D"], HM3["T"], args.n_obs
+    gp_prec = {"fp64": L.GP_FP64, "fp32": L.GP_FP32}[args.gp]
+    W, bvec, wdesc = load_weights()
+    Wt = [torch.as_tensor(w, device=dev) for w in W]
+    bt = [torch.as_tensor(x, device=dev) for x in bvec]
+
+    def make_engine(mode):
+        e = AFEngine(B, D, T, HM3["features"], kernel=HM3["kernel"], N_MS=HM3["N_MS"], N_LS=HM3["N_LS"], k=HM3["k"],
+                     local_search_grid=i4_sobol_generate(D, HM3["N_LS"]), gp_precision=gp_prec, mlp_mode=mode,
+                     device=dev)
+        e.set_policy(Wt, bt, "relu")
+        e.set_hyperparameters(HM3["lengthscale"], HM3["variance"], HM3["noise"])
+        return e
+
+    # synthetic observations, generated on the device for the resident arm and mirrored in pinned
+    # host memory for the e2e arm
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    X = torch.zeros((B, T, D), dtype=torch.float64, device=dev)
+    X[:, :n] = torch.rand((B, n, D), generator=g, dtype=torch.float64, device=dev)
+    tr = (torch.rand((B, D), generator=g, dtype=torch.float64, device=dev) - 0.5) * 0.2
+    sc = 0.9 + 0.2 * torch.rand((B,), generator=g, dtype=torch.float64, device=dev)
+    Y = torch.zeros((B, T), dtype=torch.float64, device=dev)
+    Y[:, :n] = objectives.hm3_var(X[:, :n], tr[:, None, :], sc[:, None])
+    nvec = torch.full((B,), n, dtype=torch.int32, device=dev)
+    inc = Y[:, :n].max(dim=1).values.float() if n > 0 else torch.zeros(B, device=dev)
+    tvec = torch.full((B,), float(n), device=dev)
+    Tvec = torch.full((B,), float(T), device=dev)
+
+    modes = {"fp32": L.MLP_FP32, "tf32": L.MLP_TF32, "bf16x3": L.MLP_BF16X3}
+    order = ["tf32", "bf16x3", "fp32"] if args.mlp == "auto" else [args.mlp]
+    eng = None
+    for m in order:
+        try:
+            e = make_engine(modes[m])
+            e.set_data(X, Y, nvec, n_active_max=n)
+            e.set_episode_scalars(inc, tvec, Tvec)
+            e.af_round()
+            torch.cuda.synchronize()
+            eng, args.mlp = e, m
+            break
+        except L.MboError as ex:
+            if args.mlp != "auto":
+                raise
+            sys.stderr.write("[bench] mlp mode %s unavailable: %s\n" % (m, ex))
+    assert eng is not None
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, profile=False):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        sampler = ClockSampler(local_rank) if profile else None
+        evs = []
+        l0 = eng.launches
+        for _ in range(steps):
+            flush.fill_(1)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn()
+            e.record()
+            evs.append((s, e))
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        ms = sum(s.elapsed_time(e) for s, e in evs)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        return ms, clocks, eng.launches - l0
+
+    # ---- resident arm ----
+    eng.kernel_events = []          # (tag, start, end) around the MLP launches, see engine.evaluate
+    ms, clocks, launches = timed(lambda: eng.af_round(), args.steps, args.warmup, profile=True)
+    kev = eng.kernel_events
+    eng.kernel_events = None
+    cands_step = B * 13461
+    value = world * cands_step * args.steps / (ms / 1e3)
+
+    # dominant kernel: the NeuralAF MLP launch on the 10 000-candidate local phase
+    mlp_big = [s.elapsed_time(e) for tag, s, e in kev if tag == "mlp_M%d" % (HM3["k"] * HM3["N_LS"])]
+    gp_big = [s.elapsed_time(e) for tag, s, e in kev if tag == "gp_M%d" % (HM3["k"] * HM3["N_LS"])]
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else \
+        "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+    roof = None
+    if mlp_big:
+        dur = float(np.mean(mlp_big)) / 1e3
+        ach = B * HM3["k"] * HM3["N_LS"] * MLP_FLOPS / dur / 1e12
+        roof = {"bound": "tensor", "kernel": "NeuralAF MLP (%s), B x 10000 local-grid candidates" % args.mlp,
+                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                "peak_source": peak_src, "avg_launch_ms": dur * 1e3,
+                "format_ceiling_frac": {"tf32": 0.5, "bf16x3": 1.0 / 3.0, "fp32": None}[args.mlp]}
+        if gp_big:
+            gdur = float(np.mean(gp_big)) / 1e3
+            roof["gp_posterior"] = {"avg_launch_ms": gdur * 1e3, "precision": args.gp,
+                                    "achieved_tflops": B * HM3["k"] * HM3["N_LS"] * gp_flops(n, D) / gdur / 1e12}
+
+    # ---- e2e arm: host buffers -> engine -> host actions ----
+    hX = X.cpu().pin_memory(); hY = Y.cpu().pin_memory(); hn = nvec.cpu().pin_memory()
+    hs = torch.stack([inc.cpu(), tvec.cpu(), Tvec.cpu()]).pin_memory()
+    h_act = torch.empty((B,), dtype=torch.int32).pin_memory()
+    h_x = torch.empty((B, D), dtype=torch.float64).pin_memory()
+    dX = torch.empty_like(X); dY = torch.empty_like(Y); dn = torch.empty_like(nvec)
+    ds = torch.empty((3, B), device=dev)
+
+    def e2e_step():
+        dX.copy_(hX, non_blocking=True); dY.copy_(hY, non_blocking=True); dn.copy_(hn, non_blocking=True)
+        ds.copy_(hs, non_blocking=True)
+        eng.set_data(dX, dY, dn, n_active_max=n)
+        eng.set_episode_scalars(ds[0], ds[1], ds[2])
+        out = eng.af_round()
+        h_act.copy_(out["action"], non_blocking=True)
+        h_x.copy_(out["x_action"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    ms_e, _, _ = timed(e2e_step, args.steps, args.warmup)
+    h2d = hX.numel() * 8 + hY.numel() * 8 + hn.numel() * 4 + hs.numel() * 4
+    d2h = h_act.numel() * 4 + h_x.numel() * 8
+    e2e_val = world * cands_step * args.steps / (ms_e / 1e3)
+
+    cpu_b = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_b, _, _ = cpu_arm(3, n)
+
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        line = {"metric": "AF evals/sec (GP posterior+NeuralAF per candidate)", "value": value, "unit": "AF evals/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64 GP + %s MLP" % args.mlp if args.gp == "fp64" else "f32 GP + %s MLP" % args.mlp,
+                "data": "synthetic (U[0,1] observations of Hartmann-3 variants; %s)" % wdesc,
+                "config": workload_config(args, B), "clocks": clocks,
+                "e2e": {"value": e2e_val, "unit": "AF evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e / args.steps},
+                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu_b}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,179 @@
+/*
+ * metabo_b200.h -- C ABI of libmetabo_b200.so (sm_100a only).
+ *
+ * Drop-in boundary for MetaBO's data-parallel hot path: per BO step and per episode,
+ * GP posterior (mean, std) at M candidates -> features -> NeuralAF MLP -> argmax /
+ * categorical over the M logits.  The reference (boschresearch/MetaBO) has no FFI of its
+ * own (pure Python); each entry point below names the reference function it replaces.
+ * INTEGRATION.md shows the ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every array argument is a DEVICE pointer into caller-owned memory (torch tensors);
+ *     nothing is allocated inside, workspaces are sized by the *_bytes queries;
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work (no host sync);
+ *   - return value: 0 = ok, negative = error (mbo_last_error() gives a thread-local string);
+ *     no C++ exception crosses the boundary;
+ *   - episode b of B is an independent unit (one BO episode); candidates are per episode.
+ */
+#ifndef METABO_B200_H
+#define METABO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MBO_OK 0
+#define MBO_ERR_ARG (-1)
+#define MBO_ERR_CUDA (-2)
+#define MBO_ERR_UNSUPPORTED (-3)
+
+/* GP kernels of metabo_gym.py:554-564 (GPy.kern.RBF / Matern32 / Matern52, ARD) */
+#define MBO_KERNEL_RBF 0
+#define MBO_KERNEL_MATERN32 1
+#define MBO_KERNEL_MATERN52 2
+
+/* arithmetic of the posterior kernel */
+#define MBO_GP_FP64 0 /* validation mode: everything fp64 */
+#define MBO_GP_FP32 1 /* kernel rows, solve and dots in fp32 (fit is always fp64) */
+
+/* feature sources, one per policy-input column (metabo_gym.py:630-671 column order) */
+#define MBO_FEAT_MEAN 0
+#define MBO_FEAT_STD 1
+#define MBO_FEAT_X0 2 /* MBO_FEAT_X0 + d, d < 8 */
+#define MBO_FEAT_INCUMBENT 10
+#define MBO_FEAT_TPERC 11
+#define MBO_FEAT_TIMESTEP 12
+#define MBO_FEAT_BUDGET 13
+#define MBO_MAX_FEATURES 16
+#define MBO_MAX_D 8
+#define MBO_MAX_LAYERS 8
+
+/* activation of the hidden layers (policies.py:69-74) */
+#define MBO_ACT_RELU 0
+#define MBO_ACT_TANH 1
+
+/* MLP arithmetic */
+#define MBO_MLP_FP32 0   /* CUDA-core fp32 FMA (validation mode, any architecture) */
+#define MBO_MLP_TF32 1   /* tcgen05 kind::tf32, fp32 accumulate in TMEM */
+#define MBO_MLP_BF16X3 2 /* tcgen05 kind::f16 bf16 hi/lo split, 3 MMAs per product */
+
+/* Candidate set of one call.  Candidate m of episode b is
+ *   m <  n_head                : head[b, m, :]                    (per-episode points)
+ *   m >= n_head, local == 0    : tail[m - n_head, :]              (shared by all episodes)
+ *   m >= n_head, local != 0    : tail[s, :] * (hi - lo) + lo,  s = (m-n_head) % n_tail,
+ *                                cube = (m-n_head) / n_tail, lo/hi = cubes[b, cube, {0,1}, :]
+ * which covers metabo_gym.py's three sets: multistart grid (tail only), local Sobol grids
+ * (:711-716, tail = Sobol table, cubes from util.py:45-51) and xi_t (:619, head = af maxima,
+ * tail = multistart grid), plus per-episode streaming candidates (head only).
+ * Coordinates are fp64 (as in the reference) unless head_is_f32 / tail_is_f32 is set. */
+typedef struct {
+  int M;              /* candidates per episode */
+  int D;              /* input dimension, <= MBO_MAX_D */
+  int n_head;         /* per-episode leading points */
+  int n_tail;         /* rows of the shared table */
+  int local;          /* 1: tail rows are mapped into per-episode cubes */
+  int n_cubes;        /* cubes per episode when local (M = n_head + n_cubes * n_tail) */
+  int head_is_f32;
+  int tail_is_f32;
+  const void* head;   /* [B, n_head, D] */
+  const void* tail;   /* [n_tail, D] */
+  const double* cubes; /* [B, n_cubes, 2, D] (lo row, hi row), local only */
+} mbo_candidates;
+
+const char* mbo_last_error(void);
+int mbo_version(void);
+
+/* ---------------------------------------------------------------------------------------
+ * GP fit  (replaces MetaBO.update_gp -> GPy set_XY, metabo_gym.py:610-613, and the kernel /
+ * prior-mean setup of reset_gp :549-593).  Full fp64 refit of B episodes:
+ *   Ky = K(X,X) + (noise + 1e-8) I,  L = chol(Ky) (GPy jitchol retry ladder on failure),
+ *   Linv = L^-1,  beta = Linv (Y - m),  m = mean(Y) if use_prior_mean else 0.
+ *   n[b] may be 0 (empty GP, metabo_gym.py:736-738) and differ per episode, n[b] <= nmax.
+ * gp_state: [B, mbo_gp_state_doubles(nmax, D)] fp64, opaque to the caller.
+ * status:   [B] int32, 0 ok, k>0 = number of jitter retries used, -1 = not positive definite.
+ * ------------------------------------------------------------------------------------- */
+size_t mbo_gp_state_doubles(int nmax, int D);
+int mbo_gp_fit(int B, int nmax, int D, int kernel_id, const int32_t* n,
+               const double* X /*[B,nmax,D]*/, const double* Y /*[B,nmax]*/,
+               const double* lengthscale /*[B,D]*/, const double* variance /*[B]*/,
+               const double* noise /*[B]*/, int use_prior_mean,
+               double* gp_state, int32_t* status, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * GP posterior  (replaces MetaBO.eval_gp, metabo_gym.py:732-745 -> GPy predict_noiseless):
+ *   mean = k*^T Ky^-1 (Y-m) + m,  var = max(k** - |Linv k*|^2, 1e-15),  std = sqrt(var);
+ *   empty GP: mean = 0, std = sqrt(kernel_variance).
+ * Outputs mean/std [B, M]: fp64 when out_is_f32 == 0, else fp32 (the cast get_state does).
+ * n_active_max: upper bound of n[b] over the batch (<= nmax; sizes shared memory, pass nmax
+ * if unknown).  The kernel traps nothing: an episode with n[b] > n_active_max is an error of
+ * the caller and is reported through the status word of the launch check only in debug builds.
+ * ------------------------------------------------------------------------------------- */
+int mbo_gp_posterior(int B, int nmax, int n_active_max, int kernel_id, int precision,
+                     const double* gp_state, const mbo_candidates* cand, void* mean, void* std,
+                     int out_is_f32, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * NeuralAF weights  (NeuralAF.policy_net / value_net, policies.py:87-97; mlp.py:25-50).
+ * The handle owns device copies of the weights in the layouts the kernels want (fp32 for the
+ * CUDA-core path, TF32 / bf16 hi+lo UMMA-canonical tiles for the tcgen05 path).
+ *   widths[0..n_layers]: layer sizes d_in, h_1, ..., d_out(=1);  W_l: [widths[l+1], widths[l]]
+ *   row-major (torch nn.Linear.weight), b_l: [widths[l+1]];  host or device pointers.
+ * ------------------------------------------------------------------------------------- */
+typedef struct mbo_policy mbo_policy;
+int mbo_policy_create(mbo_policy** out);
+void mbo_policy_destroy(mbo_policy* p);
+int mbo_policy_set_weights(mbo_policy* p, int n_layers, const int32_t* widths, int activation,
+                           const float* const* W, const float* const* b, int on_device, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * NeuralAF evaluation  (replaces get_state feature packing metabo_gym.py:624-677 +
+ * NeuralAF.forward policies.py:104-125 / MLP.forward mlp.py:52-61 for the policy net).
+ *   feat_src[F]   : MBO_FEAT_* code of every policy-input column (masked columns omitted)
+ *   epi[B,4] fp32 : per-episode {incumbent, t/T, timestep, budget} (get_state :642-671)
+ *   mean, std     : [B, M] fp32 from mbo_gp_posterior
+ *   logits [B, M] fp32.
+ * mode MBO_MLP_FP32 supports any architecture; the tensor-core modes need a
+ * F->H->H->H->H->1 ReLU net with H <= 208 (the shipped 4x200 policies).
+ * ------------------------------------------------------------------------------------- */
+int mbo_af_logits(const mbo_policy* p, int mode, int B, int F, const int32_t* feat_src,
+                  const mbo_candidates* cand, const float* mean, const float* std,
+                  const float* epi, float* logits, void* workspace, size_t workspace_bytes,
+                  void* stream);
+size_t mbo_af_workspace_bytes(int mode, int B, int M);
+
+/* value network on (t, T) of row 0 (policies.py:117-121): tT [B,2] fp32 -> values [B] */
+int mbo_value_net(const mbo_policy* value_net, int B, const float* tT, float* values, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Reductions over the M logits of each episode
+ *   argmax         NeuralAF.act deterministic branch (policies.py:141-142), first-max ties
+ *   topk           np.argsort(-af)[:k] of get_af_maxima (metabo_gym.py:709,719), k <= 8
+ *   sample         Categorical(logits).sample() (policies.py:144-146) by Gumbel-max with a
+ *                  counter-based generator keyed (seed, episode, step, candidate)
+ *   logp/entropy   Categorical.log_prob / entropy (policies.py:157-159)
+ * ------------------------------------------------------------------------------------- */
+int mbo_logits_argmax(int B, int M, const float* logits, int32_t* action, float* max_logit, void* stream);
+int mbo_logits_topk(int B, int M, int k, const float* logits, int32_t* idx /*[B,k]*/,
+                    float* val /*[B,k]*/, void* stream);
+int mbo_logits_sample(int B, int M, const float* logits, uint64_t seed, uint64_t step,
+                      int32_t* action, void* stream);
+int mbo_logits_logp_entropy(int B, int M, const float* logits, const int32_t* actions,
+                            float* logp, float* entropy, void* stream);
+
+/* gather candidate coordinates by index: x_out[b, j, :] = candidate idx[b, j] (fp64), the
+ * convert_idx_to_x / af_maxima gathers of metabo_gym.py:709,719,838-842 */
+int mbo_candidates_gather(int B, const mbo_candidates* cand, int k, const int32_t* idx,
+                          double* x_out /*[B,k,D]*/, void* stream);
+
+/* cubes around start points (util.py:45-51 get_cube_around, domain = unit cube):
+ * cubes[b,j,0,:] = max(x - diam/2, 0), cubes[b,j,1,:] = min(x + diam/2, 1) */
+int mbo_cubes_around(int B, int k, int D, const double* x /*[B,k,D]*/, double diam,
+                     double* cubes /*[B,k,2,D]*/, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* METABO_B200_H */

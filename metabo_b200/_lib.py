@@ -1,0 +1,70 @@
+"""ctypes binding of libmetabo_b200.so (C ABI declared in include/metabo_b200.h)."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmetabo_b200.so")
+
+KERNEL_IDS = {"RBF": 0, "Matern32": 1, "Matern52": 2}
+GP_FP64, GP_FP32 = 0, 1
+MLP_FP32, MLP_TF32, MLP_BF16X3 = 0, 1, 2
+ACT = {"relu": 0, "tanh": 1}
+FEAT_MEAN, FEAT_STD, FEAT_X0, FEAT_INCUMBENT, FEAT_TPERC, FEAT_TIMESTEP, FEAT_BUDGET = 0, 1, 2, 10, 11, 12, 13
+
+
+class Candidates(C.Structure):
+    """mirror of `mbo_candidates`"""
+    _fields_ = [("M", C.c_int), ("D", C.c_int), ("n_head", C.c_int), ("n_tail", C.c_int),
+                ("local", C.c_int), ("n_cubes", C.c_int), ("head_is_f32", C.c_int), ("tail_is_f32", C.c_int),
+                ("head", C.c_void_p), ("tail", C.c_void_p), ("cubes", C.c_void_p)]
+
+
+class MboError(RuntimeError):
+    pass
+
+
+_lib = None
+
+# every symbol include/metabo_b200.h declares: (name, restype, argtypes)
+_vp, _i, _sz, _u64, _d = C.c_void_p, C.c_int, C.c_size_t, C.c_uint64, C.c_double
+SYMBOLS = [
+    ("mbo_last_error", C.c_char_p, []),
+    ("mbo_version", _i, []),
+    ("mbo_gp_state_doubles", _sz, [_i, _i]),
+    ("mbo_gp_fit", _i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    ("mbo_gp_posterior", _i, [_i, _i, _i, _i, _i, _vp, C.POINTER(Candidates), _vp, _vp, _i, _vp]),
+    ("mbo_policy_create", _i, [C.POINTER(_vp)]),
+    ("mbo_policy_destroy", None, [_vp]),
+    ("mbo_policy_set_weights", _i, [_vp, _i, C.POINTER(C.c_int32), _i, C.POINTER(_vp), C.POINTER(_vp), _i, _vp]),
+    ("mbo_af_logits", _i, [_vp, _i, _i, _i, C.POINTER(C.c_int32), C.POINTER(Candidates), _vp, _vp, _vp, _vp, _vp,
+                           _sz, _vp]),
+    ("mbo_af_workspace_bytes", _sz, [_i, _i, _i]),
+    ("mbo_value_net", _i, [_vp, _i, _vp, _vp, _vp]),
+    ("mbo_logits_argmax", _i, [_i, _i, _vp, _vp, _vp, _vp]),
+    ("mbo_logits_topk", _i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
+    ("mbo_logits_sample", _i, [_i, _i, _vp, _u64, _u64, _vp, _vp]),
+    ("mbo_logits_logp_entropy", _i, [_i, _i, _vp, _vp, _vp, _vp, _vp]),
+    ("mbo_candidates_gather", _i, [_i, C.POINTER(Candidates), _i, _vp, _vp, _vp]),
+    ("mbo_cubes_around", _i, [_i, _i, _i, _vp, _d, _vp, _vp]),
+]
+
+
+def lib():
+    """Loads the CUDA library; there is deliberately no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MboError("libmetabo_b200.so is missing (%s): build it with `python -c 'import __graft_entry__ as g; "
+                           "g.build()'` or `make -C metabo_b200/csrc`; there is no CPU fallback" % LIB_PATH)
+        l = C.CDLL(LIB_PATH)
+        for name, res, args in SYMBOLS:
+            f = getattr(l, name)
+            f.restype = res
+            f.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise MboError("%s failed (%d): %s" % (what, rc, lib().mbo_last_error().decode()))

@@ -1,0 +1,390 @@
+// gp.cu -- batched GP fit (K0) and GP posterior (K1) for B independent BO episodes.
+//
+// Replaces, per episode, what the reference does through GPy on the CPU:
+//   fit        MetaBO.update_gp -> gp.set_XY            metabo/environment/metabo_gym.py:610-613
+//   posterior  MetaBO.eval_gp  -> gp.predict_noiseless  metabo/environment/metabo_gym.py:732-745
+// Model (GPy 1.9.8 semantics): Ky = K(X,X) + (noise + 1e-8) I,
+// var clipped at 1e-15, empty GP -> mean 0 / var = kernel variance.
+//
+// Numerics differ from GPy's *route* on purpose: distances are formed directly (no Gram trick)
+// and the variance uses v = L^-1 k* (|v|^2) instead of an explicit Ky^-1 quadratic form; on the
+// ill-conditioned states (duplicate observations, cond ~4e9) this is ~5 orders of magnitude more
+// accurate than the GPy route (see tests/test_gp_gpu.py and DESIGN.md "GP precision").
+//
+// gp_state blob per episode (fp64):  header[16] | Xs[NP][D] (X / lengthscale) | beta[NP] |
+// LinvB: for every 8-row block ib, (ib+8) x 8 doubles, element (j, r) = Linv[ib + r][j]
+// (zero above the diagonal / beyond n) so the posterior kernel reads 8 rows of one column with
+// two broadcast LDS.128.
+#include "common.cuh"
+
+namespace mbo {
+
+template <typename T> __device__ __forceinline__ T t_exp(T x);
+template <> __device__ __forceinline__ double t_exp<double>(double x) { return exp(x); }
+template <> __device__ __forceinline__ float t_exp<float>(float x) { return __expf(x); }
+template <typename T> __device__ __forceinline__ T t_sqrt(T x);
+template <> __device__ __forceinline__ double t_sqrt<double>(double x) { return sqrt(x); }
+template <> __device__ __forceinline__ float t_sqrt<float>(float x) { return sqrtf(x); }
+
+template <typename T>
+__device__ __forceinline__ T kernel_of_r2(int kid, T var, T r2) {
+  if (kid == MBO_KERNEL_RBF) return var * t_exp<T>(T(-0.5) * r2);
+  T r = t_sqrt<T>(r2);
+  if (kid == MBO_KERNEL_MATERN32) {
+    const T s3 = T(1.7320508075688772935);
+    return var * (T(1) + s3 * r) * t_exp<T>(-s3 * r);
+  }
+  const T s5 = T(2.2360679774997896964);
+  return var * (T(1) + s5 * r + T(5.0 / 3.0) * r2) * t_exp<T>(-s5 * r);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K0: fit.  One CTA per episode.
+// ------------------------------------------------------------------------------------------------
+constexpr int FIT_THREADS = 128;
+
+__global__ void __launch_bounds__(FIT_THREADS)
+gp_fit_kernel(int nmax, int D, int kid, const int32_t* __restrict__ n_arr, const double* __restrict__ X,
+              const double* __restrict__ Y, const double* __restrict__ lengthscale,
+              const double* __restrict__ variance, const double* __restrict__ noise, int use_prior_mean,
+              double* __restrict__ gp_state, int32_t* __restrict__ status) {
+  extern __shared__ double sm[];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int n = min(n_arr[b], nmax);
+  const int NP = gp_np(nmax);
+  const int lda = NP + 1;
+  double* A = sm;                    // [NP][lda]
+  double* Xs = A + (size_t)NP * lda; // [NP][D]
+  double* yv = Xs + NP * D;          // [NP]
+  double* red = yv + NP;             // [FIT_THREADS]
+  __shared__ int s_fail;
+  __shared__ double s_m;
+
+  const size_t stride = gp_state_doubles(nmax, D);
+  double* st = gp_state + (size_t)b * stride;
+  const double var = variance[b];
+
+  // zero the whole blob first (padding rows/cols must be exactly 0 for the posterior kernel)
+  for (int i = tid; i < (int)stride; i += FIT_THREADS) st[i] = 0.0;
+  __syncthreads();
+  if (tid == 0) {
+    st[0] = (double)n;
+    st[2] = var;
+    for (int d = 0; d < D; ++d) st[4 + d] = lengthscale[b * D + d];
+  }
+  if (n == 0) {
+    if (tid == 0) { st[1] = 0.0; st[3] = 0.0; status[b] = 0; }
+    return;
+  }
+  // scaled inputs and targets
+  for (int i = tid; i < n * D; i += FIT_THREADS) {
+    int d = i % D;
+    Xs[i] = X[(size_t)b * nmax * D + i] / lengthscale[b * D + d];
+  }
+  double part = 0.0;
+  for (int i = tid; i < n; i += FIT_THREADS) { double y = Y[(size_t)b * nmax + i]; yv[i] = y; part += y; }
+  red[tid] = part;
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0.0;
+    for (int i = 0; i < FIT_THREADS; ++i) s += red[i];
+    s_m = use_prior_mean ? s / (double)n : 0.0;   // metabo_gym.py:573 np.mean(self.Y)
+  }
+  __syncthreads();
+  const double m = s_m;
+  for (int i = tid; i < n; i += FIT_THREADS) yv[i] -= m;
+
+  const double diag0 = var + noise[b] + 1e-8;      // k(x,x) + sigma_n^2 + GPy's 1e-8
+  double jitter = 0.0;
+  int tries = 0;
+  while (true) {
+    // ---- build the lower triangle of Ky ----
+    for (int e = tid; e < n * n; e += FIT_THREADS) {
+      int i = e / n, j = e - i * n;
+      if (j > i) continue;
+      double v;
+      if (i == j) {
+        v = diag0 + jitter;
+      } else {
+        double r2 = 0.0;
+        for (int d = 0; d < D; ++d) { double t = Xs[i * D + d] - Xs[j * D + d]; r2 += t * t; }
+        v = kernel_of_r2<double>(kid, var, r2);
+      }
+      A[i * lda + j] = v;
+    }
+    if (tid == 0) s_fail = 0;
+    __syncthreads();
+    // ---- right-looking Cholesky, lower, in place ----
+    for (int k = 0; k < n; ++k) {
+      if (tid == 0) {
+        double akk = A[k * lda + k];
+        if (!(akk > 0.0)) { s_fail = 1; akk = 1.0; }
+        A[k * lda + k] = sqrt(akk);
+      }
+      __syncthreads();
+      if (s_fail) break;
+      const double inv = 1.0 / A[k * lda + k];
+      for (int i = k + 1 + tid; i < n; i += FIT_THREADS) A[i * lda + k] *= inv;
+      __syncthreads();
+      // trailing update: A[i][j] -= A[i][k] * A[j][k], k < j <= i
+      const int rem = n - k - 1;
+      for (int e = tid; e < rem * rem; e += FIT_THREADS) {
+        int ii = e / rem, jj = e - ii * rem;
+        if (jj > ii) continue;
+        int i = k + 1 + ii, j = k + 1 + jj;
+        A[i * lda + j] -= A[i * lda + k] * A[j * lda + k];
+      }
+      __syncthreads();
+    }
+    __syncthreads();
+    if (!s_fail) break;
+    // GPy jitchol: jitter = mean(diag) * 1e-6, x10 per retry, 5 tries
+    ++tries;
+    if (tries > 5) break;
+    jitter = (tries == 1) ? diag0 * 1e-6 : jitter * 10.0;
+    __syncthreads();
+  }
+  if (s_fail) {
+    if (tid == 0) { status[b] = -1; st[3] = -1.0; st[0] = 0.0; }  // degrade to the empty-GP prediction
+    return;
+  }
+  // ---- in-place inverse of the lower-triangular factor, row by row ----
+  // Linv[i][c] = -(sum_{j=c}^{i-1} L[i][j] Linv[j][c]) / L[i][i],  Linv[i][i] = 1 / L[i][i]
+  for (int i = 0; i < n; ++i) {   // n <= nmax <= FIT_THREADS: thread c owns column c
+    double val = 0.0;
+    if (tid <= i) {
+      const double dinv = 1.0 / A[i * lda + i];
+      if (tid == i) {
+        val = dinv;
+      } else {
+        double s = 0.0;
+        for (int j = tid; j < i; ++j) s += A[i * lda + j] * A[j * lda + tid];
+        val = -s * dinv;
+      }
+    }
+    __syncthreads();
+    if (tid <= i) A[i * lda + tid] = val;
+    __syncthreads();
+  }
+  // ---- beta = Linv (y - m) ----
+  for (int i = tid; i < n; i += FIT_THREADS) {
+    double s = 0.0;
+    for (int j = 0; j <= i; ++j) s += A[i * lda + j] * yv[j];
+    st[gp_off_beta(NP, D) + i] = s;
+  }
+  for (int i = tid; i < n * D; i += FIT_THREADS) st[gp_off_xs() + i] = Xs[i];
+  // ---- blocked Linv ----
+  double* LB = st + gp_off_linv(NP, D);
+  const int npn = gp_np(n);
+  for (int ib = 0; ib < npn; ib += 8) {
+    double* blk = LB + gp_linv_block_off(ib);
+    const int cols = ib + 8;
+    for (int e = tid; e < cols * 8; e += FIT_THREADS) {
+      int j = e >> 3, r = e & 7;
+      int i = ib + r;
+      blk[e] = (i < n && j <= i) ? A[i * lda + j] : 0.0;
+    }
+  }
+  if (tid == 0) { st[1] = m; st[3] = (double)tries; status[b] = tries; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: posterior.  CTA = 128 threads, tile = 128*TC candidates of one episode.
+//   phase 1: episode blob -> smem
+//   phase 2: thread computes k*_j for its TC candidates into its private smem column
+//   phase 3: v = Linv k* in 8-row register blocks (2 broadcast LDS.128 per column feed 8*TC FMAs),
+//            mean += v_i beta_i, q += v_i^2
+// ------------------------------------------------------------------------------------------------
+constexpr int POST_THREADS = 128;
+
+template <typename T, int TC>
+__global__ void __launch_bounds__(POST_THREADS)
+gp_posterior_kernel(int nmax, int kid, const double* __restrict__ gp_state, mbo_candidates cand,
+                    int tiles_per_episode, void* __restrict__ mean_out, void* __restrict__ std_out,
+                    int out_is_f32) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int D = cand.D;
+  const int b = blockIdx.x / tiles_per_episode;
+  const int tile = blockIdx.x - b * tiles_per_episode;
+  const int tid = threadIdx.x;
+  const size_t stride = gp_state_doubles(nmax, D);
+  const double* st = gp_state + (size_t)b * stride;
+  const int NPmax = gp_np(nmax);
+  const int n = (int)st[0];
+  const int NP = gp_np(n);
+  const double m = st[1];
+  const double var = st[2];
+
+  T* sXs = (T*)smraw;                         // [NP][D]
+  T* sBeta = sXs + NP * D;                    // [NP]
+  T* sL = sBeta + NP;                         // blocked Linv, 16B aligned (NP*D + NP is even... padded below)
+  {
+    size_t off = (size_t)(NP * D + NP);
+    off = (off + 3) & ~(size_t)3;
+    sL = sXs + off;
+  }
+  const int lcount = gp_linv_doubles(NP);
+  T* sK = sL + lcount;                        // [NP][POST_THREADS*TC]
+  for (int i = tid; i < NP * D; i += POST_THREADS) sXs[i] = (T)st[gp_off_xs() + i];
+  for (int i = tid; i < NP; i += POST_THREADS) sBeta[i] = (T)st[gp_off_beta(NPmax, D) + i];
+  for (int i = tid; i < lcount; i += POST_THREADS) sL[i] = (T)st[gp_off_linv(NPmax, D) + i];
+  __syncthreads();
+
+  const int m0 = tile * POST_THREADS * TC;
+  T xs[TC][MBO_MAX_D];
+#pragma unroll
+  for (int c = 0; c < TC; ++c) {
+    int mi = m0 + tid * TC + c;
+    double x[MBO_MAX_D];
+#pragma unroll
+    for (int d = 0; d < MBO_MAX_D; ++d) x[d] = 0.0;
+    if (mi < cand.M) load_candidate(cand, b, mi, x);
+    // same operation as the fit (X / lengthscale) so a candidate equal to an observation has r == 0
+#pragma unroll
+    for (int d = 0; d < MBO_MAX_D; ++d) xs[c][d] = d < D ? (T)(x[d] / st[4 + d]) : T(0);
+  }
+  constexpr int KS = POST_THREADS * TC;
+  // phase 2
+  for (int j = 0; j < n; ++j) {
+#pragma unroll
+    for (int c = 0; c < TC; ++c) {
+      T r2 = T(0);
+#pragma unroll
+      for (int d = 0; d < MBO_MAX_D; ++d)
+        if (d < D) { T t = xs[c][d] - sXs[j * D + d]; r2 += t * t; }
+      sK[j * KS + tid * TC + c] = kernel_of_r2<T>(kid, (T)var, r2);
+    }
+  }
+  for (int j = n; j < NP; ++j) {
+#pragma unroll
+    for (int c = 0; c < TC; ++c) sK[j * KS + tid * TC + c] = T(0);
+  }
+  // phase 3 (each thread only reads the smem column it wrote: no barrier needed)
+  T q[TC], mu[TC];
+#pragma unroll
+  for (int c = 0; c < TC; ++c) { q[c] = T(0); mu[c] = T(0); }
+  for (int ib = 0; ib < NP; ib += 8) {
+    T acc[8][TC];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int c = 0; c < TC; ++c) acc[r][c] = T(0);
+    const T* blk = sL + gp_linv_block_off(ib);
+    const int cols = ib + 8;
+#pragma unroll 4
+    for (int j = 0; j < cols; ++j) {
+      T l[8];
+      if (sizeof(T) == 8) {
+        const double2* p = (const double2*)(blk + j * 8);
+        double2 a0 = p[0], a1 = p[1], a2 = p[2], a3 = p[3];
+        l[0] = (T)a0.x; l[1] = (T)a0.y; l[2] = (T)a1.x; l[3] = (T)a1.y;
+        l[4] = (T)a2.x; l[5] = (T)a2.y; l[6] = (T)a3.x; l[7] = (T)a3.y;
+      } else {
+        const float4* p = (const float4*)(blk + j * 8);
+        float4 a0 = p[0], a1 = p[1];
+        l[0] = (T)a0.x; l[1] = (T)a0.y; l[2] = (T)a0.z; l[3] = (T)a0.w;
+        l[4] = (T)a1.x; l[5] = (T)a1.y; l[6] = (T)a1.z; l[7] = (T)a1.w;
+      }
+#pragma unroll
+      for (int c = 0; c < TC; ++c) {
+        T kv = sK[j * KS + tid * TC + c];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) acc[r][c] = fma(l[r], kv, acc[r][c]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      T be = sBeta[ib + r];
+#pragma unroll
+      for (int c = 0; c < TC; ++c) {
+        q[c] = fma(acc[r][c], acc[r][c], q[c]);
+        mu[c] = fma(acc[r][c], be, mu[c]);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < TC; ++c) {
+    int mi = m0 + tid * TC + c;
+    if (mi >= cand.M) continue;
+    double mean_v, var_v;
+    if (n == 0) {
+      mean_v = 0.0;               // metabo_gym.py:737: zero, not the prior mean
+      var_v = var;
+    } else {
+      mean_v = (double)mu[c] + m;
+      var_v = var - (double)q[c];
+      var_v = var_v < 1e-15 ? 1e-15 : var_v;    // GPy clip
+    }
+    double sd = sqrt(var_v);
+    size_t o = (size_t)b * cand.M + mi;
+    if (out_is_f32) { ((float*)mean_out)[o] = (float)mean_v; ((float*)std_out)[o] = (float)sd; }
+    else { ((double*)mean_out)[o] = mean_v; ((double*)std_out)[o] = sd; }
+  }
+}
+
+template <typename T, int TC>
+static size_t posterior_smem_bytes(int nmax, int D) {
+  int NP = gp_np(nmax);
+  size_t off = (size_t)(NP * D + NP);
+  off = (off + 3) & ~(size_t)3;
+  return sizeof(T) * (off + gp_linv_doubles(NP) + (size_t)NP * POST_THREADS * TC);
+}
+
+template <typename T, int TC>
+static int launch_posterior(int B, int nmax, int ns, int kid, const double* gp_state, const mbo_candidates& cand,
+                            void* mean, void* std_, int out_is_f32, cudaStream_t s) {
+  size_t smem = posterior_smem_bytes<T, TC>(ns, cand.D);
+  auto kern = gp_posterior_kernel<T, TC>;
+  MBO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int tiles = (cand.M + POST_THREADS * TC - 1) / (POST_THREADS * TC);
+  kern<<<B * tiles, POST_THREADS, smem, s>>>(nmax, kid, gp_state, cand, tiles, mean, std_, out_is_f32);
+  MBO_LAUNCH_CHECK();
+  return MBO_OK;
+}
+
+}  // namespace mbo
+
+using namespace mbo;
+
+extern "C" size_t mbo_gp_state_doubles(int nmax, int D) { return (size_t)gp_state_doubles(nmax, D); }
+
+extern "C" int mbo_gp_fit(int B, int nmax, int D, int kernel_id, const int32_t* n, const double* X,
+                          const double* Y, const double* lengthscale, const double* variance,
+                          const double* noise, int use_prior_mean, double* gp_state, int32_t* status,
+                          void* stream) {
+  MBO_CHECK_ARG(B > 0 && nmax > 0 && nmax <= 128, "mbo_gp_fit: need B > 0 and 0 < nmax <= 128 (got %d, %d)", B, nmax);
+  MBO_CHECK_ARG(D > 0 && D <= MBO_MAX_D, "mbo_gp_fit: D must be in 1..%d", MBO_MAX_D);
+  MBO_CHECK_ARG(kernel_id >= 0 && kernel_id <= 2, "mbo_gp_fit: unknown kernel id %d", kernel_id);
+  MBO_CHECK_ARG(n && X && Y && lengthscale && variance && noise && gp_state && status, "mbo_gp_fit: null pointer");
+  int NP = gp_np(nmax);
+  size_t smem = sizeof(double) * ((size_t)NP * (NP + 1) + (size_t)NP * D + NP + FIT_THREADS);
+  MBO_CUDA(cudaFuncSetAttribute(gp_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gp_fit_kernel<<<B, FIT_THREADS, smem, (cudaStream_t)stream>>>(nmax, D, kernel_id, n, X, Y, lengthscale, variance,
+                                                               noise, use_prior_mean, gp_state, status);
+  MBO_LAUNCH_CHECK();
+  return MBO_OK;
+}
+
+extern "C" int mbo_gp_posterior(int B, int nmax, int n_active_max, int kernel_id, int precision,
+                                const double* gp_state, const mbo_candidates* cand, void* mean, void* std_,
+                                int out_is_f32, void* stream) {
+  MBO_CHECK_ARG(B > 0 && nmax > 0 && nmax <= 128, "mbo_gp_posterior: need B > 0 and 0 < nmax <= 128");
+  MBO_CHECK_ARG(kernel_id >= 0 && kernel_id <= 2, "mbo_gp_posterior: unknown kernel id %d", kernel_id);
+  MBO_CHECK_ARG(gp_state && cand && mean && std_, "mbo_gp_posterior: null pointer");
+  MBO_CHECK_ARG(n_active_max >= 0 && n_active_max <= nmax, "mbo_gp_posterior: n_active_max must be in 0..nmax");
+  const int ns = n_active_max > 0 ? n_active_max : 1;   // sizes shared memory only
+  int rc = check_candidates(cand);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (precision == MBO_GP_FP64) {
+    if (posterior_smem_bytes<double, 2>(ns, cand->D) <= 100 * 1024)
+      return launch_posterior<double, 2>(B, nmax, ns, kernel_id, gp_state, *cand, mean, std_, out_is_f32, s);
+    return launch_posterior<double, 1>(B, nmax, ns, kernel_id, gp_state, *cand, mean, std_, out_is_f32, s);
+  } else if (precision == MBO_GP_FP32) {
+    if (posterior_smem_bytes<float, 2>(ns, cand->D) <= 100 * 1024)
+      return launch_posterior<float, 2>(B, nmax, ns, kernel_id, gp_state, *cand, mean, std_, out_is_f32, s);
+    return launch_posterior<float, 1>(B, nmax, ns, kernel_id, gp_state, *cand, mean, std_, out_is_f32, s);
+  }
+  set_error("mbo_gp_posterior: unknown precision %d", precision);
+  return MBO_ERR_ARG;
+}

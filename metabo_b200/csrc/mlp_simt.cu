@@ -1,0 +1,218 @@
+// mlp_simt.cu -- CUDA-core fp32 NeuralAF evaluation (validation mode, any architecture).
+//
+// Replaces get_state feature packing (metabo/environment/metabo_gym.py:624-677) followed by
+// NeuralAF.forward (metabo/policies/policies.py:104-125) -> MLP.forward (mlp.py:52-61).
+// fp32 FMA with sequential accumulation over the input index: agrees with torch-CPU fp32 to
+// ~1e-6 relative (summation order differs).  The throughput path is neural_af_tc.cu.
+#include "common.cuh"
+#include "policy.cuh"
+
+namespace mbo {
+
+constexpr int ST = 256;   // threads
+constexpr int TILE = 32;  // rows (candidates) per CTA
+
+struct SimtNet {
+  int n_layers;
+  int widths[MBO_MAX_LAYERS + 1];
+  int activation;
+  const float* Wt[MBO_MAX_LAYERS];
+  const float* b[MBO_MAX_LAYERS];
+};
+
+struct FeatSpec {
+  int F;
+  int src[MBO_MAX_FEATURES];
+};
+
+__device__ __forceinline__ float act_fn(int a, float v) { return a == MBO_ACT_RELU ? fmaxf(v, 0.f) : tanhf(v); }
+
+// rows: either (episode, candidate) pairs with features assembled on the fly (direct == nullptr)
+// or rows of a dense [R, F] fp32 matrix (direct != nullptr; the value net path)
+__global__ void __launch_bounds__(ST)
+mlp_simt_kernel(SimtNet net, FeatSpec fs, mbo_candidates cand, int tiles_per_episode,
+                const float* __restrict__ mean, const float* __restrict__ std_, const float* __restrict__ epi,
+                const float* __restrict__ direct, int R, int hmax, float* __restrict__ out) {
+  extern __shared__ float smf[];
+  float* bufA = smf;                 // [hmax][TILE]
+  float* bufB = smf + hmax * TILE;
+  const int tid = threadIdx.x;
+  int b = 0, row0;
+  int rows_valid;
+  if (direct) {
+    row0 = blockIdx.x * TILE;
+    rows_valid = min(TILE, R - row0);
+  } else {
+    b = blockIdx.x / tiles_per_episode;
+    row0 = (blockIdx.x - b * tiles_per_episode) * TILE;
+    rows_valid = min(TILE, cand.M - row0);
+  }
+  const int F = net.widths[0];
+  // ---- layer-0 input ----
+  if (direct) {
+    for (int e = tid; e < F * TILE; e += ST) {
+      int f = e / TILE, c = e - f * TILE;
+      bufA[f * TILE + c] = c < rows_valid ? direct[(size_t)(row0 + c) * F + f] : 0.f;
+    }
+  } else {
+    if (tid < TILE) {
+      int c = tid;
+      double x[MBO_MAX_D];
+#pragma unroll
+      for (int d = 0; d < MBO_MAX_D; ++d) x[d] = 0.0;
+      float mu = 0.f, sd = 0.f;
+      if (c < rows_valid) {
+        load_candidate(cand, b, row0 + c, x);
+        mu = mean[(size_t)b * cand.M + row0 + c];
+        sd = std_[(size_t)b * cand.M + row0 + c];
+      }
+      for (int f = 0; f < F; ++f) {
+        int s = fs.src[f];
+        float v;
+        if (s == MBO_FEAT_MEAN) v = mu;
+        else if (s == MBO_FEAT_STD) v = sd;
+        else if (s >= MBO_FEAT_X0 && s < MBO_FEAT_X0 + MBO_MAX_D) {
+          v = 0.f;
+#pragma unroll
+          for (int d = 0; d < MBO_MAX_D; ++d) if (s - MBO_FEAT_X0 == d) v = (float)x[d];
+        } else v = epi[b * 4 + (s - MBO_FEAT_INCUMBENT)];
+        bufA[f * TILE + c] = c < rows_valid ? v : 0.f;
+      }
+    }
+  }
+  __syncthreads();
+  float* in = bufA;
+  float* outb = bufB;
+  for (int l = 0; l < net.n_layers; ++l) {
+    const int K = net.widths[l], N = net.widths[l + 1];
+    const float* __restrict__ Wt = net.Wt[l];
+    const float* __restrict__ bias = net.b[l];
+    const bool last = (l == net.n_layers - 1);
+    if (N >= 8) {
+      for (int o = tid; o < N; o += ST) {
+        float acc[TILE];
+        const float b0 = bias[o];
+#pragma unroll
+        for (int c = 0; c < TILE; ++c) acc[c] = b0;
+        for (int k = 0; k < K; ++k) {
+          const float w = Wt[(size_t)k * N + o];
+          const float4* a4 = (const float4*)(in + k * TILE);
+#pragma unroll
+          for (int c4 = 0; c4 < TILE / 4; ++c4) {
+            float4 a = a4[c4];
+            acc[c4 * 4 + 0] = fmaf(w, a.x, acc[c4 * 4 + 0]);
+            acc[c4 * 4 + 1] = fmaf(w, a.y, acc[c4 * 4 + 1]);
+            acc[c4 * 4 + 2] = fmaf(w, a.z, acc[c4 * 4 + 2]);
+            acc[c4 * 4 + 3] = fmaf(w, a.w, acc[c4 * 4 + 3]);
+          }
+        }
+        if (last) {
+#pragma unroll
+          for (int c = 0; c < TILE; ++c) outb[o * TILE + c] = acc[c];
+        } else {
+#pragma unroll
+          for (int c = 0; c < TILE; ++c) outb[o * TILE + c] = act_fn(net.activation, acc[c]);
+        }
+      }
+    } else {
+      // narrow output (the 1-unit head): 8 lanes per row split K
+      for (int o = 0; o < N; ++o) {
+        int c = tid >> 3, part = tid & 7;
+        float s = 0.f;
+        for (int k = part; k < K; k += 8) s = fmaf(Wt[(size_t)k * N + o], in[k * TILE + c], s);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        if (part == 0) {
+          float v = s + bias[o];
+          outb[o * TILE + c] = last ? v : act_fn(net.activation, v);
+        }
+      }
+    }
+    __syncthreads();
+    float* t = in; in = outb; outb = t;
+  }
+  // `in` now holds the output [N_out][TILE]; N_out == 1 for every MetaBO net
+  const int NO = net.widths[net.n_layers];
+  for (int e = tid; e < NO * TILE; e += ST) {
+    int o = e / TILE, c = e - o * TILE;
+    if (c < rows_valid) {
+      size_t r = direct ? (size_t)(row0 + c) : (size_t)b * cand.M + row0 + c;
+      out[r * NO + o] = in[o * TILE + c];
+    }
+  }
+}
+
+int simt_forward(const mbo_policy* p, int B, int F, const int32_t* feat_src, const mbo_candidates* cand,
+                 const float* mean, const float* std_, const float* epi, const float* direct, int R,
+                 float* out, cudaStream_t s) {
+  SimtNet net;
+  net.n_layers = p->n_layers;
+  net.activation = p->activation;
+  int hmax = 0;
+  for (int l = 0; l <= p->n_layers; ++l) { net.widths[l] = p->widths[l]; hmax = max(hmax, p->widths[l]); }
+  for (int l = 0; l < p->n_layers; ++l) { net.Wt[l] = p->d_Wt[l]; net.b[l] = p->d_b[l]; }
+  FeatSpec fs;
+  fs.F = F;
+  mbo_candidates c0;
+  memset(&c0, 0, sizeof(c0));
+  int grid, tiles = 1;
+  if (direct) {
+    grid = (R + TILE - 1) / TILE;
+  } else {
+    for (int f = 0; f < F; ++f) fs.src[f] = feat_src[f];
+    c0 = *cand;
+    tiles = (cand->M + TILE - 1) / TILE;
+    grid = B * tiles;
+  }
+  size_t smem = sizeof(float) * 2 * hmax * TILE;
+  MBO_CUDA(cudaFuncSetAttribute(mlp_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mlp_simt_kernel<<<grid, ST, smem, s>>>(net, fs, c0, tiles, mean, std_, epi, direct, R, hmax, out);
+  MBO_LAUNCH_CHECK();
+  return MBO_OK;
+}
+
+int tc_forward(const mbo_policy* p, int mode, int B, int F, const int32_t* feat_src, const mbo_candidates* cand,
+               const float* mean, const float* std_, const float* epi, float* logits, void* ws, size_t ws_bytes,
+               cudaStream_t s);   // neural_af_tc.cu
+
+}  // namespace mbo
+
+using namespace mbo;
+
+extern "C" size_t mbo_af_workspace_bytes(int mode, int B, int M) {
+  (void)mode; (void)B; (void)M;
+  return 256;
+}
+
+extern "C" int mbo_af_logits(const mbo_policy* p, int mode, int B, int F, const int32_t* feat_src,
+                             const mbo_candidates* cand, const float* mean, const float* std_,
+                             const float* epi, float* logits, void* workspace, size_t workspace_bytes,
+                             void* stream) {
+  MBO_CHECK_ARG(p && p->n_layers > 0, "mbo_af_logits: policy has no weights");
+  MBO_CHECK_ARG(B > 0 && cand && mean && std_ && epi && logits && feat_src, "mbo_af_logits: null pointer");
+  MBO_CHECK_ARG(F == p->widths[0] && F <= MBO_MAX_FEATURES, "mbo_af_logits: F=%d does not match the policy input width %d", F, p->widths[0]);
+  MBO_CHECK_ARG(p->widths[p->n_layers] == 1, "mbo_af_logits: policy head must have one output");
+  int rc = check_candidates(cand);
+  if (rc) return rc;
+  for (int f = 0; f < F; ++f) {
+    int s = feat_src[f];
+    bool ok = s == MBO_FEAT_MEAN || s == MBO_FEAT_STD || (s >= MBO_FEAT_X0 && s < MBO_FEAT_X0 + cand->D) ||
+              (s >= MBO_FEAT_INCUMBENT && s <= MBO_FEAT_BUDGET);
+    MBO_CHECK_ARG(ok, "mbo_af_logits: bad feature source %d at column %d", s, f);
+  }
+  if (mode == MBO_MLP_FP32)
+    return simt_forward(p, B, F, feat_src, cand, mean, std_, epi, nullptr, 0, logits, (cudaStream_t)stream);
+  if (mode == MBO_MLP_TF32 || mode == MBO_MLP_BF16X3)
+    return tc_forward(p, mode, B, F, feat_src, cand, mean, std_, epi, logits, workspace, workspace_bytes,
+                      (cudaStream_t)stream);
+  set_error("mbo_af_logits: unknown mode %d", mode);
+  return MBO_ERR_ARG;
+}
+
+extern "C" int mbo_value_net(const mbo_policy* p, int B, const float* tT, float* values, void* stream) {
+  MBO_CHECK_ARG(p && p->n_layers > 0 && B > 0 && tT && values, "mbo_value_net: bad argument");
+  MBO_CHECK_ARG(p->widths[p->n_layers] == 1, "mbo_value_net: head must have one output");
+  return simt_forward(p, B, p->widths[0], nullptr, nullptr, nullptr, nullptr, nullptr, tT, B, values,
+                      (cudaStream_t)stream);
+}

@@ -1,0 +1,19 @@
+// policy.cuh -- the opaque mbo_policy handle (device copies of one MLP's parameters).
+#pragma once
+#include "common.cuh"
+
+struct mbo_policy {
+  int n_layers = 0;
+  int widths[MBO_MAX_LAYERS + 1] = {0};
+  int activation = MBO_ACT_RELU;
+  float* d_Wt[MBO_MAX_LAYERS] = {nullptr};   // [in][out] fp32, for the CUDA-core kernel
+  float* d_b[MBO_MAX_LAYERS] = {nullptr};    // [out] fp32
+  float* d_W_raw = nullptr;                  // all layers, torch layout [out][in], concatenated
+  size_t raw_off[MBO_MAX_LAYERS] = {0};
+  uint64_t alloc_sig = 0;
+  // tensor-core pack (neural_af_tc.cu): UMMA-canonical K-chunked tiles, see that file
+  void* d_tc = nullptr;
+  size_t tc_bytes = 0;
+  int tc_ready = 0;       // 1 when the architecture is F->H->H->H->H->1 ReLU with H <= 208
+  int tc_H = 0, tc_F = 0;
+};

@@ -1,0 +1,177 @@
+// reduce.cu -- per-episode reductions over the M logits (one CTA per episode).
+//
+//   argmax        NeuralAF.act, deterministic branch      metabo/policies/policies.py:141-142
+//   top-k         np.argsort(-af)[:k] in get_af_maxima    metabo/environment/metabo_gym.py:709,719
+//   sample        Categorical(logits=...).sample()        metabo/policies/policies.py:144-146
+//   logp/entropy  Categorical.log_prob / .entropy         metabo/policies/policies.py:157-159
+//
+// Tie rule: the lowest index among equal values wins (torch.argmax's rule; np.argsort's order on
+// ties is unspecified in the reference, any deterministic rule is admissible).
+// The sampler is Gumbel-max over a counter-based generator keyed (seed, episode, step,
+// candidate): no state, reproducible under any sharding of episodes over GPUs, and restated
+// bit-for-bit in oracle/sampling_oracle.py for the parity tests.
+#include "common.cuh"
+
+namespace mbo {
+
+constexpr int RT = 256;
+
+struct KV {
+  float v;
+  int i;
+};
+// a "precedes" b in descending-value / ascending-index order
+__device__ __forceinline__ bool precedes(const KV& a, const KV& b) {
+  return a.v > b.v || (a.v == b.v && a.i < b.i);
+}
+__device__ __forceinline__ KV warp_best(KV x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    KV y;
+    y.v = __shfl_xor_sync(0xffffffffu, x.v, o);
+    y.i = __shfl_xor_sync(0xffffffffu, x.i, o);
+    if (precedes(y, x)) x = y;
+  }
+  return x;
+}
+__device__ KV block_best(KV x, KV* sh) {
+  x = warp_best(x);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = x;
+  __syncthreads();
+  if (w == 0) {
+    KV y = l < RT / 32 ? sh[l] : KV{-INFINITY, 0x7fffffff};
+    y = warp_best(y);
+    if (l == 0) sh[0] = y;
+  }
+  __syncthreads();
+  return sh[0];
+}
+__device__ double block_sum(double x, double* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = x;
+  __syncthreads();
+  if (w == 0) {
+    double y = l < RT / 32 ? sh[l] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) y += __shfl_xor_sync(0xffffffffu, y, o);
+    if (l == 0) sh[0] = y;
+  }
+  __syncthreads();
+  return sh[0];
+}
+
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {   // splitmix64 finaliser
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+constexpr uint64_t GOLD = 0x9E3779B97F4A7C15ull;
+__device__ __forceinline__ float gumbel_noise(uint64_t key, int m) {
+  uint64_t r = mix64(key + GOLD * (uint64_t)(m + 1));
+  float u = ((float)(r >> 40) + 0.5f) * (1.0f / 16777216.0f);   // 24-bit uniform in (0,1)
+  return -logf(-logf(u));
+}
+
+// k == 1 doubles as argmax.  noise != 0: Gumbel-max sampling (k must be 1).
+__global__ void __launch_bounds__(RT)
+topk_kernel(int M, int k, const float* __restrict__ logits, int noise, uint64_t seed, uint64_t step,
+            int32_t* __restrict__ idx, float* __restrict__ val) {
+  __shared__ KV sh[RT / 32];
+  const int b = blockIdx.x;
+  const float* lg = logits + (size_t)b * M;
+  uint64_t key = 0;
+  if (noise) key = mix64(mix64(seed + GOLD * (uint64_t)(b + 1)) ^ (step + GOLD));
+  KV prev{INFINITY, -1};
+  for (int r = 0; r < k; ++r) {
+    KV best{-INFINITY, 0x7fffffff};
+    for (int m = threadIdx.x; m < M; m += RT) {
+      float v = lg[m];
+      if (noise) v += gumbel_noise(key, m);
+      KV c{v, m};
+      if (v == v && precedes(prev, c) && precedes(c, best)) best = c;
+    }
+    best = block_best(best, sh);
+    if (threadIdx.x == 0) {
+      int bi = best.i == 0x7fffffff ? 0 : best.i;   // all-NaN row: fall back to index 0
+      idx[(size_t)b * k + r] = bi;
+      if (val) val[(size_t)b * k + r] = noise ? lg[bi] : best.v;
+    }
+    prev = best;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(RT)
+logp_entropy_kernel(int M, const float* __restrict__ logits, const int32_t* __restrict__ actions,
+                    float* __restrict__ logp, float* __restrict__ entropy) {
+  __shared__ KV sh[RT / 32];
+  __shared__ double shd[RT / 32];
+  const int b = blockIdx.x;
+  const float* lg = logits + (size_t)b * M;
+  KV best{-INFINITY, 0x7fffffff};
+  for (int m = threadIdx.x; m < M; m += RT) {
+    KV c{lg[m], m};
+    if (precedes(c, best)) best = c;
+  }
+  best = block_best(best, sh);
+  const float mx = best.v;
+  double s = 0.0, w = 0.0;
+  for (int m = threadIdx.x; m < M; m += RT) {
+    float d = lg[m] - mx;
+    float e = expf(d);
+    s += (double)e;
+    w += (double)(e * d);
+  }
+  s = block_sum(s, shd);
+  w = block_sum(w, shd);
+  if (threadIdx.x == 0) {
+    double ls = log(s);
+    if (entropy) entropy[b] = (float)(ls - w / s);
+    if (logp) {
+      int a = actions[b];
+      a = a < 0 ? 0 : (a >= M ? M - 1 : a);
+      logp[b] = (float)((double)(lg[a] - mx) - ls);
+    }
+  }
+}
+
+}  // namespace mbo
+
+using namespace mbo;
+
+extern "C" int mbo_logits_argmax(int B, int M, const float* logits, int32_t* action, float* max_logit, void* stream) {
+  MBO_CHECK_ARG(B > 0 && M > 0 && logits && action, "mbo_logits_argmax: bad argument");
+  topk_kernel<<<B, RT, 0, (cudaStream_t)stream>>>(M, 1, logits, 0, 0, 0, action, max_logit);
+  MBO_LAUNCH_CHECK();
+  return MBO_OK;
+}
+
+extern "C" int mbo_logits_topk(int B, int M, int k, const float* logits, int32_t* idx, float* val, void* stream) {
+  MBO_CHECK_ARG(B > 0 && M > 0 && logits && idx, "mbo_logits_topk: bad argument");
+  MBO_CHECK_ARG(k >= 1 && k <= 8 && k <= M, "mbo_logits_topk: k must be in 1..min(8, M)");
+  topk_kernel<<<B, RT, 0, (cudaStream_t)stream>>>(M, k, logits, 0, 0, 0, idx, val);
+  MBO_LAUNCH_CHECK();
+  return MBO_OK;
+}
+
+extern "C" int mbo_logits_sample(int B, int M, const float* logits, uint64_t seed, uint64_t step, int32_t* action,
+                                 void* stream) {
+  MBO_CHECK_ARG(B > 0 && M > 0 && logits && action, "mbo_logits_sample: bad argument");
+  topk_kernel<<<B, RT, 0, (cudaStream_t)stream>>>(M, 1, logits, 1, seed, step, action, nullptr);
+  MBO_LAUNCH_CHECK();
+  return MBO_OK;
+}
+
+extern "C" int mbo_logits_logp_entropy(int B, int M, const float* logits, const int32_t* actions, float* logp,
+                                       float* entropy, void* stream) {
+  MBO_CHECK_ARG(B > 0 && M > 0 && logits, "mbo_logits_logp_entropy: bad argument");
+  MBO_CHECK_ARG(!logp || actions, "mbo_logits_logp_entropy: logp needs actions");
+  logp_entropy_kernel<<<B, RT, 0, (cudaStream_t)stream>>>(M, logits, actions, logp, entropy);
+  MBO_LAUNCH_CHECK();
+  return MBO_OK;
+}

@@ -1,0 +1,202 @@
+"""torch-tensor wrappers of the C ABI.  All tensors must live on the current CUDA device; every
+call enqueues on torch's current stream and returns without synchronising."""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _chk(t, dtype, name):
+    if t is None:
+        return
+    if not (t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+        raise ValueError("%s must be a contiguous CUDA %s tensor" % (name, dtype))
+
+
+class CandidateSet:
+    """Device-side description of the M candidates of every episode (see mbo_candidates)."""
+
+    def __init__(self, D, head=None, tail=None, cubes=None):
+        self.D = D
+        self.head, self.tail, self.cubes = head, tail, cubes
+        n_head = 0 if head is None else head.shape[1]
+        n_tail = 0 if tail is None else tail.shape[0]
+        for t, nm in ((head, "head"), (tail, "tail")):
+            if t is not None:
+                if not (t.is_cuda and t.is_contiguous() and t.dtype in (torch.float32, torch.float64)):
+                    raise ValueError("%s must be a contiguous CUDA float32/float64 tensor" % nm)
+                if t.shape[-1] != D:
+                    raise ValueError("%s last dim must be D" % nm)
+        local = cubes is not None
+        if local:
+            _chk(cubes, torch.float64, "cubes")
+            n_cubes = cubes.shape[1]
+            M = n_head + n_cubes * n_tail
+        else:
+            n_cubes = 0
+            M = n_head + n_tail
+        self.M = M
+        self.B_head = None if head is None else head.shape[0]
+        self.c = L.Candidates(M, D, n_head, n_tail, int(local), n_cubes,
+                              int(head is not None and head.dtype == torch.float32),
+                              int(tail is not None and tail.dtype == torch.float32),
+                              0 if head is None else head.data_ptr(),
+                              0 if tail is None else tail.data_ptr(),
+                              0 if cubes is None else cubes.data_ptr())
+
+    def ref(self):
+        return C.byref(self.c)
+
+
+def gp_state_doubles(nmax, D):
+    return int(L.lib().mbo_gp_state_doubles(nmax, D))
+
+
+def gp_fit(n, X, Y, lengthscale, variance, noise, kernel="RBF", use_prior_mean=False, gp_state=None, status=None):
+    """MetaBO.update_gp for B episodes.  n [B] i32, X [B,nmax,D] f64, Y [B,nmax] f64,
+    lengthscale [B,D], variance [B], noise [B] f64.  Returns (gp_state [B,S] f64, status [B] i32)."""
+    B, nmax, D = X.shape
+    _chk(n, torch.int32, "n"); _chk(X, torch.float64, "X"); _chk(Y, torch.float64, "Y")
+    _chk(lengthscale, torch.float64, "lengthscale"); _chk(variance, torch.float64, "variance")
+    _chk(noise, torch.float64, "noise")
+    S = gp_state_doubles(nmax, D)
+    if gp_state is None:
+        gp_state = torch.empty((B, S), dtype=torch.float64, device=X.device)
+    if status is None:
+        status = torch.empty((B,), dtype=torch.int32, device=X.device)
+    L.check(L.lib().mbo_gp_fit(B, nmax, D, L.KERNEL_IDS[kernel], _p(n), _p(X), _p(Y), _p(lengthscale), _p(variance),
+                               _p(noise), int(bool(use_prior_mean)), _p(gp_state), _p(status), _stream()),
+            "mbo_gp_fit")
+    return gp_state, status
+
+
+def gp_posterior(gp_state, nmax, cand, B, kernel="RBF", precision=L.GP_FP64, out_dtype=torch.float64,
+                 n_active_max=None, mean=None, std=None):
+    """MetaBO.eval_gp for B episodes x M candidates -> (mean [B,M], std [B,M])."""
+    _chk(gp_state, torch.float64, "gp_state")
+    if mean is None:
+        mean = torch.empty((B, cand.M), dtype=out_dtype, device=gp_state.device)
+    if std is None:
+        std = torch.empty((B, cand.M), dtype=out_dtype, device=gp_state.device)
+    L.check(L.lib().mbo_gp_posterior(B, nmax, nmax if n_active_max is None else int(n_active_max),
+                                     L.KERNEL_IDS[kernel], precision, _p(gp_state), cand.ref(), _p(mean), _p(std),
+                                     int(mean.dtype == torch.float32), _stream()), "mbo_gp_posterior")
+    return mean, std
+
+
+class PolicyHandle:
+    """Owns an `mbo_policy` (device copies of one MLP in the kernels' layouts)."""
+
+    def __init__(self):
+        h = C.c_void_p()
+        L.check(L.lib().mbo_policy_create(C.byref(h)), "mbo_policy_create")
+        self.h = h
+        self.widths = None
+
+    def set_weights(self, weights, biases, activation="relu"):
+        """weights[l]: [out,in] fp32 CUDA tensors (nn.Linear.weight), biases[l]: [out]."""
+        n = len(weights)
+        ws = [w.detach().contiguous().float() for w in weights]
+        bs = [b.detach().contiguous().float() for b in biases]
+        on_dev = all(t.is_cuda for t in ws + bs)
+        if not on_dev:
+            ws = [t.cpu() for t in ws]
+            bs = [t.cpu() for t in bs]
+        widths = [ws[0].shape[1]] + [w.shape[0] for w in ws]
+        W = (C.c_void_p * n)(*[t.data_ptr() for t in ws])
+        Bv = (C.c_void_p * n)(*[t.data_ptr() for t in bs])
+        wd = (C.c_int32 * (n + 1))(*widths)
+        L.check(L.lib().mbo_policy_set_weights(self.h, n, wd, L.ACT[activation], W, Bv, int(on_dev), _stream()),
+                "mbo_policy_set_weights")
+        if not on_dev:
+            torch.cuda.current_stream().synchronize()
+        self.widths = widths
+        self._keep = (ws, bs)
+
+    def __del__(self):
+        try:
+            if self.h:
+                L.lib().mbo_policy_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+def af_logits(policy, feat_src, cand, mean, std, epi, B, mode=L.MLP_FP32, logits=None):
+    """get_state + NeuralAF.forward (policy net) for B x M candidates -> logits [B,M] fp32."""
+    _chk(mean, torch.float32, "mean"); _chk(std, torch.float32, "std"); _chk(epi, torch.float32, "epi")
+    if logits is None:
+        logits = torch.empty((B, cand.M), dtype=torch.float32, device=mean.device)
+    F = len(feat_src)
+    fs = (C.c_int32 * F)(*feat_src)
+    L.check(L.lib().mbo_af_logits(policy.h, mode, B, F, fs, cand.ref(), _p(mean), _p(std), _p(epi), _p(logits),
+                                  C.c_void_p(0), 0, _stream()), "mbo_af_logits")
+    return logits
+
+
+def value_net(policy, tT):
+    _chk(tT, torch.float32, "tT")
+    out = torch.empty((tT.shape[0],), dtype=torch.float32, device=tT.device)
+    L.check(L.lib().mbo_value_net(policy.h, tT.shape[0], _p(tT), _p(out), _stream()), "mbo_value_net")
+    return out
+
+
+def logits_argmax(logits):
+    _chk(logits, torch.float32, "logits")
+    B, M = logits.shape
+    a = torch.empty((B,), dtype=torch.int32, device=logits.device)
+    v = torch.empty((B,), dtype=torch.float32, device=logits.device)
+    L.check(L.lib().mbo_logits_argmax(B, M, _p(logits), _p(a), _p(v), _stream()), "mbo_logits_argmax")
+    return a, v
+
+
+def logits_topk(logits, k):
+    _chk(logits, torch.float32, "logits")
+    B, M = logits.shape
+    idx = torch.empty((B, k), dtype=torch.int32, device=logits.device)
+    val = torch.empty((B, k), dtype=torch.float32, device=logits.device)
+    L.check(L.lib().mbo_logits_topk(B, M, k, _p(logits), _p(idx), _p(val), _stream()), "mbo_logits_topk")
+    return idx, val
+
+
+def logits_sample(logits, seed, step):
+    _chk(logits, torch.float32, "logits")
+    B, M = logits.shape
+    a = torch.empty((B,), dtype=torch.int32, device=logits.device)
+    L.check(L.lib().mbo_logits_sample(B, M, _p(logits), int(seed), int(step), _p(a), _stream()), "mbo_logits_sample")
+    return a
+
+
+def logits_logp_entropy(logits, actions):
+    _chk(logits, torch.float32, "logits"); _chk(actions, torch.int32, "actions")
+    B, M = logits.shape
+    lp = torch.empty((B,), dtype=torch.float32, device=logits.device)
+    en = torch.empty((B,), dtype=torch.float32, device=logits.device)
+    L.check(L.lib().mbo_logits_logp_entropy(B, M, _p(logits), _p(actions), _p(lp), _p(en), _stream()),
+            "mbo_logits_logp_entropy")
+    return lp, en
+
+
+def candidates_gather(cand, idx, B):
+    _chk(idx, torch.int32, "idx")
+    k = idx.shape[1]
+    out = torch.empty((B, k, cand.D), dtype=torch.float64, device=idx.device)
+    L.check(L.lib().mbo_candidates_gather(B, cand.ref(), k, _p(idx), _p(out), _stream()), "mbo_candidates_gather")
+    return out
+
+
+def cubes_around(x, diam):
+    _chk(x, torch.float64, "x")
+    B, k, D = x.shape
+    cubes = torch.empty((B, k, 2, D), dtype=torch.float64, device=x.device)
+    L.check(L.lib().mbo_cubes_around(B, k, D, _p(x), float(diam), _p(cubes), _stream()), "mbo_cubes_around")
+    return cubes

@@ -1,0 +1,176 @@
+"""GPU parity: NeuralAF evaluation (features -> MLP -> logits) and the per-episode reductions,
+through the C ABI, against the oracle / the vectors minted from the reference.
+Reference: metabo_gym.py:624-677 (get_state), policies.py:104-161, mlp.py:52-61.
+Tolerance (north_star): logits within 1e-3 relative (relative to max|logit| of the candidate set,
+logits cross zero mid-episode); the CUDA-core fp32 mode is held to 1e-5."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import metabo_oracle as O
+from oracle import sampling_oracle as S
+
+pytestmark = pytest.mark.gpu
+
+CASES = [("bra", "weights_bra_1635.npz"), ("hm3", "weights_hm3_1988.npz"), ("gps", "weights_gps_1161.npz")]
+MODES = [("fp32", 0, 1e-5), ("tf32", 1, 1e-3), ("bf16x3", 2, 2e-5)]
+
+
+def feat_codes(features, D, mask):
+    from metabo_b200 import _lib as L
+    codes = []
+    if "posterior_mean" in features: codes.append(L.FEAT_MEAN)
+    if "posterior_std" in features: codes.append(L.FEAT_STD)
+    if "x" in features: codes += [L.FEAT_X0 + d for d in range(D)]
+    if "incumbent" in features: codes.append(L.FEAT_INCUMBENT)
+    if "timestep_perc" in features: codes.append(L.FEAT_TPERC)
+    if "timestep" in features: codes.append(L.FEAT_TIMESTEP)
+    if "budget" in features: codes.append(L.FEAT_BUDGET)
+    return [c for c, keep in zip(codes, mask) if keep]
+
+
+def make_policy(pw, net="policy_net"):
+    from metabo_b200 import ops
+    h = ops.PolicyHandle()
+    layers = pw.layers(net)
+    h.set_weights([w.cuda() for w, _ in layers], [b.cuda() for _, b in layers], pw.act)
+    return h
+
+
+def tc_supported(pw):
+    l = pw.layers("policy_net")
+    return len(l) == 5 and pw.act == "relu" and all(w.shape[0] == l[0][0].shape[0] for w, _ in l[:-1])
+
+
+@pytest.mark.parametrize("name,wfile", CASES)
+@pytest.mark.parametrize("mode_name,mode,tol", MODES)
+def test_logits_on_reference_states(golden_dir, name, wfile, mode_name, mode, tol):
+    """teacher-forced: the reference's own (mean, std, x, t, T) -> logits."""
+    from metabo_b200 import ops
+    dev = torch.device("cuda:0")
+    ep = np.load(os.path.join(golden_dir, "episode_%s.npz" % name))
+    spec = json.loads(str(ep["__env_spec__"]))
+    pw = O.PolicyWeights.from_npz(os.path.join(golden_dir, wfile))
+    if mode != 0 and not tc_supported(pw):
+        pytest.skip("tensor-core path needs the 4x200 ReLU architecture")
+    pol = make_policy(pw)
+    D, T = spec["D"], spec["T"]
+    codes = feat_codes(spec["features"], D, pw.mask)
+    for t in ep["keep"]:
+        p = "t%02d_" % int(t)
+        state, xi = ep[p + "state"], ep[p + "xi_t"]
+        cs = ops.CandidateSet(D, tail=torch.as_tensor(xi, dtype=torch.float64, device=dev).contiguous())
+        mean = torch.as_tensor(state[None, :, 0].copy(), device=dev)
+        std = torch.as_tensor(state[None, :, 1].copy(), device=dev)
+        epi = torch.tensor([[float(ep[p + "incumbent"]), int(t) / T, float(int(t)), float(T)]],
+                           dtype=torch.float32, device=dev)
+        lg = ops.af_logits(pol, codes, cs, mean, std, epi, 1, mode=mode)
+        torch.cuda.synchronize()
+        got, ref = lg[0].cpu().numpy(), ep[p + "logits"]
+        scale = np.max(np.abs(ref))
+        assert np.max(np.abs(got - ref)) <= tol * scale + 1e-6, (name, int(t), mode_name)
+        if mode == 0:
+            # deterministic-eval action: identical unless the reference's top two are within tolerance
+            a_ref = int(ep[p + "action"])
+            a, _ = ops.logits_argmax(lg)
+            a = int(a[0])
+            assert a == a_ref or abs(ref[a] - ref[a_ref]) <= 2 * tol * scale
+
+
+def test_value_net_matches_reference(golden_dir):
+    from metabo_b200 import ops
+    pw = O.PolicyWeights.from_npz(os.path.join(golden_dir, "weights_bra_1635.npz"))
+    vh = make_policy(pw, "value_net")
+    tT = torch.tensor([[0., 30.], [7., 30.], [29., 30.]], device="cuda:0")
+    v = ops.value_net(vh, tT).cpu().numpy()
+    states = np.zeros((3, 4, 6), dtype=np.float32)
+    states[:, :, 4] = tT[:, 0].cpu().numpy()[:, None]
+    states[:, :, 5] = 30.0
+    _, vo = O.policy_forward(pw, states)
+    np.testing.assert_allclose(v, vo.numpy(), rtol=1e-5, atol=1e-5)
+
+
+def test_end_to_end_gp_features_logits_vs_oracle(golden_dir):
+    """GP fit -> posterior (fp32 cast) -> features -> logits for B ragged episodes against the
+    oracle's get_state + NeuralAF.forward on well-conditioned synthetic Hartmann-3 states."""
+    from metabo_b200 import ops
+    dev = torch.device("cuda:0")
+    pw = O.PolicyWeights.from_npz(os.path.join(golden_dir, "weights_hm3_1988.npz"))
+    pol = make_policy(pw)
+    rng = np.random.RandomState(11)
+    D, T, B = 3, 30, 6
+    feats = ["posterior_mean", "posterior_std", "timestep", "budget", "x"]
+    var, noise, ls = 0.83, 1e-5, np.array([0.716, 0.298, 0.186])
+    ts = [0, 1, 5, 12, 20, 30]
+    grids = O.Grids(D, N_MS=2000, N_LS=2000, k=5)
+    X = np.zeros((B, T, D)); Y = np.zeros((B, T))
+    for b, t in enumerate(ts):
+        X[b, :t] = rng.rand(t, D)
+        Y[b, :t] = O.hm3_var(X[b, :t], np.zeros(3), 1.0)[:, 0]
+    tt = lambda a, dt=torch.float64: torch.as_tensor(a, dtype=dt, device=dev).contiguous()
+    state, status = ops.gp_fit(tt(np.array(ts), torch.int32), tt(X), tt(Y), tt(np.tile(ls, (B, 1))),
+                               tt(np.full(B, var)), tt(np.full(B, noise)))
+    cs = ops.CandidateSet(D, tail=tt(grids.multistart_grid))
+    mean, std = ops.gp_posterior(state, T, cs, B, out_dtype=torch.float32)
+    epi = tt(np.array([[0.0, t / T, t, T] for t in ts]), torch.float32)
+    codes = feat_codes(feats, D, pw.mask)
+    lg = ops.af_logits(pol, codes, cs, mean, std, epi, B, mode=0).cpu().numpy()
+    for b, t in enumerate(ts):
+        gp = O.EpisodeGP(D, "RBF", var, ls, noise)
+        gp.set_data(X[b, :t], Y[b, :t])
+        s = O.get_state(gp, grids.multistart_grid, feats, t, T)
+        ref = O.policy_forward(pw, s[None])[0][0].numpy()
+        assert np.max(np.abs(lg[b] - ref)) <= 1e-3 * np.max(np.abs(ref)) + 1e-5, (b, t)
+
+
+def test_reductions_vs_numpy_and_torch():
+    from metabo_b200 import ops
+    rng = np.random.RandomState(2)
+    B, M = 9, 4999
+    lg = (rng.randn(B, M) * 3).astype(np.float32)
+    lg[0, 100] = lg[0, 4000] = lg[0].max() + 1.0        # exact tie -> first index
+    lg[1, :] = -7.5                                     # all equal
+    lgt = torch.as_tensor(lg, device="cuda:0")
+    a, v = ops.logits_argmax(lgt)
+    assert np.array_equal(a.cpu().numpy(), np.argmax(lg, axis=1))
+    assert np.array_equal(v.cpu().numpy(), lg.max(axis=1))
+    idx, val = ops.logits_topk(lgt, 5)
+    ref_idx = np.argsort(-lg, axis=1, kind="stable")[:, :5]
+    assert np.array_equal(idx.cpu().numpy(), ref_idx)
+    acts = torch.as_tensor(rng.randint(0, M, size=B).astype(np.int32), device="cuda:0")
+    lp, en = ops.logits_logp_entropy(lgt, acts)
+    lpo, eno = O.categorical_logp_entropy(torch.as_tensor(lg), acts.cpu().numpy())
+    np.testing.assert_allclose(lp.cpu().numpy(), lpo.numpy(), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(en.cpu().numpy(), eno.numpy(), rtol=1e-5, atol=1e-5)
+    # large-magnitude logits as the shipped Branin net produces (|logit| ~ 1500)
+    big = (1349.0 + rng.rand(2, 966)).astype(np.float32)
+    lp2, en2 = ops.logits_logp_entropy(torch.as_tensor(big, device="cuda:0"),
+                                       torch.zeros(2, dtype=torch.int32, device="cuda:0"))
+    lpo2, eno2 = O.categorical_logp_entropy(torch.as_tensor(big), np.zeros(2, dtype=np.int64))
+    np.testing.assert_allclose(lp2.cpu().numpy(), lpo2.numpy(), rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(en2.cpu().numpy(), eno2.numpy(), rtol=1e-5, atol=1e-4)
+
+
+def test_sampler_matches_oracle_noise_and_distribution():
+    from metabo_b200 import ops
+    rng = np.random.RandomState(5)
+    B, M = 64, 50
+    lg = (rng.randn(B, M) * 2).astype(np.float32)
+    lgt = torch.as_tensor(lg, device="cuda:0")
+    a = ops.logits_sample(lgt, seed=1234, step=7).cpu().numpy()
+    for b in range(B):
+        noisy = lg[b] + S.gumbel_noise(1234, b, 7, M)
+        assert noisy[a[b]] >= noisy.max() - 1e-4            # same noise, device logf within an ulp
+    a2 = ops.logits_sample(lgt, seed=1234, step=7).cpu().numpy()
+    assert np.array_equal(a, a2)                             # counter-based: reproducible
+    # chi-square of the empirical distribution of one row over 20000 steps (rows = steps trick)
+    n = 20000
+    row = np.tile(lg[0, :8][None], (n, 1)).astype(np.float32)
+    acts = ops.logits_sample(torch.as_tensor(row, device="cuda:0"), seed=99, step=0).cpu().numpy()
+    p = np.exp(row[0] - row[0].max()); p /= p.sum()
+    cnt = np.bincount(acts, minlength=8)
+    chi2 = np.sum((cnt - n * p) ** 2 / (n * p))
+    assert chi2 < 30.0                                       # 7 dof, p ~ 1e-4
