@@ -1,11 +1,620 @@
-// neural_af_tc.cu -- placeholder, replaced by the tcgen05 kernel.
+// neural_af_tc.cu -- fused NeuralAF evaluation on tcgen05 tensor cores (sm_100a).
+//
+// Replaces get_state feature packing (metabo/environment/metabo_gym.py:624-677) followed by
+// NeuralAF.forward -> MLP.forward (metabo/policies/policies.py:104-125, mlp.py:52-61) for the
+// shipped F -> H -> H -> H -> H -> 1 ReLU policies (H = 200): features and hidden activations
+// never touch HBM; one CTA owns a tile of 128 candidates of one episode.
+//
+// Data flow per tile (TMEM columns: R0 = [0,208), R1 = [208,416), S = [416,448)):
+//   features (fp32)  --split hi/lo tf32-->  S                         (epilogue warps, tcgen05.st)
+//   L0: D(R0)  = S * W0^T     3xTF32 (hi*hi + lo*hi + hi*lo), bias folded in as a ones column
+//   E0: R0 <- act(relu(D))    in place, converted to the MMA operand format
+//   L1: D(R1)  = A(R0) * W1^T ; E1 in place on R1 ; L2: D(R0) = A(R1) * W2^T ; E2 ; L3: D(R1) = A(R0) * W3^T
+//   E3: logit = sum_j relu(D_j + b3_j) * w4_j + b4                    (CUDA cores, fp32)
+// The A operand of every MMA comes from TMEM (tcgen05.mma "TS" form), the B operand (weights,
+// K-major, no-swizzle canonical layout) streams from L2 through a shared-memory ring filled with
+// cp.async.bulk (TMA engine, 1-D) and released by tcgen05.commit.  The epilogue of layer l hands
+// the next layer its K range chunk by chunk (mbarriers), so the MMAs of layer l+1 start while the
+// epilogue of layer l is still converting.
+//
+// Arithmetic modes (hidden layers): MBO_MLP_TF32   kind::tf32, operands rounded to tf32 (rna);
+//                                   MBO_MLP_BF16X3 kind::f16 bf16, a = a_hi + a_lo, w = w_hi + w_lo,
+//                                                  a*w ~ a_hi*w_hi + a_lo*w_hi + a_hi*w_lo.
+// Warp roles (192 threads): warps 0-3 epilogue (TMEM lanes 32*w..), warp 4 TMA producer + TMEM
+// allocation, warp 5 MMA issuer.  Every mbarrier wait is bounded (globaltimer) and raises a
+// device-side error flag instead of hanging.
 #include "common.cuh"
 #include "policy.cuh"
+#include <cuda_bf16.h>
+
 namespace mbo {
-int tc_pack_weights(mbo_policy* p, cudaStream_t) { p->tc_ready = 0; return MBO_OK; }
-int tc_forward(const mbo_policy*, int, int, int, const int32_t*, const mbo_candidates*, const float*, const float*,
-               const float*, float*, void*, size_t, cudaStream_t) {
-  set_error("tensor-core NeuralAF path not built yet");
-  return MBO_ERR_UNSUPPORTED;
+
+constexpr int TC_N = 208;            // padded hidden width (UMMA N, multiple of 16)
+constexpr int TC_M = 128;            // candidates per tile (UMMA M)
+constexpr int TC_THREADS = 192;
+constexpr int TC_K0 = 8;             // layer-0 K (features + ones column, <= 8)
+constexpr int CHUNK_ROW_BYTES = TC_N * 16;   // one 16-byte K chunk for all 208 rows = 3328 B
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t COL_R0 = 0, COL_R1 = 208, COL_S = 416;
+
+template <int MODE> struct ModeCfg;
+template <> struct ModeCfg<MBO_MLP_TF32> {
+  static constexpr int K = 200;                // 25 slices of 8
+  static constexpr int SLICE_K = 8;
+  static constexpr int SLICES = 25;
+  static constexpr int SLICES_PER_STAGE = 5;
+  static constexpr int STAGES_PER_LAYER = 5;
+  static constexpr int STAGE_BYTES = SLICES_PER_STAGE * 2 * CHUNK_ROW_BYTES;   // 33 280
+  static constexpr int NSTAGE = 6;
+  static constexpr int CHUNK_COLS = 40;        // accumulator columns converted per hand-off
+  static constexpr int NCHUNK = 5;
+};
+template <> struct ModeCfg<MBO_MLP_BF16X3> {
+  static constexpr int K = 208;                // 13 slices of 16
+  static constexpr int SLICE_K = 16;
+  static constexpr int SLICES = 13;
+  static constexpr int SLICES_PER_STAGE = 1;
+  static constexpr int STAGES_PER_LAYER = 13;
+  static constexpr int STAGE_BYTES = 2 * 2 * CHUNK_ROW_BYTES;                  // hi + lo: 13 312
+  static constexpr int NSTAGE = 14;
+  static constexpr int CHUNK_COLS = 32;
+  static constexpr int NCHUNK = 7;             // 6 x 32 + 1 x 16
+};
+
+constexpr int W0_BYTES = 2 * (TC_K0 / 4) * CHUNK_ROW_BYTES;   // hi + lo: 13 312
+constexpr int TAIL_FLOATS = 4 * TC_N + 4;                    // b1 b2 b3 w4 | b4
+
+// packed-weight buffer layout (bytes): [W0][tf32 hidden x3][bf16 hidden x3][tail floats]
+struct PackLayout {
+  size_t off_w0, off_tf32, off_bf16, off_tail, total;
+};
+__host__ __device__ inline PackLayout pack_layout() {
+  PackLayout p;
+  p.off_w0 = 0;
+  p.off_tf32 = W0_BYTES;
+  p.off_bf16 = p.off_tf32 + (size_t)3 * ModeCfg<MBO_MLP_TF32>::STAGES_PER_LAYER * ModeCfg<MBO_MLP_TF32>::STAGE_BYTES;
+  p.off_tail = p.off_bf16 + (size_t)3 * ModeCfg<MBO_MLP_BF16X3>::STAGES_PER_LAYER * ModeCfg<MBO_MLP_BF16X3>::STAGE_BYTES;
+  p.total = p.off_tail + sizeof(float) * TAIL_FLOATS;
+  return p;
 }
+
+// ------------------------------------------------------------------------------------------------
+// small PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
 }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+constexpr uint64_t WAIT_TIMEOUT_NS = 2000000000ull;   // 2 s: far beyond any legitimate wait
+// bounded wait; returns false (and latches *abort) on timeout or when another role already aborted
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag) {
+  if (mbar_try_wait(bar, parity)) return true;
+  const uint64_t t0 = globaltimer_ns();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3ff) == 0) {
+      if (*abort_flag) return false;
+      if (globaltimer_ns() - t0 > WAIT_TIMEOUT_NS) { *abort_flag = 1; return false; }
+    }
+  }
+  return true;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T
+__device__ __forceinline__ void mma_ts_tf32(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_ts_bf16(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// K-major, no-swizzle canonical layout: LBO = byte distance between the two 16-byte K chunks of one
+// MMA, SBO = byte distance between 8-row groups (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t make_bdesc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(CHUNK_ROW_BYTES >> 4) << 16) |
+         ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
+}
+// cute::UMMA::InstrDescriptor: c_format f32, a/b format, K-major both, N>>3 at bit 17, M>>4 at bit 24
+__host__ __device__ constexpr uint32_t make_idesc(uint32_t ab_format) {
+  return (1u << 4) | (ab_format << 7) | (ab_format << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+}
+constexpr uint32_t IDESC_TF32 = make_idesc(2), IDESC_BF16 = make_idesc(1);
+
+#define TMEM_LD8(taddr, v)                                                                              \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                 \
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) \
+               : "r"(taddr))
+#define TMEM_ST8(taddr, v)                                                                              \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"                 \
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) \
+               : "memory")
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------
+// weight packing
+// ------------------------------------------------------------------------------------------------
+struct PackArgs {
+  const float* W[5];
+  const float* b[5];
+  int F, H;
+};
+
+__global__ void tc_pack_kernel(PackArgs a, unsigned char* __restrict__ out) {
+  const PackLayout pl = pack_layout();
+  const size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // 32-bit word index
+  const size_t byte = w * 4;
+  if (byte >= pl.total) return;
+  uint32_t* dst = (uint32_t*)(out + byte);
+  const int F = a.F, H = a.H;
+  if (byte < pl.off_tf32) {
+    // W0: [part][chunk][n][4 floats]; k = chunk*4 + e; column F carries the bias
+    size_t i = byte / 4;
+    int e = i % 4; i /= 4;
+    int n = i % TC_N; i /= TC_N;
+    int chunk = i % (TC_K0 / 4); i /= (TC_K0 / 4);
+    int part = (int)i;
+    int k = chunk * 4 + e;
+    float v = 0.f;
+    if (n < H) v = k < F ? a.W[0][n * F + k] : (k == F ? a.b[0][n] : 0.f);
+    float hi = tf32_rna(v);
+    float lo = tf32_rna(v - hi);
+    *dst = __float_as_uint(part == 0 ? hi : lo);
+  } else if (byte < pl.off_bf16) {
+    using C = ModeCfg<MBO_MLP_TF32>;
+    size_t i = (byte - pl.off_tf32) / 4;
+    int e = i % 4; i /= 4;
+    int n = i % TC_N; i /= TC_N;
+    int chunk = i % 2; i /= 2;
+    int slice = i % C::SLICES_PER_STAGE; i /= C::SLICES_PER_STAGE;
+    int stage = i % C::STAGES_PER_LAYER; i /= C::STAGES_PER_LAYER;
+    int layer = (int)i + 1;
+    int k = (stage * C::SLICES_PER_STAGE + slice) * C::SLICE_K + chunk * 4 + e;
+    float v = (n < H && k < H) ? a.W[layer][n * H + k] : 0.f;
+    *dst = __float_as_uint(tf32_rna(v));
+  } else if (byte < pl.off_tail) {
+    using C = ModeCfg<MBO_MLP_BF16X3>;
+    size_t i = (byte - pl.off_bf16) / 4;
+    int pair = i % 4; i /= 4;
+    int n = i % TC_N; i /= TC_N;
+    int chunk = i % 2; i /= 2;
+    int part = i % 2; i /= 2;
+    int stage = i % C::STAGES_PER_LAYER; i /= C::STAGES_PER_LAYER;
+    int layer = (int)i + 1;
+    int k = stage * C::SLICE_K + chunk * 8 + pair * 2;
+    float v0 = (n < H && k < H) ? a.W[layer][n * H + k] : 0.f;
+    float v1 = (n < H && k + 1 < H) ? a.W[layer][n * H + k + 1] : 0.f;
+    __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+    __nv_bfloat16 o0 = h0, o1 = h1;
+    if (part == 1) {
+      o0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
+      o1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+    }
+    *dst = (uint32_t)__bfloat16_as_ushort(o0) | ((uint32_t)__bfloat16_as_ushort(o1) << 16);
+  } else {
+    size_t i = (byte - pl.off_tail) / 4;
+    float v = 0.f;
+    if (i < (size_t)3 * TC_N) {
+      int l = (int)(i / TC_N) + 1, n = (int)(i % TC_N);
+      v = n < H ? a.b[l][n] : 0.f;
+    } else if (i < (size_t)4 * TC_N) {
+      int n = (int)(i - 3 * TC_N);
+      v = n < H ? a.W[4][n] : 0.f;
+    } else if (i == (size_t)4 * TC_N) {
+      v = a.b[4][0];
+    }
+    *dst = __float_as_uint(v);
+  }
+}
+
+int tc_pack_weights(mbo_policy* p, cudaStream_t s) {
+  p->tc_ready = 0;
+  if (p->n_layers != 5 || p->activation != MBO_ACT_RELU) return MBO_OK;
+  const int F = p->widths[0], H = p->widths[1];
+  if (F + 1 > TC_K0 || H > TC_N || H < 8 || p->widths[5] != 1) return MBO_OK;
+  for (int l = 1; l <= 4; ++l)
+    if (p->widths[l] != H) return MBO_OK;
+  const PackLayout pl = pack_layout();
+  if (!p->d_tc || p->tc_bytes != pl.total) {
+    if (p->d_tc) cudaFree(p->d_tc);
+    p->d_tc = nullptr;
+    MBO_CUDA(cudaMalloc(&p->d_tc, pl.total));
+    p->tc_bytes = pl.total;
+  }
+  PackArgs a;
+  for (int l = 0; l < 5; ++l) { a.W[l] = p->d_W_raw + p->raw_off[l]; a.b[l] = p->d_b[l]; }
+  a.F = F; a.H = H;
+  size_t words = pl.total / 4;
+  tc_pack_kernel<<<(unsigned)((words + 255) / 256), 256, 0, s>>>(a, (unsigned char*)p->d_tc);
+  MBO_LAUNCH_CHECK();
+  p->tc_ready = 1;
+  p->tc_F = F; p->tc_H = H;
+  return MBO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the fused kernel
+// ------------------------------------------------------------------------------------------------
+struct TcFeat {
+  int F;
+  int src[8];
+};
+
+template <int MODE>
+struct TcSmem {
+  using C = ModeCfg<MODE>;
+  static constexpr size_t off_ring = 0;
+  static constexpr size_t off_w0 = off_ring + (size_t)C::NSTAGE * C::STAGE_BYTES;
+  static constexpr size_t off_tail = off_w0 + W0_BYTES;
+  static constexpr size_t off_bars = off_tail + sizeof(float) * TAIL_FLOATS;
+  static constexpr int n_bars = 2 * C::NSTAGE + C::NCHUNK + 2 + 3;   // ring, a_ready, d_full[2], feat_full, s_free, w0_full
+  static constexpr size_t off_misc = off_bars + 8 * n_bars;
+  static constexpr size_t total = off_misc + 16;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candidates cand, int B,
+                    int tiles_per_episode, const float* __restrict__ mean, const float* __restrict__ std_,
+                    const float* __restrict__ epi, float* __restrict__ logits, int* __restrict__ err_flag) {
+  using C = ModeCfg<MODE>;
+  using SM = TcSmem<MODE>;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const PackLayout pl = pack_layout();
+
+  unsigned char* ring = smem + SM::off_ring;
+  float* s_tail = (float*)(smem + SM::off_tail);
+  uint64_t* bars = (uint64_t*)(smem + SM::off_bars);
+  uint32_t* s_tmem = (uint32_t*)(smem + SM::off_misc);
+  volatile int* s_abort = (volatile int*)(smem + SM::off_misc + 4);
+
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR_WFULL = [&](int s) { return bar0 + 8u * (uint32_t)s; };
+  auto BAR_WEMPTY = [&](int s) { return bar0 + 8u * (uint32_t)(C::NSTAGE + s); };
+  auto BAR_AREADY = [&](int c) { return bar0 + 8u * (uint32_t)(2 * C::NSTAGE + c); };
+  auto BAR_DFULL = [&](int i) { return bar0 + 8u * (uint32_t)(2 * C::NSTAGE + C::NCHUNK + i); };
+  const uint32_t BAR_FEAT = bar0 + 8u * (uint32_t)(2 * C::NSTAGE + C::NCHUNK + 2);
+  const uint32_t BAR_SFREE = BAR_FEAT + 8u;
+  const uint32_t BAR_W0 = BAR_FEAT + 16u;
+
+  const int total_tiles = B * tiles_per_episode;
+  const int my_tiles = total_tiles > (int)blockIdx.x ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  // ---- one-time setup ----
+  if (tid == 0) {
+    *s_abort = 0;
+    for (int s = 0; s < C::NSTAGE; ++s) { mbar_init(BAR_WFULL(s), 1); mbar_init(BAR_WEMPTY(s), 1); }
+    for (int c = 0; c < C::NCHUNK; ++c) mbar_init(BAR_AREADY(c), 128);
+    mbar_init(BAR_DFULL(0), 1);
+    mbar_init(BAR_DFULL(1), 1);
+    mbar_init(BAR_FEAT, 128);
+    mbar_init(BAR_SFREE, 1);
+    mbar_init(BAR_W0, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < TAIL_FLOATS; i += TC_THREADS) s_tail[i] = ((const float*)(pack + pl.off_tail))[i];
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+
+  if (warp == 4) {
+    // ================= TMA producer =================
+    if (lane == 0 && my_tiles > 0) {
+      mbar_expect_tx(BAR_W0, W0_BYTES);
+      bulk_g2s(smem_u32(smem + SM::off_w0), pack + pl.off_w0, W0_BYTES, BAR_W0);
+      const unsigned char* wsrc = pack + (MODE == MBO_MLP_TF32 ? pl.off_tf32 : pl.off_bf16);
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      for (int t = 0; t < my_tiles && ok; ++t) {
+        for (int ls = 0; ls < 3 * C::STAGES_PER_LAYER; ++ls) {
+          if (!mbar_wait(BAR_WEMPTY(stage), phase ^ 1u, s_abort)) { ok = false; break; }
+          mbar_expect_tx(BAR_WFULL(stage), C::STAGE_BYTES);
+          bulk_g2s(smem_u32(ring + (size_t)stage * C::STAGE_BYTES), wsrc + (size_t)ls * C::STAGE_BYTES, C::STAGE_BYTES,
+                   BAR_WFULL(stage));
+          if (++stage == C::NSTAGE) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ================= MMA issuer =================
+    if (lane == 0 && my_tiles > 0) {
+      bool ok = mbar_wait(BAR_W0, 0, s_abort);
+      int stage = 0;
+      uint32_t wphase = 0, aphase = 0, fphase = 0;
+      const uint32_t w0_addr = smem_u32(smem + SM::off_w0);
+      for (int t = 0; t < my_tiles && ok; ++t) {
+        // ---- L0: D(R0) = S * W0^T, 3xTF32 ----
+        if (!mbar_wait(BAR_FEAT, fphase, s_abort)) { ok = false; break; }
+        fphase ^= 1u;
+        tc_fence_after();
+        {
+          const uint32_t a_hi = tmem + COL_S, a_lo = tmem + COL_S + 16;
+          const uint64_t b_hi = make_bdesc(w0_addr), b_lo = make_bdesc(w0_addr + (TC_K0 / 4) * CHUNK_ROW_BYTES);
+          mma_ts_tf32(tmem + COL_R0, a_hi, b_hi, IDESC_TF32, 0);
+          mma_ts_tf32(tmem + COL_R0, a_lo, b_hi, IDESC_TF32, 1);
+          mma_ts_tf32(tmem + COL_R0, a_hi, b_lo, IDESC_TF32, 1);
+          tc_commit(BAR_SFREE);
+          tc_commit(BAR_DFULL(0));
+        }
+        // ---- L1..L3 ----
+        for (int l = 1; l <= 3 && ok; ++l) {
+          const uint32_t colA = (l & 1) ? COL_R0 : COL_R1;
+          const uint32_t colD = (l & 1) ? COL_R1 : COL_R0;
+          int slice = 0;
+          for (int c = 0; c < C::NCHUNK && ok; ++c) {
+            if (!mbar_wait(BAR_AREADY(c), aphase, s_abort)) { ok = false; break; }
+            tc_fence_after();
+            const int slices_in_chunk = (MODE == MBO_MLP_TF32) ? 5 : (c == C::NCHUNK - 1 ? 1 : 2);
+            for (int sc = 0; sc < slices_in_chunk; ++sc, ++slice) {
+              const int sis = slice % C::SLICES_PER_STAGE;
+              if (sis == 0) {
+                if (!mbar_wait(BAR_WFULL(stage), wphase, s_abort)) { ok = false; break; }
+                tc_fence_after();
+              }
+              const uint32_t sbase = smem_u32(ring + (size_t)stage * C::STAGE_BYTES);
+              if (MODE == MBO_MLP_TF32) {
+                const uint64_t bd = make_bdesc(sbase + sis * 2 * CHUNK_ROW_BYTES);
+                mma_ts_tf32(tmem + colD, tmem + colA + slice * 8, bd, IDESC_TF32, slice > 0 ? 1u : 0u);
+              } else {
+                // chunk c of the accumulator holds [hi(16 cols) | lo(16 cols)] of its 32 K values
+                const uint32_t a_hi = tmem + colA + (slice >> 1) * 32 + (slice & 1) * 8;
+                const uint32_t a_lo = a_hi + (slice == C::SLICES - 1 ? 8 : 16);   // the last chunk is 16 columns wide
+                const uint64_t b_hi = make_bdesc(sbase), b_lo = make_bdesc(sbase + 2 * CHUNK_ROW_BYTES);
+                mma_ts_bf16(tmem + colD, a_hi, b_hi, IDESC_BF16, slice > 0 ? 1u : 0u);
+                mma_ts_bf16(tmem + colD, a_lo, b_hi, IDESC_BF16, 1u);
+                mma_ts_bf16(tmem + colD, a_hi, b_lo, IDESC_BF16, 1u);
+              }
+              if (sis == C::SLICES_PER_STAGE - 1) {
+                tc_commit(BAR_WEMPTY(stage));
+                if (++stage == C::NSTAGE) { stage = 0; wphase ^= 1u; }
+              }
+            }
+          }
+          aphase ^= 1u;
+          tc_commit(BAR_DFULL(l & 1));
+        }
+      }
+    }
+  } else {
+    // ================= epilogue warps (thread = TMEM lane = candidate row) =================
+    const int row = tid;                                    // 0..127
+    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    uint32_t dphase[2] = {0, 0};
+    uint32_t sphase = 0;
+    bool ok = true;
+    const float* s_b[3] = {s_tail, s_tail + TC_N, s_tail + 2 * TC_N};
+    const float* s_w4 = s_tail + 3 * TC_N;
+
+    auto build_features = [&](int t_idx) {
+      // tile -> (episode, first candidate)
+      const int tile = (int)blockIdx.x + t_idx * (int)gridDim.x;
+      const int b = tile / tiles_per_episode;
+      const int m = (tile - b * tiles_per_episode) * TC_M + row;
+      float f[TC_K0];
+#pragma unroll
+      for (int i = 0; i < TC_K0; ++i) f[i] = 0.f;
+      if (m < cand.M) {
+        double x[MBO_MAX_D];
+#pragma unroll
+        for (int d = 0; d < MBO_MAX_D; ++d) x[d] = 0.0;
+        load_candidate(cand, b, m, x);
+        const float mu = mean[(size_t)b * cand.M + m], sd = std_[(size_t)b * cand.M + m];
+#pragma unroll
+        for (int i = 0; i < TC_K0 - 1; ++i) {
+          if (i < fs.F) {
+            const int s = fs.src[i];
+            float v;
+            if (s == MBO_FEAT_MEAN) v = mu;
+            else if (s == MBO_FEAT_STD) v = sd;
+            else if (s >= MBO_FEAT_X0 && s < MBO_FEAT_X0 + MBO_MAX_D) {
+              v = 0.f;
+#pragma unroll
+              for (int d = 0; d < MBO_MAX_D; ++d) if (s - MBO_FEAT_X0 == d) v = (float)x[d];
+            } else v = epi[b * 4 + (s - MBO_FEAT_INCUMBENT)];
+            f[i] = v;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < TC_K0; ++i) if (i == fs.F) f[i] = 1.0f;    // bias column
+      }
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float h = tf32_rna(f[i]);
+        hi[i] = __float_as_uint(h);
+        lo[i] = __float_as_uint(tf32_rna(f[i] - h));
+      }
+      TMEM_ST8(tlane + COL_S, hi);
+      TMEM_ST8(tlane + COL_S + 16, lo);
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(BAR_FEAT);
+    };
+
+    if (my_tiles > 0) build_features(0);
+    for (int t = 0; t < my_tiles && ok; ++t) {
+      // ---- E0..E2: relu(D + b) -> next layer's A operand, in place ----
+      for (int l = 0; l < 3 && ok; ++l) {
+        const uint32_t col = (l & 1) ? COL_R1 : COL_R0;
+        if (!mbar_wait(BAR_DFULL(l & 1), dphase[l & 1], s_abort)) { ok = false; break; }
+        dphase[l & 1] ^= 1u;
+        tc_fence_after();
+        const float* bias = (l == 0) ? nullptr : s_b[l - 1];
+#pragma unroll 1
+        for (int c = 0; c < C::NCHUNK; ++c) {
+          const int c0 = c * C::CHUNK_COLS;
+          const int ncols = (MODE == MBO_MLP_TF32) ? 40 : (c == C::NCHUNK - 1 ? 16 : 32);
+          uint32_t v[40];
+#pragma unroll
+          for (int g = 0; g < 5; ++g)
+            if (g * 8 < ncols) TMEM_LD8(tlane + col + c0 + g * 8, (&v[g * 8]));
+          tmem_wait_ld();
+          if (MODE == MBO_MLP_TF32) {
+#pragma unroll
+            for (int j = 0; j < 40; ++j) {
+              float a = __uint_as_float(v[j]);
+              if (bias) a += bias[c0 + j];
+              v[j] = __float_as_uint(tf32_rna(fmaxf(a, 0.f)));
+            }
+#pragma unroll
+            for (int g = 0; g < 5; ++g) TMEM_ST8(tlane + col + c0 + g * 8, (&v[g * 8]));
+          } else {
+            uint32_t ph[16], plo[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float a0 = 0.f, a1 = 0.f;
+              if (2 * j < ncols) {
+                a0 = __uint_as_float(v[2 * j]);
+                a1 = __uint_as_float(v[2 * j + 1]);
+                if (bias) { a0 += bias[c0 + 2 * j]; a1 += bias[c0 + 2 * j + 1]; }
+                a0 = fmaxf(a0, 0.f);
+                a1 = fmaxf(a1, 0.f);
+              }
+              __nv_bfloat16 h0 = __float2bfloat16_rn(a0), h1 = __float2bfloat16_rn(a1);
+              __nv_bfloat16 l0 = __float2bfloat16_rn(a0 - __bfloat162float(h0));
+              __nv_bfloat16 l1 = __float2bfloat16_rn(a1 - __bfloat162float(h1));
+              ph[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+              plo[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            }
+            if (ncols == 32) {
+              TMEM_ST8(tlane + col + c0, (&ph[0]));
+              TMEM_ST8(tlane + col + c0 + 8, (&ph[8]));
+              TMEM_ST8(tlane + col + c0 + 16, (&plo[0]));
+              TMEM_ST8(tlane + col + c0 + 24, (&plo[8]));
+            } else {   // last chunk: 16 K values -> 8 columns hi at +0, 8 columns lo at +8 (stays inside the region)
+              TMEM_ST8(tlane + col + c0, (&ph[0]));
+              TMEM_ST8(tlane + col + c0 + 8, (&plo[0]));
+            }
+          }
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(BAR_AREADY(c));
+        }
+        if (l == 2 && t + 1 < my_tiles) {
+          // features of the next tile while L3 runs
+          if (!mbar_wait(BAR_SFREE, sphase, s_abort)) { ok = false; break; }
+          sphase ^= 1u;
+          tc_fence_after();
+          build_features(t + 1);
+        } else if (l == 2) {
+          sphase ^= 1u;   // keep parity bookkeeping aligned with the commits (last tile: nobody waits)
+        }
+      }
+      if (!ok) break;
+      // ---- E3: logit = relu(D + b3) . w4 + b4 ----
+      if (!mbar_wait(BAR_DFULL(1), dphase[1], s_abort)) { ok = false; break; }
+      dphase[1] ^= 1u;
+      tc_fence_after();
+      float acc = 0.f;
+#pragma unroll 1
+      for (int g = 0; g < TC_N / 8; ++g) {
+        uint32_t v[8];
+        TMEM_LD8(tlane + COL_R1 + g * 8, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          acc = fmaf(fmaxf(__uint_as_float(v[j]) + s_b[2][g * 8 + j], 0.f), s_w4[g * 8 + j], acc);
+      }
+      tc_fence_before();   // order this tile's TMEM reads before the next hand-offs
+      const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+      const int b = tile / tiles_per_episode;
+      const int m = (tile - b * tiles_per_episode) * TC_M + row;
+      if (m < cand.M) logits[(size_t)b * cand.M + m] = acc + s_tail[4 * TC_N];
+    }
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tid == 0 && *s_abort) atomicExch(err_flag, 1);
+  if (warp == 4) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+static int g_num_sms = 0;
+
+template <int MODE>
+static int launch_tc(const mbo_policy* p, int B, const TcFeat& fs, const mbo_candidates& cand, const float* mean,
+                     const float* std_, const float* epi, float* logits, int* err_flag, cudaStream_t s) {
+  using SM = TcSmem<MODE>;
+  auto kern = neural_af_tc_kernel<MODE>;
+  MBO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::total));
+  if (g_num_sms == 0) {
+    int dev = 0;
+    MBO_CUDA(cudaGetDevice(&dev));
+    MBO_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int tiles_per_episode = (cand.M + TC_M - 1) / TC_M;
+  const int total = B * tiles_per_episode;
+  const int grid = total < g_num_sms ? total : g_num_sms;
+  kern<<<grid, TC_THREADS, SM::total, s>>>((const unsigned char*)p->d_tc, fs, cand, B, tiles_per_episode, mean, std_,
+                                           epi, logits, err_flag);
+  MBO_LAUNCH_CHECK();
+  return MBO_OK;
+}
+
+int tc_forward(const mbo_policy* p, int mode, int B, int F, const int32_t* feat_src, const mbo_candidates* cand,
+               const float* mean, const float* std_, const float* epi, float* logits, void* ws, size_t ws_bytes,
+               cudaStream_t s) {
+  if (!p->tc_ready) {
+    set_error("tensor-core NeuralAF path needs a F->H->H->H->H->1 ReLU policy with F <= %d and H <= %d", TC_K0 - 1, TC_N);
+    return MBO_ERR_UNSUPPORTED;
+  }
+  MBO_CHECK_ARG(ws && ws_bytes >= sizeof(int), "mbo_af_logits: tensor-core modes need a workspace of mbo_af_workspace_bytes()");
+  TcFeat fs;
+  fs.F = F;
+  for (int i = 0; i < 8; ++i) fs.src[i] = i < F ? feat_src[i] : 0;
+  int* err_flag = (int*)ws;
+  if (mode == MBO_MLP_TF32) return launch_tc<MBO_MLP_TF32>(p, B, fs, *cand, mean, std_, epi, logits, err_flag, s);
+  return launch_tc<MBO_MLP_BF16X3>(p, B, fs, *cand, mean, std_, epi, logits, err_flag, s);
+}
+
+}  // namespace mbo

