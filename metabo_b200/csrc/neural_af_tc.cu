@@ -20,18 +20,21 @@
 // Arithmetic modes (hidden layers): MBO_MLP_TF32   kind::tf32, operands rounded to tf32 (rna);
 //                                   MBO_MLP_BF16X3 kind::f16 bf16, a = a_hi + a_lo, w = w_hi + w_lo,
 //                                                  a*w ~ a_hi*w_hi + a_lo*w_hi + a_hi*w_lo.
-// Warp roles (192 threads): warps 0-3 epilogue (TMEM lanes 32*w..), warp 4 TMA producer + TMEM
-// allocation, warp 5 MMA issuer.  Every mbarrier wait is bounded (globaltimer) and raises a
+// Warp roles (320 threads): warps 0-7 epilogue (TMEM lanes 32*(w&3).., chunk parity w>>2), warp 8 TMA
+// producer + TMEM allocation, warp 9 MMA issuer.  Every mbarrier wait is bounded (globaltimer) and raises a
 // device-side error flag instead of hanging.
 #include "common.cuh"
 #include "policy.cuh"
 #include <cuda_bf16.h>
+#include <stdlib.h>
+#include "tmem_ldst.cuh"
 
 namespace mbo {
 
 constexpr int TC_N = 208;            // padded hidden width (UMMA N, multiple of 16)
 constexpr int TC_M = 128;            // candidates per tile (UMMA M)
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;        // 8 epilogue warps + TMA warp + MMA warp
+constexpr int WARP_TMA = 8, WARP_MMA = 9;
 constexpr int TC_K0 = 8;             // layer-0 K (features + ones column, <= 8)
 constexpr int CHUNK_ROW_BYTES = TC_N * 16;   // one 16-byte K chunk for all 208 rows = 3328 B
 constexpr uint32_t TMEM_COLS = 512;
@@ -152,20 +155,30 @@ __device__ __forceinline__ uint64_t make_bdesc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(CHUNK_ROW_BYTES >> 4) << 16) |
          ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
 }
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) {          // start address + LBO (low word)
+  return ((saddr & 0x3FFFFu) >> 4) | ((uint32_t)(CHUNK_ROW_BYTES >> 4) << 16);
+}
+__device__ __forceinline__ uint64_t make_desc64(uint32_t lo) {          // high word: SBO = 128 B, version 1
+  constexpr uint32_t HI = (uint32_t)(128 >> 4) | (1u << 14);
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(HI));
+  return d;
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 // cute::UMMA::InstrDescriptor: c_format f32, a/b format, K-major both, N>>3 at bit 17, M>>4 at bit 24
 __host__ __device__ constexpr uint32_t make_idesc(uint32_t ab_format) {
   return (1u << 4) | (ab_format << 7) | (ab_format << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 }
 constexpr uint32_t IDESC_TF32 = make_idesc(2), IDESC_BF16 = make_idesc(1);
 
-#define TMEM_LD8(taddr, v)                                                                              \
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                 \
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) \
-               : "r"(taddr))
-#define TMEM_ST8(taddr, v)                                                                              \
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"                 \
-               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) \
-               : "memory")
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -287,14 +300,68 @@ struct TcSmem {
   static constexpr size_t off_bars = off_tail + sizeof(float) * TAIL_FLOATS;
   static constexpr int n_bars = 2 * C::NSTAGE + C::NCHUNK + 2 + 3;   // ring, a_ready, d_full[2], feat_full, s_free, w0_full
   static constexpr size_t off_misc = off_bars + 8 * n_bars;
-  static constexpr size_t total = off_misc + 16;
+  static constexpr size_t off_part = off_misc + 16;
+  static constexpr size_t total = off_part + sizeof(float) * TC_M;
+};
+
+// per-mode conversion of one accumulator chunk into the next layer's A operand (in registers)
+template <int MODE> struct ChunkOps;
+template <> struct ChunkOps<MBO_MLP_TF32> {
+  // 40 columns: relu(acc + bias) rounded to tf32, stored in place
+  static __device__ __forceinline__ void load(uint32_t taddr, uint32_t* v, int) {
+    tmem_ld32(taddr, v);
+    tmem_ld8(taddr + 32, v + 32);
+  }
+  static __device__ __forceinline__ void convert_store(uint32_t taddr, uint32_t* v, const float* bias, int) {
+#pragma unroll
+    for (int j = 0; j < 40; ++j) {
+      float a = __uint_as_float(v[j]);
+      if (bias) a += bias[j];
+      v[j] = __float_as_uint(tf32_rna(fmaxf(a, 0.f)));
+    }
+    tmem_st32(taddr, v);
+    tmem_st8(taddr + 32, v + 32);
+  }
+};
+template <> struct ChunkOps<MBO_MLP_BF16X3> {
+  // 32 columns (16 for the last chunk) -> [hi: bf16 pairs | lo: bf16 pairs] in place
+  static __device__ __forceinline__ void load(uint32_t taddr, uint32_t* v, int ncols) {
+    if (ncols == 32) tmem_ld32(taddr, v);
+    else tmem_ld16(taddr, v);
+  }
+  static __device__ __forceinline__ void convert_store(uint32_t taddr, uint32_t* v, const float* bias, int ncols) {
+    uint32_t ph[16], plo[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float a0 = 0.f, a1 = 0.f;
+      if (2 * j < ncols) {
+        a0 = __uint_as_float(v[2 * j]);
+        a1 = __uint_as_float(v[2 * j + 1]);
+        if (bias) { a0 += bias[2 * j]; a1 += bias[2 * j + 1]; }
+        a0 = fmaxf(a0, 0.f);
+        a1 = fmaxf(a1, 0.f);
+      }
+      __nv_bfloat16 h0 = __float2bfloat16_rn(a0), h1 = __float2bfloat16_rn(a1);
+      __nv_bfloat16 l0 = __float2bfloat16_rn(a0 - __bfloat162float(h0));
+      __nv_bfloat16 l1 = __float2bfloat16_rn(a1 - __bfloat162float(h1));
+      ph[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      plo[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    if (ncols == 32) {
+      tmem_st16(taddr, ph);
+      tmem_st16(taddr + 16, plo);
+    } else {   // last chunk: 16 K values -> 8 columns hi at +0, 8 columns lo at +8 (stays inside the region)
+      tmem_st8(taddr, ph);
+      tmem_st8(taddr + 8, plo);
+    }
+  }
 };
 
 template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candidates cand, int B,
                     int tiles_per_episode, const float* __restrict__ mean, const float* __restrict__ std_,
-                    const float* __restrict__ epi, float* __restrict__ logits, int* __restrict__ err_flag) {
+                    const float* __restrict__ epi, float* __restrict__ logits, int* __restrict__ err_flag, int debug_noload) {
   using C = ModeCfg<MODE>;
   using SM = TcSmem<MODE>;
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -306,6 +373,7 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
   uint64_t* bars = (uint64_t*)(smem + SM::off_bars);
   uint32_t* s_tmem = (uint32_t*)(smem + SM::off_misc);
   volatile int* s_abort = (volatile int*)(smem + SM::off_misc + 4);
+  float* s_part = (float*)(smem + SM::off_part);          // [128] partial head sums of the upper column half
 
   const uint32_t bar0 = smem_u32(bars);
   auto BAR_WFULL = [&](int s) { return bar0 + 8u * (uint32_t)s; };
@@ -332,7 +400,7 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = tid; i < TAIL_FLOATS; i += TC_THREADS) s_tail[i] = ((const float*)(pack + pl.off_tail))[i];
-  if (warp == 4) {
+  if (warp == WARP_TMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -341,89 +409,114 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
   tc_fence_after();
   const uint32_t tmem = *s_tmem;
 
-  if (warp == 4) {
-    // ================= TMA producer =================
-    if (lane == 0 && my_tiles > 0) {
-      mbar_expect_tx(BAR_W0, W0_BYTES);
-      bulk_g2s(smem_u32(smem + SM::off_w0), pack + pl.off_w0, W0_BYTES, BAR_W0);
+  if (warp == WARP_TMA) {
+    // ================= TMA producer (warp-uniform control flow, one elected lane issues) =================
+    const bool leader = elect_one();
+    if (my_tiles > 0) {
+      if (leader) {
+        mbar_expect_tx(BAR_W0, W0_BYTES);
+        bulk_g2s(smem_u32(smem + SM::off_w0), pack + pl.off_w0, W0_BYTES, BAR_W0);
+      }
       const unsigned char* wsrc = pack + (MODE == MBO_MLP_TF32 ? pl.off_tf32 : pl.off_bf16);
-      int stage = 0;
-      uint32_t phase = 0;
+      const uint32_t ring_addr = smem_u32(ring);
+      uint32_t stage = 0, phase = 0;
       bool ok = true;
       for (int t = 0; t < my_tiles && ok; ++t) {
         for (int ls = 0; ls < 3 * C::STAGES_PER_LAYER; ++ls) {
           if (!mbar_wait(BAR_WEMPTY(stage), phase ^ 1u, s_abort)) { ok = false; break; }
-          mbar_expect_tx(BAR_WFULL(stage), C::STAGE_BYTES);
-          bulk_g2s(smem_u32(ring + (size_t)stage * C::STAGE_BYTES), wsrc + (size_t)ls * C::STAGE_BYTES, C::STAGE_BYTES,
-                   BAR_WFULL(stage));
+          if (leader) {
+            if (debug_noload && (t > 0 || ls >= C::NSTAGE)) {
+              mbar_arrive(BAR_WFULL(stage));    // timing experiment only: pretend the stage is resident
+            } else {
+              mbar_expect_tx(BAR_WFULL(stage), C::STAGE_BYTES);
+              bulk_g2s(ring_addr + stage * C::STAGE_BYTES, wsrc + (size_t)ls * C::STAGE_BYTES, C::STAGE_BYTES,
+                       BAR_WFULL(stage));
+            }
+          }
           if (++stage == C::NSTAGE) { stage = 0; phase ^= 1u; }
         }
       }
     }
-  } else if (warp == 5) {
-    // ================= MMA issuer =================
-    if (lane == 0 && my_tiles > 0) {
+  } else if (warp == WARP_MMA) {
+    // ================= MMA issuer (warp-uniform control flow, one elected lane issues) =================
+    // Everything that feeds a tcgen05.mma is a base register plus a compile-time constant: the single
+    // issuing thread must spend far fewer cycles per MMA than the ~104 the tensor pipe needs for it.
+    const bool leader = elect_one();
+    if (my_tiles > 0) {
       bool ok = mbar_wait(BAR_W0, 0, s_abort);
-      int stage = 0;
-      uint32_t wphase = 0, aphase = 0, fphase = 0;
-      const uint32_t w0_addr = smem_u32(smem + SM::off_w0);
+      uint32_t stage = 0, wphase = 0, aphase = 0, fphase = 0;
+      const uint32_t w0_lo = desc_lo(smem_u32(smem + SM::off_w0));
+      const uint32_t ring_lo = desc_lo(smem_u32(ring));
+      constexpr uint32_t STAGE_D = C::STAGE_BYTES >> 4;            // descriptor units (16 B)
+      constexpr uint32_t SLICE_D = (2 * CHUNK_ROW_BYTES) >> 4;     // one K slice = two 16-byte chunks
       for (int t = 0; t < my_tiles && ok; ++t) {
         // ---- L0: D(R0) = S * W0^T, 3xTF32 ----
         if (!mbar_wait(BAR_FEAT, fphase, s_abort)) { ok = false; break; }
         fphase ^= 1u;
         tc_fence_after();
-        {
+        if (leader) {
           const uint32_t a_hi = tmem + COL_S, a_lo = tmem + COL_S + 16;
-          const uint64_t b_hi = make_bdesc(w0_addr), b_lo = make_bdesc(w0_addr + (TC_K0 / 4) * CHUNK_ROW_BYTES);
-          mma_ts_tf32(tmem + COL_R0, a_hi, b_hi, IDESC_TF32, 0);
-          mma_ts_tf32(tmem + COL_R0, a_lo, b_hi, IDESC_TF32, 1);
-          mma_ts_tf32(tmem + COL_R0, a_hi, b_lo, IDESC_TF32, 1);
+          mma_ts_tf32(tmem + COL_R0, a_hi, make_desc64(w0_lo), IDESC_TF32, 0);
+          mma_ts_tf32(tmem + COL_R0, a_lo, make_desc64(w0_lo), IDESC_TF32, 1);
+          mma_ts_tf32(tmem + COL_R0, a_hi, make_desc64(w0_lo + SLICE_D * (TC_K0 / 8)), IDESC_TF32, 1);
           tc_commit(BAR_SFREE);
           tc_commit(BAR_DFULL(0));
         }
         // ---- L1..L3 ----
-        for (int l = 1; l <= 3 && ok; ++l) {
-          const uint32_t colA = (l & 1) ? COL_R0 : COL_R1;
-          const uint32_t colD = (l & 1) ? COL_R1 : COL_R0;
-          int slice = 0;
-          for (int c = 0; c < C::NCHUNK && ok; ++c) {
+#pragma unroll
+        for (int l = 1; l <= 3; ++l) {
+          if (!ok) break;
+          const uint32_t tA = tmem + ((l & 1) ? COL_R0 : COL_R1);
+          const uint32_t tD = tmem + ((l & 1) ? COL_R1 : COL_R0);
+#pragma unroll
+          for (int c = 0; c < C::NCHUNK; ++c) {
+            if (!ok) break;
             if (!mbar_wait(BAR_AREADY(c), aphase, s_abort)) { ok = false; break; }
-            tc_fence_after();
-            const int slices_in_chunk = (MODE == MBO_MLP_TF32) ? 5 : (c == C::NCHUNK - 1 ? 1 : 2);
-            for (int sc = 0; sc < slices_in_chunk; ++sc, ++slice) {
-              const int sis = slice % C::SLICES_PER_STAGE;
-              if (sis == 0) {
+            if (MODE == MBO_MLP_TF32) {
+              // chunk c == ring stage: 5 slices of K=8
+              if (!mbar_wait(BAR_WFULL(stage), wphase, s_abort)) { ok = false; break; }
+              tc_fence_after();
+              if (leader) {
+                const uint32_t lo = ring_lo + stage * STAGE_D;
+#pragma unroll
+                for (int sc = 0; sc < 5; ++sc)
+                  mma_ts_tf32(tD, tA + (c * 5 + sc) * 8, make_desc64(lo + sc * SLICE_D), IDESC_TF32, (c | sc) ? 1u : 0u);
+                tc_commit(BAR_WEMPTY(stage));
+              }
+              if (++stage == C::NSTAGE) { stage = 0; wphase ^= 1u; }
+            } else {
+              // chunk c holds [hi(16 cols) | lo(16 cols)] of 32 K values = 2 slices (1 in the last chunk); slice == stage
+              constexpr int LASTC = C::NCHUNK - 1;
+#pragma unroll
+              for (int sc = 0; sc < 2; ++sc) {
+                if (c == LASTC && sc == 1) break;
                 if (!mbar_wait(BAR_WFULL(stage), wphase, s_abort)) { ok = false; break; }
                 tc_fence_after();
-              }
-              const uint32_t sbase = smem_u32(ring + (size_t)stage * C::STAGE_BYTES);
-              if (MODE == MBO_MLP_TF32) {
-                const uint64_t bd = make_bdesc(sbase + sis * 2 * CHUNK_ROW_BYTES);
-                mma_ts_tf32(tmem + colD, tmem + colA + slice * 8, bd, IDESC_TF32, slice > 0 ? 1u : 0u);
-              } else {
-                // chunk c of the accumulator holds [hi(16 cols) | lo(16 cols)] of its 32 K values
-                const uint32_t a_hi = tmem + colA + (slice >> 1) * 32 + (slice & 1) * 8;
-                const uint32_t a_lo = a_hi + (slice == C::SLICES - 1 ? 8 : 16);   // the last chunk is 16 columns wide
-                const uint64_t b_hi = make_bdesc(sbase), b_lo = make_bdesc(sbase + 2 * CHUNK_ROW_BYTES);
-                mma_ts_bf16(tmem + colD, a_hi, b_hi, IDESC_BF16, slice > 0 ? 1u : 0u);
-                mma_ts_bf16(tmem + colD, a_lo, b_hi, IDESC_BF16, 1u);
-                mma_ts_bf16(tmem + colD, a_hi, b_lo, IDESC_BF16, 1u);
-              }
-              if (sis == C::SLICES_PER_STAGE - 1) {
-                tc_commit(BAR_WEMPTY(stage));
+                if (leader) {
+                  const uint32_t lo = ring_lo + stage * STAGE_D;
+                  const uint32_t a_hi = tA + c * 32 + sc * 8;
+                  const uint32_t a_lo = a_hi + (c == LASTC ? 8 : 16);
+                  mma_ts_bf16(tD, a_hi, make_desc64(lo), IDESC_BF16, (c | sc) ? 1u : 0u);
+                  mma_ts_bf16(tD, a_lo, make_desc64(lo), IDESC_BF16, 1u);
+                  mma_ts_bf16(tD, a_hi, make_desc64(lo + SLICE_D), IDESC_BF16, 1u);
+                  tc_commit(BAR_WEMPTY(stage));
+                }
                 if (++stage == C::NSTAGE) { stage = 0; wphase ^= 1u; }
               }
             }
           }
           aphase ^= 1u;
-          tc_commit(BAR_DFULL(l & 1));
+          if (leader) tc_commit(BAR_DFULL(l & 1));
         }
       }
     }
   } else {
-    // ================= epilogue warps (thread = TMEM lane = candidate row) =================
-    const int row = tid;                                    // 0..127
-    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    // ================= epilogue warps =================
+    // warp w: TMEM lanes 32*(w&3)..+31 (thread = candidate row), column half h = w>>2:
+    // half h converts chunks h, h+2, ...; half 1 also builds the next tile's features
+    const int quad = warp & 3, half = warp >> 2;
+    const int row = quad * 32 + lane;                       // 0..127
+    const uint32_t tlane = tmem + ((uint32_t)(quad * 32) << 16);
     uint32_t dphase[2] = {0, 0};
     uint32_t sphase = 0;
     bool ok = true;
@@ -431,7 +524,6 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
     const float* s_w4 = s_tail + 3 * TC_N;
 
     auto build_features = [&](int t_idx) {
-      // tile -> (episode, first candidate)
       const int tile = (int)blockIdx.x + t_idx * (int)gridDim.x;
       const int b = tile / tiles_per_episode;
       const int m = (tile - b * tiles_per_episode) * TC_M + row;
@@ -469,14 +561,15 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
         hi[i] = __float_as_uint(h);
         lo[i] = __float_as_uint(tf32_rna(f[i] - h));
       }
-      TMEM_ST8(tlane + COL_S, hi);
-      TMEM_ST8(tlane + COL_S + 16, lo);
+      tmem_st8(tlane + COL_S, hi);
+      tmem_st8(tlane + COL_S + 16, lo);
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(BAR_FEAT);
     };
 
-    if (my_tiles > 0) build_features(0);
+    if (my_tiles > 0 && half == 1) build_features(0);
+    constexpr int MAXI = (C::NCHUNK + 1) / 2;
     for (int t = 0; t < my_tiles && ok; ++t) {
       // ---- E0..E2: relu(D + b) -> next layer's A operand, in place ----
       for (int l = 0; l < 3 && ok; ++l) {
@@ -485,86 +578,65 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
         dphase[l & 1] ^= 1u;
         tc_fence_after();
         const float* bias = (l == 0) ? nullptr : s_b[l - 1];
-#pragma unroll 1
-        for (int c = 0; c < C::NCHUNK; ++c) {
-          const int c0 = c * C::CHUNK_COLS;
-          const int ncols = (MODE == MBO_MLP_TF32) ? 40 : (c == C::NCHUNK - 1 ? 16 : 32);
-          uint32_t v[40];
+        uint32_t va[40], vb[40];
+        auto ncols_of = [&](int c) { return (MODE == MBO_MLP_TF32) ? 40 : (c == C::NCHUNK - 1 ? 16 : 32); };
+        ChunkOps<MODE>::load(tlane + col + half * C::CHUNK_COLS, va, ncols_of(half));
 #pragma unroll
-          for (int g = 0; g < 5; ++g)
-            if (g * 8 < ncols) TMEM_LD8(tlane + col + c0 + g * 8, (&v[g * 8]));
-          tmem_wait_ld();
-          if (MODE == MBO_MLP_TF32) {
-#pragma unroll
-            for (int j = 0; j < 40; ++j) {
-              float a = __uint_as_float(v[j]);
-              if (bias) a += bias[c0 + j];
-              v[j] = __float_as_uint(tf32_rna(fmaxf(a, 0.f)));
-            }
-#pragma unroll
-            for (int g = 0; g < 5; ++g) TMEM_ST8(tlane + col + c0 + g * 8, (&v[g * 8]));
-          } else {
-            uint32_t ph[16], plo[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float a0 = 0.f, a1 = 0.f;
-              if (2 * j < ncols) {
-                a0 = __uint_as_float(v[2 * j]);
-                a1 = __uint_as_float(v[2 * j + 1]);
-                if (bias) { a0 += bias[c0 + 2 * j]; a1 += bias[c0 + 2 * j + 1]; }
-                a0 = fmaxf(a0, 0.f);
-                a1 = fmaxf(a1, 0.f);
-              }
-              __nv_bfloat16 h0 = __float2bfloat16_rn(a0), h1 = __float2bfloat16_rn(a1);
-              __nv_bfloat16 l0 = __float2bfloat16_rn(a0 - __bfloat162float(h0));
-              __nv_bfloat16 l1 = __float2bfloat16_rn(a1 - __bfloat162float(h1));
-              ph[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-              plo[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-            }
-            if (ncols == 32) {
-              TMEM_ST8(tlane + col + c0, (&ph[0]));
-              TMEM_ST8(tlane + col + c0 + 8, (&ph[8]));
-              TMEM_ST8(tlane + col + c0 + 16, (&plo[0]));
-              TMEM_ST8(tlane + col + c0 + 24, (&plo[8]));
-            } else {   // last chunk: 16 K values -> 8 columns hi at +0, 8 columns lo at +8 (stays inside the region)
-              TMEM_ST8(tlane + col + c0, (&ph[0]));
-              TMEM_ST8(tlane + col + c0 + 8, (&plo[0]));
-            }
+        for (int i = 0; i < MAXI; ++i) {
+          const int c = half + 2 * i;
+          if (c < C::NCHUNK) {
+            uint32_t* cur = (i & 1) ? vb : va;
+            uint32_t* nxt = (i & 1) ? va : vb;
+            tmem_wait_ld();
+            if (c + 2 < C::NCHUNK) ChunkOps<MODE>::load(tlane + col + (c + 2) * C::CHUNK_COLS, nxt, ncols_of(c + 2));
+            ChunkOps<MODE>::convert_store(tlane + col + c * C::CHUNK_COLS, cur, bias ? bias + c * C::CHUNK_COLS : nullptr,
+                                          ncols_of(c));
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(BAR_AREADY(c));
           }
-          tmem_wait_st();
-          tc_fence_before();
-          mbar_arrive(BAR_AREADY(c));
         }
-        if (l == 2 && t + 1 < my_tiles) {
-          // features of the next tile while L3 runs
-          if (!mbar_wait(BAR_SFREE, sphase, s_abort)) { ok = false; break; }
+        if (l == 2 && half == 1) {
+          if (t + 1 < my_tiles) {
+            // features of the next tile while L3 runs
+            if (!mbar_wait(BAR_SFREE, sphase, s_abort)) { ok = false; break; }
+            tc_fence_after();
+            build_features(t + 1);
+          }
           sphase ^= 1u;
-          tc_fence_after();
-          build_features(t + 1);
-        } else if (l == 2) {
-          sphase ^= 1u;   // keep parity bookkeeping aligned with the commits (last tile: nobody waits)
         }
       }
       if (!ok) break;
-      // ---- E3: logit = relu(D + b3) . w4 + b4 ----
+      // ---- E3: logit = relu(D + b3) . w4 + b4, columns split between the two halves ----
       if (!mbar_wait(BAR_DFULL(1), dphase[1], s_abort)) { ok = false; break; }
       dphase[1] ^= 1u;
       tc_fence_after();
       float acc = 0.f;
-#pragma unroll 1
-      for (int g = 0; g < TC_N / 8; ++g) {
-        uint32_t v[8];
-        TMEM_LD8(tlane + COL_R1 + g * 8, v);
+      {
+        const int cb = half * 104;
+        uint32_t v0[64], v1[40];
+        tmem_ld64(tlane + COL_R1 + cb, v0);
+        tmem_wait_ld();
+        tmem_ld32(tlane + COL_R1 + cb + 64, v1);
+        tmem_ld8(tlane + COL_R1 + cb + 96, v1 + 32);
+#pragma unroll
+        for (int j = 0; j < 64; ++j)
+          acc = fmaf(fmaxf(__uint_as_float(v0[j]) + s_b[2][cb + j], 0.f), s_w4[cb + j], acc);
         tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          acc = fmaf(fmaxf(__uint_as_float(v[j]) + s_b[2][g * 8 + j], 0.f), s_w4[g * 8 + j], acc);
+        for (int j = 0; j < 40; ++j)
+          acc = fmaf(fmaxf(__uint_as_float(v1[j]) + s_b[2][cb + 64 + j], 0.f), s_w4[cb + 64 + j], acc);
       }
       tc_fence_before();   // order this tile's TMEM reads before the next hand-offs
-      const int tile = (int)blockIdx.x + t * (int)gridDim.x;
-      const int b = tile / tiles_per_episode;
-      const int m = (tile - b * tiles_per_episode) * TC_M + row;
-      if (m < cand.M) logits[(size_t)b * cand.M + m] = acc + s_tail[4 * TC_N];
+      if (half == 1) s_part[row] = acc;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+      if (half == 0) {
+        const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+        const int b = tile / tiles_per_episode;
+        const int m = (tile - b * tiles_per_episode) * TC_M + row;
+        if (m < cand.M) logits[(size_t)b * cand.M + m] = acc + s_part[row] + s_tail[4 * TC_N];
+      }
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");   // s_part reusable
     }
   }
 
@@ -573,7 +645,7 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
   __syncthreads();
   tc_fence_after();
   if (tid == 0 && *s_abort) atomicExch(err_flag, 1);
-  if (warp == 4) {
+  if (warp == WARP_TMA) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
   }
@@ -596,7 +668,7 @@ static int launch_tc(const mbo_policy* p, int B, const TcFeat& fs, const mbo_can
   const int total = B * tiles_per_episode;
   const int grid = total < g_num_sms ? total : g_num_sms;
   kern<<<grid, TC_THREADS, SM::total, s>>>((const unsigned char*)p->d_tc, fs, cand, B, tiles_per_episode, mean, std_,
-                                           epi, logits, err_flag);
+                                           epi, logits, err_flag, getenv("MBO_TC_DEBUG_NOLOAD") ? 1 : 0);
   MBO_LAUNCH_CHECK();
   return MBO_OK;
 }
