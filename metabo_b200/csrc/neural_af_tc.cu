@@ -65,7 +65,7 @@ template <> struct ModeCfg<MBO_MLP_BF16X3> {
 };
 
 constexpr int W0_BYTES = 2 * (TC_K0 / 4) * CHUNK_ROW_BYTES;   // hi + lo: 13 312
-constexpr int TAIL_FLOATS = 4 * TC_N + 4;                    // b1 b2 b3 w4 | b4
+constexpr int TAIL_FLOATS = 5 * TC_N + 4;                    // zeros(b0 is folded into W0) b1 b2 b3 | w4 | b4
 
 // packed-weight buffer layout (bytes): [W0][tf32 hidden x3][bf16 hidden x3][tail floats]
 struct PackLayout {
@@ -245,13 +245,15 @@ __global__ void tc_pack_kernel(PackArgs a, unsigned char* __restrict__ out) {
   } else {
     size_t i = (byte - pl.off_tail) / 4;
     float v = 0.f;
-    if (i < (size_t)3 * TC_N) {
-      int l = (int)(i / TC_N) + 1, n = (int)(i % TC_N);
-      v = n < H ? a.b[l][n] : 0.f;
+    if (i < (size_t)TC_N) {
+      v = 0.f;
     } else if (i < (size_t)4 * TC_N) {
-      int n = (int)(i - 3 * TC_N);
+      int l = (int)(i / TC_N), n = (int)(i % TC_N);
+      v = n < H ? a.b[l][n] : 0.f;
+    } else if (i < (size_t)5 * TC_N) {
+      int n = (int)(i - 4 * TC_N);
       v = n < H ? a.W[4][n] : 0.f;
-    } else if (i == (size_t)4 * TC_N) {
+    } else if (i == (size_t)5 * TC_N) {
       v = a.b[4][0];
     }
     *dst = __float_as_uint(v);
@@ -313,11 +315,16 @@ template <> struct ChunkOps<MBO_MLP_TF32> {
     tmem_ld8(taddr + 32, v + 32);
   }
   static __device__ __forceinline__ void convert_store(uint32_t taddr, uint32_t* v, const float* bias, int) {
+    const float4* b4 = reinterpret_cast<const float4*>(bias);      // shared memory, 16-byte aligned
 #pragma unroll
-    for (int j = 0; j < 40; ++j) {
-      float a = __uint_as_float(v[j]);
-      if (bias) a += bias[j];
-      v[j] = __float_as_uint(tf32_rna(fmaxf(a, 0.f)));
+    for (int j = 0; j < 10; ++j) {
+      const float4 b = b4[j];
+      // relu(acc + bias), then round-to-nearest to tf32 by adding half an ulp: the tensor core ignores
+      // the low 13 mantissa bits of a kind::tf32 operand, so no masking is needed
+      v[4 * j + 0] = __float_as_uint(fmaxf(__uint_as_float(v[4 * j + 0]) + b.x, 0.f)) + 0x1000u;
+      v[4 * j + 1] = __float_as_uint(fmaxf(__uint_as_float(v[4 * j + 1]) + b.y, 0.f)) + 0x1000u;
+      v[4 * j + 2] = __float_as_uint(fmaxf(__uint_as_float(v[4 * j + 2]) + b.z, 0.f)) + 0x1000u;
+      v[4 * j + 3] = __float_as_uint(fmaxf(__uint_as_float(v[4 * j + 3]) + b.w, 0.f)) + 0x1000u;
     }
     tmem_st32(taddr, v);
     tmem_st8(taddr + 32, v + 32);
@@ -331,21 +338,21 @@ template <> struct ChunkOps<MBO_MLP_BF16X3> {
   }
   static __device__ __forceinline__ void convert_store(uint32_t taddr, uint32_t* v, const float* bias, int ncols) {
     uint32_t ph[16], plo[16];
+    const float2* b2 = reinterpret_cast<const float2*>(bias);      // shared memory, 8-byte aligned
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       float a0 = 0.f, a1 = 0.f;
       if (2 * j < ncols) {
-        a0 = __uint_as_float(v[2 * j]);
-        a1 = __uint_as_float(v[2 * j + 1]);
-        if (bias) { a0 += bias[2 * j]; a1 += bias[2 * j + 1]; }
-        a0 = fmaxf(a0, 0.f);
-        a1 = fmaxf(a1, 0.f);
+        const float2 b = b2[j];
+        a0 = fmaxf(__uint_as_float(v[2 * j]) + b.x, 0.f);
+        a1 = fmaxf(__uint_as_float(v[2 * j + 1]) + b.y, 0.f);
       }
-      __nv_bfloat16 h0 = __float2bfloat16_rn(a0), h1 = __float2bfloat16_rn(a1);
-      __nv_bfloat16 l0 = __float2bfloat16_rn(a0 - __bfloat162float(h0));
-      __nv_bfloat16 l1 = __float2bfloat16_rn(a1 - __bfloat162float(h1));
-      ph[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-      plo[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+      const __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);      // .x (low half) = element 2j
+      const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
+      const float h0 = __uint_as_float(hb << 16), h1 = __uint_as_float(hb & 0xffff0000u);
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(a0 - h0, a1 - h1);
+      ph[j] = hb;
+      plo[j] = *reinterpret_cast<const uint32_t*>(&lo);
     }
     if (ncols == 32) {
       tmem_st16(taddr, ph);
@@ -520,8 +527,7 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
     uint32_t dphase[2] = {0, 0};
     uint32_t sphase = 0;
     bool ok = true;
-    const float* s_b[3] = {s_tail, s_tail + TC_N, s_tail + 2 * TC_N};
-    const float* s_w4 = s_tail + 3 * TC_N;
+    const float* s_w4 = s_tail + 4 * TC_N;          // s_tail = [zeros | b1 | b2 | b3 | w4 | b4]
 
     auto build_features = [&](int t_idx) {
       const int tile = (int)blockIdx.x + t_idx * (int)gridDim.x;
@@ -577,7 +583,7 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
         if (!mbar_wait(BAR_DFULL(l & 1), dphase[l & 1], s_abort)) { ok = false; break; }
         dphase[l & 1] ^= 1u;
         tc_fence_after();
-        const float* bias = (l == 0) ? nullptr : s_b[l - 1];
+        const float* bias = s_tail + l * TC_N;
         uint32_t va[40], vb[40];
         auto ncols_of = [&](int c) { return (MODE == MBO_MLP_TF32) ? 40 : (c == C::NCHUNK - 1 ? 16 : 32); };
         ChunkOps<MODE>::load(tlane + col + half * C::CHUNK_COLS, va, ncols_of(half));
@@ -589,8 +595,7 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
             uint32_t* nxt = (i & 1) ? va : vb;
             tmem_wait_ld();
             if (c + 2 < C::NCHUNK) ChunkOps<MODE>::load(tlane + col + (c + 2) * C::CHUNK_COLS, nxt, ncols_of(c + 2));
-            ChunkOps<MODE>::convert_store(tlane + col + c * C::CHUNK_COLS, cur, bias ? bias + c * C::CHUNK_COLS : nullptr,
-                                          ncols_of(c));
+            ChunkOps<MODE>::convert_store(tlane + col + c * C::CHUNK_COLS, cur, bias + c * C::CHUNK_COLS, ncols_of(c));
             tmem_wait_st();
             tc_fence_before();
             mbar_arrive(BAR_AREADY(c));
@@ -619,13 +624,25 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
         tmem_wait_ld();
         tmem_ld32(tlane + COL_R1 + cb + 64, v1);
         tmem_ld8(tlane + COL_R1 + cb + 96, v1 + 32);
+        const float4* b3 = reinterpret_cast<const float4*>(s_tail + 3 * TC_N + cb);
+        const float4* w4 = reinterpret_cast<const float4*>(s_w4 + cb);
 #pragma unroll
-        for (int j = 0; j < 64; ++j)
-          acc = fmaf(fmaxf(__uint_as_float(v0[j]) + s_b[2][cb + j], 0.f), s_w4[cb + j], acc);
+        for (int j = 0; j < 16; ++j) {
+          const float4 b = b3[j], w = w4[j];
+          acc = fmaf(fmaxf(__uint_as_float(v0[4 * j + 0]) + b.x, 0.f), w.x, acc);
+          acc = fmaf(fmaxf(__uint_as_float(v0[4 * j + 1]) + b.y, 0.f), w.y, acc);
+          acc = fmaf(fmaxf(__uint_as_float(v0[4 * j + 2]) + b.z, 0.f), w.z, acc);
+          acc = fmaf(fmaxf(__uint_as_float(v0[4 * j + 3]) + b.w, 0.f), w.w, acc);
+        }
         tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 40; ++j)
-          acc = fmaf(fmaxf(__uint_as_float(v1[j]) + s_b[2][cb + 64 + j], 0.f), s_w4[cb + 64 + j], acc);
+        for (int j = 0; j < 10; ++j) {
+          const float4 b = b3[16 + j], w = w4[16 + j];
+          acc = fmaf(fmaxf(__uint_as_float(v1[4 * j + 0]) + b.x, 0.f), w.x, acc);
+          acc = fmaf(fmaxf(__uint_as_float(v1[4 * j + 1]) + b.y, 0.f), w.y, acc);
+          acc = fmaf(fmaxf(__uint_as_float(v1[4 * j + 2]) + b.z, 0.f), w.z, acc);
+          acc = fmaf(fmaxf(__uint_as_float(v1[4 * j + 3]) + b.w, 0.f), w.w, acc);
+        }
       }
       tc_fence_before();   // order this tile's TMEM reads before the next hand-offs
       if (half == 1) s_part[row] = acc;
@@ -634,7 +651,7 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
         const int tile = (int)blockIdx.x + t * (int)gridDim.x;
         const int b = tile / tiles_per_episode;
         const int m = (tile - b * tiles_per_episode) * TC_M + row;
-        if (m < cand.M) logits[(size_t)b * cand.M + m] = acc + s_part[row] + s_tail[4 * TC_N];
+        if (m < cand.M) logits[(size_t)b * cand.M + m] = acc + s_part[row] + s_tail[5 * TC_N];
       }
       asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");   // s_part reusable
     }
