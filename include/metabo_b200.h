@@ -144,6 +144,14 @@ int mbo_af_logits(const mbo_policy* p, int mode, int B, int F, const int32_t* fe
                   void* stream);
 size_t mbo_af_workspace_bytes(int mode, int B, int M);
 
+/* Same network on an already materialised state tensor (NeuralAF.forward on arbitrary input,
+ * policies.py:104-115; the PPO update re-evaluates stored states, ppo.py:148):
+ *   states [B, M, F_state] fp32, cols[F] = state column feeding policy input i (the boolean
+ *   feature mask of policies.py:109-113 expressed as indices) -> logits [B, M] fp32. */
+int mbo_af_logits_dense(const mbo_policy* p, int mode, int B, int M, int F_state, int F,
+                        const int32_t* cols, const float* states, float* logits, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
 /* value network on (t, T) of row 0 (policies.py:117-121): tT [B,2] fp32 -> values [B] */
 int mbo_value_net(const mbo_policy* value_net, int B, const float* tT, float* values, void* stream);
 

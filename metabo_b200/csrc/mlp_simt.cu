@@ -22,7 +22,9 @@ struct SimtNet {
 
 struct FeatSpec {
   int F;
-  int src[MBO_MAX_FEATURES];
+  int src[MBO_MAX_FEATURES];   // MBO_FEAT_* codes, or state-column indices in dense mode
+  const float* dense;          // [B, M, dense_F] materialised states, or nullptr
+  int dense_F;
 };
 
 __device__ __forceinline__ float act_fn(int a, float v) { return a == MBO_ACT_RELU ? fmaxf(v, 0.f) : tanhf(v); }
@@ -61,7 +63,7 @@ mlp_simt_kernel(SimtNet net, FeatSpec fs, mbo_candidates cand, int tiles_per_epi
 #pragma unroll
       for (int d = 0; d < MBO_MAX_D; ++d) x[d] = 0.0;
       float mu = 0.f, sd = 0.f;
-      if (c < rows_valid) {
+      if (c < rows_valid && !fs.dense) {
         load_candidate(cand, b, row0 + c, x);
         mu = mean[(size_t)b * cand.M + row0 + c];
         sd = std_[(size_t)b * cand.M + row0 + c];
@@ -69,7 +71,8 @@ mlp_simt_kernel(SimtNet net, FeatSpec fs, mbo_candidates cand, int tiles_per_epi
       for (int f = 0; f < F; ++f) {
         int s = fs.src[f];
         float v;
-        if (s == MBO_FEAT_MEAN) v = mu;
+        if (fs.dense) v = c < rows_valid ? fs.dense[((size_t)b * cand.M + row0 + c) * fs.dense_F + s] : 0.f;
+        else if (s == MBO_FEAT_MEAN) v = mu;
         else if (s == MBO_FEAT_STD) v = sd;
         else if (s >= MBO_FEAT_X0 && s < MBO_FEAT_X0 + MBO_MAX_D) {
           v = 0.f;
@@ -145,7 +148,7 @@ mlp_simt_kernel(SimtNet net, FeatSpec fs, mbo_candidates cand, int tiles_per_epi
 
 int simt_forward(const mbo_policy* p, int B, int F, const int32_t* feat_src, const mbo_candidates* cand,
                  const float* mean, const float* std_, const float* epi, const float* direct, int R,
-                 float* out, cudaStream_t s) {
+                 float* out, cudaStream_t s, const float* dense = nullptr, int dense_F = 0) {
   SimtNet net;
   net.n_layers = p->n_layers;
   net.activation = p->activation;
@@ -154,6 +157,8 @@ int simt_forward(const mbo_policy* p, int B, int F, const int32_t* feat_src, con
   for (int l = 0; l < p->n_layers; ++l) { net.Wt[l] = p->d_Wt[l]; net.b[l] = p->d_b[l]; }
   FeatSpec fs;
   fs.F = F;
+  fs.dense = dense;
+  fs.dense_F = dense_F;
   mbo_candidates c0;
   memset(&c0, 0, sizeof(c0));
   int grid, tiles = 1;
@@ -174,7 +179,7 @@ int simt_forward(const mbo_policy* p, int B, int F, const int32_t* feat_src, con
 
 int tc_forward(const mbo_policy* p, int mode, int B, int F, const int32_t* feat_src, const mbo_candidates* cand,
                const float* mean, const float* std_, const float* epi, float* logits, void* ws, size_t ws_bytes,
-               cudaStream_t s);   // neural_af_tc.cu
+               cudaStream_t s, const float* dense = nullptr, int dense_F = 0);   // neural_af_tc.cu
 
 }  // namespace mbo
 
@@ -207,6 +212,27 @@ extern "C" int mbo_af_logits(const mbo_policy* p, int mode, int B, int F, const 
     return tc_forward(p, mode, B, F, feat_src, cand, mean, std_, epi, logits, workspace, workspace_bytes,
                       (cudaStream_t)stream);
   set_error("mbo_af_logits: unknown mode %d", mode);
+  return MBO_ERR_ARG;
+}
+
+extern "C" int mbo_af_logits_dense(const mbo_policy* p, int mode, int B, int M, int F_state, int F,
+                                   const int32_t* cols, const float* states, float* logits, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  MBO_CHECK_ARG(p && p->n_layers > 0, "mbo_af_logits_dense: policy has no weights");
+  MBO_CHECK_ARG(B > 0 && M > 0 && states && logits && cols, "mbo_af_logits_dense: bad argument");
+  MBO_CHECK_ARG(F == p->widths[0] && F <= MBO_MAX_FEATURES, "mbo_af_logits_dense: F=%d does not match the policy input width %d", F, p->widths[0]);
+  MBO_CHECK_ARG(p->widths[p->n_layers] == 1, "mbo_af_logits_dense: policy head must have one output");
+  for (int f = 0; f < F; ++f) MBO_CHECK_ARG(cols[f] >= 0 && cols[f] < F_state, "mbo_af_logits_dense: column index out of range");
+  mbo_candidates c;
+  memset(&c, 0, sizeof(c));
+  c.M = M;
+  c.D = 1;
+  if (mode == MBO_MLP_FP32)
+    return simt_forward(p, B, F, cols, &c, nullptr, nullptr, nullptr, nullptr, 0, logits, (cudaStream_t)stream, states, F_state);
+  if (mode == MBO_MLP_TF32 || mode == MBO_MLP_BF16X3)
+    return tc_forward(p, mode, B, F, cols, &c, nullptr, nullptr, nullptr, logits, workspace, workspace_bytes,
+                      (cudaStream_t)stream, states, F_state);
+  set_error("mbo_af_logits_dense: unknown mode %d", mode);
   return MBO_ERR_ARG;
 }
 

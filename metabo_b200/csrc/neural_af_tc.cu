@@ -290,7 +290,9 @@ int tc_pack_weights(mbo_policy* p, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------
 struct TcFeat {
   int F;
-  int src[8];
+  int src[8];          // MBO_FEAT_* codes, or state-column indices in dense mode
+  const float* dense;  // [B, M, dense_F] materialised states, or nullptr
+  int dense_F;
 };
 
 template <int MODE>
@@ -536,7 +538,14 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
       float f[TC_K0];
 #pragma unroll
       for (int i = 0; i < TC_K0; ++i) f[i] = 0.f;
-      if (m < cand.M) {
+      if (m < cand.M && fs.dense) {
+        const float* srow = fs.dense + ((size_t)b * cand.M + m) * fs.dense_F;
+#pragma unroll
+        for (int i = 0; i < TC_K0 - 1; ++i)
+          if (i < fs.F) f[i] = srow[fs.src[i]];
+#pragma unroll
+        for (int i = 0; i < TC_K0; ++i) if (i == fs.F) f[i] = 1.0f;    // bias column
+      } else if (m < cand.M) {
         double x[MBO_MAX_D];
 #pragma unroll
         for (int d = 0; d < MBO_MAX_D; ++d) x[d] = 0.0;
@@ -692,7 +701,7 @@ static int launch_tc(const mbo_policy* p, int B, const TcFeat& fs, const mbo_can
 
 int tc_forward(const mbo_policy* p, int mode, int B, int F, const int32_t* feat_src, const mbo_candidates* cand,
                const float* mean, const float* std_, const float* epi, float* logits, void* ws, size_t ws_bytes,
-               cudaStream_t s) {
+               cudaStream_t s, const float* dense, int dense_F) {
   if (!p->tc_ready) {
     set_error("tensor-core NeuralAF path needs a F->H->H->H->H->1 ReLU policy with F <= %d and H <= %d", TC_K0 - 1, TC_N);
     return MBO_ERR_UNSUPPORTED;
@@ -700,6 +709,8 @@ int tc_forward(const mbo_policy* p, int mode, int B, int F, const int32_t* feat_
   MBO_CHECK_ARG(ws && ws_bytes >= sizeof(int), "mbo_af_logits: tensor-core modes need a workspace of mbo_af_workspace_bytes()");
   TcFeat fs;
   fs.F = F;
+  fs.dense = dense;
+  fs.dense_F = dense_F;
   for (int i = 0; i < 8; ++i) fs.src[i] = i < F ? feat_src[i] : 0;
   int* err_flag = (int*)ws;
   if (mode == MBO_MLP_TF32) return launch_tc<MBO_MLP_TF32>(p, B, fs, *cand, mean, std_, epi, logits, err_flag, s);

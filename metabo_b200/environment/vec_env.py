@@ -1,0 +1,170 @@
+"""VecMetaBO: B MetaBO episodes in lock-step, resident on one GPU.
+
+This is the data-parallel axis of the reference (`n_workers` forked EnvRunner processes, one BO
+episode each, metabo/ppo/batchrecorder.py:199-225) turned into a batch dimension: lane b owns the
+RNG stream `RandomState(lane_seeds[b])` exactly like `MetaBO.seed` (metabo_gym.py:162-166) and its
+episodes are the ones the reference worker with that seed would play.
+
+Per episode step (MetaBO.step, metabo_gym.py:195-217) for all lanes at once:
+    x = xi_t[action] -> y = f(x) (device) -> append (add_data :595-608) -> reward (:679-704)
+    -> GP refit + AF-optimisation round (AFEngine.af_round) -> next state / logits.
+The AF round whose state is never acted on (after the T-th step, metabo_gym.py:211-214) is skipped.
+Only fixed horizons (T_min == T_max) are supported in lock-step mode.
+"""
+import numpy as np
+import torch
+
+from .. import _lib as L
+from ..engine import AFEngine
+from ..sobol import i4_sobol_generate
+from .functions import FunctionSampler
+
+
+class VecMetaBO:
+    def __init__(self, B, lane_seeds, gp_precision="fp64", mlp_mode="bf16x3", device=None, lane_rngs=None,
+                 **kwargs):
+        self.kwargs = kwargs
+        self.B = B
+        self.D = kwargs["D"]
+        if "T" in kwargs:
+            self.T = kwargs["T"]
+        else:
+            if kwargs["T_min"] != kwargs["T_max"]:
+                raise NotImplementedError("VecMetaBO runs lanes in lock-step: T_min must equal T_max")
+            self.T = kwargs["T_min"]
+        if kwargs.get("n_init_samples", 0) != 0:
+            raise NotImplementedError("n_init_samples > 0 is only used by the EI/Random baselines")
+        self.features = kwargs["features"]
+        self.reward_transformation = kwargs["reward_transformation"]
+        if self.reward_transformation not in ("none", "neg_linear", "neg_log10"):
+            raise ValueError("Unknown reward transformation!")
+        self.f_type, self.f_opts = kwargs["f_type"], kwargs["f_opts"]
+        self.kernel = kwargs.get("kernel", "RBF")
+        if self.kernel not in L.KERNEL_IDS:
+            raise ValueError("Unknown kernel function for GP model!")
+        self.use_prior_mean_function = bool(kwargs.get("use_prior_mean_function", False))
+        self.do_local_af_opt = kwargs["local_af_opt"]
+        if lane_rngs is not None:
+            # several lanes may share one RandomState (the sequential episodes of one reference worker)
+            assert len(lane_rngs) == B
+            self.rngs = list(lane_rngs)
+        else:
+            assert len(lane_seeds) == B
+            self.rngs = []
+            for s in lane_seeds:
+                r = np.random.RandomState()
+                r.seed(int(s))
+                self.rngs.append(r)
+        gp_prec = {"fp64": L.GP_FP64, "fp32": L.GP_FP32}[gp_precision]
+        mode = {"fp32": L.MLP_FP32, "tf32": L.MLP_TF32, "bf16x3": L.MLP_BF16X3}[mlp_mode]
+        common = dict(kernel=self.kernel, use_prior_mean=self.use_prior_mean_function, gp_precision=gp_prec,
+                      mlp_mode=mode, device=device, T_training=kwargs.get("T_training"))
+        if self.do_local_af_opt:
+            self.engine = AFEngine(B, self.D, self.T, self.features, N_MS=kwargs["N_MS"], N_LS=kwargs["N_LS"],
+                                   k=kwargs["k"], local_search_grid=i4_sobol_generate(self.D, kwargs["N_LS"]),
+                                   **common)
+            grid = None
+        else:
+            grid_np = i4_sobol_generate(self.D, kwargs["cardinality_domain"])
+            self.engine = AFEngine(B, self.D, self.T, self.features, discrete_domain=grid_np, **common)
+            grid = self.engine.xi_table
+        self.dev = self.engine.dev
+        self.cardinality_xi_t = self.engine.M_final
+        self.n_features = self.engine.n_features
+        self.sampler = FunctionSampler(self.f_type, self.f_opts, self.D, self.dev, discrete_grid=grid)
+        self.fixed_hyper = (kwargs.get("kernel_lengthscale"), kwargs.get("kernel_variance"), kwargs.get("noise_variance"))
+        self.policy = None
+        self.t = 0
+        self.fb = None
+        self.cur = None          # output of the AF round that produced the current state
+        self.sample_seed = 0
+        self.round_counter = 0
+
+    # -- policy ----------------------------------------------------------------------------------
+    def set_policy(self, pi):
+        """Bind a NeuralAF: its weights feed the engine's kernels (replaces set_af_functions +
+        the per-step numpy callback of metabo_gym.py:168-174, 708, 718)."""
+        self.policy = pi
+        self.engine.codes_policy = [c for c, m in zip(self.engine.codes_all, pi.policy_mask()) if m]
+        self.sync_policy()
+
+    def sync_policy(self):
+        pi = self.policy
+        dev = self.dev
+        self.engine.set_policy([l.weight.detach().to(dev) for l in pi.policy_net.fc],
+                               [l.bias.detach().to(dev) for l in pi.policy_net.fc], pi.activation)
+        if pi.use_value_network:
+            self.engine.set_value_net([l.weight.detach().to(dev) for l in pi.value_net.fc],
+                                      [l.bias.detach().to(dev) for l in pi.value_net.fc], pi.activation)
+        if not pi.tensor_core_ok():
+            self.engine.mlp_mode = L.MLP_FP32
+
+    # -- episode control -------------------------------------------------------------------------
+    def reset(self, deterministic=True):
+        """New objective per lane, empty GP, AF round on the empty GP (MetaBO.reset, :176-193)."""
+        eng = self.engine
+        self.t = 0
+        self.fb, hyper = self.sampler.draw(self.rngs)
+        if hyper is not None:
+            eng.set_hyperparameters(np.repeat(hyper[0][:, None], self.D, axis=1), hyper[1], hyper[2])
+        else:
+            eng.set_hyperparameters(self.fixed_hyper[0], self.fixed_hyper[1], self.fixed_hyper[2])
+        eng.n.zero_()
+        eng.n_active_max = 0
+        self.best = torch.full((self.B,), -float("inf"), dtype=torch.float64, device=self.dev)
+        self._round(deterministic)
+
+    def _round(self, deterministic):
+        eng = self.engine
+        inc = torch.where(torch.isinf(self.best), self.fb.y_min, self.best)      # metabo_gym.py:723-730
+        eng.set_episode_scalars(inc.float(), torch.full((self.B,), float(self.t), device=self.dev),
+                                torch.full((self.B,), float(self.T), device=self.dev))
+        self.cur = eng.af_round(deterministic=deterministic, seed=self.sample_seed, step=self.round_counter,
+                                want_stats=False)
+        self.round_counter += 1
+
+    def values(self):
+        """value net on (t, T) (policies.py:117-121) for the current state of every lane."""
+        if self.engine.value is None:
+            return torch.zeros(self.B, device=self.dev)
+        from .. import ops
+        cols = []
+        for idx in (self.policy.t_idx, self.policy.T_idx):       # state columns the value net reads (row 0)
+            code = self.engine.codes_all[idx]
+            if not (L.FEAT_INCUMBENT <= code <= L.FEAT_BUDGET):
+                raise NotImplementedError("value net inputs must be per-episode scalar features")
+            cols.append(code - L.FEAT_INCUMBENT)
+        return ops.value_net(self.engine.value, self.engine.epi[:, cols].contiguous())
+
+    def current_state(self):
+        """state [B, M, F] fp32 as get_state packs it (materialised on demand)."""
+        return self.engine.state_tensor(self.cur["cand"], self.cur["mean"], self.cur["std"])
+
+    def step(self, deterministic=True, advance=True, actions=None):
+        """Apply the action chosen by the last AF round (or `actions` [B] int32, indices into xi_t).
+        Returns (reward [B] f64, done bool)."""
+        eng = self.engine
+        if actions is None:
+            x = self.cur["x_action"]                              # [B, D] fp64
+        else:
+            from .. import ops
+            a = torch.as_tensor(actions, dtype=torch.int32, device=self.dev).reshape(self.B, 1).contiguous()
+            x = ops.candidates_gather(self.cur["cand"], a, self.B)[:, 0]
+        y = self.fb.eval(x)
+        eng.X[:, self.t] = x
+        eng.Y[:, self.t] = y
+        self.t += 1
+        eng.n.fill_(self.t)
+        eng.n_active_max = self.t
+        self.best = torch.maximum(self.best, y)
+        regret = self.fb.y_max - self.best                        # min(y_max - Y)
+        if self.reward_transformation == "none":
+            reward = regret
+        elif self.reward_transformation == "neg_linear":
+            reward = -regret
+        else:
+            reward = -torch.log10(torch.clamp(regret, min=1e-20))
+        done = self.t == self.T
+        if not done and advance:
+            self._round(deterministic)
+        return reward, done

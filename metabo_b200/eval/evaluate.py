@@ -1,0 +1,68 @@
+"""eval_experiment drop-in for the MetaBO policy (metabo/eval/evaluate.py:59-167): loads a trained
+NeuralAF from the reference's checkpoint files (params_N / weights_N / stats_N, shipped iclr2020
+runs included), plays T * n_episodes steps through the GPU BatchRecorder and stores the same
+`Result` pickle.  The baseline AFs (EI, TAF, ...) are outside the hot path and raise."""
+import os
+import pickle as pkl
+from collections import namedtuple
+from datetime import datetime
+
+import numpy as np
+import torch
+
+from .. import gym_compat as gym
+from ..policies.policies import NeuralAF
+from ..ppo.batchrecorder import BatchRecorder
+
+Result = namedtuple("Result",
+                    "logpath env_id env_specs policy policy_specs deterministic load_iter T n_episodes rewards")
+
+
+def load_metabo_policy(logpath, load_iter, env, device, deterministic):
+    with open(os.path.join(logpath, "params_" + str(load_iter)), "rb") as f:
+        train_params = pkl.load(f)
+    pi = NeuralAF(observation_space=env.observation_space, action_space=env.action_space,
+                  deterministic=deterministic, options=train_params["policy_options"])
+    with open(os.path.join(logpath, "weights_" + str(load_iter)), "rb") as f:
+        pi.load_state_dict(torch.load(f, map_location="cpu", weights_only=False))
+    with open(os.path.join(logpath, "stats_" + str(load_iter)), "rb") as f:
+        stats = pkl.load(f)
+    return pi, train_params, stats
+
+
+def eval_experiment(eval_spec):
+    env_id = eval_spec["env_id"]
+    policy = eval_spec["policy"]
+    if policy != "MetaBO":
+        raise ValueError("Unknown policy!" if policy not in ("GP-UCB", "EI", "TAF-ME", "TAF-RANKING", "PI",
+                                                              "EPS-GREEDY", "GMM-UCB", "Random")
+                         else "baseline AF '%s' is outside the GPU hot path" % policy)
+    logpath, savepath = eval_spec["logpath"], eval_spec["savepath"]
+    n_workers, n_episodes, T = eval_spec["n_workers"], eval_spec["n_episodes"], eval_spec["T"]
+    assert n_episodes % n_workers == 0
+    load_iter, deterministic = eval_spec["load_iter"], eval_spec["deterministic"]
+    os.makedirs(savepath, exist_ok=True)
+    env_seeds = eval_spec["env_seed_offset"] + np.arange(n_workers)
+    env_specs = gym.registry.env_specs[env_id]._kwargs
+    with open(os.path.join(logpath, "params_" + str(load_iter)), "rb") as f:
+        policy_specs = pkl.load(f)
+
+    def policy_fn(osp, asp, det):
+        return NeuralAF(observation_space=osp, action_space=asp, deterministic=det,
+                        options=policy_specs["policy_options"])
+
+    br = BatchRecorder(size=T * n_episodes, env_id=env_id, env_seeds=list(env_seeds), policy_fn=policy_fn,
+                       n_workers=n_workers, deterministic=deterministic, store_states=False)
+    pi, _, _ = load_metabo_policy(logpath, load_iter, br, "cpu", deterministic)
+    br.set_worker_weights(pi=pi)
+    br.record_batch(gamma=1.0, lam=1.0)
+    rewards = tuple(t.reward for t in br.memory)
+    br.cleanup()
+    with open(os.path.join(savepath, "000_eval_overview_{}.txt".format(policy)), "w") as f:
+        print("Evaluation timestamp: {}\nEnvironment-ID: {}\nEnvironment-seeds:\n{}".format(
+            datetime.strftime(datetime.now(), "%Y-%m-%d-%H-%M-%S"), env_id, env_seeds), file=f)
+    result = Result(logpath=logpath, env_id=env_id, env_specs=env_specs, policy=policy, policy_specs=policy_specs,
+                    deterministic=deterministic, load_iter=load_iter, T=T, n_episodes=n_episodes, rewards=rewards)
+    with open(os.path.join(savepath, "result_metabo_iter_{:04d}".format(load_iter)), "wb") as f:
+        pkl.dump(result, f)
+    return result

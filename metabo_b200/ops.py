@@ -156,6 +156,20 @@ def af_logits(policy, feat_src, cand, mean, std, epi, B, mode=L.MLP_FP32, logits
     return logits
 
 
+def af_logits_dense(policy, cols, states, mode=L.MLP_FP32, logits=None):
+    """NeuralAF.forward (policy net) on materialised states [B,M,F_state] fp32 -> logits [B,M]."""
+    _chk(states, torch.float32, "states")
+    B, M, Fs = states.shape
+    if logits is None:
+        logits = torch.empty((B, M), dtype=torch.float32, device=states.device)
+    F = len(cols)
+    cc = (C.c_int32 * F)(*cols)
+    ws = policy.workspace(states.device) if mode != L.MLP_FP32 else None
+    L.check(L.lib().mbo_af_logits_dense(policy.h, mode, B, M, Fs, F, cc, _p(states), _p(logits), _p(ws),
+                                        0 if ws is None else ws.numel() * 4, _stream()), "mbo_af_logits_dense")
+    return logits
+
+
 def value_net(policy, tT):
     _chk(tT, torch.float32, "tT")
     out = torch.empty((tT.shape[0],), dtype=torch.float32, device=tT.device)

@@ -1,0 +1,274 @@
+"""PPO drop-in (metabo/ppo/ppo.py:43-264): same constructor, params keys, loss, update schedule,
+log / checkpoint files; rollouts come from the GPU-resident BatchRecorder and minibatches stay on
+the device.  Under torch.distributed (one process per GPU, NCCL over NVLink) the rollout lanes and
+every minibatch are sharded across ranks and the policy update all-reduces
+
+  * the flat fp32 gradient (sum; the loss of each rank is already divided by the GLOBAL minibatch
+    size, so the reduced gradient equals the single-process gradient on the concatenated minibatch),
+  * (sum, sum of squares, count) of the advantages, so the per-minibatch advantage normalisation of
+    ppo.py:141-144 is the global one,
+
+and every rank applies the identical Adam step (weights stay replicated, no broadcast).
+"""
+import collections
+import copy
+import json
+import os
+import pickle as pkl
+import random
+import time
+from datetime import datetime
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.optim
+
+from .. import gym_compat as gym
+from .batchrecorder import BatchRecorder
+
+
+def dist_ctx():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def normalize_advantages(advs, world=1):
+    """(advs - mean) / std with the biased std over the GLOBAL minibatch (ppo.py:141-144)."""
+    s = torch.stack([advs.sum(), (advs * advs).sum(), torch.tensor(float(advs.numel()), device=advs.device,
+                                                                   dtype=advs.dtype)]).double()
+    if world > 1:
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+    n = s[2]
+    mean = s[0] / n
+    var = torch.clamp(s[1] / n - mean * mean, min=0.0)
+    std = torch.sqrt(var)
+    if std == 0 or torch.isnan(std):
+        return advs
+    return ((advs.double() - mean) / std).to(advs.dtype)
+
+
+def ppo_minibatch_loss(pi, states, actions, advs, tdlamrets, logprobs_old, params, n_global):
+    """Loss terms of one (local shard of a) minibatch, each already divided by the global minibatch
+    size n_global so that summing gradients over ranks gives the reference's mean-reduced loss
+    (ppo.py:148-168)."""
+    vpreds, logprobs, entropies = pi.predict_vals_logps_ents(states=states, actions=actions)
+    assert logprobs_old.dim() == vpreds.dim() == logprobs.dim() == entropies.dim() == 1
+    ratios = torch.exp(logprobs - logprobs_old)
+    clipped = ratios.clamp(1 - params["epsilon"], 1 + params["epsilon"])
+    loss_ppo = -torch.sum(torch.min(ratios * advs, clipped * advs)) / n_global
+    loss_value = torch.sum((vpreds - tdlamrets) ** 2) / n_global
+    loss_ent = -torch.sum(entropies) / n_global
+    loss = loss_ppo + params["value_coeff"] * loss_value + params["ent_coeff"] * loss_ent
+    return loss, loss_ppo, loss_value, loss_ent
+
+
+def allreduce_gradients(parameters, world):
+    """one flat fp32 all-reduce (sum) per optimiser step (~0.97 MB for the 4x200 nets)"""
+    if world == 1:
+        return
+    grads = [p.grad for p in parameters if p.grad is not None]
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
+
+
+class PPO:
+    def __init__(self, policy_fn, params, logpath, save_interval, verbose=False):
+        self.params = params
+        self.rank, self.world = dist_ctx()
+        self.env_spec = gym.registry.env_specs[self.params["env_id"]]
+        self.set_all_seeds()
+
+        self.logpath = logpath
+        if self.rank == 0:
+            try:
+                os.makedirs(logpath, exist_ok=False)
+            except FileExistsError:
+                raise ValueError("Logpath is not empty!")
+        self.save_interval = save_interval
+        self.verbose = verbose
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("metabo_b200.ppo needs a CUDA device (no CPU fallback)")
+        self.device = torch.device("cuda", torch.cuda.current_device())
+
+        # rollout lanes: workers are sharded contiguously over ranks, seeds keep their meaning
+        nw, bs = self.params["n_workers"], self.params["batch_size"]
+        if nw % self.world or bs % self.world or self.params["minibatch_size"] % self.world:
+            raise ValueError("n_workers, batch_size and minibatch_size must be divisible by the number of ranks")
+        lw = nw // self.world
+        seeds = list(self.params["env_seeds"])[self.rank * lw:(self.rank + 1) * lw]
+        self.batch_recorder = BatchRecorder(size=bs // self.world, env_id=self.params["env_id"], env_seeds=seeds,
+                                            policy_fn=policy_fn, n_workers=lw, device=self.device,
+                                            mlp_mode=self.params.get("mlp_mode"))
+        osp, asp = self.batch_recorder.observation_space, self.batch_recorder.action_space
+        self.pi = policy_fn(osp, asp, False).to(self.device)
+        self.old_pi = policy_fn(osp, asp, False).to(self.device)
+        if self.world > 1:   # identical initial weights on every rank
+            for p in self.pi.parameters():
+                dist.broadcast(p.data, src=0)
+        self.optimizer = torch.optim.Adam(self.pi.parameters(), lr=self.params["lr"])
+
+        self.stats = dict()
+        self.stats["n_timesteps"] = 0
+        self.stats["n_optsteps"] = 0
+        self.stats["n_iters"] = 0
+        self.stats["t_train"] = 0
+        self.stats["avg_step_rews"] = np.array([])
+        self.stats["avg_init_rews"] = np.array([])
+        self.stats["avg_term_rews"] = np.array([])
+        self.stats["avg_ep_rews"] = np.array([])
+        self.t_batch = None
+        self.rew_buffer = collections.deque(maxlen=50)
+        if self.rank == 0:
+            self.write_overview_logfile()
+
+    def set_all_seeds(self):
+        np.random.seed(self.params["seed"])
+        random.seed(self.params["seed"])
+        torch.manual_seed(self.params["seed"])
+        torch.cuda.manual_seed_all(self.params["seed"])
+
+    def write_overview_logfile(self):
+        s = ""
+        s += "********* OVERVIEW OF RUN *********\n"
+        s += "Logpath        : {}\n".format(self.logpath)
+        s += "Logfile created: {}\n".format(datetime.strftime(datetime.now(), "%Y-%m-%d-%H-%M-%S"))
+        s += "Environment-ID:  {}\n".format(self.params["env_id"])
+        s += "Environment-kwargs:\n"
+        s += json.dumps(self.env_spec._kwargs, indent=2)
+        s += "\n"
+        s += "PPO-parameters:\n"
+        s += json.dumps(self.params, indent=2)
+        s += "\n"
+        s += "Batchrecorder:\n"
+        s += json.dumps(self.batch_recorder.overview_dict(), indent=2)
+        with open(os.path.join(self.logpath, "000_overview.txt"), "w") as f:
+            print(s, file=f)
+        if not self.verbose:
+            print(s)
+
+    def optimize_on_batch(self):
+        now = time.time()
+        self.iter_log_str += " OPTIMIZING...\n"
+        self.old_pi.load_state_dict(self.pi.state_dict())
+        self.old_pi.set_requires_grad(False)
+        local_mb = self.params["minibatch_size"] // self.world
+        for ep in range(self.params["n_epochs"]):
+            sums = torch.zeros(4, device=self.device)
+            n_minibatches = 0
+            for mb in self.batch_recorder.iterate_device(local_mb, shuffle=True):
+                states, actions = mb["states"], mb["actions"]
+                tdlamrets = mb["tdlamrets"]
+                advs = mb["advs"] if self.params["loss_type"] == "GAElam" else mb["tdlamrets"]
+                n_global = states.shape[0] * self.world
+                if self.params["normalize_advs"]:
+                    advs = normalize_advantages(advs, self.world)
+                with torch.no_grad():
+                    _, logprobs_old, _ = self.old_pi.predict_vals_logps_ents(states=states, actions=actions)
+                loss, l_ppo, l_val, l_ent = ppo_minibatch_loss(self.pi, states, actions, advs, tdlamrets, logprobs_old,
+                                                               self.params, n_global)
+                self.optimizer.zero_grad()
+                loss.backward()
+                allreduce_gradients(list(self.pi.parameters()), self.world)
+                self.optimizer.step()
+                self.stats["n_optsteps"] += 1
+                with torch.no_grad():
+                    sums += torch.stack([l_ppo, l_val, l_ent, loss]).detach()
+                n_minibatches += 1
+            if self.world > 1:
+                dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+            avg = (sums / n_minibatches).tolist()
+            self.iter_log_str += "   loss_ppo = {: .4g}, loss_value = {: .4g}, loss_ent = {: .4g}, loss = {: .4g}\n".format(*avg)
+        torch.cuda.synchronize(self.device)
+        t_optim = time.time() - now
+        self.iter_log_str += "  Took {:.2f}s".format(t_optim)
+        return t_optim
+
+    def _global_batch_stats(self, bs):
+        """sum the per-rank batch statistics (each rank recorded batch_size / world steps)"""
+        if self.world == 1:
+            return bs
+        br = self.batch_recorder
+        v = torch.tensor([br.reward_sum, float(len(br)), float(br.n_new), float(np.sum(br.initial_rewards)),
+                          float(np.sum(br.terminal_rewards))], dtype=torch.float64, device=self.device)
+        dist.all_reduce(v, op=dist.ReduceOp.SUM)
+        rs, n, nn, si, st = v.tolist()
+        bs = dict(bs)
+        bs.update(size=int(n), avg_step_reward=rs / n, avg_initial_reward=si / nn, avg_terminal_reward=st / nn,
+                  avg_ep_reward=rs / nn, avg_ep_len=n / nn, n_new=int(nn))
+        return bs
+
+    def train(self):
+        while self.stats["n_timesteps"] < self.params["max_steps"]:
+            self.iter_log_str = ""
+            t_weights = self.batch_recorder.set_worker_weights(copy.deepcopy(self.pi))
+            self.stats["t_train"] += t_weights
+            t_batch = self.batch_recorder.record_batch(gamma=self.params["gamma"], lam=self.params["lambda"])
+            self.stats["t_train"] += t_batch
+            batch_stats = self._global_batch_stats(self.batch_recorder.get_batch_stats())
+            self.stats["n_timesteps"] += batch_stats["size"]
+            self.stats["batch_stats"] = batch_stats
+            self.stats["avg_step_rews"] = np.append(self.stats["avg_step_rews"], batch_stats["avg_step_reward"])
+            self.stats["avg_init_rews"] = np.append(self.stats["avg_init_rews"], batch_stats["avg_initial_reward"])
+            self.stats["avg_term_rews"] = np.append(self.stats["avg_term_rews"], batch_stats["avg_terminal_reward"])
+            self.stats["avg_ep_rews"] = np.append(self.stats["avg_ep_rews"], batch_stats["avg_ep_reward"])
+            self.stats["perc"] = 100 * self.stats["n_timesteps"] / self.params["max_steps"]
+            batch_stats["t_batch"] = t_batch
+            batch_stats["sps"] = batch_stats["size"] / batch_stats["t_batch"]
+            self.add_iter_log_str(batch_stats=batch_stats)
+            if self.stats["n_iters"] % self.save_interval == 0 or self.stats["n_iters"] == 0 or \
+                    self.stats["n_timesteps"] >= self.params["max_steps"]:
+                self.store_weights()
+            t_optim = self.optimize_on_batch()
+            self.stats["t_train"] += t_optim
+            self.stats["t_optim"] = t_optim
+            self.store_log()
+            self.stats["n_iters"] += 1
+        self.batch_recorder.cleanup()
+
+    def store_log(self):
+        if self.rank != 0:
+            return
+        with open(os.path.join(self.logpath, "log"), "a") as f:
+            print(self.iter_log_str, file=f)
+        if not self.verbose:
+            print(self.iter_log_str)
+        with open(os.path.join(self.logpath, "stats_" + str(self.stats["n_iters"])), "wb") as f:
+            pkl.dump(self.stats, f)
+        with open(os.path.join(self.logpath, "params_" + str(self.stats["n_iters"])), "wb") as f:
+            pkl.dump(self.params, f)
+
+    def store_weights(self):
+        if self.rank != 0:
+            return
+        with open(os.path.join(self.logpath, "weights_" + str(self.stats["n_iters"])), "wb") as f:
+            torch.save({k: v.cpu() for k, v in self.pi.state_dict().items()}, f)
+
+    def add_iter_log_str(self, batch_stats):
+        s = "\n******************** ITERATION {:2d} ********************\n".format(self.stats["n_iters"])
+        s += " RUN STATISTICS (BEFORE OPTIMIZATION):\n"
+        s += "   environment          = {}\n".format(self.params["env_id"])
+        s += "   n_timesteps  = {:d} ({:.2f}%)\n".format(self.stats["n_timesteps"], self.stats["perc"])
+        s += "   n_optsteps   = {:d}\n".format(self.stats["n_optsteps"])
+        s += "   t_total      = {:.2f}s\n".format(self.stats["t_train"])
+        s += " BATCH STATISTICS (BEFORE OPTIMIZATION):\n"
+        s += "   n_workers    = {:d}\n".format(self.params["n_workers"])
+        s += "   worker_seeds = {}\n".format(self.params["env_seeds"])
+        s += "   size         = {:d}\n".format(batch_stats["size"])
+        s += "    per_worker  = {:}\n".format(batch_stats["worker_sizes"])
+        s += "   avg_step_rew = {:.4g}\n".format(batch_stats["avg_step_reward"])
+        s += "   avg_init_rew = {:.4g}\n".format(batch_stats["avg_initial_reward"])
+        s += "   avg_term_rew = {:.4g}\n".format(batch_stats["avg_terminal_reward"])
+        s += "   avg_ep_rew   = {:.4g}\n".format(batch_stats["avg_ep_reward"])
+        s += "   n_new        = {:d}\n".format(batch_stats["n_new"])
+        s += "    per_worker  = {:}\n".format(batch_stats["worker_n_news"])
+        s += "   avg_ep_len   = {:.2f}\n".format(batch_stats["avg_ep_len"])
+        s += "   t_batch      = {:.2f}s ({:.0f}sps)\n".format(batch_stats["t_batch"], batch_stats["sps"])
+        self.iter_log_str += s

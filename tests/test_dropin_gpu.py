@@ -1,0 +1,192 @@
+"""GPU tests of the drop-in layer (NeuralAF, MetaBO env, VecMetaBO, BatchRecorder, PPO, evaluate)
+against the oracle and the vectors minted from the reference."""
+import json
+import os
+import pickle as pkl
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import metabo_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+BRA_SPEC = {
+    "env_id": "MetaBO-BRA-v0", "D": 2, "f_type": "BRA-var", "f_opts": {"bound_translation": 0.1, "bound_scaling": 0.1},
+    "features": ["posterior_mean", "posterior_std", "timestep", "budget", "x"], "T": 30, "n_init_samples": 0,
+    "pass_X_to_pi": False, "kernel_lengthscale": [0.235, 0.578], "kernel_variance": 2.0, "noise_variance": 8.9e-16,
+    "use_prior_mean_function": False, "local_af_opt": True, "N_MS": 1000, "N_LS": 1000, "k": 5,
+    "reward_transformation": "none"}
+
+
+def _policy(golden_dir, wfile, deterministic=True, mode="bf16x3", M=966, F=6):
+    from metabo_b200 import gym_compat as gym
+    from metabo_b200.policies.policies import NeuralAF
+    pw = O.PolicyWeights.from_npz(os.path.join(golden_dir, wfile))
+    opts = dict(pw.options, mlp_mode=mode)
+    obs = gym.spaces.Box(low=-1e5, high=1e5, shape=(M, F), dtype=np.float32)
+    pi = NeuralAF(obs, gym.spaces.Discrete(M), deterministic=deterministic, options=opts)
+    pi.load_state_dict({k: v.clone() for k, v in pw.sd.items()})
+    return pi, pw
+
+
+@pytest.mark.parametrize("wfile,F,M", [("weights_bra_1635.npz", 6, 966), ("weights_gps_1161.npz", 6, 2000)])
+def test_neural_af_api_matches_reference_semantics(golden_dir, wfile, F, M):
+    pi, pw = _policy(golden_dir, wfile, M=M, F=F)
+    rng = np.random.RandomState(0)
+    states = rng.randn(3, M, F).astype(np.float32)
+    states[:, :, -2] = 7.0
+    states[:, :, -1] = 30.0
+    lo, vo = O.policy_forward(pw, states)
+    with torch.no_grad():
+        lg, v = pi.forward(torch.from_numpy(states))          # CPU tensors in, kernel path, CPU tensors out
+    assert lg.device.type == "cpu" and lg.shape == (3, M) and v.shape == (3,)
+    scale = float(lo.abs().max())
+    assert float((lg - lo).abs().max()) <= 2e-5 * scale + 1e-5
+    np.testing.assert_allclose(v.numpy(), vo.numpy(), rtol=1e-5, atol=1e-5)
+    af = pi.af(states[0])
+    assert af.shape == (M,) and np.allclose(af, lg[0].numpy())
+    a, val = pi.act(torch.from_numpy(states[0]))
+    assert a.dim() == 0 and val.dim() == 0
+    assert float(lo[0, int(a)]) >= float(lo[0].max()) - 2e-5 * scale - 1e-5
+    acts = torch.tensor([1.0, 5.0, 9.0])                      # float actions, as ppo.py:132 passes them
+    with torch.no_grad():
+        pi.set_requires_grad(False)
+        v2, lp, en = pi.predict_vals_logps_ents(torch.from_numpy(states), acts)
+    lpo, eno = O.categorical_logp_entropy(lo.double(), acts.numpy())
+    np.testing.assert_allclose(lp.numpy(), lpo.numpy(), rtol=1e-4, atol=2e-4 * scale)
+    np.testing.assert_allclose(en.numpy(), eno.numpy(), rtol=1e-3, atol=1e-3)
+    # autograd path (PPO update) on the GPU agrees with the kernel path
+    pi.set_requires_grad(True)
+    pi_cuda = pi.to("cuda")
+    lg2, _ = pi_cuda.forward(torch.from_numpy(states).cuda())
+    assert lg2.requires_grad
+    assert float((lg2.detach().cpu() - lo).abs().max()) <= 1e-4 * scale + 1e-5
+
+
+def test_single_env_deterministic_branin_episode(golden_dir):
+    """evaluate_metabo_branin.py settings, seed 100: the first state is a pure function of the
+    weights (empty GP) and must equal the reference's; the free-running episode must reach the
+    optimum like the reference did (its final simple regret: 3.8e-6)."""
+    from metabo_b200.environment.metabo_gym import MetaBO
+    ep = np.load(os.path.join(golden_dir, "episode_bra.npz"))
+    pi, pw = _policy(golden_dir, "weights_bra_1635.npz")
+    env = MetaBO(**BRA_SPEC)
+    env.set_af_functions(pi.af)
+    env.seed(100)
+    state = env.reset()
+    assert state.shape == (966, 6) and state.dtype == np.float32
+    assert env.observation_space.contains(state)
+    ref_state = ep["t00_state"]
+    # multistart part of xi_t is identical; the 5 local maxima may permute/tie (flat AF on the empty GP)
+    assert np.array_equal(state[5:], ref_state[5:])
+    assert abs(env.y_max - float(ep["y_max"])) < 1e-12        # same objective drawn from RandomState(100)
+    rewards = []
+    for t in range(30):
+        action, value = pi.act(torch.from_numpy(state))
+        assert env.action_space.contains(int(action))
+        state, r, done, info = env.step(action.numpy())
+        rewards.append(r)
+        assert env.X.shape == (t + 1, 2) and env.Y.shape == (t + 1, 1)
+    assert done and env.is_terminal()
+    assert np.all(np.diff(rewards) <= 1e-12)                  # simple regret is non-increasing
+    assert rewards[-1] < 1e-3, rewards[-1]
+    m, s = env.eval_gp(env.X)                                 # GP interpolates its data (sigma ~ 1e-4 floor)
+    assert np.max(np.abs(m - env.Y[:, 0])) < 1e-3 and np.max(s) < 1e-3
+
+
+def test_vec_env_lanes_are_batch_invariant(golden_dir):
+    """Episodes are independent units: lane b of a B=4 batch is bitwise the episode a B=1 batch
+    with the same seed plays (this is what makes sharding over GPUs collective-free)."""
+    from metabo_b200.environment.vec_env import VecMetaBO
+    pi, _ = _policy(golden_dir, "weights_bra_1635.npz")
+    spec = dict(BRA_SPEC, T=6)
+    seeds = [100, 101, 102, 103]
+
+    def run(lane_seeds):
+        env = VecMetaBO(len(lane_seeds), lane_seeds, **spec)
+        env.set_policy(pi)
+        env.reset()
+        rs, acts = [], []
+        for _ in range(spec["T"]):
+            acts.append(env.cur["action"].clone())
+            r, done = env.step()
+            rs.append(r.clone())
+        torch.cuda.synchronize()
+        return torch.stack(rs, 1).cpu().numpy(), torch.stack(acts, 1).cpu().numpy(), env.engine.X.cpu().numpy()
+
+    r4, a4, x4 = run(seeds)
+    for b, s in enumerate(seeds):
+        r1, a1, x1 = run([s])
+        assert np.array_equal(r4[b], r1[0]) and np.array_equal(a4[b], a1[0]) and np.array_equal(x4[b], x1[0])
+
+
+def test_batchrecorder_and_ppo_iteration(golden_dir, tmp_path):
+    from metabo_b200 import gym_compat as gym
+    from metabo_b200.policies.policies import NeuralAF
+    from metabo_b200.ppo.ppo import PPO
+    spec = dict(BRA_SPEC, T=5, N_MS=100, N_LS=50, k=3, reward_transformation="neg_log10",
+                f_opts={"bound_translation": 0.1, "bound_scaling": 0.1, "M": 50})
+    gym.register(id="MetaBO-TEST-v0", entry_point="metabo.environment.metabo_gym:MetaBO", max_episode_steps=5, kwargs=spec)
+    params = {"batch_size": 40, "max_steps": 80, "minibatch_size": 10, "n_epochs": 2, "lr": 1e-3, "epsilon": 0.15,
+              "value_coeff": 1.0, "ent_coeff": 0.01, "gamma": 0.98, "lambda": 0.98, "loss_type": "GAElam",
+              "normalize_advs": True, "n_workers": 4, "env_id": "MetaBO-TEST-v0", "seed": 0, "env_seeds": [0, 1, 2, 3],
+              "policy_options": {"activations": "relu", "arch_spec": [200] * 4, "use_value_network": True, "t_idx": -2,
+                                 "T_idx": -1, "arch_spec_value": [200] * 4}}
+
+    def policy_fn(osp, asp, det):
+        return NeuralAF(osp, asp, det, options=params["policy_options"])
+
+    logpath = str(tmp_path / "log")
+    ppo = PPO(policy_fn=policy_fn, params=params, logpath=logpath, save_interval=1)
+    w0 = ppo.pi.policy_net.fc[0].weight.detach().clone()
+    ppo.train()
+    br = ppo.batch_recorder
+    assert len(br) == 40 and br.is_full()
+    mem = br.memory
+    assert len(mem) == 40 and [m.new for m in mem[:6]] == [1, 0, 0, 0, 0, 1]     # worker-major, episode-major
+    assert mem[0].state.shape == (103, 6) and mem[0].state.dtype == np.float32
+    # GAE on the device == reference formula on the host
+    for lane in range(2):
+        tr = mem[lane * 5:(lane + 1) * 5]
+        a_o, r_o = O.gae([t.reward for t in tr], [float(t.value) for t in tr], [t.new for t in tr], 1,
+                         float(tr[-1].value), 0.98, 0.98)
+        np.testing.assert_allclose([t.adv for t in tr], a_o, rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose([t.tdlamret for t in tr], r_o, rtol=1e-5, atol=1e-5)
+    stats = br.get_batch_stats()
+    assert stats["n_new"] == 8 and stats["avg_ep_len"] == 5
+    assert not torch.equal(w0, ppo.pi.policy_net.fc[0].weight.detach())          # the update moved the weights
+    for f in ("000_overview.txt", "log", "stats_0", "stats_1", "params_1", "weights_0", "weights_1"):
+        assert os.path.exists(os.path.join(logpath, f)), f
+    st = pkl.load(open(os.path.join(logpath, "stats_1"), "rb"))
+    assert st["n_timesteps"] == 80 and st["n_optsteps"] == 2 * 2 * 4 and "sps" in st["batch_stats"]
+    sd = torch.load(os.path.join(logpath, "weights_1"), weights_only=False)
+    assert set(sd) == set(ppo.pi.state_dict())
+    from metabo_b200.ppo.util import get_best_iter_idx, get_last_iter_idx
+    assert get_last_iter_idx(logpath) == 1 and get_best_iter_idx(logpath) in (0, 1)
+
+
+def test_eval_experiment_with_shipped_checkpoint_layout(golden_dir, tmp_path):
+    """evaluate.py flow on a checkpoint directory laid out like metabo/iclr2020/**."""
+    from metabo_b200 import gym_compat as gym
+    from metabo_b200.eval.evaluate import eval_experiment
+    pw = O.PolicyWeights.from_npz(os.path.join(golden_dir, "weights_hm3_1988.npz"))
+    logpath = tmp_path / "MetaBO-HM3-v0"
+    os.makedirs(logpath)
+    pkl.dump({"policy_options": pw.options}, open(logpath / "params_1988", "wb"))
+    torch.save({k: v for k, v in pw.sd.items()}, logpath / "weights_1988")
+    pkl.dump({"avg_step_rews": [0.0]}, open(logpath / "stats_1988", "wb"))
+    spec = {"env_id": "MetaBO-HM3-v0", "D": 3, "f_type": "HM3-var", "f_opts": {"bound_translation": 0.1, "bound_scaling": 0.1},
+            "features": ["posterior_mean", "posterior_std", "timestep", "budget", "x"], "T": 30, "n_init_samples": 0,
+            "pass_X_to_pi": False, "kernel_lengthscale": [0.716, 0.298, 0.186], "kernel_variance": 0.83,
+            "noise_variance": 1.688e-11, "use_prior_mean_function": False, "local_af_opt": True, "N_MS": 2000,
+            "N_LS": 2000, "k": 5, "reward_transformation": "none"}
+    gym.register(id=spec["env_id"], entry_point="metabo.environment.metabo_gym:MetaBO", max_episode_steps=30, kwargs=spec)
+    res = eval_experiment({"env_id": spec["env_id"], "env_seed_offset": 100, "policy": "MetaBO", "logpath": str(logpath),
+                           "load_iter": 1988, "deterministic": True, "policy_specs": {}, "savepath": str(tmp_path / "eval"),
+                           "n_workers": 4, "n_episodes": 8, "T": 30})
+    r = np.array(res.rewards).reshape(8, 30)
+    assert np.all(np.diff(r, axis=1) <= 1e-12)
+    assert np.median(r[:, -1]) < 5e-2                         # reference: median simple regret ~1e-3 after 30 steps
+    assert os.path.exists(tmp_path / "eval" / "result_metabo_iter_1988")
