@@ -130,59 +130,98 @@ def workload_config(args, B, ref=False):
 
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled (NVML, every 10 ms) DURING the timed region."""
+    BITS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+            0x80: "hw_power_brake_slowdown"}
 
-    def __init__(self, gpu_index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+    def __init__(self, device):
+        import threading
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.stop_flag = threading.Event()
+        self.h = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
-                                      stderr=subprocess.DEVNULL)
-        except OSError:
-            pass
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(device).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(device.index or 0)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:          # pragma: no cover
+            sys.stderr.write("[bench] NVML unavailable: %s\n" % e)
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+
+    def _run(self):
+        if self.h is None:
+            return
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.BITS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.p is None:
-            return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.f.read().splitlines():
-            parts = [x.strip() for x in ln.split(",")]
-            if len(parts) < 9:
-                continue
-            try:
-                sm.append(float(parts[1])); mx.append(float(parts[2]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, parts[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
-        if sm:
-            # "under load" = samples in the upper half of the observed power/clock activity
-            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                   "samples": len(sm)}
-        try:
-            os.unlink(self.f.name)
-        except OSError:
-            pass
-        return out
+        self.stop_flag.set()
+        self.th.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_min_mhz": float(min(self.samples)),
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def ppo_rollout_rate(dev, world, rank):
+    """Supplementary BASELINE metric: PPO env-steps/s exactly as the reference defines `sps`
+    (batch size / t_batch, rollout only, ppo.py:213) on the train_metabo_branin.py environment
+    (stochastic policy, M=50 training functions, neg_log10 reward) with 1024 episodes per GPU."""
+    import torch
+    import torch.distributed as dist
+    from metabo_b200 import gym_compat as gym
+    from metabo_b200.policies.policies import NeuralAF
+    from metabo_b200.ppo.batchrecorder import BatchRecorder
+    spec = {"env_id": "MetaBO-BRA-v0", "D": 2, "f_type": "BRA-var",
+            "f_opts": {"bound_translation": 0.1, "bound_scaling": 0.1, "M": 50},
+            "features": ["posterior_mean", "posterior_std", "timestep", "budget", "x"], "T": 30, "n_init_samples": 0,
+            "pass_X_to_pi": False, "kernel_lengthscale": [0.235, 0.578], "kernel_variance": 2.0,
+            "noise_variance": 8.9e-16, "use_prior_mean_function": False, "local_af_opt": True, "N_MS": 1000,
+            "N_LS": 1000, "k": 5, "reward_transformation": "neg_log10"}
+    gym.register(id=spec["env_id"], entry_point="metabo.environment.metabo_gym:MetaBO", max_episode_steps=30, kwargs=spec)
+    opts = {"activations": "relu", "arch_spec": [200] * 4, "use_value_network": True, "t_idx": -2, "T_idx": -1,
+            "arch_spec_value": [200] * 4, "mlp_mode": "tf32"}
+    n_workers, eps = 64, 16
+    size = n_workers * eps * 30
+    br = BatchRecorder(size=size, env_id=spec["env_id"], env_seeds=list(range(rank * n_workers, (rank + 1) * n_workers)),
+                       policy_fn=lambda o, a, d: NeuralAF(o, a, d, options=opts), n_workers=n_workers,
+                       deterministic=False, store_states=False, mlp_mode="tf32", device=dev)
+    br.record_batch(0.98, 0.98)                       # warm-up
+    if world > 1:
+        dist.barrier()
+    t = br.record_batch(0.98, 0.98)
+    if world > 1:
+        tt = torch.tensor([t], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t = float(tt[0])
+    return {"env_steps_per_s": world * size / t, "t_batch_s": t, "batch_steps": world * size,
+            "config": "train_metabo_branin.py env (C3), stochastic NeuralAF 4x200, 1024 episodes x T=30 per GPU, "
+                      "6927 candidates per step, tf32 MLP + fp64 GP, transitions kept on device without states"}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--B", type=int, default=1024, help="episodes per GPU")
@@ -190,6 +229,7 @@ def main():
     ap.add_argument("--gp", default="fp64", choices=["fp64", "fp32"])
     ap.add_argument("--mlp", default="auto", choices=["auto", "fp32", "tf32", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ppo", action="store_true", help="skip the supplementary PPO rollout env-steps/s figure")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -272,7 +312,7 @@ def main():
         for _ in range(warmup):
             fn()
         barrier()
-        sampler = ClockSampler(local_rank) if profile else None
+        sampler = ClockSampler(dev) if profile else None
         evs = []
         l0 = eng.launches
         for _ in range(steps):
@@ -345,6 +385,10 @@ def main():
     d2h = h_act.numel() * 4 + h_x.numel() * 8
     e2e_val = world * cands_step * args.steps / (ms_e / 1e3)
 
+    ppo_info = None
+    if not args.no_ppo:
+        ppo_info = ppo_rollout_rate(dev, world, rank)
+
     cpu_b = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_b, _, _ = cpu_arm(3, n)
@@ -360,7 +404,7 @@ def main():
                 "config": workload_config(args, B), "clocks": clocks,
                 "e2e": {"value": e2e_val, "unit": "AF evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e / args.steps},
-                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu_b}
+                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu_b, "ppo_rollout": ppo_info}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
