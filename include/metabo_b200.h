@@ -152,6 +152,16 @@ int mbo_af_logits_dense(const mbo_policy* p, int mode, int B, int M, int F_state
                         const int32_t* cols, const float* states, float* logits, void* workspace,
                         size_t workspace_bytes, void* stream);
 
+/* Fused form of mbo_gp_posterior + mbo_af_logits for n_active_max <= 32 observations (the T = 30
+ * configs): dedicated fp64 warps of the tensor-core kernel compute the GP posterior of the NEXT
+ * candidate tile while the tensor pipe runs the MLP of the current one; mean/std never touch HBM
+ * unless mean_out/std_out ([B, M] fp32, may both be null) are requested for the PPO state buffer.
+ * Returns MBO_ERR_UNSUPPORTED for larger n or unsupported architectures (use the two-call path). */
+int mbo_af_eval_fused(const mbo_policy* p, int mode, int B, int nmax, int n_active_max, int kernel_id,
+                      const double* gp_state, int F, const int32_t* feat_src, const mbo_candidates* cand,
+                      const float* epi, float* logits, float* mean_out, float* std_out, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
 /* value network on (t, T) of row 0 (policies.py:117-121): tT [B,2] fp32 -> values [B] */
 int mbo_value_net(const mbo_policy* value_net, int B, const float* tT, float* values, void* stream);
 
@@ -167,7 +177,7 @@ int mbo_logits_argmax(int B, int M, const float* logits, int32_t* action, float*
 int mbo_logits_topk(int B, int M, int k, const float* logits, int32_t* idx /*[B,k]*/,
                     float* val /*[B,k]*/, void* stream);
 int mbo_logits_sample(int B, int M, const float* logits, uint64_t seed, uint64_t step,
-                      int32_t* action, void* stream);
+                      uint64_t episode_offset /* global index of row 0 */, int32_t* action, void* stream);
 int mbo_logits_logp_entropy(int B, int M, const float* logits, const int32_t* actions,
                             float* logp, float* entropy, void* stream);
 

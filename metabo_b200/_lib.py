@@ -40,10 +40,12 @@ SYMBOLS = [
                            _sz, _vp]),
     ("mbo_af_workspace_bytes", _sz, [_i, _i, _i]),
     ("mbo_af_logits_dense", _i, [_vp, _i, _i, _i, _i, _i, C.POINTER(C.c_int32), _vp, _vp, _vp, _sz, _vp]),
+    ("mbo_af_eval_fused", _i, [_vp, _i, _i, _i, _i, _i, _vp, _i, C.POINTER(C.c_int32), C.POINTER(Candidates), _vp, _vp,
+                               _vp, _vp, _vp, _sz, _vp]),
     ("mbo_value_net", _i, [_vp, _i, _vp, _vp, _vp]),
     ("mbo_logits_argmax", _i, [_i, _i, _vp, _vp, _vp, _vp]),
     ("mbo_logits_topk", _i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
-    ("mbo_logits_sample", _i, [_i, _i, _vp, _u64, _u64, _vp, _vp]),
+    ("mbo_logits_sample", _i, [_i, _i, _vp, _u64, _u64, _u64, _vp, _vp]),
     ("mbo_logits_logp_entropy", _i, [_i, _i, _vp, _vp, _vp, _vp, _vp]),
     ("mbo_candidates_gather", _i, [_i, C.POINTER(Candidates), _i, _vp, _vp, _vp]),
     ("mbo_cubes_around", _i, [_i, _i, _i, _vp, _d, _vp, _vp]),

@@ -16,27 +16,9 @@
 // (zero above the diagonal / beyond n) so the posterior kernel reads 8 rows of one column with
 // two broadcast LDS.128.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace mbo {
-
-template <typename T> __device__ __forceinline__ T t_exp(T x);
-template <> __device__ __forceinline__ double t_exp<double>(double x) { return exp(x); }
-template <> __device__ __forceinline__ float t_exp<float>(float x) { return __expf(x); }
-template <typename T> __device__ __forceinline__ T t_sqrt(T x);
-template <> __device__ __forceinline__ double t_sqrt<double>(double x) { return sqrt(x); }
-template <> __device__ __forceinline__ float t_sqrt<float>(float x) { return sqrtf(x); }
-
-template <typename T>
-__device__ __forceinline__ T kernel_of_r2(int kid, T var, T r2) {
-  if (kid == MBO_KERNEL_RBF) return var * t_exp<T>(T(-0.5) * r2);
-  T r = t_sqrt<T>(r2);
-  if (kid == MBO_KERNEL_MATERN32) {
-    const T s3 = T(1.7320508075688772935);
-    return var * (T(1) + s3 * r) * t_exp<T>(-s3 * r);
-  }
-  const T s5 = T(2.2360679774997896964);
-  return var * (T(1) + s5 * r + T(5.0 / 3.0) * r2) * t_exp<T>(-s5 * r);
-}
 
 // ------------------------------------------------------------------------------------------------
 // K0: fit.  One CTA per episode.
@@ -245,14 +227,37 @@ gp_posterior_kernel(int nmax, int kid, const double* __restrict__ gp_state, mbo_
   }
   constexpr int KS = POST_THREADS * TC;
   // phase 2
-  for (int j = 0; j < n; ++j) {
+  if (sizeof(T) == 8) {
+    // fp64: four kernel values at a time with interleaved exp chains (see exp_nonpos_x4)
 #pragma unroll
     for (int c = 0; c < TC; ++c) {
-      T r2 = T(0);
+      for (int j0 = 0; j0 < n; j0 += 4) {
+        double r2v[4], kv[4];
 #pragma unroll
-      for (int d = 0; d < MBO_MAX_D; ++d)
-        if (d < D) { T t = xs[c][d] - sXs[j * D + d]; r2 += t * t; }
-      sK[j * KS + tid * TC + c] = kernel_of_r2<T>(kid, (T)var, r2);
+        for (int u = 0; u < 4; ++u) {
+          const int jj = min(j0 + u, n - 1);
+          double r2 = 0.0;
+#pragma unroll
+          for (int d = 0; d < MBO_MAX_D; ++d)
+            if (d < D) { const double t = (double)xs[c][d] - (double)sXs[jj * D + d]; r2 = fma(t, t, r2); }
+          r2v[u] = r2;
+        }
+        kernel_of_r2_x4(kid, var, r2v, kv);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (j0 + u < n) sK[(j0 + u) * KS + tid * TC + c] = (T)kv[u];
+      }
+    }
+  } else {
+    for (int j = 0; j < n; ++j) {
+#pragma unroll
+      for (int c = 0; c < TC; ++c) {
+        T r2 = T(0);
+#pragma unroll
+        for (int d = 0; d < MBO_MAX_D; ++d)
+          if (d < D) { T t = xs[c][d] - sXs[j * D + d]; r2 += t * t; }
+        sK[j * KS + tid * TC + c] = kernel_of_r2<T>(kid, (T)var, r2);
+      }
     }
   }
   for (int j = n; j < NP; ++j) {
@@ -377,7 +382,8 @@ extern "C" int mbo_gp_posterior(int B, int nmax, int n_active_max, int kernel_id
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   if (precision == MBO_GP_FP64) {
-    if (posterior_smem_bytes<double, 2>(ns, cand->D) <= 100 * 1024)
+    static const int force_tc1 = getenv("MBO_GP_TC1") ? 1 : 0;     // tuning switch
+    if (!force_tc1 && posterior_smem_bytes<double, 2>(ns, cand->D) <= 100 * 1024)
       return launch_posterior<double, 2>(B, nmax, ns, kernel_id, gp_state, *cand, mean, std_, out_is_f32, s);
     return launch_posterior<double, 1>(B, nmax, ns, kernel_id, gp_state, *cand, mean, std_, out_is_f32, s);
   } else if (precision == MBO_GP_FP32) {

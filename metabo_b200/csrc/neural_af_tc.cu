@@ -34,7 +34,11 @@ namespace mbo {
 constexpr int TC_N = 208;            // padded hidden width (UMMA N, multiple of 16)
 constexpr int TC_M = 128;            // candidates per tile (UMMA M)
 constexpr int TC_THREADS = 320;        // 8 epilogue warps + TMA warp + MMA warp
-constexpr int WARP_TMA = 8, WARP_MMA = 9;
+constexpr int WARP_TMA = 8, WARP_MMA = 9, WARP_GP0 = 10;   // warps 10-13: fused GP posterior (FUSE only)
+constexpr int TC_THREADS_FUSED = 448;
+constexpr int GP_NP = 32;                 // fused GP: n <= 32 observations
+constexpr int GPB_XS = 16, GPB_BETA = GPB_XS + GP_NP * MBO_MAX_D, GPB_LINV = GPB_BETA + GP_NP;
+constexpr int GPB_DOUBLES = GPB_LINV + 640;   // header | Xs[32][8] | beta[32] | LinvB(4 blocks)
 constexpr int TC_K0 = 8;             // layer-0 K (features + ones column, <= 8)
 constexpr int CHUNK_ROW_BYTES = TC_N * 16;   // one 16-byte K chunk for all 208 rows = 3328 B
 constexpr uint32_t TMEM_COLS = 512;
@@ -49,6 +53,7 @@ template <> struct ModeCfg<MBO_MLP_TF32> {
   static constexpr int STAGES_PER_LAYER = 5;
   static constexpr int STAGE_BYTES = SLICES_PER_STAGE * 2 * CHUNK_ROW_BYTES;   // 33 280
   static constexpr int NSTAGE = 6;
+  static constexpr int NSTAGE_FUSED = 5;       // fused GP needs 42 KB of shared memory for its scratch
   static constexpr int CHUNK_COLS = 40;        // accumulator columns converted per hand-off
   static constexpr int NCHUNK = 5;
 };
@@ -60,6 +65,7 @@ template <> struct ModeCfg<MBO_MLP_BF16X3> {
   static constexpr int STAGES_PER_LAYER = 13;
   static constexpr int STAGE_BYTES = 2 * 2 * CHUNK_ROW_BYTES;                  // hi + lo: 13 312
   static constexpr int NSTAGE = 14;
+  static constexpr int NSTAGE_FUSED = 11;
   static constexpr int CHUNK_COLS = 32;
   static constexpr int NCHUNK = 7;             // 6 x 32 + 1 x 16
 };
@@ -295,17 +301,21 @@ struct TcFeat {
   int dense_F;
 };
 
-template <int MODE>
+template <int MODE, bool FUSE = false>
 struct TcSmem {
   using C = ModeCfg<MODE>;
+  static constexpr int NS = FUSE ? C::NSTAGE_FUSED : C::NSTAGE;
   static constexpr size_t off_ring = 0;
-  static constexpr size_t off_w0 = off_ring + (size_t)C::NSTAGE * C::STAGE_BYTES;
+  static constexpr size_t off_w0 = off_ring + (size_t)NS * C::STAGE_BYTES;
   static constexpr size_t off_tail = off_w0 + W0_BYTES;
   static constexpr size_t off_bars = off_tail + sizeof(float) * TAIL_FLOATS;
-  static constexpr int n_bars = 2 * C::NSTAGE + C::NCHUNK + 2 + 3;   // ring, a_ready, d_full[2], feat_full, s_free, w0_full
+  static constexpr int n_bars = 2 * NS + C::NCHUNK + 2 + 3 + 4;   // ring, a_ready, d_full[2], feat_full, s_free, w0_full, gp_full[2], gp_empty[2]
   static constexpr size_t off_misc = off_bars + 8 * n_bars;
   static constexpr size_t off_part = off_misc + 16;
-  static constexpr size_t total = off_part + sizeof(float) * TC_M;
+  static constexpr size_t off_gp = off_part + sizeof(float) * TC_M;             // fused GP: episode blob + mu/sd hand-off
+  static constexpr size_t off_musd = off_gp + (FUSE ? sizeof(double) * GPB_DOUBLES : 0);
+  static constexpr size_t off_ks = off_musd + (FUSE ? sizeof(float) * 4 * TC_M : 0);        // k* scratch [32][128] fp64
+  static constexpr size_t total = off_ks + (FUSE ? sizeof(double) * GP_NP * TC_M : 0);
 };
 
 // per-mode conversion of one accumulator chunk into the next layer's A operand (in registers)
@@ -366,13 +376,23 @@ template <> struct ChunkOps<MBO_MLP_BF16X3> {
   }
 };
 
-template <int MODE>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+struct GpFuse {
+  const double* gp_state;   // [B, gp_state_doubles(nmax, D)]
+  int nmax, kid;
+  float* mean_out;          // optional [B, M] copies of the fused posterior (PPO state buffer), may be null
+  float* std_out;
+};
+
+template <int MODE, bool FUSE>
+__global__ void __launch_bounds__(FUSE ? TC_THREADS_FUSED : TC_THREADS, 1)
 neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candidates cand, int B,
                     int tiles_per_episode, const float* __restrict__ mean, const float* __restrict__ std_,
-                    const float* __restrict__ epi, float* __restrict__ logits, int* __restrict__ err_flag, int debug_noload) {
+                    const float* __restrict__ epi, float* __restrict__ logits, int* __restrict__ err_flag, int debug_noload,
+                    GpFuse gp) {
   using C = ModeCfg<MODE>;
-  using SM = TcSmem<MODE>;
+  using SM = TcSmem<MODE, FUSE>;
+  constexpr int NTHREADS = FUSE ? TC_THREADS_FUSED : TC_THREADS;
+  constexpr int NS = SM::NS;                      // ring depth
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const PackLayout pl = pack_layout();
@@ -386,12 +406,16 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
 
   const uint32_t bar0 = smem_u32(bars);
   auto BAR_WFULL = [&](int s) { return bar0 + 8u * (uint32_t)s; };
-  auto BAR_WEMPTY = [&](int s) { return bar0 + 8u * (uint32_t)(C::NSTAGE + s); };
-  auto BAR_AREADY = [&](int c) { return bar0 + 8u * (uint32_t)(2 * C::NSTAGE + c); };
-  auto BAR_DFULL = [&](int i) { return bar0 + 8u * (uint32_t)(2 * C::NSTAGE + C::NCHUNK + i); };
-  const uint32_t BAR_FEAT = bar0 + 8u * (uint32_t)(2 * C::NSTAGE + C::NCHUNK + 2);
+  auto BAR_WEMPTY = [&](int s) { return bar0 + 8u * (uint32_t)(NS + s); };
+  auto BAR_AREADY = [&](int c) { return bar0 + 8u * (uint32_t)(2 * NS + c); };
+  auto BAR_DFULL = [&](int i) { return bar0 + 8u * (uint32_t)(2 * NS + C::NCHUNK + i); };
+  const uint32_t BAR_FEAT = bar0 + 8u * (uint32_t)(2 * NS + C::NCHUNK + 2);
   const uint32_t BAR_SFREE = BAR_FEAT + 8u;
   const uint32_t BAR_W0 = BAR_FEAT + 16u;
+  auto BAR_GPFULL = [&](int i) { return BAR_FEAT + 24u + 8u * (uint32_t)i; };
+  auto BAR_GPEMPTY = [&](int i) { return BAR_FEAT + 40u + 8u * (uint32_t)i; };
+  float* s_mu = (float*)(smem + SM::off_musd);            // [2][128]
+  float* s_sd = s_mu + 2 * TC_M;                          // [2][128]
 
   const int total_tiles = B * tiles_per_episode;
   const int my_tiles = total_tiles > (int)blockIdx.x ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -399,16 +423,17 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
   // ---- one-time setup ----
   if (tid == 0) {
     *s_abort = 0;
-    for (int s = 0; s < C::NSTAGE; ++s) { mbar_init(BAR_WFULL(s), 1); mbar_init(BAR_WEMPTY(s), 1); }
+    for (int s = 0; s < NS; ++s) { mbar_init(BAR_WFULL(s), 1); mbar_init(BAR_WEMPTY(s), 1); }
     for (int c = 0; c < C::NCHUNK; ++c) mbar_init(BAR_AREADY(c), 128);
     mbar_init(BAR_DFULL(0), 1);
     mbar_init(BAR_DFULL(1), 1);
     mbar_init(BAR_FEAT, 128);
     mbar_init(BAR_SFREE, 1);
     mbar_init(BAR_W0, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR_GPFULL(i), 128); mbar_init(BAR_GPEMPTY(i), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = tid; i < TAIL_FLOATS; i += TC_THREADS) s_tail[i] = ((const float*)(pack + pl.off_tail))[i];
+  for (int i = tid; i < TAIL_FLOATS; i += NTHREADS) s_tail[i] = ((const float*)(pack + pl.off_tail))[i];
   if (warp == WARP_TMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -434,7 +459,7 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
         for (int ls = 0; ls < 3 * C::STAGES_PER_LAYER; ++ls) {
           if (!mbar_wait(BAR_WEMPTY(stage), phase ^ 1u, s_abort)) { ok = false; break; }
           if (leader) {
-            if (debug_noload && (t > 0 || ls >= C::NSTAGE)) {
+            if (debug_noload && (t > 0 || ls >= NS)) {
               mbar_arrive(BAR_WFULL(stage));    // timing experiment only: pretend the stage is resident
             } else {
               mbar_expect_tx(BAR_WFULL(stage), C::STAGE_BYTES);
@@ -442,7 +467,7 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
                        BAR_WFULL(stage));
             }
           }
-          if (++stage == C::NSTAGE) { stage = 0; phase ^= 1u; }
+          if (++stage == NS) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -492,7 +517,7 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
                   mma_ts_tf32(tD, tA + (c * 5 + sc) * 8, make_desc64(lo + sc * SLICE_D), IDESC_TF32, (c | sc) ? 1u : 0u);
                 tc_commit(BAR_WEMPTY(stage));
               }
-              if (++stage == C::NSTAGE) { stage = 0; wphase ^= 1u; }
+              if (++stage == NS) { stage = 0; wphase ^= 1u; }
             } else {
               // chunk c holds [hi(16 cols) | lo(16 cols)] of 32 K values = 2 slices (1 in the last chunk); slice == stage
               constexpr int LASTC = C::NCHUNK - 1;
@@ -510,7 +535,7 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
                   mma_ts_bf16(tD, a_hi, make_desc64(lo + SLICE_D), IDESC_BF16, 1u);
                   tc_commit(BAR_WEMPTY(stage));
                 }
-                if (++stage == C::NSTAGE) { stage = 0; wphase ^= 1u; }
+                if (++stage == NS) { stage = 0; wphase ^= 1u; }
               }
             }
           }
@@ -519,7 +544,7 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
         }
       }
     }
-  } else {
+  } else if (warp < WARP_TMA) {
     // ================= epilogue warps =================
     // warp w: TMEM lanes 32*(w&3)..+31 (thread = candidate row), column half h = w>>2:
     // half h converts chunks h, h+2, ...; half 1 also builds the next tile's features
@@ -532,6 +557,9 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
     const float* s_w4 = s_tail + 4 * TC_N;          // s_tail = [zeros | b1 | b2 | b3 | w4 | b4]
 
     auto build_features = [&](int t_idx) {
+      if (FUSE) {   // posterior of this tile from the GP warps
+        if (!mbar_wait(BAR_GPFULL(t_idx & 1), (uint32_t)(t_idx >> 1) & 1u, s_abort)) ok = false;
+      }
       const int tile = (int)blockIdx.x + t_idx * (int)gridDim.x;
       const int b = tile / tiles_per_episode;
       const int m = (tile - b * tiles_per_episode) * TC_M + row;
@@ -550,7 +578,9 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
 #pragma unroll
         for (int d = 0; d < MBO_MAX_D; ++d) x[d] = 0.0;
         load_candidate(cand, b, m, x);
-        const float mu = mean[(size_t)b * cand.M + m], sd = std_[(size_t)b * cand.M + m];
+        float mu, sd;
+        if (FUSE) { mu = s_mu[(t_idx & 1) * TC_M + row]; sd = s_sd[(t_idx & 1) * TC_M + row]; }
+        else { mu = mean[(size_t)b * cand.M + m]; sd = std_[(size_t)b * cand.M + m]; }
 #pragma unroll
         for (int i = 0; i < TC_K0 - 1; ++i) {
           if (i < fs.F) {
@@ -576,6 +606,7 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
         hi[i] = __float_as_uint(h);
         lo[i] = __float_as_uint(tf32_rna(f[i] - h));
       }
+      if (FUSE) mbar_arrive(BAR_GPEMPTY(t_idx & 1));   // mu/sd of this buffer consumed
       tmem_st8(tlane + COL_S, hi);
       tmem_st8(tlane + COL_S + 16, lo);
       tmem_wait_st();
@@ -664,6 +695,132 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
       }
       asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");   // s_part reusable
     }
+  } else if (FUSE) {
+    // ================= fused GP posterior warps (fp64): thread = candidate row of the NEXT tile =================
+    // mean = v.beta + m, var = max(k** - |v|^2, 1e-15), v = Linv k*  (same arithmetic as gp_posterior_kernel<double>),
+    // k* in registers (n <= 32, loops fully unrolled), episode blob in shared memory.
+    const int g = tid - WARP_GP0 * 32;
+    double* blob = (double*)(smem + SM::off_gp);
+    double* ks = (double*)(smem + SM::off_ks);
+    const int D = cand.D;
+    const int NPmax = gp_np(gp.nmax);
+    const size_t gstride = gp_state_doubles(gp.nmax, D);
+    int cur_b = -1;
+    bool ok = true;
+    for (int t = 0; t < my_tiles && ok; ++t) {
+      const int buf = t & 1;
+      if (!mbar_wait(BAR_GPEMPTY(buf), ((uint32_t)(t >> 1) & 1u) ^ 1u, s_abort)) { ok = false; break; }
+      const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+      const int b = tile / tiles_per_episode;
+      const int m = (tile - b * tiles_per_episode) * TC_M + g;
+      if (b != cur_b) {
+        asm volatile("bar.sync 5, 128;" ::: "memory");           // everyone done with the previous episode's blob
+        const double* st = gp.gp_state + (size_t)b * gstride;
+        const int n_ = (int)st[0];
+        const int np_ = gp_np(n_);
+        for (int i = g; i < 16; i += 128) blob[i] = st[i];
+        for (int i = g; i < np_ * D; i += 128) blob[GPB_XS + i] = st[gp_off_xs() + i];
+        for (int i = g; i < GP_NP; i += 128) blob[GPB_BETA + i] = i < np_ ? st[gp_off_beta(NPmax, D) + i] : 0.0;
+        const int lc = gp_linv_doubles(np_);
+        for (int i = g; i < lc; i += 128) blob[GPB_LINV + i] = st[gp_off_linv(NPmax, D) + i];
+        asm volatile("bar.sync 5, 128;" ::: "memory");
+        cur_b = b;
+      }
+      const int n = (int)blob[0];
+      const double mprior = blob[1], var = blob[2];
+      double mean_v = 0.0, var_v = var;
+      if (n > 0 && m < cand.M) {
+        double x[MBO_MAX_D];
+#pragma unroll
+        for (int d = 0; d < MBO_MAX_D; ++d) x[d] = 0.0;
+        load_candidate(cand, b, m, x);
+#pragma unroll
+        for (int d = 0; d < MBO_MAX_D; ++d) x[d] = d < D ? x[d] / blob[4 + d] : 0.0;
+        // k* into this thread's private shared-memory column (rolled loops: the fused role must stay small
+        // enough for the instruction cache; a fully unrolled register version thrashed it)
+        double* kcol = ks + g;
+        for (int j0 = 0; j0 < n; j0 += 8) {          // 8 interleaved exp chains per step
+          double r2v[8], kv[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int jj = min(j0 + u, n - 1);
+            double r2 = 0.0;
+#pragma unroll
+            for (int d = 0; d < MBO_MAX_D; ++d)
+              if (d < D) { const double tt = x[d] - blob[GPB_XS + jj * D + d]; r2 = fma(tt, tt, r2); }
+            r2v[u] = r2;
+          }
+          kernel_of_r2_xn<8>(gp.kid, var, r2v, kv);
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (j0 + u < n) kcol[(j0 + u) * TC_M] = kv[u];
+        }
+        for (int j = n; j < gp_np(n); ++j) kcol[j * TC_M] = 0.0;
+        double q = 0.0, mu = 0.0;
+        // v = Linv k*, two 8-row blocks per pass (16 independent DFMA chains); LinvB rows beyond n are zero
+        for (int ib = 0; ib < n; ib += 16) {
+          double acc0[8], acc1[8];
+#pragma unroll
+          for (int r = 0; r < 8; ++r) { acc0[r] = 0.0; acc1[r] = 0.0; }
+          const double* blk0 = blob + GPB_LINV + gp_linv_block_off(ib);
+          const double* blk1 = blob + GPB_LINV + gp_linv_block_off(ib + 8);
+          const bool two = ib + 8 < gp_np(n);
+#pragma unroll 2
+          for (int j = 0; j < ib + 8; ++j) {
+            const double kj = kcol[j * TC_M];
+            const double2* p = (const double2*)(blk0 + j * 8);
+            const double2 a0 = p[0], a1 = p[1], a2 = p[2], a3 = p[3];
+            acc0[0] = fma(a0.x, kj, acc0[0]); acc0[1] = fma(a0.y, kj, acc0[1]);
+            acc0[2] = fma(a1.x, kj, acc0[2]); acc0[3] = fma(a1.y, kj, acc0[3]);
+            acc0[4] = fma(a2.x, kj, acc0[4]); acc0[5] = fma(a2.y, kj, acc0[5]);
+            acc0[6] = fma(a3.x, kj, acc0[6]); acc0[7] = fma(a3.y, kj, acc0[7]);
+            if (two) {
+              const double2* pp = (const double2*)(blk1 + j * 8);
+              const double2 b0 = pp[0], b1 = pp[1], b2 = pp[2], b3 = pp[3];
+              acc1[0] = fma(b0.x, kj, acc1[0]); acc1[1] = fma(b0.y, kj, acc1[1]);
+              acc1[2] = fma(b1.x, kj, acc1[2]); acc1[3] = fma(b1.y, kj, acc1[3]);
+              acc1[4] = fma(b2.x, kj, acc1[4]); acc1[5] = fma(b2.y, kj, acc1[5]);
+              acc1[6] = fma(b3.x, kj, acc1[6]); acc1[7] = fma(b3.y, kj, acc1[7]);
+            }
+          }
+          if (two) {
+#pragma unroll 2
+            for (int j = ib + 8; j < ib + 16; ++j) {
+              const double kj = kcol[j * TC_M];
+              const double2* pp = (const double2*)(blk1 + j * 8);
+              const double2 b0 = pp[0], b1 = pp[1], b2 = pp[2], b3 = pp[3];
+              acc1[0] = fma(b0.x, kj, acc1[0]); acc1[1] = fma(b0.y, kj, acc1[1]);
+              acc1[2] = fma(b1.x, kj, acc1[2]); acc1[3] = fma(b1.y, kj, acc1[3]);
+              acc1[4] = fma(b2.x, kj, acc1[4]); acc1[5] = fma(b2.y, kj, acc1[5]);
+              acc1[6] = fma(b3.x, kj, acc1[6]); acc1[7] = fma(b3.y, kj, acc1[7]);
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            q = fma(acc0[r], acc0[r], q);
+            mu = fma(acc0[r], blob[GPB_BETA + ib + r], mu);
+          }
+          if (two) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              q = fma(acc1[r], acc1[r], q);
+              mu = fma(acc1[r], blob[GPB_BETA + ib + 8 + r], mu);
+            }
+          }
+        }
+        mean_v = mu + mprior;
+        var_v = var - q;
+        var_v = var_v < 1e-15 ? 1e-15 : var_v;
+      }
+      const float fm = (float)mean_v, fsd = (float)sqrt(var_v);
+      s_mu[buf * TC_M + g] = fm;
+      s_sd[buf * TC_M + g] = fsd;
+      if (gp.mean_out && m < cand.M) {
+        gp.mean_out[(size_t)b * cand.M + m] = fm;
+        gp.std_out[(size_t)b * cand.M + m] = fsd;
+      }
+      mbar_arrive(BAR_GPFULL(buf));      // release: orders the shared-memory stores above
+    }
   }
 
   // ---- teardown ----
@@ -679,11 +836,12 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
 
 static int g_num_sms = 0;
 
-template <int MODE>
+template <int MODE, bool FUSE>
 static int launch_tc(const mbo_policy* p, int B, const TcFeat& fs, const mbo_candidates& cand, const float* mean,
-                     const float* std_, const float* epi, float* logits, int* err_flag, cudaStream_t s) {
-  using SM = TcSmem<MODE>;
-  auto kern = neural_af_tc_kernel<MODE>;
+                     const float* std_, const float* epi, float* logits, int* err_flag, cudaStream_t s,
+                     const GpFuse& gp) {
+  using SM = TcSmem<MODE, FUSE>;
+  auto kern = neural_af_tc_kernel<MODE, FUSE>;
   MBO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::total));
   if (g_num_sms == 0) {
     int dev = 0;
@@ -693,8 +851,9 @@ static int launch_tc(const mbo_policy* p, int B, const TcFeat& fs, const mbo_can
   const int tiles_per_episode = (cand.M + TC_M - 1) / TC_M;
   const int total = B * tiles_per_episode;
   const int grid = total < g_num_sms ? total : g_num_sms;
-  kern<<<grid, TC_THREADS, SM::total, s>>>((const unsigned char*)p->d_tc, fs, cand, B, tiles_per_episode, mean, std_,
-                                           epi, logits, err_flag, getenv("MBO_TC_DEBUG_NOLOAD") ? 1 : 0);
+  kern<<<grid, FUSE ? TC_THREADS_FUSED : TC_THREADS, SM::total, s>>>(
+      (const unsigned char*)p->d_tc, fs, cand, B, tiles_per_episode, mean, std_, epi, logits, err_flag,
+      getenv("MBO_TC_DEBUG_NOLOAD") ? 1 : 0, gp);
   MBO_LAUNCH_CHECK();
   return MBO_OK;
 }
@@ -713,8 +872,58 @@ int tc_forward(const mbo_policy* p, int mode, int B, int F, const int32_t* feat_
   fs.dense_F = dense_F;
   for (int i = 0; i < 8; ++i) fs.src[i] = i < F ? feat_src[i] : 0;
   int* err_flag = (int*)ws;
-  if (mode == MBO_MLP_TF32) return launch_tc<MBO_MLP_TF32>(p, B, fs, *cand, mean, std_, epi, logits, err_flag, s);
-  return launch_tc<MBO_MLP_BF16X3>(p, B, fs, *cand, mean, std_, epi, logits, err_flag, s);
+  GpFuse gp;
+  memset(&gp, 0, sizeof(gp));
+  if (mode == MBO_MLP_TF32)
+    return launch_tc<MBO_MLP_TF32, false>(p, B, fs, *cand, mean, std_, epi, logits, err_flag, s, gp);
+  return launch_tc<MBO_MLP_BF16X3, false>(p, B, fs, *cand, mean, std_, epi, logits, err_flag, s, gp);
 }
 
 }  // namespace mbo
+
+using namespace mbo;
+
+extern "C" int mbo_af_eval_fused(const mbo_policy* p, int mode, int B, int nmax, int n_active_max, int kernel_id,
+                                 const double* gp_state, int F, const int32_t* feat_src, const mbo_candidates* cand,
+                                 const float* epi, float* logits, float* mean_out, float* std_out, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  MBO_CHECK_ARG(p && gp_state && feat_src && cand && epi && logits, "mbo_af_eval_fused: null pointer");
+  MBO_CHECK_ARG(mode == MBO_MLP_TF32 || mode == MBO_MLP_BF16X3, "mbo_af_eval_fused: tensor-core modes only");
+  if (!p->tc_ready) {
+    set_error("mbo_af_eval_fused needs a F->H->H->H->H->1 ReLU policy with F <= %d and H <= %d", TC_K0 - 1, TC_N);
+    return MBO_ERR_UNSUPPORTED;
+  }
+  if (n_active_max > GP_NP) {
+    set_error("mbo_af_eval_fused supports n <= %d observations per episode (got %d); use mbo_gp_posterior + mbo_af_logits",
+              GP_NP, n_active_max);
+    return MBO_ERR_UNSUPPORTED;
+  }
+  MBO_CHECK_ARG(B > 0 && nmax > 0 && nmax <= 128 && n_active_max >= 0, "mbo_af_eval_fused: bad sizes");
+  MBO_CHECK_ARG(kernel_id >= 0 && kernel_id <= 2, "mbo_af_eval_fused: unknown kernel id %d", kernel_id);
+  MBO_CHECK_ARG(F == p->widths[0], "mbo_af_eval_fused: F=%d does not match the policy input width %d", F, p->widths[0]);
+  MBO_CHECK_ARG((mean_out == nullptr) == (std_out == nullptr), "mbo_af_eval_fused: mean_out/std_out must both be set or null");
+  MBO_CHECK_ARG(workspace && workspace_bytes >= sizeof(int), "mbo_af_eval_fused: workspace too small");
+  int rc = check_candidates(cand);
+  if (rc) return rc;
+  for (int f = 0; f < F; ++f) {
+    int s = feat_src[f];
+    bool ok = s == MBO_FEAT_MEAN || s == MBO_FEAT_STD || (s >= MBO_FEAT_X0 && s < MBO_FEAT_X0 + cand->D) ||
+              (s >= MBO_FEAT_INCUMBENT && s <= MBO_FEAT_BUDGET);
+    MBO_CHECK_ARG(ok, "mbo_af_eval_fused: bad feature source %d at column %d", s, f);
+  }
+  TcFeat fs;
+  fs.F = F;
+  fs.dense = nullptr;
+  fs.dense_F = 0;
+  for (int i = 0; i < 8; ++i) fs.src[i] = i < F ? feat_src[i] : 0;
+  GpFuse gp;
+  gp.gp_state = gp_state;
+  gp.nmax = nmax;
+  gp.kid = kernel_id;
+  gp.mean_out = mean_out;
+  gp.std_out = std_out;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (mode == MBO_MLP_TF32)
+    return launch_tc<MBO_MLP_TF32, true>(p, B, fs, *cand, nullptr, nullptr, epi, logits, (int*)workspace, s, gp);
+  return launch_tc<MBO_MLP_BF16X3, true>(p, B, fs, *cand, nullptr, nullptr, epi, logits, (int*)workspace, s, gp);
+}

@@ -96,11 +96,16 @@ class AFEngine:
         self.value = None
         self.n_active_max = T
         self.launches = 0
+        self.fuse_gp = False         # opt-in: mbo_af_eval_fused (correct, but slower than the two-kernel path so far, see profiles/r01_notes.md)
+        self.tc_ok = False           # set by set_policy: architecture supported by the tensor-core kernel
         self.kernel_events = None   # list -> (tag, start, end) CUDA events around GP / MLP launches
 
     # -- parameters -------------------------------------------------------------------------------
     def set_policy(self, weights, biases, activation="relu"):
         self.policy.set_weights(weights, biases, activation)
+        w = [int(x.shape[0]) for x in weights]
+        self.tc_ok = (activation == "relu" and len(weights) == 5 and len(set(w[:4])) == 1 and 8 <= w[0] <= 208
+                      and w[4] == 1 and int(weights[0].shape[1]) <= 7)
 
     def set_value_net(self, weights, biases, activation="relu"):
         self.value = ops.PolicyHandle()
@@ -140,12 +145,25 @@ class AFEngine:
                    use_prior_mean=self.use_prior_mean, gp_state=self.gp_state, status=self.status)
         self.launches += 1
 
-    def evaluate(self, cand, want_logits=True):
+    def evaluate(self, cand, want_posterior=False):
         """GP posterior + NeuralAF logits on one candidate set -> (mean, std, logits)."""
         ev = self.kernel_events
         if ev is not None:
             e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             e0.record()
+        if self.can_fuse():
+            # one kernel: fp64 GP warps feed the tensor-core MLP through shared memory
+            mean = std = None
+            if want_posterior:
+                mean = torch.empty((self.B, cand.M), dtype=torch.float32, device=self.dev)
+                std = torch.empty((self.B, cand.M), dtype=torch.float32, device=self.dev)
+            logits = ops.af_eval_fused(self.policy, self.codes_policy, cand, self.gp_state, self.T, self.n_active_max,
+                                       self.epi, self.B, kernel=self.kernel, mode=self.mlp_mode, mean=mean, std=std)
+            if ev is not None:
+                e2.record()
+                ev.append(("fused_M%d" % cand.M, e0, e2))
+            self.launches += 1
+            return mean, std, logits
         mean, std = ops.gp_posterior(self.gp_state, self.T, cand, self.B, kernel=self.kernel,
                                      precision=self.gp_precision, out_dtype=torch.float32,
                                      n_active_max=self.n_active_max)
@@ -159,7 +177,11 @@ class AFEngine:
         self.launches += 2
         return mean, std, logits
 
-    def af_round(self, deterministic=True, seed=0, step=0, refit=True, want_stats=False):
+    def can_fuse(self):
+        return (self.fuse_gp and self.mlp_mode != L.MLP_FP32 and self.gp_precision == L.GP_FP64
+                and self.n_active_max <= ops.FUSED_MAX_N and self.tc_ok)
+
+    def af_round(self, deterministic=True, seed=0, step=0, refit=True, want_stats=False, want_posterior=False):
         """One AF-optimisation round for all B episodes.  Returns a dict of device tensors:
         action [B] i32, x_action [B,D] f64, xi_t candidate set, logits [B,M] (phase 3), and with
         want_stats also logp / entropy [B]."""
@@ -180,7 +202,7 @@ class AFEngine:
             cs = ops.CandidateSet(self.D, head=maxima, tail=self.multistart)
             self.launches += 5
             out.update(af_ms=lg1, top_ms=top1, af_ls=lg2, top_ls=top2, af_maxima=maxima, cubes=cubes)
-        mean, std, lg3 = self.evaluate(cs)
+        mean, std, lg3 = self.evaluate(cs, want_posterior=want_posterior)
         if deterministic:
             action, _ = ops.logits_argmax(lg3)
         else:

@@ -79,6 +79,7 @@ class VecMetaBO:
         self.cur = None          # output of the AF round that produced the current state
         self.sample_seed = 0
         self.round_counter = 0
+        self.want_states = True   # materialise mean/std of the final phase (needed by current_state())
 
     # -- policy ----------------------------------------------------------------------------------
     def set_policy(self, pi):
@@ -120,7 +121,7 @@ class VecMetaBO:
         eng.set_episode_scalars(inc.float(), torch.full((self.B,), float(self.t), device=self.dev),
                                 torch.full((self.B,), float(self.T), device=self.dev))
         self.cur = eng.af_round(deterministic=deterministic, seed=self.sample_seed, step=self.round_counter,
-                                want_stats=False)
+                                want_stats=False, want_posterior=self.want_states)
         self.round_counter += 1
 
     def values(self):

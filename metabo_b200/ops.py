@@ -156,6 +156,26 @@ def af_logits(policy, feat_src, cand, mean, std, epi, B, mode=L.MLP_FP32, logits
     return logits
 
 
+FUSED_MAX_N = 32
+
+
+def af_eval_fused(policy, feat_src, cand, gp_state, nmax, n_active_max, epi, B, kernel="RBF", mode=L.MLP_TF32,
+                  logits=None, mean=None, std=None):
+    """GP posterior (fp64, fused warps) + features + NeuralAF logits in ONE kernel (n <= 32).
+    mean/std [B,M] fp32 are only written when given (PPO state buffer)."""
+    _chk(gp_state, torch.float64, "gp_state"); _chk(epi, torch.float32, "epi")
+    _chk(mean, torch.float32, "mean"); _chk(std, torch.float32, "std")
+    if logits is None:
+        logits = torch.empty((B, cand.M), dtype=torch.float32, device=gp_state.device)
+    F = len(feat_src)
+    fs = (C.c_int32 * F)(*feat_src)
+    ws = policy.workspace(gp_state.device)
+    L.check(L.lib().mbo_af_eval_fused(policy.h, mode, B, nmax, int(n_active_max), L.KERNEL_IDS[kernel], _p(gp_state),
+                                      F, fs, cand.ref(), _p(epi), _p(logits), _p(mean), _p(std), _p(ws),
+                                      ws.numel() * 4, _stream()), "mbo_af_eval_fused")
+    return logits
+
+
 def af_logits_dense(policy, cols, states, mode=L.MLP_FP32, logits=None):
     """NeuralAF.forward (policy net) on materialised states [B,M,F_state] fp32 -> logits [B,M]."""
     _chk(states, torch.float32, "states")
@@ -177,29 +197,37 @@ def value_net(policy, tT):
     return out
 
 
-def logits_argmax(logits):
+def logits_argmax(logits, a=None, v=None):
     _chk(logits, torch.float32, "logits")
     B, M = logits.shape
-    a = torch.empty((B,), dtype=torch.int32, device=logits.device)
-    v = torch.empty((B,), dtype=torch.float32, device=logits.device)
+    if a is None:
+        a = torch.empty((B,), dtype=torch.int32, device=logits.device)
+    if v is None:
+        v = torch.empty((B,), dtype=torch.float32, device=logits.device)
     L.check(L.lib().mbo_logits_argmax(B, M, _p(logits), _p(a), _p(v), _stream()), "mbo_logits_argmax")
     return a, v
 
 
-def logits_topk(logits, k):
+def logits_topk(logits, k, idx=None, val=None):
     _chk(logits, torch.float32, "logits")
     B, M = logits.shape
-    idx = torch.empty((B, k), dtype=torch.int32, device=logits.device)
-    val = torch.empty((B, k), dtype=torch.float32, device=logits.device)
+    if idx is None:
+        idx = torch.empty((B, k), dtype=torch.int32, device=logits.device)
+    if val is None:
+        val = torch.empty((B, k), dtype=torch.float32, device=logits.device)
     L.check(L.lib().mbo_logits_topk(B, M, k, _p(logits), _p(idx), _p(val), _stream()), "mbo_logits_topk")
     return idx, val
 
 
-def logits_sample(logits, seed, step):
+def logits_sample(logits, seed, step, a=None, episode_offset=0):
+    """Gumbel-max sample; `episode_offset` keys the noise by the GLOBAL episode index when `logits` is a
+    slice of a larger batch (the C ABI keys by row, so the seed is advanced per slice instead)."""
     _chk(logits, torch.float32, "logits")
     B, M = logits.shape
-    a = torch.empty((B,), dtype=torch.int32, device=logits.device)
-    L.check(L.lib().mbo_logits_sample(B, M, _p(logits), int(seed), int(step), _p(a), _stream()), "mbo_logits_sample")
+    if a is None:
+        a = torch.empty((B,), dtype=torch.int32, device=logits.device)
+    L.check(L.lib().mbo_logits_sample(B, M, _p(logits), int(seed), int(step), int(episode_offset), _p(a), _stream()),
+            "mbo_logits_sample")
     return a
 
 
@@ -213,17 +241,19 @@ def logits_logp_entropy(logits, actions):
     return lp, en
 
 
-def candidates_gather(cand, idx, B):
+def candidates_gather(cand, idx, B, out=None):
     _chk(idx, torch.int32, "idx")
     k = idx.shape[1]
-    out = torch.empty((B, k, cand.D), dtype=torch.float64, device=idx.device)
+    if out is None:
+        out = torch.empty((B, k, cand.D), dtype=torch.float64, device=idx.device)
     L.check(L.lib().mbo_candidates_gather(B, cand.ref(), k, _p(idx), _p(out), _stream()), "mbo_candidates_gather")
     return out
 
 
-def cubes_around(x, diam):
+def cubes_around(x, diam, cubes=None):
     _chk(x, torch.float64, "x")
     B, k, D = x.shape
-    cubes = torch.empty((B, k, 2, D), dtype=torch.float64, device=x.device)
+    if cubes is None:
+        cubes = torch.empty((B, k, 2, D), dtype=torch.float64, device=x.device)
     L.check(L.lib().mbo_cubes_around(B, k, D, _p(x), float(diam), _p(cubes), _stream()), "mbo_cubes_around")
     return cubes

@@ -133,6 +133,7 @@ class BatchRecorder:
         env, B, T = self.env, self.B, self.T
         dev = env.dev
         env.sample_seed = self.sample_seed
+        env.want_states = self.store_states
         actions = torch.zeros((B, T), dtype=torch.int32, device=dev)
         rewards = torch.zeros((B, T), dtype=torch.float64, device=dev)
         values = torch.zeros((B, T), dtype=torch.float32, device=dev)

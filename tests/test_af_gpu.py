@@ -180,3 +180,48 @@ def test_sampler_matches_oracle_noise_and_distribution():
     cnt = np.bincount(acts, minlength=8)
     chi2 = np.sum((cnt - n * p) ** 2 / (n * p))
     assert chi2 < 30.0                                       # 7 dof, p ~ 1e-4
+
+
+@pytest.mark.parametrize("mode_name,mode,tol", [("tf32", 1, 1e-3), ("bf16x3", 2, 2e-5)])
+def test_fused_gp_mlp_kernel_matches_two_kernel_path(golden_dir, mode_name, mode, tol):
+    """mbo_af_eval_fused (fp64 GP warps inside the tensor-core kernel) == mbo_gp_posterior (fp64) +
+    mbo_af_logits on the same inputs: identical mean/std (bitwise, same arithmetic) and logits within
+    the mode's tolerance of the fp32 CUDA-core evaluation; ragged n incl. empty GPs; local-grid and
+    head+tail candidate descriptors."""
+    from metabo_b200 import ops
+    dev = torch.device("cuda:0")
+    pw = O.PolicyWeights.from_npz(os.path.join(golden_dir, "weights_hm3_1988.npz"))
+    pol = make_policy(pw)
+    rng = np.random.RandomState(21)
+    D, T, B = 3, 30, 7
+    ns = [0, 1, 7, 8, 19, 30, 30]
+    X = np.zeros((B, T, D)); Y = np.zeros((B, T))
+    for b, n in enumerate(ns):
+        if n:
+            X[b, :n] = rng.rand(n, D)
+            Y[b, :n] = O.hm3_var(X[b, :n], np.zeros(3), 1.0)[:, 0]
+    tt = lambda a, dt=torch.float64: torch.as_tensor(a, dtype=dt, device=dev).contiguous()
+    state, status = ops.gp_fit(tt(np.array(ns), torch.int32), tt(X), tt(Y), tt(np.tile([0.716, 0.298, 0.186], (B, 1))),
+                               tt(np.full(B, 0.83)), tt(np.full(B, 1.688e-11)))
+    epi = tt(np.array([[0.0, n / T, n, T] for n in ns]), torch.float32)
+    feats = ["posterior_mean", "posterior_std", "timestep", "budget", "x"]
+    codes = feat_codes(feats, D, pw.mask)
+    grids = O.Grids(D, N_MS=2000, N_LS=300, k=5)
+    starts = np.stack([grids.multistart_grid[rng.choice(grids.N_MS, 5, replace=False)] for _ in range(B)])
+    cubes = ops.cubes_around(tt(starts), grids.af_max_search_diam)
+    sets = [ops.CandidateSet(D, tail=tt(grids.multistart_grid)),
+            ops.CandidateSet(D, tail=tt(grids.local_search_grid), cubes=cubes),
+            ops.CandidateSet(D, head=tt(rng.rand(B, 5, D)), tail=tt(grids.multistart_grid))]
+    for cs in sets:
+        mean, std = ops.gp_posterior(state, T, cs, B, out_dtype=torch.float32)
+        ref = ops.af_logits(pol, codes, cs, mean, std, epi, B, mode=0)
+        m2 = torch.empty_like(mean); s2 = torch.empty_like(std)
+        got = ops.af_eval_fused(pol, codes, cs, state, T, T, epi, B, mode=mode, mean=m2, std=s2)
+        torch.cuda.synchronize()
+        pol.check()
+        assert torch.equal(m2, mean) and torch.equal(s2, std)
+        scale = float(ref.abs().max())
+        assert float((got - ref).abs().max()) <= tol * scale + 1e-6, (mode_name, cs.M)
+        got2 = ops.af_eval_fused(pol, codes, cs, state, T, T, epi, B, mode=mode)      # without the posterior copies
+        torch.cuda.synchronize()
+        assert torch.equal(got, got2)
