@@ -96,6 +96,9 @@ class AFEngine:
         self.value = None
         self.n_active_max = T
         self.launches = 0
+        self.reuse_multistart = False   # phase 3 reuses the phase-1 results of the multistart grid (VecMetaBO turns it on)
+        self.evals_skipped = 0
+        self.episode_offset = 0         # global index of lane 0 (keys the sampler under sharding)
         self.fuse_gp = False         # opt-in: mbo_af_eval_fused (correct, but slower than the two-kernel path so far, see profiles/r01_notes.md)
         self.tc_ok = False           # set by set_policy: architecture supported by the tensor-core kernel
         self.kernel_events = None   # list -> (tag, start, end) CUDA events around GP / MLP launches
@@ -191,7 +194,7 @@ class AFEngine:
         if self.discrete:
             cs = ops.CandidateSet(self.D, tail=self.xi_table)
         else:
-            _, _, lg1 = self.evaluate(self.cs_ms)
+            mean1, std1, lg1 = self.evaluate(self.cs_ms, want_posterior=want_posterior and self.reuse_multistart)
             top1, _ = ops.logits_topk(lg1, self.k)
             starts = ops.candidates_gather(self.cs_ms, top1, self.B)
             cubes = ops.cubes_around(starts, self.diam)
@@ -202,11 +205,22 @@ class AFEngine:
             cs = ops.CandidateSet(self.D, head=maxima, tail=self.multistart)
             self.launches += 5
             out.update(af_ms=lg1, top_ms=top1, af_ls=lg2, top_ls=top2, af_maxima=maxima, cubes=cubes)
-        mean, std, lg3 = self.evaluate(cs, want_posterior=want_posterior)
+        if self.reuse_multistart and not self.discrete:
+            # xi_t = [af_maxima; multistart grid]: the grid part was evaluated in phase 1 with the same GP state,
+            # so only the k new points are evaluated and the phase-1 results are reused (bitwise identical to
+            # re-evaluating them: every candidate row is computed independently of its neighbours)
+            cs_head = ops.CandidateSet(self.D, head=maxima)
+            mh, sh, lgh = self.evaluate(cs_head, want_posterior=want_posterior)
+            lg3 = torch.cat([lgh, lg1], dim=1)
+            mean = torch.cat([mh, mean1], dim=1) if (want_posterior and mean1 is not None) else None
+            std = torch.cat([sh, std1], dim=1) if (want_posterior and std1 is not None) else None
+            self.evals_skipped += self.B * self.N_MS
+        else:
+            mean, std, lg3 = self.evaluate(cs, want_posterior=want_posterior)
         if deterministic:
             action, _ = ops.logits_argmax(lg3)
         else:
-            action = ops.logits_sample(lg3, seed, step)
+            action = ops.logits_sample(lg3, seed, step, episode_offset=self.episode_offset)
         x_action = ops.candidates_gather(cs, action[:, None].contiguous(), self.B)[:, 0]
         self.launches += 2
         out.update(cand=cs, mean=mean, std=std, logits=lg3, action=action, x_action=x_action)

@@ -69,6 +69,7 @@ class VecMetaBO:
             self.engine = AFEngine(B, self.D, self.T, self.features, discrete_domain=grid_np, **common)
             grid = self.engine.xi_table
         self.dev = self.engine.dev
+        self.engine.reuse_multistart = True
         self.cardinality_xi_t = self.engine.M_final
         self.n_features = self.engine.n_features
         self.sampler = FunctionSampler(self.f_type, self.f_opts, self.D, self.dev, discrete_grid=grid)

