@@ -424,10 +424,10 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
   if (tid == 0) {
     *s_abort = 0;
     for (int s = 0; s < NS; ++s) { mbar_init(BAR_WFULL(s), 1); mbar_init(BAR_WEMPTY(s), 1); }
-    for (int c = 0; c < C::NCHUNK; ++c) mbar_init(BAR_AREADY(c), 128);
+    for (int c = 0; c < C::NCHUNK; ++c) mbar_init(BAR_AREADY(c), 4);     // one elected arrive per epilogue warp
     mbar_init(BAR_DFULL(0), 1);
     mbar_init(BAR_DFULL(1), 1);
-    mbar_init(BAR_FEAT, 128);
+    mbar_init(BAR_FEAT, 4);
     mbar_init(BAR_SFREE, 1);
     mbar_init(BAR_W0, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(BAR_GPFULL(i), 128); mbar_init(BAR_GPEMPTY(i), 128); }
@@ -611,7 +611,8 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
       tmem_st8(tlane + COL_S + 16, lo);
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(BAR_FEAT);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR_FEAT);
     };
 
     if (my_tiles > 0 && half == 1) build_features(0);
@@ -638,7 +639,8 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
             ChunkOps<MODE>::convert_store(tlane + col + c * C::CHUNK_COLS, cur, bias + c * C::CHUNK_COLS, ncols_of(c));
             tmem_wait_st();
             tc_fence_before();
-            mbar_arrive(BAR_AREADY(c));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR_AREADY(c));
           }
         }
         if (l == 2 && half == 1) {
