@@ -136,7 +136,7 @@ int mbo_policy_set_weights(mbo_policy* p, int n_layers, const int32_t* widths, i
  *   mean, std     : [B, M] fp32 from mbo_gp_posterior
  *   logits [B, M] fp32.
  * mode MBO_MLP_FP32 supports any architecture; the tensor-core modes need a
- * F->H->H->H->H->1 ReLU net with H <= 208 (the shipped 4x200 policies).
+ * F->H->H->H->H->1 ReLU net with F <= 15 and H <= 208 (the shipped 4x200 policies).
  * ------------------------------------------------------------------------------------- */
 int mbo_af_logits(const mbo_policy* p, int mode, int B, int F, const int32_t* feat_src,
                   const mbo_candidates* cand, const float* mean, const float* std,

@@ -39,7 +39,7 @@ constexpr int TC_THREADS_FUSED = 448;
 constexpr int GP_NP = 32;                 // fused GP: n <= 32 observations
 constexpr int GPB_XS = 16, GPB_BETA = GPB_XS + GP_NP * MBO_MAX_D, GPB_LINV = GPB_BETA + GP_NP;
 constexpr int GPB_DOUBLES = GPB_LINV + 640;   // header | Xs[32][8] | beta[32] | LinvB(4 blocks)
-constexpr int TC_K0 = 8;             // layer-0 K (features + ones column, <= 8)
+constexpr int TC_K0 = 16;            // layer-0 K capacity (features + ones column <= 16); 8 are used when F <= 7
 constexpr int CHUNK_ROW_BYTES = TC_N * 16;   // one 16-byte K chunk for all 208 rows = 3328 B
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t COL_R0 = 0, COL_R1 = 208, COL_S = 416;
@@ -53,7 +53,7 @@ template <> struct ModeCfg<MBO_MLP_TF32> {
   static constexpr int STAGES_PER_LAYER = 5;
   static constexpr int STAGE_BYTES = SLICES_PER_STAGE * 2 * CHUNK_ROW_BYTES;   // 33 280
   static constexpr int NSTAGE = 6;
-  static constexpr int NSTAGE_FUSED = 5;       // fused GP needs 42 KB of shared memory for its scratch
+  static constexpr int NSTAGE_FUSED = 4;       // fused GP needs 42 KB of shared memory for its scratch
   static constexpr int CHUNK_COLS = 40;        // accumulator columns converted per hand-off
   static constexpr int NCHUNK = 5;
 };
@@ -270,7 +270,7 @@ int tc_pack_weights(mbo_policy* p, cudaStream_t s) {
   p->tc_ready = 0;
   if (p->n_layers != 5 || p->activation != MBO_ACT_RELU) return MBO_OK;
   const int F = p->widths[0], H = p->widths[1];
-  if (F + 1 > TC_K0 || H > TC_N || H < 8 || p->widths[5] != 1) return MBO_OK;
+  if (F + 1 > TC_K0 || H > TC_N || H < 8 || p->widths[5] != 1) return MBO_OK;   // F <= 15
   for (int l = 1; l <= 4; ++l)
     if (p->widths[l] != H) return MBO_OK;
   const PackLayout pl = pack_layout();
@@ -296,7 +296,8 @@ int tc_pack_weights(mbo_policy* p, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------
 struct TcFeat {
   int F;
-  int src[8];          // MBO_FEAT_* codes, or state-column indices in dense mode
+  int k0_slices;       // 1: F + 1 <= 8 (one K=8 slice for layer 0), 2: F + 1 <= 16
+  int src[TC_K0];      // MBO_FEAT_* codes, or state-column indices in dense mode
   const float* dense;  // [B, M, dense_F] materialised states, or nullptr
   int dense_F;
 };
@@ -490,9 +491,13 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
         tc_fence_after();
         if (leader) {
           const uint32_t a_hi = tmem + COL_S, a_lo = tmem + COL_S + 16;
-          mma_ts_tf32(tmem + COL_R0, a_hi, make_desc64(w0_lo), IDESC_TF32, 0);
-          mma_ts_tf32(tmem + COL_R0, a_lo, make_desc64(w0_lo), IDESC_TF32, 1);
-          mma_ts_tf32(tmem + COL_R0, a_hi, make_desc64(w0_lo + SLICE_D * (TC_K0 / 8)), IDESC_TF32, 1);
+          constexpr uint32_t W0_PART_D = (uint32_t)((TC_K0 / 4) * CHUNK_ROW_BYTES) >> 4;     // hi -> lo part
+          for (int sl = 0; sl < fs.k0_slices; ++sl) {
+            const uint32_t wl = w0_lo + sl * SLICE_D;
+            mma_ts_tf32(tmem + COL_R0, a_hi + sl * 8, make_desc64(wl), IDESC_TF32, sl ? 1u : 0u);
+            mma_ts_tf32(tmem + COL_R0, a_lo + sl * 8, make_desc64(wl), IDESC_TF32, 1);
+            mma_ts_tf32(tmem + COL_R0, a_hi + sl * 8, make_desc64(wl + W0_PART_D), IDESC_TF32, 1);
+          }
           tc_commit(BAR_SFREE);
           tc_commit(BAR_DFULL(0));
         }
@@ -599,16 +604,21 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
 #pragma unroll
         for (int i = 0; i < TC_K0; ++i) if (i == fs.F) f[i] = 1.0f;    // bias column
       }
-      uint32_t hi[8], lo[8];
+      uint32_t hi[TC_K0], lo[TC_K0];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < TC_K0; ++i) {
         float h = tf32_rna(f[i]);
         hi[i] = __float_as_uint(h);
         lo[i] = __float_as_uint(tf32_rna(f[i] - h));
       }
       if (FUSE) mbar_arrive(BAR_GPEMPTY(t_idx & 1));   // mu/sd of this buffer consumed
-      tmem_st8(tlane + COL_S, hi);
-      tmem_st8(tlane + COL_S + 16, lo);
+      if (fs.k0_slices == 1) {
+        tmem_st8(tlane + COL_S, hi);
+        tmem_st8(tlane + COL_S + 16, lo);
+      } else {
+        tmem_st16(tlane + COL_S, hi);
+        tmem_st16(tlane + COL_S + 16, lo);
+      }
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
@@ -872,7 +882,8 @@ int tc_forward(const mbo_policy* p, int mode, int B, int F, const int32_t* feat_
   fs.F = F;
   fs.dense = dense;
   fs.dense_F = dense_F;
-  for (int i = 0; i < 8; ++i) fs.src[i] = i < F ? feat_src[i] : 0;
+  fs.k0_slices = (F + 1 <= 8) ? 1 : 2;
+  for (int i = 0; i < TC_K0; ++i) fs.src[i] = i < F ? feat_src[i] : 0;
   int* err_flag = (int*)ws;
   GpFuse gp;
   memset(&gp, 0, sizeof(gp));
@@ -917,7 +928,8 @@ extern "C" int mbo_af_eval_fused(const mbo_policy* p, int mode, int B, int nmax,
   fs.F = F;
   fs.dense = nullptr;
   fs.dense_F = 0;
-  for (int i = 0; i < 8; ++i) fs.src[i] = i < F ? feat_src[i] : 0;
+  fs.k0_slices = (F + 1 <= 8) ? 1 : 2;
+  for (int i = 0; i < TC_K0; ++i) fs.src[i] = i < F ? feat_src[i] : 0;
   GpFuse gp;
   gp.gp_state = gp_state;
   gp.nmax = nmax;

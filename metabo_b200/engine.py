@@ -108,7 +108,7 @@ class AFEngine:
         self.policy.set_weights(weights, biases, activation)
         w = [int(x.shape[0]) for x in weights]
         self.tc_ok = (activation == "relu" and len(weights) == 5 and len(set(w[:4])) == 1 and 8 <= w[0] <= 208
-                      and w[4] == 1 and int(weights[0].shape[1]) <= 7)
+                      and w[4] == 1 and int(weights[0].shape[1]) <= 15)
 
     def set_value_net(self, weights, biases, activation="relu"):
         self.value = ops.PolicyHandle()

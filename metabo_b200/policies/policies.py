@@ -112,7 +112,7 @@ class NeuralAF(nn.Module):
     def tensor_core_ok(self):
         a = self.policy_net.arch_spec
         return (self.activation == "relu" and len(a) == 4 and len(set(a)) == 1 and 8 <= a[0] <= 208
-                and self.N_features_policy <= 7)
+                and self.N_features_policy <= 15)
 
     def _values_kernel(self, states):
         if not self.use_value_network:

@@ -271,3 +271,38 @@ def test_sampler_is_invariant_under_sharding():
     part = ops.logits_sample(lg[7:].contiguous(), seed=5, step=3, episode_offset=7).cpu().numpy()
     assert np.array_equal(full[7:], part)
     assert np.array_equal(S.sample(lg.cpu().numpy(), 5, 3), full) or True   # oracle noise differs by <= 1 ulp of logf
+
+
+@pytest.mark.parametrize("D", [4, 6])
+def test_tensor_core_kernel_with_wide_feature_vectors(D):
+    """F = D + 4 features (8 and 10 > 7) take the two-slice layer-0 path of the tcgen05 kernel."""
+    from metabo_b200 import ops, _lib as L
+    dev = torch.device("cuda:0")
+    rng = np.random.RandomState(D)
+    F = D + 4
+    dims = [F, 200, 200, 200, 200, 1]
+    W = [torch.as_tensor(rng.normal(0, 0.08, (dims[i + 1], dims[i])).astype(np.float32), device=dev) for i in range(5)]
+    b = [torch.as_tensor(rng.normal(0, 0.05, dims[i + 1]).astype(np.float32), device=dev) for i in range(5)]
+    pol = ops.PolicyHandle(); pol.set_weights(W, b, "relu")
+    B, M = 3, 777
+    cs = ops.CandidateSet(D, tail=torch.as_tensor(rng.rand(M, D), device=dev))
+    mean = torch.as_tensor(rng.randn(B, M).astype(np.float32), device=dev)
+    std = torch.as_tensor(rng.rand(B, M).astype(np.float32), device=dev)
+    epi = torch.as_tensor(np.array([[0.1, 0.2, 6.0, 30.0]] * B, dtype=np.float32), device=dev)
+    codes = [L.FEAT_MEAN, L.FEAT_STD] + [L.FEAT_X0 + d for d in range(D)] + [L.FEAT_TIMESTEP, L.FEAT_BUDGET]
+    ref = ops.af_logits(pol, codes, cs, mean, std, epi, B, mode=0)
+    # torch fp64 ground truth of the same network
+    x = cs.tail.float()[None].expand(B, M, D)
+    feats = torch.cat([mean[..., None], std[..., None], x, epi[:, None, 2:3].expand(B, M, 1), epi[:, None, 3:4].expand(B, M, 1)], 2).double()
+    h = feats
+    for i in range(4):
+        h = torch.relu(h @ W[i].double().T + b[i].double())
+    truth = (h @ W[4].double().T + b[4].double())[..., 0]
+    scale = float(truth.abs().max())
+    assert float((ref.double() - truth).abs().max()) <= 1e-5 * scale
+    # random N(0, 0.08) nets cancel heavily (|logit| ~ 0.3 from O(1) hidden activations): TF32's operand rounding is
+    # then ~4e-3 of max|logit|; the 1e-3 bar is stated (and tested above) on the shipped policies
+    for mode, tol in ((1, 1e-2), (2, 2e-5)):
+        got = ops.af_logits(pol, codes, cs, mean, std, epi, B, mode=mode)
+        torch.cuda.synchronize(); pol.check()
+        assert float((got.double() - truth).abs().max()) <= tol * scale, (D, mode)
