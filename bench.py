@@ -353,8 +353,15 @@ def main():
     if mlp_big:
         dur = float(np.mean(mlp_big)) / 1e3
         ach = B * HM3["k"] * HM3["N_LS"] * MLP_FLOPS / dur / 1e12
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tp) and B == 1024:
+            tj = json.load(open(tp)).get(args.mlp)
+            if tj:
+                traffic = tj["dram_read_bytes"] + tj["dram_write_bytes"]     # one ncu --set full capture of this launch shape
         roof = {"bound": "tensor", "kernel": "NeuralAF MLP (%s), B x 10000 local-grid candidates" % args.mlp,
-                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
+                "traffic_unit": "bytes per launch (dram read+write, ncu)",
                 "peak_source": peak_src, "avg_launch_ms": dur * 1e3,
                 "format_ceiling_frac": {"tf32": 0.5, "bf16x3": 1.0 / 3.0, "fp32": None}[args.mlp]}
         if gp_big:
