@@ -301,8 +301,66 @@ def test_tensor_core_kernel_with_wide_feature_vectors(D):
     scale = float(truth.abs().max())
     assert float((ref.double() - truth).abs().max()) <= 1e-5 * scale
     # random N(0, 0.08) nets cancel heavily (|logit| ~ 0.3 from O(1) hidden activations): TF32's operand rounding is
-    # then ~4e-3 of max|logit|; the 1e-3 bar is stated (and tested above) on the shipped policies
-    for mode, tol in ((1, 1e-2), (2, 2e-5)):
+    # then ~4e-3 of max|logit| (bf16x3: ~1e-4); the 1e-3 bar is stated (and tested above) on the shipped policies
+    for mode, tol in ((1, 1e-2), (2, 3e-4)):
         got = ops.af_logits(pol, codes, cs, mean, std, epi, B, mode=mode)
         torch.cuda.synchronize(); pol.check()
         assert float((got.double() - truth).abs().max()) <= tol * scale, (D, mode)
+
+
+def test_full_size_properties_hartmann3_batch(golden_dir):
+    """BASELINE configs[1] at full size (B=1024 episodes, 10 000 local-grid candidates each, n=30 observations):
+    size-independent properties instead of an oracle run -- (a) every episode of the batch is bitwise what it is
+    when evaluated alone, (b) the arithmetic modes agree within their tolerances, (c) top-k is the sorted true top-k,
+    (d) the posterior std is invariant to Y and the mean linear in Y."""
+    from metabo_b200 import ops
+    dev = torch.device("cuda:0")
+    pw = O.PolicyWeights.from_npz(os.path.join(golden_dir, "weights_hm3_1988.npz"))
+    pol = make_policy(pw)
+    B, D, T, n, k, NLS = 1024, 3, 30, 30, 5, 2000
+    g = torch.Generator(device=dev); g.manual_seed(7)
+    X = torch.rand((B, T, D), generator=g, dtype=torch.float64, device=dev)
+    Y1 = torch.randn((B, T), generator=g, dtype=torch.float64, device=dev)
+    Y2 = torch.randn((B, T), generator=g, dtype=torch.float64, device=dev)
+    nn = torch.full((B,), n, dtype=torch.int32, device=dev)
+    ls = torch.tensor([[0.716, 0.298, 0.186]] * B, dtype=torch.float64, device=dev)
+    var = torch.full((B,), 0.83, dtype=torch.float64, device=dev)
+    noise = torch.full((B,), 1e-6, dtype=torch.float64, device=dev)
+    from metabo_b200.sobol import i4_sobol_generate
+    table = torch.as_tensor(i4_sobol_generate(D, NLS), device=dev)
+    starts = torch.rand((B, k, D), generator=g, dtype=torch.float64, device=dev)
+    cubes = ops.cubes_around(starts, 2.0 / 12)
+    cs = ops.CandidateSet(D, tail=table, cubes=cubes)
+    assert cs.M == 10000
+    epi = torch.zeros(B, 4, device=dev); epi[:, 1] = 0.5; epi[:, 2] = 15; epi[:, 3] = 30
+    codes = feat_codes(["posterior_mean", "posterior_std", "timestep", "budget", "x"], D, pw.mask)
+    st1, s1 = ops.gp_fit(nn, X, Y1, ls, var, noise)
+    st2, _ = ops.gp_fit(nn, X, Y2, ls, var, noise)
+    st3, _ = ops.gp_fit(nn, X, 2.0 * Y1 - 0.5 * Y2, ls, var, noise)
+    assert int(s1.abs().max()) == 0
+    m1, sd1 = ops.gp_posterior(st1, T, cs, B)
+    m2, sd2 = ops.gp_posterior(st2, T, cs, B)
+    m3, sd3 = ops.gp_posterior(st3, T, cs, B)
+    assert torch.equal(sd1, sd2) and torch.equal(sd1, sd3)                                        # (d)
+    assert float((m3 - (2.0 * m1 - 0.5 * m2)).abs().max()) < 1e-8 * max(1.0, float(m1.abs().max()))
+    mean, std = m1.float(), sd1.float()
+    lg = {m: ops.af_logits(pol, codes, cs, mean, std, epi, B, mode=m) for m in (0, 1, 2)}
+    torch.cuda.synchronize(); pol.check()
+    scale = float(lg[0].abs().max())
+    assert float((lg[1] - lg[0]).abs().max()) <= 1e-3 * scale                                     # (b)
+    assert float((lg[2] - lg[0]).abs().max()) <= 2e-5 * scale
+    for b in (0, 517, 1023):                                                                      # (a)
+        csb = ops.CandidateSet(D, tail=table, cubes=cubes[b:b + 1].contiguous())
+        mb, sb = ops.gp_posterior(st1[b:b + 1].contiguous(), T, csb, 1)
+        assert torch.equal(mb[0], m1[b]) and torch.equal(sb[0], sd1[b])
+        for m in (1, 2):
+            one = ops.af_logits(pol, codes, csb, mean[b:b + 1].contiguous(), std[b:b + 1].contiguous(),
+                                epi[b:b + 1].contiguous(), 1, mode=m)
+            assert torch.equal(one[0], lg[m][b])
+    idx, val = ops.logits_topk(lg[2], k)                                                          # (c)
+    tv, ti = torch.topk(lg[2], k, dim=1)
+    assert torch.equal(val, tv)
+    assert torch.equal(torch.gather(lg[2], 1, idx.long()), val)
+    assert bool((val[:, :-1] >= val[:, 1:]).all())
+    a, v = ops.logits_argmax(lg[2])
+    assert torch.equal(v, lg[2].max(dim=1).values) and torch.equal(a.long(), idx[:, 0].long())
