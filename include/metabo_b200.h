@@ -144,6 +144,15 @@ int mbo_af_logits(const mbo_policy* p, int mode, int B, int F, const int32_t* fe
                   void* stream);
 size_t mbo_af_workspace_bytes(int mode, int B, int M);
 
+/* NeuralAF evaluation with the top-k selection of get_af_maxima (metabo_gym.py:709,719) fused into the
+ * tensor-core kernel's epilogue: every epilogue warp emits its k best (logit, index) pairs, a merge kernel
+ * reduces them per episode -> topk_idx / topk_val [B,k] (value descending, ties by lowest index, k <= 8).
+ * `logits` may be null: then the M logits of an episode never reach HBM. */
+int mbo_af_topk(const mbo_policy* p, int mode, int B, int F, const int32_t* feat_src,
+                const mbo_candidates* cand, const float* mean, const float* std, const float* epi, int k,
+                int32_t* topk_idx, float* topk_val, float* logits, void* workspace, size_t workspace_bytes,
+                void* stream);
+
 /* Same network on an already materialised state tensor (NeuralAF.forward on arbitrary input,
  * policies.py:104-115; the PPO update re-evaluates stored states, ppo.py:148):
  *   states [B, M, F_state] fp32, cols[F] = state column feeding policy input i (the boolean

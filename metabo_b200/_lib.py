@@ -39,6 +39,8 @@ SYMBOLS = [
     ("mbo_af_logits", _i, [_vp, _i, _i, _i, C.POINTER(C.c_int32), C.POINTER(Candidates), _vp, _vp, _vp, _vp, _vp,
                            _sz, _vp]),
     ("mbo_af_workspace_bytes", _sz, [_i, _i, _i]),
+    ("mbo_af_topk", _i, [_vp, _i, _i, _i, C.POINTER(C.c_int32), C.POINTER(Candidates), _vp, _vp, _vp, _i, _vp, _vp, _vp,
+                         _vp, _sz, _vp]),
     ("mbo_af_logits_dense", _i, [_vp, _i, _i, _i, _i, _i, C.POINTER(C.c_int32), _vp, _vp, _vp, _sz, _vp]),
     ("mbo_af_eval_fused", _i, [_vp, _i, _i, _i, _i, _i, _vp, _i, C.POINTER(C.c_int32), C.POINTER(Candidates), _vp, _vp,
                                _vp, _vp, _vp, _sz, _vp]),

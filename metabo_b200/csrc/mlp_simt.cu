@@ -179,15 +179,46 @@ int simt_forward(const mbo_policy* p, int B, int F, const int32_t* feat_src, con
 
 int tc_forward(const mbo_policy* p, int mode, int B, int F, const int32_t* feat_src, const mbo_candidates* cand,
                const float* mean, const float* std_, const float* epi, float* logits, void* ws, size_t ws_bytes,
-               cudaStream_t s, const float* dense = nullptr, int dense_F = 0);   // neural_af_tc.cu
+               cudaStream_t s, const float* dense = nullptr, int dense_F = 0, int topk = 0, int32_t* topk_idx = nullptr,
+               float* topk_val = nullptr);   // neural_af_tc.cu
+size_t tc_workspace_bytes(int B, int M);
 
 }  // namespace mbo
 
 using namespace mbo;
 
 extern "C" size_t mbo_af_workspace_bytes(int mode, int B, int M) {
-  (void)mode; (void)B; (void)M;
-  return 256;
+  if (mode == MBO_MLP_FP32) return 256;
+  return tc_workspace_bytes(B, M);     // error flag + per-warp top-k partial lists of the fused epilogue
+}
+
+static int check_af_args(const char* who, const mbo_policy* p, int B, int F, const int32_t* feat_src,
+                         const mbo_candidates* cand, const float* mean, const float* std_, const float* epi) {
+  MBO_CHECK_ARG(p && p->n_layers > 0, "%s: policy has no weights", who);
+  MBO_CHECK_ARG(B > 0 && cand && mean && std_ && epi && feat_src, "%s: null pointer", who);
+  MBO_CHECK_ARG(F == p->widths[0] && F <= MBO_MAX_FEATURES, "%s: F=%d does not match the policy input width %d", who, F, p->widths[0]);
+  MBO_CHECK_ARG(p->widths[p->n_layers] == 1, "%s: policy head must have one output", who);
+  int rc = check_candidates(cand);
+  if (rc) return rc;
+  for (int f = 0; f < F; ++f) {
+    int s = feat_src[f];
+    bool ok = s == MBO_FEAT_MEAN || s == MBO_FEAT_STD || (s >= MBO_FEAT_X0 && s < MBO_FEAT_X0 + cand->D) ||
+              (s >= MBO_FEAT_INCUMBENT && s <= MBO_FEAT_BUDGET);
+    MBO_CHECK_ARG(ok, "%s: bad feature source %d at column %d", who, s, f);
+  }
+  return MBO_OK;
+}
+
+extern "C" int mbo_af_topk(const mbo_policy* p, int mode, int B, int F, const int32_t* feat_src,
+                           const mbo_candidates* cand, const float* mean, const float* std_, const float* epi, int k,
+                           int32_t* topk_idx, float* topk_val, float* logits, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+  int rc = check_af_args("mbo_af_topk", p, B, F, feat_src, cand, mean, std_, epi);
+  if (rc) return rc;
+  MBO_CHECK_ARG(mode == MBO_MLP_TF32 || mode == MBO_MLP_BF16X3, "mbo_af_topk: tensor-core modes only (use mbo_af_logits + mbo_logits_topk)");
+  MBO_CHECK_ARG(topk_idx && k >= 1, "mbo_af_topk: bad k / null output");
+  return tc_forward(p, mode, B, F, feat_src, cand, mean, std_, epi, logits, workspace, workspace_bytes,
+                    (cudaStream_t)stream, nullptr, 0, k, topk_idx, topk_val);
 }
 
 extern "C" int mbo_af_logits(const mbo_policy* p, int mode, int B, int F, const int32_t* feat_src,

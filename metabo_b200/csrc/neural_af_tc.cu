@@ -384,12 +384,20 @@ struct GpFuse {
   float* std_out;
 };
 
+// fused top-k epilogue: every epilogue warp (32 candidate rows) emits its k best (logit, index) pairs into
+// part_val / part_idx [(episode * tiles_per_episode + tile) * 4 + quad][8]; topk_merge_kernel reduces them per episode
+struct TcTopk {
+  int k;                 // 0 = off, else 1..8
+  float* part_val;
+  int32_t* part_idx;
+};
+
 template <int MODE, bool FUSE>
 __global__ void __launch_bounds__(FUSE ? TC_THREADS_FUSED : TC_THREADS, 1)
 neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candidates cand, int B,
                     int tiles_per_episode, const float* __restrict__ mean, const float* __restrict__ std_,
                     const float* __restrict__ epi, float* __restrict__ logits, int* __restrict__ err_flag, int debug_noload,
-                    GpFuse gp) {
+                    GpFuse gp, TcTopk tk) {
   using C = ModeCfg<MODE>;
   using SM = TcSmem<MODE, FUSE>;
   constexpr int NTHREADS = FUSE ? TC_THREADS_FUSED : TC_THREADS;
@@ -697,15 +705,42 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
         }
       }
       tc_fence_before();   // order this tile's TMEM reads before the next hand-offs
+      float lgt = 0.f;
+      int tile_m = 0x7fffffff, tile_id = 0;
       if (half == 1) s_part[row] = acc;
       asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
       if (half == 0) {
         const int tile = (int)blockIdx.x + t * (int)gridDim.x;
         const int b = tile / tiles_per_episode;
         const int m = (tile - b * tiles_per_episode) * TC_M + row;
-        if (m < cand.M) logits[(size_t)b * cand.M + m] = acc + s_part[row] + s_tail[5 * TC_N];
+        lgt = acc + s_part[row] + s_tail[5 * TC_N];
+        tile_m = m;
+        tile_id = tile;
+        if (logits && m < cand.M) logits[(size_t)b * cand.M + m] = lgt;
       }
       asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");   // s_part reusable
+      if (tk.k && half == 0) {
+        // warp top-k over this warp's 32 rows (value descending, index ascending; NaN / padding never win), off the
+        // pair barrier's critical path; two REDUX per round on an order-preserving integer key
+        const bool valid = tile_m < cand.M && lgt == lgt;
+        const uint32_t u = __float_as_uint(lgt + 0.0f);                                 // -0 -> +0 (compare equal as floats)
+        uint32_t key = valid ? ((u & 0x80000000u) ? ~u : (u | 0x80000000u)) : 0u;     // 0 < every valid key
+        int mi = valid ? tile_m : 0x7fffffff;
+        uint32_t outk = 0u;
+        int outm = 0x7fffffff;
+        for (int r = 0; r < tk.k; ++r) {
+          const uint32_t bk = __reduce_max_sync(0xffffffffu, key);
+          const int bm = __reduce_min_sync(0xffffffffu, key == bk ? mi : 0x7fffffff);
+          if (lane == r) { outk = bk; outm = bm; }
+          if (mi == bm) { key = 0u; mi = 0x7fffffff; }
+        }
+        if (lane < tk.k) {
+          const size_t p = ((size_t)tile_id * 4 + quad) * 8 + lane;
+          const uint32_t uo = (outk & 0x80000000u) ? (outk & 0x7fffffffu) : ~outk;
+          tk.part_val[p] = outk ? __uint_as_float(uo) : -INFINITY;
+          tk.part_idx[p] = outk ? outm : 0x7fffffff;
+        }
+      }
     }
   } else if (FUSE) {
     // ================= fused GP posterior warps (fp64): thread = candidate row of the NEXT tile =================
@@ -846,12 +881,55 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
   }
 }
 
+// per episode: merge the 4 * tiles_per_episode warp partial lists into the episode's top-k
+__global__ void __launch_bounds__(128)
+topk_merge_kernel(int n_lists, int k, const float* __restrict__ part_val, const int32_t* __restrict__ part_idx,
+                  int32_t* __restrict__ out_idx, float* __restrict__ out_val) {
+  __shared__ float sv[4];
+  __shared__ int si[4];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const float* pv = part_val + (size_t)b * n_lists * 8;
+  const int32_t* pi = part_idx + (size_t)b * n_lists * 8;
+  float prev_v = INFINITY;
+  int prev_i = -1;
+  for (int r = 0; r < k; ++r) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int e = tid; e < n_lists * k; e += 128) {
+      const int l = e / k, j = e - l * k;
+      const float v = pv[l * 8 + j];
+      const int i = pi[l * 8 + j];
+      const bool after_prev = (v < prev_v) || (v == prev_v && i > prev_i);
+      if (i != 0x7fffffff && after_prev && (v > bv || (v == bv && i < bi))) { bv = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    __syncthreads();
+    if (lane == 0) { sv[w] = bv; si[w] = bi; }
+    __syncthreads();
+    bv = sv[0]; bi = si[0];
+#pragma unroll
+    for (int q = 1; q < 4; ++q)
+      if (sv[q] > bv || (sv[q] == bv && si[q] < bi)) { bv = sv[q]; bi = si[q]; }
+    if (tid == 0) {
+      out_idx[(size_t)b * k + r] = bi == 0x7fffffff ? 0 : bi;
+      if (out_val) out_val[(size_t)b * k + r] = bv;
+    }
+    prev_v = bv;
+    prev_i = bi;
+  }
+}
+
 static int g_num_sms = 0;
 
 template <int MODE, bool FUSE>
 static int launch_tc(const mbo_policy* p, int B, const TcFeat& fs, const mbo_candidates& cand, const float* mean,
                      const float* std_, const float* epi, float* logits, int* err_flag, cudaStream_t s,
-                     const GpFuse& gp) {
+                     const GpFuse& gp, const TcTopk& tk) {
   using SM = TcSmem<MODE, FUSE>;
   auto kern = neural_af_tc_kernel<MODE, FUSE>;
   MBO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::total));
@@ -865,14 +943,14 @@ static int launch_tc(const mbo_policy* p, int B, const TcFeat& fs, const mbo_can
   const int grid = total < g_num_sms ? total : g_num_sms;
   kern<<<grid, FUSE ? TC_THREADS_FUSED : TC_THREADS, SM::total, s>>>(
       (const unsigned char*)p->d_tc, fs, cand, B, tiles_per_episode, mean, std_, epi, logits, err_flag,
-      getenv("MBO_TC_DEBUG_NOLOAD") ? 1 : 0, gp);
+      getenv("MBO_TC_DEBUG_NOLOAD") ? 1 : 0, gp, tk);
   MBO_LAUNCH_CHECK();
   return MBO_OK;
 }
 
 int tc_forward(const mbo_policy* p, int mode, int B, int F, const int32_t* feat_src, const mbo_candidates* cand,
                const float* mean, const float* std_, const float* epi, float* logits, void* ws, size_t ws_bytes,
-               cudaStream_t s, const float* dense, int dense_F) {
+               cudaStream_t s, const float* dense, int dense_F, int topk, int32_t* topk_idx, float* topk_val) {
   if (!p->tc_ready) {
     set_error("tensor-core NeuralAF path needs a F->H->H->H->H->1 ReLU policy with F <= %d and H <= %d", TC_K0 - 1, TC_N);
     return MBO_ERR_UNSUPPORTED;
@@ -887,9 +965,31 @@ int tc_forward(const mbo_policy* p, int mode, int B, int F, const int32_t* feat_
   int* err_flag = (int*)ws;
   GpFuse gp;
   memset(&gp, 0, sizeof(gp));
+  TcTopk tk;
+  memset(&tk, 0, sizeof(tk));
+  const int tiles = (cand->M + TC_M - 1) / TC_M;
+  const size_t n_part = (size_t)B * tiles * 4 * 8;
+  if (topk) {
+    MBO_CHECK_ARG(topk >= 1 && topk <= 8 && topk <= cand->M && topk_idx, "mbo_af_topk: k must be in 1..min(8, M)");
+    MBO_CHECK_ARG(ws_bytes >= 256 + n_part * 8, "mbo_af_topk: workspace smaller than mbo_af_workspace_bytes()");
+    tk.k = topk;
+    tk.part_val = (float*)((char*)ws + 256);
+    tk.part_idx = (int32_t*)((char*)ws + 256 + n_part * 4);
+  }
+  int rc;
   if (mode == MBO_MLP_TF32)
-    return launch_tc<MBO_MLP_TF32, false>(p, B, fs, *cand, mean, std_, epi, logits, err_flag, s, gp);
-  return launch_tc<MBO_MLP_BF16X3, false>(p, B, fs, *cand, mean, std_, epi, logits, err_flag, s, gp);
+    rc = launch_tc<MBO_MLP_TF32, false>(p, B, fs, *cand, mean, std_, epi, logits, err_flag, s, gp, tk);
+  else
+    rc = launch_tc<MBO_MLP_BF16X3, false>(p, B, fs, *cand, mean, std_, epi, logits, err_flag, s, gp, tk);
+  if (rc || !topk) return rc;
+  topk_merge_kernel<<<B, 128, 0, s>>>(tiles * 4, topk, tk.part_val, tk.part_idx, topk_idx, topk_val);
+  MBO_LAUNCH_CHECK();
+  return MBO_OK;
+}
+
+size_t tc_workspace_bytes(int B, int M) {
+  const int tiles = (M + TC_M - 1) / TC_M;
+  return 256 + (size_t)B * tiles * 4 * 8 * 8;
 }
 
 }  // namespace mbo
@@ -937,7 +1037,9 @@ extern "C" int mbo_af_eval_fused(const mbo_policy* p, int mode, int B, int nmax,
   gp.mean_out = mean_out;
   gp.std_out = std_out;
   cudaStream_t s = (cudaStream_t)stream;
+  TcTopk tk;
+  memset(&tk, 0, sizeof(tk));
   if (mode == MBO_MLP_TF32)
-    return launch_tc<MBO_MLP_TF32, true>(p, B, fs, *cand, nullptr, nullptr, epi, logits, (int*)workspace, s, gp);
-  return launch_tc<MBO_MLP_BF16X3, true>(p, B, fs, *cand, nullptr, nullptr, epi, logits, (int*)workspace, s, gp);
+    return launch_tc<MBO_MLP_TF32, true>(p, B, fs, *cand, nullptr, nullptr, epi, logits, (int*)workspace, s, gp, tk);
+  return launch_tc<MBO_MLP_BF16X3, true>(p, B, fs, *cand, nullptr, nullptr, epi, logits, (int*)workspace, s, gp, tk);
 }

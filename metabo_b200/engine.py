@@ -99,6 +99,8 @@ class AFEngine:
         self.reuse_multistart = False   # phase 3 reuses the phase-1 results of the multistart grid (VecMetaBO turns it on)
         self.evals_skipped = 0
         self.episode_offset = 0         # global index of lane 0 (keys the sampler under sharding)
+        self.fuse_topk = False          # opt-in: top-k selection in the tensor-core kernel epilogue (mbo_af_topk); measured slower, see profiles/r01_notes.md
+        self.keep_phase_logits = False  # also materialise the phase-1/2 logits (parity tests, smoke)
         self.fuse_gp = False         # opt-in: mbo_af_eval_fused (correct, but slower than the two-kernel path so far, see profiles/r01_notes.md)
         self.tc_ok = False           # set by set_policy: architecture supported by the tensor-core kernel
         self.kernel_events = None   # list -> (tag, start, end) CUDA events around GP / MLP launches
@@ -148,6 +150,33 @@ class AFEngine:
                    use_prior_mean=self.use_prior_mean, gp_state=self.gp_state, status=self.status)
         self.launches += 1
 
+    def evaluate_topk(self, cand, k, want_logits=False):
+        """GP posterior + NeuralAF + top-k; on the tensor-core path the selection is fused into the kernel's
+        epilogue and the logits are only written when asked for.  Returns (mean, std, logits or None, idx)."""
+        if self.mlp_mode == L.MLP_FP32 or not self.tc_ok or not self.fuse_topk or self.can_fuse():
+            mean, std, lg = self.evaluate(cand, want_posterior=True)
+            idx, _ = ops.logits_topk(lg, k)
+            self.launches += 1
+            return mean, std, lg, idx
+        ev = self.kernel_events
+        if ev is not None:
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record()
+        mean, std = ops.gp_posterior(self.gp_state, self.T, cand, self.B, kernel=self.kernel,
+                                     precision=self.gp_precision, out_dtype=torch.float32,
+                                     n_active_max=self.n_active_max)
+        if ev is not None:
+            e1.record()
+        lg = torch.empty((self.B, cand.M), dtype=torch.float32, device=self.dev) if want_logits else None
+        idx, _ = ops.af_topk(self.policy, self.codes_policy, cand, mean, std, self.epi, self.B, k, mode=self.mlp_mode,
+                             logits=lg)
+        if ev is not None:
+            e2.record()
+            ev.append(("gp_M%d" % cand.M, e0, e1))
+            ev.append(("mlp_M%d" % cand.M, e1, e2))
+        self.launches += 3
+        return mean, std, lg, idx
+
     def evaluate(self, cand, want_posterior=False):
         """GP posterior + NeuralAF logits on one candidate set -> (mean, std, logits)."""
         ev = self.kernel_events
@@ -194,16 +223,14 @@ class AFEngine:
         if self.discrete:
             cs = ops.CandidateSet(self.D, tail=self.xi_table)
         else:
-            mean1, std1, lg1 = self.evaluate(self.cs_ms, want_posterior=want_posterior and self.reuse_multistart)
-            top1, _ = ops.logits_topk(lg1, self.k)
+            mean1, std1, lg1, top1 = self.evaluate_topk(self.cs_ms, self.k, want_logits=self.reuse_multistart or self.keep_phase_logits)
             starts = ops.candidates_gather(self.cs_ms, top1, self.B)
             cubes = ops.cubes_around(starts, self.diam)
             cs_ls = ops.CandidateSet(self.D, tail=self.local_table, cubes=cubes)
-            _, _, lg2 = self.evaluate(cs_ls)
-            top2, _ = ops.logits_topk(lg2, self.k)
+            _, _, lg2, top2 = self.evaluate_topk(cs_ls, self.k, want_logits=self.keep_phase_logits)
             maxima = ops.candidates_gather(cs_ls, top2, self.B)
             cs = ops.CandidateSet(self.D, head=maxima, tail=self.multistart)
-            self.launches += 5
+            self.launches += 3
             out.update(af_ms=lg1, top_ms=top1, af_ls=lg2, top_ls=top2, af_maxima=maxima, cubes=cubes)
         if self.reuse_multistart and not self.discrete:
             # xi_t = [af_maxima; multistart grid]: the grid part was evaluated in phase 1 with the same GP state,

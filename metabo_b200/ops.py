@@ -123,9 +123,11 @@ class PolicyHandle:
         self.widths = widths
         self._keep = (ws, bs)
 
-    def workspace(self, device):
-        if self.ws is None or self.ws.device != device:
-            self.ws = torch.zeros(64, dtype=torch.int32, device=device)
+    def workspace(self, device, nbytes=256):
+        """word 0 = sticky error flag of the tensor-core kernels; the rest holds top-k partial lists"""
+        n = (int(nbytes) + 3) // 4
+        if self.ws is None or self.ws.device != device or self.ws.numel() < n:
+            self.ws = torch.zeros(max(n, 64), dtype=torch.int32, device=device)
         return self.ws
 
     def check(self):
@@ -157,6 +159,24 @@ def af_logits(policy, feat_src, cand, mean, std, epi, B, mode=L.MLP_FP32, logits
 
 
 FUSED_MAX_N = 32
+
+
+def af_topk(policy, feat_src, cand, mean, std, epi, B, k, mode=L.MLP_TF32, logits=None, idx=None, val=None):
+    """NeuralAF logits + top-k fused in the tensor-core kernel's epilogue -> (idx [B,k] i32, val [B,k] f32).
+    `logits` (optional [B,M] buffer) is only written when given."""
+    _chk(mean, torch.float32, "mean"); _chk(std, torch.float32, "std"); _chk(epi, torch.float32, "epi")
+    _chk(logits, torch.float32, "logits")
+    if idx is None:
+        idx = torch.empty((B, k), dtype=torch.int32, device=mean.device)
+    if val is None:
+        val = torch.empty((B, k), dtype=torch.float32, device=mean.device)
+    F = len(feat_src)
+    fs = (C.c_int32 * F)(*feat_src)
+    nbytes = int(L.lib().mbo_af_workspace_bytes(mode, B, cand.M))
+    ws = policy.workspace(mean.device, nbytes)
+    L.check(L.lib().mbo_af_topk(policy.h, mode, B, F, fs, cand.ref(), _p(mean), _p(std), _p(epi), int(k), _p(idx), _p(val),
+                                _p(logits), _p(ws), ws.numel() * 4, _stream()), "mbo_af_topk")
+    return idx, val
 
 
 def af_eval_fused(policy, feat_src, cand, gp_state, nmax, n_active_max, epi, B, kernel="RBF", mode=L.MLP_TF32,

@@ -364,3 +364,35 @@ def test_full_size_properties_hartmann3_batch(golden_dir):
     assert bool((val[:, :-1] >= val[:, 1:]).all())
     a, v = ops.logits_argmax(lg[2])
     assert torch.equal(v, lg[2].max(dim=1).values) and torch.equal(a.long(), idx[:, 0].long())
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_fused_topk_epilogue_equals_logits_then_topk(golden_dir, mode):
+    """mbo_af_topk (selection inside the tensor-core kernel's epilogue + merge kernel, logits optional) returns
+    exactly what mbo_af_logits followed by mbo_logits_topk returns; ragged M, exact ties, k = 1 and 5."""
+    from metabo_b200 import ops
+    dev = torch.device("cuda:0")
+    pw = O.PolicyWeights.from_npz(os.path.join(golden_dir, "weights_hm3_1988.npz"))
+    pol = make_policy(pw)
+    rng = np.random.RandomState(31)
+    codes = [0, 1, 2, 3, 4, 12, 13]
+    for B, M in ((1, 5), (3, 127), (2, 1733), (16, 10000)):
+        x = rng.rand(M, 3)
+        if M > 300:
+            x[200] = x[7]; x[M - 1] = x[7]                        # duplicated candidates -> exact logit ties
+        cs = ops.CandidateSet(3, tail=torch.as_tensor(x, device=dev))
+        mean = torch.as_tensor(np.tile(rng.randn(1, M), (B, 1)).astype(np.float32), device=dev)
+        std = torch.as_tensor(np.tile(rng.rand(1, M), (B, 1)).astype(np.float32), device=dev)
+        if M > 300:
+            mean[:, 200] = mean[:, 7]; mean[:, M - 1] = mean[:, 7]; std[:, 200] = std[:, 7]; std[:, M - 1] = std[:, 7]
+        epi = torch.as_tensor(np.array([[0.0, 0.3, 9.0, 30.0]] * B, dtype=np.float32), device=dev)
+        lg = ops.af_logits(pol, codes, cs, mean, std, epi, B, mode=mode)
+        for k in (1, min(5, M)):
+            ri, rv = ops.logits_topk(lg, k)
+            lg2 = torch.empty_like(lg)
+            i1, v1 = ops.af_topk(pol, codes, cs, mean, std, epi, B, k, mode=mode, logits=lg2)
+            i2, v2 = ops.af_topk(pol, codes, cs, mean, std, epi, B, k, mode=mode)          # logits never written
+            torch.cuda.synchronize(); pol.check()
+            assert torch.equal(lg2, lg)
+            assert torch.equal(i1, ri) and torch.equal(v1, rv), (B, M, k)
+            assert torch.equal(i2, ri) and torch.equal(v2, rv), (B, M, k)
