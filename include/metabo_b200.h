@@ -186,6 +186,7 @@ int mbo_logits_argmax(int B, int M, const float* logits, int32_t* action, float*
 int mbo_logits_topk(int B, int M, int k, const float* logits, int32_t* idx /*[B,k]*/,
                     float* val /*[B,k]*/, void* stream);
 int mbo_logits_sample(int B, int M, const float* logits, uint64_t seed, uint64_t step,
+                      const uint64_t* step_dev /* optional device counter added to `step` (CUDA-graph replays) */,
                       uint64_t episode_offset /* global index of row 0 */, int32_t* action, void* stream);
 int mbo_logits_logp_entropy(int B, int M, const float* logits, const int32_t* actions,
                             float* logp, float* entropy, void* stream);

@@ -47,7 +47,7 @@ SYMBOLS = [
     ("mbo_value_net", _i, [_vp, _i, _vp, _vp, _vp]),
     ("mbo_logits_argmax", _i, [_i, _i, _vp, _vp, _vp, _vp]),
     ("mbo_logits_topk", _i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
-    ("mbo_logits_sample", _i, [_i, _i, _vp, _u64, _u64, _u64, _vp, _vp]),
+    ("mbo_logits_sample", _i, [_i, _i, _vp, _u64, _u64, _vp, _u64, _vp, _vp]),
     ("mbo_logits_logp_entropy", _i, [_i, _i, _vp, _vp, _vp, _vp, _vp]),
     ("mbo_candidates_gather", _i, [_i, C.POINTER(Candidates), _i, _vp, _vp, _vp]),
     ("mbo_cubes_around", _i, [_i, _i, _i, _vp, _d, _vp, _vp]),

@@ -80,12 +80,13 @@ __device__ __forceinline__ float gumbel_noise(uint64_t key, int m) {
 // k == 1 doubles as argmax.  noise != 0: Gumbel-max sampling (k must be 1).
 __global__ void __launch_bounds__(RT)
 topk_kernel(int M, int k, const float* __restrict__ logits, int noise, uint64_t seed, uint64_t step,
-            uint64_t episode_offset, int32_t* __restrict__ idx, float* __restrict__ val) {
+            const uint64_t* __restrict__ step_dev, uint64_t episode_offset, int32_t* __restrict__ idx,
+            float* __restrict__ val) {
   __shared__ KV sh[RT / 32];
   const int b = blockIdx.x;
   const float* lg = logits + (size_t)b * M;
   uint64_t key = 0;
-  if (noise) key = mix64(mix64(seed + GOLD * (episode_offset + (uint64_t)b + 1)) ^ (step + GOLD));
+  if (noise) key = mix64(mix64(seed + GOLD * (episode_offset + (uint64_t)b + 1)) ^ (step + (step_dev ? *step_dev : 0ull) + GOLD));
   KV prev{INFINITY, -1};
   for (int r = 0; r < k; ++r) {
     KV best{-INFINITY, 0x7fffffff};
@@ -146,7 +147,7 @@ using namespace mbo;
 
 extern "C" int mbo_logits_argmax(int B, int M, const float* logits, int32_t* action, float* max_logit, void* stream) {
   MBO_CHECK_ARG(B > 0 && M > 0 && logits && action, "mbo_logits_argmax: bad argument");
-  topk_kernel<<<B, RT, 0, (cudaStream_t)stream>>>(M, 1, logits, 0, 0, 0, 0, action, max_logit);
+  topk_kernel<<<B, RT, 0, (cudaStream_t)stream>>>(M, 1, logits, 0, 0, 0, nullptr, 0, action, max_logit);
   MBO_LAUNCH_CHECK();
   return MBO_OK;
 }
@@ -154,15 +155,15 @@ extern "C" int mbo_logits_argmax(int B, int M, const float* logits, int32_t* act
 extern "C" int mbo_logits_topk(int B, int M, int k, const float* logits, int32_t* idx, float* val, void* stream) {
   MBO_CHECK_ARG(B > 0 && M > 0 && logits && idx, "mbo_logits_topk: bad argument");
   MBO_CHECK_ARG(k >= 1 && k <= 8 && k <= M, "mbo_logits_topk: k must be in 1..min(8, M)");
-  topk_kernel<<<B, RT, 0, (cudaStream_t)stream>>>(M, k, logits, 0, 0, 0, 0, idx, val);
+  topk_kernel<<<B, RT, 0, (cudaStream_t)stream>>>(M, k, logits, 0, 0, 0, nullptr, 0, idx, val);
   MBO_LAUNCH_CHECK();
   return MBO_OK;
 }
 
 extern "C" int mbo_logits_sample(int B, int M, const float* logits, uint64_t seed, uint64_t step,
-                                 uint64_t episode_offset, int32_t* action, void* stream) {
+                                 const uint64_t* step_dev, uint64_t episode_offset, int32_t* action, void* stream) {
   MBO_CHECK_ARG(B > 0 && M > 0 && logits && action, "mbo_logits_sample: bad argument");
-  topk_kernel<<<B, RT, 0, (cudaStream_t)stream>>>(M, 1, logits, 1, seed, step, episode_offset, action, nullptr);
+  topk_kernel<<<B, RT, 0, (cudaStream_t)stream>>>(M, 1, logits, 1, seed, step, step_dev, episode_offset, action, nullptr);
   MBO_LAUNCH_CHECK();
   return MBO_OK;
 }

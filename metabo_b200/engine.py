@@ -213,7 +213,8 @@ class AFEngine:
         return (self.fuse_gp and self.mlp_mode != L.MLP_FP32 and self.gp_precision == L.GP_FP64
                 and self.n_active_max <= ops.FUSED_MAX_N and self.tc_ok)
 
-    def af_round(self, deterministic=True, seed=0, step=0, refit=True, want_stats=False, want_posterior=False):
+    def af_round(self, deterministic=True, seed=0, step=0, refit=True, want_stats=False, want_posterior=False,
+                 step_dev=None):
         """One AF-optimisation round for all B episodes.  Returns a dict of device tensors:
         action [B] i32, x_action [B,D] f64, xi_t candidate set, logits [B,M] (phase 3), and with
         want_stats also logp / entropy [B]."""
@@ -247,7 +248,7 @@ class AFEngine:
         if deterministic:
             action, _ = ops.logits_argmax(lg3)
         else:
-            action = ops.logits_sample(lg3, seed, step, episode_offset=self.episode_offset)
+            action = ops.logits_sample(lg3, seed, step, episode_offset=self.episode_offset, step_dev=step_dev)
         x_action = ops.candidates_gather(cs, action[:, None].contiguous(), self.B)[:, 0]
         self.launches += 2
         out.update(cand=cs, mean=mean, std=std, logits=lg3, action=action, x_action=x_action)

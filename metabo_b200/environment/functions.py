@@ -20,7 +20,14 @@ def _scale_to_domain(X, domain):
 
 
 class FunctionBatch:
-    """y = f_b(x_b) for every lane b; y_max / y_min per lane (metabo_gym.py:546-547)."""
+    """y = f_b(x_b) for every lane b; y_max / y_min per lane (metabo_gym.py:546-547).
+    The parameter tensors listed in `_tensors` are persistent: a new draw is copied INTO them (`copy_from`), so
+    device pointers stay valid across episodes (CUDA-graph replays of the episode loop read them)."""
+    _tensors = ()
+
+    def copy_from(self, other):
+        for name in self._tensors:
+            getattr(self, name).copy_(getattr(other, name))
 
     def eval(self, x):                                         # x [B, D] fp64 device -> [B]
         raise NotImplementedError
@@ -28,6 +35,7 @@ class FunctionBatch:
 
 class BraninBatch(FunctionBatch):
     D = 2
+    _tensors = ("t", "s", "y_max", "x_max", "y_min")
 
     def __init__(self, t, s, device):
         self.t = torch.as_tensor(np.asarray(t, dtype=np.float64).reshape(-1, 2), device=device)
@@ -42,6 +50,7 @@ class BraninBatch(FunctionBatch):
 
 class Hartmann3Batch(FunctionBatch):
     D = 3
+    _tensors = ("t", "s", "y_max", "x_max", "y_min")
 
     def __init__(self, t, s, device):
         self.t = torch.as_tensor(np.asarray(t, dtype=np.float64).reshape(-1, 3), device=device)
@@ -56,6 +65,7 @@ class Hartmann3Batch(FunctionBatch):
 
 class GPSampleBatch(FunctionBatch):
     """Sparse-spectrum GP samples (objectives.py:239-314): f(x) = sqrt(2 sv / m) * theta . cos(W x + b)."""
+    _tensors = ("W", "b", "theta", "scale", "y_max", "y_min")
 
     def __init__(self, W, b, theta, signal_var, min_regret, device):
         self.W = torch.as_tensor(W, device=device)             # [B, m, D]

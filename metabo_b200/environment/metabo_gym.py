@@ -117,9 +117,9 @@ class MetaBO(gym.Env):
     def step(self, action):
         v = self._vec
         assert v.t < v.T
-        reward, done = v.step(deterministic=True, advance=False, actions=[int(np.asarray(action))])
-        # the reference also evaluates the state after the last step (metabo_gym.py:211-214)
-        v._round(True)
+        reward, done = v.step(deterministic=True, advance=True, actions=[int(np.asarray(action))])
+        if done:   # the reference also evaluates the state after the last step (metabo_gym.py:211-214)
+            v.cur = v._round(v.t, True)
         self._sync_views()
         return self._state(), float(reward[0]), bool(done), {}
 

@@ -79,8 +79,14 @@ class VecMetaBO:
         self.fb = None
         self.cur = None          # output of the AF round that produced the current state
         self.sample_seed = 0
-        self.round_counter = 0
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.dev)   # sampler step counter (device resident)
         self.want_states = True   # materialise mean/std of the final phase (needed by current_state())
+        self.best = torch.full((self.B,), -float("inf"), dtype=torch.float64, device=self.dev)
+        self.reward = torch.zeros((self.B,), dtype=torch.float64, device=self.dev)
+        # CUDA graphs: the device work of "round at t=0" and of "step at time t" is captured once per t and replayed
+        # (the loop is launch-bound for reference-sized batches); opt-in, the BatchRecorder turns it on
+        self.use_graphs = False
+        self._graphs = {}
 
     # -- policy ----------------------------------------------------------------------------------
     def set_policy(self, pi):
@@ -88,7 +94,9 @@ class VecMetaBO:
         the per-step numpy callback of metabo_gym.py:168-174, 708, 718)."""
         self.policy = pi
         self.engine.codes_policy = [c for c, m in zip(self.engine.codes_all, pi.policy_mask()) if m]
+        self._graphs = {}
         self.sync_policy()
+        self.engine.policy.workspace(self.dev, 256)
 
     def sync_policy(self):
         pi = self.policy
@@ -102,30 +110,60 @@ class VecMetaBO:
             self.engine.mlp_mode = L.MLP_FP32
 
     # -- episode control -------------------------------------------------------------------------
+    def _unit(self, key, fn):
+        """Run the device work `fn` eagerly, or (use_graphs) capture it the second time `key` is seen and replay
+        it afterwards.  `fn` must be pure stream work on persistent / graph-owned tensors."""
+        if not self.use_graphs:
+            return fn()
+        ent = self._graphs.get(key)
+        if ent is None:
+            self._graphs[key] = {}
+            return fn()                                   # warm-up run (eager)
+        if "graph" not in ent:
+            torch.cuda.synchronize(self.dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = fn()
+            ent["graph"], ent["out"] = g, out
+        ent["graph"].replay()
+        return ent["out"]
+
     def reset(self, deterministic=True):
         """New objective per lane, empty GP, AF round on the empty GP (MetaBO.reset, :176-193)."""
         eng = self.engine
         self.t = 0
-        self.fb, hyper = self.sampler.draw(self.rngs)
+        fb, hyper = self.sampler.draw(self.rngs)
+        if self.fb is None:
+            self.fb = fb
+        else:
+            self.fb.copy_from(fb)                         # persistent parameter tensors (graph replays read them)
         if hyper is not None:
             eng.set_hyperparameters(np.repeat(hyper[0][:, None], self.D, axis=1), hyper[1], hyper[2])
         else:
             eng.set_hyperparameters(self.fixed_hyper[0], self.fixed_hyper[1], self.fixed_hyper[2])
+        self.cur = self._unit(("round0", deterministic, self.want_states), lambda: self._reset_device(deterministic))
+
+    def _reset_device(self, deterministic):
+        eng = self.engine
         eng.n.zero_()
         eng.n_active_max = 0
-        self.best = torch.full((self.B,), -float("inf"), dtype=torch.float64, device=self.dev)
-        self._round(deterministic)
+        self.best.fill_(-float("inf"))
+        return self._round(0, deterministic)
 
-    def _round(self, deterministic):
+    def _round(self, t, deterministic):
         eng = self.engine
         inc = torch.where(torch.isinf(self.best), self.fb.y_min, self.best)      # metabo_gym.py:723-730
-        eng.set_episode_scalars(inc.float(), torch.full((self.B,), float(self.t), device=self.dev),
+        eng.set_episode_scalars(inc.float(), torch.full((self.B,), float(t), device=self.dev),
                                 torch.full((self.B,), float(self.T), device=self.dev))
-        self.cur = eng.af_round(deterministic=deterministic, seed=self.sample_seed, step=self.round_counter,
-                                want_stats=False, want_posterior=self.want_states)
-        self.round_counter += 1
+        cur = eng.af_round(deterministic=deterministic, seed=self.sample_seed, step=0, step_dev=self.step_dev,
+                           want_stats=False, want_posterior=self.want_states)
+        self.step_dev += 1
+        cur["value"] = self._values()
+        if self.want_states:
+            cur["state"] = eng.state_tensor(cur["cand"], cur["mean"], cur["std"])
+        return cur
 
-    def values(self):
+    def _values(self):
         """value net on (t, T) (policies.py:117-121) for the current state of every lane."""
         if self.engine.value is None:
             return torch.zeros(self.B, device=self.dev)
@@ -136,29 +174,49 @@ class VecMetaBO:
             if not (L.FEAT_INCUMBENT <= code <= L.FEAT_BUDGET):
                 raise NotImplementedError("value net inputs must be per-episode scalar features")
             cols.append(code - L.FEAT_INCUMBENT)
-        return ops.value_net(self.engine.value, self.engine.epi[:, cols].contiguous())
+        epi = self.engine.epi
+        return ops.value_net(self.engine.value, torch.stack([epi[:, cols[0]], epi[:, cols[1]]], dim=1).contiguous())
+
+    def values(self):
+        return self.cur["value"]
 
     def current_state(self):
-        """state [B, M, F] fp32 as get_state packs it (materialised on demand)."""
+        """state [B, M, F] fp32 as get_state packs it"""
+        if "state" in self.cur:
+            return self.cur["state"]
         return self.engine.state_tensor(self.cur["cand"], self.cur["mean"], self.cur["std"])
 
     def step(self, deterministic=True, advance=True, actions=None):
         """Apply the action chosen by the last AF round (or `actions` [B] int32, indices into xi_t).
         Returns (reward [B] f64, done bool)."""
+        t = self.t
+        done = (t + 1) == self.T
+        if actions is not None:
+            out = self._step_device(t, deterministic, advance and not done, self.cur, actions)
+        else:
+            prev = self.cur
+            out = self._unit(("step", t, deterministic, advance and not done, self.want_states),
+                             lambda: self._step_device(t, deterministic, advance and not done, prev, None))
+        self.t = t + 1
+        self.engine.n_active_max = self.t
+        if out.get("cur") is not None:
+            self.cur = out["cur"]
+        return out["reward"], done
+
+    def _step_device(self, t, deterministic, do_round, prev, actions):
         eng = self.engine
         if actions is None:
-            x = self.cur["x_action"]                              # [B, D] fp64
+            x = prev["x_action"]                                  # [B, D] fp64
         else:
             from .. import ops
             a = torch.as_tensor(actions, dtype=torch.int32, device=self.dev).reshape(self.B, 1).contiguous()
-            x = ops.candidates_gather(self.cur["cand"], a, self.B)[:, 0]
+            x = ops.candidates_gather(prev["cand"], a, self.B)[:, 0]
         y = self.fb.eval(x)
-        eng.X[:, self.t] = x
-        eng.Y[:, self.t] = y
-        self.t += 1
-        eng.n.fill_(self.t)
-        eng.n_active_max = self.t
-        self.best = torch.maximum(self.best, y)
+        eng.X[:, t] = x
+        eng.Y[:, t] = y
+        eng.n.fill_(t + 1)
+        eng.n_active_max = t + 1
+        torch.maximum(self.best, y, out=self.best)
         regret = self.fb.y_max - self.best                        # min(y_max - Y)
         if self.reward_transformation == "none":
             reward = regret
@@ -166,7 +224,7 @@ class VecMetaBO:
             reward = -regret
         else:
             reward = -torch.log10(torch.clamp(regret, min=1e-20))
-        done = self.t == self.T
-        if not done and advance:
-            self._round(deterministic)
-        return reward, done
+        out = {"reward": reward, "cur": None}
+        if do_round:
+            out["cur"] = self._round(t + 1, deterministic)
+        return out

@@ -9,9 +9,21 @@ _BRA_T_RANGE = ((-0.12, 0.87), (-0.81, 0.18))
 _HM3_T_RANGE = ((-0.11, 0.88), (-0.55, 0.44), (-0.85, 0.14))
 
 
+_CONST = {}
+
+
+def _const(name, values, like):
+    """device-resident constant, created once per (device, dtype): the evaluation must not issue host->device
+    copies (it runs inside CUDA-graph captures of the episode loop)"""
+    key = (name, like.device, like.dtype)
+    if key not in _CONST:
+        _CONST[key] = torch.tensor(values, dtype=like.dtype, device=like.device)
+    return _CONST[key]
+
+
 def _clip_t(t, rng):
-    lo = torch.tensor([r[0] for r in rng], dtype=t.dtype, device=t.device)
-    hi = torch.tensor([r[1] for r in rng], dtype=t.dtype, device=t.device)
+    lo = _const(("lo", rng), [r[0] for r in rng], t)
+    hi = _const(("hi", rng), [r[1] for r in rng], t)
     return torch.minimum(torch.maximum(t, lo), hi)
 
 
@@ -41,9 +53,9 @@ _HM3_P = ((3689, 1170, 2673), (4699, 4387, 7470), (1091, 8732, 5547), (381, 5743
 
 def hm3(x):
     """x [..., 3] -> [...] (normalised, negated Hartmann-3: maximise)."""
-    A = torch.tensor(_HM3_A, dtype=x.dtype, device=x.device)
-    P = 1e-4 * torch.tensor(_HM3_P, dtype=x.dtype, device=x.device)
-    al = torch.tensor(_HM3_ALPHA, dtype=x.dtype, device=x.device)
+    A = _const("hm3A", _HM3_A, x)
+    P = _const("hm3P", [[1e-4 * v for v in row] for row in _HM3_P], x)
+    al = _const("hm3alpha", _HM3_ALPHA, x)
     e = (A * (x[..., None, :] - P) ** 2).sum(-1)
     f = -(al * torch.exp(-e)).sum(-1)
     return -(1 / 0.95 * (f - (-0.93)))

@@ -239,15 +239,16 @@ def logits_topk(logits, k, idx=None, val=None):
     return idx, val
 
 
-def logits_sample(logits, seed, step, a=None, episode_offset=0):
-    """Gumbel-max sample; `episode_offset` keys the noise by the GLOBAL episode index when `logits` is a
-    slice of a larger batch (the C ABI keys by row, so the seed is advanced per slice instead)."""
+def logits_sample(logits, seed, step, a=None, episode_offset=0, step_dev=None):
+    """Gumbel-max sample; `episode_offset` keys the noise by the GLOBAL episode index when `logits` is a slice of a
+    larger batch; `step_dev` (int64 device scalar) is added to `step` on the device so that a captured CUDA graph
+    draws fresh noise on every replay."""
     _chk(logits, torch.float32, "logits")
     B, M = logits.shape
     if a is None:
         a = torch.empty((B,), dtype=torch.int32, device=logits.device)
-    L.check(L.lib().mbo_logits_sample(B, M, _p(logits), int(seed), int(step), int(episode_offset), _p(a), _stream()),
-            "mbo_logits_sample")
+    L.check(L.lib().mbo_logits_sample(B, M, _p(logits), int(seed), int(step), _p(step_dev), int(episode_offset), _p(a),
+                                      _stream()), "mbo_logits_sample")
     return a
 
 

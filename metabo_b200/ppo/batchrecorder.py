@@ -15,6 +15,7 @@ Restriction: `size / n_workers` must be a multiple of the (fixed) horizon T, whi
 shipped config; then every worker batch ends on an episode boundary and the bootstrap term of
 :111-113 vanishes (nonterminal = 0).
 """
+import os
 import random
 import time
 
@@ -57,7 +58,7 @@ def gae_device(rewards, values, gamma, lam):
 
 class BatchRecorder:
     def __init__(self, size, env_id, env_seeds, policy_fn, n_workers, deterministic=False, store_states=True,
-                 gp_precision="fp64", mlp_mode=None, device=None):
+                 gp_precision="fp64", mlp_mode=None, device=None, use_graphs=True):
         self.env_id = env_id
         self.deterministic = bool(deterministic)
         assert size > 0
@@ -90,6 +91,7 @@ class BatchRecorder:
         self._opts = dict(gp_precision=gp_precision, device=device)
         self._mlp_mode = mlp_mode
         self.store_states = store_states
+        self.use_graphs = use_graphs
         self._build_env(policy_fn)
         self.sample_seed = int(self.env_seeds[-1])     # the reference's workers all inherit env_seeds[-1] (Appendix D)
         self.clear()
@@ -105,6 +107,7 @@ class BatchRecorder:
         self.pi = policy_fn(self.observation_space, self.action_space, self.deterministic)
         self.pi.set_requires_grad(False)
         self.env.set_policy(self.pi)
+        self.env.use_graphs = bool(self.use_graphs) and os.environ.get("MBO_NO_GRAPHS") is None
 
     def clear(self):
         self.cur_size = self.size

@@ -190,3 +190,38 @@ def test_eval_experiment_with_shipped_checkpoint_layout(golden_dir, tmp_path):
     assert np.all(np.diff(r, axis=1) <= 1e-12)
     assert np.median(r[:, -1]) < 5e-2                         # reference: median simple regret ~1e-3 after 30 steps
     assert os.path.exists(tmp_path / "eval" / "result_metabo_iter_1988")
+
+
+def test_cuda_graph_replay_equals_eager_rollouts(golden_dir):
+    """The episode loop captured as CUDA graphs (one per BO step index) must reproduce the eager rollouts bit for
+    bit over several consecutive batches (new objectives every episode, stochastic policy: fresh Gumbel noise on
+    every replay through the device-resident step counter)."""
+    from metabo_b200 import gym_compat as gym
+    from metabo_b200.policies.policies import NeuralAF
+    from metabo_b200.ppo.batchrecorder import BatchRecorder
+    pw = O.PolicyWeights.from_npz(os.path.join(golden_dir, "weights_bra_1635.npz"))
+    spec = dict(BRA_SPEC, T=6, N_MS=400, N_LS=200, f_opts={"bound_translation": 0.1, "bound_scaling": 0.1, "M": 50},
+                reward_transformation="neg_log10", env_id="MetaBO-GRAPH-v0")
+    gym.register(id=spec["env_id"], entry_point="metabo.environment.metabo_gym:MetaBO", max_episode_steps=6, kwargs=spec)
+    opts = dict(pw.options, mlp_mode="tf32")
+
+    def run(use_graphs):
+        fn = lambda o, a, d: NeuralAF(o, a, d, options=opts)
+        br = BatchRecorder(size=6 * 12, env_id=spec["env_id"], env_seeds=[3, 4, 5], policy_fn=fn, n_workers=3,
+                           deterministic=False, store_states=True, mlp_mode="tf32", use_graphs=use_graphs)
+        pi = fn(br.observation_space, br.action_space, False)
+        pi.load_state_dict({k: v.clone() for k, v in pw.sd.items()})
+        br.set_worker_weights(pi)
+        outs = []
+        for _ in range(4):                       # batch 1 eager warm-up, batch 2 capture, batches 3-4 replay
+            br.record_batch(0.98, 0.98)
+            outs.append({k: v.clone() for k, v in br.buf.items()})
+        return outs, br
+
+    eager, _ = run(False)
+    graph, br = run(True)
+    assert br.env.use_graphs and any("graph" in e for e in br.env._graphs.values())
+    for a, b in zip(eager, graph):
+        for k in ("actions", "rewards", "values", "states", "advs"):
+            assert torch.equal(a[k], b[k]), k
+    assert not torch.equal(eager[2]["actions"], eager[3]["actions"])      # different noise / objectives per batch

@@ -51,10 +51,12 @@ GPS = {"env_id": "MetaBO-GP-v0", "D": 3, "f_type": "GP",
 
 def run_eval(name, spec, npz, n_workers, n_episodes, mode, cands):
     br = recorder(spec, npz, n_workers, n_episodes, 100, True, mode)
-    br.record_batch(1.0, 1.0)                     # warm-up (also the measured regrets)
-    t = br.record_batch(1.0, 1.0)
+    br.record_batch(1.0, 1.0)                     # eager warm-up
+    t_capture = br.record_batch(1.0, 1.0)         # CUDA-graph capture of the T+1 per-step units
+    br.record_batch(1.0, 1.0)
+    t = br.record_batch(1.0, 1.0)                 # steady state: graph replays
     r = br.buf["rewards"].cpu().numpy()
-    out = {"config": name, "episodes": n_episodes, "T": spec["T"], "mlp_mode": mode, "t_batch_s": t,
+    out = {"config": name, "episodes": n_episodes, "T": spec["T"], "mlp_mode": mode, "t_batch_s": t, "t_capture_s": t_capture,
            "env_steps_per_s": spec["T"] * n_episodes / t, "af_evals_per_s": spec["T"] * n_episodes * cands / t,
            "final": {"median": float(np.median(r[:, -1])), "p30": float(np.percentile(r[:, -1], 30)),
                      "p70": float(np.percentile(r[:, -1], 70)), "mean": float(r[:, -1].mean())}}
@@ -78,7 +80,7 @@ def main():
     if "C3" in which:
         spec = dict(BRA, f_opts={"bound_translation": 0.1, "bound_scaling": 0.1, "M": 50}, reward_transformation="neg_log10")
         gym.register(id=spec["env_id"], entry_point="metabo.environment.metabo_gym:MetaBO", max_episode_steps=30, kwargs=spec)
-        params = {"batch_size": 1200, "max_steps": 3 * 1200, "minibatch_size": 60, "n_epochs": 4, "lr": 1e-4, "epsilon": 0.15,
+        params = {"batch_size": 1200, "max_steps": 6 * 1200, "minibatch_size": 60, "n_epochs": 4, "lr": 1e-4, "epsilon": 0.15,
                   "value_coeff": 1.0, "ent_coeff": 0.01, "gamma": 0.98, "lambda": 0.98, "loss_type": "GAElam", "normalize_advs": True,
                   "n_workers": 10, "env_id": spec["env_id"], "seed": 0, "env_seeds": list(range(10)), "mlp_mode": "tf32",
                   "policy_options": {"activations": "relu", "arch_spec": [200] * 4, "use_value_network": True, "t_idx": -2, "T_idx": -1,
@@ -89,7 +91,7 @@ def main():
                   save_interval=10, verbose=True)
         t0 = time.time(); ppo.train(); wall = time.time() - t0
         st = ppo.stats
-        print(json.dumps({"config": "C3 train_metabo_branin: 3 PPO iterations (batch 1200 = 40 episodes, 80 optimiser steps each, "
+        print(json.dumps({"config": "C3 train_metabo_branin: 6 PPO iterations (batch 1200 = 40 episodes, 80 optimiser steps each, "
                           "minibatch 60x966 candidates, torch autograd update)", "wall_s": wall, "t_batch_s": st["batch_stats"]["t_batch"],
                           "rollout_sps": st["batch_stats"]["sps"], "t_optim_s": st["t_optim"],
                           "e2e_steps_per_s": st["n_timesteps"] / st["t_train"], "avg_step_rews": list(map(float, st["avg_step_rews"])),
