@@ -118,7 +118,7 @@ class NeuralAF(nn.Module):
         if not self.use_value_network:
             return torch.zeros(states.shape[0], device=states.device)
         _, hv = self.kernel_handles()
-        tT = states[:, 0, [self.t_idx, self.T_idx]].contiguous()
+        tT = torch.stack([states[:, 0, self.t_idx], states[:, 0, self.T_idx]], dim=1).contiguous()
         return ops.value_net(hv, tT)
 
     # -- reference API ---------------------------------------------------------------------------
@@ -127,11 +127,18 @@ class NeuralAF(nn.Module):
         assert states.shape[-1] == self.N_features
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         if needs_grad:
-            # autograd path (PPO update): torch ops on the parameters' device
-            logits = self.policy_net.forward(states[:, :, self.policy_mask()])
+            # autograd path (PPO update): torch ops on the parameters' device; no host->device index tensors are
+            # created here so that the whole update step can be captured in a CUDA graph
+            cols = self.policy_columns()
+            if len(cols) == self.N_features:
+                pin = states
+            else:
+                lo, hi = cols[0], cols[-1] + 1
+                pin = states[:, :, lo:hi] if cols == list(range(lo, hi)) else torch.stack([states[:, :, c] for c in cols], dim=2)
+            logits = self.policy_net.forward(pin)
             logits = logits.squeeze(2)
             if self.use_value_network:
-                tT = states[:, [0], [self.t_idx, self.T_idx]]
+                tT = torch.stack([states[:, 0, self.t_idx], states[:, 0, self.T_idx]], dim=1)
                 values = self.value_net.forward(tT).squeeze(1)
             else:
                 values = torch.zeros(states.shape[0]).to(logits.device)

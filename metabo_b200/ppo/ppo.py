@@ -36,17 +36,18 @@ def dist_ctx():
 
 def normalize_advantages(advs, world=1):
     """(advs - mean) / std with the biased std over the GLOBAL minibatch (ppo.py:141-144)."""
-    s = torch.stack([advs.sum(), (advs * advs).sum(), torch.tensor(float(advs.numel()), device=advs.device,
-                                                                   dtype=advs.dtype)]).double()
+    cnt = torch.full((), float(advs.numel()), device=advs.device, dtype=advs.dtype)    # fill kernel, no H2D copy
+    s = torch.stack([advs.sum(), (advs * advs).sum(), cnt]).double()
     if world > 1:
         dist.all_reduce(s, op=dist.ReduceOp.SUM)
     n = s[2]
     mean = s[0] / n
     var = torch.clamp(s[1] / n - mean * mean, min=0.0)
     std = torch.sqrt(var)
-    if std == 0 or torch.isnan(std):
-        return advs
-    return ((advs.double() - mean) / std).to(advs.dtype)
+    ok = (std > 0) & ~torch.isnan(std)            # ppo.py:143: leave the advantages alone if std is 0 / NaN
+    safe = torch.where(ok, std, torch.ones_like(std))
+    normed = ((advs.double() - mean) / safe).to(advs.dtype)
+    return torch.where(ok, normed, advs)          # branch-free: capturable in a CUDA graph
 
 
 def ppo_minibatch_loss(pi, states, actions, advs, tdlamrets, logprobs_old, params, n_global):
@@ -113,7 +114,10 @@ class PPO:
         if self.world > 1:   # identical initial weights on every rank
             for p in self.pi.parameters():
                 dist.broadcast(p.data, src=0)
-        self.optimizer = torch.optim.Adam(self.pi.parameters(), lr=self.params["lr"])
+        self.optimizer = torch.optim.Adam(self.pi.parameters(), lr=self.params["lr"], capturable=True)
+        self.use_update_graph = self.world == 1 and os.environ.get("MBO_NO_GRAPHS") is None and \
+            self.params.get("update_graph", True)
+        self._upd = None        # (static inputs, CUDAGraph, static outputs) of one captured optimiser step
 
         self.stats = dict()
         self.stats["n_timesteps"] = 0
@@ -154,33 +158,72 @@ class PPO:
         if not self.verbose:
             print(s)
 
+    def _update_step(self, mb):
+        """one optimiser step on the (local shard of a) minibatch `mb` (dict of device tensors), ppo.py:129-178"""
+        states, actions, tdlamrets = mb["states"], mb["actions"], mb["tdlamrets"]
+        advs = mb["advs"] if self.params["loss_type"] == "GAElam" else mb["tdlamrets"]
+        n_global = states.shape[0] * self.world
+        if self.params["normalize_advs"]:
+            advs = normalize_advantages(advs, self.world)
+        with torch.no_grad():
+            _, logprobs_old, _ = self.old_pi.predict_vals_logps_ents(states=states, actions=actions)
+        loss, l_ppo, l_val, l_ent = ppo_minibatch_loss(self.pi, states, actions, advs, tdlamrets, logprobs_old,
+                                                       self.params, n_global)
+        self.optimizer.zero_grad(set_to_none=True)
+        loss.backward()
+        allreduce_gradients(list(self.pi.parameters()), self.world)
+        self.optimizer.step()
+        return torch.stack([l_ppo, l_val, l_ent, loss]).detach()
+
+    def _graphed_update(self, mb):
+        """The optimiser step is ~100 small kernels (autograd MLP on 60 x 966 rows, Categorical terms, Adam): it is
+        launch-bound, so it is captured once in a CUDA graph (static input buffers) and replayed per minibatch."""
+        n = mb["states"].shape[0]
+        if self._upd is None or self._upd[0]["states"].shape != mb["states"].shape:
+            static = {k: torch.empty_like(v) for k, v in mb.items() if v is not None}
+            for k in static:
+                static[k].copy_(mb[k])
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            snap = [p.detach().clone() for p in self.pi.parameters()]
+            opt_snap = [{k: v.clone() for k, v in st.items() if torch.is_tensor(v)} for st in self.optimizer.state.values()]
+            with torch.cuda.stream(side):
+                for _ in range(3):                                   # warm-up on a side stream (torch graph recipe)
+                    self._update_step(static)
+            torch.cuda.current_stream().wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self._update_step(static)
+            # the warm-up steps were real optimiser steps on this minibatch: undo them so that the numbers of
+            # optimiser steps and the parameter trajectory are exactly those of the eager schedule
+            with torch.no_grad():
+                for p, q in zip(self.pi.parameters(), snap):
+                    p.copy_(q)
+                for st, sn in zip(self.optimizer.state.values(), opt_snap):
+                    for k, v in sn.items():
+                        st[k].copy_(v)
+            self._upd = (static, g, out, self.stats["n_optsteps"])
+        static, g, out, _ = self._upd
+        for k in static:
+            static[k].copy_(mb[k])
+        g.replay()
+        return out.clone()
+
     def optimize_on_batch(self):
         now = time.time()
         self.iter_log_str += " OPTIMIZING...\n"
         self.old_pi.load_state_dict(self.pi.state_dict())
         self.old_pi.set_requires_grad(False)
+        self.old_pi.kernel_handles()      # re-pack the frozen policy's kernel weights NOW: a replayed graph cannot do it
         local_mb = self.params["minibatch_size"] // self.world
         for ep in range(self.params["n_epochs"]):
             sums = torch.zeros(4, device=self.device)
             n_minibatches = 0
             for mb in self.batch_recorder.iterate_device(local_mb, shuffle=True):
-                states, actions = mb["states"], mb["actions"]
-                tdlamrets = mb["tdlamrets"]
-                advs = mb["advs"] if self.params["loss_type"] == "GAElam" else mb["tdlamrets"]
-                n_global = states.shape[0] * self.world
-                if self.params["normalize_advs"]:
-                    advs = normalize_advantages(advs, self.world)
-                with torch.no_grad():
-                    _, logprobs_old, _ = self.old_pi.predict_vals_logps_ents(states=states, actions=actions)
-                loss, l_ppo, l_val, l_ent = ppo_minibatch_loss(self.pi, states, actions, advs, tdlamrets, logprobs_old,
-                                                               self.params, n_global)
-                self.optimizer.zero_grad()
-                loss.backward()
-                allreduce_gradients(list(self.pi.parameters()), self.world)
-                self.optimizer.step()
+                mb = {k: v for k, v in mb.items() if k in ("states", "actions", "tdlamrets", "advs")}
+                graphable = self.use_update_graph and mb["states"].shape[0] == local_mb and self.stats["n_optsteps"] > 0
+                sums += self._graphed_update(mb) if graphable else self._update_step(mb)
                 self.stats["n_optsteps"] += 1
-                with torch.no_grad():
-                    sums += torch.stack([l_ppo, l_val, l_ent, loss]).detach()
                 n_minibatches += 1
             if self.world > 1:
                 dist.all_reduce(sums, op=dist.ReduceOp.SUM)

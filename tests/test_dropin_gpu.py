@@ -225,3 +225,33 @@ def test_cuda_graph_replay_equals_eager_rollouts(golden_dir):
         for k in ("actions", "rewards", "values", "states", "advs"):
             assert torch.equal(a[k], b[k]), k
     assert not torch.equal(eager[2]["actions"], eager[3]["actions"])      # different noise / objectives per batch
+
+
+def test_graph_captured_ppo_update_equals_eager(golden_dir, tmp_path, monkeypatch):
+    """PPO.optimize_on_batch with the optimiser step captured in a CUDA graph follows the eager trajectory
+    (same minibatch order, same Adam state): weights after two iterations agree to fp32 round-off."""
+    import random
+    from metabo_b200 import gym_compat as gym
+    from metabo_b200.policies.policies import NeuralAF
+    from metabo_b200.ppo.ppo import PPO
+    spec = dict(BRA_SPEC, T=5, N_MS=100, N_LS=50, k=3, reward_transformation="neg_log10", env_id="MetaBO-UPD-v0",
+                f_opts={"bound_translation": 0.1, "bound_scaling": 0.1, "M": 50})
+    gym.register(id=spec["env_id"], entry_point="metabo.environment.metabo_gym:MetaBO", max_episode_steps=5, kwargs=spec)
+
+    def run(update_graph, name):
+        params = {"batch_size": 80, "max_steps": 160, "minibatch_size": 10, "n_epochs": 2, "lr": 1e-3, "epsilon": 0.15,
+                  "value_coeff": 1.0, "ent_coeff": 0.01, "gamma": 0.98, "lambda": 0.98, "loss_type": "GAElam",
+                  "normalize_advs": True, "n_workers": 4, "env_id": spec["env_id"], "seed": 0, "env_seeds": [0, 1, 2, 3],
+                  "update_graph": update_graph,
+                  "policy_options": {"activations": "relu", "arch_spec": [200] * 4, "use_value_network": True, "t_idx": -2,
+                                     "T_idx": -1, "arch_spec_value": [200] * 4}}
+        ppo = PPO(policy_fn=lambda o, a, d: NeuralAF(o, a, d, options=params["policy_options"]), params=params,
+                  logpath=str(tmp_path / name), save_interval=10, verbose=True)
+        ppo.train()
+        return torch.cat([p.detach().reshape(-1) for p in ppo.pi.parameters()]), ppo
+
+    w_e, _ = run(False, "eager")
+    w_g, ppo = run(True, "graph")
+    assert ppo._upd is not None                                   # the graph path was taken
+    assert ppo.stats["n_optsteps"] == 2 * 2 * 8
+    assert float((w_e - w_g).abs().max()) <= 1e-5 * float(w_e.abs().max())
