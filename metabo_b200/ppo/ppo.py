@@ -115,6 +115,8 @@ class PPO:
             for p in self.pi.parameters():
                 dist.broadcast(p.data, src=0)
         self.optimizer = torch.optim.Adam(self.pi.parameters(), lr=self.params["lr"], capturable=True)
+        # autograd GEMMs of the update: "highest" = fp32 (reference numerics), "high" = TF32 tensor cores
+        torch.set_float32_matmul_precision(self.params.get("update_matmul_precision", "highest"))
         self.use_update_graph = self.world == 1 and os.environ.get("MBO_NO_GRAPHS") is None and \
             self.params.get("update_graph", True)
         self._upd = None        # (static inputs, CUDAGraph, static outputs) of one captured optimiser step
