@@ -392,7 +392,7 @@ struct TcTopk {
   int32_t* part_idx;
 };
 
-template <int MODE, bool FUSE>
+template <int MODE, bool FUSE, int K0S>     // K0S: K = 8 slices of layer 0 (1: F + 1 <= 8, 2: F + 1 <= 16)
 __global__ void __launch_bounds__(FUSE ? TC_THREADS_FUSED : TC_THREADS, 1)
 neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candidates cand, int B,
                     int tiles_per_episode, const float* __restrict__ mean, const float* __restrict__ std_,
@@ -500,7 +500,8 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
         if (leader) {
           const uint32_t a_hi = tmem + COL_S, a_lo = tmem + COL_S + 16;
           constexpr uint32_t W0_PART_D = (uint32_t)((TC_K0 / 4) * CHUNK_ROW_BYTES) >> 4;     // hi -> lo part
-          for (int sl = 0; sl < fs.k0_slices; ++sl) {
+#pragma unroll
+          for (int sl = 0; sl < K0S; ++sl) {
             const uint32_t wl = w0_lo + sl * SLICE_D;
             mma_ts_tf32(tmem + COL_R0, a_hi + sl * 8, make_desc64(wl), IDESC_TF32, sl ? 1u : 0u);
             mma_ts_tf32(tmem + COL_R0, a_lo + sl * 8, make_desc64(wl), IDESC_TF32, 1);
@@ -569,33 +570,31 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
     bool ok = true;
     const float* s_w4 = s_tail + 4 * TC_N;          // s_tail = [zeros | b1 | b2 | b3 | w4 | b4]
 
-    auto build_features = [&](int t_idx) {
-      if (FUSE) {   // posterior of this tile from the GP warps
-        if (!mbar_wait(BAR_GPFULL(t_idx & 1), (uint32_t)(t_idx >> 1) & 1u, s_abort)) ok = false;
-      }
+    // Feature vector of this thread's row for tile `t_idx` (fp32, ones column appended).  It is gathered one tile
+    // AHEAD into registers (`pf`) so that the global-memory latency of mean/std/candidates never sits between the
+    // last hidden-layer epilogue and the head epilogue (half-0 warps wait for half-1 at the pair barrier there).
+    constexpr int KF = 8 * K0S;                        // feature slots (incl. the ones column)
+    auto gather_features = [&](int t_idx, float* f) {
       const int tile = (int)blockIdx.x + t_idx * (int)gridDim.x;
       const int b = tile / tiles_per_episode;
       const int m = (tile - b * tiles_per_episode) * TC_M + row;
-      float f[TC_K0];
 #pragma unroll
-      for (int i = 0; i < TC_K0; ++i) f[i] = 0.f;
-      if (m < cand.M && fs.dense) {
+      for (int i = 0; i < KF; ++i) f[i] = 0.f;
+      if (t_idx >= my_tiles || m >= cand.M) return;
+      if (fs.dense) {
         const float* srow = fs.dense + ((size_t)b * cand.M + m) * fs.dense_F;
 #pragma unroll
-        for (int i = 0; i < TC_K0 - 1; ++i)
+        for (int i = 0; i < KF - 1; ++i)
           if (i < fs.F) f[i] = srow[fs.src[i]];
-#pragma unroll
-        for (int i = 0; i < TC_K0; ++i) if (i == fs.F) f[i] = 1.0f;    // bias column
-      } else if (m < cand.M) {
+      } else {
         double x[MBO_MAX_D];
 #pragma unroll
         for (int d = 0; d < MBO_MAX_D; ++d) x[d] = 0.0;
         load_candidate(cand, b, m, x);
-        float mu, sd;
-        if (FUSE) { mu = s_mu[(t_idx & 1) * TC_M + row]; sd = s_sd[(t_idx & 1) * TC_M + row]; }
-        else { mu = mean[(size_t)b * cand.M + m]; sd = std_[(size_t)b * cand.M + m]; }
+        float mu = 0.f, sd = 0.f;
+        if (!FUSE) { mu = mean[(size_t)b * cand.M + m]; sd = std_[(size_t)b * cand.M + m]; }
 #pragma unroll
-        for (int i = 0; i < TC_K0 - 1; ++i) {
+        for (int i = 0; i < KF - 1; ++i) {
           if (i < fs.F) {
             const int s = fs.src[i];
             float v;
@@ -609,18 +608,35 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
             f[i] = v;
           }
         }
-#pragma unroll
-        for (int i = 0; i < TC_K0; ++i) if (i == fs.F) f[i] = 1.0f;    // bias column
       }
-      uint32_t hi[TC_K0], lo[TC_K0];
 #pragma unroll
-      for (int i = 0; i < TC_K0; ++i) {
-        float h = tf32_rna(f[i]);
+      for (int i = 0; i < KF; ++i) if (i == fs.F) f[i] = 1.0f;    // bias column
+    };
+    float pf[KF];                                   // prefetched features of the next tile to be built
+
+    auto build_features = [&](int t_idx) {
+      if (FUSE) {   // posterior of this tile from the GP warps
+        if (!mbar_wait(BAR_GPFULL(t_idx & 1), (uint32_t)(t_idx >> 1) & 1u, s_abort)) ok = false;
+        const int tile = (int)blockIdx.x + t_idx * (int)gridDim.x;
+        const int b = tile / tiles_per_episode;
+        const int m = (tile - b * tiles_per_episode) * TC_M + row;
+        if (m < cand.M && !fs.dense) {
+#pragma unroll
+          for (int i = 0; i < KF - 1; ++i) {
+            if (i < fs.F && fs.src[i] == MBO_FEAT_MEAN) pf[i] = s_mu[(t_idx & 1) * TC_M + row];
+            if (i < fs.F && fs.src[i] == MBO_FEAT_STD) pf[i] = s_sd[(t_idx & 1) * TC_M + row];
+          }
+        }
+      }
+      uint32_t hi[KF], lo[KF];
+#pragma unroll
+      for (int i = 0; i < KF; ++i) {
+        float h = tf32_rna(pf[i]);
         hi[i] = __float_as_uint(h);
-        lo[i] = __float_as_uint(tf32_rna(f[i] - h));
+        lo[i] = __float_as_uint(tf32_rna(pf[i] - h));
       }
       if (FUSE) mbar_arrive(BAR_GPEMPTY(t_idx & 1));   // mu/sd of this buffer consumed
-      if (fs.k0_slices == 1) {
+      if (K0S == 1) {
         tmem_st8(tlane + COL_S, hi);
         tmem_st8(tlane + COL_S + 16, lo);
       } else {
@@ -631,9 +647,10 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR_FEAT);
+      gather_features(t_idx + 1, pf);                  // loads for the next tile are in flight from here on
     };
 
-    if (my_tiles > 0 && half == 1) build_features(0);
+    if (my_tiles > 0 && half == 1) { gather_features(0, pf); build_features(0); }
     constexpr int MAXI = (C::NCHUNK + 1) / 2;
     for (int t = 0; t < my_tiles && ok; ++t) {
       // ---- E0..E2: relu(D + b) -> next layer's A operand, in place ----
@@ -926,12 +943,12 @@ topk_merge_kernel(int n_lists, int k, const float* __restrict__ part_val, const 
 
 static int g_num_sms = 0;
 
-template <int MODE, bool FUSE>
-static int launch_tc(const mbo_policy* p, int B, const TcFeat& fs, const mbo_candidates& cand, const float* mean,
+template <int MODE, bool FUSE, int K0S>
+static int launch_tc_k(const mbo_policy* p, int B, const TcFeat& fs, const mbo_candidates& cand, const float* mean,
                      const float* std_, const float* epi, float* logits, int* err_flag, cudaStream_t s,
                      const GpFuse& gp, const TcTopk& tk) {
   using SM = TcSmem<MODE, FUSE>;
-  auto kern = neural_af_tc_kernel<MODE, FUSE>;
+  auto kern = neural_af_tc_kernel<MODE, FUSE, K0S>;
   MBO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::total));
   if (g_num_sms == 0) {
     int dev = 0;
@@ -946,6 +963,14 @@ static int launch_tc(const mbo_policy* p, int B, const TcFeat& fs, const mbo_can
       getenv("MBO_TC_DEBUG_NOLOAD") ? 1 : 0, gp, tk);
   MBO_LAUNCH_CHECK();
   return MBO_OK;
+}
+
+template <int MODE, bool FUSE>
+static int launch_tc(const mbo_policy* p, int B, const TcFeat& fs, const mbo_candidates& cand, const float* mean,
+                     const float* std_, const float* epi, float* logits, int* err_flag, cudaStream_t s,
+                     const GpFuse& gp, const TcTopk& tk) {
+  if (fs.k0_slices == 1) return launch_tc_k<MODE, FUSE, 1>(p, B, fs, cand, mean, std_, epi, logits, err_flag, s, gp, tk);
+  return launch_tc_k<MODE, FUSE, 2>(p, B, fs, cand, mean, std_, epi, logits, err_flag, s, gp, tk);
 }
 
 int tc_forward(const mbo_policy* p, int mode, int B, int F, const int32_t* feat_src, const mbo_candidates* cand,
