@@ -230,7 +230,7 @@ def main():
     ap.add_argument("--B", type=int, default=1024, help="episodes per GPU")
     ap.add_argument("--n-obs", dest="n_obs", type=int, default=30)
     ap.add_argument("--gp", default="fp64", choices=["fp64", "fp32"])
-    ap.add_argument("--mlp", default="auto", choices=["auto", "fp32", "tf32", "bf16x3"])
+    ap.add_argument("--mlp", default="auto", choices=["auto", "fp32", "tf32", "bf16x3", "fp16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ppo", action="store_true", help="skip the supplementary PPO rollout env-steps/s figure")
     args = ap.parse_args()
@@ -286,8 +286,8 @@ def main():
     tvec = torch.full((B,), float(n), device=dev)
     Tvec = torch.full((B,), float(T), device=dev)
 
-    modes = {"fp32": L.MLP_FP32, "tf32": L.MLP_TF32, "bf16x3": L.MLP_BF16X3}
-    order = ["tf32", "bf16x3", "fp32"] if args.mlp == "auto" else [args.mlp]
+    modes = L.MLP_MODES
+    order = ["fp16", "tf32", "bf16x3", "fp32"] if args.mlp == "auto" else [args.mlp]
     eng = None
     for m in order:
         try:
@@ -366,7 +366,7 @@ def main():
                 "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
                 "traffic_unit": "bytes per launch (dram read+write, ncu)",
                 "peak_source": peak_src, "avg_launch_ms": dur * 1e3,
-                "format_ceiling_frac": {"tf32": 0.5, "bf16x3": 1.0 / 3.0, "fp32": None}[args.mlp]}
+                "format_ceiling_frac": {"fp16": 1.0, "tf32": 0.5, "bf16x3": 1.0 / 3.0, "fp32": None}[args.mlp]}
         if gp_big:
             gdur = float(np.mean(gp_big)) / 1e3
             roof["gp_posterior"] = {"avg_launch_ms": gdur * 1e3, "precision": args.gp,

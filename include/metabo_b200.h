@@ -59,6 +59,9 @@ extern "C" {
 #define MBO_MLP_FP32 0   /* CUDA-core fp32 FMA (validation mode, any architecture) */
 #define MBO_MLP_TF32 1   /* tcgen05 kind::tf32, fp32 accumulate in TMEM */
 #define MBO_MLP_BF16X3 2 /* tcgen05 kind::f16 bf16 hi/lo split, 3 MMAs per product */
+#define MBO_MLP_FP16 3   /* tcgen05 kind::f16 fp16: tf32's 11-bit significand at twice the rate, biases inside the
+                            MMAs (H <= 206); activations beyond fp16's range (65504 after the per-layer power-of-two
+                            renormalisation) are clamped and set bit 1 of the workspace's error word */
 
 /* Candidate set of one call.  Candidate m of episode b is
  *   m <  n_head                : head[b, m, :]                    (per-episode points)

@@ -7,7 +7,8 @@ LIB_PATH = os.environ.get("MBO_LIB_PATH", os.path.join(_HERE, "libmetabo_b200.so
 
 KERNEL_IDS = {"RBF": 0, "Matern32": 1, "Matern52": 2}
 GP_FP64, GP_FP32 = 0, 1
-MLP_FP32, MLP_TF32, MLP_BF16X3 = 0, 1, 2
+MLP_FP32, MLP_TF32, MLP_BF16X3, MLP_FP16 = 0, 1, 2, 3
+MLP_MODES = {"fp32": MLP_FP32, "tf32": MLP_TF32, "bf16x3": MLP_BF16X3, "fp16": MLP_FP16}
 ACT = {"relu": 0, "tanh": 1}
 FEAT_MEAN, FEAT_STD, FEAT_X0, FEAT_INCUMBENT, FEAT_TPERC, FEAT_TIMESTEP, FEAT_BUDGET = 0, 1, 2, 10, 11, 12, 13
 

@@ -215,7 +215,7 @@ extern "C" int mbo_af_topk(const mbo_policy* p, int mode, int B, int F, const in
                            void* stream) {
   int rc = check_af_args("mbo_af_topk", p, B, F, feat_src, cand, mean, std_, epi);
   if (rc) return rc;
-  MBO_CHECK_ARG(mode == MBO_MLP_TF32 || mode == MBO_MLP_BF16X3, "mbo_af_topk: tensor-core modes only (use mbo_af_logits + mbo_logits_topk)");
+  MBO_CHECK_ARG(mode == MBO_MLP_TF32 || mode == MBO_MLP_BF16X3 || mode == MBO_MLP_FP16, "mbo_af_topk: tensor-core modes only (use mbo_af_logits + mbo_logits_topk)");
   MBO_CHECK_ARG(topk_idx && k >= 1, "mbo_af_topk: bad k / null output");
   return tc_forward(p, mode, B, F, feat_src, cand, mean, std_, epi, logits, workspace, workspace_bytes,
                     (cudaStream_t)stream, nullptr, 0, k, topk_idx, topk_val);
@@ -239,7 +239,7 @@ extern "C" int mbo_af_logits(const mbo_policy* p, int mode, int B, int F, const 
   }
   if (mode == MBO_MLP_FP32)
     return simt_forward(p, B, F, feat_src, cand, mean, std_, epi, nullptr, 0, logits, (cudaStream_t)stream);
-  if (mode == MBO_MLP_TF32 || mode == MBO_MLP_BF16X3)
+  if (mode == MBO_MLP_TF32 || mode == MBO_MLP_BF16X3 || mode == MBO_MLP_FP16)
     return tc_forward(p, mode, B, F, feat_src, cand, mean, std_, epi, logits, workspace, workspace_bytes,
                       (cudaStream_t)stream);
   set_error("mbo_af_logits: unknown mode %d", mode);
@@ -260,7 +260,7 @@ extern "C" int mbo_af_logits_dense(const mbo_policy* p, int mode, int B, int M, 
   c.D = 1;
   if (mode == MBO_MLP_FP32)
     return simt_forward(p, B, F, cols, &c, nullptr, nullptr, nullptr, nullptr, 0, logits, (cudaStream_t)stream, states, F_state);
-  if (mode == MBO_MLP_TF32 || mode == MBO_MLP_BF16X3)
+  if (mode == MBO_MLP_TF32 || mode == MBO_MLP_BF16X3 || mode == MBO_MLP_FP16)
     return tc_forward(p, mode, B, F, cols, &c, nullptr, nullptr, nullptr, logits, workspace, workspace_bytes,
                       (cudaStream_t)stream, states, F_state);
   set_error("mbo_af_logits_dense: unknown mode %d", mode);

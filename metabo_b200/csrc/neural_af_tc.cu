@@ -19,22 +19,50 @@
 //
 // Arithmetic modes (hidden layers): MBO_MLP_TF32   kind::tf32, operands rounded to tf32 (rna);
 //                                   MBO_MLP_BF16X3 kind::f16 bf16, a = a_hi + a_lo, w = w_hi + w_lo,
-//                                                  a*w ~ a_hi*w_hi + a_lo*w_hi + a_hi*w_lo.
-// Warp roles (320 threads): warps 0-7 epilogue (TMEM lanes 32*(w&3).., chunk parity w>>2), warp 8 TMA
-// producer + TMEM allocation, warp 9 MMA issuer.  Every mbarrier wait is bounded (globaltimer) and raises a
-// device-side error flag instead of hanging.
+//                                                  a*w ~ a_hi*w_hi + a_lo*w_hi + a_hi*w_lo;
+//                                   MBO_MLP_FP16   kind::f16 fp16: same 11-bit significand as tf32 at twice the tensor
+//                                                  rate.  Biases ride in the MMA (a ones column that the weights
+//                                                  propagate from layer to layer), so an epilogue element costs half
+//                                                  an instruction (cvt.rn.satfinite.relu.f16x2.f32); layers with an
+//                                                  unusual weight scale are renormalised by a power of two at pack
+//                                                  time (exact: ReLU is positively homogeneous); an activation that
+//                                                  reaches the fp16 range limit raises bit 1 of the error flag.
+// Warp roles (448 threads): warps 0-7 epilogue (TMEM lanes 32*(w&3).., chunk parity w>>2), warp 8 TMA
+// producer + TMEM allocation, warp 9 MMA issuer, warps 10-13 feature warps: they gather mean/std/candidates of the
+// tiles ahead from global memory and write the layer-0 operand into TMEM, so that this latency (~4 000 cycles per
+// tile when the epilogue warps did it) is off the tensor pipe's critical path.  Every mbarrier wait is bounded
+// (globaltimer) and raises a device-side error flag instead of hanging.
 #include "common.cuh"
 #include "policy.cuh"
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include "tmem_ldst.cuh"
+
+#ifdef MBO_TC_TRACE
+// debug build only (make EXTRA=-DMBO_TC_TRACE): clock64 stamps of pipeline events of CTA 0, tiles T0..T0+3
+__device__ long long g_tc_trace[8192];
+#ifndef MBO_TC_TRACE_CTA_B
+#define MBO_TC_TRACE_CTA_B 82
+#endif
+#define TC_STAT_BEGIN() const long long _ts = clock64()
+#define TC_STAT_END(acc) (acc) += clock64() - _ts
+#ifndef MBO_TC_TRACE_T0
+#define MBO_TC_TRACE_T0 200
+#endif
+#define TC_TRACE(slot) do { if ((blockIdx.x == 0 || blockIdx.x == MBO_TC_TRACE_CTA_B) && t >= MBO_TC_TRACE_T0 && t < MBO_TC_TRACE_T0 + 4 && lane == 0) g_tc_trace[(blockIdx.x ? 2048 : 0) + (t - MBO_TC_TRACE_T0) * 512 + (slot)] = clock64(); } while (0)
+#else
+#define TC_TRACE(slot) do { } while (0)
+#define TC_STAT_BEGIN() do { } while (0)
+#define TC_STAT_END(acc) do { } while (0)
+#endif
 
 namespace mbo {
 
 constexpr int TC_N = 208;            // padded hidden width (UMMA N, multiple of 16)
 constexpr int TC_M = 128;            // candidates per tile (UMMA M)
-constexpr int TC_THREADS = 320;        // 8 epilogue warps + TMA warp + MMA warp
-constexpr int WARP_TMA = 8, WARP_MMA = 9, WARP_GP0 = 10;   // warps 10-13: fused GP posterior (FUSE only)
+constexpr int TC_THREADS = 448;        // 8 epilogue warps + TMA warp + MMA warp + 4 feature warps
+constexpr int WARP_TMA = 8, WARP_MMA = 9, WARP_GP0 = 10;   // warps 10-13: feature warps, or the fused GP posterior (FUSE)
 constexpr int TC_THREADS_FUSED = 448;
 constexpr int GP_NP = 32;                 // fused GP: n <= 32 observations
 constexpr int GPB_XS = 16, GPB_BETA = GPB_XS + GP_NP * MBO_MAX_D, GPB_LINV = GPB_BETA + GP_NP;
@@ -70,12 +98,26 @@ template <> struct ModeCfg<MBO_MLP_BF16X3> {
   static constexpr int NCHUNK = 7;             // 6 x 32 + 1 x 16
 };
 
+template <> struct ModeCfg<MBO_MLP_FP16> {
+  static constexpr int K = 208;                // 13 slices of 16; K columns H, H+1 carry the bias (hi, lo)
+  static constexpr int SLICE_K = 16;
+  static constexpr int SLICES = 13;
+  static constexpr int SLICES_PER_STAGE = 2;
+  static constexpr int STAGES_PER_LAYER = 7;   // the last stage holds one slice
+  static constexpr int STAGE_BYTES = 2 * 2 * CHUNK_ROW_BYTES;                  // 13 312
+  static constexpr int NSTAGE = 14;            // two layers resident
+  static constexpr int NSTAGE_FUSED = 11;
+  static constexpr int CHUNK_COLS = 32;
+  static constexpr int NCHUNK = 7;             // 6 x 32 + 1 x 16
+};
+
 constexpr int W0_BYTES = 2 * (TC_K0 / 4) * CHUNK_ROW_BYTES;   // hi + lo: 13 312
 constexpr int TAIL_FLOATS = 5 * TC_N + 4;                    // zeros(b0 is folded into W0) b1 b2 b3 | w4 | b4
 
-// packed-weight buffer layout (bytes): [W0][tf32 hidden x3][bf16 hidden x3][tail floats]
+// packed-weight buffer layout (bytes):
+//   [W0][tf32 hidden x3][bf16 hidden x3][tail floats] | fp16 mode: [W0h][fp16 hidden x3][tail floats][scale exponents]
 struct PackLayout {
-  size_t off_w0, off_tf32, off_bf16, off_tail, total;
+  size_t off_w0, off_tf32, off_bf16, off_tail, off_w0h, off_f16, off_tailh, off_scale, total;
 };
 __host__ __device__ inline PackLayout pack_layout() {
   PackLayout p;
@@ -83,7 +125,11 @@ __host__ __device__ inline PackLayout pack_layout() {
   p.off_tf32 = W0_BYTES;
   p.off_bf16 = p.off_tf32 + (size_t)3 * ModeCfg<MBO_MLP_TF32>::STAGES_PER_LAYER * ModeCfg<MBO_MLP_TF32>::STAGE_BYTES;
   p.off_tail = p.off_bf16 + (size_t)3 * ModeCfg<MBO_MLP_BF16X3>::STAGES_PER_LAYER * ModeCfg<MBO_MLP_BF16X3>::STAGE_BYTES;
-  p.total = p.off_tail + sizeof(float) * TAIL_FLOATS;
+  p.off_w0h = p.off_tail + sizeof(float) * TAIL_FLOATS;
+  p.off_f16 = p.off_w0h + W0_BYTES;
+  p.off_tailh = p.off_f16 + (size_t)3 * ModeCfg<MBO_MLP_FP16>::STAGES_PER_LAYER * ModeCfg<MBO_MLP_FP16>::STAGE_BYTES;
+  p.off_scale = p.off_tailh + sizeof(float) * TAIL_FLOATS;
+  p.total = p.off_scale + 32;
   return p;
 }
 
@@ -120,9 +166,10 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   return t;
 }
 constexpr uint64_t WAIT_TIMEOUT_NS = 2000000000ull;   // 2 s: far beyond any legitimate wait
-// bounded wait; returns false (and latches *abort) on timeout or when another role already aborted
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag) {
-  if (mbar_try_wait(bar, parity)) return true;
+// bounded wait; returns false (and latches *abort) on timeout or when another role already aborted.
+// The slow path is kept out of line: it is inlined at ~60 call sites otherwise, and the kernel's instruction
+// footprint is what the instruction caches (and the GPC-level fetch path behind them) see.
+__device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, volatile int* abort_flag) {
   const uint64_t t0 = globaltimer_ns();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
@@ -132,6 +179,10 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatil
     }
   }
   return true;
+}
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag) {
+  if (mbar_try_wait(bar, parity)) return true;
+  return mbar_wait_slow(bar, parity, abort_flag);
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -183,7 +234,7 @@ __device__ __forceinline__ bool elect_one() {
 __host__ __device__ constexpr uint32_t make_idesc(uint32_t ab_format) {
   return (1u << 4) | (ab_format << 7) | (ab_format << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 }
-constexpr uint32_t IDESC_TF32 = make_idesc(2), IDESC_BF16 = make_idesc(1);
+constexpr uint32_t IDESC_TF32 = make_idesc(2), IDESC_BF16 = make_idesc(1), IDESC_F16 = make_idesc(0);
 
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -196,6 +247,59 @@ struct PackArgs {
   const float* b[5];
   int F, H;
 };
+
+// fp16 mode: per-layer power-of-two renormalisation.  The RMS magnitude of layer l's output is estimated from the
+// weights alone: est_0 = 1, est_{l+1}^2 = g_l^2 est_l^2 + rms(b_l)^2 with g_l the RMS row norm of W_l.  The
+// cumulative exponent E_l = -rint(log2 est_{l+1}) (0 while |E_l| < 6, so the shipped policies run unscaled) brings
+// the activations handed to layer l+1 to O(1); layer l is packed as 2^(E_l - E_{l-1}) W_l with bias 2^E_l b_l and
+// the head as 2^-E_3 w4 -- the same function in exact arithmetic because relu(c x) = c relu(x) for c > 0.
+// exps[0..3] = per-layer exponents, exps[4] = sticky "a packed value left fp16's range" flag (set by the pack).
+__global__ void tc_scale_kernel(PackArgs a, int* __restrict__ exps) {
+  __shared__ double sh[256];
+  __shared__ double ssq[8];
+  const int F = a.F, H = a.H;
+  for (int q = 0; q < 8; ++q) {              // q < 4: sum W_q^2, q >= 4: sum b_{q-4}^2
+    const int l = q & 3;
+    const int cnt = q < 4 ? H * (l == 0 ? F : H) : H;
+    const float* src = q < 4 ? a.W[l] : a.b[l];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) { const double w = src[i]; acc += w * w; }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) ssq[q] = sh[0];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    double est2 = 1.0;
+    int Eprev = 0;
+    for (int l = 0; l < 4; ++l) {
+      est2 = ssq[l] / H * est2 + ssq[4 + l] / H;
+      int E = Eprev;
+      if (est2 > 0.0 && est2 < 1e300) {       // zero, inf or NaN parameters: keep the previous scale
+        E = -(int)rint(0.5 * log2(est2));
+        if (E > -6 && E < 6) E = 0;
+        E = E > Eprev + 20 ? Eprev + 20 : (E < Eprev - 20 ? Eprev - 20 : E);
+        E = E > 60 ? 60 : (E < -60 ? -60 : E);
+      }
+      exps[l] = E - Eprev;
+      Eprev = E;
+    }
+    exps[4] = 0;
+  }
+}
+
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {   // lo -> bits 0..15
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float f16_bits_to_float(uint32_t h) {
+  return __half2float(__ushort_as_half((unsigned short)h));
+}
 
 __global__ void tc_pack_kernel(PackArgs a, unsigned char* __restrict__ out) {
   const PackLayout pl = pack_layout();
@@ -248,7 +352,7 @@ __global__ void tc_pack_kernel(PackArgs a, unsigned char* __restrict__ out) {
       o1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
     }
     *dst = (uint32_t)__bfloat16_as_ushort(o0) | ((uint32_t)__bfloat16_as_ushort(o1) << 16);
-  } else {
+  } else if (byte < pl.off_w0h) {
     size_t i = (byte - pl.off_tail) / 4;
     float v = 0.f;
     if (i < (size_t)TC_N) {
@@ -263,6 +367,64 @@ __global__ void tc_pack_kernel(PackArgs a, unsigned char* __restrict__ out) {
       v = a.b[4][0];
     }
     *dst = __float_as_uint(v);
+  } else if (byte < pl.off_scale) {
+    // ---- fp16 mode (needs H + 2 <= 208): scaled weights, bias and ones columns inside the MMAs ----
+    const int* ex = (const int*)(out + pl.off_scale);          // written by tc_scale_kernel (stream order)
+    if (byte < pl.off_f16) {
+      // W0h: as W0, scaled by 2^e0; rows H, H+1 read the features' ones column -> D0[:, H] = D0[:, H+1] = 1
+      size_t i = (byte - pl.off_w0h) / 4;
+      int e = i % 4; i /= 4;
+      int n = i % TC_N; i /= TC_N;
+      int chunk = i % (TC_K0 / 4); i /= (TC_K0 / 4);
+      int part = (int)i;
+      int k = chunk * 4 + e;
+      float v = 0.f;
+      if (n < H) v = ldexpf(k < F ? a.W[0][n * F + k] : (k == F ? a.b[0][n] : 0.f), ex[0]);
+      else if (n < H + 2 && k == F) v = 1.0f;
+      float hi = tf32_rna(v);
+      float lo = tf32_rna(v - hi);
+      *dst = __float_as_uint(part == 0 ? hi : lo);
+    } else if (byte < pl.off_tailh) {
+      using C = ModeCfg<MBO_MLP_FP16>;
+      size_t i = (byte - pl.off_f16) / 4;
+      int pair = i % 4; i /= 4;
+      int n = i % TC_N; i /= TC_N;
+      int chunk = i % 2; i /= 2;
+      int slice = i % C::SLICES_PER_STAGE; i /= C::SLICES_PER_STAGE;
+      int stage = i % C::STAGES_PER_LAYER; i /= C::STAGES_PER_LAYER;
+      int layer = (int)i + 1;
+      int k = (stage * C::SLICES_PER_STAGE + slice) * C::SLICE_K + chunk * 8 + pair * 2;
+      int cum = 0;
+      for (int l = 0; l <= layer; ++l) cum += ex[l];
+      float v[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int kk = k + u;
+        float x = 0.f;
+        if (n < H) {
+          if (kk < H) x = ldexpf(a.W[layer][n * H + kk], ex[layer]);
+          else if (kk == H || kk == H + 1) {
+            const float bs = ldexpf(a.b[layer][n], cum);
+            const float bh = f16_bits_to_float(pack_f16x2_sat(bs, 0.f) & 0xffffu);
+            x = kk == H ? bs : bs - bh;          // hi is rounded by the final conversion (and range-checked there)
+          }
+        } else if (n < H + 2 && kk == H) x = 1.0f;           // keeps the ones columns alive in the next layer
+        v[u] = x;
+      }
+      if (!(fabsf(v[0]) <= 65504.f) || !(fabsf(v[1]) <= 65504.f)) atomicOr((int*)(out + pl.off_scale) + 4, 1);
+      *dst = pack_f16x2_sat(v[0], v[1]);
+    } else {
+      // tail of the fp16 mode: biases live in the MMAs; head weights undo the cumulative scale
+      size_t i = (byte - pl.off_tailh) / 4;
+      float v = 0.f;
+      if (i >= (size_t)4 * TC_N && i < (size_t)5 * TC_N) {
+        int n = (int)(i - 4 * TC_N);
+        v = n < H ? ldexpf(a.W[4][n], -(ex[0] + ex[1] + ex[2] + ex[3])) : 0.f;
+      } else if (i == (size_t)5 * TC_N) {
+        v = a.b[4][0];
+      }
+      *dst = __float_as_uint(v);
+    }
   }
 }
 
@@ -284,9 +446,12 @@ int tc_pack_weights(mbo_policy* p, cudaStream_t s) {
   for (int l = 0; l < 5; ++l) { a.W[l] = p->d_W_raw + p->raw_off[l]; a.b[l] = p->d_b[l]; }
   a.F = F; a.H = H;
   size_t words = pl.total / 4;
+  tc_scale_kernel<<<1, 256, 0, s>>>(a, (int*)((unsigned char*)p->d_tc + pl.off_scale));
+  MBO_LAUNCH_CHECK();
   tc_pack_kernel<<<(unsigned)((words + 255) / 256), 256, 0, s>>>(a, (unsigned char*)p->d_tc);
   MBO_LAUNCH_CHECK();
   p->tc_ready = 1;
+  p->tc_f16 = H + 2 <= TC_N;     // two spare K columns for the bias
   p->tc_F = F; p->tc_H = H;
   return MBO_OK;
 }
@@ -302,13 +467,21 @@ struct TcFeat {
   int dense_F;
 };
 
-template <int MODE, bool FUSE = false>
+// MBO_MLP_FP16 (not FUSE) keeps the even weight stages of all three hidden layers resident in shared memory
+// (chunks 0, 2, 4 and the half stage 6: 46 592 B per layer) and streams only the odd ones (1, 3, 5) through a short
+// ring: 120 KB instead of 260 KB per tile from L2.  The chip-wide L2 -> SM rate (~6 300 B/clk, 43 B/clk per SM) is what
+// bounds a kernel that re-streams all weights for every 128-candidate tile (tf32 mode: 520 KB per tile = 12 200 clk).
+template <int MODE, bool FUSE = false, int K0S = 2>
 struct TcSmem {
   using C = ModeCfg<MODE>;
-  static constexpr int NS = FUSE ? C::NSTAGE_FUSED : C::NSTAGE;
+  static constexpr bool RES = MODE == MBO_MLP_FP16 && !FUSE;
+  static constexpr int NS = RES ? (K0S == 1 ? 5 : 4) : (FUSE ? C::NSTAGE_FUSED : C::NSTAGE);
+  static constexpr size_t RES_LAYER_BYTES = RES ? (size_t)3 * C::STAGE_BYTES + C::STAGE_BYTES / 2 : 0;
+  static constexpr size_t W0_SMEM = RES ? (size_t)K0S * (W0_BYTES / 2) : (size_t)W0_BYTES;   // RES: only the slices in use
   static constexpr size_t off_ring = 0;
-  static constexpr size_t off_w0 = off_ring + (size_t)NS * C::STAGE_BYTES;
-  static constexpr size_t off_tail = off_w0 + W0_BYTES;
+  static constexpr size_t off_res = off_ring + (size_t)NS * C::STAGE_BYTES;
+  static constexpr size_t off_w0 = off_res + 3 * RES_LAYER_BYTES;
+  static constexpr size_t off_tail = off_w0 + W0_SMEM;
   static constexpr size_t off_bars = off_tail + sizeof(float) * TAIL_FLOATS;
   static constexpr int n_bars = 2 * NS + C::NCHUNK + 2 + 3 + 4;   // ring, a_ready, d_full[2], feat_full, s_free, w0_full, gp_full[2], gp_empty[2]
   static constexpr size_t off_misc = off_bars + 8 * n_bars;
@@ -377,6 +550,30 @@ template <> struct ChunkOps<MBO_MLP_BF16X3> {
   }
 };
 
+template <> struct ChunkOps<MBO_MLP_FP16> {
+  // 32 columns (16 for the last chunk) -> fp16 pairs in the first half of the chunk's own columns; the bias is
+  // already in the accumulator.  `sat` tracks the largest converted bit pattern (values are >= 0, so unsigned
+  // 16-bit compares order them) for the range check at the end of the kernel.
+  static __device__ __forceinline__ void load(uint32_t taddr, uint32_t* v, int ncols) {
+    if (ncols == 32) tmem_ld32(taddr, v);
+    else tmem_ld16(taddr, v);
+  }
+  static __device__ __forceinline__ void convert_store(uint32_t taddr, uint32_t* v, int ncols, uint32_t& sat) {
+    uint32_t ph[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      ph[j] = 0u;
+      if (2 * j < ncols) {
+        asm("cvt.rn.satfinite.relu.f16x2.f32 %0, %1, %2;"
+            : "=r"(ph[j]) : "f"(__uint_as_float(v[2 * j + 1])), "f"(__uint_as_float(v[2 * j])));
+        sat = __vmaxu2(sat, ph[j]);
+      }
+    }
+    if (ncols == 32) tmem_st16(taddr, ph);
+    else tmem_st8(taddr, ph);
+  }
+};
+
 struct GpFuse {
   const double* gp_state;   // [B, gp_state_doubles(nmax, D)]
   int nmax, kid;
@@ -399,9 +596,10 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
                     const float* __restrict__ epi, float* __restrict__ logits, int* __restrict__ err_flag, int debug_noload,
                     GpFuse gp, TcTopk tk) {
   using C = ModeCfg<MODE>;
-  using SM = TcSmem<MODE, FUSE>;
+  using SM = TcSmem<MODE, FUSE, K0S>;
   constexpr int NTHREADS = FUSE ? TC_THREADS_FUSED : TC_THREADS;
   constexpr int NS = SM::NS;                      // ring depth
+  constexpr bool RES = SM::RES;                   // fp16: even weight stages resident, odd ones streamed
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const PackLayout pl = pack_layout();
@@ -426,6 +624,10 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
   float* s_mu = (float*)(smem + SM::off_musd);            // [2][128]
   float* s_sd = s_mu + 2 * TC_M;                          // [2][128]
 
+#ifdef MBO_TC_TRACE
+  const long long trace_c0 = clock64();
+  const uint64_t trace_g0 = globaltimer_ns();
+#endif
   const int total_tiles = B * tiles_per_episode;
   const int my_tiles = total_tiles > (int)blockIdx.x ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
@@ -442,7 +644,9 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
     for (int i = 0; i < 2; ++i) { mbar_init(BAR_GPFULL(i), 128); mbar_init(BAR_GPEMPTY(i), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = tid; i < TAIL_FLOATS; i += NTHREADS) s_tail[i] = ((const float*)(pack + pl.off_tail))[i];
+  constexpr bool F16 = MODE == MBO_MLP_FP16;
+  for (int i = tid; i < TAIL_FLOATS; i += NTHREADS)
+    s_tail[i] = ((const float*)(pack + (F16 ? pl.off_tailh : pl.off_tail)))[i];
   if (warp == WARP_TMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -456,24 +660,40 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
     // ================= TMA producer (warp-uniform control flow, one elected lane issues) =================
     const bool leader = elect_one();
     if (my_tiles > 0) {
+      const unsigned char* wsrc = pack + (MODE == MBO_MLP_TF32 ? pl.off_tf32 : (F16 ? pl.off_f16 : pl.off_bf16));
       if (leader) {
-        mbar_expect_tx(BAR_W0, W0_BYTES);
-        bulk_g2s(smem_u32(smem + SM::off_w0), pack + pl.off_w0, W0_BYTES, BAR_W0);
+        if constexpr (RES) {
+          // layer-0 weights (only the K slices in use, hi and lo part) + the resident stages, one barrier
+          mbar_expect_tx(BAR_W0, (uint32_t)(SM::W0_SMEM + 3 * SM::RES_LAYER_BYTES));
+          constexpr uint32_t PART = (uint32_t)(SM::W0_SMEM / 2);
+          bulk_g2s(smem_u32(smem + SM::off_w0), pack + pl.off_w0h, PART, BAR_W0);
+          bulk_g2s(smem_u32(smem + SM::off_w0) + PART, pack + pl.off_w0h + W0_BYTES / 2, PART, BAR_W0);
+          for (int l = 0; l < 3; ++l)
+            for (int j = 0; j < 4; ++j)
+              bulk_g2s(smem_u32(smem + SM::off_res) + (uint32_t)(l * SM::RES_LAYER_BYTES) + j * C::STAGE_BYTES,
+                       wsrc + (size_t)(l * C::STAGES_PER_LAYER + 2 * j) * C::STAGE_BYTES,
+                       j < 3 ? C::STAGE_BYTES : C::STAGE_BYTES / 2, BAR_W0);
+        } else {
+          mbar_expect_tx(BAR_W0, W0_BYTES);
+          bulk_g2s(smem_u32(smem + SM::off_w0), pack + (F16 ? pl.off_w0h : pl.off_w0), W0_BYTES, BAR_W0);
+        }
       }
-      const unsigned char* wsrc = pack + (MODE == MBO_MLP_TF32 ? pl.off_tf32 : pl.off_bf16);
       const uint32_t ring_addr = smem_u32(ring);
       uint32_t stage = 0, phase = 0;
       bool ok = true;
       for (int t = 0; t < my_tiles && ok; ++t) {
         for (int ls = 0; ls < 3 * C::STAGES_PER_LAYER; ++ls) {
+          if (RES && ((ls % C::STAGES_PER_LAYER) & 1) == 0) continue;      // even stages are resident
           if (!mbar_wait(BAR_WEMPTY(stage), phase ^ 1u, s_abort)) { ok = false; break; }
           if (leader) {
             if (debug_noload && (t > 0 || ls >= NS)) {
               mbar_arrive(BAR_WFULL(stage));    // timing experiment only: pretend the stage is resident
             } else {
-              mbar_expect_tx(BAR_WFULL(stage), C::STAGE_BYTES);
-              bulk_g2s(ring_addr + stage * C::STAGE_BYTES, wsrc + (size_t)ls * C::STAGE_BYTES, C::STAGE_BYTES,
-                       BAR_WFULL(stage));
+              // fp16 mode: the last stage of a layer holds one slice
+              const uint32_t bytes = (F16 && (ls % C::STAGES_PER_LAYER) == C::STAGES_PER_LAYER - 1) ? C::STAGE_BYTES / 2
+                                                                                                  : C::STAGE_BYTES;
+              mbar_expect_tx(BAR_WFULL(stage), bytes);
+              bulk_g2s(ring_addr + stage * C::STAGE_BYTES, wsrc + (size_t)ls * C::STAGE_BYTES, bytes, BAR_WFULL(stage));
             }
           }
           if (++stage == NS) { stage = 0; phase ^= 1u; }
@@ -488,18 +708,27 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
     if (my_tiles > 0) {
       bool ok = mbar_wait(BAR_W0, 0, s_abort);
       uint32_t stage = 0, wphase = 0, aphase = 0, fphase = 0;
+      long long st_feat = 0, st_a = 0, st_w = 0;
+      (void)st_feat; (void)st_a; (void)st_w;
       const uint32_t w0_lo = desc_lo(smem_u32(smem + SM::off_w0));
       const uint32_t ring_lo = desc_lo(smem_u32(ring));
+      const uint32_t res_lo = desc_lo(smem_u32(smem + SM::off_res));
+      (void)res_lo;
       constexpr uint32_t STAGE_D = C::STAGE_BYTES >> 4;            // descriptor units (16 B)
       constexpr uint32_t SLICE_D = (2 * CHUNK_ROW_BYTES) >> 4;     // one K slice = two 16-byte chunks
       for (int t = 0; t < my_tiles && ok; ++t) {
         // ---- L0: D(R0) = S * W0^T, 3xTF32 ----
-        if (!mbar_wait(BAR_FEAT, fphase, s_abort)) { ok = false; break; }
+        {
+          TC_STAT_BEGIN();
+          if (!mbar_wait(BAR_FEAT, fphase, s_abort)) { ok = false; break; }
+          TC_STAT_END(st_feat);
+        }
         fphase ^= 1u;
         tc_fence_after();
+        TC_TRACE(0);
         if (leader) {
           const uint32_t a_hi = tmem + COL_S, a_lo = tmem + COL_S + 16;
-          constexpr uint32_t W0_PART_D = (uint32_t)((TC_K0 / 4) * CHUNK_ROW_BYTES) >> 4;     // hi -> lo part
+          constexpr uint32_t W0_PART_D = (uint32_t)(RES ? SM::W0_SMEM / 2 : (TC_K0 / 4) * CHUNK_ROW_BYTES) >> 4;   // hi -> lo part
 #pragma unroll
           for (int sl = 0; sl < K0S; ++sl) {
             const uint32_t wl = w0_lo + sl * SLICE_D;
@@ -510,25 +739,77 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
           tc_commit(BAR_SFREE);
           tc_commit(BAR_DFULL(0));
         }
-        // ---- L1..L3 ----
-#pragma unroll
+        TC_TRACE(1);
+        // ---- L1..L3 (rolled: three copies of the chunk loop are instruction-cache footprint for nothing) ----
+#pragma unroll 1
         for (int l = 1; l <= 3; ++l) {
           if (!ok) break;
           const uint32_t tA = tmem + ((l & 1) ? COL_R0 : COL_R1);
           const uint32_t tD = tmem + ((l & 1) ? COL_R1 : COL_R0);
+          if constexpr (F16 && !RES) {
+            // The ring holds two whole layers, so this layer's 7 stages have normally been resident for a long
+            // time: check them all now, while the epilogue is still converting the first chunk.  A ready
+            // mbarrier wait still costs ~80 cycles of latency, and with two 104-cycle MMAs per chunk the issuing
+            // thread cannot afford two of them per chunk.
+            TC_STAT_BEGIN();
+            uint32_t st = stage, ph = wphase;
+#pragma unroll
+            for (int i = 0; i < C::STAGES_PER_LAYER; ++i) {
+              if (!mbar_wait(BAR_WFULL(st), ph, s_abort)) { ok = false; break; }
+              if (++st == NS) { st = 0; ph ^= 1u; }
+            }
+            TC_STAT_END(st_w);
+            if (!ok) break;
+          }
 #pragma unroll
           for (int c = 0; c < C::NCHUNK; ++c) {
             if (!ok) break;
-            if (!mbar_wait(BAR_AREADY(c), aphase, s_abort)) { ok = false; break; }
+            {
+              TC_STAT_BEGIN();
+              if (!mbar_wait(BAR_AREADY(c), aphase, s_abort)) { ok = false; break; }
+              TC_STAT_END(st_a);
+            }
+            TC_TRACE(10 * l + c);
             if (MODE == MBO_MLP_TF32) {
               // chunk c == ring stage: 5 slices of K=8
-              if (!mbar_wait(BAR_WFULL(stage), wphase, s_abort)) { ok = false; break; }
+              {
+                TC_STAT_BEGIN();
+                if (!mbar_wait(BAR_WFULL(stage), wphase, s_abort)) { ok = false; break; }
+                TC_STAT_END(st_w);
+              }
               tc_fence_after();
               if (leader) {
                 const uint32_t lo = ring_lo + stage * STAGE_D;
 #pragma unroll
                 for (int sc = 0; sc < 5; ++sc)
                   mma_ts_tf32(tD, tA + (c * 5 + sc) * 8, make_desc64(lo + sc * SLICE_D), IDESC_TF32, (c | sc) ? 1u : 0u);
+                tc_commit(BAR_WEMPTY(stage));
+              }
+              if (++stage == NS) { stage = 0; wphase ^= 1u; }
+            } else if (RES) {
+              // fp16 pairs of 32 K values in the chunk's first 16 columns = 2 slices (1 in the last chunk);
+              // even chunks read resident weights, odd chunks the ring
+              if (c & 1) {
+                TC_STAT_BEGIN();
+                if (!mbar_wait(BAR_WFULL(stage), wphase, s_abort)) { ok = false; break; }
+                TC_STAT_END(st_w);
+              }
+              tc_fence_after();
+              if (leader) {
+                const uint32_t lo = (c & 1) ? ring_lo + stage * STAGE_D
+                                            : res_lo + (uint32_t)(((l - 1) * SM::RES_LAYER_BYTES + (c >> 1) * C::STAGE_BYTES) >> 4);
+                mma_ts_bf16(tD, tA + c * 32, make_desc64(lo), IDESC_F16, c ? 1u : 0u);
+                if (c != C::NCHUNK - 1) mma_ts_bf16(tD, tA + c * 32 + 8, make_desc64(lo + SLICE_D), IDESC_F16, 1u);
+                if (c & 1) tc_commit(BAR_WEMPTY(stage));
+              }
+              if (c & 1) { if (++stage == NS) { stage = 0; wphase ^= 1u; } }
+            } else if (F16) {
+              // chunk c == ring stage: fp16 pairs of 32 K values in the chunk's first 16 columns = 2 slices (1 in the last)
+              tc_fence_after();
+              if (leader) {
+                const uint32_t lo = ring_lo + stage * STAGE_D;
+                mma_ts_bf16(tD, tA + c * 32, make_desc64(lo), IDESC_F16, c ? 1u : 0u);
+                if (c != C::NCHUNK - 1) mma_ts_bf16(tD, tA + c * 32 + 8, make_desc64(lo + SLICE_D), IDESC_F16, 1u);
                 tc_commit(BAR_WEMPTY(stage));
               }
               if (++stage == NS) { stage = 0; wphase ^= 1u; }
@@ -555,62 +836,68 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
           }
           aphase ^= 1u;
           if (leader) tc_commit(BAR_DFULL(l & 1));
+          TC_TRACE(10 * l + 8);
         }
       }
+#ifdef MBO_TC_TRACE
+      if (lane == 0 && blockIdx.x < 148) {
+        g_tc_trace[5120 + blockIdx.x * 8 + 0] = st_feat;
+        g_tc_trace[5120 + blockIdx.x * 8 + 1] = st_a;
+        g_tc_trace[5120 + blockIdx.x * 8 + 2] = st_w;
+      }
+#endif
     }
-  } else if (warp < WARP_TMA) {
-    // ================= epilogue warps =================
-    // warp w: TMEM lanes 32*(w&3)..+31 (thread = candidate row), column half h = w>>2:
-    // half h converts chunks h, h+2, ...; half 1 also builds the next tile's features
+  } else if (warp < WARP_TMA || !FUSE) {
+    // ================= epilogue warps (0-7) and feature warps (10-13, !FUSE) =================
+    // epilogue warp w: TMEM lanes 32*(w&3)..+31 (thread = candidate row), column half h = w>>2:
+    // half h converts chunks h, h+2, ...; FUSE: half 1 also builds the next tile's features (the GP warps feed it)
+    const bool feat_warp = warp >= WARP_GP0;
     const int quad = warp & 3, half = warp >> 2;
     const int row = quad * 32 + lane;                       // 0..127
     const uint32_t tlane = tmem + ((uint32_t)(quad * 32) << 16);
-    uint32_t dphase[2] = {0, 0};
+    uint32_t dph = 0;                                // bit i = phase of d_full[i]
     uint32_t sphase = 0;
+    uint32_t sat = 0u;                               // fp16 mode: largest activation bit pattern seen
     bool ok = true;
+    long long st_d = 0, st_build = 0;
+    (void)st_d; (void)st_build;
     const float* s_w4 = s_tail + 4 * TC_N;          // s_tail = [zeros | b1 | b2 | b3 | w4 | b4]
 
     // Feature vector of this thread's row for tile `t_idx` (fp32, ones column appended).  It is gathered one tile
     // AHEAD into registers (`pf`) so that the global-memory latency of mean/std/candidates never sits between the
     // last hidden-layer epilogue and the head epilogue (half-0 warps wait for half-1 at the pair barrier there).
     constexpr int KF = 8 * K0S;                        // feature slots (incl. the ones column)
+    // All loops here are rolled and `f` is indexed at run time (local memory): this code runs once per tile on warps
+    // with plenty of slack, and its size is what matters (the unrolled version was 1 400 of the kernel's 4 700
+    // instructions and streamed through the instruction cache on every tile).
     auto gather_features = [&](int t_idx, float* f) {
       const int tile = (int)blockIdx.x + t_idx * (int)gridDim.x;
       const int b = tile / tiles_per_episode;
       const int m = (tile - b * tiles_per_episode) * TC_M + row;
-#pragma unroll
+#pragma unroll 1
       for (int i = 0; i < KF; ++i) f[i] = 0.f;
       if (t_idx >= my_tiles || m >= cand.M) return;
       if (fs.dense) {
         const float* srow = fs.dense + ((size_t)b * cand.M + m) * fs.dense_F;
-#pragma unroll
-        for (int i = 0; i < KF - 1; ++i)
-          if (i < fs.F) f[i] = srow[fs.src[i]];
+#pragma unroll 1
+        for (int i = 0; i < fs.F; ++i) f[i] = srow[fs.src[i]];
       } else {
         double x[MBO_MAX_D];
-#pragma unroll
-        for (int d = 0; d < MBO_MAX_D; ++d) x[d] = 0.0;
-        load_candidate(cand, b, m, x);
+        load_candidate_rolled(cand, b, m, x);
         float mu = 0.f, sd = 0.f;
         if (!FUSE) { mu = mean[(size_t)b * cand.M + m]; sd = std_[(size_t)b * cand.M + m]; }
-#pragma unroll
-        for (int i = 0; i < KF - 1; ++i) {
-          if (i < fs.F) {
-            const int s = fs.src[i];
-            float v;
-            if (s == MBO_FEAT_MEAN) v = mu;
-            else if (s == MBO_FEAT_STD) v = sd;
-            else if (s >= MBO_FEAT_X0 && s < MBO_FEAT_X0 + MBO_MAX_D) {
-              v = 0.f;
-#pragma unroll
-              for (int d = 0; d < MBO_MAX_D; ++d) if (s - MBO_FEAT_X0 == d) v = (float)x[d];
-            } else v = epi[b * 4 + (s - MBO_FEAT_INCUMBENT)];
-            f[i] = v;
-          }
+#pragma unroll 1
+        for (int i = 0; i < fs.F; ++i) {
+          const int s = fs.src[i];
+          float v;
+          if (s == MBO_FEAT_MEAN) v = mu;
+          else if (s == MBO_FEAT_STD) v = sd;
+          else if (s >= MBO_FEAT_X0 && s < MBO_FEAT_X0 + MBO_MAX_D) v = (s - MBO_FEAT_X0 < cand.D) ? (float)x[s - MBO_FEAT_X0] : 0.f;
+          else v = epi[b * 4 + (s - MBO_FEAT_INCUMBENT)];
+          f[i] = v;
         }
       }
-#pragma unroll
-      for (int i = 0; i < KF; ++i) if (i == fs.F) f[i] = 1.0f;    // bias column
+      f[fs.F] = 1.0f;    // bias column
     };
     float pf[KF];                                   // prefetched features of the next tile to be built
 
@@ -647,18 +934,43 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR_FEAT);
-      gather_features(t_idx + 1, pf);                  // loads for the next tile are in flight from here on
+      if (FUSE) gather_features(t_idx + 1, pf);
     };
 
-    if (my_tiles > 0 && half == 1) { gather_features(0, pf); build_features(0); }
+    if (feat_warp) {
+      // ---- feature warps: S(t) may be overwritten once L0(t-1) has been committed (s_free) ----
+#pragma unroll 1
+      for (int t = -1; t < my_tiles && ok; ++t) {
+        if (t > 0) {
+          if (!mbar_wait(BAR_SFREE, sphase, s_abort)) { ok = false; break; }
+          sphase ^= 1u;
+          tc_fence_after();
+        }
+        if (quad == 0) TC_TRACE(300);
+        {
+          TC_STAT_BEGIN();
+          if (t >= 0) build_features(t);
+          gather_features(t + 1, pf);                  // one tile ahead: the loads land while this warp waits for s_free
+          TC_STAT_END(st_build);
+        }
+        if (quad == 0) TC_TRACE(301);
+      }
+    }
+    if (FUSE && my_tiles > 0 && half == 1) { gather_features(0, pf); build_features(0); }
     constexpr int MAXI = (C::NCHUNK + 1) / 2;
-    for (int t = 0; t < my_tiles && ok; ++t) {
+    for (int t = 0; t < my_tiles && ok && !feat_warp; ++t) {
       // ---- E0..E2: relu(D + b) -> next layer's A operand, in place ----
+#pragma unroll 1
       for (int l = 0; l < 3 && ok; ++l) {
         const uint32_t col = (l & 1) ? COL_R1 : COL_R0;
-        if (!mbar_wait(BAR_DFULL(l & 1), dphase[l & 1], s_abort)) { ok = false; break; }
-        dphase[l & 1] ^= 1u;
+        {
+          TC_STAT_BEGIN();
+          if (!mbar_wait(BAR_DFULL(l & 1), (dph >> (l & 1)) & 1u, s_abort)) { ok = false; break; }
+          TC_STAT_END(st_d);
+        }
+        dph ^= 1u << (l & 1);
         tc_fence_after();
+        if (quad == 0) TC_TRACE(100 + 100 * half + 20 * l);
         const float* bias = s_tail + l * TC_N;
         uint32_t va[40], vb[40];
         auto ncols_of = [&](int c) { return (MODE == MBO_MLP_TF32) ? 40 : (c == C::NCHUNK - 1 ? 16 : 32); };
@@ -671,28 +983,37 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
             uint32_t* nxt = (i & 1) ? va : vb;
             tmem_wait_ld();
             if (c + 2 < C::NCHUNK) ChunkOps<MODE>::load(tlane + col + (c + 2) * C::CHUNK_COLS, nxt, ncols_of(c + 2));
-            ChunkOps<MODE>::convert_store(tlane + col + c * C::CHUNK_COLS, cur, bias + c * C::CHUNK_COLS, ncols_of(c));
+            if constexpr (F16) ChunkOps<MODE>::convert_store(tlane + col + c * C::CHUNK_COLS, cur, ncols_of(c), sat);
+            else ChunkOps<MODE>::convert_store(tlane + col + c * C::CHUNK_COLS, cur, bias + c * C::CHUNK_COLS, ncols_of(c));
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR_AREADY(c));
+            if (quad == 0) TC_TRACE(100 + 100 * half + 20 * l + 1 + i);
           }
         }
-        if (l == 2 && half == 1) {
+        if (FUSE && l == 2 && half == 1) {
           if (t + 1 < my_tiles) {
             // features of the next tile while L3 runs
             if (!mbar_wait(BAR_SFREE, sphase, s_abort)) { ok = false; break; }
             tc_fence_after();
+            if (quad == 0) TC_TRACE(100 + 100 * half + 80);
             build_features(t + 1);
+            if (quad == 0) TC_TRACE(100 + 100 * half + 81);
           }
           sphase ^= 1u;
         }
       }
       if (!ok) break;
       // ---- E3: logit = relu(D + b3) . w4 + b4, columns split between the two halves ----
-      if (!mbar_wait(BAR_DFULL(1), dphase[1], s_abort)) { ok = false; break; }
-      dphase[1] ^= 1u;
+      {
+        TC_STAT_BEGIN();
+        if (!mbar_wait(BAR_DFULL(1), (dph >> 1) & 1u, s_abort)) { ok = false; break; }
+        TC_STAT_END(st_d);
+      }
+      dph ^= 2u;
       tc_fence_after();
+      if (quad == 0) TC_TRACE(100 + 100 * half + 70);
       float acc = 0.f;
       {
         const int cb = half * 104;
@@ -703,25 +1024,48 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
         tmem_ld8(tlane + COL_R1 + cb + 96, v1 + 32);
         const float4* b3 = reinterpret_cast<const float4*>(s_tail + 3 * TC_N + cb);
         const float4* w4 = reinterpret_cast<const float4*>(s_w4 + cb);
+        if constexpr (F16) {       // b3 is already in the accumulator; two independent chains
+          float acc2 = 0.f;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float4 b = b3[j], w = w4[j];
-          acc = fmaf(fmaxf(__uint_as_float(v0[4 * j + 0]) + b.x, 0.f), w.x, acc);
-          acc = fmaf(fmaxf(__uint_as_float(v0[4 * j + 1]) + b.y, 0.f), w.y, acc);
-          acc = fmaf(fmaxf(__uint_as_float(v0[4 * j + 2]) + b.z, 0.f), w.z, acc);
-          acc = fmaf(fmaxf(__uint_as_float(v0[4 * j + 3]) + b.w, 0.f), w.w, acc);
-        }
-        tmem_wait_ld();
+          for (int j = 0; j < 16; ++j) {
+            const float4 w = w4[j];
+            acc = fmaf(fmaxf(__uint_as_float(v0[4 * j + 0]), 0.f), w.x, acc);
+            acc2 = fmaf(fmaxf(__uint_as_float(v0[4 * j + 1]), 0.f), w.y, acc2);
+            acc = fmaf(fmaxf(__uint_as_float(v0[4 * j + 2]), 0.f), w.z, acc);
+            acc2 = fmaf(fmaxf(__uint_as_float(v0[4 * j + 3]), 0.f), w.w, acc2);
+          }
+          tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 10; ++j) {
-          const float4 b = b3[16 + j], w = w4[16 + j];
-          acc = fmaf(fmaxf(__uint_as_float(v1[4 * j + 0]) + b.x, 0.f), w.x, acc);
-          acc = fmaf(fmaxf(__uint_as_float(v1[4 * j + 1]) + b.y, 0.f), w.y, acc);
-          acc = fmaf(fmaxf(__uint_as_float(v1[4 * j + 2]) + b.z, 0.f), w.z, acc);
-          acc = fmaf(fmaxf(__uint_as_float(v1[4 * j + 3]) + b.w, 0.f), w.w, acc);
+          for (int j = 0; j < 10; ++j) {
+            const float4 w = w4[16 + j];
+            acc = fmaf(fmaxf(__uint_as_float(v1[4 * j + 0]), 0.f), w.x, acc);
+            acc2 = fmaf(fmaxf(__uint_as_float(v1[4 * j + 1]), 0.f), w.y, acc2);
+            acc = fmaf(fmaxf(__uint_as_float(v1[4 * j + 2]), 0.f), w.z, acc);
+            acc2 = fmaf(fmaxf(__uint_as_float(v1[4 * j + 3]), 0.f), w.w, acc2);
+          }
+          acc += acc2;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float4 b = b3[j], w = w4[j];
+            acc = fmaf(fmaxf(__uint_as_float(v0[4 * j + 0]) + b.x, 0.f), w.x, acc);
+            acc = fmaf(fmaxf(__uint_as_float(v0[4 * j + 1]) + b.y, 0.f), w.y, acc);
+            acc = fmaf(fmaxf(__uint_as_float(v0[4 * j + 2]) + b.z, 0.f), w.z, acc);
+            acc = fmaf(fmaxf(__uint_as_float(v0[4 * j + 3]) + b.w, 0.f), w.w, acc);
+          }
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 10; ++j) {
+            const float4 b = b3[16 + j], w = w4[16 + j];
+            acc = fmaf(fmaxf(__uint_as_float(v1[4 * j + 0]) + b.x, 0.f), w.x, acc);
+            acc = fmaf(fmaxf(__uint_as_float(v1[4 * j + 1]) + b.y, 0.f), w.y, acc);
+            acc = fmaf(fmaxf(__uint_as_float(v1[4 * j + 2]) + b.z, 0.f), w.z, acc);
+            acc = fmaf(fmaxf(__uint_as_float(v1[4 * j + 3]) + b.w, 0.f), w.w, acc);
+          }
         }
       }
       tc_fence_before();   // order this tile's TMEM reads before the next hand-offs
+      if (quad == 0) TC_TRACE(100 + 100 * half + 71);
       float lgt = 0.f;
       int tile_m = 0x7fffffff, tile_id = 0;
       if (half == 1) s_part[row] = acc;
@@ -736,6 +1080,7 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
         if (logits && m < cand.M) logits[(size_t)b * cand.M + m] = lgt;
       }
       asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");   // s_part reusable
+      if (quad == 0) TC_TRACE(100 + 100 * half + 72);
       if (tk.k && half == 0) {
         // warp top-k over this warp's 32 rows (value descending, index ascending; NaN / padding never win), off the
         // pair barrier's critical path; two REDUX per round on an order-preserving integer key
@@ -745,6 +1090,7 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
         int mi = valid ? tile_m : 0x7fffffff;
         uint32_t outk = 0u;
         int outm = 0x7fffffff;
+#pragma unroll 1
         for (int r = 0; r < tk.k; ++r) {
           const uint32_t bk = __reduce_max_sync(0xffffffffu, key);
           const int bm = __reduce_min_sync(0xffffffffu, key == bk ? mi : 0x7fffffff);
@@ -759,6 +1105,12 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
         }
       }
     }
+#ifdef MBO_TC_TRACE
+    if (lane == 0 && blockIdx.x < 148 && warp == 0) g_tc_trace[5120 + blockIdx.x * 8 + 3] = st_d;
+    if (lane == 0 && blockIdx.x < 148 && warp == WARP_GP0) g_tc_trace[5120 + blockIdx.x * 8 + 4] = st_build;
+#endif
+    // fp16 mode: an activation at the range limit (65504, or NaN) was clamped somewhere -> bit 1 of the flag
+    if (F16 && ((sat & 0xffffu) >= 0x7bffu || (sat >> 16) >= 0x7bffu)) atomicOr(err_flag, 2);
   } else if (FUSE) {
     // ================= fused GP posterior warps (fp64): thread = candidate row of the NEXT tile =================
     // mean = v.beta + m, var = max(k** - |v|^2, 1e-15), v = Linv k*  (same arithmetic as gp_posterior_kernel<double>),
@@ -891,7 +1243,17 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (tid == 0 && *s_abort) atomicExch(err_flag, 1);
+#ifdef MBO_TC_TRACE
+  if (tid == 0 && blockIdx.x < 148) {     // per-CTA totals: cycles, nanoseconds, tiles
+    g_tc_trace[4096 + blockIdx.x * 3 + 0] = clock64() - trace_c0;
+    g_tc_trace[4096 + blockIdx.x * 3 + 1] = (long long)(globaltimer_ns() - trace_g0);
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    g_tc_trace[4096 + blockIdx.x * 3 + 2] = my_tiles + ((long long)smid << 20);
+  }
+#endif
+  if (tid == 0 && *s_abort) atomicOr(err_flag, 1);
+  if (F16 && tid == 0 && ((const int*)(pack + pl.off_scale))[4]) atomicOr(err_flag, 2);   // a packed weight/bias was clamped
   if (warp == WARP_TMA) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
@@ -947,7 +1309,7 @@ template <int MODE, bool FUSE, int K0S>
 static int launch_tc_k(const mbo_policy* p, int B, const TcFeat& fs, const mbo_candidates& cand, const float* mean,
                      const float* std_, const float* epi, float* logits, int* err_flag, cudaStream_t s,
                      const GpFuse& gp, const TcTopk& tk) {
-  using SM = TcSmem<MODE, FUSE>;
+  using SM = TcSmem<MODE, FUSE, K0S>;
   auto kern = neural_af_tc_kernel<MODE, FUSE, K0S>;
   MBO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::total));
   if (g_num_sms == 0) {
@@ -1002,8 +1364,14 @@ int tc_forward(const mbo_policy* p, int mode, int B, int F, const int32_t* feat_
     tk.part_idx = (int32_t*)((char*)ws + 256 + n_part * 4);
   }
   int rc;
+  if (mode == MBO_MLP_FP16 && !p->tc_f16) {
+    set_error("MBO_MLP_FP16 needs H <= %d (two spare K columns carry the bias); use MBO_MLP_TF32", TC_N - 2);
+    return MBO_ERR_UNSUPPORTED;
+  }
   if (mode == MBO_MLP_TF32)
     rc = launch_tc<MBO_MLP_TF32, false>(p, B, fs, *cand, mean, std_, epi, logits, err_flag, s, gp, tk);
+  else if (mode == MBO_MLP_FP16)
+    rc = launch_tc<MBO_MLP_FP16, false>(p, B, fs, *cand, mean, std_, epi, logits, err_flag, s, gp, tk);
   else
     rc = launch_tc<MBO_MLP_BF16X3, false>(p, B, fs, *cand, mean, std_, epi, logits, err_flag, s, gp, tk);
   if (rc || !topk) return rc;
@@ -1026,7 +1394,7 @@ extern "C" int mbo_af_eval_fused(const mbo_policy* p, int mode, int B, int nmax,
                                  const float* epi, float* logits, float* mean_out, float* std_out, void* workspace,
                                  size_t workspace_bytes, void* stream) {
   MBO_CHECK_ARG(p && gp_state && feat_src && cand && epi && logits, "mbo_af_eval_fused: null pointer");
-  MBO_CHECK_ARG(mode == MBO_MLP_TF32 || mode == MBO_MLP_BF16X3, "mbo_af_eval_fused: tensor-core modes only");
+  MBO_CHECK_ARG(mode == MBO_MLP_TF32 || mode == MBO_MLP_BF16X3 || mode == MBO_MLP_FP16, "mbo_af_eval_fused: tensor-core modes only");
   if (!p->tc_ready) {
     set_error("mbo_af_eval_fused needs a F->H->H->H->H->1 ReLU policy with F <= %d and H <= %d", TC_K0 - 1, TC_N);
     return MBO_ERR_UNSUPPORTED;
@@ -1064,7 +1432,21 @@ extern "C" int mbo_af_eval_fused(const mbo_policy* p, int mode, int B, int nmax,
   cudaStream_t s = (cudaStream_t)stream;
   TcTopk tk;
   memset(&tk, 0, sizeof(tk));
+  if (mode == MBO_MLP_FP16 && !p->tc_f16) {
+    set_error("MBO_MLP_FP16 needs H <= %d (two spare K columns carry the bias); use MBO_MLP_TF32", TC_N - 2);
+    return MBO_ERR_UNSUPPORTED;
+  }
   if (mode == MBO_MLP_TF32)
     return launch_tc<MBO_MLP_TF32, true>(p, B, fs, *cand, nullptr, nullptr, epi, logits, (int*)workspace, s, gp, tk);
+  if (mode == MBO_MLP_FP16)
+    return launch_tc<MBO_MLP_FP16, true>(p, B, fs, *cand, nullptr, nullptr, epi, logits, (int*)workspace, s, gp, tk);
   return launch_tc<MBO_MLP_BF16X3, true>(p, B, fs, *cand, nullptr, nullptr, epi, logits, (int*)workspace, s, gp, tk);
 }
+
+#ifdef MBO_TC_TRACE
+extern "C" int mbo_debug_tc_trace(long long* host_out, int n) {
+  MBO_CUDA(cudaDeviceSynchronize());
+  MBO_CUDA(cudaMemcpyFromSymbol(host_out, g_tc_trace, sizeof(long long) * (n < 8192 ? n : 8192)));
+  return MBO_OK;
+}
+#endif

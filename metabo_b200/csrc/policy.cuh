@@ -15,5 +15,6 @@ struct mbo_policy {
   void* d_tc = nullptr;
   size_t tc_bytes = 0;
   int tc_ready = 0;       // 1 when the architecture is F->H->H->H->H->1 ReLU with H <= 208
+  int tc_f16 = 0;         // 1 when additionally H <= 206 (MBO_MLP_FP16 folds the bias into two spare K columns)
   int tc_H = 0, tc_F = 0;
 };

@@ -111,6 +111,8 @@ class AFEngine:
         w = [int(x.shape[0]) for x in weights]
         self.tc_ok = (activation == "relu" and len(weights) == 5 and len(set(w[:4])) == 1 and 8 <= w[0] <= 208
                       and w[4] == 1 and int(weights[0].shape[1]) <= 15)
+        if self.mlp_mode == L.MLP_FP16 and w[0] > 206:
+            self.mlp_mode = L.MLP_TF32    # fp16 mode needs two spare K columns; tf32 has the same significand
 
     def set_value_net(self, weights, biases, activation="relu"):
         self.value = ops.PolicyHandle()

@@ -56,7 +56,7 @@ class VecMetaBO:
                 r.seed(int(s))
                 self.rngs.append(r)
         gp_prec = {"fp64": L.GP_FP64, "fp32": L.GP_FP32}[gp_precision]
-        mode = {"fp32": L.MLP_FP32, "tf32": L.MLP_TF32, "bf16x3": L.MLP_BF16X3}[mlp_mode]
+        mode = L.MLP_MODES[mlp_mode]
         common = dict(kernel=self.kernel, use_prior_mean=self.use_prior_mean_function, gp_precision=gp_prec,
                       mlp_mode=mode, device=device, T_training=kwargs.get("T_training"))
         if self.do_local_af_opt:

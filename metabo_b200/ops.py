@@ -132,9 +132,14 @@ class PolicyHandle:
 
     def check(self):
         """Synchronises and raises if a tensor-core kernel reported a pipeline time-out."""
-        if self.ws is not None and int(self.ws[0].item()) != 0:
-            self.ws.zero_()
-            raise L.MboError("neural_af_tc kernel aborted: an mbarrier wait timed out (pipeline bug)")
+        if self.ws is not None:
+            flag = int(self.ws[0].item())
+            if flag != 0:
+                self.ws.zero_()
+                if flag & 1:
+                    raise L.MboError("neural_af_tc kernel aborted: an mbarrier wait timed out (pipeline bug)")
+                raise L.MboError("MBO_MLP_FP16: a hidden activation reached the fp16 range limit and was clamped; "
+                                 "use mlp_mode 'tf32' or 'bf16x3' for this policy")
 
     def __del__(self):
         try:

@@ -13,7 +13,7 @@ from .. import _lib as L
 from .. import ops
 from .mlp import MLP
 
-_MODES = {"fp32": L.MLP_FP32, "tf32": L.MLP_TF32, "bf16x3": L.MLP_BF16X3}
+_MODES = L.MLP_MODES
 
 
 class NeuralAF(nn.Module):
@@ -107,6 +107,8 @@ class NeuralAF(nn.Module):
         mode = _MODES[self.mlp_mode]
         if mode != L.MLP_FP32 and not self.tensor_core_ok():
             mode = L.MLP_FP32
+        if mode == L.MLP_FP16 and self.policy_net.arch_spec[0] > 206:
+            mode = L.MLP_TF32          # fp16 mode needs two spare K columns; tf32 has the same significand
         return mode
 
     def tensor_core_ok(self):

@@ -16,7 +16,7 @@ from oracle import sampling_oracle as S
 pytestmark = pytest.mark.gpu
 
 CASES = [("bra", "weights_bra_1635.npz"), ("hm3", "weights_hm3_1988.npz"), ("gps", "weights_gps_1161.npz")]
-MODES = [("fp32", 0, 1e-5), ("tf32", 1, 1e-3), ("bf16x3", 2, 2e-5)]
+MODES = [("fp32", 0, 1e-5), ("tf32", 1, 1e-3), ("bf16x3", 2, 2e-5), ("fp16", 3, 1e-3)]
 
 
 def feat_codes(features, D, mask):
@@ -182,7 +182,7 @@ def test_sampler_matches_oracle_noise_and_distribution():
     assert chi2 < 30.0                                       # 7 dof, p ~ 1e-4
 
 
-@pytest.mark.parametrize("mode_name,mode,tol", [("tf32", 1, 1e-3), ("bf16x3", 2, 2e-5)])
+@pytest.mark.parametrize("mode_name,mode,tol", [("tf32", 1, 1e-3), ("bf16x3", 2, 2e-5), ("fp16", 3, 1e-3)])
 def test_fused_gp_mlp_kernel_matches_two_kernel_path(golden_dir, mode_name, mode, tol):
     """mbo_af_eval_fused (fp64 GP warps inside the tensor-core kernel) == mbo_gp_posterior (fp64) +
     mbo_af_logits on the same inputs: identical mean/std (bitwise, same arithmetic) and logits within
@@ -302,7 +302,7 @@ def test_tensor_core_kernel_with_wide_feature_vectors(D):
     assert float((ref.double() - truth).abs().max()) <= 1e-5 * scale
     # random N(0, 0.08) nets cancel heavily (|logit| ~ 0.3 from O(1) hidden activations): TF32's operand rounding is
     # then ~4e-3 of max|logit| (bf16x3: ~1e-4); the 1e-3 bar is stated (and tested above) on the shipped policies
-    for mode, tol in ((1, 1e-2), (2, 3e-4)):
+    for mode, tol in ((1, 1e-2), (2, 3e-4), (3, 1e-2)):
         got = ops.af_logits(pol, codes, cs, mean, std, epi, B, mode=mode)
         torch.cuda.synchronize(); pol.check()
         assert float((got.double() - truth).abs().max()) <= tol * scale, (D, mode)
@@ -366,7 +366,7 @@ def test_full_size_properties_hartmann3_batch(golden_dir):
     assert torch.equal(v, lg[2].max(dim=1).values) and torch.equal(a.long(), idx[:, 0].long())
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3])
 def test_fused_topk_epilogue_equals_logits_then_topk(golden_dir, mode):
     """mbo_af_topk (selection inside the tensor-core kernel's epilogue + merge kernel, logits optional) returns
     exactly what mbo_af_logits followed by mbo_logits_topk returns; ragged M, exact ties, k = 1 and 5."""
@@ -396,3 +396,91 @@ def test_fused_topk_epilogue_equals_logits_then_topk(golden_dir, mode):
             assert torch.equal(lg2, lg)
             assert torch.equal(i1, ri) and torch.equal(v1, rv), (B, M, k)
             assert torch.equal(i2, ri) and torch.equal(v2, rv), (B, M, k)
+
+
+def _random_relu_net(rng, F, H, w_std, b_std, dev):
+    dims = [F, H, H, H, H, 1]
+    W = [torch.as_tensor(rng.normal(0, w_std, (dims[i + 1], dims[i])).astype(np.float32), device=dev) for i in range(5)]
+    b = [torch.as_tensor(rng.normal(0, b_std, dims[i + 1]).astype(np.float32), device=dev) for i in range(5)]
+    return W, b
+
+
+def _truth_logits(W, b, feats):
+    h = feats.double()
+    for i in range(4):
+        h = torch.relu(h @ W[i].double().T + b[i].double())
+    return (h @ W[4].double().T + b[4].double())[..., 0]
+
+
+@pytest.mark.parametrize("w_std,b_std", [(1e-4, 1e-5), (0.01, 0.0), (0.07, 0.05), (30.0, 10.0)])
+def test_fp16_mode_renormalises_layers_by_powers_of_two(w_std, b_std):
+    """MBO_MLP_FP16 folds a power-of-two scale into layers whose weights are far from O(1) (exact, ReLU is
+    positively homogeneous): nets whose activations would underflow (w ~ 1e-4: a4 ~ 1e-12) or overflow
+    (w ~ 30: a4 ~ 1e9) in plain fp16 agree with the fp64 truth as closely as the tf32 mode does."""
+    from metabo_b200 import ops, _lib as L
+    dev = torch.device("cuda:0")
+    rng = np.random.RandomState(5)
+    D, B, M = 3, 2, 1000
+    W, b = _random_relu_net(rng, 7, 200, w_std, b_std, dev)
+    b[4].zero_()                      # keep the (tiny or huge) hidden signal visible in the fp32 logit
+    pol = ops.PolicyHandle(); pol.set_weights(W, b, "relu")
+    cs = ops.CandidateSet(D, tail=torch.as_tensor(rng.rand(M, D), device=dev))
+    mean = torch.as_tensor(rng.randn(B, M).astype(np.float32), device=dev)
+    std = torch.as_tensor(rng.rand(B, M).astype(np.float32), device=dev)
+    epi = torch.as_tensor(np.array([[0.1, 0.2, 6.0, 30.0]] * B, dtype=np.float32), device=dev)
+    codes = [0, 1, 2, 3, 4, 12, 13]
+    x = cs.tail.float()[None].expand(B, M, D)
+    feats = torch.cat([mean[..., None], std[..., None], x, epi[:, None, 2:3].expand(B, M, 1), epi[:, None, 3:4].expand(B, M, 1)], 2)
+    truth = _truth_logits(W, b, feats)
+    scale = float(truth.abs().max())
+    e16 = float((ops.af_logits(pol, codes, cs, mean, std, epi, B, mode=L.MLP_FP16).double() - truth).abs().max())
+    e32 = float((ops.af_logits(pol, codes, cs, mean, std, epi, B, mode=L.MLP_TF32).double() - truth).abs().max())
+    torch.cuda.synchronize(); pol.check()
+    assert e16 <= 4.0 * e32 + 1e-6 * scale, (w_std, e16, e32, scale)
+    assert e16 <= 2e-2 * scale                                    # random nets cancel heavily, see the wide-feature test
+
+
+def test_fp16_mode_flags_activations_beyond_its_range():
+    """A layer-0 row norm inside the unscaled band but inputs of 1e6 push activations past 65504: the kernel clamps
+    (satfinite) and raises bit 1 of the workspace flag, which PolicyHandle.check() turns into an error."""
+    from metabo_b200 import ops, _lib as L
+    dev = torch.device("cuda:0")
+    rng = np.random.RandomState(6)
+    W, b = _random_relu_net(rng, 7, 200, 0.07, 0.0, dev)
+    W[0] = W[0] * 5.0
+    pol = ops.PolicyHandle(); pol.set_weights(W, b, "relu")
+    B, M = 1, 300
+    cs = ops.CandidateSet(3, tail=torch.as_tensor(rng.rand(M, 3), device=dev))
+    mean = torch.full((B, M), 1e6, dtype=torch.float32, device=dev)
+    std = torch.ones((B, M), dtype=torch.float32, device=dev)
+    epi = torch.as_tensor(np.array([[0.1, 0.2, 6.0, 30.0]], dtype=np.float32), device=dev)
+    lg = ops.af_logits(pol, [0, 1, 2, 3, 4, 12, 13], cs, mean, std, epi, B, mode=L.MLP_FP16)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(lg).all())
+    with pytest.raises(L.MboError, match="fp16 range"):
+        pol.check()
+    ops.af_logits(pol, [0, 1, 2, 3, 4, 12, 13], cs, mean, std, epi, B, mode=L.MLP_TF32)   # tf32 has fp32's range
+    torch.cuda.synchronize(); pol.check()
+
+
+def test_fp16_mode_needs_two_spare_columns():
+    from metabo_b200 import ops, _lib as L
+    dev = torch.device("cuda:0")
+    rng = np.random.RandomState(8)
+    for H, ok in ((206, True), (208, False)):
+        W, b = _random_relu_net(rng, 7, H, 0.07, 0.05, dev)
+        pol = ops.PolicyHandle(); pol.set_weights(W, b, "relu")
+        M = 130
+        cs = ops.CandidateSet(3, tail=torch.as_tensor(rng.rand(M, 3), device=dev))
+        mean = torch.as_tensor(rng.randn(1, M).astype(np.float32), device=dev)
+        std = torch.as_tensor(rng.rand(1, M).astype(np.float32), device=dev)
+        epi = torch.as_tensor(np.array([[0.1, 0.2, 6.0, 30.0]], dtype=np.float32), device=dev)
+        codes = [0, 1, 2, 3, 4, 12, 13]
+        ref = ops.af_logits(pol, codes, cs, mean, std, epi, 1, mode=L.MLP_FP32)
+        if ok:
+            got = ops.af_logits(pol, codes, cs, mean, std, epi, 1, mode=L.MLP_FP16)
+            torch.cuda.synchronize(); pol.check()
+            assert float((got - ref).abs().max()) <= 1e-2 * float(ref.abs().max())
+        else:
+            with pytest.raises(L.MboError, match="H <= 206"):
+                ops.af_logits(pol, codes, cs, mean, std, epi, 1, mode=L.MLP_FP16)

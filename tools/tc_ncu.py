@@ -3,7 +3,7 @@ import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from metabo_b200 import ops
-mode = {"tf32": 1, "bf16x3": 2}[sys.argv[1] if len(sys.argv) > 1 else "tf32"]
+mode = {"tf32": 1, "bf16x3": 2, "fp16": 3}[sys.argv[1] if len(sys.argv) > 1 else "tf32"]
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 M = int(sys.argv[3]) if len(sys.argv) > 3 else 10000
 dev = torch.device("cuda:0")

@@ -16,7 +16,7 @@ for B, M in [(1,128),(1,100),(3,1733),(64,10000)]:
     std = torch.as_tensor(rng.rand(B,M).astype(np.float32), device=dev)
     epi = torch.as_tensor(np.stack([np.zeros(B), np.full(B,0.4), rng.randint(0,30,B).astype(float), np.full(B,30.)],1).astype(np.float32), device=dev)
     ref = ops.af_logits(pol, codes, cs, mean, std, epi, B, mode=0)
-    for name, mode in (("tf32",1),("bf16x3",2)):
+    for name, mode in (("fp16",3),("tf32",1),("bf16x3",2)):
         try:
             got = ops.af_logits(pol, codes, cs, mean, std, epi, B, mode=mode)
             torch.cuda.synchronize(); pol.check()
@@ -29,7 +29,7 @@ B, M = 1024, 10000
 x = torch.as_tensor(rng.rand(M,3), device=dev); cs = ops.CandidateSet(3, tail=x)
 mean = torch.randn(B,M,device=dev); std = torch.rand(B,M,device=dev)
 epi = torch.zeros(B,4,device=dev); epi[:,2]=15; epi[:,3]=30
-for name, mode in (("tf32",1),("bf16x3",2),("fp32",0)):
+for name, mode in (("fp16",3),("tf32",1),("bf16x3",2),("fp32",0)):
     try:
         lg = ops.af_logits(pol, codes, cs, mean, std, epi, B, mode=mode); torch.cuda.synchronize()
         s,e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
