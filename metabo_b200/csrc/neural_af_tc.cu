@@ -50,9 +50,11 @@ __device__ long long g_tc_trace[8192];
 #ifndef MBO_TC_TRACE_T0
 #define MBO_TC_TRACE_T0 200
 #endif
-#define TC_TRACE(slot) do { if ((blockIdx.x == 0 || blockIdx.x == MBO_TC_TRACE_CTA_B) && t >= MBO_TC_TRACE_T0 && t < MBO_TC_TRACE_T0 + 4 && lane == 0) g_tc_trace[(blockIdx.x ? 2048 : 0) + (t - MBO_TC_TRACE_T0) * 512 + (slot)] = clock64(); } while (0)
+#define TC_TRACE_T(tt, slot) do { if ((blockIdx.x == 0 || blockIdx.x == MBO_TC_TRACE_CTA_B) && (tt) >= MBO_TC_TRACE_T0 && (tt) < MBO_TC_TRACE_T0 + 4 && lane == 0) g_tc_trace[(blockIdx.x ? 2048 : 0) + ((tt) - MBO_TC_TRACE_T0) * 512 + (slot)] = clock64(); } while (0)
+#define TC_TRACE(slot) TC_TRACE_T(t, slot)
 #else
 #define TC_TRACE(slot) do { } while (0)
+#define TC_TRACE_T(tt, slot) do { } while (0)
 #define TC_STAT_BEGIN() do { } while (0)
 #define TC_STAT_END(acc) do { } while (0)
 #endif
@@ -483,8 +485,8 @@ struct TcSmem {
   static constexpr size_t off_w0 = off_res + 3 * RES_LAYER_BYTES;
   static constexpr size_t off_tail = off_w0 + W0_SMEM;
   static constexpr size_t off_bars = off_tail + sizeof(float) * TAIL_FLOATS;
-  static constexpr int n_bars = 2 * NS + C::NCHUNK + 2 + 3 + 4;   // ring, a_ready, d_full[2], feat_full, s_free, w0_full, gp_full[2], gp_empty[2]
-  static constexpr size_t off_misc = off_bars + 8 * n_bars;
+  static constexpr int n_bars = 2 * NS + C::NCHUNK + 2 + 3 + 4 + 1;   // ring, a_ready, d_full[2], feat_full, s_free, w0_full, gp_full[2], gp_empty[2], r1_free
+  static constexpr size_t off_misc = off_bars + ((8 * n_bars + 15) & ~(size_t)15);   // keep what follows 16-byte aligned
   static constexpr size_t off_part = off_misc + 16;
   static constexpr size_t off_gp = off_part + sizeof(float) * TC_M;             // fused GP: episode blob + mu/sd hand-off
   static constexpr size_t off_musd = off_gp + (FUSE ? sizeof(double) * GPB_DOUBLES : 0);
@@ -551,26 +553,23 @@ template <> struct ChunkOps<MBO_MLP_BF16X3> {
 };
 
 template <> struct ChunkOps<MBO_MLP_FP16> {
-  // 32 columns (16 for the last chunk) -> fp16 pairs in the first half of the chunk's own columns; the bias is
-  // already in the accumulator.  `sat` tracks the largest converted bit pattern (values are >= 0, so unsigned
-  // 16-bit compares order them) for the range check at the end of the kernel.
-  static __device__ __forceinline__ void load(uint32_t taddr, uint32_t* v, int ncols) {
-    if (ncols == 32) tmem_ld32(taddr, v);
-    else tmem_ld16(taddr, v);
-  }
+  // 32 accumulator columns -> 16 columns of fp16 pairs at the start of the chunk's own columns; the bias is already
+  // in the accumulator.  The last chunk has 16 real columns: it is processed like the others (one code path, no
+  // run-time choice between load/store shapes) -- the 16 extra columns it reads belong to the neighbouring TMEM
+  // region, and the 8 extra columns it writes (K = 208..223) are never an MMA operand.  `sat` tracks the largest
+  // converted bit pattern of the real columns (values are >= 0, so unsigned 16-bit compares order them) for the
+  // range check at the end of the kernel.
+  static __device__ __forceinline__ void load(uint32_t taddr, uint32_t* v, int) { tmem_ld32(taddr, v); }
   static __device__ __forceinline__ void convert_store(uint32_t taddr, uint32_t* v, int ncols, uint32_t& sat) {
     uint32_t ph[16];
+    const uint32_t tail_mask = ncols == 32 ? 0xffffffffu : 0u;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      ph[j] = 0u;
-      if (2 * j < ncols) {
-        asm("cvt.rn.satfinite.relu.f16x2.f32 %0, %1, %2;"
-            : "=r"(ph[j]) : "f"(__uint_as_float(v[2 * j + 1])), "f"(__uint_as_float(v[2 * j])));
-        sat = __vmaxu2(sat, ph[j]);
-      }
+      asm("cvt.rn.satfinite.relu.f16x2.f32 %0, %1, %2;"
+          : "=r"(ph[j]) : "f"(__uint_as_float(v[2 * j + 1])), "f"(__uint_as_float(v[2 * j])));
+      sat = __vmaxu2(sat, j < 8 ? ph[j] : (ph[j] & tail_mask));
     }
-    if (ncols == 32) tmem_st16(taddr, ph);
-    else tmem_st8(taddr, ph);
+    tmem_st16(taddr, ph);
   }
 };
 
@@ -621,6 +620,7 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
   const uint32_t BAR_W0 = BAR_FEAT + 16u;
   auto BAR_GPFULL = [&](int i) { return BAR_FEAT + 24u + 8u * (uint32_t)i; };
   auto BAR_GPEMPTY = [&](int i) { return BAR_FEAT + 40u + 8u * (uint32_t)i; };
+  const uint32_t BAR_R1FREE = BAR_FEAT + 56u;       // the head epilogue has read the previous tile's D3 out of R1
   float* s_mu = (float*)(smem + SM::off_musd);            // [2][128]
   float* s_sd = s_mu + 2 * TC_M;                          // [2][128]
 
@@ -642,6 +642,7 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
     mbar_init(BAR_SFREE, 1);
     mbar_init(BAR_W0, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(BAR_GPFULL(i), 128); mbar_init(BAR_GPEMPTY(i), 128); }
+    mbar_init(BAR_R1FREE, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   constexpr bool F16 = MODE == MBO_MLP_FP16;
@@ -746,6 +747,11 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
           if (!ok) break;
           const uint32_t tA = tmem + ((l & 1) ? COL_R0 : COL_R1);
           const uint32_t tD = tmem + ((l & 1) ? COL_R1 : COL_R0);
+          if (l == 1 && t > 0) {
+            // L1 overwrites R1: the head epilogue of the previous tile must have its accumulators in registers.
+            // (Layer 0's first chunks come from the feature warps, so a_ready alone no longer implies this.)
+            if (!mbar_wait(BAR_R1FREE, (uint32_t)(t - 1) & 1u, s_abort)) { ok = false; break; }
+          }
           if constexpr (F16 && !RES) {
             // The ring holds two whole layers, so this layer's 7 stages have normally been resident for a long
             // time: check them all now, while the epilogue is still converting the first chunk.  A ready
@@ -937,27 +943,59 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
       if (FUSE) gather_features(t_idx + 1, pf);
     };
 
+    // relu(D + b) -> next layer's A operand, in place, for chunks c0, c0 + step, ... < cend of the region at `col`
+    // (loads double-buffered); every finished chunk is handed to the MMA warp through its own mbarrier.
+    constexpr int MAXI = (C::NCHUNK + 1) / 2;
+    // layer 0's first chunks are converted by the feature warps: at a tile boundary the epilogue warps are still
+    // busy with the previous tile's head layer, and layer 1 would otherwise wait ~1 100 cycles for them
+    // (fp16 mode only: the tf32 / bf16x3 chunk conversions are register-heavy, a second instance of them spills,
+    // and those modes are bound by weight streaming rather than by this hand-off)
+    constexpr int NFEAT = (FUSE || !F16) ? 0 : 3;
+    auto convert_chunks = [&](uint32_t col, const float* bias, int c0, int step, int cend, int tt, int trace_slot) {
+      uint32_t va[C::CHUNK_COLS], vb[C::CHUNK_COLS];
+      auto ncols_of = [&](int c) { return (MODE == MBO_MLP_TF32) ? 40 : (c == C::NCHUNK - 1 ? 16 : 32); };
+      if (c0 < cend) ChunkOps<MODE>::load(tlane + col + c0 * C::CHUNK_COLS, va, ncols_of(c0));
+#pragma unroll
+      for (int i = 0; i < MAXI; ++i) {
+        const int c = c0 + step * i;
+        if (c < cend) {
+          uint32_t* cur = (i & 1) ? vb : va;
+          uint32_t* nxt = (i & 1) ? va : vb;
+          tmem_wait_ld();
+          if (c + step < cend) ChunkOps<MODE>::load(tlane + col + (c + step) * C::CHUNK_COLS, nxt, ncols_of(c + step));
+          if constexpr (F16) ChunkOps<MODE>::convert_store(tlane + col + c * C::CHUNK_COLS, cur, ncols_of(c), sat);
+          else ChunkOps<MODE>::convert_store(tlane + col + c * C::CHUNK_COLS, cur, bias + c * C::CHUNK_COLS, ncols_of(c));
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR_AREADY(c));
+          if (quad == 0) TC_TRACE_T(tt, trace_slot + i);
+        }
+      }
+    };
+
     if (feat_warp) {
       // ---- feature warps: S(t) may be overwritten once L0(t-1) has been committed (s_free) ----
 #pragma unroll 1
-      for (int t = -1; t < my_tiles && ok; ++t) {
-        if (t > 0) {
+      for (int t = -2; t < my_tiles && ok; ++t) {
+        if (t >= 0) {
+          // L0(t) committed: D0 is complete in R0 and S may be overwritten
           if (!mbar_wait(BAR_SFREE, sphase, s_abort)) { ok = false; break; }
           sphase ^= 1u;
           tc_fence_after();
+          if (quad == 0) TC_TRACE(300);
+          convert_chunks(COL_R0, s_tail, 0, 1, NFEAT, t, 310);
         }
-        if (quad == 0) TC_TRACE(300);
         {
           TC_STAT_BEGIN();
-          if (t >= 0) build_features(t);
-          gather_features(t + 1, pf);                  // one tile ahead: the loads land while this warp waits for s_free
+          if (t >= -1 && t + 1 < my_tiles) build_features(t + 1);
+          gather_features(t + 2, pf);                  // loads land while this warp waits for the next s_free
           TC_STAT_END(st_build);
         }
-        if (quad == 0) TC_TRACE(301);
+        if (t >= 0 && quad == 0) TC_TRACE(301);
       }
     }
     if (FUSE && my_tiles > 0 && half == 1) { gather_features(0, pf); build_features(0); }
-    constexpr int MAXI = (C::NCHUNK + 1) / 2;
     for (int t = 0; t < my_tiles && ok && !feat_warp; ++t) {
       // ---- E0..E2: relu(D + b) -> next layer's A operand, in place ----
 #pragma unroll 1
@@ -972,26 +1010,7 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
         tc_fence_after();
         if (quad == 0) TC_TRACE(100 + 100 * half + 20 * l);
         const float* bias = s_tail + l * TC_N;
-        uint32_t va[40], vb[40];
-        auto ncols_of = [&](int c) { return (MODE == MBO_MLP_TF32) ? 40 : (c == C::NCHUNK - 1 ? 16 : 32); };
-        ChunkOps<MODE>::load(tlane + col + half * C::CHUNK_COLS, va, ncols_of(half));
-#pragma unroll
-        for (int i = 0; i < MAXI; ++i) {
-          const int c = half + 2 * i;
-          if (c < C::NCHUNK) {
-            uint32_t* cur = (i & 1) ? vb : va;
-            uint32_t* nxt = (i & 1) ? va : vb;
-            tmem_wait_ld();
-            if (c + 2 < C::NCHUNK) ChunkOps<MODE>::load(tlane + col + (c + 2) * C::CHUNK_COLS, nxt, ncols_of(c + 2));
-            if constexpr (F16) ChunkOps<MODE>::convert_store(tlane + col + c * C::CHUNK_COLS, cur, ncols_of(c), sat);
-            else ChunkOps<MODE>::convert_store(tlane + col + c * C::CHUNK_COLS, cur, bias + c * C::CHUNK_COLS, ncols_of(c));
-            tmem_wait_st();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(BAR_AREADY(c));
-            if (quad == 0) TC_TRACE(100 + 100 * half + 20 * l + 1 + i);
-          }
-        }
+        convert_chunks(col, bias, half + (l == 0 ? NFEAT : 0), 2, C::NCHUNK, t, 100 + 100 * half + 20 * l + 1);
         if (FUSE && l == 2 && half == 1) {
           if (t + 1 < my_tiles) {
             // features of the next tile while L3 runs
@@ -1035,6 +1054,8 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
             acc2 = fmaf(fmaxf(__uint_as_float(v0[4 * j + 3]), 0.f), w.w, acc2);
           }
           tmem_wait_ld();
+          tc_fence_before();
+          if (lane == 0) mbar_arrive(BAR_R1FREE);
 #pragma unroll
           for (int j = 0; j < 10; ++j) {
             const float4 w = w4[16 + j];
@@ -1054,6 +1075,8 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
             acc = fmaf(fmaxf(__uint_as_float(v0[4 * j + 3]) + b.w, 0.f), w.w, acc);
           }
           tmem_wait_ld();
+          tc_fence_before();
+          if (lane == 0) mbar_arrive(BAR_R1FREE);
 #pragma unroll
           for (int j = 0; j < 10; ++j) {
             const float4 b = b3[16 + j], w = w4[16 + j];
