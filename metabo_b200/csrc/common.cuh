@@ -88,10 +88,9 @@ __device__ __forceinline__ void load_candidate(const mbo_candidates& c, int b, i
   }
 }
 
-// Same arithmetic as load_candidate with rolled loops (x indexed at run time, i.e. in local memory): ~10x fewer
-// instructions, for callers whose instruction footprint matters more than their latency (the feature warps of
-// the tcgen05 kernel).
-__device__ __forceinline__ void load_candidate_rolled(const mbo_candidates& c, int b, int m, double* x) {
+// Same arithmetic as load_candidate in a fraction of the instructions (one code path for head / tail and f32 / f64
+// sources instead of four unrolled ones); all loads are independent, so one memory round trip covers them.
+__device__ __forceinline__ void load_candidate_compact(const mbo_candidates& c, int b, int m, double* x) {
   const int D = c.D;
   const bool head = m < c.n_head;
   int r = m - c.n_head;
@@ -100,13 +99,20 @@ __device__ __forceinline__ void load_candidate_rolled(const mbo_candidates& c, i
   const size_t o = head ? ((size_t)b * c.n_head + m) * D : (size_t)r * D;
   const void* src = head ? c.head : c.tail;
   const bool f32 = head ? c.head_is_f32 != 0 : c.tail_is_f32 != 0;
-#pragma unroll 1
-  for (int d = 0; d < D; ++d) x[d] = f32 ? (double)((const float*)src)[o + d] : ((const double*)src)[o + d];
-  if (!head && c.local) {
-    const double* lo = c.cubes + ((size_t)b * c.n_cubes + cube) * 2 * D;
-    const double* hi = lo + D;
-#pragma unroll 1
-    for (int d = 0; d < D; ++d) x[d] = __dadd_rn(__dmul_rn(x[d], hi[d] - lo[d]), lo[d]);
+  const bool local = !head && c.local;
+  const double* lo = c.cubes + ((size_t)b * c.n_cubes + cube) * 2 * D;
+  double l[MBO_MAX_D], h[MBO_MAX_D];
+#pragma unroll
+  for (int d = 0; d < MBO_MAX_D; ++d) {
+    x[d] = 0.0; l[d] = 0.0; h[d] = 0.0;
+    if (d < D) {
+      x[d] = f32 ? (double)((const float*)src)[o + d] : ((const double*)src)[o + d];
+      if (local) { l[d] = lo[d]; h[d] = lo[D + d]; }
+    }
+  }
+  if (local) {
+#pragma unroll
+    for (int d = 0; d < MBO_MAX_D; ++d) x[d] = __dadd_rn(__dmul_rn(x[d], h[d] - l[d]), l[d]);   // util.py:35-37, two roundings
   }
 }
 

@@ -37,6 +37,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
+#include <type_traits>
 #include "tmem_ldst.cuh"
 
 #ifdef MBO_TC_TRACE
@@ -168,23 +169,46 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   return t;
 }
 constexpr uint64_t WAIT_TIMEOUT_NS = 2000000000ull;   // 2 s: far beyond any legitimate wait
-// bounded wait; returns false (and latches *abort) on timeout or when another role already aborted.
-// The slow path is kept out of line: it is inlined at ~60 call sites otherwise, and the kernel's instruction
-// footprint is what the instruction caches (and the GPC-level fetch path behind them) see.
-__device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, volatile int* abort_flag) {
+// Bounded wait.  On a time-out (a pipeline bug) the CTA-wide abort flag is latched and from then on every wait of
+// every role returns immediately: the roles run through their remaining loop iterations on garbage, the kernel ends,
+// and the host sees bit 0 of the error word.  The slow path is out of line and the call sites carry no result
+// handling: they are inlined ~45 times, and the kernel's instruction footprint is what the instruction caches (and
+// the GPC-level fetch path behind them) see.
+__device__ __forceinline__ int lds_i32(uint32_t addr) {
+  int v;
+  asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, uint32_t abort_addr) {
+  if (lds_i32(abort_addr)) return;
   const uint64_t t0 = globaltimer_ns();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if ((++spins & 0x3ff) == 0) {
-      if (*abort_flag) return false;
-      if (globaltimer_ns() - t0 > WAIT_TIMEOUT_NS) { *abort_flag = 1; return false; }
+      if (lds_i32(abort_addr)) return;
+      if (globaltimer_ns() - t0 > WAIT_TIMEOUT_NS) {
+        asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(abort_addr), "r"(1) : "memory");
+        return;
+      }
     }
   }
-  return true;
 }
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag) {
-  if (mbar_try_wait(bar, parity)) return true;
-  return mbar_wait_slow(bar, parity, abort_flag);
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t abort_addr) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity, abort_addr);
+}
+// Two waits whose ~90-cycle try_wait latencies overlap (both probes are issued before either result is used).
+__device__ __forceinline__ void mbar_wait2(uint32_t bar_a, uint32_t par_a, uint32_t bar_b, uint32_t par_b,
+                                           uint32_t abort_addr) {
+  uint32_t ok_a, ok_b;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%2], %3;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 q, [%4], %5;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "selp.u32 %1, 1, 0, q;\n\t}"
+      : "=r"(ok_a), "=r"(ok_b) : "r"(bar_a), "r"(par_a), "r"(bar_b), "r"(par_b) : "memory");
+  if (!ok_a) mbar_wait_slow(bar_a, par_a, abort_addr);
+  if (!ok_b) mbar_wait_slow(bar_b, par_b, abort_addr);
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -469,20 +493,27 @@ struct TcFeat {
   int dense_F;
 };
 
-// MBO_MLP_FP16 (not FUSE) keeps the even weight stages of all three hidden layers resident in shared memory
-// (chunks 0, 2, 4 and the half stage 6: 46 592 B per layer) and streams only the odd ones (1, 3, 5) through a short
-// ring: 120 KB instead of 260 KB per tile from L2.  The chip-wide L2 -> SM rate (~6 300 B/clk, 43 B/clk per SM) is what
-// bounds a kernel that re-streams all weights for every 128-candidate tile (tf32 mode: 520 KB per tile = 12 200 clk).
+// MBO_MLP_FP16 (not FUSE) keeps most weight stages resident in shared memory: all of layer 2 and the first NRES1
+// stages of layers 1 and 3.  The remaining stages of layers 1 and 3 (chunks NRES1..6) time-share one set of slots:
+// when layer 1 is complete (an epilogue thread sees d_full) the slots are refilled with layer 3's stages, when layer
+// 3 is complete with the next tile's layer-1 stages -- 120 KB instead of 260 KB per tile from L2, issued from code
+// that is hot anyway.  The chip-wide L2 -> SM rate (~6 300 B/clk, 43 B/clk per SM) is what bounds a kernel that
+// re-streams all weights for every 128-candidate tile (tf32 mode: 520 KB per tile = 12 200 clk); and a dedicated
+// producer warp whose loop body runs once per ~900 cycles pays an instruction-cache miss on every pass.
 template <int MODE, bool FUSE = false, int K0S = 2>
 struct TcSmem {
   using C = ModeCfg<MODE>;
   static constexpr bool RES = MODE == MBO_MLP_FP16 && !FUSE;
-  static constexpr int NS = RES ? (K0S == 1 ? 5 : 4) : (FUSE ? C::NSTAGE_FUSED : C::NSTAGE);
-  static constexpr size_t RES_LAYER_BYTES = RES ? (size_t)3 * C::STAGE_BYTES + C::STAGE_BYTES / 2 : 0;
+  static constexpr int NRES1 = K0S == 1 ? 2 : 1;                      // resident leading stages of layers 1 and 3
+  static constexpr int NSLOT = C::STAGES_PER_LAYER - NRES1;           // time-shared slots (the last one is half a stage)
+  static constexpr int NS = RES ? NSLOT : (FUSE ? C::NSTAGE_FUSED : C::NSTAGE);
+  static constexpr size_t SLOT_BYTES = RES ? (size_t)(NSLOT - 1) * C::STAGE_BYTES + C::STAGE_BYTES / 2 : 0;
+  static constexpr size_t L2_BYTES = (size_t)6 * C::STAGE_BYTES + C::STAGE_BYTES / 2;
+  static constexpr size_t RES_BYTES = RES ? (size_t)2 * NRES1 * C::STAGE_BYTES + L2_BYTES : 0;   // [L1 | L2 | L3]
   static constexpr size_t W0_SMEM = RES ? (size_t)K0S * (W0_BYTES / 2) : (size_t)W0_BYTES;   // RES: only the slices in use
   static constexpr size_t off_ring = 0;
-  static constexpr size_t off_res = off_ring + (size_t)NS * C::STAGE_BYTES;
-  static constexpr size_t off_w0 = off_res + 3 * RES_LAYER_BYTES;
+  static constexpr size_t off_res = off_ring + (RES ? SLOT_BYTES : (size_t)NS * C::STAGE_BYTES);
+  static constexpr size_t off_w0 = off_res + RES_BYTES;
   static constexpr size_t off_tail = off_w0 + W0_SMEM;
   static constexpr size_t off_bars = off_tail + sizeof(float) * TAIL_FLOATS;
   static constexpr int n_bars = 2 * NS + C::NCHUNK + 2 + 3 + 4 + 1;   // ring, a_ready, d_full[2], feat_full, s_free, w0_full, gp_full[2], gp_empty[2], r1_free
@@ -599,6 +630,11 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
   constexpr int NTHREADS = FUSE ? TC_THREADS_FUSED : TC_THREADS;
   constexpr int NS = SM::NS;                      // ring depth
   constexpr bool RES = SM::RES;                   // fp16: even weight stages resident, odd ones streamed
+  // fp16 (not FUSE): the feature warps own layer 0's epilogue.  At a tile boundary the epilogue warps are busy with
+  // the previous tile's head layer for ~1 500 cycles; layer 1 no longer waits for them.  (The tf32 / bf16x3 chunk
+  // conversions are register-heavy -- a second instance of them spills -- and those modes are bound by weight
+  // streaming rather than by this hand-off.)
+  constexpr bool E0_BY_FEAT = MODE == MBO_MLP_FP16 && !FUSE;
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const PackLayout pl = pack_layout();
@@ -607,7 +643,8 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
   float* s_tail = (float*)(smem + SM::off_tail);
   uint64_t* bars = (uint64_t*)(smem + SM::off_bars);
   uint32_t* s_tmem = (uint32_t*)(smem + SM::off_misc);
-  volatile int* s_abort = (volatile int*)(smem + SM::off_misc + 4);
+  volatile int* s_abort_p = (volatile int*)(smem + SM::off_misc + 4);
+  const uint32_t s_abort = smem_u32(smem + SM::off_misc + 4);     // shared-window address: cheap to pass to the slow wait path
   float* s_part = (float*)(smem + SM::off_part);          // [128] partial head sums of the upper column half
 
   const uint32_t bar0 = smem_u32(bars);
@@ -633,7 +670,7 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
 
   // ---- one-time setup ----
   if (tid == 0) {
-    *s_abort = 0;
+    *s_abort_p = 0;
     for (int s = 0; s < NS; ++s) { mbar_init(BAR_WFULL(s), 1); mbar_init(BAR_WEMPTY(s), 1); }
     for (int c = 0; c < C::NCHUNK; ++c) mbar_init(BAR_AREADY(c), 4);     // one elected arrive per epilogue warp
     mbar_init(BAR_DFULL(0), 1);
@@ -657,6 +694,21 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
   tc_fence_after();
   const uint32_t tmem = *s_tmem;
 
+  // RES: (re)fill the time-shared weight slots with stages NRES1..6 of hidden layer `li` (0: layer 1, 2: layer 3).
+  // Called by ONE thread, after it has observed the completion of every MMA that read the slots' old contents.
+  auto refill_slots = [&](int li) {
+    if constexpr (RES) {
+      const unsigned char* src = pack + pl.off_f16 + (size_t)(li * C::STAGES_PER_LAYER + SM::NRES1) * C::STAGE_BYTES;
+      const uint32_t dst = smem_u32(ring);
+#pragma unroll 1
+      for (int j = 0; j < SM::NSLOT; ++j) {
+        const uint32_t bytes = j < SM::NSLOT - 1 ? C::STAGE_BYTES : C::STAGE_BYTES / 2;
+        mbar_expect_tx(BAR_WFULL(j), bytes);
+        bulk_g2s(dst + j * C::STAGE_BYTES, src + (size_t)j * C::STAGE_BYTES, bytes, BAR_WFULL(j));
+      }
+    }
+  };
+
   if (warp == WARP_TMA) {
     // ================= TMA producer (warp-uniform control flow, one elected lane issues) =================
     const bool leader = elect_one();
@@ -665,15 +717,20 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
       if (leader) {
         if constexpr (RES) {
           // layer-0 weights (only the K slices in use, hi and lo part) + the resident stages, one barrier
-          mbar_expect_tx(BAR_W0, (uint32_t)(SM::W0_SMEM + 3 * SM::RES_LAYER_BYTES));
+          mbar_expect_tx(BAR_W0, (uint32_t)(SM::W0_SMEM + SM::RES_BYTES));
           constexpr uint32_t PART = (uint32_t)(SM::W0_SMEM / 2);
           bulk_g2s(smem_u32(smem + SM::off_w0), pack + pl.off_w0h, PART, BAR_W0);
           bulk_g2s(smem_u32(smem + SM::off_w0) + PART, pack + pl.off_w0h + W0_BYTES / 2, PART, BAR_W0);
-          for (int l = 0; l < 3; ++l)
-            for (int j = 0; j < 4; ++j)
-              bulk_g2s(smem_u32(smem + SM::off_res) + (uint32_t)(l * SM::RES_LAYER_BYTES) + j * C::STAGE_BYTES,
-                       wsrc + (size_t)(l * C::STAGES_PER_LAYER + 2 * j) * C::STAGE_BYTES,
-                       j < 3 ? C::STAGE_BYTES : C::STAGE_BYTES / 2, BAR_W0);
+          const uint32_t res = smem_u32(smem + SM::off_res);
+          for (int j = 0; j < SM::NRES1; ++j) {
+            bulk_g2s(res + j * C::STAGE_BYTES, wsrc + (size_t)j * C::STAGE_BYTES, C::STAGE_BYTES, BAR_W0);
+            bulk_g2s(res + (uint32_t)(SM::NRES1 * C::STAGE_BYTES + SM::L2_BYTES) + j * C::STAGE_BYTES,
+                     wsrc + (size_t)(2 * C::STAGES_PER_LAYER + j) * C::STAGE_BYTES, C::STAGE_BYTES, BAR_W0);
+          }
+          for (int j = 0; j < C::STAGES_PER_LAYER; ++j)
+            bulk_g2s(res + (SM::NRES1 + j) * C::STAGE_BYTES, wsrc + (size_t)(C::STAGES_PER_LAYER + j) * C::STAGE_BYTES,
+                     j < C::STAGES_PER_LAYER - 1 ? C::STAGE_BYTES : C::STAGE_BYTES / 2, BAR_W0);
+          refill_slots(0);                            // the first tile's layer-1 stages
         } else {
           mbar_expect_tx(BAR_W0, W0_BYTES);
           bulk_g2s(smem_u32(smem + SM::off_w0), pack + (F16 ? pl.off_w0h : pl.off_w0), W0_BYTES, BAR_W0);
@@ -681,11 +738,11 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
       }
       const uint32_t ring_addr = smem_u32(ring);
       uint32_t stage = 0, phase = 0;
-      bool ok = true;
-      for (int t = 0; t < my_tiles && ok; ++t) {
+#pragma unroll 1
+      for (int t = 0; t < (RES ? 0 : my_tiles); ++t) {      // RES: no streaming loop, the epilogue refills the slots
+#pragma unroll 1
         for (int ls = 0; ls < 3 * C::STAGES_PER_LAYER; ++ls) {
-          if (RES && ((ls % C::STAGES_PER_LAYER) & 1) == 0) continue;      // even stages are resident
-          if (!mbar_wait(BAR_WEMPTY(stage), phase ^ 1u, s_abort)) { ok = false; break; }
+          mbar_wait(BAR_WEMPTY(stage), phase ^ 1u, s_abort);
           if (leader) {
             if (debug_noload && (t > 0 || ls >= NS)) {
               mbar_arrive(BAR_WFULL(stage));    // timing experiment only: pretend the stage is resident
@@ -707,7 +764,7 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
     // issuing thread must spend far fewer cycles per MMA than the ~104 the tensor pipe needs for it.
     const bool leader = elect_one();
     if (my_tiles > 0) {
-      bool ok = mbar_wait(BAR_W0, 0, s_abort);
+      mbar_wait(BAR_W0, 0, s_abort);
       uint32_t stage = 0, wphase = 0, aphase = 0, fphase = 0;
       long long st_feat = 0, st_a = 0, st_w = 0;
       (void)st_feat; (void)st_a; (void)st_w;
@@ -717,11 +774,11 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
       (void)res_lo;
       constexpr uint32_t STAGE_D = C::STAGE_BYTES >> 4;            // descriptor units (16 B)
       constexpr uint32_t SLICE_D = (2 * CHUNK_ROW_BYTES) >> 4;     // one K slice = two 16-byte chunks
-      for (int t = 0; t < my_tiles && ok; ++t) {
+      for (int t = 0; t < my_tiles; ++t) {
         // ---- L0: D(R0) = S * W0^T, 3xTF32 ----
         {
           TC_STAT_BEGIN();
-          if (!mbar_wait(BAR_FEAT, fphase, s_abort)) { ok = false; break; }
+          mbar_wait(BAR_FEAT, fphase, s_abort);
           TC_STAT_END(st_feat);
         }
         fphase ^= 1u;
@@ -738,19 +795,28 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
             mma_ts_tf32(tmem + COL_R0, a_hi + sl * 8, make_desc64(wl + W0_PART_D), IDESC_TF32, 1);
           }
           tc_commit(BAR_SFREE);
-          tc_commit(BAR_DFULL(0));
+          if (!E0_BY_FEAT) tc_commit(BAR_DFULL(0));
         }
         TC_TRACE(1);
+        if (RES && t > 0) {
+          // The next use of the shared slots is this tile's layer 1, ~2 000 cycles away: refill them as soon as the
+          // previous tile's layer 3 is complete.  The issuing thread is idle until layer 0's epilogue anyway.
+          mbar_wait(BAR_DFULL(1), 1u, s_abort);
+          if (leader) refill_slots(0);
+        }
         // ---- L1..L3 (rolled: three copies of the chunk loop are instruction-cache footprint for nothing) ----
 #pragma unroll 1
         for (int l = 1; l <= 3; ++l) {
-          if (!ok) break;
           const uint32_t tA = tmem + ((l & 1) ? COL_R0 : COL_R1);
           const uint32_t tD = tmem + ((l & 1) ? COL_R1 : COL_R0);
+          // RES: resident weights of this layer ([L1 | L2 | L3] region)
+          const uint32_t res_l = res_lo + (uint32_t)((l == 1 ? 0 : (l == 2 ? SM::NRES1 * C::STAGE_BYTES
+                                                                           : SM::NRES1 * C::STAGE_BYTES + SM::L2_BYTES)) >> 4);
+          (void)res_l;
           if (l == 1 && t > 0) {
             // L1 overwrites R1: the head epilogue of the previous tile must have its accumulators in registers.
             // (Layer 0's first chunks come from the feature warps, so a_ready alone no longer implies this.)
-            if (!mbar_wait(BAR_R1FREE, (uint32_t)(t - 1) & 1u, s_abort)) { ok = false; break; }
+            mbar_wait(BAR_R1FREE, (uint32_t)(t - 1) & 1u, s_abort);
           }
           if constexpr (F16 && !RES) {
             // The ring holds two whole layers, so this layer's 7 stages have normally been resident for a long
@@ -761,18 +827,19 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
             uint32_t st = stage, ph = wphase;
 #pragma unroll
             for (int i = 0; i < C::STAGES_PER_LAYER; ++i) {
-              if (!mbar_wait(BAR_WFULL(st), ph, s_abort)) { ok = false; break; }
+              mbar_wait(BAR_WFULL(st), ph, s_abort);
               if (++st == NS) { st = 0; ph ^= 1u; }
             }
             TC_STAT_END(st_w);
-            if (!ok) break;
           }
 #pragma unroll
           for (int c = 0; c < C::NCHUNK; ++c) {
-            if (!ok) break;
             {
               TC_STAT_BEGIN();
-              if (!mbar_wait(BAR_AREADY(c), aphase, s_abort)) { ok = false; break; }
+              if (RES && c >= SM::NRES1 && l != 2)      // this chunk's weights sit in a shared slot: probe both barriers at once
+                mbar_wait2(BAR_AREADY(c), aphase, BAR_WFULL(c - SM::NRES1), l == 1 ? 0u : 1u, s_abort);
+              else
+                mbar_wait(BAR_AREADY(c), aphase, s_abort);
               TC_STAT_END(st_a);
             }
             TC_TRACE(10 * l + c);
@@ -780,7 +847,7 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
               // chunk c == ring stage: 5 slices of K=8
               {
                 TC_STAT_BEGIN();
-                if (!mbar_wait(BAR_WFULL(stage), wphase, s_abort)) { ok = false; break; }
+                mbar_wait(BAR_WFULL(stage), wphase, s_abort);
                 TC_STAT_END(st_w);
               }
               tc_fence_after();
@@ -793,22 +860,16 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
               }
               if (++stage == NS) { stage = 0; wphase ^= 1u; }
             } else if (RES) {
-              // fp16 pairs of 32 K values in the chunk's first 16 columns = 2 slices (1 in the last chunk);
-              // even chunks read resident weights, odd chunks the ring
-              if (c & 1) {
-                TC_STAT_BEGIN();
-                if (!mbar_wait(BAR_WFULL(stage), wphase, s_abort)) { ok = false; break; }
-                TC_STAT_END(st_w);
-              }
+              // fp16 pairs of 32 K values in the chunk's first 16 columns = 2 slices (1 in the last chunk).  Layer 2
+              // and the first NRES1 chunks of layers 1 / 3 read resident weights, the other chunks the shared slots
+              // (layer 1's fill is the slot barrier's even phase, layer 3's the odd one).
+              const bool slot = c >= SM::NRES1 && l != 2;
               tc_fence_after();
               if (leader) {
-                const uint32_t lo = (c & 1) ? ring_lo + stage * STAGE_D
-                                            : res_lo + (uint32_t)(((l - 1) * SM::RES_LAYER_BYTES + (c >> 1) * C::STAGE_BYTES) >> 4);
+                const uint32_t lo = slot ? ring_lo + (uint32_t)(c - SM::NRES1) * STAGE_D : res_l + (uint32_t)c * STAGE_D;
                 mma_ts_bf16(tD, tA + c * 32, make_desc64(lo), IDESC_F16, c ? 1u : 0u);
                 if (c != C::NCHUNK - 1) mma_ts_bf16(tD, tA + c * 32 + 8, make_desc64(lo + SLICE_D), IDESC_F16, 1u);
-                if (c & 1) tc_commit(BAR_WEMPTY(stage));
               }
-              if (c & 1) { if (++stage == NS) { stage = 0; wphase ^= 1u; } }
             } else if (F16) {
               // chunk c == ring stage: fp16 pairs of 32 K values in the chunk's first 16 columns = 2 slices (1 in the last)
               tc_fence_after();
@@ -825,7 +886,7 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
 #pragma unroll
               for (int sc = 0; sc < 2; ++sc) {
                 if (c == LASTC && sc == 1) break;
-                if (!mbar_wait(BAR_WFULL(stage), wphase, s_abort)) { ok = false; break; }
+                mbar_wait(BAR_WFULL(stage), wphase, s_abort);
                 tc_fence_after();
                 if (leader) {
                   const uint32_t lo = ring_lo + stage * STAGE_D;
@@ -864,7 +925,6 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
     uint32_t dph = 0;                                // bit i = phase of d_full[i]
     uint32_t sphase = 0;
     uint32_t sat = 0u;                               // fp16 mode: largest activation bit pattern seen
-    bool ok = true;
     long long st_d = 0, st_build = 0;
     (void)st_d; (void)st_build;
     const float* s_w4 = s_tail + 4 * TC_N;          // s_tail = [zeros | b1 | b2 | b3 | w4 | b4]
@@ -888,20 +948,35 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
 #pragma unroll 1
         for (int i = 0; i < fs.F; ++i) f[i] = srow[fs.src[i]];
       } else {
+        // every load is issued before the first use (one memory round trip), then the policy's columns are picked
+        // from a table indexed by the MBO_FEAT_* code
         double x[MBO_MAX_D];
-        load_candidate_rolled(cand, b, m, x);
+        load_candidate_compact(cand, b, m, x);
         float mu = 0.f, sd = 0.f;
-        if (!FUSE) { mu = mean[(size_t)b * cand.M + m]; sd = std_[(size_t)b * cand.M + m]; }
-#pragma unroll 1
-        for (int i = 0; i < fs.F; ++i) {
-          const int s = fs.src[i];
-          float v;
-          if (s == MBO_FEAT_MEAN) v = mu;
-          else if (s == MBO_FEAT_STD) v = sd;
-          else if (s >= MBO_FEAT_X0 && s < MBO_FEAT_X0 + MBO_MAX_D) v = (s - MBO_FEAT_X0 < cand.D) ? (float)x[s - MBO_FEAT_X0] : 0.f;
-          else v = epi[b * 4 + (s - MBO_FEAT_INCUMBENT)];
-          f[i] = v;
+        if (!FUSE) {
+          mu = mean[(size_t)b * cand.M + m];
+          sd = std_[(size_t)b * cand.M + m];
+          // mean / std are streamed from HBM exactly once: pull the next tile's lines into L2 now, so that the next
+          // gather pays an L2 hit instead of a DRAM round trip (the gather is a serial chain on four warps and must
+          // stay well below a tile time)
+          const int tile_n = tile + (int)gridDim.x;
+          const int bn = tile_n / tiles_per_episode;
+          const int mn = (tile_n - bn * tiles_per_episode) * TC_M + row;
+          if (bn < B && mn < cand.M && (lane & 7) == 0) {       // one prefetch per 32-byte sector
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(mean + (size_t)bn * cand.M + mn));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(std_ + (size_t)bn * cand.M + mn));
+          }
         }
+        const float4 e4 = make_float4(epi[b * 4 + 0], epi[b * 4 + 1], epi[b * 4 + 2], epi[b * 4 + 3]);
+        float sv[MBO_FEAT_BUDGET + 1];
+        sv[MBO_FEAT_MEAN] = mu;
+        sv[MBO_FEAT_STD] = sd;
+#pragma unroll
+        for (int d = 0; d < MBO_MAX_D; ++d) sv[MBO_FEAT_X0 + d] = (float)x[d];
+        sv[MBO_FEAT_INCUMBENT] = e4.x; sv[MBO_FEAT_INCUMBENT + 1] = e4.y;
+        sv[MBO_FEAT_INCUMBENT + 2] = e4.z; sv[MBO_FEAT_INCUMBENT + 3] = e4.w;
+#pragma unroll 1
+        for (int i = 0; i < fs.F; ++i) f[i] = sv[fs.src[i]];
       }
       f[fs.F] = 1.0f;    // bias column
     };
@@ -909,7 +984,7 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
 
     auto build_features = [&](int t_idx) {
       if (FUSE) {   // posterior of this tile from the GP warps
-        if (!mbar_wait(BAR_GPFULL(t_idx & 1), (uint32_t)(t_idx >> 1) & 1u, s_abort)) ok = false;
+        mbar_wait(BAR_GPFULL(t_idx & 1), (uint32_t)(t_idx >> 1) & 1u, s_abort);
         const int tile = (int)blockIdx.x + t_idx * (int)gridDim.x;
         const int b = tile / tiles_per_episode;
         const int m = (tile - b * tiles_per_episode) * TC_M + row;
@@ -944,32 +1019,35 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
     };
 
     // relu(D + b) -> next layer's A operand, in place, for chunks c0, c0 + step, ... < cend of the region at `col`
-    // (loads double-buffered); every finished chunk is handed to the MMA warp through its own mbarrier.
+    // (loads double-buffered, loop rolled over pairs of chunks); every finished chunk is handed to the MMA warp
+    // through its own mbarrier.
     constexpr int MAXI = (C::NCHUNK + 1) / 2;
-    // layer 0's first chunks are converted by the feature warps: at a tile boundary the epilogue warps are still
-    // busy with the previous tile's head layer, and layer 1 would otherwise wait ~1 100 cycles for them
-    // (fp16 mode only: the tf32 / bf16x3 chunk conversions are register-heavy, a second instance of them spills,
-    // and those modes are bound by weight streaming rather than by this hand-off)
-    constexpr int NFEAT = (FUSE || !F16) ? 0 : 3;
-    auto convert_chunks = [&](uint32_t col, const float* bias, int c0, int step, int cend, int tt, int trace_slot) {
+    auto convert_chunks = [&](auto rolled, uint32_t col, const float* bias, int c0, int step, int cend, int tt, int trace_slot) {
       uint32_t va[C::CHUNK_COLS], vb[C::CHUNK_COLS];
       auto ncols_of = [&](int c) { return (MODE == MBO_MLP_TF32) ? 40 : (c == C::NCHUNK - 1 ? 16 : 32); };
+      auto one = [&](int c, uint32_t* cur, uint32_t* nxt, int i) {
+        tmem_wait_ld();
+        if (c + step < cend) ChunkOps<MODE>::load(tlane + col + (c + step) * C::CHUNK_COLS, nxt, ncols_of(c + step));
+        if constexpr (F16) ChunkOps<MODE>::convert_store(tlane + col + c * C::CHUNK_COLS, cur, ncols_of(c), sat);
+        else ChunkOps<MODE>::convert_store(tlane + col + c * C::CHUNK_COLS, cur, bias + c * C::CHUNK_COLS, ncols_of(c));
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR_AREADY(c));
+        if (quad == 0) TC_TRACE_T(tt, trace_slot + i);
+      };
       if (c0 < cend) ChunkOps<MODE>::load(tlane + col + c0 * C::CHUNK_COLS, va, ncols_of(c0));
+      if constexpr (decltype(rolled)::value) {
+#pragma unroll 1
+        for (int i = 0, c = c0; c < cend; i += 2, c += 2 * step) {
+          one(c, va, vb, i);
+          if (c + step < cend) one(c + step, vb, va, i + 1);
+        }
+      } else {       // at most MAXI chunks, unrolled (the epilogue warps' copy: its first chunk is on the critical path)
 #pragma unroll
-      for (int i = 0; i < MAXI; ++i) {
-        const int c = c0 + step * i;
-        if (c < cend) {
-          uint32_t* cur = (i & 1) ? vb : va;
-          uint32_t* nxt = (i & 1) ? va : vb;
-          tmem_wait_ld();
-          if (c + step < cend) ChunkOps<MODE>::load(tlane + col + (c + step) * C::CHUNK_COLS, nxt, ncols_of(c + step));
-          if constexpr (F16) ChunkOps<MODE>::convert_store(tlane + col + c * C::CHUNK_COLS, cur, ncols_of(c), sat);
-          else ChunkOps<MODE>::convert_store(tlane + col + c * C::CHUNK_COLS, cur, bias + c * C::CHUNK_COLS, ncols_of(c));
-          tmem_wait_st();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(BAR_AREADY(c));
-          if (quad == 0) TC_TRACE_T(tt, trace_slot + i);
+        for (int i = 0; i < MAXI; ++i) {
+          const int c = c0 + step * i;
+          if (c < cend) one(c, (i & 1) ? vb : va, (i & 1) ? va : vb, i);
         }
       }
     };
@@ -977,18 +1055,19 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
     if (feat_warp) {
       // ---- feature warps: S(t) may be overwritten once L0(t-1) has been committed (s_free) ----
 #pragma unroll 1
-      for (int t = -2; t < my_tiles && ok; ++t) {
+      for (int t = -2; t < my_tiles; ++t) {
         if (t >= 0) {
           // L0(t) committed: D0 is complete in R0 and S may be overwritten
-          if (!mbar_wait(BAR_SFREE, sphase, s_abort)) { ok = false; break; }
+          mbar_wait(BAR_SFREE, sphase, s_abort);
           sphase ^= 1u;
           tc_fence_after();
           if (quad == 0) TC_TRACE(300);
-          convert_chunks(COL_R0, s_tail, 0, 1, NFEAT, t, 310);
+          if (E0_BY_FEAT) convert_chunks(std::true_type{}, COL_R0, s_tail, 0, 1, C::NCHUNK, t, 310);
         }
         {
           TC_STAT_BEGIN();
           if (t >= -1 && t + 1 < my_tiles) build_features(t + 1);
+          if (t >= 0 && quad == 0) TC_TRACE(302);
           gather_features(t + 2, pf);                  // loads land while this warp waits for the next s_free
           TC_STAT_END(st_build);
         }
@@ -996,25 +1075,29 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
       }
     }
     if (FUSE && my_tiles > 0 && half == 1) { gather_features(0, pf); build_features(0); }
-    for (int t = 0; t < my_tiles && ok && !feat_warp; ++t) {
+    for (int t = 0; t < my_tiles && !feat_warp; ++t) {
       // ---- E0..E2: relu(D + b) -> next layer's A operand, in place ----
 #pragma unroll 1
-      for (int l = 0; l < 3 && ok; ++l) {
+      for (int l = E0_BY_FEAT ? 1 : 0; l < 3; ++l) {
         const uint32_t col = (l & 1) ? COL_R1 : COL_R0;
         {
           TC_STAT_BEGIN();
-          if (!mbar_wait(BAR_DFULL(l & 1), (dph >> (l & 1)) & 1u, s_abort)) { ok = false; break; }
+          mbar_wait(BAR_DFULL(l & 1), (dph >> (l & 1)) & 1u, s_abort);
           TC_STAT_END(st_d);
         }
         dph ^= 1u << (l & 1);
         tc_fence_after();
         if (quad == 0) TC_TRACE(100 + 100 * half + 20 * l);
         const float* bias = s_tail + l * TC_N;
-        convert_chunks(col, bias, half + (l == 0 ? NFEAT : 0), 2, C::NCHUNK, t, 100 + 100 * half + 20 * l + 1);
+        convert_chunks(std::false_type{}, col, bias, half, 2, C::NCHUNK, t, 100 + 100 * half + 20 * l + 1);
+        // Layer 1 is complete (this warp saw d_full): the shared slots take layer 3's stages.  Issuing a bulk copy
+        // costs the thread ~160 cycles, so this sits after the chunk conversions, on the half with fewer chunks;
+        // the copies land ~2 000 cycles before layer 3 needs them.
+        if (RES && l == 1 && tid == 4 * 32) refill_slots(2);
         if (FUSE && l == 2 && half == 1) {
           if (t + 1 < my_tiles) {
             // features of the next tile while L3 runs
-            if (!mbar_wait(BAR_SFREE, sphase, s_abort)) { ok = false; break; }
+            mbar_wait(BAR_SFREE, sphase, s_abort);
             tc_fence_after();
             if (quad == 0) TC_TRACE(100 + 100 * half + 80);
             build_features(t + 1);
@@ -1023,69 +1106,49 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
           sphase ^= 1u;
         }
       }
-      if (!ok) break;
       // ---- E3: logit = relu(D + b3) . w4 + b4, columns split between the two halves ----
       {
         TC_STAT_BEGIN();
-        if (!mbar_wait(BAR_DFULL(1), (dph >> 1) & 1u, s_abort)) { ok = false; break; }
+        mbar_wait(BAR_DFULL(1), (dph >> 1) & 1u, s_abort);
         TC_STAT_END(st_d);
       }
       dph ^= 2u;
       tc_fence_after();
       if (quad == 0) TC_TRACE(100 + 100 * half + 70);
-      float acc = 0.f;
+      float acc = 0.f, acc2 = 0.f;       // two independent chains
       {
+        // 104 columns per thread as three 32-column blocks and one 8-column block (rolled: this code runs once per
+        // tile, and its size matters more than the ~100 cycles of load latency the rolling exposes)
         const int cb = half * 104;
-        uint32_t v0[64], v1[40];
-        tmem_ld64(tlane + COL_R1 + cb, v0);
-        tmem_wait_ld();
-        tmem_ld32(tlane + COL_R1 + cb + 64, v1);
-        tmem_ld8(tlane + COL_R1 + cb + 96, v1 + 32);
-        const float4* b3 = reinterpret_cast<const float4*>(s_tail + 3 * TC_N + cb);
-        const float4* w4 = reinterpret_cast<const float4*>(s_w4 + cb);
-        if constexpr (F16) {       // b3 is already in the accumulator; two independent chains
-          float acc2 = 0.f;
+        const float* b3 = s_tail + 3 * TC_N + cb;
+        const float* w4 = s_w4 + cb;
+        uint32_t v[32];
+        auto dot = [&](int j0, int n4) {     // columns j0 .. j0 + 4 n4 of this thread's range
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float4 w = w4[j];
-            acc = fmaf(fmaxf(__uint_as_float(v0[4 * j + 0]), 0.f), w.x, acc);
-            acc2 = fmaf(fmaxf(__uint_as_float(v0[4 * j + 1]), 0.f), w.y, acc2);
-            acc = fmaf(fmaxf(__uint_as_float(v0[4 * j + 2]), 0.f), w.z, acc);
-            acc2 = fmaf(fmaxf(__uint_as_float(v0[4 * j + 3]), 0.f), w.w, acc2);
+          for (int j = 0; j < 8; ++j) {
+            if (j < n4) {
+              const float4 w = reinterpret_cast<const float4*>(w4 + j0)[j];
+              float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+              if constexpr (!F16) b = reinterpret_cast<const float4*>(b3 + j0)[j];   // fp16 mode: b3 is in the accumulator
+              acc = fmaf(fmaxf(__uint_as_float(v[4 * j + 0]) + b.x, 0.f), w.x, acc);
+              acc2 = fmaf(fmaxf(__uint_as_float(v[4 * j + 1]) + b.y, 0.f), w.y, acc2);
+              acc = fmaf(fmaxf(__uint_as_float(v[4 * j + 2]) + b.z, 0.f), w.z, acc);
+              acc2 = fmaf(fmaxf(__uint_as_float(v[4 * j + 3]) + b.w, 0.f), w.w, acc2);
+            }
           }
+        };
+#pragma unroll 1
+        for (int q = 0; q < 3; ++q) {
+          tmem_ld32(tlane + COL_R1 + cb + 32 * q, v);
           tmem_wait_ld();
-          tc_fence_before();
-          if (lane == 0) mbar_arrive(BAR_R1FREE);
-#pragma unroll
-          for (int j = 0; j < 10; ++j) {
-            const float4 w = w4[16 + j];
-            acc = fmaf(fmaxf(__uint_as_float(v1[4 * j + 0]), 0.f), w.x, acc);
-            acc2 = fmaf(fmaxf(__uint_as_float(v1[4 * j + 1]), 0.f), w.y, acc2);
-            acc = fmaf(fmaxf(__uint_as_float(v1[4 * j + 2]), 0.f), w.z, acc);
-            acc2 = fmaf(fmaxf(__uint_as_float(v1[4 * j + 3]), 0.f), w.w, acc2);
-          }
-          acc += acc2;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float4 b = b3[j], w = w4[j];
-            acc = fmaf(fmaxf(__uint_as_float(v0[4 * j + 0]) + b.x, 0.f), w.x, acc);
-            acc = fmaf(fmaxf(__uint_as_float(v0[4 * j + 1]) + b.y, 0.f), w.y, acc);
-            acc = fmaf(fmaxf(__uint_as_float(v0[4 * j + 2]) + b.z, 0.f), w.z, acc);
-            acc = fmaf(fmaxf(__uint_as_float(v0[4 * j + 3]) + b.w, 0.f), w.w, acc);
-          }
-          tmem_wait_ld();
-          tc_fence_before();
-          if (lane == 0) mbar_arrive(BAR_R1FREE);
-#pragma unroll
-          for (int j = 0; j < 10; ++j) {
-            const float4 b = b3[16 + j], w = w4[16 + j];
-            acc = fmaf(fmaxf(__uint_as_float(v1[4 * j + 0]) + b.x, 0.f), w.x, acc);
-            acc = fmaf(fmaxf(__uint_as_float(v1[4 * j + 1]) + b.y, 0.f), w.y, acc);
-            acc = fmaf(fmaxf(__uint_as_float(v1[4 * j + 2]) + b.z, 0.f), w.z, acc);
-            acc = fmaf(fmaxf(__uint_as_float(v1[4 * j + 3]) + b.w, 0.f), w.w, acc);
-          }
+          dot(32 * q, 8);
         }
+        tmem_ld8(tlane + COL_R1 + cb + 96, v);
+        tmem_wait_ld();
+        tc_fence_before();
+        if (lane == 0) mbar_arrive(BAR_R1FREE);     // D3 is in registers: layer 1 of the next tile may overwrite R1
+        dot(96, 2);
+        acc += acc2;
       }
       tc_fence_before();   // order this tile's TMEM reads before the next hand-offs
       if (quad == 0) TC_TRACE(100 + 100 * half + 71);
@@ -1145,10 +1208,9 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
     const int NPmax = gp_np(gp.nmax);
     const size_t gstride = gp_state_doubles(gp.nmax, D);
     int cur_b = -1;
-    bool ok = true;
-    for (int t = 0; t < my_tiles && ok; ++t) {
+    for (int t = 0; t < my_tiles; ++t) {
       const int buf = t & 1;
-      if (!mbar_wait(BAR_GPEMPTY(buf), ((uint32_t)(t >> 1) & 1u) ^ 1u, s_abort)) { ok = false; break; }
+      mbar_wait(BAR_GPEMPTY(buf), ((uint32_t)(t >> 1) & 1u) ^ 1u, s_abort);
       const int tile = (int)blockIdx.x + t * (int)gridDim.x;
       const int b = tile / tiles_per_episode;
       const int m = (tile - b * tiles_per_episode) * TC_M + g;
@@ -1275,7 +1337,7 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
     g_tc_trace[4096 + blockIdx.x * 3 + 2] = my_tiles + ((long long)smid << 20);
   }
 #endif
-  if (tid == 0 && *s_abort) atomicOr(err_flag, 1);
+  if (tid == 0 && *s_abort_p) atomicOr(err_flag, 1);
   if (F16 && tid == 0 && ((const int*)(pack + pl.off_scale))[4]) atomicOr(err_flag, 2);   // a packed weight/bias was clamped
   if (warp == WARP_TMA) {
     __syncwarp();

@@ -54,7 +54,7 @@ for cta_id, tr in trs.items():
         print("MMA: feat ready", rel(tile, 0), " L0 issued", rel(tile, 1))
         for l in (1, 2, 3):
             print("MMA L%d: a_ready seen" % l, [rel(tile, 10 * l + c) for c in range(nch)], " committed", rel(tile, 10 * l + 8))
-        print("FEAT warps: s_free seen", rel(tile, 300), " E0 chunk arrives", [rel(tile, 310 + i) for i in range(3)], " build+gather done", rel(tile, 301))
+        print("FEAT warps: s_free seen", rel(tile, 300), " E0 chunk arrives", [rel(tile, 310 + i) for i in range(7)], " build done", rel(tile, 302), " gather done", rel(tile, 301))
         for half in (0, 1):
             base = 100 + 100 * half
             for l in (0, 1, 2):
