@@ -491,6 +491,8 @@ struct TcFeat {
   int src[TC_K0];      // MBO_FEAT_* codes, or state-column indices in dense mode
   const float* dense;  // [B, M, dense_F] materialised states, or nullptr
   int dense_F;
+  int standard;        // 1: src = [MEAN, STD, X0 .. X(D-1), per-episode scalars ...] -- get_state's own column order
+                       // (metabo_gym.py:624-677) with any of the scalar columns; branch-free gather
 };
 
 // MBO_MLP_FP16 (not FUSE) keeps most weight stages resident in shared memory: all of layer 2 and the first NRES1
@@ -506,6 +508,7 @@ struct TcSmem {
   static constexpr bool RES = MODE == MBO_MLP_FP16 && !FUSE;
   static constexpr int NRES1 = K0S == 1 ? 2 : 1;                      // resident leading stages of layers 1 and 3
   static constexpr int NSLOT = C::STAGES_PER_LAYER - NRES1;           // time-shared slots (the last one is half a stage)
+  static constexpr int NA = NSLOT - 3;                                // slots [0, NA) arrive with the first refill copy, the rest with the second
   static constexpr int NS = RES ? NSLOT : (FUSE ? C::NSTAGE_FUSED : C::NSTAGE);
   static constexpr size_t SLOT_BYTES = RES ? (size_t)(NSLOT - 1) * C::STAGE_BYTES + C::STAGE_BYTES / 2 : 0;
   static constexpr size_t L2_BYTES = (size_t)6 * C::STAGE_BYTES + C::STAGE_BYTES / 2;
@@ -698,14 +701,15 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
   // Called by ONE thread, after it has observed the completion of every MMA that read the slots' old contents.
   auto refill_slots = [&](int li) {
     if constexpr (RES) {
+      // two bulk copies (issuing one costs the thread ~160 cycles): slots [0, NA) on barrier 0, [NA, NSLOT) on barrier NA
       const unsigned char* src = pack + pl.off_f16 + (size_t)(li * C::STAGES_PER_LAYER + SM::NRES1) * C::STAGE_BYTES;
       const uint32_t dst = smem_u32(ring);
-#pragma unroll 1
-      for (int j = 0; j < SM::NSLOT; ++j) {
-        const uint32_t bytes = j < SM::NSLOT - 1 ? C::STAGE_BYTES : C::STAGE_BYTES / 2;
-        mbar_expect_tx(BAR_WFULL(j), bytes);
-        bulk_g2s(dst + j * C::STAGE_BYTES, src + (size_t)j * C::STAGE_BYTES, bytes, BAR_WFULL(j));
-      }
+      constexpr uint32_t BYTES_A = (uint32_t)SM::NA * C::STAGE_BYTES;
+      constexpr uint32_t BYTES_B = (uint32_t)SM::SLOT_BYTES - BYTES_A;
+      mbar_expect_tx(BAR_WFULL(0), BYTES_A);
+      bulk_g2s(dst, src, BYTES_A, BAR_WFULL(0));
+      mbar_expect_tx(BAR_WFULL(SM::NA), BYTES_B);
+      bulk_g2s(dst + BYTES_A, src + BYTES_A, BYTES_B, BAR_WFULL(SM::NA));
     }
   };
 
@@ -837,7 +841,7 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
             {
               TC_STAT_BEGIN();
               if (RES && c >= SM::NRES1 && l != 2)      // this chunk's weights sit in a shared slot: probe both barriers at once
-                mbar_wait2(BAR_AREADY(c), aphase, BAR_WFULL(c - SM::NRES1), l == 1 ? 0u : 1u, s_abort);
+                mbar_wait2(BAR_AREADY(c), aphase, BAR_WFULL(c - SM::NRES1 < SM::NA ? 0 : SM::NA), l == 1 ? 0u : 1u, s_abort);
               else
                 mbar_wait(BAR_AREADY(c), aphase, s_abort);
               TC_STAT_END(st_a);
@@ -947,6 +951,33 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
         const float* srow = fs.dense + ((size_t)b * cand.M + m) * fs.dense_F;
 #pragma unroll 1
         for (int i = 0; i < fs.F; ++i) f[i] = srow[fs.src[i]];
+      } else if (fs.standard && !FUSE) {
+        // get_state's own column order: predicated, branch-free, registers only (this is a serial chain on one warp)
+        double x[MBO_MAX_D];
+        load_candidate_compact(cand, b, m, x);
+        const float mu = mean[(size_t)b * cand.M + m], sd = std_[(size_t)b * cand.M + m];
+        const int nx = 2 + cand.D;
+#pragma unroll
+        for (int i = 0; i < KF - 1; ++i) {
+          float v = 0.f;
+          if (i == 0) v = mu;
+          else if (i == 1) v = sd;
+          else {
+            if (i - 2 < MBO_MAX_D && i < nx) v = (float)x[i - 2 < MBO_MAX_D ? i - 2 : 0];
+            if (i >= nx && i < fs.F) v = epi[b * 4 + (fs.src[i] - MBO_FEAT_INCUMBENT)];
+          }
+          f[i] = v;
+        }
+        {
+          // mean / std are streamed from HBM exactly once: pull the next tile's lines into L2 now
+          const int tile_n = tile + (int)gridDim.x;
+          const int bn = tile_n / tiles_per_episode;
+          const int mn = (tile_n - bn * tiles_per_episode) * TC_M + row;
+          if (bn < B && mn < cand.M && (lane & 7) == 0) {       // one prefetch per 32-byte sector
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(mean + (size_t)bn * cand.M + mn));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(std_ + (size_t)bn * cand.M + mn));
+          }
+        }
       } else {
         // every load is issued before the first use (one memory round trip), then the policy's columns are picked
         // from a table indexed by the MBO_FEAT_* code
@@ -1390,6 +1421,16 @@ topk_merge_kernel(int n_lists, int k, const float* __restrict__ part_val, const 
 
 static int g_num_sms = 0;
 
+// [MEAN, STD, X0 .. X(D-1), per-episode scalar codes ...]: the column order get_state produces
+static bool tc_standard_layout(int F, const int32_t* src, int D) {
+  if (F < 2 + D || src[0] != MBO_FEAT_MEAN || src[1] != MBO_FEAT_STD) return false;
+  for (int d = 0; d < D; ++d)
+    if (src[2 + d] != MBO_FEAT_X0 + d) return false;
+  for (int i = 2 + D; i < F; ++i)
+    if (src[i] < MBO_FEAT_INCUMBENT || src[i] > MBO_FEAT_BUDGET) return false;
+  return true;
+}
+
 template <int MODE, bool FUSE, int K0S>
 static int launch_tc_k(const mbo_policy* p, int B, const TcFeat& fs, const mbo_candidates& cand, const float* mean,
                      const float* std_, const float* epi, float* logits, int* err_flag, cudaStream_t s,
@@ -1434,6 +1475,7 @@ int tc_forward(const mbo_policy* p, int mode, int B, int F, const int32_t* feat_
   fs.dense_F = dense_F;
   fs.k0_slices = (F + 1 <= 8) ? 1 : 2;
   for (int i = 0; i < TC_K0; ++i) fs.src[i] = i < F ? feat_src[i] : 0;
+  fs.standard = !fs.dense && tc_standard_layout(F, feat_src, cand->D);
   int* err_flag = (int*)ws;
   GpFuse gp;
   memset(&gp, 0, sizeof(gp));
@@ -1508,6 +1550,7 @@ extern "C" int mbo_af_eval_fused(const mbo_policy* p, int mode, int B, int nmax,
   fs.dense_F = 0;
   fs.k0_slices = (F + 1 <= 8) ? 1 : 2;
   for (int i = 0; i < TC_K0; ++i) fs.src[i] = i < F ? feat_src[i] : 0;
+  fs.standard = tc_standard_layout(F, feat_src, cand->D);
   GpFuse gp;
   gp.gp_state = gp_state;
   gp.nmax = nmax;
