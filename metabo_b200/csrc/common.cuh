@@ -118,71 +118,88 @@ __device__ __forceinline__ void load_candidate_compact(const mbo_candidates& c, 
 
 // stationary kernels of GPy (Stationary.K_of_r): RBF, Matern-3/2, Matern-5/2 on the scaled squared distance
 template <typename T> __device__ __forceinline__ T t_exp(T x);
-// exp(x) for x <= 0 in fp64, branch-free (interleaves under unrolling; CUDA's exp() carries special-case
-// branches): x = k ln2 + r, |r| <= ln2/2, degree-13 Taylor polynomial (truncation 4e-18 relative), 2^k by
-// exponent arithmetic.  Max error ~1 ulp; arguments below -708 flush to exp(-708) ~ 3e-308 (kernel value 0
-// for every practical purpose).
+// exp(x) for x <= 0 in fp64, branch-free (CUDA's exp() carries special-case branches and its unrolled copies are not
+// interleaved by the compiler): x = (64 e + j) ln2/64 + r with |r| <= ln2/128, exp(x) = 2^e * 2^(j/64) * exp(r);
+// 2^(j/64) from a 64-entry table, exp(r) by a degree-5 Taylor polynomial (truncation 3.5e-17 relative), 2^e by
+// exponent arithmetic: 10 fp64 operations instead of the 18 of a table-free degree-13 version.  Error <= ~2 ulp;
+// arguments below -708 flush to exp(-708) ~ 3e-308 (kernel value 0 for every practical purpose).
+__device__ static const double MBO_EXP2_TAB[64] = {
+    1, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284,
+    1.0442737824274138, 1.0556451783605572, 1.0671404006768237, 1.0787607977571199,
+    1.0905077326652577, 1.1023825833078409, 1.1143867425958924, 1.1265216186082418,
+    1.1387886347566916, 1.1511892299529827, 1.1637248587775775, 1.1763969916502812,
+    1.189207115002721, 1.2021567314527031, 1.215247359980469, 1.22848053610687,
+    1.241857812073484, 1.2553807570246911, 1.2690509571917332, 1.2828700160787783,
+    1.2968395546510096, 1.3109612115247644, 1.3252366431597413, 1.3396675240533029,
+    1.3542555469368927, 1.3690024229745905, 1.383909881963832, 1.3989796725383112,
+    1.4142135623730951, 1.42961333839197, 1.4451808069770467, 1.460917794180647,
+    1.4768261459394993, 1.4929077282912648, 1.5091644275934228, 1.5255981507445384,
+    1.5422108254079407, 1.5590044002378369, 1.5759808451078865, 1.593142151342267,
+    1.6104903319492543, 1.6280274218573478, 1.6457554781539649, 1.6636765803267364,
+    1.681792830507429, 1.7001063537185235, 1.7186192981224779, 1.7373338352737062,
+    1.7562521603732995, 1.7753764925265212, 1.7947090750031072, 1.8142521755003989,
+    1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656,
+    1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.9784560263879509};
+constexpr double MBO_EXP_INV = 92.332482616893657;      // 64 / ln2
+constexpr double MBO_EXP_HI = 0.010830424696223417;       // ln2 / 64, upper 36 bits (k * HI is exact)
+constexpr double MBO_EXP_LO = 2.5728046223276691e-14;       // ln2 / 64 - HI
 __device__ __forceinline__ double exp_nonpos(double x) {
   x = fmax(x, -708.0);
   const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52: round-to-nearest integer in the low word
-  const double t = fma(x, 1.4426950408889634074, MAGIC);
+  const double t = fma(x, MBO_EXP_INV, MAGIC);
   const int k = __double2loint(t);
   const double kf = t - MAGIC;
-  double r = fma(kf, -6.93147180369123816490e-01, x);      // ln2 high part
-  r = fma(kf, -1.90821492927058770002e-10, r);             // ln2 low part
-  double p = 1.6059043836821613e-10;                       // 1/13!
-  p = fma(p, r, 2.08767569878681e-09);                     // 1/12!
-  p = fma(p, r, 2.505210838544172e-08);                    // 1/11!
-  p = fma(p, r, 2.755731922398589e-07);                    // 1/10!
-  p = fma(p, r, 2.7557319223985893e-06);                   // 1/9!
-  p = fma(p, r, 2.48015873015873e-05);                     // 1/8!
-  p = fma(p, r, 1.984126984126984e-04);                    // 1/7!
-  p = fma(p, r, 1.388888888888889e-03);                    // 1/6!
-  p = fma(p, r, 8.333333333333333e-03);                    // 1/5!
+  double r = fma(kf, -MBO_EXP_HI, x);
+  r = fma(kf, -MBO_EXP_LO, r);
+  double p = 8.333333333333333e-03;                        // 1/5!
   p = fma(p, r, 4.1666666666666664e-02);                   // 1/4!
   p = fma(p, r, 1.6666666666666666e-01);                   // 1/3!
   p = fma(p, r, 0.5);
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
-  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+  p *= MBO_EXP2_TAB[k & 63];
+  return __hiloint2double(__double2hiint(p) + ((k >> 6) << 20), __double2loint(p));
 }
 template <> __device__ __forceinline__ double t_exp<double>(double x) { return exp_nonpos(x); }
 
-// Four exp_nonpos evaluations with the four dependent chains interleaved step by step: one fp64 warp has to
-// cover the DFMA latency with instruction-level parallelism (the compiler does not interleave unrolled copies
-// of the scalar routine by itself).  Bitwise identical to exp_nonpos per element.
+// NV exp_nonpos evaluations with the NV dependent chains interleaved step by step: one fp64 warp has to cover the
+// DFMA latency with instruction-level parallelism.  Bitwise identical to exp_nonpos per element.  `tab` may point
+// to a shared-memory copy of MBO_EXP2_TAB.
 template <int NV>
-__device__ __forceinline__ void exp_nonpos_xn(const double* xin, double* out) {
+__device__ __forceinline__ void exp_nonpos_xn(const double* xin, double* out, const double* tab = MBO_EXP2_TAB) {
   const double MAGIC = 6755399441055744.0;
-  double x[NV], kf[NV], r[NV], p[NV];
+  double x[NV], kf[NV], r[NV], p[NV], tv[NV];
   int k[NV];
 #pragma unroll
   for (int u = 0; u < NV; ++u) x[u] = fmax(xin[u], -708.0);
 #pragma unroll
-  for (int u = 0; u < NV; ++u) { const double t = fma(x[u], 1.4426950408889634074, MAGIC); k[u] = __double2loint(t); kf[u] = t - MAGIC; }
+  for (int u = 0; u < NV; ++u) { const double t = fma(x[u], MBO_EXP_INV, MAGIC); k[u] = __double2loint(t); kf[u] = t - MAGIC; }
 #pragma unroll
-  for (int u = 0; u < NV; ++u) r[u] = fma(kf[u], -6.93147180369123816490e-01, x[u]);
+  for (int u = 0; u < NV; ++u) tv[u] = tab[k[u] & 63];
 #pragma unroll
-  for (int u = 0; u < NV; ++u) r[u] = fma(kf[u], -1.90821492927058770002e-10, r[u]);
-  const double c[13] = {2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07, 2.7557319223985893e-06,
-                        2.48015873015873e-05, 1.984126984126984e-04, 1.388888888888889e-03, 8.333333333333333e-03,
-                        4.1666666666666664e-02, 1.6666666666666666e-01, 0.5, 1.0, 1.0};
+  for (int u = 0; u < NV; ++u) r[u] = fma(kf[u], -MBO_EXP_HI, x[u]);
 #pragma unroll
-  for (int u = 0; u < NV; ++u) p[u] = 1.6059043836821613e-10;
+  for (int u = 0; u < NV; ++u) r[u] = fma(kf[u], -MBO_EXP_LO, r[u]);
+  const double c[5] = {4.1666666666666664e-02, 1.6666666666666666e-01, 0.5, 1.0, 1.0};
 #pragma unroll
-  for (int i = 0; i < 13; ++i) {
+  for (int u = 0; u < NV; ++u) p[u] = 8.333333333333333e-03;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
 #pragma unroll
     for (int u = 0; u < NV; ++u) p[u] = fma(p[u], r[u], c[i]);
   }
 #pragma unroll
-  for (int u = 0; u < NV; ++u) out[u] = __hiloint2double(__double2hiint(p[u]) + (k[u] << 20), __double2loint(p[u]));
+  for (int u = 0; u < NV; ++u) p[u] *= tv[u];
+#pragma unroll
+  for (int u = 0; u < NV; ++u) out[u] = __hiloint2double(__double2hiint(p[u]) + ((k[u] >> 6) << 20), __double2loint(p[u]));
 }
 
 __device__ __forceinline__ void exp_nonpos_x4(const double* xin, double* out) { exp_nonpos_xn<4>(xin, out); }
 
 // k(r2) for NV scaled squared distances at once (fp64), same values as kernel_of_r2<double>
 template <int NV>
-__device__ __forceinline__ void kernel_of_r2_xn(int kid, double var, const double* r2, double* out) {
+__device__ __forceinline__ void kernel_of_r2_xn(int kid, double var, const double* r2, double* out,
+                                                const double* tab = MBO_EXP2_TAB) {
   double arg[NV], pre[NV], e[NV];
   if (kid == MBO_KERNEL_RBF) {
 #pragma unroll
@@ -196,7 +213,7 @@ __device__ __forceinline__ void kernel_of_r2_xn(int kid, double var, const doubl
 #pragma unroll
     for (int u = 0; u < NV; ++u) { const double r = sqrt(r2[u]); arg[u] = -s5 * r; pre[u] = var * (1.0 + s5 * r + (5.0 / 3.0) * r2[u]); }
   }
-  exp_nonpos_xn<NV>(arg, e);
+  exp_nonpos_xn<NV>(arg, e, tab);
 #pragma unroll
   for (int u = 0; u < NV; ++u) out[u] = pre[u] * e[u];
 }
@@ -217,7 +234,8 @@ __device__ __forceinline__ T kernel_of_r2(int kid, T var, T r2) {
   return var * (T(1) + s5 * r + T(5.0 / 3.0) * r2) * t_exp<T>(-s5 * r);
 }
 
-__device__ __forceinline__ void kernel_of_r2_x4(int kid, double var, const double* r2, double* out) { kernel_of_r2_xn<4>(kid, var, r2, out); }
+__device__ __forceinline__ void kernel_of_r2_x4(int kid, double var, const double* r2, double* out,
+                                                const double* tab = MBO_EXP2_TAB) { kernel_of_r2_xn<4>(kid, var, r2, out, tab); }
 
 int check_candidates(const mbo_candidates* c);
 

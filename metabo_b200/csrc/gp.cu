@@ -179,13 +179,16 @@ gp_fit_kernel(int nmax, int D, int kid, const int32_t* __restrict__ n_arr, const
 // ------------------------------------------------------------------------------------------------
 constexpr int POST_THREADS = 128;
 
-template <typename T, int TC>
+// DT: compile-time input dimension (0 = run time, predicated to MBO_MAX_D).  The distance loops are a third of
+// the kernel's issued instructions when they are unrolled to 8 dimensions and predicated down to 3.
+template <typename T, int TC, int DT>
 __global__ void __launch_bounds__(POST_THREADS)
 gp_posterior_kernel(int nmax, int kid, const double* __restrict__ gp_state, mbo_candidates cand,
                     int tiles_per_episode, void* __restrict__ mean_out, void* __restrict__ std_out,
                     int out_is_f32) {
   extern __shared__ __align__(16) unsigned char smraw[];
-  const int D = cand.D;
+  const int D = DT ? DT : cand.D;
+  constexpr int DU = DT ? DT : MBO_MAX_D;       // unroll bound of the per-dimension loops
   const int b = blockIdx.x / tiles_per_episode;
   const int tile = blockIdx.x - b * tiles_per_episode;
   const int tid = threadIdx.x;
@@ -207,13 +210,15 @@ gp_posterior_kernel(int nmax, int kid, const double* __restrict__ gp_state, mbo_
   }
   const int lcount = gp_linv_doubles(NP);
   T* sK = sL + lcount;                        // [NP][POST_THREADS*TC]
+  __shared__ double s_exp2[64];               // shared-memory copy of the exp table (lane-varying index)
+  if (tid < 64) s_exp2[tid] = MBO_EXP2_TAB[tid];
   for (int i = tid; i < NP * D; i += POST_THREADS) sXs[i] = (T)st[gp_off_xs() + i];
   for (int i = tid; i < NP; i += POST_THREADS) sBeta[i] = (T)st[gp_off_beta(NPmax, D) + i];
   for (int i = tid; i < lcount; i += POST_THREADS) sL[i] = (T)st[gp_off_linv(NPmax, D) + i];
   __syncthreads();
 
   const int m0 = tile * POST_THREADS * TC;
-  T xs[TC][MBO_MAX_D];
+  T xs[TC][DU];
 #pragma unroll
   for (int c = 0; c < TC; ++c) {
     int mi = m0 + tid * TC + c;
@@ -223,7 +228,7 @@ gp_posterior_kernel(int nmax, int kid, const double* __restrict__ gp_state, mbo_
     if (mi < cand.M) load_candidate(cand, b, mi, x);
     // same operation as the fit (X / lengthscale) so a candidate equal to an observation has r == 0
 #pragma unroll
-    for (int d = 0; d < MBO_MAX_D; ++d) xs[c][d] = d < D ? (T)(x[d] / st[4 + d]) : T(0);
+    for (int d = 0; d < DU; ++d) xs[c][d] = d < D ? (T)(x[d] / st[4 + d]) : T(0);
   }
   constexpr int KS = POST_THREADS * TC;
   // phase 2
@@ -238,11 +243,11 @@ gp_posterior_kernel(int nmax, int kid, const double* __restrict__ gp_state, mbo_
           const int jj = min(j0 + u, n - 1);
           double r2 = 0.0;
 #pragma unroll
-          for (int d = 0; d < MBO_MAX_D; ++d)
-            if (d < D) { const double t = (double)xs[c][d] - (double)sXs[jj * D + d]; r2 = fma(t, t, r2); }
+          for (int d = 0; d < DU; ++d)
+            if (DT || d < D) { const double t = (double)xs[c][d] - (double)sXs[jj * D + d]; r2 = fma(t, t, r2); }
           r2v[u] = r2;
         }
-        kernel_of_r2_x4(kid, var, r2v, kv);
+        kernel_of_r2_x4(kid, var, r2v, kv, s_exp2);
 #pragma unroll
         for (int u = 0; u < 4; ++u)
           if (j0 + u < n) sK[(j0 + u) * KS + tid * TC + c] = (T)kv[u];
@@ -254,8 +259,8 @@ gp_posterior_kernel(int nmax, int kid, const double* __restrict__ gp_state, mbo_
       for (int c = 0; c < TC; ++c) {
         T r2 = T(0);
 #pragma unroll
-        for (int d = 0; d < MBO_MAX_D; ++d)
-          if (d < D) { T t = xs[c][d] - sXs[j * D + d]; r2 += t * t; }
+        for (int d = 0; d < DU; ++d)
+          if (DT || d < D) { T t = xs[c][d] - sXs[j * D + d]; r2 += t * t; }
         sK[j * KS + tid * TC + c] = kernel_of_r2<T>(kid, (T)var, r2);
       }
     }
@@ -339,7 +344,14 @@ template <typename T, int TC>
 static int launch_posterior(int B, int nmax, int ns, int kid, const double* gp_state, const mbo_candidates& cand,
                             void* mean, void* std_, int out_is_f32, cudaStream_t s) {
   size_t smem = posterior_smem_bytes<T, TC>(ns, cand.D);
-  auto kern = gp_posterior_kernel<T, TC>;
+  // the dimensions of the shipped experiments get their own instantiation (fp64 only), everything else the generic one
+  auto kern = gp_posterior_kernel<T, TC, 0>;
+  if (sizeof(T) == 8) {
+    if (cand.D == 2) kern = gp_posterior_kernel<T, TC, 2>;
+    else if (cand.D == 3) kern = gp_posterior_kernel<T, TC, 3>;
+    else if (cand.D == 4) kern = gp_posterior_kernel<T, TC, 4>;
+    else if (cand.D == 6) kern = gp_posterior_kernel<T, TC, 6>;
+  }
   MBO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int tiles = (cand.M + POST_THREADS * TC - 1) / (POST_THREADS * TC);
   kern<<<B * tiles, POST_THREADS, smem, s>>>(nmax, kid, gp_state, cand, tiles, mean, std_, out_is_f32);

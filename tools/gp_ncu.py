@@ -3,7 +3,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from metabo_b200 import ops
 dev = torch.device("cuda:0")
-B, M, D, T, n = 256, 10000, 3, 30, 30
+B, M, D, T, n = 1024, 10000, 3, 30, 30
 g = torch.Generator(device=dev); g.manual_seed(0)
 cs = ops.CandidateSet(D, tail=torch.rand((M, D), generator=g, dtype=torch.float64, device=dev))
 X = torch.rand((B, T, D), generator=g, dtype=torch.float64, device=dev)
