@@ -199,12 +199,12 @@ def ppo_rollout_rate(dev, world, rank):
             "N_LS": 1000, "k": 5, "reward_transformation": "neg_log10"}
     gym.register(id=spec["env_id"], entry_point="metabo.environment.metabo_gym:MetaBO", max_episode_steps=30, kwargs=spec)
     opts = {"activations": "relu", "arch_spec": [200] * 4, "use_value_network": True, "t_idx": -2, "T_idx": -1,
-            "arch_spec_value": [200] * 4, "mlp_mode": "tf32"}
+            "arch_spec_value": [200] * 4, "mlp_mode": "fp16"}
     n_workers, eps = 64, 16
     size = n_workers * eps * 30
     br = BatchRecorder(size=size, env_id=spec["env_id"], env_seeds=list(range(rank * n_workers, (rank + 1) * n_workers)),
                        policy_fn=lambda o, a, d: NeuralAF(o, a, d, options=opts), n_workers=n_workers,
-                       deterministic=False, store_states=False, mlp_mode="tf32", device=dev)
+                       deterministic=False, store_states=False, mlp_mode="fp16", device=dev)
     br.record_batch(0.98, 0.98)                       # eager warm-up
     br.record_batch(0.98, 0.98)                       # CUDA-graph capture of the per-step units
     br.record_batch(0.98, 0.98)                       # first replay
@@ -217,7 +217,7 @@ def ppo_rollout_rate(dev, world, rank):
         t = float(tt[0])
     return {"env_steps_per_s": world * size / t, "t_batch_s": t, "batch_steps": world * size,
             "config": "train_metabo_branin.py env (C3), stochastic NeuralAF 4x200, 1024 episodes x T=30 per GPU, "
-                      "6927 candidates per step (phase 3 reuses the multistart results of phase 1: 5199 evaluated), tf32 MLP + fp64 GP, "
+                      "6927 candidates per step (phase 3 reuses the multistart results of phase 1: 5199 evaluated), fp16 MLP + fp64 GP, "
                       "CUDA-graph replay of the episode loop, transitions kept on device without states"}
 
 
@@ -415,6 +415,7 @@ def main():
                 "e2e": {"value": e2e_val, "unit": "AF evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e / args.steps},
                 "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu_b, "ppo_rollout": ppo_info}
+        eng.policy.check()            # raises if a tensor-core kernel timed out or the fp16 mode clamped an activation
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -68,9 +68,11 @@ def main():
     if "C1" in which:
         run_eval("C1 evaluate_metabo_branin (100 episodes, 10 workers, deterministic, weights_1635)", BRA, "weights_bra_1635.npz", 10, 100, "bf16x3", 6927)
         run_eval("C1 same, tf32", BRA, "weights_bra_1635.npz", 10, 100, "tf32", 6927)
+        run_eval("C1 same, fp16", BRA, "weights_bra_1635.npz", 10, 100, "fp16", 6927)
     if "C2" in which:
         run_eval("C2 evaluate_metabo_hm3 at B=1024 (64 workers x 16 episodes, deterministic, weights_1988)", HM3, "weights_hm3_1988.npz", 64, 1024, "bf16x3", 13461)
         run_eval("C2 same, tf32", HM3, "weights_hm3_1988.npz", 64, 1024, "tf32", 13461)
+        run_eval("C2 same, fp16", HM3, "weights_hm3_1988.npz", 64, 1024, "fp16", 13461)
     if "C4" in which:
         run_eval("C4 train_metabo_gps env, T=30, M=2000, 2x20 policy (SIMT fp32), 1000 episodes", GPS, "weights_gps_1161.npz", 10, 1000, "fp32", 2000)
         g100 = dict(GPS, T=100)
@@ -82,9 +84,9 @@ def main():
         gym.register(id=spec["env_id"], entry_point="metabo.environment.metabo_gym:MetaBO", max_episode_steps=30, kwargs=spec)
         params = {"batch_size": 1200, "max_steps": 6 * 1200, "minibatch_size": 60, "n_epochs": 4, "lr": 1e-4, "epsilon": 0.15,
                   "value_coeff": 1.0, "ent_coeff": 0.01, "gamma": 0.98, "lambda": 0.98, "loss_type": "GAElam", "normalize_advs": True,
-                  "n_workers": 10, "env_id": spec["env_id"], "seed": 0, "env_seeds": list(range(10)), "mlp_mode": "tf32", "update_matmul_precision": prec,
+                  "n_workers": 10, "env_id": spec["env_id"], "seed": 0, "env_seeds": list(range(10)), "mlp_mode": "fp16", "update_matmul_precision": prec,
                   "policy_options": {"activations": "relu", "arch_spec": [200] * 4, "use_value_network": True, "t_idx": -2, "T_idx": -1,
-                                     "arch_spec_value": [200] * 4, "mlp_mode": "tf32"}}
+                                     "arch_spec_value": [200] * 4, "mlp_mode": "fp16"}}
         import tempfile
         lp = os.path.join(tempfile.mkdtemp(), "log")
         ppo = PPO(policy_fn=lambda o, a, d: NeuralAF(o, a, d, options=params["policy_options"]), params=params, logpath=lp,
