@@ -6,15 +6,15 @@
 // never touch HBM; one CTA owns a tile of 128 candidates of one episode.
 //
 // Data flow per tile (TMEM columns: R0 = [0,208), R1 = [208,416), S = [416,448)):
-//   features (fp32)  --split hi/lo tf32-->  S                         (epilogue warps, tcgen05.st)
+//   features (fp32)  --split hi/lo tf32-->  S                         (feature warps, tcgen05.st)
 //   L0: D(R0)  = S * W0^T     3xTF32 (hi*hi + lo*hi + hi*lo), bias folded in as a ones column
-//   E0: R0 <- act(relu(D))    in place, converted to the MMA operand format
+//   E0: R0 <- act(relu(D))    in place, converted to the MMA operand format (fp16 mode: by the feature warps)
 //   L1: D(R1)  = A(R0) * W1^T ; E1 in place on R1 ; L2: D(R0) = A(R1) * W2^T ; E2 ; L3: D(R1) = A(R0) * W3^T
 //   E3: logit = sum_j relu(D_j + b3_j) * w4_j + b4                    (CUDA cores, fp32)
-// The A operand of every MMA comes from TMEM (tcgen05.mma "TS" form), the B operand (weights,
-// K-major, no-swizzle canonical layout) streams from L2 through a shared-memory ring filled with
-// cp.async.bulk (TMA engine, 1-D) and released by tcgen05.commit.  The epilogue of layer l hands
-// the next layer its K range chunk by chunk (mbarriers), so the MMAs of layer l+1 start while the
+// The A operand of every MMA comes from TMEM (tcgen05.mma "TS" form), the B operand (weights, K-major, no-swizzle
+// canonical layout) from shared memory: tf32 / bf16x3 stream it from L2 through a ring filled with cp.async.bulk (TMA
+// engine, 1-D) and released by tcgen05.commit; the fp16 mode keeps most of it resident (see TcSmem).  The epilogue of
+// layer l hands the next layer its K range chunk by chunk (mbarriers), so the MMAs of layer l+1 start while the
 // epilogue of layer l is still converting.
 //
 // Arithmetic modes (hidden layers): MBO_MLP_TF32   kind::tf32, operands rounded to tf32 (rna);
