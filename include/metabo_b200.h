@@ -55,6 +55,11 @@ extern "C" {
 #define MBO_ACT_RELU 0
 #define MBO_ACT_TANH 1
 
+/* closed-form acquisition functions (mbo_af_closed_form) */
+#define MBO_AF_EI 0
+#define MBO_AF_UCB 1
+#define MBO_AF_PI 2
+
 /* MLP arithmetic */
 #define MBO_MLP_FP32 0   /* CUDA-core fp32 FMA (validation mode, any architecture) */
 #define MBO_MLP_TF32 1   /* tcgen05 kind::tf32, fp32 accumulate in TMEM */
@@ -185,6 +190,13 @@ int mbo_value_net(const mbo_policy* value_net, int B, const float* tT, float* va
  *                  counter-based generator keyed (seed, episode, step, candidate)
  *   logp/entropy   Categorical.log_prob / entropy (policies.py:157-159)
  * ------------------------------------------------------------------------------------- */
+/* Closed-form acquisition functions of the reference's baselines on the GP posterior (policies.py:181-307):
+ * kind MBO_AF_EI, MBO_AF_PI (p0 = xi), MBO_AF_UCB (p0 = kappa; p1 > 0 selects the GP-UCB schedule with delta = p1 and
+ * input dimension D).  mean, std [B,M] fp32 from mbo_gp_posterior, epi [B,4] as in mbo_af_logits (incumbent, -,
+ * timestep, -).  af [B,M] fp32: feed it to mbo_logits_argmax / mbo_logits_topk like NeuralAF logits. */
+int mbo_af_closed_form(int kind, int B, int M, const float* mean, const float* std, const float* epi, double p0,
+                       double p1, int D, float* af, void* stream);
+
 int mbo_logits_argmax(int B, int M, const float* logits, int32_t* action, float* max_logit, void* stream);
 int mbo_logits_topk(int B, int M, int k, const float* logits, int32_t* idx /*[B,k]*/,
                     float* val /*[B,k]*/, void* stream);

@@ -8,6 +8,7 @@ LIB_PATH = os.environ.get("MBO_LIB_PATH", os.path.join(_HERE, "libmetabo_b200.so
 KERNEL_IDS = {"RBF": 0, "Matern32": 1, "Matern52": 2}
 GP_FP64, GP_FP32 = 0, 1
 MLP_FP32, MLP_TF32, MLP_BF16X3, MLP_FP16 = 0, 1, 2, 3
+AF_EI, AF_UCB, AF_PI = 0, 1, 2
 MLP_MODES = {"fp32": MLP_FP32, "tf32": MLP_TF32, "bf16x3": MLP_BF16X3, "fp16": MLP_FP16}
 ACT = {"relu": 0, "tanh": 1}
 FEAT_MEAN, FEAT_STD, FEAT_X0, FEAT_INCUMBENT, FEAT_TPERC, FEAT_TIMESTEP, FEAT_BUDGET = 0, 1, 2, 10, 11, 12, 13
@@ -46,6 +47,7 @@ SYMBOLS = [
     ("mbo_af_eval_fused", _i, [_vp, _i, _i, _i, _i, _i, _vp, _i, C.POINTER(C.c_int32), C.POINTER(Candidates), _vp, _vp,
                                _vp, _vp, _vp, _sz, _vp]),
     ("mbo_value_net", _i, [_vp, _i, _vp, _vp, _vp]),
+    ("mbo_af_closed_form", _i, [_i, _i, _i, _vp, _vp, _vp, _d, _d, _i, _vp, _vp]),
     ("mbo_logits_argmax", _i, [_i, _i, _vp, _vp, _vp, _vp]),
     ("mbo_logits_topk", _i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
     ("mbo_logits_sample", _i, [_i, _i, _vp, _u64, _u64, _vp, _u64, _vp, _vp]),

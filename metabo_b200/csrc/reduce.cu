@@ -141,9 +141,61 @@ logp_entropy_kernel(int M, const float* __restrict__ logits, const int32_t* __re
   }
 }
 
+// Closed-form acquisition functions on the GP posterior (the reference's baselines):
+//   EI   metabo/policies/policies.py:236-267   (m - inc) Phi(z) + s phi(z),  z = (m - inc) / s,   0 where s == 0
+//   PI   metabo/policies/policies.py:270-307   Phi((m - (inc + xi)) / s),                         0 where s == 0
+//   UCB  metabo/policies/policies.py:181-233   m + kappa s;  kappa fixed, or GP-UCB:
+//        kappa_t = sqrt(2 log((t + 1)^(D/2 + 2) pi^2 / (3 delta)))
+// The reference evaluates them on the float32 state: differences and z are formed in fp32 and widened, pdf / cdf are
+// fp64 (scipy.stats.norm); the same here, result stored as fp32 next to the NeuralAF logits so that the top-k /
+// argmax kernels serve both.
+__global__ void __launch_bounds__(256)
+closed_form_af_kernel(int kind, size_t total, int M, const float* __restrict__ mean, const float* __restrict__ std_,
+                      const float* __restrict__ epi, double p0, double p1, int D, float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int b = (int)(i / (size_t)M);
+  const float m = mean[i], s = std_[i];
+  const float inc = epi[b * 4 + 0];
+  double r;
+  if (kind == MBO_AF_UCB) {
+    double kappa = p0;
+    if (p1 > 0.0) {                                  // GP-UCB schedule (delta = p1)
+      const double t = (double)epi[b * 4 + 2] + 1.0;
+      kappa = sqrt(2.0 * log(pow(t, 0.5 * D + 2.0) * 9.869604401089358 / (3.0 * p1)));
+    }
+    r = (double)m + kappa * (double)s;
+  } else if (s == 0.0f) {
+    r = 0.0;
+  } else if (kind == MBO_AF_EI) {
+    const float d = m - inc;
+    const double z = (double)(d / s);
+    const double pdf = 0.3989422804014327 * exp(-0.5 * z * z);
+    const double cdf = 0.5 * erfc(-z * 0.7071067811865476);
+    r = (double)d * cdf + (double)s * pdf;
+  } else {                                           // PI, xi = p0
+    const float d = m - (float)((double)inc + p0);
+    const double z = (double)(d / s);
+    r = 0.5 * erfc(-z * 0.7071067811865476);
+  }
+  out[i] = (float)r;
+}
+
 }  // namespace mbo
 
 using namespace mbo;
+
+extern "C" int mbo_af_closed_form(int kind, int B, int M, const float* mean, const float* std_, const float* epi,
+                                  double p0, double p1, int D, float* af, void* stream) {
+  MBO_CHECK_ARG(kind == MBO_AF_EI || kind == MBO_AF_UCB || kind == MBO_AF_PI, "mbo_af_closed_form: unknown kind %d", kind);
+  MBO_CHECK_ARG(B > 0 && M > 0 && mean && std_ && epi && af, "mbo_af_closed_form: bad argument");
+  MBO_CHECK_ARG(!(kind == MBO_AF_UCB && p1 > 0.0) || D > 0, "mbo_af_closed_form: GP-UCB needs D");
+  const size_t total = (size_t)B * M;
+  closed_form_af_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(kind, total, M, mean, std_, epi,
+                                                                                           p0, p1, D, af);
+  MBO_LAUNCH_CHECK();
+  return MBO_OK;
+}
 
 extern "C" int mbo_logits_argmax(int B, int M, const float* logits, int32_t* action, float* max_logit, void* stream) {
   MBO_CHECK_ARG(B > 0 && M > 0 && logits && action, "mbo_logits_argmax: bad argument");

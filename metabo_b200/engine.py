@@ -103,6 +103,7 @@ class AFEngine:
         self.keep_phase_logits = False  # also materialise the phase-1/2 logits (parity tests, smoke)
         self.fuse_gp = False         # opt-in: mbo_af_eval_fused (correct, but slower than the two-kernel path so far, see profiles/r01_notes.md)
         self.tc_ok = False           # set by set_policy: architecture supported by the tensor-core kernel
+        self.closed_form = None      # (kind, p0, p1): EI / UCB / PI of the reference's baselines instead of the NeuralAF
         self.kernel_events = None   # list -> (tag, start, end) CUDA events around GP / MLP launches
 
     # -- parameters -------------------------------------------------------------------------------
@@ -155,7 +156,7 @@ class AFEngine:
     def evaluate_topk(self, cand, k, want_logits=False):
         """GP posterior + NeuralAF + top-k; on the tensor-core path the selection is fused into the kernel's
         epilogue and the logits are only written when asked for.  Returns (mean, std, logits or None, idx)."""
-        if self.mlp_mode == L.MLP_FP32 or not self.tc_ok or not self.fuse_topk or self.can_fuse():
+        if self.closed_form is not None or self.mlp_mode == L.MLP_FP32 or not self.tc_ok or not self.fuse_topk or self.can_fuse():
             mean, std, lg = self.evaluate(cand, want_posterior=True)
             idx, _ = ops.logits_topk(lg, k)
             self.launches += 1
@@ -185,6 +186,14 @@ class AFEngine:
         if ev is not None:
             e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             e0.record()
+        if self.closed_form is not None:
+            mean, std = ops.gp_posterior(self.gp_state, self.T, cand, self.B, kernel=self.kernel,
+                                         precision=self.gp_precision, out_dtype=torch.float32,
+                                         n_active_max=self.n_active_max)
+            kind, p0, p1 = self.closed_form
+            af = ops.af_closed_form(kind, mean, std, self.epi, p0=p0, p1=p1, D=self.D)
+            self.launches += 2
+            return mean, std, af
         if self.can_fuse():
             # one kernel: fp64 GP warps feed the tensor-core MLP through shared memory
             mean = std = None
@@ -212,7 +221,7 @@ class AFEngine:
         return mean, std, logits
 
     def can_fuse(self):
-        return (self.fuse_gp and self.mlp_mode != L.MLP_FP32 and self.gp_precision == L.GP_FP64
+        return (self.closed_form is None and self.fuse_gp and self.mlp_mode != L.MLP_FP32 and self.gp_precision == L.GP_FP64
                 and self.n_active_max <= ops.FUSED_MAX_N and self.tc_ok)
 
     def af_round(self, deterministic=True, seed=0, step=0, refit=True, want_stats=False, want_posterior=False,

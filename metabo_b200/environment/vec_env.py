@@ -32,8 +32,8 @@ class VecMetaBO:
             if kwargs["T_min"] != kwargs["T_max"]:
                 raise NotImplementedError("VecMetaBO runs lanes in lock-step: T_min must equal T_max")
             self.T = kwargs["T_min"]
-        if kwargs.get("n_init_samples", 0) != 0:
-            raise NotImplementedError("n_init_samples > 0 is only used by the EI/Random baselines")
+        self.n_init_samples = int(kwargs.get("n_init_samples", 0))       # Sobol initial design (metabo_gym.py:59-61, 202-204)
+        assert self.n_init_samples <= self.T
         self.features = kwargs["features"]
         self.reward_transformation = kwargs["reward_transformation"]
         if self.reward_transformation not in ("none", "neg_linear", "neg_log10"):
@@ -69,6 +69,8 @@ class VecMetaBO:
             self.engine = AFEngine(B, self.D, self.T, self.features, discrete_domain=grid_np, **common)
             grid = self.engine.xi_table
         self.dev = self.engine.dev
+        self.initial_design = (torch.as_tensor(i4_sobol_generate(self.D, self.n_init_samples), device=self.dev)
+                               if self.n_init_samples > 0 else None)
         self.engine.reuse_multistart = True
         self.cardinality_xi_t = self.engine.M_final
         self.n_features = self.engine.n_features
@@ -93,13 +95,20 @@ class VecMetaBO:
         """Bind a NeuralAF: its weights feed the engine's kernels (replaces set_af_functions +
         the per-step numpy callback of metabo_gym.py:168-174, 708, 718)."""
         self.policy = pi
-        self.engine.codes_policy = [c for c, m in zip(self.engine.codes_all, pi.policy_mask()) if m]
         self._graphs = {}
+        if hasattr(pi, "engine_spec"):
+            # closed-form baseline AF (EI / UCB / PI, policies.py:181-307): no network, no value function
+            self.engine.closed_form = pi.engine_spec()
+            return
+        self.engine.closed_form = None
+        self.engine.codes_policy = [c for c, m in zip(self.engine.codes_all, pi.policy_mask()) if m]
         self.sync_policy()
         self.engine.policy.workspace(self.dev, 256)
 
     def sync_policy(self):
         pi = self.policy
+        if hasattr(pi, "engine_spec"):
+            return
         dev = self.dev
         self.engine.set_policy([l.weight.detach().to(dev) for l in pi.policy_net.fc],
                                [l.bias.detach().to(dev) for l in pi.policy_net.fc], pi.activation)
@@ -165,7 +174,7 @@ class VecMetaBO:
 
     def _values(self):
         """value net on (t, T) (policies.py:117-121) for the current state of every lane."""
-        if self.engine.value is None:
+        if self.engine.value is None or self.engine.closed_form is not None:
             return torch.zeros(self.B, device=self.dev)
         from .. import ops
         cols = []
@@ -205,7 +214,9 @@ class VecMetaBO:
 
     def _step_device(self, t, deterministic, do_round, prev, actions):
         eng = self.engine
-        if actions is None:
+        if t < self.n_init_samples:
+            x = self.initial_design[t][None, :].expand(self.B, self.D)   # the action is ignored (metabo_gym.py:202-204)
+        elif actions is None:
             x = prev["x_action"]                                  # [B, D] fp64
         else:
             from .. import ops

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from .. import gym_compat as gym
-from ..policies.policies import NeuralAF
+from ..policies.policies import NeuralAF, EI, PI, UCB
 from ..ppo.batchrecorder import BatchRecorder
 
 Result = namedtuple("Result",
@@ -33,28 +33,40 @@ def load_metabo_policy(logpath, load_iter, env, device, deterministic):
 def eval_experiment(eval_spec):
     env_id = eval_spec["env_id"]
     policy = eval_spec["policy"]
-    if policy != "MetaBO":
-        raise ValueError("Unknown policy!" if policy not in ("GP-UCB", "EI", "TAF-ME", "TAF-RANKING", "PI",
-                                                              "EPS-GREEDY", "GMM-UCB", "Random")
-                         else "baseline AF '%s' is outside the GPU hot path" % policy)
+    if policy not in ("MetaBO", "EI", "GP-UCB", "PI"):
+        raise ValueError("Unknown policy!" if policy not in ("TAF-ME", "TAF-RANKING", "EPS-GREEDY", "GMM-UCB", "Random")
+                         else "baseline '%s' is outside the GPU hot path" % policy)
     logpath, savepath = eval_spec["logpath"], eval_spec["savepath"]
     n_workers, n_episodes, T = eval_spec["n_workers"], eval_spec["n_episodes"], eval_spec["T"]
     assert n_episodes % n_workers == 0
-    load_iter, deterministic = eval_spec["load_iter"], eval_spec["deterministic"]
+    load_iter, deterministic = eval_spec.get("load_iter"), eval_spec.get("deterministic", True)
     os.makedirs(savepath, exist_ok=True)
     env_seeds = eval_spec["env_seed_offset"] + np.arange(n_workers)
     env_specs = gym.registry.env_specs[env_id]._kwargs
-    with open(os.path.join(logpath, "params_" + str(load_iter)), "rb") as f:
-        policy_specs = pkl.load(f)
+    feature_order = ["posterior_mean", "posterior_std", "incumbent", "timestep"]     # metabo_gym.py:95
+    if policy == "MetaBO":
+        with open(os.path.join(logpath, "params_" + str(load_iter)), "rb") as f:
+            policy_specs = pkl.load(f)
 
-    def policy_fn(osp, asp, det):
-        return NeuralAF(observation_space=osp, action_space=asp, deterministic=det,
-                        options=policy_specs["policy_options"])
+        def policy_fn(osp, asp, det):
+            return NeuralAF(observation_space=osp, action_space=asp, deterministic=det,
+                            options=policy_specs["policy_options"])
+    else:
+        # closed-form baselines on the same GP kernels (evaluate.py:102-118)
+        policy_specs = eval_spec["policy_specs"]
+        if policy == "EI":
+            policy_fn = lambda *_: EI(feature_order=feature_order)
+        elif policy == "PI":
+            policy_fn = lambda *_: PI(feature_order=feature_order, xi=policy_specs["xi"])
+        else:
+            policy_fn = lambda *_: UCB(feature_order=feature_order, kappa=policy_specs["kappa"], D=env_specs["D"],
+                                       delta=policy_specs["delta"])
 
     br = BatchRecorder(size=T * n_episodes, env_id=env_id, env_seeds=list(env_seeds), policy_fn=policy_fn,
                        n_workers=n_workers, deterministic=deterministic, store_states=False)
-    pi, _, _ = load_metabo_policy(logpath, load_iter, br, "cpu", deterministic)
-    br.set_worker_weights(pi=pi)
+    if policy == "MetaBO":
+        pi, _, _ = load_metabo_policy(logpath, load_iter, br, "cpu", deterministic)
+        br.set_worker_weights(pi=pi)
     br.record_batch(gamma=1.0, lam=1.0)
     rewards = tuple(t.reward for t in br.memory)
     br.cleanup()
@@ -63,6 +75,7 @@ def eval_experiment(eval_spec):
             datetime.strftime(datetime.now(), "%Y-%m-%d-%H-%M-%S"), env_id, env_seeds), file=f)
     result = Result(logpath=logpath, env_id=env_id, env_specs=env_specs, policy=policy, policy_specs=policy_specs,
                     deterministic=deterministic, load_iter=load_iter, T=T, n_episodes=n_episodes, rewards=rewards)
-    with open(os.path.join(savepath, "result_metabo_iter_{:04d}".format(load_iter)), "wb") as f:
+    fn = "result_metabo_iter_{:04d}".format(load_iter) if policy == "MetaBO" else "result_{}".format(policy)   # evaluate.py:165
+    with open(os.path.join(savepath, fn), "wb") as f:
         pkl.dump(result, f)
     return result

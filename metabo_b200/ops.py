@@ -222,6 +222,18 @@ def value_net(policy, tT):
     return out
 
 
+def af_closed_form(kind, mean, std, epi, p0=0.0, p1=0.0, D=0, out=None):
+    """EI / UCB / PI of the reference's baselines (policies.py:181-307) on a GP posterior -> af [B,M] fp32.
+    kind: L.AF_EI, L.AF_UCB (p0 = kappa, p1 = delta > 0 for the GP-UCB schedule), L.AF_PI (p0 = xi)."""
+    _chk(mean, torch.float32, "mean"); _chk(std, torch.float32, "std"); _chk(epi, torch.float32, "epi")
+    B, M = mean.shape
+    if out is None:
+        out = torch.empty((B, M), dtype=torch.float32, device=mean.device)
+    L.check(L.lib().mbo_af_closed_form(int(kind), B, M, _p(mean), _p(std), _p(epi), float(p0), float(p1), int(D),
+                                       _p(out), _stream()), "mbo_af_closed_form")
+    return out
+
+
 def logits_argmax(logits, a=None, v=None):
     _chk(logits, torch.float32, "logits")
     B, M = logits.shape

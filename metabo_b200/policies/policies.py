@@ -205,3 +205,85 @@ class NeuralAF(nn.Module):
         if type(m) == nn.Linear:
             m.weight.data.normal_(mean=0.0, std=0.01)
             m.bias.data.fill_(0.0)
+
+
+class _ClosedFormAF:
+    """Shared part of the baseline AFs (metabo/policies/policies.py:181-307): same constructor arguments, `af`,
+    `act`, `set_requires_grad`, `reset` as the reference; evaluated by `mbo_af_closed_form` on the GPU.  Bound to a
+    VecMetaBO (set_policy) they replace the NeuralAF inside the AF-optimisation rounds; `af` / `act` on a
+    materialised state keep the reference's calling convention.  Ties: lowest index (the reference draws uniformly
+    among exact ties from numpy's global RNG)."""
+    kind = None
+
+    def engine_spec(self):
+        raise NotImplementedError
+
+    def _columns(self, state):
+        fo = self.feature_order
+        st = np.asarray(state, dtype=np.float32)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        mean = torch.as_tensor(st[None, :, fo.index("posterior_mean")].copy(), device=dev)
+        std = torch.as_tensor(st[None, :, fo.index("posterior_std")].copy(), device=dev)
+        epi = torch.zeros((1, 4), dtype=torch.float32, device=dev)
+        if "incumbent" in fo:
+            epi[0, 0] = float(st[0, fo.index("incumbent")])
+        if "timestep" in fo:
+            epi[0, 2] = float(st[0, fo.index("timestep")])
+        return mean, std, epi
+
+    def _af_device(self, state):
+        mean, std, epi = self._columns(state)
+        kind, p0, p1 = self.engine_spec()
+        return ops.af_closed_form(kind, mean, std, epi, p0=p0, p1=p1, D=getattr(self, "D", 0) or 0)
+
+    def af(self, state):
+        return self._af_device(state)[0].to("cpu").numpy().astype(self.out_dtype)
+
+    def act(self, state):
+        st = state.numpy() if isinstance(state, torch.Tensor) else state
+        a, _ = ops.logits_argmax(self._af_device(st))
+        return a[0].to("cpu", torch.int64), torch.tensor(0.0)
+
+    def set_requires_grad(self, flag):
+        pass
+
+    def reset(self):
+        pass
+
+
+class UCB(_ClosedFormAF):
+    out_dtype = np.float32
+
+    def __init__(self, feature_order, kappa, D=None, delta=None):
+        self.feature_order = list(feature_order)
+        self.kappa = kappa
+        self.D = D
+        self.delta = delta
+        assert not (self.kappa == "gp_ucb" and self.D is None)
+        assert not (self.kappa == "gp_ucb" and self.delta is None)
+
+    def engine_spec(self):
+        if self.kappa == "gp_ucb":
+            return L.AF_UCB, 0.0, float(self.delta)
+        return L.AF_UCB, float(self.kappa), 0.0
+
+
+class EI(_ClosedFormAF):
+    out_dtype = np.float64
+
+    def __init__(self, feature_order):
+        self.feature_order = list(feature_order)
+
+    def engine_spec(self):
+        return L.AF_EI, 0.0, 0.0
+
+
+class PI(_ClosedFormAF):
+    out_dtype = np.float64
+
+    def __init__(self, feature_order, xi):
+        self.feature_order = list(feature_order)
+        self.xi = xi
+
+    def engine_spec(self):
+        return L.AF_PI, float(self.xi), 0.0

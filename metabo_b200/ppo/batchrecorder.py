@@ -106,6 +106,8 @@ class BatchRecorder:
         self.action_space = gym.spaces.Discrete(self.env.cardinality_xi_t)
         self.pi = policy_fn(self.observation_space, self.action_space, self.deterministic)
         self.pi.set_requires_grad(False)
+        if hasattr(self.pi, "engine_spec"):
+            self.deterministic = True          # closed-form baselines act by argmax (policies.py:191-199)
         self.env.set_policy(self.pi)
         self.env.use_graphs = bool(self.use_graphs) and os.environ.get("MBO_NO_GRAPHS") is None
 

@@ -319,3 +319,42 @@ def hm3_max(t, s):
     t_range = np.array([[-0.11, 0.88], [-0.55, 0.44], [-0.85, 0.14]])
     pos = np.array([[0.114614, 0.555649, 0.852547]])
     return float(s * hm3(pos)[0, 0]), pos + np.clip(t, t_range[:, 0], t_range[:, 1])
+
+
+# ---------------------------------------------------------------------------------------------
+# Closed-form baseline acquisition functions (metabo/policies/policies.py:181-307), restated on the float32 state
+# with the reference's dtype flow: differences and z in float32, pdf / cdf in float64 (scipy.stats.norm).
+# ---------------------------------------------------------------------------------------------
+def ei_af(mean, std, incumbent):
+    """EI.af, policies.py:249-261.  mean, std, incumbent float32 [M] -> float64 [M] (0 where std == 0)."""
+    from scipy.stats import norm
+    mean, std, incumbent = (np.asarray(a, dtype=np.float32) for a in (mean, std, incumbent))
+    mask = std != 0.0
+    out = np.zeros(mean.shape, dtype=np.float64)
+    d = (mean - incumbent)[mask]
+    z = (d / std[mask]).astype(np.float64)
+    out[mask] = d * norm.cdf(z) + std[mask] * norm.pdf(z)
+    return out
+
+
+def pi_af(mean, std, incumbent, xi):
+    """PI.af, policies.py:289-301."""
+    from scipy.stats import norm
+    mean, std, incumbent = (np.asarray(a, dtype=np.float32) for a in (mean, std, incumbent))
+    mask = std != 0.0
+    out = np.zeros(mean.shape, dtype=np.float64)
+    z = ((mean[mask] - (incumbent[mask] + xi).astype(np.float32)) / std[mask]).astype(np.float64)
+    out[mask] = norm.cdf(z)
+    return out
+
+
+def ucb_af(mean, std, kappa, timestep=None, D=None, delta=None):
+    """UCB.af / compute_kappa, policies.py:201-229 (kappa == "gp_ucb": the GP-UCB schedule on timestep + 1)."""
+    mean, std = np.asarray(mean, dtype=np.float32), np.asarray(std, dtype=np.float32)
+    if kappa == "gp_ucb":
+        t = np.asarray(timestep, dtype=np.float32) + 1
+        tau = 2 * np.log(t.astype(np.float64) ** (D / 2 + 2) * np.pi ** 2 / (3 * delta))
+        k = np.sqrt(tau)
+    else:
+        k = float(kappa)
+    return mean.astype(np.float64) + k * std.astype(np.float64)

@@ -65,6 +65,27 @@ def test_neural_af_api_matches_reference_semantics(golden_dir, wfile, F, M):
     assert float((lg2.detach().cpu() - lo).abs().max()) <= 1e-4 * scale + 1e-5
 
 
+@pytest.mark.parametrize("mode,tol", [("fp16", 2e-3), ("tf32", 2e-3)])
+def test_neural_af_forward_fast_modes_on_materialised_states(golden_dir, mode, tol):
+    """NeuralAF.forward on materialised states (the dense feature source of the tensor-core kernel) in the two
+    throughput modes: logits within 2e-3 of the fp32 oracle on these synthetic U[0,1] states (the 1e-3 bar is stated
+    and tested on the reference's own states in test_af_gpu.py), argmax the oracle's unless near-tied."""
+    pi, pw = _policy(golden_dir, "weights_hm3_1988.npz", mode=mode, M=1733, F=7)
+    rng = np.random.RandomState(3)
+    states = rng.rand(4, 1733, 7).astype(np.float32)
+    states[:, :, -2] = 11.0
+    states[:, :, -1] = 30.0
+    lo, _ = O.policy_forward(pw, states)
+    with torch.no_grad():
+        lg, _ = pi.forward(torch.from_numpy(states))
+    scale = float(lo.abs().max())
+    assert float((lg - lo).abs().max()) <= tol * scale
+    top = lo.max(dim=1).values
+    picked = lo.gather(1, lg.argmax(dim=1, keepdim=True))[:, 0]
+    assert bool((picked >= top - 2 * tol * scale).all())
+    pi.kernel_handles()[0].check()
+
+
 def test_single_env_deterministic_branin_episode(golden_dir):
     """evaluate_metabo_branin.py settings, seed 100: the first state is a pure function of the
     weights (empty GP) and must equal the reference's; the free-running episode must reach the
@@ -192,7 +213,8 @@ def test_eval_experiment_with_shipped_checkpoint_layout(golden_dir, tmp_path):
     assert os.path.exists(tmp_path / "eval" / "result_metabo_iter_1988")
 
 
-def test_cuda_graph_replay_equals_eager_rollouts(golden_dir):
+@pytest.mark.parametrize("mode", ["tf32", "fp16"])
+def test_cuda_graph_replay_equals_eager_rollouts(golden_dir, mode):
     """The episode loop captured as CUDA graphs (one per BO step index) must reproduce the eager rollouts bit for
     bit over several consecutive batches (new objectives every episode, stochastic policy: fresh Gumbel noise on
     every replay through the device-resident step counter)."""
@@ -201,14 +223,14 @@ def test_cuda_graph_replay_equals_eager_rollouts(golden_dir):
     from metabo_b200.ppo.batchrecorder import BatchRecorder
     pw = O.PolicyWeights.from_npz(os.path.join(golden_dir, "weights_bra_1635.npz"))
     spec = dict(BRA_SPEC, T=6, N_MS=400, N_LS=200, f_opts={"bound_translation": 0.1, "bound_scaling": 0.1, "M": 50},
-                reward_transformation="neg_log10", env_id="MetaBO-GRAPH-v0")
+                reward_transformation="neg_log10", env_id="MetaBO-GRAPH-%s-v0" % mode)
     gym.register(id=spec["env_id"], entry_point="metabo.environment.metabo_gym:MetaBO", max_episode_steps=6, kwargs=spec)
-    opts = dict(pw.options, mlp_mode="tf32")
+    opts = dict(pw.options, mlp_mode=mode)
 
     def run(use_graphs):
         fn = lambda o, a, d: NeuralAF(o, a, d, options=opts)
         br = BatchRecorder(size=6 * 12, env_id=spec["env_id"], env_seeds=[3, 4, 5], policy_fn=fn, n_workers=3,
-                           deterministic=False, store_states=True, mlp_mode="tf32", use_graphs=use_graphs)
+                           deterministic=False, store_states=True, mlp_mode=mode, use_graphs=use_graphs)
         pi = fn(br.observation_space, br.action_space, False)
         pi.load_state_dict({k: v.clone() for k, v in pw.sd.items()})
         br.set_worker_weights(pi)
