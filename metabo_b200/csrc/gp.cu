@@ -16,6 +16,7 @@
 // (zero above the diagonal / beyond n) so the posterior kernel reads 8 rows of one column with
 // two broadcast LDS.128.
 #include "common.cuh"
+#include <type_traits>
 #include <stdlib.h>
 
 namespace mbo {
@@ -181,16 +182,20 @@ constexpr int POST_THREADS = 128;
 
 // DT: compile-time input dimension (0 = run time, predicated to MBO_MAX_D).  The distance loops are a third of
 // the kernel's issued instructions when they are unrolled to 8 dimensions and predicated down to 3.
-template <typename T, int TC, int DT>
+// KID: compile-time kernel family (the three K_of_r bodies in one loop cost register moves at every merge point).
+template <typename T, int TC, int DT, int KID>
 __global__ void __launch_bounds__(POST_THREADS)
-gp_posterior_kernel(int nmax, int kid, const double* __restrict__ gp_state, mbo_candidates cand,
-                    int tiles_per_episode, void* __restrict__ mean_out, void* __restrict__ std_out,
-                    int out_is_f32) {
+gp_posterior_kernel(int nmax, int kid_rt, const double* __restrict__ gp_state, mbo_candidates cand,
+                    int tiles_per_episode, int ctas_per_episode, void* __restrict__ mean_out,
+                    void* __restrict__ std_out, int out_is_f32) {
   extern __shared__ __align__(16) unsigned char smraw[];
+  constexpr int kid = KID;
+  (void)kid_rt;
   const int D = DT ? DT : cand.D;
   constexpr int DU = DT ? DT : MBO_MAX_D;       // unroll bound of the per-dimension loops
-  const int b = blockIdx.x / tiles_per_episode;
-  const int tile = blockIdx.x - b * tiles_per_episode;
+  // a CTA loads the episode blob once and walks tiles cta, cta + ctas_per_episode, ... of that episode
+  const int b = blockIdx.x / ctas_per_episode;
+  const int cta = blockIdx.x - b * ctas_per_episode;
   const int tid = threadIdx.x;
   const size_t stride = gp_state_doubles(nmax, D);
   const double* st = gp_state + (size_t)b * stride;
@@ -217,6 +222,7 @@ gp_posterior_kernel(int nmax, int kid, const double* __restrict__ gp_state, mbo_
   for (int i = tid; i < lcount; i += POST_THREADS) sL[i] = (T)st[gp_off_linv(NPmax, D) + i];
   __syncthreads();
 
+  for (int tile = cta; tile < tiles_per_episode; tile += ctas_per_episode) {
   const int m0 = tile * POST_THREADS * TC;
   T xs[TC][DU];
 #pragma unroll
@@ -330,6 +336,7 @@ gp_posterior_kernel(int nmax, int kid, const double* __restrict__ gp_state, mbo_
     if (out_is_f32) { ((float*)mean_out)[o] = (float)mean_v; ((float*)std_out)[o] = (float)sd; }
     else { ((double*)mean_out)[o] = mean_v; ((double*)std_out)[o] = sd; }
   }
+  }   // tile loop (each thread only touches its own shared-memory column: no barrier between tiles)
 }
 
 template <typename T, int TC>
@@ -345,16 +352,25 @@ static int launch_posterior(int B, int nmax, int ns, int kid, const double* gp_s
                             void* mean, void* std_, int out_is_f32, cudaStream_t s) {
   size_t smem = posterior_smem_bytes<T, TC>(ns, cand.D);
   // the dimensions of the shipped experiments get their own instantiation (fp64 only), everything else the generic one
-  auto kern = gp_posterior_kernel<T, TC, 0>;
+  auto pick = [&](auto dt) {
+    constexpr int DTV = decltype(dt)::value;
+    return kid == MBO_KERNEL_RBF ? gp_posterior_kernel<T, TC, DTV, MBO_KERNEL_RBF>
+           : kid == MBO_KERNEL_MATERN32 ? gp_posterior_kernel<T, TC, DTV, MBO_KERNEL_MATERN32>
+                                        : gp_posterior_kernel<T, TC, DTV, MBO_KERNEL_MATERN52>;
+  };
+  auto kern = pick(std::integral_constant<int, 0>{});
   if (sizeof(T) == 8) {
-    if (cand.D == 2) kern = gp_posterior_kernel<T, TC, 2>;
-    else if (cand.D == 3) kern = gp_posterior_kernel<T, TC, 3>;
-    else if (cand.D == 4) kern = gp_posterior_kernel<T, TC, 4>;
-    else if (cand.D == 6) kern = gp_posterior_kernel<T, TC, 6>;
+    if (cand.D == 2) kern = pick(std::integral_constant<int, 2>{});
+    else if (cand.D == 3) kern = pick(std::integral_constant<int, 3>{});
+    else if (cand.D == 4) kern = pick(std::integral_constant<int, 4>{});
+    else if (cand.D == 6) kern = pick(std::integral_constant<int, 6>{});
   }
   MBO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int tiles = (cand.M + POST_THREADS * TC - 1) / (POST_THREADS * TC);
-  kern<<<B * tiles, POST_THREADS, smem, s>>>(nmax, kid, gp_state, cand, tiles, mean, std_, out_is_f32);
+  // enough CTAs to fill the machine several times over, few enough that the blob load is amortised over ~4 tiles
+  int ctas = tiles;
+  if ((long long)B * tiles > 4096) { ctas = (tiles + 3) / 4; if (ctas < 1) ctas = 1; }
+  kern<<<B * ctas, POST_THREADS, smem, s>>>(nmax, kid, gp_state, cand, tiles, ctas, mean, std_, out_is_f32);
   MBO_LAUNCH_CHECK();
   return MBO_OK;
 }
