@@ -146,6 +146,72 @@ mlp_simt_kernel(SimtNet net, FeatSpec fs, mbo_candidates cand, int tiles_per_epi
   }
 }
 
+// Dense rows, few of them (the value net: [B, 2] inputs, policies.py:117-121).  mlp_simt_kernel streams every weight
+// from L2 inside its k loop; with 32 rows per CTA a batch of 60-1024 rows is 2-32 CTAs, each paying ~800 dependent
+// L2 latencies (130-150 us).  Here a CTA handles VR rows and stages one layer's weights in shared memory with
+// coalesced 16-byte loads before using them; the arithmetic (bias first, k ascending, one fma per term) and therefore
+// the result is the same as mlp_simt_kernel's.
+constexpr int VR = 8;
+__global__ void __launch_bounds__(ST)
+mlp_rows_kernel(SimtNet net, const float* __restrict__ direct, int R, int hmax, int wmax, float* __restrict__ out) {
+  extern __shared__ __align__(16) float smv[];
+  float* sW = smv;                      // [K][N] of the current layer
+  float* bufA = smv + wmax;             // [hmax][VR]
+  float* bufB = bufA + hmax * VR;
+  const int tid = threadIdx.x;
+  const int row0 = blockIdx.x * VR;
+  const int rows_valid = min(VR, R - row0);
+  const int F = net.widths[0];
+  for (int e = tid; e < F * VR; e += ST) {
+    const int f = e / VR, c = e - f * VR;
+    bufA[f * VR + c] = c < rows_valid ? direct[(size_t)(row0 + c) * F + f] : 0.f;
+  }
+  float* in = bufA;
+  float* outb = bufB;
+  for (int l = 0; l < net.n_layers; ++l) {
+    const int K = net.widths[l], N = net.widths[l + 1];
+    const float* __restrict__ Wt = net.Wt[l];
+    const int cnt = K * N;
+    __syncthreads();                    // previous layer done with sW / wrote `in`
+    if ((cnt & 3) == 0 && (((size_t)Wt) & 15) == 0) {
+      const float4* src = reinterpret_cast<const float4*>(Wt);
+      float4* dst = reinterpret_cast<float4*>(sW);
+      for (int e = tid; e < cnt / 4; e += ST) dst[e] = src[e];
+    } else {
+      for (int e = tid; e < cnt; e += ST) sW[e] = Wt[e];
+    }
+    __syncthreads();
+    const bool last = (l == net.n_layers - 1);
+    for (int o = tid; o < N; o += ST) {
+      float acc[VR];
+      const float b0 = net.b[l][o];
+#pragma unroll
+      for (int c = 0; c < VR; ++c) acc[c] = b0;
+      for (int k = 0; k < K; ++k) {
+        const float w = sW[k * N + o];
+        const float4* a4 = reinterpret_cast<const float4*>(in + k * VR);
+#pragma unroll
+        for (int c4 = 0; c4 < VR / 4; ++c4) {
+          const float4 a = a4[c4];
+          acc[c4 * 4 + 0] = fmaf(w, a.x, acc[c4 * 4 + 0]);
+          acc[c4 * 4 + 1] = fmaf(w, a.y, acc[c4 * 4 + 1]);
+          acc[c4 * 4 + 2] = fmaf(w, a.z, acc[c4 * 4 + 2]);
+          acc[c4 * 4 + 3] = fmaf(w, a.w, acc[c4 * 4 + 3]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < VR; ++c) outb[o * VR + c] = last ? acc[c] : act_fn(net.activation, acc[c]);
+    }
+    float* t = in; in = outb; outb = t;
+  }
+  __syncthreads();
+  const int NO = net.widths[net.n_layers];
+  for (int e = tid; e < NO * VR; e += ST) {
+    const int o = e / VR, c = e - o * VR;
+    if (c < rows_valid) out[(size_t)(row0 + c) * NO + o] = in[o * VR + c];
+  }
+}
+
 int simt_forward(const mbo_policy* p, int B, int F, const int32_t* feat_src, const mbo_candidates* cand,
                  const float* mean, const float* std_, const float* epi, const float* direct, int R,
                  float* out, cudaStream_t s, const float* dense = nullptr, int dense_F = 0) {
@@ -163,6 +229,17 @@ int simt_forward(const mbo_policy* p, int B, int F, const int32_t* feat_src, con
   memset(&c0, 0, sizeof(c0));
   int grid, tiles = 1;
   if (direct) {
+    // few dense rows: weights staged in shared memory when the widest layer fits
+    int wmax = 0;
+    for (int l = 0; l < p->n_layers; ++l) wmax = max(wmax, p->widths[l] * p->widths[l + 1]);
+    wmax = (wmax + 3) & ~3;
+    const size_t smem_rows = sizeof(float) * ((size_t)wmax + 2 * (size_t)hmax * VR);
+    if (R <= 2048 && smem_rows <= 200 * 1024) {
+      MBO_CUDA(cudaFuncSetAttribute(mlp_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+      mlp_rows_kernel<<<(R + VR - 1) / VR, ST, smem_rows, s>>>(net, direct, R, hmax, wmax, out);
+      MBO_LAUNCH_CHECK();
+      return MBO_OK;
+    }
     grid = (R + TILE - 1) / TILE;
   } else {
     for (int f = 0; f < F; ++f) fs.src[f] = feat_src[f];
