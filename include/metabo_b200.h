@@ -216,6 +216,32 @@ int mbo_candidates_gather(int B, const mbo_candidates* cand, int k, const int32_
 int mbo_cubes_around(int B, int k, int D, const double* x /*[B,k,D]*/, double diam,
                      double* cubes /*[B,k,2,D]*/, void* stream);
 
+/* ---- PPO policy update ------------------------------------------------------------
+ * The policy-net half of one PPO optimiser step on one (shard of a) minibatch: replaces the autograd
+ * forward + backward of ppo.py:129-178 (clipped surrogate + entropy bonus), policies.py:150-161
+ * (Categorical(logits).log_prob / entropy) and mlp.py:25-61 for the F -> H -> H -> H -> H -> 1 ReLU
+ * policy net (H <= 207, F <= 8).  TF32 tensor-core GEMMs with fp32 accumulation, deterministic
+ * (fixed-order split-K reduction, no atomics).
+ *   states      [E, M, F_state] fp32 (the PPO buffer's states); feat_col[F] = state column of policy
+ *               feature f (policies.py:109-114 feature mask), HOST array
+ *   W, b        HOST arrays of 5 device pointers, torch layout W_l [out][in], b_l [out]
+ *   actions     [E] int32; advs, logp_old [E] fp32 (advantages already normalised, ppo.py:141-144)
+ *   inv_n_global  1 / (global minibatch size): every loss term is divided by it (ppo.py:148-168 mean)
+ *   dW, db      HOST arrays of 5 device pointers, gradients of
+ *               loss_ppo + ent_coeff * loss_ent  w.r.t. W_l, b_l (overwritten, not accumulated)
+ *   terms       [E, 4] fp32: logp(action), entropy, -min(ratio A, clip(ratio) A) / n, ratio
+ *   workspace   mbo_ppo_workspace_bytes(E, M) bytes, 256-byte aligned, zero-initialised ONCE by the
+ *               caller; its first int32 is a sticky error word (bit 0: a pipeline wait timed out)
+ * mbo_ppo_debug_offsets: byte offsets inside the workspace of h1..h4, dZ1..dZ4 ([E*M, 208] fp32 each),
+ * logits, dlogits ([E*M] fp32), terms, error word -- for the per-stage parity tests. */
+size_t mbo_ppo_workspace_bytes(int E, int M);
+int mbo_ppo_debug_offsets(int E, int M, size_t* off /*[12]*/);
+int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32_t* feat_col, int H,
+                        const float* states, const float* const* W, const float* const* b,
+                        const int32_t* actions, const float* advs, const float* logp_old, float epsilon,
+                        float ent_coeff, float inv_n_global, float* const* dW, float* const* db,
+                        float* terms, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

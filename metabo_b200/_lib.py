@@ -54,6 +54,10 @@ SYMBOLS = [
     ("mbo_logits_logp_entropy", _i, [_i, _i, _vp, _vp, _vp, _vp, _vp]),
     ("mbo_candidates_gather", _i, [_i, C.POINTER(Candidates), _i, _vp, _vp, _vp]),
     ("mbo_cubes_around", _i, [_i, _i, _i, _vp, _d, _vp, _vp]),
+    ("mbo_ppo_workspace_bytes", _sz, [_i, _i]),
+    ("mbo_ppo_debug_offsets", _i, [_i, _i, C.POINTER(_sz)]),
+    ("mbo_ppo_policy_grad", _i, [_i, _i, _i, _i, C.POINTER(C.c_int32), _i, _vp, C.POINTER(_vp), C.POINTER(_vp), _vp, _vp,
+                                 _vp, C.c_float, C.c_float, C.c_float, C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _sz, _vp]),
 ]
 
 

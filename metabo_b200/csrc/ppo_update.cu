@@ -1,0 +1,778 @@
+// ppo_update.cu -- the policy-net half of one PPO optimiser step, hand-written for sm_100a.
+//
+// Reference: ppo.py:129-178 (clipped surrogate + entropy bonus on one minibatch), policies.py:150-161
+// (Categorical(logits): log_prob(action), entropy) and the autograd backward of mlp.py:25-61 for the
+// F -> H -> H -> H -> H -> 1 ReLU policy net.  One call = forward with saved activations, loss terms,
+// dlogits, dgrad chain, wgrad of every layer.  `rows` R = E episodes x M candidates (60 x 966 in C3).
+//
+// Data layout in HBM (workspace): activations H1..H4 and pre-activation gradients dZ1..dZ4 are row-major
+// [R, 208] fp32 already rounded to tf32 (round-to-nearest, so the tensor cores' truncation is exact), column H
+// of every H_l is a ones column (bias rides inside the GEMMs: forward Wb = [W | b], wgrad column H = db),
+// columns above are zero.
+//
+// Kernels
+//   upd_pack_kernel      W1..W3 -> UMMA-canonical K-major images [W | b] (forward) and W^T (dgrad)
+//   upd_layer0_kernel    h1 = relu(x W0^T + b0)                              CUDA cores (K = F <= 8)
+//   upd_gemm_kernel<0>   h_{l+1} = relu([h_l,1] Wb^T) (+ head logit)         tcgen05 kind::tf32, A and B from smem
+//   upd_loss_kernel      per episode: log-softmax, logp(a), entropy, clipped surrogate, dlogits
+//   upd_dz4_kernel       dZ4 = dlogit (x) w4 . [h4 > 0]  (+ partial sums of dw4, db4)
+//   upd_gemm_kernel<1>   dZ_l = (dZ_{l+1} W_l) . [h_l > 0]                   tcgen05 kind::tf32
+//   upd_wgrad_kernel     dWb_l = dZ_{l+1}^T [h_l,1]  split-K over CTAs        tcgen05 kind::tf32, both operands MN-major
+//   upd_wgrad0_kernel    dW0 = dZ1^T x, db0                                   CUDA cores
+//   upd_reduce_kernel    fixed-order sum of the split-K partials -> dW, db    (deterministic, no atomics)
+//
+// Operand staging: the activation / gradient tiles are row-major fp32 in HBM; 16-byte cp.async copies place each
+// chunk where the no-swizzle UMMA canonical layout wants it (K-major for forward / dgrad, MN-major for wgrad where
+// K = rows), completion is signalled with cp.async.mbarrier.arrive.noinc, the weight images arrive by one
+// cp.async.bulk per stage.  All GEMMs here are HBM-bound (50 FLOP/B at TF32), not tensor-bound.
+#include <stdlib.h>
+#include "common.cuh"
+#include "tmem_ldst.cuh"
+
+namespace mbo {
+namespace upd {
+
+constexpr int HP = 208;             // padded width: UMMA N, row pitch of H / dZ (floats)
+constexpr int TM = 128;             // rows per output tile (UMMA M)
+constexpr int KT = 32;              // K floats per pipeline stage (forward / dgrad), K rows per stage (wgrad)
+constexpr int NKT = 7;              // ceil(208 / 32)
+constexpr int A_STAGE = TM * KT * 4;          // 16 384
+constexpr int B_STAGE = HP * KT * 4;          // 26 624
+constexpr int IMG_FLOATS = NKT * HP * KT;     // 46 592 floats per weight image
+constexpr int GEMM_STAGES = 2;
+constexpr int GEMM_THREADS = 192;   // warps 0-3: A loaders then epilogue; warp 4: MMA issue; warp 5: weight stages
+constexpr int GEMM_SMEM = GEMM_STAGES * (A_STAGE + B_STAGE) + 256;
+constexpr int WG_STAGES = 3;
+constexpr int WG_A_STAGE = 8 * 4096;          // 8 blocks of 32 columns (256 = two M blocks) x 32 K rows x 128 B
+constexpr int WG_B_STAGE = 7 * 4096;          // 7 blocks (224 >= 208 columns)
+constexpr int WG_SMEM = WG_STAGES * (WG_A_STAGE + WG_B_STAGE) + 256 + 1024;   // + alignment slack
+constexpr int WG_SPLIT = 49;                  // 49 x 3 layers = 147 CTAs, one wave
+constexpr int THIN_THREADS = 208;             // 52 four-column groups x 4 row lanes
+constexpr int THIN_CTAS = 296;
+constexpr int MAXF = 8;
+
+// ---- PTX wrappers (own namespace: neural_af_tc.cu has same-named helpers with other constants) -----------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded wait: after 2 s (a pipeline bug) the CTA-wide abort flag is latched, every later wait returns at once,
+// the kernel runs out on garbage and the host finds bit 0 of the error word set.  Nothing hangs.
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, volatile int* abort_flag) {
+  if (*abort_flag) return;
+  const uint64_t t0 = globaltimer_ns();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3ff) == 0) {
+      if (*abort_flag) return;
+      if (globaltimer_ns() - t0 > 2000000000ull) { *abort_flag = 1; return; }
+    }
+  }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity, abort_flag);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// 16-byte asynchronous copy, zero-filled when `valid` is false (src must still be a mapped address)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const uint32_t n = valid ? 16u : 0u;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+// the mbarrier gets one (counted) arrival when every cp.async this thread has issued so far is complete
+__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[smem] * B[smem]^T, both operands through shared-memory descriptors
+__device__ __forceinline__ void mma_ss_tf32(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// cute::UMMA::SmemDescriptor, no swizzle, version 1.  K-major: LBO = distance of the two 16-byte K chunks of one
+// MMA, SBO = distance of 8-row groups.  MN-major: SBO = distance of 16-byte chunks along M/N, LBO = distance of
+// 8-row K groups (mma_sm100_desc.hpp make_umma_desc<Major::MN>, INTERLEAVE).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+// cute::UMMA::InstrDescriptor: D fp32, A/B tf32, M = 128, N = 208; bits 15/16 = A/B MN-major
+constexpr uint32_t IDESC_K = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(HP >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+constexpr uint32_t IDESC_MN = IDESC_K | (1u << 15) | (1u << 16);
+
+// ---- arguments ---------------------------------------------------------------------------------------------------
+struct Net {
+  const float* W[5];
+  const float* b[5];
+  float* dW[5];
+  float* db[5];
+  int F, F_state, H;
+  int col[MAXF];     // state column of policy feature f
+};
+
+struct Ws {          // workspace carve-up (device pointers)
+  int* err;
+  float* img_fwd[3];
+  float* img_dgr[3];
+  float* Hs[4];      // h1..h4
+  float* dZ[4];      // dZ1..dZ4
+  float* logits;
+  float* dl;
+  float* terms;      // [E,4]: logp(a), entropy, -min(surr1, surr2) / n, ratio
+  float* part_big;   // [WG_SPLIT][3][HP][HP]
+  float* part_head;  // [THIN_CTAS][HP]
+  float* part_l0;    // [THIN_CTAS][HP][MAXF + 1]
+};
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static size_t carve(int E, int M, unsigned char* base, Ws* w) {
+  const size_t R = (size_t)E * M;
+  const size_t Rp = align_up(R, TM);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return base ? base + o : nullptr; };
+  Ws t;
+  t.err = (int*)take(256);
+  for (int l = 0; l < 3; ++l) t.img_fwd[l] = (float*)take((size_t)IMG_FLOATS * 4);
+  for (int l = 0; l < 3; ++l) t.img_dgr[l] = (float*)take((size_t)IMG_FLOATS * 4);
+  for (int l = 0; l < 4; ++l) t.Hs[l] = (float*)take(Rp * HP * 4);
+  for (int l = 0; l < 4; ++l) t.dZ[l] = (float*)take(Rp * HP * 4);
+  t.logits = (float*)take(Rp * 4);
+  t.dl = (float*)take(Rp * 4);
+  t.terms = (float*)take((size_t)E * 4 * 4);
+  t.part_big = (float*)take((size_t)WG_SPLIT * 3 * HP * HP * 4);
+  t.part_head = (float*)take((size_t)THIN_CTAS * HP * 4);
+  t.part_l0 = (float*)take((size_t)THIN_CTAS * HP * (MAXF + 1) * 4);
+  if (w) *w = t;
+  return off;
+}
+
+// ---- weight images -----------------------------------------------------------------------------------------------
+// K-major canonical, one 26 624-byte stage per 32 K values: [kt][16-byte K chunk c (8)][n (208)][4 floats]
+__global__ void upd_pack_kernel(Net net, Ws ws) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 6 * IMG_FLOATS) return;
+  const int img = idx / IMG_FLOATS, o = idx - img * IMG_FLOATS;
+  const int l = img >> 1, dgr = img & 1;            // layer l + 1
+  const int kt = o / (HP * KT), r = o - kt * (HP * KT);
+  const int c = r / (HP * 4), r2 = r - c * (HP * 4);
+  const int n = r2 >> 2, e = r2 & 3;
+  const int k = kt * KT + c * 4 + e;
+  const int H = net.H;
+  const float* W = net.W[l + 1];
+  float v = 0.f;
+  if (!dgr) {
+    if (n < H) v = k < H ? W[(size_t)n * H + k] : (k == H ? net.b[l + 1][n] : 0.f);     // [W | b]
+  } else {
+    if (n < H && k < H) v = W[(size_t)k * H + n];                                        // W^T: N = in, K = out
+  }
+  (dgr ? ws.img_dgr[l] : ws.img_fwd[l])[o] = tf32_rn(v);
+}
+
+// ---- layer 0 on CUDA cores ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(THIN_THREADS) upd_layer0_kernel(Net net, const float* __restrict__ states, int R,
+                                                                   float* __restrict__ H1) {
+  const int cg = threadIdx.x % 52, rsub = threadIdx.x / 52;
+  const int F = net.F, H = net.H;
+  float w[4][MAXF], bias[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int j = cg * 4 + e;
+    bias[e] = j < H ? net.b[0][j] : 0.f;
+#pragma unroll
+    for (int f = 0; f < MAXF; ++f) w[e][f] = (j < H && f < F) ? net.W[0][(size_t)j * F + f] : 0.f;
+  }
+  const int rpc = (R + gridDim.x - 1) / gridDim.x;
+  const int r_end = min(R, (int)(blockIdx.x + 1) * rpc);
+  for (int r = blockIdx.x * rpc + rsub; r < r_end; r += 4) {
+    float x[MAXF];
+#pragma unroll
+    for (int f = 0; f < MAXF; ++f) x[f] = f < F ? __ldg(states + (size_t)r * net.F_state + net.col[f]) : 0.f;
+    float o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      // torch's Linear on the CPU accumulates the dot product first and adds the bias last
+      float acc = 0.f;
+#pragma unroll
+      for (int f = 0; f < MAXF; ++f) acc = fmaf(x[f], w[e][f], acc);
+      const int j = cg * 4 + e;
+      acc = fmaxf(acc + bias[e], 0.f);
+      o[e] = j < H ? tf32_rn(acc) : (j == H ? 1.f : 0.f);
+    }
+    *(float4*)(H1 + (size_t)r * HP + cg * 4) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ---- forward / dgrad GEMM -----------------------------------------------------------------------------------------
+struct GemmArgs {
+  const float* A;        // [R, HP] rows of this GEMM (h_l for forward, dZ_{l+1} for dgrad)
+  const float* Bimg;     // weight image
+  float* Out;            // [R, HP]
+  const float* mask;     // dgrad: h_l (ReLU mask), nullptr otherwise
+  const float* w4;       // forward of the last hidden layer: head weights [H], else nullptr
+  const float* b4;
+  float* logits;         // [R]
+  int R, H;
+};
+
+template <int EPI>   // 0: forward (ReLU, ones column), 1: dgrad (mask)
+__global__ void __launch_bounds__(GEMM_THREADS) upd_gemm_kernel(GemmArgs a, int* __restrict__ err) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + GEMM_STAGES * A_STAGE;
+  uint64_t* bars = (uint64_t*)(smem + GEMM_STAGES * (A_STAGE + B_STAGE));
+  uint32_t* s_tmem = (uint32_t*)(bars + 8);
+  volatile int* s_abort = (volatile int*)(s_tmem + 1);
+  __shared__ float s_w4[HP];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row0 = blockIdx.x * TM;
+  const uint32_t bar0 = smem_u32(bars);
+  auto FULL = [&](int s) { return bar0 + 8u * s; };
+  auto EMPTY = [&](int s) { return bar0 + 8u * (GEMM_STAGES + s); };
+  const uint32_t ACCF = bar0 + 8u * (2 * GEMM_STAGES);
+
+  if (tid == 0) {
+    *s_abort = 0;
+    for (int s = 0; s < GEMM_STAGES; ++s) { mbar_init(FULL(s), 128 + 1); mbar_init(EMPTY(s), 1); }
+    mbar_init(ACCF, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (EPI == 0 && a.w4) for (int i = tid; i < HP; i += GEMM_THREADS) s_w4[i] = i < a.H ? a.w4[i] : 0.f;
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+
+  if (warp < 4) {
+    // ---- A loaders: 128 rows x 8 chunks of 16 B per stage; lane -> (chunk quarter cq, row-in-group r8): the 8 lanes
+    // of one cq write 128 contiguous bytes of one core-matrix column (conflict-free), and read 64 B per row ----
+    const int r8 = lane & 7, cq = lane >> 3;
+    for (int kt = 0; kt < NKT; ++kt) {
+      const int s = kt % GEMM_STAGES, u = kt / GEMM_STAGES;
+      if (u > 0) mbar_wait(EMPTY(s), (u - 1) & 1, s_abort);
+      const uint32_t dstA = smem_u32(sA + s * A_STAGE);
+      const int nhalf = kt == NKT - 1 ? 1 : 2;          // the last K tile holds columns 192..207 only
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int j = warp * 8 + i, group = j >> 1, chalf = j & 1;
+        if (chalf < nhalf) {
+          const int row = group * 8 + r8, c = chalf * 4 + cq;
+          const int grow = row0 + row;
+          const bool ok = grow < a.R;
+          const float* src = a.A + (size_t)(ok ? grow : 0) * HP + kt * KT + c * 4;
+          cp_async16(dstA + c * (TM * 16) + group * 128 + r8 * 16, src, ok);
+        }
+      }
+      cp_async_arrive(FULL(s));
+    }
+    // ---- epilogue: thread = row (TMEM lane), 32 columns per tcgen05.ld ----
+    mbar_wait(ACCF, 0, s_abort);
+    tc_fence_after();
+    const int row = row0 + warp * 32 + lane;
+    const bool ok = row < a.R;
+    float* out = a.Out + (size_t)(ok ? row : 0) * HP;
+    const float* mrow = EPI == 1 ? a.mask + (size_t)(ok ? row : 0) * HP : nullptr;
+    const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16);
+    float head = 0.f;
+#pragma unroll 1
+    for (int c0 = 0; c0 < HP; c0 += 32) {
+      uint32_t v[32];
+      const int nc = HP - c0 >= 32 ? 32 : 16;
+      float4 mk[8];
+      if (EPI == 1) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) if (q * 4 < nc) mk[q] = *(const float4*)(mrow + c0 + q * 4);
+      }
+      if (nc == 32) tmem_ld32(tbase + c0, v); else tmem_ld16(tbase + c0, v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (q * 4 < nc) {
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int col = c0 + q * 4 + e;
+            float x = __uint_as_float(v[q * 4 + e]);
+            if (EPI == 0) {
+              x = fmaxf(x, 0.f);
+              if (a.w4) head = fmaf(x, s_w4[col], head);
+              x = col == a.H ? 1.f : tf32_rn(x);
+            } else {
+              const float m = e == 0 ? mk[q].x : e == 1 ? mk[q].y : e == 2 ? mk[q].z : mk[q].w;
+              x = (m > 0.f && col < a.H) ? tf32_rn(x) : 0.f;
+            }
+            o[e] = x;
+          }
+          if (ok) *(float4*)(out + c0 + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      }
+    }
+    if (EPI == 0 && a.w4 && ok) a.logits[row] = head + a.b4[0];
+    tc_fence_before();
+  } else if (warp == 4) {
+    // ---- MMA issue: per stage 4 (last: 2) K = 8 steps of 128 x 208 ----
+    if (lane == 0) {
+      for (int kt = 0; kt < NKT; ++kt) {
+        const int s = kt % GEMM_STAGES, u = kt / GEMM_STAGES;
+        mbar_wait(FULL(s), u & 1, s_abort);
+        tc_fence_after();
+        const uint32_t aS = smem_u32(sA + s * A_STAGE), bS = smem_u32(sB + s * B_STAGE);
+        const int nks = kt == NKT - 1 ? 2 : 4;
+        for (int ks = 0; ks < nks; ++ks) {
+          const uint64_t ad = make_desc(aS + ks * 2 * (TM * 16), TM * 16, 128);
+          const uint64_t bd = make_desc(bS + ks * 2 * (HP * 16), HP * 16, 128);
+          mma_ss_tf32(tmem, ad, bd, IDESC_K, (kt | ks) != 0);
+        }
+        tc_commit(EMPTY(s));
+      }
+      tc_commit(ACCF);
+    }
+    __syncwarp();
+  } else {
+    // ---- weight stages: one bulk copy per K tile ----
+    if (lane == 0) {
+      for (int kt = 0; kt < NKT; ++kt) {
+        const int s = kt % GEMM_STAGES, u = kt / GEMM_STAGES;
+        if (u > 0) mbar_wait(EMPTY(s), (u - 1) & 1, s_abort);
+        mbar_expect_tx(FULL(s), B_STAGE);
+        bulk_g2s(smem_u32(sB + s * B_STAGE), a.Bimg + (size_t)kt * (HP * KT), B_STAGE, FULL(s));
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (tid == 0 && *s_abort) atomicOr(err, 1);
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+  }
+}
+
+// ---- loss terms and dlogits, one CTA per episode (policies.py:150-161, ppo.py:148-168) -----------------------------
+__device__ __forceinline__ double block_sum(double v, double* s_red) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) s_red[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int i = 0; i < nw; ++i) t += s_red[i];      // same order in every thread
+  return t;
+}
+__global__ void __launch_bounds__(256) upd_loss_kernel(int M, const float* __restrict__ logits,
+                                                        const int32_t* __restrict__ actions, const float* __restrict__ advs,
+                                                        const float* __restrict__ logp_old, float eps, float ent_coeff,
+                                                        float inv_n, float* __restrict__ dl, float* __restrict__ terms) {
+  __shared__ double s_red[8];
+  __shared__ float s_max[8];
+  const int e = blockIdx.x, tid = threadIdx.x;
+  const float* l = logits + (size_t)e * M;
+  float mx = -INFINITY;
+  for (int i = tid; i < M; i += 256) mx = fmaxf(mx, l[i]);
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((tid & 31) == 0) s_max[tid >> 5] = mx;
+  __syncthreads();
+  mx = s_max[0];
+  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, s_max[i]);
+  double se = 0.0;
+  for (int i = tid; i < M; i += 256) se += (double)expf(l[i] - mx);
+  se = block_sum(se, s_red);
+  const float lse = mx + (float)log(se);
+  double pe = 0.0;                                  // sum p log p
+  for (int i = tid; i < M; i += 256) { const float lp = l[i] - lse; pe += (double)(expf(lp) * lp); }
+  pe = block_sum(pe, s_red);
+  const float ent = (float)(-pe);
+  int act = actions[e];
+  act = act < 0 ? 0 : (act >= M ? M - 1 : act);
+  const float lpa = l[act] - lse;
+  const float adv = advs[e];
+  const float ratio = expf(lpa - logp_old[e]);
+  const float clipped = fminf(fmaxf(ratio, 1.f - eps), 1.f + eps);
+  const float s1 = ratio * adv, s2 = clipped * adv;
+  // d(-min(s1, s2) / n) / d ratio: torch.min splits a tie evenly and clamp passes the gradient inside its range, so
+  // the unclipped and the tie case both give -adv / n; when the clipped branch is the smaller one the gradient is 0
+  const float g_lp = (s1 <= s2 ? -adv * inv_n : 0.f) * ratio;
+  const float g_ent = -ent_coeff * inv_n;
+  for (int i = tid; i < M; i += 256) {
+    const float lp = l[i] - lse, p = expf(lp);
+    dl[(size_t)e * M + i] = g_lp * ((i == act ? 1.f : 0.f) - p) - g_ent * p * (lp + ent);
+  }
+  if (tid == 0) {
+    terms[e * 4 + 0] = lpa;
+    terms[e * 4 + 1] = ent;
+    terms[e * 4 + 2] = -fminf(s1, s2) * inv_n;
+    terms[e * 4 + 3] = ratio;
+  }
+}
+
+// ---- dZ4 and the head's weight gradient -------------------------------------------------------------------------------
+__global__ void __launch_bounds__(THIN_THREADS) upd_dz4_kernel(int R, int H, const float* __restrict__ H4,
+                                                                const float* __restrict__ dl, const float* __restrict__ w4,
+                                                                float* __restrict__ dZ4, float* __restrict__ part_head) {
+  __shared__ float s_acc[4][HP];
+  const int cg = threadIdx.x % 52, rsub = threadIdx.x / 52;
+  float w[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) w[e] = cg * 4 + e < H ? w4[cg * 4 + e] : 0.f;
+  const int rpc = (R + gridDim.x - 1) / gridDim.x;
+  const int r_end = min(R, (int)(blockIdx.x + 1) * rpc);
+  for (int r = blockIdx.x * rpc + rsub; r < r_end; r += 4) {
+    const float4 h = *(const float4*)(H4 + (size_t)r * HP + cg * 4);
+    const float d = __ldg(dl + r);
+    const float hv[4] = {h.x, h.y, h.z, h.w};
+    float o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      acc[e] = fmaf(d, hv[e], acc[e]);                        // column H is the ones column: db4
+      o[e] = (hv[e] > 0.f && cg * 4 + e < H) ? tf32_rn(d * w[e]) : 0.f;
+    }
+    *(float4*)(dZ4 + (size_t)r * HP + cg * 4) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) s_acc[rsub][cg * 4 + e] = acc[e];
+  __syncthreads();
+  const int j = threadIdx.x;
+  part_head[(size_t)blockIdx.x * HP + j] = (s_acc[0][j] + s_acc[1][j]) + (s_acc[2][j] + s_acc[3][j]);
+}
+
+// ---- layer-0 weight gradient: dW0[o][f] = sum_r dZ1[r][o] x[r][f], db0[o] = sum_r dZ1[r][o] ----------------------------
+__global__ void __launch_bounds__(THIN_THREADS) upd_wgrad0_kernel(Net net, const float* __restrict__ states, int R,
+                                                                   const float* __restrict__ dZ1,
+                                                                   float* __restrict__ part_l0) {
+  __shared__ float s_acc[3][HP * (MAXF + 1)];
+  const int cg = threadIdx.x % 52, rsub = threadIdx.x / 52;
+  const int F = net.F;
+  float acc[4][MAXF + 1];
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+#pragma unroll
+    for (int f = 0; f <= MAXF; ++f) acc[e][f] = 0.f;
+  const int rpc = (R + gridDim.x - 1) / gridDim.x;
+  const int r_end = min(R, (int)(blockIdx.x + 1) * rpc);
+  for (int r = blockIdx.x * rpc + rsub; r < r_end; r += 4) {
+    const float4 d = *(const float4*)(dZ1 + (size_t)r * HP + cg * 4);
+    const float dv[4] = {d.x, d.y, d.z, d.w};
+    float x[MAXF + 1];
+#pragma unroll
+    for (int f = 0; f < MAXF; ++f) x[f] = f < F ? __ldg(states + (size_t)r * net.F_state + net.col[f]) : 0.f;
+    x[MAXF] = 1.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+#pragma unroll
+      for (int f = 0; f <= MAXF; ++f) acc[e][f] = fmaf(dv[e], x[f], acc[e][f]);
+  }
+  // fixed-order reduction over the 4 row lanes: lanes 1..3 park their sums, lane 0 adds them in order
+  if (rsub > 0) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+#pragma unroll
+      for (int f = 0; f <= MAXF; ++f) s_acc[rsub - 1][(cg * 4 + e) * (MAXF + 1) + f] = acc[e][f];
+  }
+  __syncthreads();
+  if (rsub == 0) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+#pragma unroll
+      for (int f = 0; f <= MAXF; ++f) {
+        const int i = (cg * 4 + e) * (MAXF + 1) + f;
+        part_l0[(size_t)blockIdx.x * HP * (MAXF + 1) + i] = ((acc[e][f] + s_acc[0][i]) + s_acc[1][i]) + s_acc[2][i];
+      }
+  }
+}
+
+// ---- wgrad of the three H x H layers: dWb_l[o][i] = sum_r dZ_{l+1}[r][o] * [h_l, 1][r][i] -------------------------------
+// K = rows: both operands are MN-major, and for tf32 the only MN-major shared-memory layout the tensor core accepts is
+// SWIZZLE_128B_BASE32B (cute::UMMA::Layout_MN_SW128_32B_Atom; a no-swizzle MN-major tf32 descriptor reads zeros):
+// blocks of 32 columns x 32 rows, row pitch 128 B, atoms of 4 rows (512 B) whose 32-byte chunks are XOR-permuted by
+// the row index (address bits 5-6 ^= bits 7-8).  LBO = distance of 32-column blocks (4096 B), SBO = distance of 4-row
+// atoms (512 B); one K = 8 MMA reads two atoms, the next K step starts 1024 B further.
+struct WgradArgs {
+  const float* dZ[3];    // dZ_{l+1}, l = 1..3
+  const float* Hin[3];   // h_l
+  float* part;           // [WG_SPLIT][3][HP][HP]
+  int R, H;
+};
+
+__device__ __forceinline__ uint64_t make_desc_mn32(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) |
+         (1ull << 61);
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS) upd_wgrad_kernel(WgradArgs a, int* __restrict__ err) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);     // the swizzle works on address bits
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + WG_STAGES * WG_A_STAGE;
+  uint64_t* bars = (uint64_t*)(smem + WG_STAGES * (WG_A_STAGE + WG_B_STAGE));
+  uint32_t* s_tmem = (uint32_t*)(bars + 8);
+  volatile int* s_abort = (volatile int*)(s_tmem + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int split = blockIdx.x, li = blockIdx.y;
+  const int nk_total = (a.R + KT - 1) / KT;
+  const int per = (nk_total + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int kt0 = split * per, kt1 = min(nk_total, kt0 + per);
+  const int nk = max(0, kt1 - kt0);
+  const uint32_t bar0 = smem_u32(bars);
+  auto FULL = [&](int s) { return bar0 + 8u * s; };
+  auto EMPTY = [&](int s) { return bar0 + 8u * (WG_STAGES + s); };
+  const uint32_t ACCF = bar0 + 8u * (2 * WG_STAGES);
+
+  if (tid == 0) {
+    *s_abort = 0;
+    for (int s = 0; s < WG_STAGES; ++s) { mbar_init(FULL(s), 128); mbar_init(EMPTY(s), 1); }
+    mbar_init(ACCF, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // column block 7 (columns 224..255) of the A operand is never loaded: zero it once
+  for (int s = 0; s < WG_STAGES; ++s)
+    for (int i = tid; i < 4096 / 16; i += GEMM_THREADS)
+      *(float4*)(sA + s * WG_A_STAGE + 7 * 4096 + i * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+
+  if (warp < 4) {
+    // ---- loaders: per operand 7 column blocks x 8 four-row atoms per stage; one warp instruction = one atom of one
+    // block: lane -> (16-byte chunk jj of the 128-byte row, row rr of the atom): full 128-byte lines from global ----
+    const int jj = lane & 7, rr = lane >> 3;
+    const float* gA = a.dZ[li];
+    const float* gB = a.Hin[li];
+    const uint32_t sw_off = (uint32_t)((((jj >> 1) ^ rr) << 5) | ((jj & 1) << 4)) + rr * 128;   // swizzled offset inside the atom
+    for (int it = 0; it < nk; ++it) {
+      const int s = it % WG_STAGES, u = it / WG_STAGES;
+      if (u > 0) mbar_wait(EMPTY(s), (u - 1) & 1, s_abort);
+      const uint32_t dA = smem_u32(sA + s * WG_A_STAGE), dB = smem_u32(sB + s * WG_B_STAGE);
+      const int krow0 = (kt0 + it) * KT;
+#pragma unroll 4
+      for (int i = 0; i < 28; ++i) {
+        int q = warp * 28 + i;                     // 0..111: operand (2) x column block (7) x atom (8)
+        const bool isB = q >= 56;
+        q -= isB ? 56 : 0;
+        const int blk = q >> 3, atom = q & 7;
+        const int col = blk * 32 + jj * 4;
+        const int grow = krow0 + atom * 4 + rr;
+        const bool ok = grow < a.R && col < HP;
+        const float* src = (isB ? gB : gA) + (size_t)(ok ? grow : 0) * HP + (ok ? col : 0);
+        cp_async16((isB ? dB : dA) + blk * 4096 + atom * 512 + sw_off, src, ok);
+      }
+      cp_async_arrive(FULL(s));
+    }
+    // ---- epilogue: two M blocks of 128 output rows o; thread = o; row-contiguous store of the partial ----
+    if (nk > 0) { mbar_wait(ACCF, 0, s_abort); tc_fence_after(); }
+    float* part = a.part + ((size_t)split * 3 + li) * HP * HP;
+#pragma unroll 1
+    for (int mb = 0; mb < 2; ++mb) {
+      const int o = mb * 128 + warp * 32 + lane;
+      const bool ok = o < a.H;
+      const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16) + mb * 256;
+#pragma unroll 1
+      for (int c0 = 0; c0 < HP; c0 += 32) {
+        uint32_t v[32];
+        const int nc = HP - c0 >= 32 ? 32 : 16;
+        if (nk > 0) {
+          if (nc == 32) tmem_ld32(tbase + c0, v); else tmem_ld16(tbase + c0, v);
+          tmem_wait_ld();
+        } else {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) v[q] = 0u;
+        }
+        if (ok) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (q * 4 < nc)
+              *(uint4*)(part + (size_t)o * HP + c0 + q * 4) = make_uint4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 4) {
+    if (lane == 0) {
+      for (int it = 0; it < nk; ++it) {
+        const int s = it % WG_STAGES, u = it / WG_STAGES;
+        mbar_wait(FULL(s), u & 1, s_abort);
+        tc_fence_after();
+        const uint32_t aS = smem_u32(sA + s * WG_A_STAGE), bS = smem_u32(sB + s * WG_B_STAGE);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t bd = make_desc_mn32(bS + ks * 1024);
+#pragma unroll
+          for (int mb = 0; mb < 2; ++mb) {
+            const uint64_t ad = make_desc_mn32(aS + mb * (4 * 4096) + ks * 1024);
+            mma_ss_tf32(tmem + mb * 256, ad, bd, IDESC_MN, (it | ks) != 0);
+          }
+        }
+        tc_commit(EMPTY(s));
+      }
+      if (nk > 0) tc_commit(ACCF);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (tid == 0 && *s_abort) atomicOr(err, 1);
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+// ---- fixed-order reduction of every partial ------------------------------------------------------------------------------
+__global__ void upd_reduce_kernel(Net net, Ws ws, int n_thin) {
+  const int H = net.H, F = net.F;
+  const int nA = 3 * H * (H + 1), nB = H + 1, nC = H * (F + 1);
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < nA) {
+    const int l = idx / (H * (H + 1)), r = idx - l * H * (H + 1);
+    const int o = r / (H + 1), i = r - o * (H + 1);
+    float s = 0.f;
+    for (int sp = 0; sp < WG_SPLIT; ++sp) s += ws.part_big[(((size_t)sp * 3 + l) * HP + o) * HP + i];
+    if (i < H) net.dW[l + 1][(size_t)o * H + i] = s; else net.db[l + 1][o] = s;
+    return;
+  }
+  idx -= nA;
+  if (idx < nB) {
+    float s = 0.f;
+    for (int c = 0; c < n_thin; ++c) s += ws.part_head[(size_t)c * HP + idx];
+    if (idx < H) net.dW[4][idx] = s; else net.db[4][0] = s;
+    return;
+  }
+  idx -= nB;
+  if (idx < nC) {
+    const int o = idx / (F + 1), f = idx - o * (F + 1);
+    float s = 0.f;
+    for (int c = 0; c < n_thin; ++c) s += ws.part_l0[((size_t)c * HP + o) * (MAXF + 1) + (f < F ? f : MAXF)];
+    if (f < F) net.dW[0][(size_t)o * F + f] = s; else net.db[0][o] = s;
+  }
+}
+
+static bool g_attr_done = false;
+static int set_attrs() {
+  if (g_attr_done) return MBO_OK;
+  MBO_CUDA(cudaFuncSetAttribute(upd_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+  MBO_CUDA(cudaFuncSetAttribute(upd_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+  MBO_CUDA(cudaFuncSetAttribute(upd_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
+  g_attr_done = true;
+  return MBO_OK;
+}
+
+}  // namespace upd
+}  // namespace mbo
+
+using namespace mbo;
+using namespace mbo::upd;
+
+extern "C" size_t mbo_ppo_workspace_bytes(int E, int M) {
+  if (E <= 0 || M <= 0) return 0;
+  return carve(E, M, nullptr, nullptr);
+}
+
+extern "C" int mbo_ppo_debug_offsets(int E, int M, size_t* off /*[12]*/) {
+  MBO_CHECK_ARG(E > 0 && M > 0 && off, "mbo_ppo_debug_offsets: bad arguments");
+  Ws w;
+  unsigned char* base = (unsigned char*)4096;     // any non-null base: only differences are reported
+  carve(E, M, base, &w);
+  for (int l = 0; l < 4; ++l) off[l] = (unsigned char*)w.Hs[l] - base;
+  for (int l = 0; l < 4; ++l) off[4 + l] = (unsigned char*)w.dZ[l] - base;
+  off[8] = (unsigned char*)w.logits - base;
+  off[9] = (unsigned char*)w.dl - base;
+  off[10] = (unsigned char*)w.terms - base;
+  off[11] = (unsigned char*)w.part_big - base;
+  return MBO_OK;
+}
+
+extern "C" int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32_t* feat_col, int H,
+                                   const float* states, const float* const* W, const float* const* b,
+                                   const int32_t* actions, const float* advs, const float* logp_old, float epsilon,
+                                   float ent_coeff, float inv_n_global, float* const* dW, float* const* db,
+                                   float* terms, void* workspace, size_t workspace_bytes, void* stream) {
+  MBO_CHECK_ARG(E > 0 && M > 0, "mbo_ppo_policy_grad: E, M must be > 0");
+  MBO_CHECK_ARG((size_t)E * M < (1u << 30), "mbo_ppo_policy_grad: too many rows");
+  MBO_CHECK_ARG(F >= 1 && F <= MAXF && F_state >= F, "mbo_ppo_policy_grad: 1 <= F <= %d policy features of F_state", MAXF);
+  MBO_CHECK_ARG(H >= 8 && H <= HP - 1, "mbo_ppo_policy_grad: hidden width must be in 8..%d", HP - 1);
+  MBO_CHECK_ARG(states && W && b && actions && advs && logp_old && dW && db && terms && workspace && feat_col,
+                "mbo_ppo_policy_grad: null pointer");
+  MBO_CHECK_ARG(workspace_bytes >= mbo_ppo_workspace_bytes(E, M), "mbo_ppo_policy_grad: workspace too small");
+  MBO_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "mbo_ppo_policy_grad: workspace must be 256-byte aligned");
+  if (set_attrs() != MBO_OK) return MBO_ERR_CUDA;
+  cudaStream_t st = (cudaStream_t)stream;
+  Net net;
+  for (int l = 0; l < 5; ++l) {
+    MBO_CHECK_ARG(W[l] && b[l] && dW[l] && db[l], "mbo_ppo_policy_grad: null layer pointer");
+    net.W[l] = W[l]; net.b[l] = b[l]; net.dW[l] = dW[l]; net.db[l] = db[l];
+  }
+  net.F = F; net.F_state = F_state; net.H = H;
+  for (int f = 0; f < MAXF; ++f) {
+    net.col[f] = f < F ? feat_col[f] : 0;
+    MBO_CHECK_ARG(net.col[f] >= 0 && net.col[f] < F_state, "mbo_ppo_policy_grad: feature column out of range");
+  }
+  Ws ws;
+  carve(E, M, (unsigned char*)workspace, &ws);
+  const int R = E * M;
+  const int tiles = (R + TM - 1) / TM;
+
+  upd_pack_kernel<<<(6 * IMG_FLOATS + 255) / 256, 256, 0, st>>>(net, ws);
+  upd_layer0_kernel<<<THIN_CTAS, THIN_THREADS, 0, st>>>(net, states, R, ws.Hs[0]);
+  for (int l = 0; l < 3; ++l) {
+    GemmArgs g{};
+    g.A = ws.Hs[l]; g.Bimg = ws.img_fwd[l]; g.Out = ws.Hs[l + 1]; g.R = R; g.H = H;
+    if (l == 2) { g.w4 = W[4]; g.b4 = b[4]; g.logits = ws.logits; }
+    upd_gemm_kernel<0><<<tiles, GEMM_THREADS, GEMM_SMEM, st>>>(g, ws.err);
+  }
+  upd_loss_kernel<<<E, 256, 0, st>>>(M, ws.logits, actions, advs, logp_old, epsilon, ent_coeff, inv_n_global, ws.dl,
+                                      ws.terms);
+  upd_dz4_kernel<<<THIN_CTAS, THIN_THREADS, 0, st>>>(R, H, ws.Hs[3], ws.dl, W[4], ws.dZ[3], ws.part_head);
+  for (int l = 2; l >= 0; --l) {      // dZ_{l+1} = (dZ_{l+2} W_{l+1}) . [h_{l+1} > 0]
+    GemmArgs g{};
+    g.A = ws.dZ[l + 1]; g.Bimg = ws.img_dgr[l]; g.Out = ws.dZ[l]; g.mask = ws.Hs[l]; g.R = R; g.H = H;
+    upd_gemm_kernel<1><<<tiles, GEMM_THREADS, GEMM_SMEM, st>>>(g, ws.err);
+  }
+  WgradArgs wa{};
+  for (int l = 0; l < 3; ++l) { wa.dZ[l] = ws.dZ[l + 1]; wa.Hin[l] = ws.Hs[l]; }
+  wa.part = ws.part_big; wa.R = R; wa.H = H;
+
+  upd_wgrad_kernel<<<dim3(WG_SPLIT, 3), GEMM_THREADS, WG_SMEM, st>>>(wa, ws.err);
+  upd_wgrad0_kernel<<<THIN_CTAS, THIN_THREADS, 0, st>>>(net, states, R, ws.dZ[0], ws.part_l0);
+  const int n_red = 3 * H * (H + 1) + (H + 1) + H * (F + 1);
+  upd_reduce_kernel<<<(n_red + 255) / 256, 256, 0, st>>>(net, ws, THIN_CTAS);
+  MBO_CUDA(cudaMemcpyAsync(terms, ws.terms, (size_t)E * 16, cudaMemcpyDeviceToDevice, st));
+  MBO_LAUNCH_CHECK();
+  return MBO_OK;
+}

@@ -295,3 +295,57 @@ def cubes_around(x, diam, cubes=None):
         cubes = torch.empty((B, k, 2, D), dtype=torch.float64, device=x.device)
     L.check(L.lib().mbo_cubes_around(B, k, D, _p(x), float(diam), _p(cubes), _stream()), "mbo_cubes_around")
     return cubes
+
+
+class PPOPolicyGrad:
+    """Workspace + call wrapper of `mbo_ppo_policy_grad` (the policy-net forward + backward of one PPO optimiser
+    step, ppo.py:129-178) for a fixed minibatch shape [E, M, F_state]."""
+    HP = 208
+
+    def __init__(self, E, M, F_state, cols, H, device):
+        self.E, self.M, self.F_state, self.cols, self.H = int(E), int(M), int(F_state), list(cols), int(H)
+        self.nbytes = int(L.lib().mbo_ppo_workspace_bytes(self.E, self.M))
+        self.ws = torch.zeros(self.nbytes // 4 + 64, dtype=torch.int32, device=device)      # zeroed once: sticky error word
+        self.terms = torch.empty((self.E, 4), dtype=torch.float32, device=device)
+        self._cols = (C.c_int32 * len(self.cols))(*self.cols)
+
+    def __call__(self, states, weights, biases, actions, advs, logp_old, epsilon, ent_coeff, n_global, dW, db):
+        """weights / biases / dW / db: lists of 5 contiguous fp32 CUDA tensors (torch layouts); the gradients of
+        loss_ppo + ent_coeff * loss_ent are written into dW / db.  Returns terms [E, 4]."""
+        _chk(states, torch.float32, "states"); _chk(actions, torch.int32, "actions")
+        _chk(advs, torch.float32, "advs"); _chk(logp_old, torch.float32, "logp_old")
+        assert tuple(states.shape) == (self.E, self.M, self.F_state), states.shape
+        assert len(weights) == len(biases) == len(dW) == len(db) == 5
+        for t in list(weights) + list(biases) + list(dW) + list(db):
+            _chk(t, torch.float32, "parameter / gradient")
+        W = (C.c_void_p * 5)(*[t.data_ptr() for t in weights])
+        Bv = (C.c_void_p * 5)(*[t.data_ptr() for t in biases])
+        gW = (C.c_void_p * 5)(*[t.data_ptr() for t in dW])
+        gB = (C.c_void_p * 5)(*[t.data_ptr() for t in db])
+        L.check(L.lib().mbo_ppo_policy_grad(self.E, self.M, self.F_state, len(self.cols), self._cols, self.H, _p(states),
+                                            W, Bv, _p(actions), _p(advs), _p(logp_old), float(epsilon), float(ent_coeff),
+                                            1.0 / float(n_global), gW, gB, _p(self.terms), _p(self.ws), self.nbytes,
+                                            _stream()), "mbo_ppo_policy_grad")
+        return self.terms
+
+    def check(self):
+        """Synchronises; raises if a pipeline wait of the update kernels timed out."""
+        flag = int(self.ws[0].item())
+        if flag:
+            self.ws[0] = 0
+            raise L.MboError("ppo_update kernels aborted: an mbarrier wait timed out (pipeline bug)")
+
+    def debug_views(self):
+        """h1..h4, dZ1..dZ4 [R, 208], logits, dlogits [R] as views of the workspace (tests / probes)."""
+        off = (C.c_size_t * 12)()
+        L.check(L.lib().mbo_ppo_debug_offsets(self.E, self.M, off), "mbo_ppo_debug_offsets")
+        R = self.E * self.M
+        f = self.ws.view(torch.float32)
+        v = {}
+        for i, name in enumerate(["h1", "h2", "h3", "h4", "dz1", "dz2", "dz3", "dz4"]):
+            o = off[i] // 4
+            v[name] = f[o:o + R * self.HP].view(R, self.HP)
+        v["logits"] = f[off[8] // 4:off[8] // 4 + R]
+        v["dlogits"] = f[off[9] // 4:off[9] // 4 + R]
+        v["part_big"] = f[off[11] // 4:off[11] // 4 + 49 * 3 * self.HP * self.HP].view(49, 3, self.HP, self.HP)
+        return v
