@@ -9,6 +9,11 @@ every minibatch are sharded across ranks and the policy update all-reduces
     ppo.py:141-144 is the global one,
 
 and every rank applies the identical Adam step (weights stay replicated, no broadcast).
+
+Update backends (`params["update_backend"]`): "native" (default when the policy net is the shipped
+F -> H -> H -> H -> H -> 1 ReLU shape) computes the policy-net forward + backward of every optimiser step
+with the hand-written tcgen05 TF32 kernels behind `mbo_ppo_policy_grad` (csrc/ppo_update.cu); the small
+value net (2 inputs x minibatch rows) stays on torch autograd.  "autograd" is the all-torch fp32 path.
 """
 import collections
 import copy
@@ -25,6 +30,7 @@ import torch.distributed as dist
 import torch.optim
 
 from .. import gym_compat as gym
+from .. import ops
 from .batchrecorder import BatchRecorder
 
 
@@ -120,6 +126,14 @@ class PPO:
         self.use_update_graph = self.world == 1 and os.environ.get("MBO_NO_GRAPHS") is None and \
             self.params.get("update_graph", True)
         self._upd = None        # (static inputs, CUDAGraph, static outputs) of one captured optimiser step
+        backend = self.params.get("update_backend", "native")
+        if backend not in ("native", "autograd"):
+            raise ValueError("update_backend must be 'native' or 'autograd'")
+        if backend == "native" and not self.native_update_supported(self.pi):
+            backend = "autograd"          # e.g. the 2 x 20 GP-sample policy: too small for the tensor-core path
+        self.update_backend = backend
+        self._pg = None         # ops.PPOPolicyGrad for the current minibatch shape
+        self._pg_grads = None   # persistent gradient buffers of the policy net (written by the kernels)
 
         self.stats = dict()
         self.stats["n_timesteps"] = 0
@@ -160,8 +174,56 @@ class PPO:
         if not self.verbose:
             print(s)
 
+    @staticmethod
+    def native_update_supported(pi):
+        a = pi.policy_net.arch_spec
+        return (pi.activation == "relu" and len(a) == 4 and len(set(a)) == 1 and 8 <= a[0] <= 207
+                and 1 <= pi.N_features_policy <= 8)
+
+    def _update_step_native(self, mb):
+        """ppo.py:129-178 with the policy net's forward + backward on the hand-written kernels
+        (mbo_ppo_policy_grad); value net (2 inputs per minibatch row) on torch autograd."""
+        states, actions, tdlamrets = mb["states"], mb["actions"], mb["tdlamrets"]
+        advs = mb["advs"] if self.params["loss_type"] == "GAElam" else mb["tdlamrets"]
+        E, M, Fs = states.shape
+        n_global = E * self.world
+        if self.params["normalize_advs"]:
+            advs = normalize_advantages(advs, self.world)
+        pi = self.pi
+        with torch.no_grad():
+            _, logprobs_old, _ = self.old_pi.predict_vals_logps_ents(states=states, actions=actions)
+        fcs = list(pi.policy_net.fc)
+        if self._pg is None or (self._pg.E, self._pg.M, self._pg.F_state) != (E, M, Fs):
+            self._pg = ops.PPOPolicyGrad(E, M, Fs, pi.policy_columns(), pi.policy_net.arch_spec[0], states.device)
+        if self._pg_grads is None:
+            self._pg_grads = ([torch.zeros_like(l.weight) for l in fcs], [torch.zeros_like(l.bias) for l in fcs])
+        dW, db = self._pg_grads
+        self.optimizer.zero_grad(set_to_none=True)
+        terms = self._pg(states.contiguous(), [l.weight.data for l in fcs], [l.bias.data for l in fcs],
+                         actions.to(torch.int32).contiguous(), advs.to(torch.float32).contiguous(),
+                         logprobs_old.to(torch.float32).contiguous(), self.params["epsilon"], self.params["ent_coeff"],
+                         n_global, dW, db)
+        for l, gw, gb in zip(fcs, dW, db):
+            l.weight.grad, l.bias.grad = gw, gb
+        l_ppo = terms[:, 2].sum()
+        l_ent = -terms[:, 1].sum() / n_global
+        if pi.use_value_network:
+            tT = torch.stack([states[:, 0, pi.t_idx], states[:, 0, pi.T_idx]], dim=1)
+            vpreds = pi.value_net.forward(tT).squeeze(1)
+            l_val = torch.sum((vpreds - tdlamrets) ** 2) / n_global
+            (self.params["value_coeff"] * l_val).backward()
+            l_val = l_val.detach()
+        else:
+            l_val = torch.sum(tdlamrets ** 2) / n_global       # the reference's value head is the constant 0
+        allreduce_gradients(list(self.pi.parameters()), self.world)
+        self.optimizer.step()
+        loss = l_ppo + self.params["value_coeff"] * l_val + self.params["ent_coeff"] * l_ent
+        return torch.stack([l_ppo, l_val, l_ent, loss]).detach()
+
     def _update_step(self, mb):
         """one optimiser step on the (local shard of a) minibatch `mb` (dict of device tensors), ppo.py:129-178"""
+        if self.update_backend == "native":
+            return self._update_step_native(mb)
         states, actions, tdlamrets = mb["states"], mb["actions"], mb["tdlamrets"]
         advs = mb["advs"] if self.params["loss_type"] == "GAElam" else mb["tdlamrets"]
         n_global = states.shape[0] * self.world
@@ -232,6 +294,8 @@ class PPO:
             avg = (sums / n_minibatches).tolist()
             self.iter_log_str += "   loss_ppo = {: .4g}, loss_value = {: .4g}, loss_ent = {: .4g}, loss = {: .4g}\n".format(*avg)
         torch.cuda.synchronize(self.device)
+        if self._pg is not None:
+            self._pg.check()              # sticky error word of the update kernels (bounded pipeline waits)
         t_optim = time.time() - now
         self.iter_log_str += "  Took {:.2f}s".format(t_optim)
         return t_optim

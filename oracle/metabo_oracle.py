@@ -274,6 +274,42 @@ def ppo_loss(pw, pw_old, states, actions, advs, tdlamrets, epsilon, value_coeff,
                 loss_ppo=float(loss_ppo), loss_value=float(loss_value), loss_ent=float(loss_ent))
 
 
+def ppo_policy_grads(layers, states, actions, advs, logp_old, epsilon, ent_coeff, n_global, masks=None,
+                     dtype=torch.float64):
+    """Gradient of loss_ppo + ent_coeff * loss_ent (ppo.py:148-168, both divided by the minibatch size n_global)
+    w.r.t. the policy net's (W, b) by torch-CPU autograd, with Categorical(logits) restated as in
+    policies.py:150-161.  states [E, M, F] (policy columns only), layers = [(W, b)] * 5 in torch layout.
+    `masks` (optional, one bool [E*M, H] array per hidden layer) replaces the ReLU decisions: the backward of a
+    reduced-precision forward is only comparable element by element under that forward's own decisions (a
+    pre-activation within rounding error of 0 flips its ReLU and changes dZ by its full value).
+    Returns dict(dW, db, logits, logp, entropy, ratio, loss_ppo, loss_ent, dlogits, hs)."""
+    Ws = [torch.as_tensor(np.asarray(w), dtype=dtype).clone().requires_grad_() for w, _ in layers]
+    bs = [torch.as_tensor(np.asarray(b), dtype=dtype).clone().requires_grad_() for _, b in layers]
+    x = torch.as_tensor(np.asarray(states), dtype=dtype)
+    E, M, F = x.shape
+    h = x.reshape(E * M, F)
+    hs = []
+    for l in range(len(Ws) - 1):
+        z = h @ Ws[l].t() + bs[l]
+        h = torch.relu(z) if masks is None else z * torch.as_tensor(np.asarray(masks[l]), dtype=dtype)
+        hs.append(h)
+    logits = (h @ Ws[-1].t() + bs[-1]).reshape(E, M)
+    logits.retain_grad()
+    a = torch.as_tensor(np.asarray(actions), dtype=torch.int64)
+    norm = logits - torch.logsumexp(logits, dim=-1, keepdim=True)
+    logp = norm.gather(-1, a[:, None]).squeeze(-1)
+    ent = -(norm * torch.exp(norm)).sum(-1)
+    adv = torch.as_tensor(np.asarray(advs), dtype=dtype)
+    ratio = torch.exp(logp - torch.as_tensor(np.asarray(logp_old), dtype=dtype))
+    clipped = ratio.clamp(1 - epsilon, 1 + epsilon)
+    loss_ppo = -torch.sum(torch.min(ratio * adv, clipped * adv)) / n_global
+    loss_ent = -torch.sum(ent) / n_global
+    (loss_ppo + ent_coeff * loss_ent).backward()
+    return dict(dW=[w.grad for w in Ws], db=[b.grad for b in bs], logits=logits.detach(), logp=logp.detach(),
+                entropy=ent.detach(), ratio=ratio.detach(), loss_ppo=loss_ppo.item(), loss_ent=loss_ent.item(),
+                dlogits=logits.grad, hs=[t.detach() for t in hs])
+
+
 # ----------------------------------------------------------------------------------------------
 # objective functions needed for full-episode checks (objectives.py:26-93, 165-235)
 # ----------------------------------------------------------------------------------------------

@@ -1,0 +1,186 @@
+"""GPU parity tests of the hand-written PPO policy-gradient kernels (mbo_ppo_policy_grad)
+against the oracle's autograd restatement of ppo.py:148-168 / policies.py:150-161.
+
+Tolerances.  The kernels compute in TF32 (11-bit significand, fp32 accumulation): forward activations and
+logits within 2e-3 of max|.| (north-star bar for logits: 1e-3 relative on the shipped policies, checked
+below on golden states).  Gradients are compared twice: (a) element-wise, tolerance 3e-3 of max|grad| per
+tensor, against an fp64 backward that uses the KERNEL'S OWN ReLU decisions (a pre-activation within rounding
+error of zero flips its ReLU under any reduced-precision forward and changes dZ by its full value -- torch's
+own TF32 autograd deviates from fp32 autograd by the same few percent); (b) against plain fp64 autograd by
+cosine similarity of the whole gradient (> 0.995)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import metabo_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a = torch.as_tensor(a).double().cpu()
+    b = torch.as_tensor(b).double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-300))
+
+
+def _run_case(E, M, F_state, cols, H, layers, states, actions, advs, logp_old, eps=0.15, entc=0.01, n_global=None):
+    from metabo_b200 import ops
+    dev = torch.device("cuda:0")
+    n_global = n_global or E
+    pg = ops.PPOPolicyGrad(E, M, F_state, cols, H, dev)
+    Wd = [torch.as_tensor(w, dtype=torch.float32, device=dev).contiguous() for w, _ in layers]
+    bd = [torch.as_tensor(b, dtype=torch.float32, device=dev).contiguous() for _, b in layers]
+    dW = [torch.full_like(w, 7.0) for w in Wd]        # outputs are overwritten, not accumulated
+    db = [torch.full_like(b, 7.0) for b in bd]
+    args = (torch.as_tensor(states, dtype=torch.float32, device=dev).contiguous(), Wd, bd,
+            torch.as_tensor(actions, dtype=torch.int32, device=dev), torch.as_tensor(advs, dtype=torch.float32, device=dev),
+            torch.as_tensor(logp_old, dtype=torch.float32, device=dev), eps, entc, n_global)
+    terms = pg(*args, dW, db).clone()
+    torch.cuda.synchronize()
+    pg.check()
+    v = {k: t.clone() for k, t in pg.debug_views().items() if k != "part_big"}
+    dW2 = [torch.zeros_like(w) for w in Wd]
+    db2 = [torch.zeros_like(b) for b in bd]
+    pg(*args, dW2, db2)
+    torch.cuda.synchronize()
+    assert all(torch.equal(a, b) for a, b in zip(dW + db, dW2 + db2)), "run-to-run difference (split-K must be deterministic)"
+    return terms.cpu(), v, [g.cpu() for g in dW], [g.cpu() for g in db]
+
+
+def _check_against_oracle(E, M, cols, H, layers, states, actions, advs, logp_old, terms, v, dW, db, eps=0.15, entc=0.01,
+                          n_global=None, fwd_tol=2e-3):
+    n_global = n_global or E
+    pol_states = np.asarray(states)[:, :, cols]
+    ref = O.ppo_policy_grads(layers, pol_states, actions, advs, logp_old, eps, entc, n_global)
+    # forward
+    for l in range(4):
+        h = v["h%d" % (l + 1)].cpu()
+        assert _rel(h[:, :H], ref["hs"][l]) <= fwd_tol, ("h", l + 1)
+        assert bool((h[:, H] == 1).all()) and bool((h[:, H + 1:] == 0).all())
+    assert _rel(v["logits"].cpu(), ref["logits"].reshape(-1)) <= fwd_tol
+    assert _rel(terms[:, 0], ref["logp"]) <= 1e-3 and _rel(terms[:, 1], ref["entropy"]) <= 1e-4
+    assert _rel(terms[:, 3], ref["ratio"]) <= 2e-3
+    assert abs(float(terms[:, 2].sum()) - ref["loss_ppo"]) <= 2e-3 * max(1.0, abs(ref["loss_ppo"]))
+    assert _rel(v["dlogits"].cpu(), ref["dlogits"].reshape(-1)) <= 2e-3
+    # backward under the kernel's own ReLU decisions: element-wise
+    masks = [(v["h%d" % (l + 1)][:, :H] > 0).cpu().numpy() for l in range(4)]
+    own = O.ppo_policy_grads(layers, pol_states, actions, advs, logp_old, eps, entc, n_global, masks=masks)
+    for l in range(5):
+        assert _rel(dW[l], own["dW"][l]) <= 3e-3, ("dW", l, _rel(dW[l], own["dW"][l]))
+        scale = float(own["db"][l].abs().max())
+        if l < 4:           # db4 = sum of dlogits = 0 analytically: only rounding noise is left
+            assert _rel(db[l], own["db"][l]) <= 3e-3, ("db", l)
+        else:
+            assert float((db[l].double() - own["db"][l]).abs().max()) <= 1e-4 * float(ref["dlogits"].abs().sum()) + 1e-12
+    # against the exact autograd gradient: direction
+    flat = lambda gs: torch.cat([torch.as_tensor(g).double().reshape(-1) for g in gs])
+    cos = torch.nn.functional.cosine_similarity(flat(dW + db[:4]), flat(ref["dW"] + ref["db"][:4]), dim=0)
+    assert float(cos) > 0.995, float(cos)
+    flips = [int((torch.as_tensor(masks[l]) != (ref["hs"][l] > 0)).sum()) for l in range(4)]
+    return flips, float(cos)
+
+
+def _random_case(seed, E, M, F_state, cols, H):
+    rng = np.random.RandomState(seed)
+    F = len(cols)
+    dims = [F, H, H, H, H, 1]
+    layers = [(rng.normal(0, 0.08, (dims[i + 1], dims[i])).astype(np.float32), rng.normal(0, 0.05, dims[i + 1]).astype(np.float32))
+              for i in range(5)]
+    states = rng.randn(E, M, F_state).astype(np.float32)
+    actions = rng.randint(0, M, E)
+    advs = rng.randn(E).astype(np.float32)
+    with torch.no_grad():
+        lp0 = O.ppo_policy_grads(layers, states[:, :, cols], actions, advs, np.zeros(E), 0.15, 0.01, E)["logp"].numpy()
+    logp_old = (lp0 + 0.2 * rng.randn(E)).astype(np.float32)       # some ratios outside the clip range, either side
+    return layers, states, actions, advs, logp_old
+
+
+@pytest.mark.parametrize("E,M,F_state,cols,H", [
+    (7, 301, 6, [0, 1, 2, 3, 4, 5], 200),      # ragged row count (2107 = 16 * 128 + 59), the shipped width
+    (3, 50, 6, [0, 1, 2, 3], 64),              # masked features (exclude_t / exclude_T, policies.py:109-114), narrow net
+    (1, 1, 7, [0, 1, 2, 3, 4, 5, 6], 200),     # a single candidate: softmax over one logit, dlogits = 0
+    (16, 966, 6, [0, 1, 2, 3, 4, 5], 200),     # Branin minibatch rows (16 x 966)
+])
+def test_policy_grad_kernels_against_oracle(E, M, F_state, cols, H):
+    layers, states, actions, advs, logp_old = _random_case(E * 1000 + M, E, M, F_state, cols, H)
+    terms, v, dW, db = _run_case(E, M, F_state, cols, H, layers, states, actions, advs, logp_old)
+    if M == 1:
+        assert all(float(g.abs().max()) == 0.0 for g in dW[:4])      # one candidate: p = 1, every gradient vanishes
+        assert float(terms[0, 0]) == 0.0 and float(terms[0, 1]) == 0.0
+        return
+    _check_against_oracle(E, M, cols, H, layers, states, actions, advs, logp_old, terms, v, dW, db)
+
+
+def test_policy_grad_on_golden_states_with_shipped_weights(golden_dir):
+    """Six states of the reference's own Branin episode under the shipped weights_1635: the forward logits of the
+    update kernels against the logits the reference NeuralAF produced (golden), gradients against the oracle."""
+    pw = O.PolicyWeights.from_npz(os.path.join(golden_dir, "weights_bra_1635.npz"))
+    layers = [(w.numpy(), b.numpy()) for w, b in pw.layers("policy_net")]
+    ep = np.load(os.path.join(golden_dir, "episode_bra.npz"), allow_pickle=True)
+    ts = ["t00", "t01", "t02", "t07", "t15", "t29"]
+    states = np.stack([ep[t + "_state"] for t in ts]).astype(np.float32)
+    gold_logits = np.stack([ep[t + "_logits"] for t in ts])
+    E, M, F = states.shape
+    rng = np.random.RandomState(3)
+    actions = np.array([int(ep[t + "_action"]) for t in ts])
+    actions[::2] = rng.randint(0, M, len(actions[::2]))
+    advs = rng.randn(E).astype(np.float32)
+    lp0 = O.ppo_policy_grads(layers, states, actions, advs, np.zeros(E), 0.15, 0.01, E)["logp"].numpy()
+    logp_old = (lp0 + 0.1 * rng.randn(E)).astype(np.float32)
+    cols = list(range(F))
+    terms, v, dW, db = _run_case(E, M, F, cols, 200, layers, states, actions, advs, logp_old, n_global=2 * E)
+    got = v["logits"].cpu().numpy().reshape(E, M)
+    assert np.max(np.abs(got - gold_logits)) <= 1e-3 * np.max(np.abs(gold_logits))      # north-star logits bar
+    _check_against_oracle(E, M, cols, 200, layers, states, actions, advs, logp_old, terms, v, dW, db, n_global=2 * E,
+                          fwd_tol=1e-3)
+
+
+def test_policy_grad_argument_errors():
+    from metabo_b200 import ops, _lib as L
+    dev = torch.device("cuda:0")
+    with pytest.raises(L.MboError):
+        pg = ops.PPOPolicyGrad(2, 10, 6, list(range(6)), 300, dev)         # hidden width above 207
+        z = torch.zeros(2, 10, 6, device=dev)
+        W = [torch.zeros(1, device=dev)] * 5
+        pg(z, W, W, torch.zeros(2, dtype=torch.int32, device=dev), torch.zeros(2, device=dev), torch.zeros(2, device=dev),
+           0.1, 0.0, 2, W, W)
+
+
+def test_ppo_native_update_follows_autograd_update(tmp_path):
+    """One PPO iteration (rollout + 2 epochs of minibatch updates) with the native policy-gradient kernels against
+    the all-torch fp32 autograd backend from the same seeds: same rollout (bit-identical policies at the start), the
+    logged losses agree and the parameter update points the same way."""
+    from metabo_b200 import gym_compat as gym
+    from metabo_b200.policies.policies import NeuralAF
+    from metabo_b200.ppo.ppo import PPO
+    from test_dropin_gpu import BRA_SPEC
+    spec = dict(BRA_SPEC, T=5, N_MS=100, N_LS=50, k=3, reward_transformation="neg_log10", env_id="MetaBO-NATIVE-v0",
+                f_opts={"bound_translation": 0.1, "bound_scaling": 0.1, "M": 50})
+    gym.register(id=spec["env_id"], entry_point="metabo.environment.metabo_gym:MetaBO", max_episode_steps=5, kwargs=spec)
+
+    def run(backend, name):
+        params = {"batch_size": 80, "max_steps": 80, "minibatch_size": 20, "n_epochs": 2, "lr": 1e-4, "epsilon": 0.15,
+                  "value_coeff": 1.0, "ent_coeff": 0.01, "gamma": 0.98, "lambda": 0.98, "loss_type": "GAElam",
+                  "normalize_advs": True, "n_workers": 4, "env_id": spec["env_id"], "seed": 0, "env_seeds": [0, 1, 2, 3],
+                  "update_backend": backend,
+                  "policy_options": {"activations": "relu", "arch_spec": [200] * 4, "use_value_network": True, "t_idx": -2,
+                                     "T_idx": -1, "arch_spec_value": [200] * 4}}
+        ppo = PPO(policy_fn=lambda o, a, d: NeuralAF(o, a, d, options=params["policy_options"]), params=params,
+                  logpath=str(tmp_path / name), save_interval=10, verbose=True)
+        w0 = torch.cat([p.detach().reshape(-1).clone() for p in ppo.pi.parameters()])
+        ppo.train()
+        w1 = torch.cat([p.detach().reshape(-1) for p in ppo.pi.parameters()])
+        losses = [[float(x.split("=")[1]) for x in line.split(",")] for line in ppo.iter_log_str.splitlines() if "loss_ppo" in line]
+        return ppo, w0, w1, np.array(losses)
+
+    pa, w0a, w1a, la = run("autograd", "autograd")
+    pn, w0n, w1n, ln = run("native", "native")
+    assert pn.update_backend == "native" and pn._pg is not None and pa._pg is None
+    assert torch.equal(w0a, w0n)
+    assert la.shape == ln.shape == (2, 4)
+    np.testing.assert_allclose(ln, la, rtol=2e-2, atol=2e-4)
+    da, dn = (w1a - w0a).double(), (w1n - w0n).double()
+    cos = float(torch.nn.functional.cosine_similarity(da, dn, dim=0))
+    assert cos > 0.9, cos
