@@ -34,11 +34,14 @@ namespace upd {
 
 constexpr int HP = 208;             // padded width: UMMA N, row pitch of H / dZ (floats)
 constexpr int TM = 128;             // rows per output tile (UMMA M)
-constexpr int KT = 32;              // K floats per pipeline stage (forward / dgrad), K rows per stage (wgrad)
+constexpr int KT = 32;              // K floats per pipeline stage (dgrad), K rows per stage (wgrad)
 constexpr int NKT = 7;              // ceil(208 / 32)
-constexpr int A_STAGE = TM * KT * 4;          // 16 384
+constexpr int KT3 = 16;             // forward (3xTF32: hi and lo parts of both operands share a stage)
+constexpr int NKT3 = 13;            // 208 / 16
+constexpr int A_STAGE = TM * KT * 4;          // 16 384 (dgrad: 32 K values; forward: 16 K values x {hi, lo})
 constexpr int B_STAGE = HP * KT * 4;          // 26 624
-constexpr int IMG_FLOATS = NKT * HP * KT;     // 46 592 floats per weight image
+constexpr int IMG_FLOATS = NKT * HP * KT;     // 46 592 floats per weight image (forward images use 43 264 of them)
+constexpr int STG_PITCH = 36;                 // floats per row of the epilogue's per-warp staging tile (32 + 4: conflict-free)
 constexpr int GEMM_STAGES = 2;
 constexpr int GEMM_THREADS = 192;   // warps 0-3: A loaders then epilogue; warp 4: MMA issue; warp 5: weight stages
 constexpr int GEMM_SMEM = GEMM_STAGES * (A_STAGE + B_STAGE) + 256;
@@ -142,9 +145,11 @@ struct Net {
 
 struct Ws {          // workspace carve-up (device pointers)
   int* err;
-  float* img_fwd[3];
-  float* img_dgr[3];
-  float* Hs[4];      // h1..h4
+  float* img_fwd[3];  // hi parts of [W | b], KT3 stages
+  float* img_fwl[3];  // lo parts
+  float* img_dgr[3];  // W^T, KT stages
+  float* Hs[4];      // h1..h4 (tf32-rounded "hi" parts)
+  float* Hl[3];      // lo parts of h1..h3 (3xTF32 forward)
   float* dZ[4];      // dZ1..dZ4
   float* logits;
   float* dl;
@@ -163,8 +168,10 @@ static size_t carve(int E, int M, unsigned char* base, Ws* w) {
   Ws t;
   t.err = (int*)take(256);
   for (int l = 0; l < 3; ++l) t.img_fwd[l] = (float*)take((size_t)IMG_FLOATS * 4);
+  for (int l = 0; l < 3; ++l) t.img_fwl[l] = (float*)take((size_t)IMG_FLOATS * 4);
   for (int l = 0; l < 3; ++l) t.img_dgr[l] = (float*)take((size_t)IMG_FLOATS * 4);
   for (int l = 0; l < 4; ++l) t.Hs[l] = (float*)take(Rp * HP * 4);
+  for (int l = 0; l < 3; ++l) t.Hl[l] = (float*)take(Rp * HP * 4);
   for (int l = 0; l < 4; ++l) t.dZ[l] = (float*)take(Rp * HP * 4);
   t.logits = (float*)take(Rp * 4);
   t.dl = (float*)take(Rp * 4);
@@ -177,30 +184,36 @@ static size_t carve(int E, int M, unsigned char* base, Ws* w) {
 }
 
 // ---- weight images -----------------------------------------------------------------------------------------------
-// K-major canonical, one 26 624-byte stage per 32 K values: [kt][16-byte K chunk c (8)][n (208)][4 floats]
+// K-major canonical, one stage per KT (dgrad) / KT3 (forward) K values: [kt][16-byte K chunk c][n (208)][4 floats].
+// Forward: [W | b] split into tf32 hi and lo parts (3xTF32: hi*hi + lo*hi + hi*lo, fp32-level logits); dgrad: W^T.
 __global__ void upd_pack_kernel(Net net, Ws ws) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= 6 * IMG_FLOATS) return;
   const int img = idx / IMG_FLOATS, o = idx - img * IMG_FLOATS;
   const int l = img >> 1, dgr = img & 1;            // layer l + 1
-  const int kt = o / (HP * KT), r = o - kt * (HP * KT);
+  const int kt_len = dgr ? KT : KT3;
+  const int kt = o / (HP * kt_len), r = o - kt * (HP * kt_len);
   const int c = r / (HP * 4), r2 = r - c * (HP * 4);
   const int n = r2 >> 2, e = r2 & 3;
-  const int k = kt * KT + c * 4 + e;
+  const int k = kt * kt_len + c * 4 + e;
   const int H = net.H;
   const float* W = net.W[l + 1];
   float v = 0.f;
   if (!dgr) {
+    if (k >= HP) return;
     if (n < H) v = k < H ? W[(size_t)n * H + k] : (k == H ? net.b[l + 1][n] : 0.f);     // [W | b]
+    const float hi = tf32_rn(v);
+    ws.img_fwd[l][o] = hi;
+    ws.img_fwl[l][o] = tf32_rn(v - hi);
   } else {
     if (n < H && k < H) v = W[(size_t)k * H + n];                                        // W^T: N = in, K = out
+    ws.img_dgr[l][o] = tf32_rn(v);
   }
-  (dgr ? ws.img_dgr[l] : ws.img_fwd[l])[o] = tf32_rn(v);
 }
 
 // ---- layer 0 on CUDA cores ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(THIN_THREADS) upd_layer0_kernel(Net net, const float* __restrict__ states, int R,
-                                                                   float* __restrict__ H1) {
+                                                                   float* __restrict__ H1, float* __restrict__ H1lo) {
   const int cg = threadIdx.x % 52, rsub = threadIdx.x / 52;
   const int F = net.F, H = net.H;
   float w[4][MAXF], bias[4];
@@ -217,7 +230,7 @@ __global__ void __launch_bounds__(THIN_THREADS) upd_layer0_kernel(Net net, const
     float x[MAXF];
 #pragma unroll
     for (int f = 0; f < MAXF; ++f) x[f] = f < F ? __ldg(states + (size_t)r * net.F_state + net.col[f]) : 0.f;
-    float o[4];
+    float o[4], ol[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       // torch's Linear on the CPU accumulates the dot product first and adds the bias last
@@ -227,25 +240,38 @@ __global__ void __launch_bounds__(THIN_THREADS) upd_layer0_kernel(Net net, const
       const int j = cg * 4 + e;
       acc = fmaxf(acc + bias[e], 0.f);
       o[e] = j < H ? tf32_rn(acc) : (j == H ? 1.f : 0.f);
+      ol[e] = j < H ? tf32_rn(acc - o[e]) : 0.f;
     }
     *(float4*)(H1 + (size_t)r * HP + cg * 4) = make_float4(o[0], o[1], o[2], o[3]);
+    *(float4*)(H1lo + (size_t)r * HP + cg * 4) = make_float4(ol[0], ol[1], ol[2], ol[3]);
   }
 }
 
 // ---- forward / dgrad GEMM -----------------------------------------------------------------------------------------
 struct GemmArgs {
-  const float* A;        // [R, HP] rows of this GEMM (h_l for forward, dZ_{l+1} for dgrad)
-  const float* Bimg;     // weight image
-  float* Out;            // [R, HP]
-  const float* mask;     // dgrad: h_l (ReLU mask), nullptr otherwise
+  const float* A;        // [R, HP] rows of this GEMM (h_l hi part for forward, dZ_{l+1} for dgrad)
+  const float* Alo;      // forward: lo part of h_l
+  const float* Bimg;     // weight image (forward: hi parts)
+  const float* Bimg_lo;  // forward: lo parts
+  float* Out;            // [R, HP] (forward: hi part of h_{l+1})
+  float* OutLo;          // forward: lo part of h_{l+1}, or nullptr (h4 feeds only the head and the wgrad)
+  const float* mask;     // dgrad: h_l (ReLU mask)
   const float* w4;       // forward of the last hidden layer: head weights [H], else nullptr
   const float* b4;
   float* logits;         // [R]
   int R, H;
 };
 
-template <int EPI>   // 0: forward (ReLU, ones column), 1: dgrad (mask)
+// EPI 0: forward, 3xTF32 (stage = 16 K values x {hi, lo} of both operands, 3 MMAs per K = 8 step), epilogue ReLU +
+//        hi / lo split + ones column (+ head logit from the unrounded fp32 activations).
+// EPI 1: dgrad, single TF32 (stage = 32 K values), epilogue multiplies by the ReLU mask of h_l.
+// The epilogue moves every 32-column chunk through a per-warp staging tile in shared memory (the pipeline stages are
+// idle by then) so that global memory sees whole 128-byte lines: thread = row from TMEM, lane = 16-byte chunk towards HBM.
+template <int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS) upd_gemm_kernel(GemmArgs a, int* __restrict__ err) {
+  constexpr bool X3 = EPI == 0;
+  constexpr int NKT_ = X3 ? NKT3 : NKT;
+  constexpr int KT_ = X3 ? KT3 : KT;
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* sA = smem;
   unsigned char* sB = smem + GEMM_STAGES * A_STAGE;
@@ -277,84 +303,137 @@ __global__ void __launch_bounds__(GEMM_THREADS) upd_gemm_kernel(GemmArgs a, int*
   const uint32_t tmem = *s_tmem;
 
   if (warp < 4) {
-    // ---- A loaders: 128 rows x 8 chunks of 16 B per stage; lane -> (chunk quarter cq, row-in-group r8): the 8 lanes
-    // of one cq write 128 contiguous bytes of one core-matrix column (conflict-free), and read 64 B per row ----
+    // ---- A loaders: lane -> (16-byte chunk quarter cq, row-in-group r8): the 8 lanes of one cq write 128 contiguous
+    // bytes of one core-matrix column (conflict-free) and read 64 B per row ----
     const int r8 = lane & 7, cq = lane >> 3;
-    for (int kt = 0; kt < NKT; ++kt) {
+    for (int kt = 0; kt < NKT_; ++kt) {
       const int s = kt % GEMM_STAGES, u = kt / GEMM_STAGES;
       if (u > 0) mbar_wait(EMPTY(s), (u - 1) & 1, s_abort);
       const uint32_t dstA = smem_u32(sA + s * A_STAGE);
-      const int nhalf = kt == NKT - 1 ? 1 : 2;          // the last K tile holds columns 192..207 only
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int j = warp * 8 + i, group = j >> 1, chalf = j & 1;
-        if (chalf < nhalf) {
-          const int row = group * 8 + r8, c = chalf * 4 + cq;
-          const int grow = row0 + row;
+        const int j = warp * 8 + i;
+        if (X3) {
+          const int arr = j >> 4, group = j & 15;          // hi rows, then lo rows; 4 chunks = the whole K tile
+          const int grow = row0 + group * 8 + r8;
           const bool ok = grow < a.R;
-          const float* src = a.A + (size_t)(ok ? grow : 0) * HP + kt * KT + c * 4;
-          cp_async16(dstA + c * (TM * 16) + group * 128 + r8 * 16, src, ok);
+          const float* src = (arr ? a.Alo : a.A) + (size_t)(ok ? grow : 0) * HP + kt * KT_ + cq * 4;
+          cp_async16(dstA + arr * (TM * KT3 * 4) + cq * (TM * 16) + group * 128 + r8 * 16, src, ok);
+        } else {
+          const int group = j >> 1, chalf = j & 1;
+          if (kt < NKT_ - 1 || chalf == 0) {                 // the last K tile holds columns 192..207 only
+            const int c = chalf * 4 + cq;
+            const int grow = row0 + group * 8 + r8;
+            const bool ok = grow < a.R;
+            const float* src = a.A + (size_t)(ok ? grow : 0) * HP + kt * KT_ + c * 4;
+            cp_async16(dstA + c * (TM * 16) + group * 128 + r8 * 16, src, ok);
+          }
         }
       }
       cp_async_arrive(FULL(s));
     }
-    // ---- epilogue: thread = row (TMEM lane), 32 columns per tcgen05.ld ----
+    // ---- epilogue ----
     mbar_wait(ACCF, 0, s_abort);
     tc_fence_after();
-    const int row = row0 + warp * 32 + lane;
-    const bool ok = row < a.R;
-    float* out = a.Out + (size_t)(ok ? row : 0) * HP;
-    const float* mrow = EPI == 1 ? a.mask + (size_t)(ok ? row : 0) * HP : nullptr;
+    float* stg = (float*)smem + warp * (32 * STG_PITCH);            // per-warp staging tile [32 rows][36 floats]
+    const int wrow0 = row0 + warp * 32;
     const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16);
+    const int cr = lane >> 3, cc = lane & 7;                         // coalesced side: 4 rows x 8 chunks per instruction
     float head = 0.f;
 #pragma unroll 1
     for (int c0 = 0; c0 < HP; c0 += 32) {
       uint32_t v[32];
       const int nc = HP - c0 >= 32 ? 32 : 16;
-      float4 mk[8];
-      if (EPI == 1) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) if (q * 4 < nc) mk[q] = *(const float4*)(mrow + c0 + q * 4);
-      }
       if (nc == 32) tmem_ld32(tbase + c0, v); else tmem_ld16(tbase + c0, v);
-      tmem_wait_ld();
+      if (EPI == 1) {
+        // ReLU mask of h_l: whole lines from global into the staging tile
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        if (q * 4 < nc) {
-          float o[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int col = c0 + q * 4 + e;
-            float x = __uint_as_float(v[q * 4 + e]);
-            if (EPI == 0) {
-              x = fmaxf(x, 0.f);
-              if (a.w4) head = fmaf(x, s_w4[col], head);
-              x = col == a.H ? 1.f : tf32_rn(x);
-            } else {
-              const float m = e == 0 ? mk[q].x : e == 1 ? mk[q].y : e == 2 ? mk[q].z : mk[q].w;
-              x = (m > 0.f && col < a.H) ? tf32_rn(x) : 0.f;
-            }
-            o[e] = x;
-          }
-          if (ok) *(float4*)(out + c0 + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + cr, grow = wrow0 + r;
+          if (grow < a.R && cc * 4 < nc)
+            *(float4*)(stg + r * STG_PITCH + cc * 4) = *(const float4*)(a.mask + (size_t)grow * HP + c0 + cc * 4);
         }
+        __syncwarp();
+      }
+      tmem_wait_ld();
+      float x[32];
+      if (EPI == 0) {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          x[q] = fmaxf(__uint_as_float(v[q]), 0.f);
+          if (q < nc && a.w4) head = fmaf(x[q], s_w4[c0 + q], head);
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (q * 4 < nc) {
+            const float4 m = *(const float4*)(stg + lane * STG_PITCH + q * 4);
+            x[q * 4 + 0] = m.x > 0.f ? tf32_rn(__uint_as_float(v[q * 4 + 0])) : 0.f;
+            x[q * 4 + 1] = m.y > 0.f ? tf32_rn(__uint_as_float(v[q * 4 + 1])) : 0.f;
+            x[q * 4 + 2] = m.z > 0.f ? tf32_rn(__uint_as_float(v[q * 4 + 2])) : 0.f;
+            x[q * 4 + 3] = m.w > 0.f ? tf32_rn(__uint_as_float(v[q * 4 + 3])) : 0.f;
+          }
+        }
+        __syncwarp();
+      }
+#pragma unroll 1
+      for (int part = 0; part < (EPI == 0 && a.OutLo ? 2 : 1); ++part) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (q * 4 < nc) {
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float t = x[q * 4 + e];
+              if (EPI == 0) {
+                const int col = c0 + q * 4 + e;
+                const float hi = col == a.H ? 1.f : tf32_rn(t);          // columns above H are 0 (zero weight rows)
+                t = part == 0 ? hi : (col == a.H ? 0.f : tf32_rn(t - hi));
+              }
+              o[e] = t;
+            }
+            *(float4*)(stg + lane * STG_PITCH + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
+          }
+        }
+        __syncwarp();
+        float* outp = part == 0 ? a.Out : a.OutLo;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + cr, grow = wrow0 + r;
+          if (grow < a.R && cc * 4 < nc)
+            *(float4*)(outp + (size_t)grow * HP + c0 + cc * 4) = *(const float4*)(stg + r * STG_PITCH + cc * 4);
+        }
+        __syncwarp();
       }
     }
-    if (EPI == 0 && a.w4 && ok) a.logits[row] = head + a.b4[0];
+    if (EPI == 0 && a.w4 && wrow0 + lane < a.R) a.logits[wrow0 + lane] = head + a.b4[0];
     tc_fence_before();
   } else if (warp == 4) {
-    // ---- MMA issue: per stage 4 (last: 2) K = 8 steps of 128 x 208 ----
+    // ---- MMA issue ----
     if (lane == 0) {
-      for (int kt = 0; kt < NKT; ++kt) {
+      for (int kt = 0; kt < NKT_; ++kt) {
         const int s = kt % GEMM_STAGES, u = kt / GEMM_STAGES;
         mbar_wait(FULL(s), u & 1, s_abort);
         tc_fence_after();
         const uint32_t aS = smem_u32(sA + s * A_STAGE), bS = smem_u32(sB + s * B_STAGE);
-        const int nks = kt == NKT - 1 ? 2 : 4;
-        for (int ks = 0; ks < nks; ++ks) {
-          const uint64_t ad = make_desc(aS + ks * 2 * (TM * 16), TM * 16, 128);
-          const uint64_t bd = make_desc(bS + ks * 2 * (HP * 16), HP * 16, 128);
-          mma_ss_tf32(tmem, ad, bd, IDESC_K, (kt | ks) != 0);
+        if (X3) {
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint64_t ah = make_desc(aS + ks * 2 * (TM * 16), TM * 16, 128);
+            const uint64_t al = make_desc(aS + TM * KT3 * 4 + ks * 2 * (TM * 16), TM * 16, 128);
+            const uint64_t bh = make_desc(bS + ks * 2 * (HP * 16), HP * 16, 128);
+            const uint64_t bl = make_desc(bS + HP * KT3 * 4 + ks * 2 * (HP * 16), HP * 16, 128);
+            mma_ss_tf32(tmem, al, bh, IDESC_K, (kt | ks) != 0);        // small terms first
+            mma_ss_tf32(tmem, ah, bl, IDESC_K, 1);
+            mma_ss_tf32(tmem, ah, bh, IDESC_K, 1);
+          }
+        } else {
+          const int nks = kt == NKT_ - 1 ? 2 : 4;
+          for (int ks = 0; ks < nks; ++ks) {
+            const uint64_t ad = make_desc(aS + ks * 2 * (TM * 16), TM * 16, 128);
+            const uint64_t bd = make_desc(bS + ks * 2 * (HP * 16), HP * 16, 128);
+            mma_ss_tf32(tmem, ad, bd, IDESC_K, (kt | ks) != 0);
+          }
         }
         tc_commit(EMPTY(s));
       }
@@ -362,13 +441,18 @@ __global__ void __launch_bounds__(GEMM_THREADS) upd_gemm_kernel(GemmArgs a, int*
     }
     __syncwarp();
   } else {
-    // ---- weight stages: one bulk copy per K tile ----
+    // ---- weight stages: bulk copies of the packed images ----
     if (lane == 0) {
-      for (int kt = 0; kt < NKT; ++kt) {
+      for (int kt = 0; kt < NKT_; ++kt) {
         const int s = kt % GEMM_STAGES, u = kt / GEMM_STAGES;
         if (u > 0) mbar_wait(EMPTY(s), (u - 1) & 1, s_abort);
         mbar_expect_tx(FULL(s), B_STAGE);
-        bulk_g2s(smem_u32(sB + s * B_STAGE), a.Bimg + (size_t)kt * (HP * KT), B_STAGE, FULL(s));
+        if (X3) {
+          bulk_g2s(smem_u32(sB + s * B_STAGE), a.Bimg + (size_t)kt * (HP * KT3), HP * KT3 * 4, FULL(s));
+          bulk_g2s(smem_u32(sB + s * B_STAGE) + HP * KT3 * 4, a.Bimg_lo + (size_t)kt * (HP * KT3), HP * KT3 * 4, FULL(s));
+        } else {
+          bulk_g2s(smem_u32(sB + s * B_STAGE), a.Bimg + (size_t)kt * (HP * KT), B_STAGE, FULL(s));
+        }
       }
     }
     __syncwarp();
@@ -749,10 +833,11 @@ extern "C" int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32
   const int tiles = (R + TM - 1) / TM;
 
   upd_pack_kernel<<<(6 * IMG_FLOATS + 255) / 256, 256, 0, st>>>(net, ws);
-  upd_layer0_kernel<<<THIN_CTAS, THIN_THREADS, 0, st>>>(net, states, R, ws.Hs[0]);
+  upd_layer0_kernel<<<THIN_CTAS, THIN_THREADS, 0, st>>>(net, states, R, ws.Hs[0], ws.Hl[0]);
   for (int l = 0; l < 3; ++l) {
     GemmArgs g{};
-    g.A = ws.Hs[l]; g.Bimg = ws.img_fwd[l]; g.Out = ws.Hs[l + 1]; g.R = R; g.H = H;
+    g.A = ws.Hs[l]; g.Alo = ws.Hl[l]; g.Bimg = ws.img_fwd[l]; g.Bimg_lo = ws.img_fwl[l]; g.Out = ws.Hs[l + 1];
+    g.OutLo = l < 2 ? ws.Hl[l + 1] : nullptr; g.R = R; g.H = H;
     if (l == 2) { g.w4 = W[4]; g.b4 = b[4]; g.logits = ws.logits; }
     upd_gemm_kernel<0><<<tiles, GEMM_THREADS, GEMM_SMEM, st>>>(g, ws.err);
   }

@@ -1,13 +1,14 @@
 """GPU parity tests of the hand-written PPO policy-gradient kernels (mbo_ppo_policy_grad)
 against the oracle's autograd restatement of ppo.py:148-168 / policies.py:150-161.
 
-Tolerances.  The kernels compute in TF32 (11-bit significand, fp32 accumulation): forward activations and
-logits within 2e-3 of max|.| (north-star bar for logits: 1e-3 relative on the shipped policies, checked
-below on golden states).  Gradients are compared twice: (a) element-wise, tolerance 3e-3 of max|grad| per
-tensor, against an fp64 backward that uses the KERNEL'S OWN ReLU decisions (a pre-activation within rounding
-error of zero flips its ReLU under any reduced-precision forward and changes dZ by its full value -- torch's
-own TF32 autograd deviates from fp32 autograd by the same few percent); (b) against plain fp64 autograd by
-cosine similarity of the whole gradient (> 0.995)."""
+Tolerances.  Forward: 3xTF32 (hi/lo split of both operands, fp32 accumulation), i.e. fp32-level: logits, log-probs,
+ratios and dlogits within 2e-5 of max|.| of the fp64 oracle (north-star bar for logits: 1e-3); the stored
+activations are the tf32-rounded hi parts (5e-4).  Backward: single-pass TF32 GEMMs with fp32 accumulation;
+gradients are compared (a) element-wise against an fp64 backward under the KERNEL'S OWN ReLU decisions (the handful
+of pre-activations within fp32 rounding error of zero may flip their ReLU against the fp64 forward and change dZ by
+its full value) at 3e-3 of max|grad| per tensor for random nets and 2e-2 for the trained policy (its gradient is a
+small sum of large cancelling terms: the error is 2^-12 relative to the terms, not to the sum), and (b) against the
+plain fp64 autograd gradient by cosine similarity (> 0.9995)."""
 import os
 
 import numpy as np
@@ -50,34 +51,34 @@ def _run_case(E, M, F_state, cols, H, layers, states, actions, advs, logp_old, e
 
 
 def _check_against_oracle(E, M, cols, H, layers, states, actions, advs, logp_old, terms, v, dW, db, eps=0.15, entc=0.01,
-                          n_global=None, fwd_tol=2e-3):
+                          n_global=None, fwd_tol=2e-5, grad_tol=3e-3):
     n_global = n_global or E
     pol_states = np.asarray(states)[:, :, cols]
     ref = O.ppo_policy_grads(layers, pol_states, actions, advs, logp_old, eps, entc, n_global)
     # forward
     for l in range(4):
         h = v["h%d" % (l + 1)].cpu()
-        assert _rel(h[:, :H], ref["hs"][l]) <= fwd_tol, ("h", l + 1)
+        assert _rel(h[:, :H], ref["hs"][l]) <= 5e-4, ("h", l + 1)        # stored hi part: tf32 rounding of the fp32 value
         assert bool((h[:, H] == 1).all()) and bool((h[:, H + 1:] == 0).all())
     assert _rel(v["logits"].cpu(), ref["logits"].reshape(-1)) <= fwd_tol
-    assert _rel(terms[:, 0], ref["logp"]) <= 1e-3 and _rel(terms[:, 1], ref["entropy"]) <= 1e-4
-    assert _rel(terms[:, 3], ref["ratio"]) <= 2e-3
-    assert abs(float(terms[:, 2].sum()) - ref["loss_ppo"]) <= 2e-3 * max(1.0, abs(ref["loss_ppo"]))
-    assert _rel(v["dlogits"].cpu(), ref["dlogits"].reshape(-1)) <= 2e-3
+    assert _rel(terms[:, 0], ref["logp"]) <= fwd_tol and _rel(terms[:, 1], ref["entropy"]) <= 1e-4
+    assert _rel(terms[:, 3], ref["ratio"]) <= 1e-4
+    assert abs(float(terms[:, 2].sum()) - ref["loss_ppo"]) <= 1e-4 * max(1.0, abs(ref["loss_ppo"]))
+    assert _rel(v["dlogits"].cpu(), ref["dlogits"].reshape(-1)) <= 1e-4
     # backward under the kernel's own ReLU decisions: element-wise
     masks = [(v["h%d" % (l + 1)][:, :H] > 0).cpu().numpy() for l in range(4)]
     own = O.ppo_policy_grads(layers, pol_states, actions, advs, logp_old, eps, entc, n_global, masks=masks)
     for l in range(5):
-        assert _rel(dW[l], own["dW"][l]) <= 3e-3, ("dW", l, _rel(dW[l], own["dW"][l]))
+        assert _rel(dW[l], own["dW"][l]) <= grad_tol, ("dW", l, _rel(dW[l], own["dW"][l]))
         scale = float(own["db"][l].abs().max())
         if l < 4:           # db4 = sum of dlogits = 0 analytically: only rounding noise is left
-            assert _rel(db[l], own["db"][l]) <= 3e-3, ("db", l)
+            assert _rel(db[l], own["db"][l]) <= grad_tol, ("db", l)
         else:
             assert float((db[l].double() - own["db"][l]).abs().max()) <= 1e-4 * float(ref["dlogits"].abs().sum()) + 1e-12
     # against the exact autograd gradient: direction
     flat = lambda gs: torch.cat([torch.as_tensor(g).double().reshape(-1) for g in gs])
     cos = torch.nn.functional.cosine_similarity(flat(dW + db[:4]), flat(ref["dW"] + ref["db"][:4]), dim=0)
-    assert float(cos) > 0.995, float(cos)
+    assert float(cos) > 0.9995, float(cos)
     flips = [int((torch.as_tensor(masks[l]) != (ref["hs"][l] > 0)).sum()) for l in range(4)]
     return flips, float(cos)
 
@@ -91,8 +92,7 @@ def _random_case(seed, E, M, F_state, cols, H):
     states = rng.randn(E, M, F_state).astype(np.float32)
     actions = rng.randint(0, M, E)
     advs = rng.randn(E).astype(np.float32)
-    with torch.no_grad():
-        lp0 = O.ppo_policy_grads(layers, states[:, :, cols], actions, advs, np.zeros(E), 0.15, 0.01, E)["logp"].numpy()
+    lp0 = O.ppo_policy_grads(layers, states[:, :, cols], actions, advs, np.zeros(E), 0.15, 0.01, E)["logp"].numpy()
     logp_old = (lp0 + 0.2 * rng.randn(E)).astype(np.float32)       # some ratios outside the clip range, either side
     return layers, states, actions, advs, logp_old
 
@@ -132,9 +132,10 @@ def test_policy_grad_on_golden_states_with_shipped_weights(golden_dir):
     cols = list(range(F))
     terms, v, dW, db = _run_case(E, M, F, cols, 200, layers, states, actions, advs, logp_old, n_global=2 * E)
     got = v["logits"].cpu().numpy().reshape(E, M)
-    assert np.max(np.abs(got - gold_logits)) <= 1e-3 * np.max(np.abs(gold_logits))      # north-star logits bar
-    _check_against_oracle(E, M, cols, 200, layers, states, actions, advs, logp_old, terms, v, dW, db, n_global=2 * E,
-                          fwd_tol=1e-3)
+    assert np.max(np.abs(got - gold_logits)) <= 2e-5 * np.max(np.abs(gold_logits))      # north-star logits bar: 1e-3
+    flips, cos = _check_against_oracle(E, M, cols, 200, layers, states, actions, advs, logp_old, terms, v, dW, db,
+                                       n_global=2 * E, grad_tol=2e-2)
+    assert sum(flips) <= 4
 
 
 def test_policy_grad_argument_errors():
