@@ -228,7 +228,10 @@ int mbo_cubes_around(int B, int k, int D, const double* x /*[B,k,D]*/, double di
  *   actions     [E] int32; advs, logp_old [E] fp32 (advantages already normalised, ppo.py:141-144)
  *   inv_n_global  1 / (global minibatch size): every loss term is divided by it (ppo.py:148-168 mean)
  *   dW, db      HOST arrays of 5 device pointers, gradients of
- *               loss_ppo + ent_coeff * loss_ent  w.r.t. W_l, b_l (overwritten, not accumulated)
+ *               loss_ppo + ent_coeff * loss_ent  w.r.t. W_l, b_l (overwritten, not accumulated);
+ *               dW == NULL: forward only (advs / logp_old / db may be NULL): terms[:, 0:2] = log-prob and
+ *               entropy under these weights -- the frozen old policy's logprobs_old of ppo.py:146-147, in the
+ *               same arithmetic as the update itself (ratio == 1 exactly while theta == theta_old)
  *   terms       [E, 4] fp32: logp(action), entropy, -min(ratio A, clip(ratio) A) / n, ratio
  *   workspace   mbo_ppo_workspace_bytes(E, M) bytes, 256-byte aligned, zero-initialised ONCE by the
  *               caller; its first int32 is a sticky error word (bit 0: a pipeline wait timed out)
@@ -241,6 +244,14 @@ int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32_t* feat_co
                         const int32_t* actions, const float* advs, const float* logp_old, float epsilon,
                         float ent_coeff, float inv_n_global, float* const* dW, float* const* db,
                         float* terms, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Adam step (ppo.py:93, torch.optim.Adam defaults: no weight decay, no amsgrad) over n <= 32 parameter tensors in
+ * one launch: m = lerp(m, g, 1 - beta1); v = beta2 v + (1 - beta2) g^2; p -= lr / (1 - beta1^t) * m /
+ * (sqrt(v) / sqrt(1 - beta2^t) + eps).  p, g, m, v: HOST arrays of n device pointers (fp32), sizes: HOST array of
+ * element counts.  state: 3 x 8 bytes on the device {int64 step t, double, double}, zero-initialised by the caller;
+ * the call advances t on the device, so a captured CUDA graph of the step can be replayed. */
+int mbo_adam_step(int n, float* const* p, const float* const* g, float* const* m, float* const* v,
+                  const int64_t* sizes, int64_t* state, float lr, float beta1, float beta2, float eps, void* stream);
 
 #ifdef __cplusplus
 }

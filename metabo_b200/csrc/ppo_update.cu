@@ -502,8 +502,8 @@ __global__ void __launch_bounds__(256) upd_loss_kernel(int M, const float* __res
   int act = actions[e];
   act = act < 0 ? 0 : (act >= M ? M - 1 : act);
   const float lpa = l[act] - lse;
-  const float adv = advs[e];
-  const float ratio = expf(lpa - logp_old[e]);
+  const float adv = advs ? advs[e] : 0.f;
+  const float ratio = expf(lpa - (logp_old ? logp_old[e] : lpa));
   const float clipped = fminf(fmaxf(ratio, 1.f - eps), 1.f + eps);
   const float s1 = ratio * adv, s2 = clipped * adv;
   // d(-min(s1, s2) / n) / d ratio: torch.min splits a tie evenly and clamp passes the gradient inside its range, so
@@ -533,17 +533,28 @@ __global__ void __launch_bounds__(THIN_THREADS) upd_dz4_kernel(int R, int H, con
   for (int e = 0; e < 4; ++e) w[e] = cg * 4 + e < H ? w4[cg * 4 + e] : 0.f;
   const int rpc = (R + gridDim.x - 1) / gridDim.x;
   const int r_end = min(R, (int)(blockIdx.x + 1) * rpc);
-  for (int r = blockIdx.x * rpc + rsub; r < r_end; r += 4) {
-    const float4 h = *(const float4*)(H4 + (size_t)r * HP + cg * 4);
-    const float d = __ldg(dl + r);
-    const float hv[4] = {h.x, h.y, h.z, h.w};
-    float o[4];
+  constexpr int U = 4;                                   // rows in flight per thread
+  for (int r0 = blockIdx.x * rpc + rsub; r0 < r_end; r0 += 4 * U) {
+    float4 h[U];
+    float d[U];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      acc[e] = fmaf(d, hv[e], acc[e]);                        // column H is the ones column: db4
-      o[e] = (hv[e] > 0.f && cg * 4 + e < H) ? tf32_rn(d * w[e]) : 0.f;
+    for (int u = 0; u < U; ++u) {
+      const int r = r0 + 4 * u;
+      h[u] = r < r_end ? *(const float4*)(H4 + (size_t)r * HP + cg * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      d[u] = r < r_end ? __ldg(dl + r) : 0.f;
     }
-    *(float4*)(dZ4 + (size_t)r * HP + cg * 4) = make_float4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int r = r0 + 4 * u;
+      const float hv[4] = {h[u].x, h[u].y, h[u].z, h[u].w};
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        acc[e] = fmaf(d[u], hv[e], acc[e]);                     // column H is the ones column: db4
+        o[e] = (hv[e] > 0.f && cg * 4 + e < H) ? tf32_rn(d[u] * w[e]) : 0.f;
+      }
+      if (r < r_end) *(float4*)(dZ4 + (size_t)r * HP + cg * 4) = make_float4(o[0], o[1], o[2], o[3]);
+    }
   }
 #pragma unroll
   for (int e = 0; e < 4; ++e) s_acc[rsub][cg * 4 + e] = acc[e];
@@ -566,17 +577,27 @@ __global__ void __launch_bounds__(THIN_THREADS) upd_wgrad0_kernel(Net net, const
     for (int f = 0; f <= MAXF; ++f) acc[e][f] = 0.f;
   const int rpc = (R + gridDim.x - 1) / gridDim.x;
   const int r_end = min(R, (int)(blockIdx.x + 1) * rpc);
-  for (int r = blockIdx.x * rpc + rsub; r < r_end; r += 4) {
-    const float4 d = *(const float4*)(dZ1 + (size_t)r * HP + cg * 4);
-    const float dv[4] = {d.x, d.y, d.z, d.w};
-    float x[MAXF + 1];
+  constexpr int U = 4;                                   // rows in flight per thread
+  for (int r0 = blockIdx.x * rpc + rsub; r0 < r_end; r0 += 4 * U) {
+    float4 d[U];
+    float x[U][MAXF + 1];
 #pragma unroll
-    for (int f = 0; f < MAXF; ++f) x[f] = f < F ? __ldg(states + (size_t)r * net.F_state + net.col[f]) : 0.f;
-    x[MAXF] = 1.f;
+    for (int u = 0; u < U; ++u) {
+      const int r = r0 + 4 * u;
+      const bool ok = r < r_end;
+      d[u] = ok ? *(const float4*)(dZ1 + (size_t)r * HP + cg * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int e = 0; e < 4; ++e)
+      for (int f = 0; f < MAXF; ++f) x[u][f] = (ok && f < F) ? __ldg(states + (size_t)r * net.F_state + net.col[f]) : 0.f;
+      x[u][MAXF] = 1.f;
+    }
 #pragma unroll
-      for (int f = 0; f <= MAXF; ++f) acc[e][f] = fmaf(dv[e], x[f], acc[e][f]);
+    for (int u = 0; u < U; ++u) {
+      const float dv[4] = {d[u].x, d[u].y, d[u].z, d[u].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int f = 0; f <= MAXF; ++f) acc[e][f] = fmaf(dv[e], x[u][f], acc[e][f]);
+    }
   }
   // fixed-order reduction over the 4 row lanes: lanes 1..3 park their sums, lane 0 adds them in order
   if (rsub > 0) {
@@ -739,32 +760,76 @@ __global__ void __launch_bounds__(GEMM_THREADS) upd_wgrad_kernel(WgradArgs a, in
 }
 
 // ---- fixed-order reduction of every partial ------------------------------------------------------------------------------
-__global__ void upd_reduce_kernel(Net net, Ws ws, int n_thin) {
+// blocks [0, nblkA): the three H x (H + 1) layers, one thread per output, 49 split-K partials;
+// then one WARP per output of the head (H + 1) and of layer 0 (H x (F + 1)): lanes stride over the n_thin CTA partials,
+// xor-tree combine (a fixed order: bitwise reproducible).
+__global__ void __launch_bounds__(256) upd_reduce_kernel(Net net, Ws ws, int n_thin, int nblkA) {
   const int H = net.H, F = net.F;
-  const int nA = 3 * H * (H + 1), nB = H + 1, nC = H * (F + 1);
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < nA) {
+  if ((int)blockIdx.x < nblkA) {
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= 3 * H * (H + 1)) return;
     const int l = idx / (H * (H + 1)), r = idx - l * H * (H + 1);
     const int o = r / (H + 1), i = r - o * (H + 1);
+    const float* p = ws.part_big + ((size_t)l * HP + o) * HP + i;
     float s = 0.f;
-    for (int sp = 0; sp < WG_SPLIT; ++sp) s += ws.part_big[(((size_t)sp * 3 + l) * HP + o) * HP + i];
+#pragma unroll 7
+    for (int sp = 0; sp < WG_SPLIT; ++sp) s += p[(size_t)sp * 3 * HP * HP];
     if (i < H) net.dW[l + 1][(size_t)o * H + i] = s; else net.db[l + 1][o] = s;
     return;
   }
-  idx -= nA;
+  const int lane = threadIdx.x & 31;
+  int idx = ((int)blockIdx.x - nblkA) * 8 + (threadIdx.x >> 5);
+  const int nB = H + 1, nC = H * (F + 1);
+  if (idx >= nB + nC) return;
+  const float* p;
+  size_t stride;
+  float* out;
   if (idx < nB) {
-    float s = 0.f;
-    for (int c = 0; c < n_thin; ++c) s += ws.part_head[(size_t)c * HP + idx];
-    if (idx < H) net.dW[4][idx] = s; else net.db[4][0] = s;
-    return;
-  }
-  idx -= nB;
-  if (idx < nC) {
+    p = ws.part_head + idx; stride = HP;
+    out = idx < H ? net.dW[4] + idx : net.db[4];
+  } else {
+    idx -= nB;
     const int o = idx / (F + 1), f = idx - o * (F + 1);
-    float s = 0.f;
-    for (int c = 0; c < n_thin; ++c) s += ws.part_l0[((size_t)c * HP + o) * (MAXF + 1) + (f < F ? f : MAXF)];
-    if (f < F) net.dW[0][(size_t)o * F + f] = s; else net.db[0][o] = s;
+    p = ws.part_l0 + (size_t)o * (MAXF + 1) + (f < F ? f : MAXF); stride = (size_t)HP * (MAXF + 1);
+    out = f < F ? net.dW[0] + (size_t)o * F + f : net.db[0] + o;
   }
+  float s = 0.f;
+  for (int c = lane; c < n_thin; c += 32) s += p[(size_t)c * stride];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) *out = s;
+}
+
+// ---- Adam (torch.optim.Adam defaults of ppo.py:93) over every parameter tensor in one launch -------------------------
+constexpr int ADAM_MAX_TENSORS = 32;
+struct AdamArgs {
+  float* p[ADAM_MAX_TENSORS];
+  const float* g[ADAM_MAX_TENSORS];
+  float* m[ADAM_MAX_TENSORS];
+  float* v[ADAM_MAX_TENSORS];
+  long long end[ADAM_MAX_TENSORS];     // exclusive prefix end of tensor t in the flat index space
+  int n;
+};
+// state = {step (int64), 1 - beta1^step (double), 1 - beta2^step (double)} on the device: a replayed CUDA graph advances it
+__global__ void adam_tick_kernel(long long* state, double beta1, double beta2) {
+  const long long t = state[0] + 1;
+  state[0] = t;
+  ((double*)state)[1] = 1.0 - pow(beta1, (double)t);
+  ((double*)state)[2] = 1.0 - pow(beta2, (double)t);
+}
+__global__ void __launch_bounds__(256) adam_step_kernel(AdamArgs a, const long long* __restrict__ state, float lr, float beta1,
+                                                         float beta2, float eps) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= a.end[a.n - 1]) return;
+  int t = 0;
+  while (i >= a.end[t]) ++t;
+  const long long j = i - (t ? a.end[t - 1] : 0);
+  const float bc1 = (float)((const double*)state)[1], bc2s = (float)sqrt(((const double*)state)[2]);
+  const float g = a.g[t][j];
+  const float m = a.m[t][j] + (g - a.m[t][j]) * (1.f - beta1);        // exp_avg.lerp_(grad, 1 - beta1)
+  const float v = a.v[t][j] * beta2 + (1.f - beta2) * g * g;
+  a.m[t][j] = m;
+  a.v[t][j] = v;
+  a.p[t][j] -= (lr / bc1) * m / (sqrtf(v) / bc2s + eps);
 }
 
 static bool g_attr_done = false;
@@ -811,16 +876,17 @@ extern "C" int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32
   MBO_CHECK_ARG((size_t)E * M < (1u << 30), "mbo_ppo_policy_grad: too many rows");
   MBO_CHECK_ARG(F >= 1 && F <= MAXF && F_state >= F, "mbo_ppo_policy_grad: 1 <= F <= %d policy features of F_state", MAXF);
   MBO_CHECK_ARG(H >= 8 && H <= HP - 1, "mbo_ppo_policy_grad: hidden width must be in 8..%d", HP - 1);
-  MBO_CHECK_ARG(states && W && b && actions && advs && logp_old && dW && db && terms && workspace && feat_col,
-                "mbo_ppo_policy_grad: null pointer");
+  const bool fwd_only = dW == nullptr;      // log-probs / entropies under these weights only (the frozen old policy)
+  MBO_CHECK_ARG(states && W && b && actions && terms && workspace && feat_col, "mbo_ppo_policy_grad: null pointer");
+  MBO_CHECK_ARG(fwd_only || (advs && logp_old && db), "mbo_ppo_policy_grad: null pointer");
   MBO_CHECK_ARG(workspace_bytes >= mbo_ppo_workspace_bytes(E, M), "mbo_ppo_policy_grad: workspace too small");
   MBO_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "mbo_ppo_policy_grad: workspace must be 256-byte aligned");
   if (set_attrs() != MBO_OK) return MBO_ERR_CUDA;
   cudaStream_t st = (cudaStream_t)stream;
   Net net;
   for (int l = 0; l < 5; ++l) {
-    MBO_CHECK_ARG(W[l] && b[l] && dW[l] && db[l], "mbo_ppo_policy_grad: null layer pointer");
-    net.W[l] = W[l]; net.b[l] = b[l]; net.dW[l] = dW[l]; net.db[l] = db[l];
+    MBO_CHECK_ARG(W[l] && b[l] && (fwd_only || (dW[l] && db[l])), "mbo_ppo_policy_grad: null layer pointer");
+    net.W[l] = W[l]; net.b[l] = b[l]; net.dW[l] = fwd_only ? nullptr : dW[l]; net.db[l] = fwd_only ? nullptr : db[l];
   }
   net.F = F; net.F_state = F_state; net.H = H;
   for (int f = 0; f < MAXF; ++f) {
@@ -833,7 +899,7 @@ extern "C" int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32
   const int tiles = (R + TM - 1) / TM;
 
   upd_pack_kernel<<<(6 * IMG_FLOATS + 255) / 256, 256, 0, st>>>(net, ws);
-  upd_layer0_kernel<<<THIN_CTAS, THIN_THREADS, 0, st>>>(net, states, R, ws.Hs[0], ws.Hl[0]);
+  upd_layer0_kernel<<<4 * THIN_CTAS, THIN_THREADS, 0, st>>>(net, states, R, ws.Hs[0], ws.Hl[0]);
   for (int l = 0; l < 3; ++l) {
     GemmArgs g{};
     g.A = ws.Hs[l]; g.Alo = ws.Hl[l]; g.Bimg = ws.img_fwd[l]; g.Bimg_lo = ws.img_fwl[l]; g.Out = ws.Hs[l + 1];
@@ -843,6 +909,11 @@ extern "C" int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32
   }
   upd_loss_kernel<<<E, 256, 0, st>>>(M, ws.logits, actions, advs, logp_old, epsilon, ent_coeff, inv_n_global, ws.dl,
                                       ws.terms);
+  if (fwd_only) {
+    MBO_CUDA(cudaMemcpyAsync(terms, ws.terms, (size_t)E * 16, cudaMemcpyDeviceToDevice, st));
+    MBO_LAUNCH_CHECK();
+    return MBO_OK;
+  }
   upd_dz4_kernel<<<THIN_CTAS, THIN_THREADS, 0, st>>>(R, H, ws.Hs[3], ws.dl, W[4], ws.dZ[3], ws.part_head);
   for (int l = 2; l >= 0; --l) {      // dZ_{l+1} = (dZ_{l+2} W_{l+1}) . [h_{l+1} > 0]
     GemmArgs g{};
@@ -855,9 +926,30 @@ extern "C" int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32
 
   upd_wgrad_kernel<<<dim3(WG_SPLIT, 3), GEMM_THREADS, WG_SMEM, st>>>(wa, ws.err);
   upd_wgrad0_kernel<<<THIN_CTAS, THIN_THREADS, 0, st>>>(net, states, R, ws.dZ[0], ws.part_l0);
-  const int n_red = 3 * H * (H + 1) + (H + 1) + H * (F + 1);
-  upd_reduce_kernel<<<(n_red + 255) / 256, 256, 0, st>>>(net, ws, THIN_CTAS);
+  const int nblkA = (3 * H * (H + 1) + 255) / 256, nblkT = ((H + 1) + H * (F + 1) + 7) / 8;
+  upd_reduce_kernel<<<nblkA + nblkT, 256, 0, st>>>(net, ws, THIN_CTAS, nblkA);
   MBO_CUDA(cudaMemcpyAsync(terms, ws.terms, (size_t)E * 16, cudaMemcpyDeviceToDevice, st));
+  MBO_LAUNCH_CHECK();
+  return MBO_OK;
+}
+
+extern "C" int mbo_adam_step(int n, float* const* p, const float* const* g, float* const* m, float* const* v,
+                             const int64_t* sizes, int64_t* state, float lr, float beta1, float beta2, float eps,
+                             void* stream) {
+  MBO_CHECK_ARG(n >= 1 && n <= ADAM_MAX_TENSORS, "mbo_adam_step: 1..%d tensors per call", ADAM_MAX_TENSORS);
+  MBO_CHECK_ARG(p && g && m && v && sizes && state, "mbo_adam_step: null pointer");
+  AdamArgs a;
+  long long tot = 0;
+  for (int t = 0; t < n; ++t) {
+    MBO_CHECK_ARG(p[t] && g[t] && m[t] && v[t] && sizes[t] > 0, "mbo_adam_step: null / empty tensor %d", t);
+    a.p[t] = p[t]; a.g[t] = g[t]; a.m[t] = m[t]; a.v[t] = v[t];
+    tot += sizes[t];
+    a.end[t] = tot;
+  }
+  a.n = n;
+  cudaStream_t st = (cudaStream_t)stream;
+  adam_tick_kernel<<<1, 1, 0, st>>>((long long*)state, (double)beta1, (double)beta2);
+  adam_step_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(a, (const long long*)state, lr, beta1, beta2, eps);
   MBO_LAUNCH_CHECK();
   return MBO_OK;
 }

@@ -314,7 +314,8 @@ class PPOPolicyGrad:
         loss_ppo + ent_coeff * loss_ent are written into dW / db.  Returns terms [E, 4]."""
         _chk(states, torch.float32, "states"); _chk(actions, torch.int32, "actions")
         _chk(advs, torch.float32, "advs"); _chk(logp_old, torch.float32, "logp_old")
-        assert tuple(states.shape) == (self.E, self.M, self.F_state), states.shape
+        E = states.shape[0]
+        assert E <= self.E and tuple(states.shape[1:]) == (self.M, self.F_state), states.shape
         assert len(weights) == len(biases) == len(dW) == len(db) == 5
         for t in list(weights) + list(biases) + list(dW) + list(db):
             _chk(t, torch.float32, "parameter / gradient")
@@ -322,11 +323,24 @@ class PPOPolicyGrad:
         Bv = (C.c_void_p * 5)(*[t.data_ptr() for t in biases])
         gW = (C.c_void_p * 5)(*[t.data_ptr() for t in dW])
         gB = (C.c_void_p * 5)(*[t.data_ptr() for t in db])
-        L.check(L.lib().mbo_ppo_policy_grad(self.E, self.M, self.F_state, len(self.cols), self._cols, self.H, _p(states),
+        L.check(L.lib().mbo_ppo_policy_grad(E, self.M, self.F_state, len(self.cols), self._cols, self.H, _p(states),
                                             W, Bv, _p(actions), _p(advs), _p(logp_old), float(epsilon), float(ent_coeff),
                                             1.0 / float(n_global), gW, gB, _p(self.terms), _p(self.ws), self.nbytes,
                                             _stream()), "mbo_ppo_policy_grad")
-        return self.terms
+        return self.terms[:E]
+
+    def logp_entropy(self, states, weights, biases, actions):
+        """Forward only: (log-prob of the action, entropy) [E] under the given weights, in the arithmetic of the
+        update kernels (3xTF32 forward) -- ppo.py:146-147's logprobs_old of the frozen old policy."""
+        _chk(states, torch.float32, "states"); _chk(actions, torch.int32, "actions")
+        E = states.shape[0]
+        assert E <= self.E and tuple(states.shape[1:]) == (self.M, self.F_state), states.shape
+        W = (C.c_void_p * 5)(*[t.data_ptr() for t in weights])
+        Bv = (C.c_void_p * 5)(*[t.data_ptr() for t in biases])
+        L.check(L.lib().mbo_ppo_policy_grad(E, self.M, self.F_state, len(self.cols), self._cols, self.H, _p(states),
+                                            W, Bv, _p(actions), None, None, 0.0, 0.0, 1.0, None, None, _p(self.terms),
+                                            _p(self.ws), self.nbytes, _stream()), "mbo_ppo_policy_grad")
+        return self.terms[:E, 0].clone(), self.terms[:E, 1].clone()
 
     def check(self):
         """Synchronises; raises if a pipeline wait of the update kernels timed out."""
@@ -349,3 +363,40 @@ class PPOPolicyGrad:
         v["dlogits"] = f[off[9] // 4:off[9] // 4 + R]
         v["part_big"] = f[off[11] // 4:off[11] // 4 + 49 * 3 * self.HP * self.HP].view(49, 3, self.HP, self.HP)
         return v
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """torch.optim.Adam(params, lr) semantics (ppo.py:93: default betas / eps, no weight decay, no amsgrad) with the
+    whole step in one kernel launch (`mbo_adam_step`); the step counter lives on the device, so a captured CUDA graph of
+    the step can be replayed.  state[p] has torch's keys: step (shared device int64), exp_avg, exp_avg_sq."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        self._state_dev = None
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        assert closure is None
+        for group in self.param_groups:
+            ps = [p for p in group["params"] if p.grad is not None]
+            if not ps:
+                continue
+            if self._state_dev is None:
+                self._state_dev = torch.zeros(3, dtype=torch.int64, device=ps[0].device)
+            for p in ps:
+                st = self.state[p]
+                if not st:
+                    st["step"] = self._state_dev[0:1]
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                _chk(p.data, torch.float32, "parameter"); _chk(p.grad, torch.float32, "gradient")
+            n = len(ps)
+            arr = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])
+            sizes = (C.c_int64 * n)(*[p.numel() for p in ps])
+            b1, b2 = group["betas"]
+            L.check(L.lib().mbo_adam_step(n, arr([p.data for p in ps]), arr([p.grad for p in ps]),
+                                          arr([self.state[p]["exp_avg"] for p in ps]),
+                                          arr([self.state[p]["exp_avg_sq"] for p in ps]), sizes, _p(self._state_dev),
+                                          float(group["lr"]), float(b1), float(b2), float(group["eps"]), _stream()),
+                    "mbo_adam_step")
+        return None

@@ -120,7 +120,6 @@ class PPO:
         if self.world > 1:   # identical initial weights on every rank
             for p in self.pi.parameters():
                 dist.broadcast(p.data, src=0)
-        self.optimizer = torch.optim.Adam(self.pi.parameters(), lr=self.params["lr"], capturable=True)
         # autograd GEMMs of the update: "highest" = fp32 (reference numerics), "high" = TF32 tensor cores
         torch.set_float32_matmul_precision(self.params.get("update_matmul_precision", "highest"))
         self.use_update_graph = self.world == 1 and os.environ.get("MBO_NO_GRAPHS") is None and \
@@ -132,6 +131,10 @@ class PPO:
         if backend == "native" and not self.native_update_supported(self.pi):
             backend = "autograd"          # e.g. the 2 x 20 GP-sample policy: too small for the tensor-core path
         self.update_backend = backend
+        if backend == "native":       # same update rule, one launch per step (mbo_adam_step)
+            self.optimizer = ops.FusedAdam(self.pi.parameters(), lr=self.params["lr"])
+        else:
+            self.optimizer = torch.optim.Adam(self.pi.parameters(), lr=self.params["lr"], capturable=True)
         self._pg = None         # ops.PPOPolicyGrad for the current minibatch shape
         self._pg_grads = None   # persistent gradient buffers of the policy net (written by the kernels)
 
@@ -180,6 +183,22 @@ class PPO:
         return (pi.activation == "relu" and len(a) == 4 and len(set(a)) == 1 and 8 <= a[0] <= 207
                 and 1 <= pi.N_features_policy <= 8)
 
+    def _policy_grad_op(self, E, M, Fs):
+        pg = self._pg
+        if pg is None or pg.E < E or (pg.M, pg.F_state) != (M, Fs):
+            pi = self.pi
+            self._pg = ops.PPOPolicyGrad(E, M, Fs, pi.policy_columns(), pi.policy_net.arch_spec[0], self.device)
+        return self._pg
+
+    def _old_logprobs(self, states, actions):
+        """ppo.py:146-147 `logprobs_old` of the frozen old policy, by the update kernels' own forward (same
+        arithmetic as the new policy's log-probs: the ratio is exactly 1 while theta == theta_old)."""
+        fcs = list(self.old_pi.policy_net.fc)
+        pg = self._policy_grad_op(*states.shape)
+        lp, _ = pg.logp_entropy(states.contiguous(), [l.weight.data for l in fcs], [l.bias.data for l in fcs],
+                                actions.to(torch.int32).contiguous())
+        return lp
+
     def _update_step_native(self, mb):
         """ppo.py:129-178 with the policy net's forward + backward on the hand-written kernels
         (mbo_ppo_policy_grad); value net (2 inputs per minibatch row) on torch autograd."""
@@ -190,11 +209,11 @@ class PPO:
         if self.params["normalize_advs"]:
             advs = normalize_advantages(advs, self.world)
         pi = self.pi
-        with torch.no_grad():
-            _, logprobs_old, _ = self.old_pi.predict_vals_logps_ents(states=states, actions=actions)
         fcs = list(pi.policy_net.fc)
-        if self._pg is None or (self._pg.E, self._pg.M, self._pg.F_state) != (E, M, Fs):
-            self._pg = ops.PPOPolicyGrad(E, M, Fs, pi.policy_columns(), pi.policy_net.arch_spec[0], states.device)
+        self._policy_grad_op(E, M, Fs)
+        logprobs_old = mb.get("logprobs_old")
+        if logprobs_old is None:
+            logprobs_old = self._old_logprobs(states, actions)
         if self._pg_grads is None:
             self._pg_grads = ([torch.zeros_like(l.weight) for l in fcs], [torch.zeros_like(l.bias) for l in fcs])
         dW, db = self._pg_grads
@@ -280,11 +299,22 @@ class PPO:
         self.old_pi.set_requires_grad(False)
         self.old_pi.kernel_handles()      # re-pack the frozen policy's kernel weights NOW: a replayed graph cannot do it
         local_mb = self.params["minibatch_size"] // self.world
+        buf = self.batch_recorder.buf
+        buf.pop("logprobs_old", None)
+        if self.update_backend == "native":
+            # theta_old is frozen for the whole call: its log-probs (recomputed per minibatch in ppo.py:146-147) are
+            # computed once per transition here and travel with the minibatches
+            B, T = buf["actions"].shape[:2]
+            st = buf["states"].reshape((B * T,) + tuple(buf["states"].shape[2:]))
+            ac = buf["actions"].reshape(B * T)
+            with torch.no_grad():
+                lp = [self._old_logprobs(st[i:i + local_mb], ac[i:i + local_mb]) for i in range(0, B * T, local_mb)]
+            buf["logprobs_old"] = torch.cat(lp).reshape(B, T)
         for ep in range(self.params["n_epochs"]):
             sums = torch.zeros(4, device=self.device)
             n_minibatches = 0
             for mb in self.batch_recorder.iterate_device(local_mb, shuffle=True):
-                mb = {k: v for k, v in mb.items() if k in ("states", "actions", "tdlamrets", "advs")}
+                mb = {k: v for k, v in mb.items() if k in ("states", "actions", "tdlamrets", "advs", "logprobs_old")}
                 graphable = self.use_update_graph and mb["states"].shape[0] == local_mb and self.stats["n_optsteps"] > 0
                 sums += self._graphed_update(mb) if graphable else self._update_step(mb)
                 self.stats["n_optsteps"] += 1

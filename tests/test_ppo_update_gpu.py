@@ -185,3 +185,48 @@ def test_ppo_native_update_follows_autograd_update(tmp_path):
     da, dn = (w1a - w0a).double(), (w1n - w0n).double()
     cos = float(torch.nn.functional.cosine_similarity(da, dn, dim=0))
     assert cos > 0.9, cos
+
+
+def test_fused_adam_matches_torch_adam():
+    """mbo_adam_step against torch.optim.Adam (the reference's optimiser, ppo.py:93) over several steps and ragged
+    tensor sizes; a parameter without a gradient is left alone."""
+    from metabo_b200 import ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(0)
+    shapes = [(200, 6), (200,), (200, 200), (1, 200), (1,), (7, 3)]
+    pa = [torch.randn(s, generator=g).to(dev).requires_grad_() for s in shapes]
+    pb = [p.detach().clone().requires_grad_() for p in pa]
+    oa = torch.optim.Adam(pa, lr=1e-2)
+    ob = ops.FusedAdam(pb, lr=1e-2)
+    for step in range(5):
+        for i, (x, y) in enumerate(zip(pa, pb)):
+            if i == 5 and step < 2:
+                x.grad = y.grad = None
+                continue
+            gr = torch.randn(x.shape, generator=g).to(dev) * (10.0 ** (i - 3))
+            x.grad, y.grad = gr.clone(), gr.clone()
+        oa.step()
+        ob.step()
+    for x, y in zip(pa, pb):
+        assert float((x - y).abs().max()) <= 2e-6 * float(x.abs().max()) + 1e-7
+    assert int(ob.state[pb[0]]["step"].item()) == 5
+
+
+def test_old_policy_logprobs_are_bitwise_the_new_policys_at_equal_weights():
+    """ratio == 1 exactly while theta == theta_old: the forward-only call and the gradient call share their arithmetic."""
+    from metabo_b200 import ops
+    dev = torch.device("cuda:0")
+    layers, states, actions, advs, _ = _random_case(5, 6, 400, 6, list(range(6)), 200)
+    pg = ops.PPOPolicyGrad(8, 400, 6, list(range(6)), 200, dev)        # capacity above the call's E
+    W = [torch.as_tensor(w, device=dev).contiguous() for w, _ in layers]
+    b = [torch.as_tensor(x, device=dev).contiguous() for _, x in layers]
+    st = torch.as_tensor(states, device=dev)
+    ac = torch.as_tensor(actions, dtype=torch.int32, device=dev)
+    lp, en = pg.logp_entropy(st, W, b, ac)
+    dW = [torch.zeros_like(w) for w in W]
+    db = [torch.zeros_like(x) for x in b]
+    terms = pg(st, W, b, ac, torch.as_tensor(advs, device=dev), lp, 0.15, 0.01, 6, dW, db)
+    torch.cuda.synchronize()
+    pg.check()
+    assert torch.equal(terms[:, 0], lp) and torch.equal(terms[:, 1], en)
+    assert bool((terms[:, 3] == 1.0).all())
