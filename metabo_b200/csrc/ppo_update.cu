@@ -16,9 +16,9 @@
 //   upd_gemm_kernel<0>   h_{l+1} = relu([h_l,1] Wb^T) (+ head logit)         tcgen05 kind::tf32, A and B from smem
 //   upd_loss_kernel      per episode: log-softmax, logp(a), entropy, clipped surrogate, dlogits
 //   upd_dz4_kernel       dZ4 = dlogit (x) w4 . [h4 > 0]  (+ partial sums of dw4, db4)
-//   upd_gemm_kernel<1>   dZ_l = (dZ_{l+1} W_l) . [h_l > 0]                   tcgen05 kind::tf32
+//   upd_gemm_kernel<1>   dZ_l = (dZ_{l+1} W_l) . [h_l > 0] (ReLU bit words)   tcgen05 kind::tf32
 //   upd_wgrad_kernel     dWb_l = dZ_{l+1}^T [h_l,1]  split-K over CTAs        tcgen05 kind::tf32, both operands MN-major
-//   upd_wgrad0_kernel    dW0 = dZ1^T x, db0                                   CUDA cores
+//   upd_wgrad0_kernel    dW0 = (dH1 . [h1 > 0])^T x, db0                      CUDA cores
 //   upd_reduce_kernel    fixed-order sum of the split-K partials -> dW, db    (deterministic, no atomics)
 //
 // Operand staging: the activation / gradient tiles are row-major fp32 in HBM; 16-byte cp.async copies place each
@@ -42,9 +42,12 @@ constexpr int A_STAGE = TM * KT * 4;          // 16 384 (dgrad: 32 K values; for
 constexpr int B_STAGE = HP * KT * 4;          // 26 624
 constexpr int IMG_FLOATS = NKT * HP * KT;     // 46 592 floats per weight image (forward images use 43 264 of them)
 constexpr int STG_PITCH = 36;                 // floats per row of the epilogue's per-warp staging tile (32 + 4: conflict-free)
-constexpr int GEMM_STAGES = 2;
+constexpr int GEMM_MB = 1;          // 128-row blocks per CTA.  2 (shared weight stages, 3 pipeline stages, 1 CTA/SM) measured SLOWER
+                                    // (fwd 71 -> 81 us, dgrad 61 -> 94 us): two co-resident CTAs hide each other's epilogue
+constexpr int GEMM_STAGES = GEMM_MB == 1 ? 2 : 3;
 constexpr int GEMM_THREADS = 192;   // warps 0-3: A loaders then epilogue; warp 4: MMA issue; warp 5: weight stages
-constexpr int GEMM_SMEM = GEMM_STAGES * (A_STAGE + B_STAGE) + 256;
+constexpr int GEMM_A_STAGE = GEMM_MB * A_STAGE;
+constexpr int GEMM_SMEM = GEMM_STAGES * (GEMM_A_STAGE + B_STAGE) + 256;
 constexpr int WG_STAGES = 3;
 constexpr int WG_A_STAGE = 8 * 4096;          // 8 blocks of 32 columns (256 = two M blocks) x 32 K rows x 128 B
 constexpr int WG_B_STAGE = 7 * 4096;          // 7 blocks (224 >= 208 columns)
@@ -150,6 +153,7 @@ struct Ws {          // workspace carve-up (device pointers)
   float* img_dgr[3];  // W^T, KT stages
   float* Hs[4];      // h1..h4 (tf32-rounded "hi" parts)
   float* Hl[3];      // lo parts of h1..h3 (3xTF32 forward)
+  uint32_t* hbits[2]; // ReLU decisions of h2, h3: [R][8] words, bit q of word c = (h[row][32 c + q] > 0)
   float* dZ[4];      // dZ1..dZ4
   float* logits;
   float* dl;
@@ -172,6 +176,7 @@ static size_t carve(int E, int M, unsigned char* base, Ws* w) {
   for (int l = 0; l < 3; ++l) t.img_dgr[l] = (float*)take((size_t)IMG_FLOATS * 4);
   for (int l = 0; l < 4; ++l) t.Hs[l] = (float*)take(Rp * HP * 4);
   for (int l = 0; l < 3; ++l) t.Hl[l] = (float*)take(Rp * HP * 4);
+  for (int l = 0; l < 2; ++l) t.hbits[l] = (uint32_t*)take(Rp * 8 * 4);
   for (int l = 0; l < 4; ++l) t.dZ[l] = (float*)take(Rp * HP * 4);
   t.logits = (float*)take(Rp * 4);
   t.dl = (float*)take(Rp * 4);
@@ -255,7 +260,8 @@ struct GemmArgs {
   const float* Bimg_lo;  // forward: lo parts
   float* Out;            // [R, HP] (forward: hi part of h_{l+1})
   float* OutLo;          // forward: lo part of h_{l+1}, or nullptr (h4 feeds only the head and the wgrad)
-  const float* mask;     // dgrad: h_l (ReLU mask)
+  const uint32_t* bits_in;   // dgrad: ReLU decisions of h_l (nullptr: no mask, the consumer applies it)
+  uint32_t* bits_out;        // forward: ReLU decisions of h_{l+1} for the dgrad, or nullptr
   const float* w4;       // forward of the last hidden layer: head weights [H], else nullptr
   const float* b4;
   float* logits;         // [R]
@@ -274,13 +280,13 @@ __global__ void __launch_bounds__(GEMM_THREADS) upd_gemm_kernel(GemmArgs a, int*
   constexpr int KT_ = X3 ? KT3 : KT;
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* sA = smem;
-  unsigned char* sB = smem + GEMM_STAGES * A_STAGE;
-  uint64_t* bars = (uint64_t*)(smem + GEMM_STAGES * (A_STAGE + B_STAGE));
+  unsigned char* sB = smem + GEMM_STAGES * GEMM_A_STAGE;
+  uint64_t* bars = (uint64_t*)(smem + GEMM_STAGES * (GEMM_A_STAGE + B_STAGE));
   uint32_t* s_tmem = (uint32_t*)(bars + 8);
   volatile int* s_abort = (volatile int*)(s_tmem + 1);
   __shared__ float s_w4[HP];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row0 = blockIdx.x * TM;
+  const int row0 = blockIdx.x * (TM * GEMM_MB);
   const uint32_t bar0 = smem_u32(bars);
   auto FULL = [&](int s) { return bar0 + 8u * s; };
   auto EMPTY = [&](int s) { return bar0 + 8u * (GEMM_STAGES + s); };
@@ -294,7 +300,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) upd_gemm_kernel(GemmArgs a, int*
   }
   if (EPI == 0 && a.w4) for (int i = tid; i < HP; i += GEMM_THREADS) s_w4[i] = i < a.H ? a.w4[i] : 0.f;
   if (warp == 4) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(256u) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(256u * GEMM_MB) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -309,72 +315,80 @@ __global__ void __launch_bounds__(GEMM_THREADS) upd_gemm_kernel(GemmArgs a, int*
     for (int kt = 0; kt < NKT_; ++kt) {
       const int s = kt % GEMM_STAGES, u = kt / GEMM_STAGES;
       if (u > 0) mbar_wait(EMPTY(s), (u - 1) & 1, s_abort);
-      const uint32_t dstA = smem_u32(sA + s * A_STAGE);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int j = warp * 8 + i;
-        if (X3) {
-          const int arr = j >> 4, group = j & 15;          // hi rows, then lo rows; 4 chunks = the whole K tile
-          const int grow = row0 + group * 8 + r8;
-          const bool ok = grow < a.R;
-          const float* src = (arr ? a.Alo : a.A) + (size_t)(ok ? grow : 0) * HP + kt * KT_ + cq * 4;
-          cp_async16(dstA + arr * (TM * KT3 * 4) + cq * (TM * 16) + group * 128 + r8 * 16, src, ok);
-        } else {
-          const int group = j >> 1, chalf = j & 1;
-          if (kt < NKT_ - 1 || chalf == 0) {                 // the last K tile holds columns 192..207 only
-            const int c = chalf * 4 + cq;
-            const int grow = row0 + group * 8 + r8;
+      for (int mb = 0; mb < GEMM_MB; ++mb) {
+        const uint32_t dstA = smem_u32(sA + s * GEMM_A_STAGE + mb * A_STAGE);
+        const int brow0 = row0 + mb * TM;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int j = warp * 8 + i;
+          if (X3) {
+            const int arr = j >> 4, group = j & 15;          // hi rows, then lo rows; 4 chunks = the whole K tile
+            const int grow = brow0 + group * 8 + r8;
             const bool ok = grow < a.R;
-            const float* src = a.A + (size_t)(ok ? grow : 0) * HP + kt * KT_ + c * 4;
-            cp_async16(dstA + c * (TM * 16) + group * 128 + r8 * 16, src, ok);
+            const float* src = (arr ? a.Alo : a.A) + (size_t)(ok ? grow : 0) * HP + kt * KT_ + cq * 4;
+            cp_async16(dstA + arr * (TM * KT3 * 4) + cq * (TM * 16) + group * 128 + r8 * 16, src, ok);
+          } else {
+            const int group = j >> 1, chalf = j & 1;
+            if (kt < NKT_ - 1 || chalf == 0) {                 // the last K tile holds columns 192..207 only
+              const int c = chalf * 4 + cq;
+              const int grow = brow0 + group * 8 + r8;
+              const bool ok = grow < a.R;
+              const float* src = a.A + (size_t)(ok ? grow : 0) * HP + kt * KT_ + c * 4;
+              cp_async16(dstA + c * (TM * 16) + group * 128 + r8 * 16, src, ok);
+            }
           }
         }
       }
       cp_async_arrive(FULL(s));
     }
     // ---- epilogue ----
+    uint32_t mbits[GEMM_MB][8];
+    if (EPI == 1) {                        // the row's ReLU words: fetched while the last MMAs are still running
+#pragma unroll
+      for (int mb = 0; mb < GEMM_MB; ++mb) {
+        const int row = row0 + mb * TM + warp * 32 + lane;
+        uint4 w0 = make_uint4(~0u, ~0u, ~0u, ~0u), w1 = w0;
+        if (a.bits_in && row < a.R) {
+          w0 = *(const uint4*)(a.bits_in + (size_t)row * 8);
+          w1 = *(const uint4*)(a.bits_in + (size_t)row * 8 + 4);
+        }
+        mbits[mb][0] = w0.x; mbits[mb][1] = w0.y; mbits[mb][2] = w0.z; mbits[mb][3] = w0.w;
+        mbits[mb][4] = w1.x; mbits[mb][5] = w1.y; mbits[mb][6] = w1.z; mbits[mb][7] = w1.w;
+      }
+    }
     mbar_wait(ACCF, 0, s_abort);
     tc_fence_after();
     float* stg = (float*)smem + warp * (32 * STG_PITCH);            // per-warp staging tile [32 rows][36 floats]
-    const int wrow0 = row0 + warp * 32;
-    const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16);
     const int cr = lane >> 3, cc = lane & 7;                         // coalesced side: 4 rows x 8 chunks per instruction
+#pragma unroll 1
+    for (int mb = 0; mb < GEMM_MB; ++mb) {
+    const int wrow0 = row0 + mb * TM + warp * 32;
+    if (wrow0 >= a.R) break;                                         // warp-uniform: nothing to store for these rows
+    const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16) + mb * 256;
     float head = 0.f;
 #pragma unroll 1
     for (int c0 = 0; c0 < HP; c0 += 32) {
       uint32_t v[32];
       const int nc = HP - c0 >= 32 ? 32 : 16;
       if (nc == 32) tmem_ld32(tbase + c0, v); else tmem_ld16(tbase + c0, v);
-      if (EPI == 1) {
-        // ReLU mask of h_l: whole lines from global into the staging tile
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = i * 4 + cr, grow = wrow0 + r;
-          if (grow < a.R && cc * 4 < nc)
-            *(float4*)(stg + r * STG_PITCH + cc * 4) = *(const float4*)(a.mask + (size_t)grow * HP + c0 + cc * 4);
-        }
-        __syncwarp();
-      }
       tmem_wait_ld();
       float x[32];
       if (EPI == 0) {
+        uint32_t word = 0;
 #pragma unroll
         for (int q = 0; q < 32; ++q) {
           x[q] = fmaxf(__uint_as_float(v[q]), 0.f);
-          if (q < nc && a.w4) head = fmaf(x[q], s_w4[c0 + q], head);
-        }
-      } else {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          if (q * 4 < nc) {
-            const float4 m = *(const float4*)(stg + lane * STG_PITCH + q * 4);
-            x[q * 4 + 0] = m.x > 0.f ? tf32_rn(__uint_as_float(v[q * 4 + 0])) : 0.f;
-            x[q * 4 + 1] = m.y > 0.f ? tf32_rn(__uint_as_float(v[q * 4 + 1])) : 0.f;
-            x[q * 4 + 2] = m.z > 0.f ? tf32_rn(__uint_as_float(v[q * 4 + 2])) : 0.f;
-            x[q * 4 + 3] = m.w > 0.f ? tf32_rn(__uint_as_float(v[q * 4 + 3])) : 0.f;
+          if (q < nc) {
+            if (a.w4) head = fmaf(x[q], s_w4[c0 + q], head);
+            word |= (x[q] > 0.f ? 1u : 0u) << q;
           }
         }
-        __syncwarp();
+        if (a.bits_out && wrow0 + lane < a.R) a.bits_out[(size_t)(wrow0 + lane) * 8 + (c0 >> 5)] = word;
+      } else {
+        const uint32_t word = mbits[mb][c0 >> 5];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) x[q] = (q < nc && ((word >> q) & 1u)) ? tf32_rn(__uint_as_float(v[q])) : 0.f;
       }
 #pragma unroll 1
       for (int part = 0; part < (EPI == 0 && a.OutLo ? 2 : 1); ++part) {
@@ -407,6 +421,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) upd_gemm_kernel(GemmArgs a, int*
       }
     }
     if (EPI == 0 && a.w4 && wrow0 + lane < a.R) a.logits[wrow0 + lane] = head + a.b4[0];
+    }
     tc_fence_before();
   } else if (warp == 4) {
     // ---- MMA issue ----
@@ -415,24 +430,31 @@ __global__ void __launch_bounds__(GEMM_THREADS) upd_gemm_kernel(GemmArgs a, int*
         const int s = kt % GEMM_STAGES, u = kt / GEMM_STAGES;
         mbar_wait(FULL(s), u & 1, s_abort);
         tc_fence_after();
-        const uint32_t aS = smem_u32(sA + s * A_STAGE), bS = smem_u32(sB + s * B_STAGE);
+        const uint32_t aS0 = smem_u32(sA + s * GEMM_A_STAGE), bS = smem_u32(sB + s * B_STAGE);
         if (X3) {
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks) {
-            const uint64_t ah = make_desc(aS + ks * 2 * (TM * 16), TM * 16, 128);
-            const uint64_t al = make_desc(aS + TM * KT3 * 4 + ks * 2 * (TM * 16), TM * 16, 128);
             const uint64_t bh = make_desc(bS + ks * 2 * (HP * 16), HP * 16, 128);
             const uint64_t bl = make_desc(bS + HP * KT3 * 4 + ks * 2 * (HP * 16), HP * 16, 128);
-            mma_ss_tf32(tmem, al, bh, IDESC_K, (kt | ks) != 0);        // small terms first
-            mma_ss_tf32(tmem, ah, bl, IDESC_K, 1);
-            mma_ss_tf32(tmem, ah, bh, IDESC_K, 1);
+#pragma unroll
+            for (int mb = 0; mb < GEMM_MB; ++mb) {
+              const uint32_t aS = aS0 + mb * A_STAGE;
+              const uint64_t ah = make_desc(aS + ks * 2 * (TM * 16), TM * 16, 128);
+              const uint64_t al = make_desc(aS + TM * KT3 * 4 + ks * 2 * (TM * 16), TM * 16, 128);
+              mma_ss_tf32(tmem + mb * 256, al, bh, IDESC_K, (kt | ks) != 0);        // small terms first
+              mma_ss_tf32(tmem + mb * 256, ah, bl, IDESC_K, 1);
+              mma_ss_tf32(tmem + mb * 256, ah, bh, IDESC_K, 1);
+            }
           }
         } else {
           const int nks = kt == NKT_ - 1 ? 2 : 4;
           for (int ks = 0; ks < nks; ++ks) {
-            const uint64_t ad = make_desc(aS + ks * 2 * (TM * 16), TM * 16, 128);
             const uint64_t bd = make_desc(bS + ks * 2 * (HP * 16), HP * 16, 128);
-            mma_ss_tf32(tmem, ad, bd, IDESC_K, (kt | ks) != 0);
+#pragma unroll
+            for (int mb = 0; mb < GEMM_MB; ++mb) {
+              const uint64_t ad = make_desc(aS0 + mb * A_STAGE + ks * 2 * (TM * 16), TM * 16, 128);
+              mma_ss_tf32(tmem + mb * 256, ad, bd, IDESC_K, (kt | ks) != 0);
+            }
           }
         }
         tc_commit(EMPTY(s));
@@ -461,7 +483,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) upd_gemm_kernel(GemmArgs a, int*
   if (tid == 0 && *s_abort) atomicOr(err, 1);
   if (warp == 4) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u * GEMM_MB) : "memory");
   }
 }
 
@@ -565,7 +587,7 @@ __global__ void __launch_bounds__(THIN_THREADS) upd_dz4_kernel(int R, int H, con
 
 // ---- layer-0 weight gradient: dW0[o][f] = sum_r dZ1[r][o] x[r][f], db0[o] = sum_r dZ1[r][o] ----------------------------
 __global__ void __launch_bounds__(THIN_THREADS) upd_wgrad0_kernel(Net net, const float* __restrict__ states, int R,
-                                                                   const float* __restrict__ dZ1,
+                                                                   const float* __restrict__ dH1, const float* __restrict__ H1,
                                                                    float* __restrict__ part_l0) {
   __shared__ float s_acc[3][HP * (MAXF + 1)];
   const int cg = threadIdx.x % 52, rsub = threadIdx.x / 52;
@@ -585,7 +607,12 @@ __global__ void __launch_bounds__(THIN_THREADS) upd_wgrad0_kernel(Net net, const
     for (int u = 0; u < U; ++u) {
       const int r = r0 + 4 * u;
       const bool ok = r < r_end;
-      d[u] = ok ? *(const float4*)(dZ1 + (size_t)r * HP + cg * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      d[u] = ok ? *(const float4*)(dH1 + (size_t)r * HP + cg * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 h = ok ? *(const float4*)(H1 + (size_t)r * HP + cg * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      d[u].x = h.x > 0.f ? d[u].x : 0.f;          // dZ1 = dH1 . [h1 > 0] (the ones column has a zero dH1)
+      d[u].y = h.y > 0.f ? d[u].y : 0.f;
+      d[u].z = h.z > 0.f ? d[u].z : 0.f;
+      d[u].w = h.w > 0.f ? d[u].w : 0.f;
 #pragma unroll
       for (int f = 0; f < MAXF; ++f) x[u][f] = (ok && f < F) ? __ldg(states + (size_t)r * net.F_state + net.col[f]) : 0.f;
       x[u][MAXF] = 1.f;
@@ -896,14 +923,14 @@ extern "C" int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32
   Ws ws;
   carve(E, M, (unsigned char*)workspace, &ws);
   const int R = E * M;
-  const int tiles = (R + TM - 1) / TM;
+  const int tiles = (R + TM * GEMM_MB - 1) / (TM * GEMM_MB);
 
   upd_pack_kernel<<<(6 * IMG_FLOATS + 255) / 256, 256, 0, st>>>(net, ws);
   upd_layer0_kernel<<<4 * THIN_CTAS, THIN_THREADS, 0, st>>>(net, states, R, ws.Hs[0], ws.Hl[0]);
   for (int l = 0; l < 3; ++l) {
     GemmArgs g{};
     g.A = ws.Hs[l]; g.Alo = ws.Hl[l]; g.Bimg = ws.img_fwd[l]; g.Bimg_lo = ws.img_fwl[l]; g.Out = ws.Hs[l + 1];
-    g.OutLo = l < 2 ? ws.Hl[l + 1] : nullptr; g.R = R; g.H = H;
+    g.OutLo = l < 2 ? ws.Hl[l + 1] : nullptr; g.bits_out = l < 2 ? ws.hbits[l] : nullptr; g.R = R; g.H = H;
     if (l == 2) { g.w4 = W[4]; g.b4 = b[4]; g.logits = ws.logits; }
     upd_gemm_kernel<0><<<tiles, GEMM_THREADS, GEMM_SMEM, st>>>(g, ws.err);
   }
@@ -917,7 +944,8 @@ extern "C" int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32
   upd_dz4_kernel<<<THIN_CTAS, THIN_THREADS, 0, st>>>(R, H, ws.Hs[3], ws.dl, W[4], ws.dZ[3], ws.part_head);
   for (int l = 2; l >= 0; --l) {      // dZ_{l+1} = (dZ_{l+2} W_{l+1}) . [h_{l+1} > 0]
     GemmArgs g{};
-    g.A = ws.dZ[l + 1]; g.Bimg = ws.img_dgr[l]; g.Out = ws.dZ[l]; g.mask = ws.Hs[l]; g.R = R; g.H = H;
+    g.A = ws.dZ[l + 1]; g.Bimg = ws.img_dgr[l]; g.Out = ws.dZ[l]; g.bits_in = l > 0 ? ws.hbits[l - 1] : nullptr;   // l = 0: dH1, masked in wgrad0
+    g.R = R; g.H = H;
     upd_gemm_kernel<1><<<tiles, GEMM_THREADS, GEMM_SMEM, st>>>(g, ws.err);
   }
   WgradArgs wa{};
@@ -925,7 +953,7 @@ extern "C" int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32
   wa.part = ws.part_big; wa.R = R; wa.H = H;
 
   upd_wgrad_kernel<<<dim3(WG_SPLIT, 3), GEMM_THREADS, WG_SMEM, st>>>(wa, ws.err);
-  upd_wgrad0_kernel<<<THIN_CTAS, THIN_THREADS, 0, st>>>(net, states, R, ws.dZ[0], ws.part_l0);
+  upd_wgrad0_kernel<<<THIN_CTAS, THIN_THREADS, 0, st>>>(net, states, R, ws.dZ[0], ws.Hs[0], ws.part_l0);
   const int nblkA = (3 * H * (H + 1) + 255) / 256, nblkT = ((H + 1) + H * (F + 1) + 7) / 8;
   upd_reduce_kernel<<<nblkA + nblkT, 256, 0, st>>>(net, ws, THIN_CTAS, nblkA);
   MBO_CUDA(cudaMemcpyAsync(terms, ws.terms, (size_t)E * 16, cudaMemcpyDeviceToDevice, st));

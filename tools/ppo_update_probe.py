@@ -87,7 +87,7 @@ print("dlogits rel err %.3e" % rel(v["dlogits"], logits.grad.reshape(-1)))
 for l in range(3, -1, -1):
     # dZ_l = dh_l * [h_l > 0]
     ref = hs[l].grad * (hs[l].detach() > 0)
-    got = v["dz%d" % (l + 1)]
+    got = v["dz%d" % (l + 1)] * (v["h1"] > 0) if l == 0 else v["dz%d" % (l + 1)]     # l = 0: the kernel stores dH1
     print("dz%d  rel err %.3e   pad cols zero %s" % (l + 1, rel(got[:, :H], ref), bool((got[:, H:] == 0).all())))
 for l in range(5):
     print("dW%d rel err %.3e   db%d rel err %.3e   (max |dW| %.3e)" % (l, rel(dW[l], Ws[l].grad), l, rel(db[l], bs[l].grad),
@@ -103,7 +103,8 @@ with torch.no_grad():
     dz = (dl64[:, None] * W64[4]) * (myh[3] > 0)
     x64 = states.reshape(E * M, F).double()
     for l in range(3, -1, -1):
-        print("  own-mask reference: dz%d rel err %.3e" % (l + 1, rel(v["dz%d" % (l + 1)][:, :H].double(), dz)), end="")
+        gdz = v["dz%d" % (l + 1)] * (v["h1"] > 0) if l == 0 else v["dz%d" % (l + 1)]
+        print("  own-mask reference: dz%d rel err %.3e" % (l + 1, rel(gdz[:, :H].double(), dz)), end="")
         inp = myh[l - 1] if l > 0 else x64
         print("   dW%d %.3e   db%d %.3e" % (l, rel(dW[l].double(), dz.t() @ inp), l, rel(db[l].double(), dz.sum(0))))
         if l > 0:
