@@ -34,17 +34,20 @@ namespace upd {
 
 constexpr int HP = 208;             // padded width: UMMA N, row pitch of H / dZ (floats)
 constexpr int TM = 128;             // rows per output tile (UMMA M)
-constexpr int KT = 32;              // K floats per pipeline stage (dgrad), K rows per stage (wgrad)
-constexpr int NKT = 7;              // ceil(208 / 32)
-constexpr int KT3 = 16;             // forward (3xTF32: hi and lo parts of both operands share a stage)
-constexpr int NKT3 = 13;            // 208 / 16
-constexpr int A_STAGE = TM * KT * 4;          // 16 384 (dgrad: 32 K values; forward: 16 K values x {hi, lo})
-constexpr int B_STAGE = HP * KT * 4;          // 26 624
-constexpr int IMG_FLOATS = NKT * HP * KT;     // 46 592 floats per weight image (forward images use 43 264 of them)
+// The GEMM pipelines are latency-bound (a stage is refilled only after its MMAs completed), so stages are small and
+// many: what counts is the number of stages in flight, 3 of 4 here.
+constexpr int KT = 16;              // K floats per pipeline stage of the dgrad GEMM (two K = 8 MMA steps)
+constexpr int NKT = 13;             // 208 / 16
+constexpr int KT3 = 8;              // forward (3xTF32: hi and lo parts of both operands share a stage; one K = 8 step)
+constexpr int NKT3 = 26;            // 208 / 8
+constexpr int WG_KT = 32;           // K rows per stage of the wgrad GEMM
+constexpr int A_STAGE = TM * KT * 4;          // 8 192 (dgrad: 16 K values; forward: 8 K values x {hi, lo})
+constexpr int B_STAGE = HP * KT * 4;          // 13 312
+constexpr int IMG_FLOATS = NKT * HP * KT;     // 43 264 floats per weight image
 constexpr int STG_PITCH = 36;                 // floats per row of the epilogue's per-warp staging tile (32 + 4: conflict-free)
 constexpr int GEMM_MB = 1;          // 128-row blocks per CTA.  2 (shared weight stages, 3 pipeline stages, 1 CTA/SM) measured SLOWER
                                     // (fwd 71 -> 81 us, dgrad 61 -> 94 us): two co-resident CTAs hide each other's epilogue
-constexpr int GEMM_STAGES = GEMM_MB == 1 ? 2 : 3;
+constexpr int GEMM_STAGES = 4;
 constexpr int GEMM_THREADS = 192;   // warps 0-3: A loaders then epilogue; warp 4: MMA issue; warp 5: weight stages
 constexpr int GEMM_A_STAGE = GEMM_MB * A_STAGE;
 constexpr int GEMM_SMEM = GEMM_STAGES * (GEMM_A_STAGE + B_STAGE) + 256;
@@ -189,7 +192,8 @@ static size_t carve(int E, int M, unsigned char* base, Ws* w) {
 }
 
 // ---- weight images -----------------------------------------------------------------------------------------------
-// K-major canonical, one stage per KT (dgrad) / KT3 (forward) K values: [kt][16-byte K chunk c][n (208)][4 floats].
+// K-major canonical, one stage per KT (dgrad) / KT3 (forward) K values: [kt][16-byte K chunk c][n (208)][4 floats]
+// (4 chunks per dgrad stage, 2 per forward stage).
 // Forward: [W | b] split into tf32 hi and lo parts (3xTF32: hi*hi + lo*hi + hi*lo, fp32-level logits); dgrad: W^T.
 __global__ void upd_pack_kernel(Net net, Ws ws) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -282,7 +286,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) upd_gemm_kernel(GemmArgs a, int*
   unsigned char* sA = smem;
   unsigned char* sB = smem + GEMM_STAGES * GEMM_A_STAGE;
   uint64_t* bars = (uint64_t*)(smem + GEMM_STAGES * (GEMM_A_STAGE + B_STAGE));
-  uint32_t* s_tmem = (uint32_t*)(bars + 8);
+  uint32_t* s_tmem = (uint32_t*)(bars + 2 * GEMM_STAGES + 2);
   volatile int* s_abort = (volatile int*)(s_tmem + 1);
   __shared__ float s_w4[HP];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -320,23 +324,17 @@ __global__ void __launch_bounds__(GEMM_THREADS) upd_gemm_kernel(GemmArgs a, int*
         const uint32_t dstA = smem_u32(sA + s * GEMM_A_STAGE + mb * A_STAGE);
         const int brow0 = row0 + mb * TM;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int j = warp * 8 + i;
+        for (int i = 0; i < 4; ++i) {
+          const int j = warp * 4 + i;
+          const int grow = brow0 + j * 8 + r8;               // j = 8-row group
+          const bool ok = grow < a.R;
           if (X3) {
-            const int arr = j >> 4, group = j & 15;          // hi rows, then lo rows; 4 chunks = the whole K tile
-            const int grow = brow0 + group * 8 + r8;
-            const bool ok = grow < a.R;
-            const float* src = (arr ? a.Alo : a.A) + (size_t)(ok ? grow : 0) * HP + kt * KT_ + cq * 4;
-            cp_async16(dstA + arr * (TM * KT3 * 4) + cq * (TM * 16) + group * 128 + r8 * 16, src, ok);
+            const int arr = cq >> 1, c = cq & 1;               // lanes 0-15: hi part, 16-31: lo part; 2 chunks = the K tile
+            const float* src = (arr ? a.Alo : a.A) + (size_t)(ok ? grow : 0) * HP + kt * KT_ + c * 4;
+            cp_async16(dstA + arr * (TM * KT3 * 4) + c * (TM * 16) + j * 128 + r8 * 16, src, ok);
           } else {
-            const int group = j >> 1, chalf = j & 1;
-            if (kt < NKT_ - 1 || chalf == 0) {                 // the last K tile holds columns 192..207 only
-              const int c = chalf * 4 + cq;
-              const int grow = brow0 + group * 8 + r8;
-              const bool ok = grow < a.R;
-              const float* src = a.A + (size_t)(ok ? grow : 0) * HP + kt * KT_ + c * 4;
-              cp_async16(dstA + c * (TM * 16) + group * 128 + r8 * 16, src, ok);
-            }
+            const float* src = a.A + (size_t)(ok ? grow : 0) * HP + kt * KT_ + cq * 4;
+            cp_async16(dstA + cq * (TM * 16) + j * 128 + r8 * 16, src, ok);
           }
         }
       }
@@ -432,23 +430,20 @@ __global__ void __launch_bounds__(GEMM_THREADS) upd_gemm_kernel(GemmArgs a, int*
         tc_fence_after();
         const uint32_t aS0 = smem_u32(sA + s * GEMM_A_STAGE), bS = smem_u32(sB + s * B_STAGE);
         if (X3) {
+          const uint64_t bh = make_desc(bS, HP * 16, 128);
+          const uint64_t bl = make_desc(bS + HP * KT3 * 4, HP * 16, 128);
 #pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {
-            const uint64_t bh = make_desc(bS + ks * 2 * (HP * 16), HP * 16, 128);
-            const uint64_t bl = make_desc(bS + HP * KT3 * 4 + ks * 2 * (HP * 16), HP * 16, 128);
-#pragma unroll
-            for (int mb = 0; mb < GEMM_MB; ++mb) {
-              const uint32_t aS = aS0 + mb * A_STAGE;
-              const uint64_t ah = make_desc(aS + ks * 2 * (TM * 16), TM * 16, 128);
-              const uint64_t al = make_desc(aS + TM * KT3 * 4 + ks * 2 * (TM * 16), TM * 16, 128);
-              mma_ss_tf32(tmem + mb * 256, al, bh, IDESC_K, (kt | ks) != 0);        // small terms first
-              mma_ss_tf32(tmem + mb * 256, ah, bl, IDESC_K, 1);
-              mma_ss_tf32(tmem + mb * 256, ah, bh, IDESC_K, 1);
-            }
+          for (int mb = 0; mb < GEMM_MB; ++mb) {
+            const uint32_t aS = aS0 + mb * A_STAGE;
+            const uint64_t ah = make_desc(aS, TM * 16, 128);
+            const uint64_t al = make_desc(aS + TM * KT3 * 4, TM * 16, 128);
+            mma_ss_tf32(tmem + mb * 256, al, bh, IDESC_K, kt != 0);        // small terms first
+            mma_ss_tf32(tmem + mb * 256, ah, bl, IDESC_K, 1);
+            mma_ss_tf32(tmem + mb * 256, ah, bh, IDESC_K, 1);
           }
         } else {
-          const int nks = kt == NKT_ - 1 ? 2 : 4;
-          for (int ks = 0; ks < nks; ++ks) {
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
             const uint64_t bd = make_desc(bS + ks * 2 * (HP * 16), HP * 16, 128);
 #pragma unroll
             for (int mb = 0; mb < GEMM_MB; ++mb) {
@@ -673,7 +668,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) upd_wgrad_kernel(WgradArgs a, in
   volatile int* s_abort = (volatile int*)(s_tmem + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int split = blockIdx.x, li = blockIdx.y;
-  const int nk_total = (a.R + KT - 1) / KT;
+  const int nk_total = (a.R + WG_KT - 1) / WG_KT;
   const int per = (nk_total + (int)gridDim.x - 1) / (int)gridDim.x;
   const int kt0 = split * per, kt1 = min(nk_total, kt0 + per);
   const int nk = max(0, kt1 - kt0);
@@ -713,7 +708,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) upd_wgrad_kernel(WgradArgs a, in
       const int s = it % WG_STAGES, u = it / WG_STAGES;
       if (u > 0) mbar_wait(EMPTY(s), (u - 1) & 1, s_abort);
       const uint32_t dA = smem_u32(sA + s * WG_A_STAGE), dB = smem_u32(sB + s * WG_B_STAGE);
-      const int krow0 = (kt0 + it) * KT;
+      const int krow0 = (kt0 + it) * WG_KT;
 #pragma unroll 4
       for (int i = 0; i < 28; ++i) {
         int q = warp * 28 + i;                     // 0..111: operand (2) x column block (7) x atom (8)

@@ -72,7 +72,7 @@ def _check_against_oracle(E, M, cols, H, layers, states, actions, advs, logp_old
         assert _rel(dW[l], own["dW"][l]) <= grad_tol, ("dW", l, _rel(dW[l], own["dW"][l]))
         scale = float(own["db"][l].abs().max())
         if l < 4:           # db4 = sum of dlogits = 0 analytically: only rounding noise is left
-            assert _rel(db[l], own["db"][l]) <= grad_tol, ("db", l)
+            assert _rel(db[l], own["db"][l]) <= grad_tol, ("db", l, _rel(db[l], own["db"][l]))
         else:
             assert float((db[l].double() - own["db"][l]).abs().max()) <= 1e-4 * float(ref["dlogits"].abs().sum()) + 1e-12
     # against the exact autograd gradient: direction
