@@ -107,6 +107,10 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// whole-range L2 prefetch: DRAM sees one sequential burst instead of the pipeline's strided 32-byte pieces
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 // 16-byte asynchronous copy, zero-filled when `valid` is false (src must still be a mapped address)
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
   const uint32_t n = valid ? 16u : 0u;
@@ -270,6 +274,7 @@ struct GemmArgs {
   const float* b4;
   float* logits;         // [R]
   int R, H;
+  int dbg;               // timing experiments (MBO_UPD_DBG): 1 no epilogue, 2 no MMAs, 4 no A loads, 8 no weight loads
 };
 
 // EPI 0: forward, 3xTF32 (stage = 16 K values x {hi, lo} of both operands, 3 MMAs per K = 8 step), epilogue ReLU +
@@ -328,6 +333,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) upd_gemm_kernel(GemmArgs a, int*
           const int j = warp * 4 + i;
           const int grow = brow0 + j * 8 + r8;               // j = 8-row group
           const bool ok = grow < a.R;
+          if (a.dbg & 4) continue;
           if (X3) {
             const int arr = cq >> 1, c = cq & 1;               // lanes 0-15: hi part, 16-31: lo part; 2 chunks = the K tile
             const float* src = (arr ? a.Alo : a.A) + (size_t)(ok ? grow : 0) * HP + kt * KT_ + c * 4;
@@ -362,7 +368,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) upd_gemm_kernel(GemmArgs a, int*
 #pragma unroll 1
     for (int mb = 0; mb < GEMM_MB; ++mb) {
     const int wrow0 = row0 + mb * TM + warp * 32;
-    if (wrow0 >= a.R) break;                                         // warp-uniform: nothing to store for these rows
+    if (wrow0 >= a.R || (a.dbg & 1)) break;                                         // warp-uniform: nothing to store for these rows
     const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16) + mb * 256;
     float head = 0.f;
 #pragma unroll 1
@@ -429,7 +435,8 @@ __global__ void __launch_bounds__(GEMM_THREADS) upd_gemm_kernel(GemmArgs a, int*
         mbar_wait(FULL(s), u & 1, s_abort);
         tc_fence_after();
         const uint32_t aS0 = smem_u32(sA + s * GEMM_A_STAGE), bS = smem_u32(sB + s * B_STAGE);
-        if (X3) {
+        if (a.dbg & 2) {
+        } else if (X3) {
           const uint64_t bh = make_desc(bS, HP * 16, 128);
           const uint64_t bl = make_desc(bS + HP * KT3 * 4, HP * 16, 128);
 #pragma unroll
@@ -458,11 +465,25 @@ __global__ void __launch_bounds__(GEMM_THREADS) upd_gemm_kernel(GemmArgs a, int*
     }
     __syncwarp();
   } else {
+    // ---- the CTA's A tile is one contiguous block of rows (pitch = row length): pull it into L2 in 16-row pieces.
+    // The pipeline reads 32 (forward) or 64 bytes per row and stage, i.e. every DRAM page of the tile 26 / 13 times
+    // over; without this the kernel ran at ~1.3 TB/s of DRAM reads ----
+    {
+      const int piece = lane & 7, arr = lane >> 3;                 // arr 0: A, 1: Alo (forward only)
+      const int r_lo = row0 + piece * 16 * GEMM_MB;
+      const int nrow = min(16 * GEMM_MB, a.R - r_lo);
+      if (nrow > 0 && (arr == 0 || (X3 && arr == 1)))
+        bulk_prefetch_l2((arr ? a.Alo : a.A) + (size_t)r_lo * HP, (uint32_t)nrow * HP * 4);
+    }
     // ---- weight stages: bulk copies of the packed images ----
     if (lane == 0) {
       for (int kt = 0; kt < NKT_; ++kt) {
         const int s = kt % GEMM_STAGES, u = kt / GEMM_STAGES;
         if (u > 0) mbar_wait(EMPTY(s), (u - 1) & 1, s_abort);
+        if (a.dbg & 8) {
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(FULL(s)) : "memory");
+          continue;
+        }
         mbar_expect_tx(FULL(s), B_STAGE);
         if (X3) {
           bulk_g2s(smem_u32(sB + s * B_STAGE), a.Bimg + (size_t)kt * (HP * KT3), HP * KT3 * 4, FULL(s));
@@ -919,13 +940,15 @@ extern "C" int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32
   carve(E, M, (unsigned char*)workspace, &ws);
   const int R = E * M;
   const int tiles = (R + TM * GEMM_MB - 1) / (TM * GEMM_MB);
+  const char* dbg_env = getenv("MBO_UPD_DBG");
+  const int dbg = dbg_env ? atoi(dbg_env) : 0;
 
   upd_pack_kernel<<<(6 * IMG_FLOATS + 255) / 256, 256, 0, st>>>(net, ws);
   upd_layer0_kernel<<<4 * THIN_CTAS, THIN_THREADS, 0, st>>>(net, states, R, ws.Hs[0], ws.Hl[0]);
   for (int l = 0; l < 3; ++l) {
     GemmArgs g{};
     g.A = ws.Hs[l]; g.Alo = ws.Hl[l]; g.Bimg = ws.img_fwd[l]; g.Bimg_lo = ws.img_fwl[l]; g.Out = ws.Hs[l + 1];
-    g.OutLo = l < 2 ? ws.Hl[l + 1] : nullptr; g.bits_out = l < 2 ? ws.hbits[l] : nullptr; g.R = R; g.H = H;
+    g.OutLo = l < 2 ? ws.Hl[l + 1] : nullptr; g.bits_out = l < 2 ? ws.hbits[l] : nullptr; g.R = R; g.H = H; g.dbg = dbg;
     if (l == 2) { g.w4 = W[4]; g.b4 = b[4]; g.logits = ws.logits; }
     upd_gemm_kernel<0><<<tiles, GEMM_THREADS, GEMM_SMEM, st>>>(g, ws.err);
   }
@@ -940,7 +963,7 @@ extern "C" int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32
   for (int l = 2; l >= 0; --l) {      // dZ_{l+1} = (dZ_{l+2} W_{l+1}) . [h_{l+1} > 0]
     GemmArgs g{};
     g.A = ws.dZ[l + 1]; g.Bimg = ws.img_dgr[l]; g.Out = ws.dZ[l]; g.bits_in = l > 0 ? ws.hbits[l - 1] : nullptr;   // l = 0: dH1, masked in wgrad0
-    g.R = R; g.H = H;
+    g.R = R; g.H = H; g.dbg = dbg;
     upd_gemm_kernel<1><<<tiles, GEMM_THREADS, GEMM_SMEM, st>>>(g, ws.err);
   }
   WgradArgs wa{};
