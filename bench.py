@@ -221,6 +221,67 @@ def ppo_rollout_rate(dev, world, rank):
                       "CUDA-graph replay of the episode loop, transitions kept on device without states"}
 
 
+def ppo_update_rate(dev):
+    """Supplementary: one PPO optimiser step's policy-net forward + backward on a train_metabo_branin.py minibatch
+    (60 transitions x 966 candidates, 4x200 ReLU policy): the hand-written kernels behind mbo_ppo_policy_grad
+    (3xTF32 forward, TF32 backward) timed with CUDA events, next to torch's fp32 autograd of the same loss."""
+    import torch
+    from metabo_b200 import ops
+    E, M, F, H = 60, 966, 6, 200
+    g = torch.Generator().manual_seed(0)
+    dims = [F, H, H, H, H, 1]
+    W = [(torch.randn(dims[i + 1], dims[i], generator=g) * 0.08).to(dev).requires_grad_() for i in range(5)]
+    b = [(torch.randn(dims[i + 1], generator=g) * 0.05).to(dev).requires_grad_() for i in range(5)]
+    st = torch.randn(E, M, F, generator=g).to(dev)
+    ac = torch.randint(0, M, (E,), generator=g).to(dev)
+    adv = torch.randn(E, generator=g).to(dev)
+    pg = ops.PPOPolicyGrad(E, M, F, list(range(F)), H, dev)
+    Wd, bd = [w.detach() for w in W], [x.detach() for x in b]
+    dW, db = [torch.zeros_like(w) for w in Wd], [torch.zeros_like(x) for x in bd]
+    a32 = ac.to(torch.int32)
+    lpo, _ = pg.logp_entropy(st, Wd, bd, a32)
+
+    def native():
+        pg(st, Wd, bd, a32, adv, lpo, 0.15, 0.01, E, dW, db)
+
+    def autograd():
+        for p_ in W + b:
+            p_.grad = None
+        h = st.reshape(E * M, F)
+        for l in range(4):
+            h = torch.relu(h @ W[l].t() + b[l])
+        logits = (h @ W[4].t() + b[4]).reshape(E, M)
+        norm = logits - torch.logsumexp(logits, -1, keepdim=True)
+        lp = norm.gather(-1, ac[:, None]).squeeze(-1)
+        ent = -(norm * norm.exp()).sum(-1)
+        ratio = torch.exp(lp - lpo)
+        loss = -torch.min(ratio * adv, ratio.clamp(0.85, 1.15) * adv).sum() / E - 0.01 * ent.sum() / E
+        loss.backward()
+
+    def timeit(fn, n):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / n
+
+    prec = torch.get_float32_matmul_precision()
+    torch.set_float32_matmul_precision("highest")
+    t_nat, t_ref = timeit(native, 30), timeit(autograd, 10)
+    torch.set_float32_matmul_precision(prec)
+    pg.check()
+    flops = 3 * 2 * E * M * (F * H + 3 * H * H + H)
+    return {"policy_grad_ms": t_nat, "algorithmic_tflops": flops / t_nat / 1e9, "torch_fp32_autograd_ms": t_ref,
+            "launches_per_step": 13,
+            "config": "train_metabo_branin.py minibatch (C3): 60 x 966 candidates, F=6, 4x200 ReLU policy; forward 3xTF32 "
+                      "(fp32-level logits), backward single-pass TF32, deterministic split-K"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -396,8 +457,11 @@ def main():
     e2e_val = world * cands_step * args.steps / (ms_e / 1e3)
 
     ppo_info = None
+    upd_info = None
     if not args.no_ppo:
         ppo_info = ppo_rollout_rate(dev, world, rank)
+        if rank == 0:
+            upd_info = ppo_update_rate(dev)
 
     cpu_b = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -414,7 +478,7 @@ def main():
                 "config": workload_config(args, B), "clocks": clocks,
                 "e2e": {"value": e2e_val, "unit": "AF evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e / args.steps},
-                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu_b, "ppo_rollout": ppo_info}
+                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu_b, "ppo_rollout": ppo_info, "ppo_update": upd_info}
         eng.policy.check()            # raises if a tensor-core kernel timed out or the fp16 mode clamped an activation
         print(json.dumps(line))
     if world > 1:

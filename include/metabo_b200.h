@@ -248,10 +248,12 @@ int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32_t* feat_co
 /* Adam step (ppo.py:93, torch.optim.Adam defaults: no weight decay, no amsgrad) over n <= 32 parameter tensors in
  * one launch: m = lerp(m, g, 1 - beta1); v = beta2 v + (1 - beta2) g^2; p -= lr / (1 - beta1^t) * m /
  * (sqrt(v) / sqrt(1 - beta2^t) + eps).  p, g, m, v: HOST arrays of n device pointers (fp32), sizes: HOST array of
- * element counts.  state: 3 x 8 bytes on the device {int64 step t, double, double}, zero-initialised by the caller;
- * the call advances t on the device, so a captured CUDA graph of the step can be replayed. */
+ * element counts.  state: HOST array of n device pointers, each to 3 x 8 bytes {int64 step t, double, double},
+ * zero-initialised by the caller (one step count per tensor, as torch keeps it); the call advances t on the device,
+ * so a captured CUDA graph of the step can be replayed. */
 int mbo_adam_step(int n, float* const* p, const float* const* g, float* const* m, float* const* v,
-                  const int64_t* sizes, int64_t* state, float lr, float beta1, float beta2, float eps, void* stream);
+                  const int64_t* sizes, int64_t* const* state, float lr, float beta1, float beta2, float eps,
+                  void* stream);
 
 #ifdef __cplusplus
 }

@@ -58,7 +58,8 @@ SYMBOLS = [
     ("mbo_ppo_debug_offsets", _i, [_i, _i, C.POINTER(_sz)]),
     ("mbo_ppo_policy_grad", _i, [_i, _i, _i, _i, C.POINTER(C.c_int32), _i, _vp, C.POINTER(_vp), C.POINTER(_vp), _vp, _vp,
                                  _vp, C.c_float, C.c_float, C.c_float, C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _sz, _vp]),
-    ("mbo_adam_step", _i, [_i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_int64), _vp,
+    ("mbo_adam_step", _i, [_i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_int64),
+                           C.POINTER(_vp),
                            C.c_float, C.c_float, C.c_float, C.c_float, _vp]),
 ]
 

@@ -850,23 +850,28 @@ struct AdamArgs {
   float* m[ADAM_MAX_TENSORS];
   float* v[ADAM_MAX_TENSORS];
   long long end[ADAM_MAX_TENSORS];     // exclusive prefix end of tensor t in the flat index space
+  long long* st[ADAM_MAX_TENSORS];     // per-tensor state {step, 1 - beta1^step, 1 - beta2^step}
   int n;
 };
-// state = {step (int64), 1 - beta1^step (double), 1 - beta2^step (double)} on the device: a replayed CUDA graph advances it
-__global__ void adam_tick_kernel(long long* state, double beta1, double beta2) {
+// per-tensor state = {step (int64), 1 - beta1^step (double), 1 - beta2^step (double)} on the device (torch keeps one step
+// per parameter: a tensor without a gradient does not advance); a replayed CUDA graph advances it
+__global__ void adam_tick_kernel(AdamArgs a, double beta1, double beta2) {
+  const int i = threadIdx.x;
+  if (i >= a.n) return;
+  long long* state = a.st[i];
   const long long t = state[0] + 1;
   state[0] = t;
   ((double*)state)[1] = 1.0 - pow(beta1, (double)t);
   ((double*)state)[2] = 1.0 - pow(beta2, (double)t);
 }
-__global__ void __launch_bounds__(256) adam_step_kernel(AdamArgs a, const long long* __restrict__ state, float lr, float beta1,
-                                                         float beta2, float eps) {
+__global__ void __launch_bounds__(256) adam_step_kernel(AdamArgs a, float lr, float beta1, float beta2, float eps) {
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   if (i >= a.end[a.n - 1]) return;
   int t = 0;
   while (i >= a.end[t]) ++t;
   const long long j = i - (t ? a.end[t - 1] : 0);
-  const float bc1 = (float)((const double*)state)[1], bc2s = (float)sqrt(((const double*)state)[2]);
+  const double* state = (const double*)a.st[t];
+  const float bc1 = (float)state[1], bc2s = (float)sqrt(state[2]);
   const float g = a.g[t][j];
   const float m = a.m[t][j] + (g - a.m[t][j]) * (1.f - beta1);        // exp_avg.lerp_(grad, 1 - beta1)
   const float v = a.v[t][j] * beta2 + (1.f - beta2) * g * g;
@@ -980,22 +985,22 @@ extern "C" int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32
 }
 
 extern "C" int mbo_adam_step(int n, float* const* p, const float* const* g, float* const* m, float* const* v,
-                             const int64_t* sizes, int64_t* state, float lr, float beta1, float beta2, float eps,
+                             const int64_t* sizes, int64_t* const* state, float lr, float beta1, float beta2, float eps,
                              void* stream) {
   MBO_CHECK_ARG(n >= 1 && n <= ADAM_MAX_TENSORS, "mbo_adam_step: 1..%d tensors per call", ADAM_MAX_TENSORS);
   MBO_CHECK_ARG(p && g && m && v && sizes && state, "mbo_adam_step: null pointer");
   AdamArgs a;
   long long tot = 0;
   for (int t = 0; t < n; ++t) {
-    MBO_CHECK_ARG(p[t] && g[t] && m[t] && v[t] && sizes[t] > 0, "mbo_adam_step: null / empty tensor %d", t);
-    a.p[t] = p[t]; a.g[t] = g[t]; a.m[t] = m[t]; a.v[t] = v[t];
+    MBO_CHECK_ARG(p[t] && g[t] && m[t] && v[t] && state[t] && sizes[t] > 0, "mbo_adam_step: null / empty tensor %d", t);
+    a.p[t] = p[t]; a.g[t] = g[t]; a.m[t] = m[t]; a.v[t] = v[t]; a.st[t] = (long long*)state[t];
     tot += sizes[t];
     a.end[t] = tot;
   }
   a.n = n;
   cudaStream_t st = (cudaStream_t)stream;
-  adam_tick_kernel<<<1, 1, 0, st>>>((long long*)state, (double)beta1, (double)beta2);
-  adam_step_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(a, (const long long*)state, lr, beta1, beta2, eps);
+  adam_tick_kernel<<<1, ADAM_MAX_TENSORS, 0, st>>>(a, (double)beta1, (double)beta2);
+  adam_step_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(a, lr, beta1, beta2, eps);
   MBO_LAUNCH_CHECK();
   return MBO_OK;
 }

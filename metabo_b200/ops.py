@@ -367,12 +367,11 @@ class PPOPolicyGrad:
 
 class FusedAdam(torch.optim.Optimizer):
     """torch.optim.Adam(params, lr) semantics (ppo.py:93: default betas / eps, no weight decay, no amsgrad) with the
-    whole step in one kernel launch (`mbo_adam_step`); the step counter lives on the device, so a captured CUDA graph of
-    the step can be replayed.  state[p] has torch's keys: step (shared device int64), exp_avg, exp_avg_sq."""
+    whole step in one kernel launch (`mbo_adam_step`); the step counters live on the device, so a captured CUDA graph of
+    the step can be replayed.  state[p] has torch's keys: step (device int64, one per parameter), exp_avg, exp_avg_sq."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
-        self._state_dev = None
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -381,12 +380,11 @@ class FusedAdam(torch.optim.Optimizer):
             ps = [p for p in group["params"] if p.grad is not None]
             if not ps:
                 continue
-            if self._state_dev is None:
-                self._state_dev = torch.zeros(3, dtype=torch.int64, device=ps[0].device)
             for p in ps:
                 st = self.state[p]
                 if not st:
-                    st["step"] = self._state_dev[0:1]
+                    st["_dev"] = torch.zeros(3, dtype=torch.int64, device=p.device)     # step, 1 - b1^t, 1 - b2^t (doubles)
+                    st["step"] = st["_dev"][0:1]
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 _chk(p.data, torch.float32, "parameter"); _chk(p.grad, torch.float32, "gradient")
@@ -396,7 +394,8 @@ class FusedAdam(torch.optim.Optimizer):
             b1, b2 = group["betas"]
             L.check(L.lib().mbo_adam_step(n, arr([p.data for p in ps]), arr([p.grad for p in ps]),
                                           arr([self.state[p]["exp_avg"] for p in ps]),
-                                          arr([self.state[p]["exp_avg_sq"] for p in ps]), sizes, _p(self._state_dev),
+                                          arr([self.state[p]["exp_avg_sq"] for p in ps]), sizes,
+                                          arr([self.state[p]["_dev"] for p in ps]),
                                           float(group["lr"]), float(b1), float(b2), float(group["eps"]), _stream()),
                     "mbo_adam_step")
         return None
