@@ -50,11 +50,15 @@ for it in range(iters):
         continue
     ref = ops.af_logits(pol, codes, cs, mean, std, epi, B, mode=L.MLP_FP32)
     scale = float(ref.abs().max()) + 1e-30
+    # a random net's logits can cancel to ~0 (max |logit| 0.04 with O(1) hidden activations): the 11-bit modes are then
+    # judged on the scale of the head layer's terms, not of their cancelled sum
+    w_head = pol._keep[0][-1]
+    scale11 = max(scale, 0.02 * float(w_head.abs().sum()))
     for name, mode, tol in (("fp16", L.MLP_FP16, 2e-2), ("tf32", L.MLP_TF32, 2e-2), ("bf16x3", L.MLP_BF16X3, 1e-3)):
         got = ops.af_logits(pol, codes, cs, mean, std, epi, B, mode=mode)
         got2 = ops.af_logits(pol, codes, cs, mean, std, epi, B, mode=mode)
         torch.cuda.synchronize(); pol.check()
-        err = float((got - ref).abs().max()) / scale
+        err = float((got - ref).abs().max()) / (scale if name == "bf16x3" else scale11)
         if only >= 0:
             d = (got - ref).abs()
             idx = int(d.argmax())
