@@ -245,6 +245,19 @@ int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32_t* feat_co
                         float ent_coeff, float inv_n_global, float* const* dW, float* const* db,
                         float* terms, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Value-net half of the optimiser step: forward + backward of value_coeff * mean((vpreds - tdlamrets)^2)
+ * (ppo.py:150-156) for the 2 -> Hv -> Hv -> Hv -> Hv -> 1 ReLU value net of policies.py:87-92, whose inputs are
+ * states[e, 0, t_col] and states[e, 0, T_col] (policies.py:116-121); fp32 CUDA cores.
+ *   states       device pointer to the minibatch states, state_stride = floats between consecutive transitions (M * F)
+ *   coeff        value_coeff / (global minibatch size)
+ *   dW, db       gradients (overwritten); values [E] = vpreds; vterms [E] = (vpreds - tdlamrets)^2
+ *   workspace    mbo_ppo_value_workspace_bytes(E, Hv) bytes */
+size_t mbo_ppo_value_workspace_bytes(int E, int Hv);
+int mbo_ppo_value_grad(int E, size_t state_stride, int t_col, int T_col, int Hv, const float* states,
+                       const float* const* W, const float* const* b, const float* tdlamrets, float coeff,
+                       float* const* dW, float* const* db, float* values, float* vterms, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
 /* Adam step (ppo.py:93, torch.optim.Adam defaults: no weight decay, no amsgrad) over n <= 32 parameter tensors in
  * one launch: m = lerp(m, g, 1 - beta1); v = beta2 v + (1 - beta2) g^2; p -= lr / (1 - beta1^t) * m /
  * (sqrt(v) / sqrt(1 - beta2^t) + eps).  p, g, m, v: HOST arrays of n device pointers (fp32), sizes: HOST array of

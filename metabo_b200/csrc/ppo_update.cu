@@ -1004,3 +1004,164 @@ extern "C" int mbo_adam_step(int n, float* const* p, const float* const* g, floa
   MBO_LAUNCH_CHECK();
   return MBO_OK;
 }
+
+// ======================================================================================================================
+// Value-net half of the optimiser step (ppo.py:150-156: loss_value = mean((vpreds - tdlamrets)^2), policies.py:116-121:
+// value net on states[:, 0, [t_idx, T_idx]]).  E rows x (2 -> Hv -> Hv -> Hv -> Hv -> 1): 40 MFLOP, CUDA cores, fp32,
+// 15 small launches (forward x5, loss, wgrad x5, dgrad x4) instead of ~45 torch kernels.
+// ======================================================================================================================
+namespace mbo {
+namespace upd {
+
+constexpr int V_MAXH = 256;
+
+// out[e][j] = act(b[j] + sum_k in[e][k] W[j][k]).  One warp per (4 rows, 1 output column): lanes split K (coalesced
+// reads of the W row and of the activation rows), xor-tree sum.  Layer 0 reads its two inputs from the state tensor
+// (row 0 of every episode's state matrix, columns c0 / c1).
+__global__ void __launch_bounds__(256) v_fwd_kernel(int E, int Kin, int Hout, const float* __restrict__ in, size_t in_stride,
+                                                     int c0, int c1, const float* __restrict__ W, const float* __restrict__ b,
+                                                     float* __restrict__ out, int relu) {
+  const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int n_eg = (E + 3) >> 2;
+  if (warp >= n_eg * Hout) return;
+  const int j = warp / n_eg, e0 = (warp - j * n_eg) * 4;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c0 >= 0) {
+    if (lane < 2) {
+      const float w = W[(size_t)j * 2 + lane];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        if (e0 + r < E) acc[r] = in[(size_t)(e0 + r) * in_stride + (lane ? c1 : c0)] * w;
+    }
+  } else {
+    for (int k = lane; k < Kin; k += 32) {
+      const float w = W[(size_t)j * Kin + k];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        if (e0 + r < E) acc[r] = fmaf(in[(size_t)(e0 + r) * in_stride + k], w, acc[r]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+    for (int o = 16; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+  if (lane < 4 && e0 + lane < E) {
+    const float v = (lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3]) + b[j];
+    out[(size_t)(e0 + lane) * Hout + j] = relu ? fmaxf(v, 0.f) : v;
+  }
+}
+
+// dv[e] = 2 (v[e] - ret[e]) * coeff (coeff = value_coeff / n_global), vterms[e] = (v - ret)^2
+__global__ void v_loss_kernel(int E, const float* __restrict__ v, const float* __restrict__ ret, float coeff,
+                              float* __restrict__ dv, float* __restrict__ values, float* __restrict__ vterms) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const float d = v[e] - ret[e];
+  dv[e] = 2.f * d * coeff;
+  values[e] = v[e];
+  vterms[e] = d * d;
+}
+
+// dIn[e][i] = [h[e][i] > 0] * sum_o dZ[e][o] W[o][i].  One warp per (2 rows, 32 input columns): lane = column
+// (coalesced W rows), dZ broadcast, four independent chains over o.
+__global__ void __launch_bounds__(256) v_dgrad_kernel(int E, int Kin, int Hout, const float* __restrict__ dZ,
+                                                       const float* __restrict__ W, const float* __restrict__ h,
+                                                       float* __restrict__ dIn) {
+  const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int n_ig = (Kin + 31) >> 5, n_eg = (E + 1) >> 1;
+  if (warp >= n_ig * n_eg) return;
+  const int eg = warp / n_ig, i = (warp - eg * n_ig) * 32 + lane;
+  const int e0 = eg * 2, e1 = min(e0 + 1, E - 1);
+  const bool ok = i < Kin;
+  const float* z0 = dZ + (size_t)e0 * Hout;
+  const float* z1 = dZ + (size_t)e1 * Hout;
+  float a0[2] = {0.f, 0.f}, a1[2] = {0.f, 0.f};
+  int o = 0;
+  for (; o + 1 < Hout; o += 2) {
+    const float w0 = ok ? W[(size_t)o * Kin + i] : 0.f, w1 = ok ? W[(size_t)(o + 1) * Kin + i] : 0.f;
+    a0[0] = fmaf(z0[o], w0, a0[0]); a0[1] = fmaf(z0[o + 1], w1, a0[1]);
+    a1[0] = fmaf(z1[o], w0, a1[0]); a1[1] = fmaf(z1[o + 1], w1, a1[1]);
+  }
+  if (o < Hout) {
+    const float w0 = ok ? W[(size_t)o * Kin + i] : 0.f;
+    a0[0] = fmaf(z0[o], w0, a0[0]);
+    a1[0] = fmaf(z1[o], w0, a1[0]);
+  }
+  if (ok) {
+    dIn[(size_t)e0 * Kin + i] = h[(size_t)e0 * Kin + i] > 0.f ? a0[0] + a0[1] : 0.f;
+    if (e0 + 1 < E) dIn[(size_t)(e0 + 1) * Kin + i] = h[(size_t)(e0 + 1) * Kin + i] > 0.f ? a1[0] + a1[1] : 0.f;
+  }
+}
+
+// dW[o][i] = sum_e dZ[e][o] in[e][i], db[o] = sum_e dZ[e][o]; one thread per (o, i), four independent chains over e
+__global__ void __launch_bounds__(256) v_wgrad_kernel(int E, int Kin, int Hout, const float* __restrict__ dZ,
+                                                       const float* __restrict__ in, size_t in_stride, int c0, int c1,
+                                                       float* __restrict__ dW, float* __restrict__ db) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= Hout * Kin) return;
+  const int o = idx / Kin, i = idx - o * Kin;
+  const int col = c0 >= 0 ? (i == 0 ? c0 : c1) : i;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f}, accb[4] = {0.f, 0.f, 0.f, 0.f};
+  int e = 0;
+  for (; e + 3 < E; e += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float d = dZ[(size_t)(e + u) * Hout + o];
+      acc[u] = fmaf(d, in[(size_t)(e + u) * in_stride + col], acc[u]);
+      accb[u] += d;
+    }
+  }
+  for (; e < E; ++e) {
+    const float d = dZ[(size_t)e * Hout + o];
+    acc[0] = fmaf(d, in[(size_t)e * in_stride + col], acc[0]);
+    accb[0] += d;
+  }
+  dW[idx] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  if (i == 0) db[o] = (accb[0] + accb[1]) + (accb[2] + accb[3]);
+}
+
+}  // namespace upd
+}  // namespace mbo
+
+extern "C" size_t mbo_ppo_value_workspace_bytes(int E, int Hv) {
+  if (E <= 0 || Hv <= 0) return 0;
+  return (size_t)6 * E * Hv * 4 + 2 * (size_t)E * 4 + 1024;
+}
+
+extern "C" int mbo_ppo_value_grad(int E, size_t state_stride, int t_col, int T_col, int Hv, const float* states,
+                                  const float* const* W, const float* const* b, const float* tdlamrets, float coeff,
+                                  float* const* dW, float* const* db, float* values, float* vterms, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  MBO_CHECK_ARG(E > 0 && Hv >= 1 && Hv <= V_MAXH, "mbo_ppo_value_grad: E > 0, hidden width 1..%d", V_MAXH);
+  MBO_CHECK_ARG(states && W && b && tdlamrets && dW && db && values && vterms && workspace, "mbo_ppo_value_grad: null pointer");
+  MBO_CHECK_ARG(t_col >= 0 && T_col >= 0 && (size_t)t_col < state_stride && (size_t)T_col < state_stride,
+                "mbo_ppo_value_grad: t / T column outside the state row");
+  MBO_CHECK_ARG(workspace_bytes >= mbo_ppo_value_workspace_bytes(E, Hv), "mbo_ppo_value_grad: workspace too small");
+  for (int l = 0; l < 5; ++l) MBO_CHECK_ARG(W[l] && b[l] && dW[l] && db[l], "mbo_ppo_value_grad: null layer pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* base = (float*)workspace;
+  float* h[4];
+  for (int l = 0; l < 4; ++l) h[l] = base + (size_t)l * E * Hv;
+  float* dz[2] = {base + (size_t)4 * E * Hv, base + (size_t)5 * E * Hv};
+  float* v = base + (size_t)6 * E * Hv;
+  float* dv = v + E;
+  using namespace mbo::upd;
+  const int n_eg4 = (E + 3) / 4;
+  const int gF = (n_eg4 * Hv + 7) / 8, gF1 = (n_eg4 + 7) / 8;             // 8 warps per CTA, one warp per (4 rows, column)
+  const int gD = (((Hv + 31) / 32) * ((E + 1) / 2) + 7) / 8;              // one warp per (2 rows, 32 columns)
+  v_fwd_kernel<<<gF, 256, 0, st>>>(E, 2, Hv, states, state_stride, t_col, T_col, W[0], b[0], h[0], 1);
+  for (int l = 1; l < 4; ++l) v_fwd_kernel<<<gF, 256, 0, st>>>(E, Hv, Hv, h[l - 1], (size_t)Hv, -1, -1, W[l], b[l], h[l], 1);
+  v_fwd_kernel<<<gF1, 256, 0, st>>>(E, Hv, 1, h[3], (size_t)Hv, -1, -1, W[4], b[4], v, 0);
+  v_loss_kernel<<<(E + 127) / 128, 128, 0, st>>>(E, v, tdlamrets, coeff, dv, values, vterms);
+  // head: dW4 = dv^T h4, dz(h4) = dv (x) w4 . [h4 > 0]
+  v_wgrad_kernel<<<(Hv + 255) / 256, 256, 0, st>>>(E, Hv, 1, dv, h[3], (size_t)Hv, -1, -1, dW[4], db[4]);
+  v_dgrad_kernel<<<gD, 256, 0, st>>>(E, Hv, 1, dv, W[4], h[3], dz[0]);
+  int cur = 0;
+  for (int l = 3; l >= 1; --l) {
+    v_wgrad_kernel<<<(Hv * Hv + 255) / 256, 256, 0, st>>>(E, Hv, Hv, dz[cur], h[l - 1], (size_t)Hv, -1, -1, dW[l], db[l]);
+    v_dgrad_kernel<<<gD, 256, 0, st>>>(E, Hv, Hv, dz[cur], W[l], h[l - 1], dz[cur ^ 1]);
+    cur ^= 1;
+  }
+  v_wgrad_kernel<<<(Hv * 2 + 255) / 256, 256, 0, st>>>(E, 2, Hv, dz[cur], states, state_stride, t_col, T_col, dW[0], db[0]);
+  MBO_LAUNCH_CHECK();
+  return MBO_OK;
+}

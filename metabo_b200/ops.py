@@ -365,6 +365,31 @@ class PPOPolicyGrad:
         return v
 
 
+class PPOValueGrad:
+    """Workspace + call wrapper of `mbo_ppo_value_grad` (value-net forward + backward of one optimiser step)."""
+
+    def __init__(self, E, Hv, device):
+        self.E, self.Hv = int(E), int(Hv)
+        self.nbytes = int(L.lib().mbo_ppo_value_workspace_bytes(self.E, self.Hv))
+        self.ws = torch.zeros(self.nbytes // 4 + 64, dtype=torch.float32, device=device)
+        self.values = torch.empty(self.E, dtype=torch.float32, device=device)
+        self.vterms = torch.empty(self.E, dtype=torch.float32, device=device)
+
+    def __call__(self, states, t_col, T_col, weights, biases, tdlamrets, coeff, dW, db):
+        """states [E, M, F] fp32 contiguous; returns (values [E], (values - tdlamrets)^2 [E]); gradients of
+        coeff * sum((values - tdlamrets)^2) are written into dW / db."""
+        _chk(states, torch.float32, "states"); _chk(tdlamrets, torch.float32, "tdlamrets")
+        E, M, F = states.shape
+        assert E <= self.E and len(weights) == len(biases) == len(dW) == len(db) == 5
+        for t in list(weights) + list(biases) + list(dW) + list(db):
+            _chk(t, torch.float32, "parameter / gradient")
+        arr = lambda ts: (C.c_void_p * 5)(*[t.data_ptr() for t in ts])
+        L.check(L.lib().mbo_ppo_value_grad(E, M * F, int(t_col) % F, int(T_col) % F, self.Hv, _p(states), arr(weights),
+                                           arr(biases), _p(tdlamrets), float(coeff), arr(dW), arr(db), _p(self.values),
+                                           _p(self.vterms), _p(self.ws), self.nbytes, _stream()), "mbo_ppo_value_grad")
+        return self.values[:E], self.vterms[:E]
+
+
 class FusedAdam(torch.optim.Optimizer):
     """torch.optim.Adam(params, lr) semantics (ppo.py:93: default betas / eps, no weight decay, no amsgrad) with the
     whole step in one kernel launch (`mbo_adam_step`); the step counters live on the device, so a captured CUDA graph of

@@ -12,8 +12,9 @@ and every rank applies the identical Adam step (weights stay replicated, no broa
 
 Update backends (`params["update_backend"]`): "native" (default when the policy net is the shipped
 F -> H -> H -> H -> H -> 1 ReLU shape) computes the policy-net forward + backward of every optimiser step
-with the hand-written tcgen05 TF32 kernels behind `mbo_ppo_policy_grad` (csrc/ppo_update.cu); the small
-value net (2 inputs x minibatch rows) stays on torch autograd.  "autograd" is the all-torch fp32 path.
+with the hand-written tcgen05 kernels behind `mbo_ppo_policy_grad` (csrc/ppo_update.cu), the small value net
+(2 inputs x minibatch rows) with `mbo_ppo_value_grad` (fp32 CUDA cores) and Adam with `mbo_adam_step`.
+"autograd" is the all-torch fp32 path.
 """
 import collections
 import copy
@@ -137,6 +138,8 @@ class PPO:
             self.optimizer = torch.optim.Adam(self.pi.parameters(), lr=self.params["lr"], capturable=True)
         self._pg = None         # ops.PPOPolicyGrad for the current minibatch shape
         self._pg_grads = None   # persistent gradient buffers of the policy net (written by the kernels)
+        self._vg = None         # ops.PPOValueGrad
+        self._vg_grads = None
 
         self.stats = dict()
         self.stats["n_timesteps"] = 0
@@ -183,6 +186,11 @@ class PPO:
         return (pi.activation == "relu" and len(a) == 4 and len(set(a)) == 1 and 8 <= a[0] <= 207
                 and 1 <= pi.N_features_policy <= 8)
 
+    @staticmethod
+    def native_value_supported(pi):
+        a = pi.value_net.arch_spec
+        return pi.activation == "relu" and len(a) == 4 and len(set(a)) == 1 and 1 <= a[0] <= 256
+
     def _policy_grad_op(self, E, M, Fs):
         pg = self._pg
         if pg is None or pg.E < E or (pg.M, pg.F_state) != (M, Fs):
@@ -226,7 +234,20 @@ class PPO:
             l.weight.grad, l.bias.grad = gw, gb
         l_ppo = terms[:, 2].sum()
         l_ent = -terms[:, 1].sum() / n_global
-        if pi.use_value_network:
+        if pi.use_value_network and self.native_value_supported(pi):
+            vfc = list(pi.value_net.fc)
+            if self._vg is None or self._vg.E < E:
+                self._vg = ops.PPOValueGrad(E, pi.value_net.arch_spec[0], states.device)
+            if self._vg_grads is None:
+                self._vg_grads = ([torch.zeros_like(l.weight) for l in vfc], [torch.zeros_like(l.bias) for l in vfc])
+            vW, vb = self._vg_grads
+            _, vterms = self._vg(states.contiguous(), pi.t_idx, pi.T_idx, [l.weight.data for l in vfc],
+                                 [l.bias.data for l in vfc], tdlamrets.to(torch.float32).contiguous(),
+                                 self.params["value_coeff"] / n_global, vW, vb)
+            for l, gw, gb in zip(vfc, vW, vb):
+                l.weight.grad, l.bias.grad = gw, gb
+            l_val = vterms.sum() / n_global
+        elif pi.use_value_network:
             tT = torch.stack([states[:, 0, pi.t_idx], states[:, 0, pi.T_idx]], dim=1)
             vpreds = pi.value_net.forward(tT).squeeze(1)
             l_val = torch.sum((vpreds - tdlamrets) ** 2) / n_global

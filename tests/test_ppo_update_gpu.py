@@ -236,3 +236,38 @@ def test_old_policy_logprobs_are_bitwise_the_new_policys_at_equal_weights():
     pg.check()
     assert torch.equal(terms[:, 0], lp) and torch.equal(terms[:, 1], en)
     assert bool((terms[:, 3] == 1.0).all())
+
+
+@pytest.mark.parametrize("E,Hv", [(60, 200), (7, 20), (119, 200)])
+def test_value_net_grad_matches_autograd(E, Hv):
+    """mbo_ppo_value_grad (ppo.py:150-156 value loss through the 2 -> Hv x 4 -> 1 value net on states[:, 0, [t, T]],
+    policies.py:116-121) against torch-CPU fp64 autograd: values 1e-5, gradients 1e-4 of max|grad| per tensor."""
+    from metabo_b200 import ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(E)
+    M, F = 11, 6
+    dims = [2, Hv, Hv, Hv, Hv, 1]
+    W = [torch.randn(dims[i + 1], dims[i], generator=g) * (0.5 if i == 0 else 0.15) for i in range(5)]
+    b = [torch.randn(dims[i + 1], generator=g) * 0.1 for i in range(5)]
+    states = torch.randn(E, M, F, generator=g)
+    states[:, :, -2] = torch.randint(0, 30, (E, 1), generator=g).float()
+    states[:, :, -1] = 30.0
+    ret = torch.randn(E, generator=g)
+    coeff = 1.0 / (2 * E)
+    Wr = [w.double().clone().requires_grad_() for w in W]
+    br = [x.double().clone().requires_grad_() for x in b]
+    h = torch.stack([states[:, 0, -2], states[:, 0, -1]], 1).double()
+    for l in range(4):
+        h = torch.relu(h @ Wr[l].t() + br[l])
+    v = (h @ Wr[4].t() + br[4]).squeeze(1)
+    (coeff * ((v - ret.double()) ** 2).sum()).backward()
+    vg = ops.PPOValueGrad(E + 3, Hv, dev)
+    Wd, bd = [w.to(dev).contiguous() for w in W], [x.to(dev).contiguous() for x in b]
+    dW, db = [torch.full_like(w, 3.0) for w in Wd], [torch.full_like(x, 3.0) for x in bd]
+    vals, vterms = vg(states.to(dev), -2, -1, Wd, bd, ret.to(dev), coeff, dW, db)
+    torch.cuda.synchronize()
+    assert _rel(vals, v.detach()) <= 1e-5
+    assert _rel(vterms, ((v - ret.double()) ** 2).detach()) <= 1e-4
+    for l in range(5):
+        assert _rel(dW[l], Wr[l].grad) <= 1e-4, ("dW", l)
+        assert _rel(db[l], br[l].grad) <= 1e-4, ("db", l)
