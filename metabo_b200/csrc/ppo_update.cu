@@ -57,7 +57,8 @@ constexpr int WG_B_STAGE = 7 * 4096;          // 7 blocks (224 >= 208 columns)
 constexpr int WG_SMEM = WG_STAGES * (WG_A_STAGE + WG_B_STAGE) + 256 + 1024;   // + alignment slack
 constexpr int WG_SPLIT = 49;                  // 49 x 3 layers = 147 CTAs, one wave
 constexpr int THIN_THREADS = 208;             // 52 four-column groups x 4 row lanes
-constexpr int THIN_CTAS = 296;
+constexpr int THIN_CTAS = 592;             // dz4 / layer 0: 4 per SM (latency-bound streams: 33 -> 22 us for dz4)
+constexpr int WG0_CTAS = 296;              // layer-0 wgrad: its per-CTA partial (208 x 9 floats) makes more CTAs a loss
 constexpr int MAXF = 8;
 
 // ---- PTX wrappers (own namespace: neural_af_tc.cu has same-named helpers with other constants) -----------------
@@ -806,7 +807,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) upd_wgrad_kernel(WgradArgs a, in
 // blocks [0, nblkA): the three H x (H + 1) layers, one thread per output, 49 split-K partials;
 // then one WARP per output of the head (H + 1) and of layer 0 (H x (F + 1)): lanes stride over the n_thin CTA partials,
 // xor-tree combine (a fixed order: bitwise reproducible).
-__global__ void __launch_bounds__(256) upd_reduce_kernel(Net net, Ws ws, int n_thin, int nblkA) {
+__global__ void __launch_bounds__(256) upd_reduce_kernel(Net net, Ws ws, int n_head, int n_l0, int nblkA) {
   const int H = net.H, F = net.F;
   if ((int)blockIdx.x < nblkA) {
     const int idx = blockIdx.x * 256 + threadIdx.x;
@@ -827,11 +828,13 @@ __global__ void __launch_bounds__(256) upd_reduce_kernel(Net net, Ws ws, int n_t
   const float* p;
   size_t stride;
   float* out;
+  int n_thin = n_head;
   if (idx < nB) {
     p = ws.part_head + idx; stride = HP;
     out = idx < H ? net.dW[4] + idx : net.db[4];
   } else {
     idx -= nB;
+    n_thin = n_l0;
     const int o = idx / (F + 1), f = idx - o * (F + 1);
     p = ws.part_l0 + (size_t)o * (MAXF + 1) + (f < F ? f : MAXF); stride = (size_t)HP * (MAXF + 1);
     out = f < F ? net.dW[0] + (size_t)o * F + f : net.db[0] + o;
@@ -976,9 +979,9 @@ extern "C" int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32
   wa.part = ws.part_big; wa.R = R; wa.H = H;
 
   upd_wgrad_kernel<<<dim3(WG_SPLIT, 3), GEMM_THREADS, WG_SMEM, st>>>(wa, ws.err);
-  upd_wgrad0_kernel<<<THIN_CTAS, THIN_THREADS, 0, st>>>(net, states, R, ws.dZ[0], ws.Hs[0], ws.part_l0);
+  upd_wgrad0_kernel<<<WG0_CTAS, THIN_THREADS, 0, st>>>(net, states, R, ws.dZ[0], ws.Hs[0], ws.part_l0);
   const int nblkA = (3 * H * (H + 1) + 255) / 256, nblkT = ((H + 1) + H * (F + 1) + 7) / 8;
-  upd_reduce_kernel<<<nblkA + nblkT, 256, 0, st>>>(net, ws, THIN_CTAS, nblkA);
+  upd_reduce_kernel<<<nblkA + nblkT, 256, 0, st>>>(net, ws, THIN_CTAS, WG0_CTAS, nblkA);
   MBO_CUDA(cudaMemcpyAsync(terms, ws.terms, (size_t)E * 16, cudaMemcpyDeviceToDevice, st));
   MBO_LAUNCH_CHECK();
   return MBO_OK;
@@ -1061,35 +1064,35 @@ __global__ void v_loss_kernel(int E, const float* __restrict__ v, const float* _
   vterms[e] = d * d;
 }
 
-// dIn[e][i] = [h[e][i] > 0] * sum_o dZ[e][o] W[o][i].  One warp per (2 rows, 32 input columns): lane = column
-// (coalesced W rows), dZ broadcast, four independent chains over o.
+// dIn[e][i] = [h[e][i] > 0] * sum_o dZ[e][o] W[o][i].  CTA = (32 input columns, 8 rows): the W column block and the 8
+// dZ rows are staged in shared memory with every thread loading (the first version walked W with one L2 round trip per
+// 8 outputs and took 11 us); warp = row, lane = column.
 __global__ void __launch_bounds__(256) v_dgrad_kernel(int E, int Kin, int Hout, const float* __restrict__ dZ,
                                                        const float* __restrict__ W, const float* __restrict__ h,
                                                        float* __restrict__ dIn) {
-  const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const int n_ig = (Kin + 31) >> 5, n_eg = (E + 1) >> 1;
-  if (warp >= n_ig * n_eg) return;
-  const int eg = warp / n_ig, i = (warp - eg * n_ig) * 32 + lane;
-  const int e0 = eg * 2, e1 = min(e0 + 1, E - 1);
-  const bool ok = i < Kin;
-  const float* z0 = dZ + (size_t)e0 * Hout;
-  const float* z1 = dZ + (size_t)e1 * Hout;
-  float a0[2] = {0.f, 0.f}, a1[2] = {0.f, 0.f};
+  __shared__ float Ws[V_MAXH][32];
+  __shared__ float Zs[8][V_MAXH];
+  const int i0 = blockIdx.x * 32, e0 = blockIdx.y * 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int t = threadIdx.x; t < Hout * 32; t += 256) {
+    const int o = t >> 5, ii = t & 31;
+    Ws[o][ii] = i0 + ii < Kin ? W[(size_t)o * Kin + i0 + ii] : 0.f;
+  }
+  for (int t = threadIdx.x; t < 8 * Hout; t += 256) {
+    const int r = t / Hout, o = t - r * Hout;
+    Zs[r][o] = e0 + r < E ? dZ[(size_t)(e0 + r) * Hout + o] : 0.f;
+  }
+  __syncthreads();
+  const int e = e0 + warp, i = i0 + lane;
+  if (e >= E || i >= Kin) return;
+  float a[4] = {0.f, 0.f, 0.f, 0.f};
   int o = 0;
-  for (; o + 1 < Hout; o += 2) {
-    const float w0 = ok ? W[(size_t)o * Kin + i] : 0.f, w1 = ok ? W[(size_t)(o + 1) * Kin + i] : 0.f;
-    a0[0] = fmaf(z0[o], w0, a0[0]); a0[1] = fmaf(z0[o + 1], w1, a0[1]);
-    a1[0] = fmaf(z1[o], w0, a1[0]); a1[1] = fmaf(z1[o + 1], w1, a1[1]);
+  for (; o + 3 < Hout; o += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a[u] = fmaf(Zs[warp][o + u], Ws[o + u][lane], a[u]);
   }
-  if (o < Hout) {
-    const float w0 = ok ? W[(size_t)o * Kin + i] : 0.f;
-    a0[0] = fmaf(z0[o], w0, a0[0]);
-    a1[0] = fmaf(z1[o], w0, a1[0]);
-  }
-  if (ok) {
-    dIn[(size_t)e0 * Kin + i] = h[(size_t)e0 * Kin + i] > 0.f ? a0[0] + a0[1] : 0.f;
-    if (e0 + 1 < E) dIn[(size_t)(e0 + 1) * Kin + i] = h[(size_t)(e0 + 1) * Kin + i] > 0.f ? a1[0] + a1[1] : 0.f;
-  }
+  for (; o < Hout; ++o) a[0] = fmaf(Zs[warp][o], Ws[o][lane], a[0]);
+  dIn[(size_t)e * Kin + i] = h[(size_t)e * Kin + i] > 0.f ? (a[0] + a[1]) + (a[2] + a[3]) : 0.f;
 }
 
 // dW[o][i] = sum_e dZ[e][o] in[e][i], db[o] = sum_e dZ[e][o]; one thread per (o, i), four independent chains over e
@@ -1147,7 +1150,7 @@ extern "C" int mbo_ppo_value_grad(int E, size_t state_stride, int t_col, int T_c
   using namespace mbo::upd;
   const int n_eg4 = (E + 3) / 4;
   const int gF = (n_eg4 * Hv + 7) / 8, gF1 = (n_eg4 + 7) / 8;             // 8 warps per CTA, one warp per (4 rows, column)
-  const int gD = (((Hv + 31) / 32) * ((E + 1) / 2) + 7) / 8;              // one warp per (2 rows, 32 columns)
+  const dim3 gD((Hv + 31) / 32, (E + 7) / 8);                             // CTA = (32 columns, 8 rows)
   v_fwd_kernel<<<gF, 256, 0, st>>>(E, 2, Hv, states, state_stride, t_col, T_col, W[0], b[0], h[0], 1);
   for (int l = 1; l < 4; ++l) v_fwd_kernel<<<gF, 256, 0, st>>>(E, Hv, Hv, h[l - 1], (size_t)Hv, -1, -1, W[l], b[l], h[l], 1);
   v_fwd_kernel<<<gF1, 256, 0, st>>>(E, Hv, 1, h[3], (size_t)Hv, -1, -1, W[4], b[4], v, 0);
