@@ -43,7 +43,7 @@ constexpr int NKT3 = 26;            // 208 / 8
 constexpr int WG_KT = 32;           // K rows per stage of the wgrad GEMM
 constexpr int A_STAGE = TM * KT * 4;          // 8 192 (dgrad: 16 K values; forward: 8 K values x {hi, lo})
 constexpr int B_STAGE = HP * KT * 4;          // 13 312
-constexpr int IMG_FLOATS = NKT * HP * KT;     // 43 264 floats per weight image
+constexpr int IMG_FLOATS = 7 * HP * 32;       // 46 592 floats per weight image (the 32-K-per-stage dgrad image is the largest)
 constexpr int STG_PITCH = 36;                 // floats per row of the epilogue's per-warp staging tile (32 + 4: conflict-free)
 constexpr int GEMM_MB = 1;          // 128-row blocks per CTA.  2 (shared weight stages, 3 pipeline stages, 1 CTA/SM) measured SLOWER
                                     // (fwd 71 -> 81 us, dgrad 61 -> 94 us): two co-resident CTAs hide each other's epilogue
@@ -159,6 +159,7 @@ struct Ws {          // workspace carve-up (device pointers)
   float* img_fwd[3];  // hi parts of [W | b], KT3 stages
   float* img_fwl[3];  // lo parts
   float* img_dgr[3];  // W^T, KT stages
+  float* img_dgp[3];  // W^T, 32 K values per stage (persistent dgrad)
   float* Hs[4];      // h1..h4 (tf32-rounded "hi" parts)
   float* Hl[3];      // lo parts of h1..h3 (3xTF32 forward)
   uint32_t* hbits[2]; // ReLU decisions of h2, h3: [R][8] words, bit q of word c = (h[row][32 c + q] > 0)
@@ -182,6 +183,7 @@ static size_t carve(int E, int M, unsigned char* base, Ws* w) {
   for (int l = 0; l < 3; ++l) t.img_fwd[l] = (float*)take((size_t)IMG_FLOATS * 4);
   for (int l = 0; l < 3; ++l) t.img_fwl[l] = (float*)take((size_t)IMG_FLOATS * 4);
   for (int l = 0; l < 3; ++l) t.img_dgr[l] = (float*)take((size_t)IMG_FLOATS * 4);
+  for (int l = 0; l < 3; ++l) t.img_dgp[l] = (float*)take((size_t)IMG_FLOATS * 4);
   for (int l = 0; l < 4; ++l) t.Hs[l] = (float*)take(Rp * HP * 4);
   for (int l = 0; l < 3; ++l) t.Hl[l] = (float*)take(Rp * HP * 4);
   for (int l = 0; l < 2; ++l) t.hbits[l] = (uint32_t*)take(Rp * 8 * 4);
@@ -202,10 +204,10 @@ static size_t carve(int E, int M, unsigned char* base, Ws* w) {
 // Forward: [W | b] split into tf32 hi and lo parts (3xTF32: hi*hi + lo*hi + hi*lo, fp32-level logits); dgrad: W^T.
 __global__ void upd_pack_kernel(Net net, Ws ws) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= 6 * IMG_FLOATS) return;
+  if (idx >= 9 * IMG_FLOATS) return;
   const int img = idx / IMG_FLOATS, o = idx - img * IMG_FLOATS;
-  const int l = img >> 1, dgr = img & 1;            // layer l + 1
-  const int kt_len = dgr ? KT : KT3;
+  const int kind = img / 3, l = img - kind * 3;     // kind 0: forward hi / lo, 1: dgrad (KT), 2: dgrad (32 per stage); layer l + 1
+  const int kt_len = kind == 0 ? KT3 : (kind == 1 ? KT : 32);
   const int kt = o / (HP * kt_len), r = o - kt * (HP * kt_len);
   const int c = r / (HP * 4), r2 = r - c * (HP * 4);
   const int n = r2 >> 2, e = r2 & 3;
@@ -213,15 +215,16 @@ __global__ void upd_pack_kernel(Net net, Ws ws) {
   const int H = net.H;
   const float* W = net.W[l + 1];
   float v = 0.f;
-  if (!dgr) {
+  if (kind == 0) {
     if (k >= HP) return;
     if (n < H) v = k < H ? W[(size_t)n * H + k] : (k == H ? net.b[l + 1][n] : 0.f);     // [W | b]
     const float hi = tf32_rn(v);
     ws.img_fwd[l][o] = hi;
     ws.img_fwl[l][o] = tf32_rn(v - hi);
   } else {
+    if (kind == 1 && k >= HP) return;
     if (n < H && k < H) v = W[(size_t)k * H + n];                                        // W^T: N = in, K = out
-    ws.img_dgr[l][o] = tf32_rn(v);
+    (kind == 1 ? ws.img_dgr[l] : ws.img_dgp[l])[o] = tf32_rn(v);
   }
 }
 
@@ -501,6 +504,247 @@ __global__ void __launch_bounds__(GEMM_THREADS) upd_gemm_kernel(GemmArgs a, int*
   if (warp == 4) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u * GEMM_MB) : "memory");
+  }
+}
+
+// ---- persistent variant of the forward / dgrad GEMM ----------------------------------------------------------------
+// One CTA per SM over a contiguous range of rows (R / grid, rounded up to 8), 128-row tiles inside it; two accumulators
+// in TMEM (2 x 256 columns) so that the epilogue warps drain tile i while the loaders / MMA warp already run tile i + 1;
+// 8 pipeline stages (7 in flight).  Warps 0-3: epilogue, 4-7: A loaders, 8: MMA issue, 9: weight stages.
+constexpr int PG_STAGES = 8;
+constexpr int PG_THREADS = 320;
+constexpr int PG_STG_BYTES = 4 * 32 * STG_PITCH * 4;                                     // 18 432
+constexpr int PG_SMEM = PG_STAGES * (A_STAGE + B_STAGE) + 1024 + PG_STG_BYTES + 256;
+
+template <int EPI>
+__global__ void __launch_bounds__(PG_THREADS, 1) upd_gemm_persist_kernel(GemmArgs a, int* __restrict__ err) {
+  constexpr bool X3 = EPI == 0;
+  // forward: 8 stages of 8 K values (hi + lo of both operands); dgrad: 4 stages of 32 K values, so that every row gives a
+  // whole 128-byte line per stage (LDGSTS costs per line touched: 8 rows x 64 B per instruction ran at ~80 cycles per
+  // instruction, 4 rows x 128 B at ~28) -- chunk planes padded by 16 B to keep those stores conflict-free
+  constexpr int NKT_ = X3 ? NKT3 : 7;
+  constexpr int KT_ = X3 ? KT3 : 32;
+  constexpr int NST = X3 ? PG_STAGES : 4;
+  constexpr int LBO_A = X3 ? TM * 16 : TM * 16 + 16;
+  constexpr int A_ST = X3 ? A_STAGE : 8 * LBO_A;
+  constexpr int B_ST = X3 ? B_STAGE : HP * 32 * 4;
+  static_assert(NST * (A_ST + B_ST) <= PG_STAGES * (A_STAGE + B_STAGE) + 1024, "stage budget");
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + NST * A_ST;
+  float* s_stg = (float*)(smem + PG_STAGES * (A_STAGE + B_STAGE) + 1024);
+  uint64_t* bars = (uint64_t*)(smem + PG_STAGES * (A_STAGE + B_STAGE) + 1024 + PG_STG_BYTES);
+  uint32_t* s_tmem = (uint32_t*)(bars + 2 * PG_STAGES + 4);
+  volatile int* s_abort = (volatile int*)(s_tmem + 1);
+  __shared__ float s_w4[HP];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar0 = smem_u32(bars);
+  auto FULL = [&](int s) { return bar0 + 8u * s; };
+  auto EMPTY = [&](int s) { return bar0 + 8u * (NST + s); };
+  auto ACCF = [&](int i) { return bar0 + 8u * (2 * NST + i); };
+  auto ACCE = [&](int i) { return bar0 + 8u * (2 * NST + 2 + i); };
+  // this CTA's rows
+  const int rpc = (((a.R + (int)gridDim.x - 1) / (int)gridDim.x) + 7) & ~7;
+  const int r_begin = min(a.R, (int)blockIdx.x * rpc), r_end = min(a.R, r_begin + rpc);
+  const int n_tiles = (r_end - r_begin + TM - 1) / TM;
+
+  if (tid == 0) {
+    *s_abort = 0;
+    for (int s = 0; s < NST; ++s) { mbar_init(FULL(s), 128 + 1); mbar_init(EMPTY(s), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(ACCF(i), 1); mbar_init(ACCE(i), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (EPI == 0 && a.w4) for (int i = tid; i < HP; i += PG_THREADS) s_w4[i] = i < a.H ? a.w4[i] : 0.f;
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+
+  if (warp < 4) {
+    // ---- epilogue warps ----
+    float* stg = s_stg + warp * (32 * STG_PITCH);
+    const int cr = lane >> 3, cc = lane & 7;
+    for (int t = 0; t < n_tiles; ++t) {
+      const int slot = t & 1;
+      const int wrow0 = r_begin + t * TM + warp * 32;
+      uint32_t mbits[8];
+      if (EPI == 1) {
+        const int row = wrow0 + lane;
+        uint4 w0 = make_uint4(~0u, ~0u, ~0u, ~0u), w1 = w0;
+        if (a.bits_in && row < r_end) {
+          w0 = *(const uint4*)(a.bits_in + (size_t)row * 8);
+          w1 = *(const uint4*)(a.bits_in + (size_t)row * 8 + 4);
+        }
+        mbits[0] = w0.x; mbits[1] = w0.y; mbits[2] = w0.z; mbits[3] = w0.w;
+        mbits[4] = w1.x; mbits[5] = w1.y; mbits[6] = w1.z; mbits[7] = w1.w;
+      }
+      mbar_wait(ACCF(slot), (t >> 1) & 1, s_abort);
+      tc_fence_after();
+      const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16) + slot * 256;
+      const bool live = wrow0 < r_end;                       // warp-uniform
+      float head = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < HP; c0 += 32) {
+        uint32_t v[32];
+        const int nc = HP - c0 >= 32 ? 32 : 16;
+        if (nc == 32) tmem_ld32(tbase + c0, v); else tmem_ld16(tbase + c0, v);
+        tmem_wait_ld();
+        if (c0 + 32 >= HP) {                                 // the accumulator is in registers: hand the slot back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ACCE(slot)) : "memory");
+        }
+        if (!live) continue;
+        float x[32];
+        if (EPI == 0) {
+          uint32_t word = 0;
+#pragma unroll
+          for (int q = 0; q < 32; ++q) {
+            x[q] = fmaxf(__uint_as_float(v[q]), 0.f);
+            if (q < nc) {
+              if (a.w4) head = fmaf(x[q], s_w4[c0 + q], head);
+              word |= (x[q] > 0.f ? 1u : 0u) << q;
+            }
+          }
+          if (a.bits_out && wrow0 + lane < r_end) a.bits_out[(size_t)(wrow0 + lane) * 8 + (c0 >> 5)] = word;
+        } else {
+          const uint32_t word = mbits[c0 >> 5];
+#pragma unroll
+          for (int q = 0; q < 32; ++q) x[q] = (q < nc && ((word >> q) & 1u)) ? tf32_rn(__uint_as_float(v[q])) : 0.f;
+        }
+#pragma unroll 1
+        for (int part = 0; part < (EPI == 0 && a.OutLo ? 2 : 1); ++part) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            if (q * 4 < nc) {
+              float o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float tt = x[q * 4 + e];
+                if (EPI == 0) {
+                  const int col = c0 + q * 4 + e;
+                  const float hi = col == a.H ? 1.f : tf32_rn(tt);
+                  tt = part == 0 ? hi : (col == a.H ? 0.f : tf32_rn(tt - hi));
+                }
+                o[e] = tt;
+              }
+              *(float4*)(stg + lane * STG_PITCH + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+          }
+          __syncwarp();
+          float* outp = part == 0 ? a.Out : a.OutLo;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + cr, grow = wrow0 + r;
+            if (grow < r_end && cc * 4 < nc)
+              *(float4*)(outp + (size_t)grow * HP + c0 + cc * 4) = *(const float4*)(stg + r * STG_PITCH + cc * 4);
+          }
+          __syncwarp();
+        }
+      }
+      if (EPI == 0 && a.w4 && wrow0 + lane < r_end) a.logits[wrow0 + lane] = head + a.b4[0];
+    }
+  } else if (warp < 8) {
+    // ---- A loaders ----
+    const int lw = warp - 4;
+    const int r8 = lane & 7, cq = lane >> 3;
+    int g = 0;
+    for (int t = 0; t < n_tiles; ++t) {
+      const int row0 = r_begin + t * TM;
+      for (int kt = 0; kt < NKT_; ++kt, ++g) {
+        const int s = g % NST, u = g / NST;
+        if (u > 0) mbar_wait(EMPTY(s), (u - 1) & 1, s_abort);
+        const uint32_t dstA = smem_u32(sA + s * A_ST);
+        if (X3) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int j = lw * 4 + i;
+            const int grow = row0 + j * 8 + r8;
+            const bool ok = grow < r_end;
+            const int arr = cq >> 1, c = cq & 1;
+            const float* src = (arr ? a.Alo : a.A) + (size_t)(ok ? grow : 0) * HP + kt * KT_ + c * 4;
+            cp_async16(dstA + arr * (TM * KT3 * 4) + c * (TM * 16) + j * 128 + r8 * 16, src, ok);
+          }
+        } else {
+          // lane -> (row of 4, chunk of 8): one instruction = 4 whole 128-byte lines
+          const int lr = lane >> 3, c = lane & 7;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = (lw * 8 + i) * 4 + lr;
+            const int grow = row0 + row;
+            const bool ok = grow < r_end && kt * KT_ + c * 4 < HP;
+            const float* src = a.A + (size_t)(ok ? grow : 0) * HP + (ok ? kt * KT_ + c * 4 : 0);
+            cp_async16(dstA + c * LBO_A + (row >> 3) * 128 + (row & 7) * 16, src, ok);
+          }
+        }
+        cp_async_arrive(FULL(s));
+      }
+    }
+  } else if (warp == 8) {
+    // ---- MMA issue ----
+    if (lane == 0) {
+      int g = 0;
+      for (int t = 0; t < n_tiles; ++t) {
+        const int slot = t & 1;
+        if (t >= 2) { mbar_wait(ACCE(slot), ((t >> 1) - 1) & 1, s_abort); tc_fence_after(); }
+        const uint32_t d = tmem + slot * 256;
+        for (int kt = 0; kt < NKT_; ++kt, ++g) {
+          const int s = g % NST, u = g / NST;
+          mbar_wait(FULL(s), u & 1, s_abort);
+          tc_fence_after();
+          const uint32_t aS = smem_u32(sA + s * A_ST), bS = smem_u32(sB + s * B_ST);
+          if (X3) {
+            const uint64_t bh = make_desc(bS, HP * 16, 128);
+            const uint64_t bl = make_desc(bS + HP * KT3 * 4, HP * 16, 128);
+            const uint64_t ah = make_desc(aS, TM * 16, 128);
+            const uint64_t al = make_desc(aS + TM * KT3 * 4, TM * 16, 128);
+            mma_ss_tf32(d, al, bh, IDESC_K, kt != 0);        // small terms first
+            mma_ss_tf32(d, ah, bl, IDESC_K, 1);
+            mma_ss_tf32(d, ah, bh, IDESC_K, 1);
+          } else {
+            const int nks = kt == NKT_ - 1 ? 2 : 4;            // the last stage holds K 192..207
+            for (int ks = 0; ks < nks; ++ks) {
+              const uint64_t bd = make_desc(bS + ks * 2 * (HP * 16), HP * 16, 128);
+              const uint64_t ad = make_desc(aS + ks * 2 * LBO_A, LBO_A, 128);
+              mma_ss_tf32(d, ad, bd, IDESC_K, (kt | ks) != 0);
+            }
+          }
+          tc_commit(EMPTY(s));
+        }
+        tc_commit(ACCF(slot));
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---- weight stages ----
+    if (lane == 0) {
+      int g = 0;
+      for (int t = 0; t < n_tiles; ++t) {
+        for (int kt = 0; kt < NKT_; ++kt, ++g) {
+          const int s = g % NST, u = g / NST;
+          if (u > 0) mbar_wait(EMPTY(s), (u - 1) & 1, s_abort);
+          mbar_expect_tx(FULL(s), B_ST);
+          if (X3) {
+            bulk_g2s(smem_u32(sB + s * B_ST), a.Bimg + (size_t)kt * (HP * KT3), HP * KT3 * 4, FULL(s));
+            bulk_g2s(smem_u32(sB + s * B_ST) + HP * KT3 * 4, a.Bimg_lo + (size_t)kt * (HP * KT3), HP * KT3 * 4, FULL(s));
+          } else {
+            bulk_g2s(smem_u32(sB + s * B_ST), a.Bimg + (size_t)kt * (HP * 32), B_ST, FULL(s));
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0 && *s_abort) atomicOr(err, 1);
+  if (warp == 8) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
   }
 }
 
@@ -884,11 +1128,15 @@ __global__ void __launch_bounds__(256) adam_step_kernel(AdamArgs a, float lr, fl
 }
 
 static bool g_attr_done = false;
+static int g_num_sms = 148;
 static int set_attrs() {
   if (g_attr_done) return MBO_OK;
   MBO_CUDA(cudaFuncSetAttribute(upd_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
   MBO_CUDA(cudaFuncSetAttribute(upd_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
   MBO_CUDA(cudaFuncSetAttribute(upd_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
+  MBO_CUDA(cudaFuncSetAttribute(upd_gemm_persist_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM));
+  MBO_CUDA(cudaFuncSetAttribute(upd_gemm_persist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM));
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev); }
   g_attr_done = true;
   return MBO_OK;
 }
@@ -950,15 +1198,23 @@ extern "C" int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32
   const int tiles = (R + TM * GEMM_MB - 1) / (TM * GEMM_MB);
   const char* dbg_env = getenv("MBO_UPD_DBG");
   const int dbg = dbg_env ? atoi(dbg_env) : 0;
+  // which GEMM variant runs (both are kept and tested against each other): measured on the C3 minibatch, the persistent
+  // double-buffered kernel wins for the dgrad (33.5 vs 38 us) and loses for the 3xTF32 forward (81 vs 75 us)
+  const char* pf_env = getenv("MBO_UPD_PERSIST_FWD");
+  const char* pd_env = getenv("MBO_UPD_PERSIST_DGRAD");
+  const bool persist_fwd = pf_env ? atoi(pf_env) != 0 : false;
+  const bool persist = pd_env ? atoi(pd_env) != 0 : true;
+  const int pg_grid = g_num_sms < tiles ? g_num_sms : tiles;
 
-  upd_pack_kernel<<<(6 * IMG_FLOATS + 255) / 256, 256, 0, st>>>(net, ws);
+  upd_pack_kernel<<<(9 * IMG_FLOATS + 255) / 256, 256, 0, st>>>(net, ws);
   upd_layer0_kernel<<<4 * THIN_CTAS, THIN_THREADS, 0, st>>>(net, states, R, ws.Hs[0], ws.Hl[0]);
   for (int l = 0; l < 3; ++l) {
     GemmArgs g{};
     g.A = ws.Hs[l]; g.Alo = ws.Hl[l]; g.Bimg = ws.img_fwd[l]; g.Bimg_lo = ws.img_fwl[l]; g.Out = ws.Hs[l + 1];
     g.OutLo = l < 2 ? ws.Hl[l + 1] : nullptr; g.bits_out = l < 2 ? ws.hbits[l] : nullptr; g.R = R; g.H = H; g.dbg = dbg;
     if (l == 2) { g.w4 = W[4]; g.b4 = b[4]; g.logits = ws.logits; }
-    upd_gemm_kernel<0><<<tiles, GEMM_THREADS, GEMM_SMEM, st>>>(g, ws.err);
+    if (persist_fwd) upd_gemm_persist_kernel<0><<<pg_grid, PG_THREADS, PG_SMEM, st>>>(g, ws.err);
+    else upd_gemm_kernel<0><<<tiles, GEMM_THREADS, GEMM_SMEM, st>>>(g, ws.err);
   }
   upd_loss_kernel<<<E, 256, 0, st>>>(M, ws.logits, actions, advs, logp_old, epsilon, ent_coeff, inv_n_global, ws.dl,
                                       ws.terms);
@@ -970,9 +1226,10 @@ extern "C" int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32
   upd_dz4_kernel<<<THIN_CTAS, THIN_THREADS, 0, st>>>(R, H, ws.Hs[3], ws.dl, W[4], ws.dZ[3], ws.part_head);
   for (int l = 2; l >= 0; --l) {      // dZ_{l+1} = (dZ_{l+2} W_{l+1}) . [h_{l+1} > 0]
     GemmArgs g{};
-    g.A = ws.dZ[l + 1]; g.Bimg = ws.img_dgr[l]; g.Out = ws.dZ[l]; g.bits_in = l > 0 ? ws.hbits[l - 1] : nullptr;   // l = 0: dH1, masked in wgrad0
+    g.A = ws.dZ[l + 1]; g.Bimg = persist ? ws.img_dgp[l] : ws.img_dgr[l]; g.Out = ws.dZ[l]; g.bits_in = l > 0 ? ws.hbits[l - 1] : nullptr;   // l = 0: dH1, masked in wgrad0
     g.R = R; g.H = H; g.dbg = dbg;
-    upd_gemm_kernel<1><<<tiles, GEMM_THREADS, GEMM_SMEM, st>>>(g, ws.err);
+    if (persist) upd_gemm_persist_kernel<1><<<pg_grid, PG_THREADS, PG_SMEM, st>>>(g, ws.err);
+    else upd_gemm_kernel<1><<<tiles, GEMM_THREADS, GEMM_SMEM, st>>>(g, ws.err);
   }
   WgradArgs wa{};
   for (int l = 0; l < 3; ++l) { wa.dZ[l] = ws.dZ[l + 1]; wa.Hin[l] = ws.Hs[l]; }

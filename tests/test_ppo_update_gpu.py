@@ -271,3 +271,22 @@ def test_value_net_grad_matches_autograd(E, Hv):
     for l in range(5):
         assert _rel(dW[l], Wr[l].grad) <= 1e-4, ("dW", l)
         assert _rel(db[l], br[l].grad) <= 1e-4, ("db", l)
+
+
+def test_gemm_kernel_variants_agree_bitwise(monkeypatch):
+    """The persistent double-buffered GEMM kernel (default for the dgrad) and the one-tile-per-CTA kernel (default for the
+    forward) issue the same MMA sequence per output tile: every activation, dZ and gradient is bitwise identical whichever
+    variant runs, on a ragged row count that gives the persistent CTAs partial and empty tiles."""
+    layers, states, actions, advs, logp_old = _random_case(11, 9, 517, 6, list(range(6)), 200)
+    outs = []
+    for fwd, dgr in (("0", "1"), ("1", "0"), ("0", "0"), ("1", "1")):
+        monkeypatch.setenv("MBO_UPD_PERSIST_FWD", fwd)
+        monkeypatch.setenv("MBO_UPD_PERSIST_DGRAD", dgr)
+        terms, v, dW, db = _run_case(9, 517, 6, list(range(6)), 200, layers, states, actions, advs, logp_old)
+        outs.append((terms, v, dW, db))
+    t0, v0, dW0, db0 = outs[0]
+    for terms, v, dW, db in outs[1:]:
+        assert torch.equal(terms, t0)
+        for k in ("h1", "h2", "h3", "h4", "dz1", "dz2", "dz3", "dz4", "logits", "dlogits"):
+            assert torch.equal(v[k], v0[k]), k
+        assert all(torch.equal(a, b) for a, b in zip(dW + db, dW0 + db0))
