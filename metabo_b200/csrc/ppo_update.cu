@@ -598,7 +598,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) upd_gemm_persist_kernel(GemmArg
           __syncwarp();
           if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ACCE(slot)) : "memory");
         }
-        if (!live) continue;
+        if (!live || (a.dbg & 1)) continue;
         float x[32];
         if (EPI == 0) {
           uint32_t word = 0;
@@ -659,7 +659,8 @@ __global__ void __launch_bounds__(PG_THREADS, 1) upd_gemm_persist_kernel(GemmArg
         const int s = g % NST, u = g / NST;
         if (u > 0) mbar_wait(EMPTY(s), (u - 1) & 1, s_abort);
         const uint32_t dstA = smem_u32(sA + s * A_ST);
-        if (X3) {
+        if (a.dbg & 4) {
+        } else if (X3) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int j = lw * 4 + i;
@@ -697,7 +698,8 @@ __global__ void __launch_bounds__(PG_THREADS, 1) upd_gemm_persist_kernel(GemmArg
           mbar_wait(FULL(s), u & 1, s_abort);
           tc_fence_after();
           const uint32_t aS = smem_u32(sA + s * A_ST), bS = smem_u32(sB + s * B_ST);
-          if (X3) {
+          if (a.dbg & 2) {
+          } else if (X3) {
             const uint64_t bh = make_desc(bS, HP * 16, 128);
             const uint64_t bl = make_desc(bS + HP * KT3 * 4, HP * 16, 128);
             const uint64_t ah = make_desc(aS, TM * 16, 128);
@@ -727,6 +729,10 @@ __global__ void __launch_bounds__(PG_THREADS, 1) upd_gemm_persist_kernel(GemmArg
         for (int kt = 0; kt < NKT_; ++kt, ++g) {
           const int s = g % NST, u = g / NST;
           if (u > 0) mbar_wait(EMPTY(s), (u - 1) & 1, s_abort);
+          if (a.dbg & 8) {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(FULL(s)) : "memory");
+            continue;
+          }
           mbar_expect_tx(FULL(s), B_ST);
           if (X3) {
             bulk_g2s(smem_u32(sB + s * B_ST), a.Bimg + (size_t)kt * (HP * KT3), HP * KT3 * 4, FULL(s));
