@@ -117,6 +117,11 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool v
   const uint32_t n = valid ? 16u : 0u;
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 // the mbarrier gets one (counted) arrival when every cp.async this thread has issued so far is complete
 __device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
@@ -256,11 +261,11 @@ __global__ void __launch_bounds__(THIN_THREADS) upd_layer0_kernel(Net net, const
       for (int f = 0; f < MAXF; ++f) acc = fmaf(x[f], w[e][f], acc);
       const int j = cg * 4 + e;
       acc = fmaxf(acc + bias[e], 0.f);
-      o[e] = j < H ? tf32_rn(acc) : (j == H ? 1.f : 0.f);
+      o[e] = j < H ? (H1lo ? tf32_rn(acc) : acc) : (j == H ? 1.f : 0.f);
       ol[e] = j < H ? tf32_rn(acc - o[e]) : 0.f;
     }
     *(float4*)(H1 + (size_t)r * HP + cg * 4) = make_float4(o[0], o[1], o[2], o[3]);
-    *(float4*)(H1lo + (size_t)r * HP + cg * 4) = make_float4(ol[0], ol[1], ol[2], ol[3]);
+    if (H1lo) *(float4*)(H1lo + (size_t)r * HP + cg * 4) = make_float4(ol[0], ol[1], ol[2], ol[3]);
   }
 }
 
@@ -279,6 +284,7 @@ struct GemmArgs {
   float* logits;         // [R]
   int R, H;
   int dbg;               // timing experiments (MBO_UPD_DBG): 1 no epilogue, 2 no MMAs, 4 no A loads, 8 no weight loads
+  int onchip_lo;         // forward: A is plain fp32 in HBM, its tf32 hi / lo split is made in shared memory by the loaders
 };
 
 // EPI 0: forward, 3xTF32 (stage = 16 K values x {hi, lo} of both operands, 3 MMAs per K = 8 step), epilogue ReLU +
@@ -287,7 +293,7 @@ struct GemmArgs {
 // The epilogue moves every 32-column chunk through a per-warp staging tile in shared memory (the pipeline stages are
 // idle by then) so that global memory sees whole 128-byte lines: thread = row from TMEM, lane = 16-byte chunk towards HBM.
 template <int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS) upd_gemm_kernel(GemmArgs a, int* __restrict__ err) {
+__global__ void __launch_bounds__(GEMM_THREADS, 2) upd_gemm_kernel(GemmArgs a, int* __restrict__ err) {
   constexpr bool X3 = EPI == 0;
   constexpr int NKT_ = X3 ? NKT3 : NKT;
   constexpr int KT_ = X3 ? KT3 : KT;
@@ -325,6 +331,45 @@ __global__ void __launch_bounds__(GEMM_THREADS) upd_gemm_kernel(GemmArgs a, int*
     // ---- A loaders: lane -> (16-byte chunk quarter cq, row-in-group r8): the 8 lanes of one cq write 128 contiguous
     // bytes of one core-matrix column (conflict-free) and read 64 B per row ----
     const int r8 = lane & 7, cq = lane >> 3;
+    if (X3 && a.onchip_lo) {
+      // ---- forward, activations stored once as plain fp32: every thread copies 2 chunks (16 B) per stage and, two
+      // stages later, splits exactly those chunks in place into tf32 hi (written back) and lo (second half of the
+      // stage) -- only its own cp.async groups have to be complete, no cross-thread hand-off ----
+      auto chunk_addr = [&](int kt, int i) {
+        const int j = warp * 4 + i * 2 + (cq >> 1);
+        return smem_u32(sA + (kt % GEMM_STAGES) * GEMM_A_STAGE) + (cq & 1) * (TM * 16) + j * 128 + r8 * 16;
+      };
+      auto split_stage = [&](int kt) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const uint32_t ad = chunk_addr(kt, i);
+          float4 v;
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ad) : "memory");
+          const float4 hi = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+          const float4 lo = make_float4(tf32_rn(v.x - hi.x), tf32_rn(v.y - hi.y), tf32_rn(v.z - hi.z), tf32_rn(v.w - hi.w));
+          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(ad), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(ad + TM * KT3 * 4), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(FULL(kt % GEMM_STAGES));
+      };
+      for (int kt = 0; kt < NKT_; ++kt) {
+        const int s = kt % GEMM_STAGES, u = kt / GEMM_STAGES;
+        if (u > 0) mbar_wait(EMPTY(s), (u - 1) & 1, s_abort);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int j = warp * 4 + i * 2 + (cq >> 1);
+          const int grow = row0 + j * 8 + r8;
+          const bool ok = grow < a.R;
+          const float* src = a.A + (size_t)(ok ? grow : 0) * HP + kt * KT_ + (cq & 1) * 4;
+          cp_async16(chunk_addr(kt, i), src, ok);
+        }
+        cp_async_commit();
+        if (kt >= 2) { cp_async_wait<2>(); split_stage(kt - 2); }
+      }
+      cp_async_wait<1>(); split_stage(NKT_ - 2);
+      cp_async_wait<0>(); split_stage(NKT_ - 1);
+    } else
     for (int kt = 0; kt < NKT_; ++kt) {
       const int s = kt % GEMM_STAGES, u = kt / GEMM_STAGES;
       if (u > 0) mbar_wait(EMPTY(s), (u - 1) & 1, s_abort);
@@ -399,7 +444,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) upd_gemm_kernel(GemmArgs a, int*
         for (int q = 0; q < 32; ++q) x[q] = (q < nc && ((word >> q) & 1u)) ? tf32_rn(__uint_as_float(v[q])) : 0.f;
       }
 #pragma unroll 1
-      for (int part = 0; part < (EPI == 0 && a.OutLo ? 2 : 1); ++part) {
+      for (int part = 0; part < (EPI == 0 && a.OutLo && !a.onchip_lo ? 2 : 1); ++part) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           if (q * 4 < nc) {
@@ -409,7 +454,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) upd_gemm_kernel(GemmArgs a, int*
               float t = x[q * 4 + e];
               if (EPI == 0) {
                 const int col = c0 + q * 4 + e;
-                const float hi = col == a.H ? 1.f : tf32_rn(t);          // columns above H are 0 (zero weight rows)
+                const float hi = col == a.H ? 1.f : (a.onchip_lo ? t : tf32_rn(t));   // columns above H are 0 (zero weight rows)
                 t = part == 0 ? hi : (col == a.H ? 0.f : tf32_rn(t - hi));
               }
               o[e] = t;
@@ -1206,18 +1251,20 @@ extern "C" int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32
   const int dbg = dbg_env ? atoi(dbg_env) : 0;
   // which GEMM variant runs (both are kept and tested against each other): measured on the C3 minibatch, the persistent
   // double-buffered kernel wins for the dgrad (33.5 vs 38 us) and loses for the 3xTF32 forward (81 vs 75 us)
+  const char* ol_env = getenv("MBO_UPD_ONCHIP_LO");
+  const int onchip_lo = ol_env ? atoi(ol_env) != 0 : 1;
   const char* pf_env = getenv("MBO_UPD_PERSIST_FWD");
   const char* pd_env = getenv("MBO_UPD_PERSIST_DGRAD");
-  const bool persist_fwd = pf_env ? atoi(pf_env) != 0 : false;
+  const bool persist_fwd = (pf_env ? atoi(pf_env) != 0 : false) && !onchip_lo;
   const bool persist = pd_env ? atoi(pd_env) != 0 : true;
   const int pg_grid = g_num_sms < tiles ? g_num_sms : tiles;
 
   upd_pack_kernel<<<(9 * IMG_FLOATS + 255) / 256, 256, 0, st>>>(net, ws);
-  upd_layer0_kernel<<<4 * THIN_CTAS, THIN_THREADS, 0, st>>>(net, states, R, ws.Hs[0], ws.Hl[0]);
+  upd_layer0_kernel<<<4 * THIN_CTAS, THIN_THREADS, 0, st>>>(net, states, R, ws.Hs[0], onchip_lo ? nullptr : ws.Hl[0]);
   for (int l = 0; l < 3; ++l) {
     GemmArgs g{};
     g.A = ws.Hs[l]; g.Alo = ws.Hl[l]; g.Bimg = ws.img_fwd[l]; g.Bimg_lo = ws.img_fwl[l]; g.Out = ws.Hs[l + 1];
-    g.OutLo = l < 2 ? ws.Hl[l + 1] : nullptr; g.bits_out = l < 2 ? ws.hbits[l] : nullptr; g.R = R; g.H = H; g.dbg = dbg;
+    g.OutLo = l < 2 ? ws.Hl[l + 1] : nullptr; g.bits_out = l < 2 ? ws.hbits[l] : nullptr; g.R = R; g.H = H; g.dbg = dbg; g.onchip_lo = onchip_lo;
     if (l == 2) { g.w4 = W[4]; g.b4 = b[4]; g.logits = ws.logits; }
     if (persist_fwd) upd_gemm_persist_kernel<0><<<pg_grid, PG_THREADS, PG_SMEM, st>>>(g, ws.err);
     else upd_gemm_kernel<0><<<tiles, GEMM_THREADS, GEMM_SMEM, st>>>(g, ws.err);
