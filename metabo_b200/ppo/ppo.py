@@ -126,6 +126,7 @@ class PPO:
         self.use_update_graph = self.world == 1 and os.environ.get("MBO_NO_GRAPHS") is None and \
             self.params.get("update_graph", True)
         self._upd = None        # (static inputs, CUDAGraph, static outputs) of one captured optimiser step
+        self._ep = None         # native backend: one captured EPOCH (all minibatch steps) over static copies of the batch
         backend = self.params.get("update_backend", "native")
         if backend not in ("native", "autograd"):
             raise ValueError("update_backend must be 'native' or 'autograd'")
@@ -313,6 +314,43 @@ class PPO:
         g.replay()
         return out.clone()
 
+    _MB_KEYS = ("states", "actions", "tdlamrets", "advs", "logprobs_old")
+
+    def _graphed_epoch(self, order, local_mb):
+        """All optimiser steps of one epoch (ppo.py:127-178) as ONE captured CUDA graph (native backend): the batch lives
+        in static device buffers, the shuffled order in a static index tensor, every minibatch is gathered by a
+        captured index_select at its fixed offset; a replay reads the new order / batch.  Removes ~0.15 ms of host
+        launch overhead per optimiser step (80 graph launches per iteration -> 4)."""
+        br = self.batch_recorder
+        buf = br.buf
+        n = br.B * br.T
+        flat = {k: buf[k].reshape((n,) + tuple(buf[k].shape[2:])) for k in self._MB_KEYS}
+        sig = tuple((k, tuple(v.shape), v.dtype) for k, v in flat.items())
+        if self._ep is None or self._ep["sig"] != sig:
+            static = {k: v.clone() for k, v in flat.items()}
+            perm = torch.zeros(n, dtype=torch.int64, device=self.device)
+            bounds = br._minibatch_bounds(local_mb)
+            E_max = max(b - a for a, b in bounds)
+            self._policy_grad_op(E_max, *flat["states"].shape[1:])          # size the workspaces before the capture
+            if self.pi.use_value_network and self.native_value_supported(self.pi) and (self._vg is None or self._vg.E < E_max):
+                self._vg = ops.PPOValueGrad(E_max, self.pi.value_net.arch_spec[0], self.device)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                sums = torch.zeros(4, device=self.device)
+                for a, b in bounds:
+                    sel = perm[a:b]
+                    sums = sums + self._update_step({k: v.index_select(0, sel) for k, v in static.items()})
+            self._ep = dict(sig=sig, static=static, perm=perm, graph=g, sums=sums, bounds=bounds, src=None)
+        ep = self._ep
+        if ep["src"] is not buf["states"]:                 # a new batch: refresh the static copies once per iteration
+            for k, v in flat.items():
+                ep["static"][k].copy_(v)
+            ep["src"] = buf["states"]
+        ep["perm"].copy_(torch.as_tensor(order, dtype=torch.int64), non_blocking=False)
+        ep["graph"].replay()
+        return ep["sums"].clone(), len(ep["bounds"])
+
     def optimize_on_batch(self):
         now = time.time()
         self.iter_log_str += " OPTIMIZING...\n"
@@ -334,7 +372,11 @@ class PPO:
         for ep in range(self.params["n_epochs"]):
             sums = torch.zeros(4, device=self.device)
             n_minibatches = 0
-            for mb in self.batch_recorder.iterate_device(local_mb, shuffle=True):
+            if (self.update_backend == "native" and self.use_update_graph and self.stats["n_optsteps"] > 0
+                    and self.params.get("epoch_graph", True)):
+                sums, n_minibatches = self._graphed_epoch(self.batch_recorder._order(True), local_mb)
+                self.stats["n_optsteps"] += n_minibatches
+            for mb in (() if n_minibatches else self.batch_recorder.iterate_device(local_mb, shuffle=True)):
                 mb = {k: v for k, v in mb.items() if k in ("states", "actions", "tdlamrets", "advs", "logprobs_old")}
                 graphable = self.use_update_graph and mb["states"].shape[0] == local_mb and self.stats["n_optsteps"] > 0
                 sums += self._graphed_update(mb) if graphable else self._update_step(mb)

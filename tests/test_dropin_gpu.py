@@ -274,6 +274,6 @@ def test_graph_captured_ppo_update_equals_eager(golden_dir, tmp_path, monkeypatc
 
     w_e, _ = run(False, "eager")
     w_g, ppo = run(True, "graph")
-    assert ppo._upd is not None                                   # the graph path was taken
+    assert ppo._upd is not None or ppo._ep is not None            # a graph path was taken (native backend: one graph per epoch)
     assert ppo.stats["n_optsteps"] == 2 * 2 * 8
     assert float((w_e - w_g).abs().max()) <= 1e-5 * float(w_e.abs().max())
