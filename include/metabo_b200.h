@@ -258,6 +258,19 @@ int mbo_ppo_value_grad(int E, size_t state_stride, int t_col, int T_col, int Hv,
                        float* const* dW, float* const* db, float* values, float* vterms, void* workspace,
                        size_t workspace_bytes, void* stream);
 
+/* Minibatch gather + advantage normalisation of one optimiser step (ppo.py:129-144; batchrecorder.py:318-333 yields the
+ * shuffled minibatches): transitions sel[0..E) (device int64 indices into the flattened batch) are gathered from the
+ * batch arrays; advantages become (adv - mean) / std with the biased std of the minibatch (left alone if std is 0 / NaN).
+ * row_floats = M * F floats per state.  logp_old_all may be NULL (zeros are written). */
+int mbo_ppo_prepare_minibatch(int E, size_t row_floats, const int64_t* sel, const float* states_all,
+                              const int32_t* actions_all, const float* advs_all, const float* tdlamrets_all,
+                              const float* logp_old_all, int normalize_advs, float* states, int32_t* actions,
+                              float* advs, float* tdlamrets, float* logp_old, void* stream);
+/* out4 = {loss_ppo, loss_value, loss_ent, loss} (ppo.py:158-168) from mbo_ppo_policy_grad's terms [E,4] and
+ * mbo_ppo_value_grad's vterms [E] (NULL: no value net). */
+int mbo_ppo_loss_sums(int E, const float* terms, const float* vterms, float inv_n_global, float value_coeff,
+                      float ent_coeff, float* out4, void* stream);
+
 /* Adam step (ppo.py:93, torch.optim.Adam defaults: no weight decay, no amsgrad) over n <= 32 parameter tensors in
  * one launch: m = lerp(m, g, 1 - beta1); v = beta2 v + (1 - beta2) g^2; p -= lr / (1 - beta1^t) * m /
  * (sqrt(v) / sqrt(1 - beta2^t) + eps).  p, g, m, v: HOST arrays of n device pointers (fp32), sizes: HOST array of

@@ -1478,3 +1478,97 @@ extern "C" int mbo_ppo_value_grad(int E, size_t state_stride, int t_col, int T_c
   MBO_LAUNCH_CHECK();
   return MBO_OK;
 }
+
+// ======================================================================================================================
+// Minibatch gather + advantage normalisation (ppo.py:129-144) and the logged loss sums (ppo.py:158-176) as two / one
+// launches instead of ~30 torch kernels per optimiser step.
+// ======================================================================================================================
+namespace mbo {
+namespace upd {
+
+// block 0: scalars of the E selected transitions + (adv - mean) / std with the biased std in double (ppo.py:141-144: left
+// alone if std is 0 or NaN); blocks 1..: state rows
+__global__ void __launch_bounds__(256) prep_kernel(int E, size_t row_floats, const long long* __restrict__ sel,
+                                                    const float* __restrict__ states_all, const int32_t* __restrict__ actions_all,
+                                                    const float* __restrict__ advs_all, const float* __restrict__ ret_all,
+                                                    const float* __restrict__ lpo_all, int normalize,
+                                                    float* __restrict__ states, int32_t* __restrict__ actions,
+                                                    float* __restrict__ advs, float* __restrict__ ret, float* __restrict__ lpo) {
+  if (blockIdx.x == 0) {
+    __shared__ double s_red[8];
+    double s = 0.0, s2 = 0.0;
+    for (int e = threadIdx.x; e < E; e += 256) { const double a = (double)advs_all[sel[e]]; s += a; s2 += a * a; }
+    s = block_sum(s, s_red);
+    s2 = block_sum(s2, s_red);
+    const double mean = s / E;
+    const double var = fmax(s2 / E - mean * mean, 0.0);
+    const double sd = sqrt(var);
+    const bool ok = normalize && sd > 0.0 && !isnan(sd);
+    for (int e = threadIdx.x; e < E; e += 256) {
+      const long long i = sel[e];
+      const float a = advs_all[i];
+      advs[e] = ok ? (float)(((double)a - mean) / sd) : a;
+      actions[e] = actions_all[i];
+      ret[e] = ret_all[i];
+      lpo[e] = lpo_all ? lpo_all[i] : 0.f;
+    }
+    return;
+  }
+  const int per = (E + (int)gridDim.x - 2) / ((int)gridDim.x - 1);
+  const int e0 = ((int)blockIdx.x - 1) * per, e1 = min(E, e0 + per);
+  for (int e = e0; e < e1; ++e) {
+    const float* src = states_all + (size_t)sel[e] * row_floats;
+    float* dst = states + (size_t)e * row_floats;
+    if ((row_floats & 3) == 0) {
+      for (size_t i = threadIdx.x; i < row_floats / 4; i += 256) ((float4*)dst)[i] = ((const float4*)src)[i];
+    } else {
+      for (size_t i = threadIdx.x; i < row_floats; i += 256) dst[i] = src[i];
+    }
+  }
+}
+
+// out = {loss_ppo, loss_value, loss_ent, loss} of ppo.py:158-168 from the per-transition terms
+__global__ void __launch_bounds__(256) loss_sums_kernel(int E, const float* __restrict__ terms, const float* __restrict__ vterms,
+                                                         float inv_n, float value_coeff, float ent_coeff, float* __restrict__ out) {
+  __shared__ double s_red[8];
+  double p = 0.0, h = 0.0, v = 0.0;
+  for (int e = threadIdx.x; e < E; e += 256) {
+    p += (double)terms[e * 4 + 2];
+    h += (double)terms[e * 4 + 1];
+    v += vterms ? (double)vterms[e] : 0.0;
+  }
+  p = block_sum(p, s_red);
+  h = block_sum(h, s_red);
+  v = block_sum(v, s_red);
+  if (threadIdx.x == 0) {
+    const float l_ppo = (float)p, l_val = (float)(v * inv_n), l_ent = (float)(-h * inv_n);
+    out[0] = l_ppo; out[1] = l_val; out[2] = l_ent;
+    out[3] = l_ppo + value_coeff * l_val + ent_coeff * l_ent;
+  }
+}
+
+}  // namespace upd
+}  // namespace mbo
+
+extern "C" int mbo_ppo_prepare_minibatch(int E, size_t row_floats, const int64_t* sel, const float* states_all,
+                                         const int32_t* actions_all, const float* advs_all, const float* tdlamrets_all,
+                                         const float* logp_old_all, int normalize_advs, float* states, int32_t* actions,
+                                         float* advs, float* tdlamrets, float* logp_old, void* stream) {
+  MBO_CHECK_ARG(E > 0 && row_floats > 0, "mbo_ppo_prepare_minibatch: E, row_floats must be > 0");
+  MBO_CHECK_ARG(sel && states_all && actions_all && advs_all && tdlamrets_all && states && actions && advs && tdlamrets &&
+                logp_old, "mbo_ppo_prepare_minibatch: null pointer");
+  const int nb = 1 + (E < 296 ? E : 296);
+  mbo::upd::prep_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(E, row_floats, (const long long*)sel, states_all, actions_all,
+                                                              advs_all, tdlamrets_all, logp_old_all, normalize_advs, states,
+                                                              actions, advs, tdlamrets, logp_old);
+  MBO_LAUNCH_CHECK();
+  return MBO_OK;
+}
+
+extern "C" int mbo_ppo_loss_sums(int E, const float* terms, const float* vterms, float inv_n_global, float value_coeff,
+                                 float ent_coeff, float* out4, void* stream) {
+  MBO_CHECK_ARG(E > 0 && terms && out4, "mbo_ppo_loss_sums: bad arguments");
+  mbo::upd::loss_sums_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(E, terms, vterms, inv_n_global, value_coeff, ent_coeff, out4);
+  MBO_LAUNCH_CHECK();
+  return MBO_OK;
+}

@@ -365,6 +365,28 @@ class PPOPolicyGrad:
         return v
 
 
+def ppo_prepare_minibatch(sel, flat, normalize, out):
+    """Gathers the transitions `sel` (int64 device indices) of the flattened batch `flat` (dict: states [n,M,F] f32,
+    actions [n] i32, advs / tdlamrets / logprobs_old [n] f32) into the preallocated minibatch tensors `out` and
+    normalises the advantages (ppo.py:141-144)."""
+    _chk(sel, torch.int64, "sel")
+    E = sel.shape[0]
+    st = flat["states"]
+    lpo = flat.get("logprobs_old")
+    L.check(L.lib().mbo_ppo_prepare_minibatch(E, st.shape[1] * st.shape[2], _p(sel), _p(st), _p(flat["actions"]),
+                                              _p(flat["advs"]), _p(flat["tdlamrets"]), _p(lpo), int(bool(normalize)),
+                                              _p(out["states"]), _p(out["actions"]), _p(out["advs"]), _p(out["tdlamrets"]),
+                                              _p(out["logprobs_old"]), _stream()), "mbo_ppo_prepare_minibatch")
+    return out
+
+
+def ppo_loss_sums(terms, vterms, n_global, value_coeff, ent_coeff, out):
+    E = terms.shape[0]
+    L.check(L.lib().mbo_ppo_loss_sums(E, _p(terms), _p(vterms), 1.0 / float(n_global), float(value_coeff), float(ent_coeff),
+                                      _p(out), _stream()), "mbo_ppo_loss_sums")
+    return out
+
+
 class PPOValueGrad:
     """Workspace + call wrapper of `mbo_ppo_value_grad` (value-net forward + backward of one optimiser step)."""
 

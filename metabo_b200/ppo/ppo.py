@@ -141,6 +141,8 @@ class PPO:
         self._pg_grads = None   # persistent gradient buffers of the policy net (written by the kernels)
         self._vg = None         # ops.PPOValueGrad
         self._vg_grads = None
+        self._loss4 = None
+        self._mbufs = {}        # minibatch buffers of mbo_ppo_prepare_minibatch, by minibatch size
 
         self.stats = dict()
         self.stats["n_timesteps"] = 0
@@ -208,14 +210,15 @@ class PPO:
                                 actions.to(torch.int32).contiguous())
         return lp
 
-    def _update_step_native(self, mb):
-        """ppo.py:129-178 with the policy net's forward + backward on the hand-written kernels
-        (mbo_ppo_policy_grad); value net (2 inputs per minibatch row) on torch autograd."""
+    def _update_step_native(self, mb, prepared=False):
+        """ppo.py:129-178 on the hand-written kernels: policy net (mbo_ppo_policy_grad), value net (mbo_ppo_value_grad),
+        Adam (mbo_adam_step).  prepared=True: `mb` comes from mbo_ppo_prepare_minibatch (gathered, advantages already
+        normalised, int32 actions) and the logged loss sums are one more kernel -- no torch op is left in the step."""
         states, actions, tdlamrets = mb["states"], mb["actions"], mb["tdlamrets"]
-        advs = mb["advs"] if self.params["loss_type"] == "GAElam" else mb["tdlamrets"]
+        advs = mb["advs"] if (prepared or self.params["loss_type"] == "GAElam") else mb["tdlamrets"]
         E, M, Fs = states.shape
         n_global = E * self.world
-        if self.params["normalize_advs"]:
+        if self.params["normalize_advs"] and not prepared:
             advs = normalize_advantages(advs, self.world)
         pi = self.pi
         fcs = list(pi.policy_net.fc)
@@ -233,8 +236,6 @@ class PPO:
                          n_global, dW, db)
         for l, gw, gb in zip(fcs, dW, db):
             l.weight.grad, l.bias.grad = gw, gb
-        l_ppo = terms[:, 2].sum()
-        l_ent = -terms[:, 1].sum() / n_global
         if pi.use_value_network and self.native_value_supported(pi):
             vfc = list(pi.value_net.fc)
             if self._vg is None or self._vg.E < E:
@@ -247,6 +248,12 @@ class PPO:
                                  self.params["value_coeff"] / n_global, vW, vb)
             for l, gw, gb in zip(vfc, vW, vb):
                 l.weight.grad, l.bias.grad = gw, gb
+            if prepared and self.world == 1:
+                self.optimizer.step()
+                if self._loss4 is None:
+                    self._loss4 = torch.zeros(4, device=self.device)
+                return ops.ppo_loss_sums(terms, vterms, n_global, self.params["value_coeff"], self.params["ent_coeff"],
+                                         self._loss4)
             l_val = vterms.sum() / n_global
         elif pi.use_value_network:
             tT = torch.stack([states[:, 0, pi.t_idx], states[:, 0, pi.T_idx]], dim=1)
@@ -258,6 +265,8 @@ class PPO:
             l_val = torch.sum(tdlamrets ** 2) / n_global       # the reference's value head is the constant 0
         allreduce_gradients(list(self.pi.parameters()), self.world)
         self.optimizer.step()
+        l_ppo = terms[:, 2].sum()
+        l_ent = -terms[:, 1].sum() / n_global
         loss = l_ppo + self.params["value_coeff"] * l_val + self.params["ent_coeff"] * l_ent
         return torch.stack([l_ppo, l_val, l_ent, loss]).detach()
 
@@ -316,6 +325,14 @@ class PPO:
 
     _MB_KEYS = ("states", "actions", "tdlamrets", "advs", "logprobs_old")
 
+    def _minibatch_buffers(self, E, states):
+        if E not in self._mbufs:
+            f = lambda dt: torch.zeros(E, dtype=dt, device=self.device)
+            self._mbufs[E] = dict(states=torch.zeros((E,) + tuple(states.shape[1:]), dtype=torch.float32, device=self.device),
+                                  actions=f(torch.int32), advs=f(torch.float32), tdlamrets=f(torch.float32),
+                                  logprobs_old=f(torch.float32))
+        return self._mbufs[E]
+
     def _graphed_epoch(self, order, local_mb):
         """All optimiser steps of one epoch (ppo.py:127-178) as ONE captured CUDA graph (native backend): the batch lives
         in static device buffers, the shuffled order in a static index tensor, every minibatch is gathered by a
@@ -334,13 +351,27 @@ class PPO:
             self._policy_grad_op(E_max, *flat["states"].shape[1:])          # size the workspaces before the capture
             if self.pi.use_value_network and self.native_value_supported(self.pi) and (self._vg is None or self._vg.E < E_max):
                 self._vg = ops.PPOValueGrad(E_max, self.pi.value_net.arch_spec[0], self.device)
+            src = dict(static)
+            if self.params["loss_type"] != "GAElam":
+                src["advs"] = static["tdlamrets"]
+            fused = (self.world == 1 and all(v.is_contiguous() for v in static.values()) and static["actions"].dtype == torch.int32
+                     and self.params.get("fused_minibatch", True))
+            for a, b in bounds:
+                self._minibatch_buffers(b - a, static["states"])
+            if self._loss4 is None:
+                self._loss4 = torch.zeros(4, device=self.device)
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 sums = torch.zeros(4, device=self.device)
                 for a, b in bounds:
                     sel = perm[a:b]
-                    sums = sums + self._update_step({k: v.index_select(0, sel) for k, v in static.items()})
+                    if fused:       # gather + advantage normalisation in one kernel, loss sums in another
+                        mbuf = ops.ppo_prepare_minibatch(sel, src, self.params["normalize_advs"],
+                                                         self._minibatch_buffers(b - a, static["states"]))
+                        sums = sums + self._update_step_native(mbuf, prepared=True)
+                    else:
+                        sums = sums + self._update_step({k: v.index_select(0, sel) for k, v in static.items()})
             self._ep = dict(sig=sig, static=static, perm=perm, graph=g, sums=sums, bounds=bounds, src=None)
         ep = self._ep
         if ep["src"] is not buf["states"]:                 # a new batch: refresh the static copies once per iteration

@@ -260,20 +260,33 @@ def test_graph_captured_ppo_update_equals_eager(golden_dir, tmp_path, monkeypatc
                 f_opts={"bound_translation": 0.1, "bound_scaling": 0.1, "M": 50})
     gym.register(id=spec["env_id"], entry_point="metabo.environment.metabo_gym:MetaBO", max_episode_steps=5, kwargs=spec)
 
-    def run(update_graph, name):
+    def run(update_graph, name, **extra):
         params = {"batch_size": 80, "max_steps": 160, "minibatch_size": 10, "n_epochs": 2, "lr": 1e-3, "epsilon": 0.15,
                   "value_coeff": 1.0, "ent_coeff": 0.01, "gamma": 0.98, "lambda": 0.98, "loss_type": "GAElam",
                   "normalize_advs": True, "n_workers": 4, "env_id": spec["env_id"], "seed": 0, "env_seeds": [0, 1, 2, 3],
                   "update_graph": update_graph,
                   "policy_options": {"activations": "relu", "arch_spec": [200] * 4, "use_value_network": True, "t_idx": -2,
                                      "T_idx": -1, "arch_spec_value": [200] * 4}}
+        params.update(extra)
         ppo = PPO(policy_fn=lambda o, a, d: NeuralAF(o, a, d, options=params["policy_options"]), params=params,
                   logpath=str(tmp_path / name), save_interval=10, verbose=True)
         ppo.train()
         return torch.cat([p.detach().reshape(-1) for p in ppo.pi.parameters()]), ppo
 
     w_e, _ = run(False, "eager")
-    w_g, ppo = run(True, "graph")
-    assert ppo._upd is not None or ppo._ep is not None            # a graph path was taken (native backend: one graph per epoch)
-    assert ppo.stats["n_optsteps"] == 2 * 2 * 8
+    # same kernels, same order: per-step graphs and the one-graph-per-epoch path (minibatches gathered by torch ops)
+    # follow the eager trajectory exactly
+    w_s, ppo_s = run(True, "step_graph", epoch_graph=False)
+    assert ppo_s._upd is not None and ppo_s.stats["n_optsteps"] == 2 * 2 * 8
+    assert float((w_e - w_s).abs().max()) <= 1e-5 * float(w_e.abs().max())
+    w_g, ppo = run(True, "epoch_graph", fused_minibatch=False)
+    assert ppo._ep is not None and ppo.stats["n_optsteps"] == 2 * 2 * 8
     assert float((w_e - w_g).abs().max()) <= 1e-5 * float(w_e.abs().max())
+    # default: minibatch gather + advantage normalisation in mbo_ppo_prepare_minibatch (double sums instead of torch's fp32
+    # reductions: last-bit differences in the advantages, which Adam turns into +-lr steps wherever a gradient entry is at
+    # noise level -- this freshly initialised policy): logged losses agree, weights within Adam's step bound
+    w_f, ppo_f = run(True, "epoch_fused")
+    assert ppo_f._ep is not None
+    log = lambda p: [float(x.split("=")[1]) for line in p.iter_log_str.splitlines() if "loss_ppo" in line for x in line.split(",")[1:]]
+    np.testing.assert_allclose(log(ppo_f), log(ppo), rtol=1e-3)
+    assert float((w_f - w_g).abs().max()) <= 2.5 * 1e-3 * 24

@@ -290,3 +290,37 @@ def test_gemm_kernel_variants_agree_bitwise(monkeypatch):
         for k in ("h1", "h2", "h3", "h4", "dz1", "dz2", "dz3", "dz4", "logits", "dlogits"):
             assert torch.equal(v[k], v0[k]), k
         assert all(torch.equal(a, b) for a, b in zip(dW + db, dW0 + db0))
+
+
+def test_prepare_minibatch_and_loss_sums_match_torch():
+    """mbo_ppo_prepare_minibatch (gather + ppo.py:141-144 advantage normalisation) and mbo_ppo_loss_sums (ppo.py:158-168)
+    against the torch expressions of the drop-in layer."""
+    from metabo_b200 import ops
+    from metabo_b200.ppo.ppo import normalize_advantages
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(7)
+    n, M, F, E = 50, 13, 6, 17
+    flat = dict(states=torch.randn(n, M, F, generator=g).to(dev), actions=torch.randint(0, M, (n,), generator=g).to(dev).to(torch.int32),
+                advs=torch.randn(n, generator=g).to(dev) * 3 + 1, tdlamrets=torch.randn(n, generator=g).to(dev),
+                logprobs_old=torch.randn(n, generator=g).to(dev))
+    sel = torch.randperm(n, generator=g)[:E].to(dev)
+    out = dict(states=torch.zeros(E, M, F, device=dev), actions=torch.zeros(E, dtype=torch.int32, device=dev),
+               advs=torch.zeros(E, device=dev), tdlamrets=torch.zeros(E, device=dev), logprobs_old=torch.zeros(E, device=dev))
+    for normalize in (True, False):
+        ops.ppo_prepare_minibatch(sel, flat, normalize, out)
+        torch.cuda.synchronize()
+        for k in ("states", "actions", "tdlamrets", "logprobs_old"):
+            assert torch.equal(out[k], flat[k].index_select(0, sel)), k
+        ref = flat["advs"].index_select(0, sel)
+        ref = normalize_advantages(ref) if normalize else ref
+        assert float((out["advs"] - ref).abs().max()) <= 2e-6 * float(ref.abs().max())
+    flat["advs"][:] = 2.5                                            # std == 0: advantages are left alone
+    ops.ppo_prepare_minibatch(sel, flat, True, out)
+    assert bool((out["advs"] == 2.5).all())
+    terms = torch.randn(E, 4, generator=g).to(dev)
+    vterms = torch.rand(E, generator=g).to(dev)
+    out4 = torch.zeros(4, device=dev)
+    ops.ppo_loss_sums(terms, vterms, 2 * E, 0.7, 0.01, out4)
+    l_ppo, l_val, l_ent = terms[:, 2].sum(), vterms.sum() / (2 * E), -terms[:, 1].sum() / (2 * E)
+    ref4 = torch.stack([l_ppo, l_val, l_ent, l_ppo + 0.7 * l_val + 0.01 * l_ent])
+    assert float((out4 - ref4).abs().max()) <= 1e-5 * float(ref4.abs().max())
