@@ -1251,6 +1251,10 @@ extern "C" int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32
   const int dbg = dbg_env ? atoi(dbg_env) : 0;
   // which GEMM variant runs (both are kept and tested against each other): measured on the C3 minibatch, the persistent
   // double-buffered kernel wins for the dgrad (33.5 vs 38 us) and loses for the 3xTF32 forward (81 vs 75 us)
+  const char* l0_env = getenv("MBO_L0_CTAS");
+  const char* w0_env = getenv("MBO_WG0_CTAS");
+  const int l0_ctas = l0_env ? atoi(l0_env) : 4 * THIN_CTAS;
+  const int wg0_ctas = w0_env ? (atoi(w0_env) < THIN_CTAS ? atoi(w0_env) : THIN_CTAS) : WG0_CTAS;
   const char* ol_env = getenv("MBO_UPD_ONCHIP_LO");
   const int onchip_lo = ol_env ? atoi(ol_env) != 0 : 1;
   const char* pf_env = getenv("MBO_UPD_PERSIST_FWD");
@@ -1260,7 +1264,7 @@ extern "C" int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32
   const int pg_grid = g_num_sms < tiles ? g_num_sms : tiles;
 
   upd_pack_kernel<<<(9 * IMG_FLOATS + 255) / 256, 256, 0, st>>>(net, ws);
-  upd_layer0_kernel<<<4 * THIN_CTAS, THIN_THREADS, 0, st>>>(net, states, R, ws.Hs[0], onchip_lo ? nullptr : ws.Hl[0]);
+  upd_layer0_kernel<<<l0_ctas, THIN_THREADS, 0, st>>>(net, states, R, ws.Hs[0], onchip_lo ? nullptr : ws.Hl[0]);
   for (int l = 0; l < 3; ++l) {
     GemmArgs g{};
     g.A = ws.Hs[l]; g.Alo = ws.Hl[l]; g.Bimg = ws.img_fwd[l]; g.Bimg_lo = ws.img_fwl[l]; g.Out = ws.Hs[l + 1];
@@ -1289,9 +1293,9 @@ extern "C" int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32
   wa.part = ws.part_big; wa.R = R; wa.H = H;
 
   upd_wgrad_kernel<<<dim3(WG_SPLIT, 3), GEMM_THREADS, WG_SMEM, st>>>(wa, ws.err);
-  upd_wgrad0_kernel<<<WG0_CTAS, THIN_THREADS, 0, st>>>(net, states, R, ws.dZ[0], ws.Hs[0], ws.part_l0);
+  upd_wgrad0_kernel<<<wg0_ctas, THIN_THREADS, 0, st>>>(net, states, R, ws.dZ[0], ws.Hs[0], ws.part_l0);
   const int nblkA = (3 * H * (H + 1) + 255) / 256, nblkT = ((H + 1) + H * (F + 1) + 7) / 8;
-  upd_reduce_kernel<<<nblkA + nblkT, 256, 0, st>>>(net, ws, THIN_CTAS, WG0_CTAS, nblkA);
+  upd_reduce_kernel<<<nblkA + nblkT, 256, 0, st>>>(net, ws, THIN_CTAS, wg0_ctas, nblkA);
   MBO_CUDA(cudaMemcpyAsync(terms, ws.terms, (size_t)E * 16, cudaMemcpyDeviceToDevice, st));
   MBO_LAUNCH_CHECK();
   return MBO_OK;
