@@ -5,18 +5,19 @@
 // F -> H -> H -> H -> H -> 1 ReLU policy net.  One call = forward with saved activations, loss terms,
 // dlogits, dgrad chain, wgrad of every layer.  `rows` R = E episodes x M candidates (60 x 966 in C3).
 //
-// Data layout in HBM (workspace): activations H1..H4 and pre-activation gradients dZ1..dZ4 are row-major
-// [R, 208] fp32 already rounded to tf32 (round-to-nearest, so the tensor cores' truncation is exact), column H
-// of every H_l is a ones column (bias rides inside the GEMMs: forward Wb = [W | b], wgrad column H = db),
-// columns above are zero.
+// Data layout in HBM (workspace): activations H1..H4 are row-major [R, 208] plain fp32, stored once; the forward GEMM's
+// loader threads split them in shared memory into tf32 hi + lo (3xTF32).  Pre-activation gradients dZ1..dZ4 are
+// row-major [R, 208] fp32 rounded to nearest tf32 by their producers (the tensor core's truncation is then exact).
+// Column H of every H_l is a ones column (bias rides inside the GEMMs: forward Wb = [W | b], wgrad column H = db),
+// columns above are zero.  ReLU decisions of h2, h3 travel as bit words [R][8] from the forward to the dgrad epilogue.
 //
 // Kernels
 //   upd_pack_kernel      W1..W3 -> UMMA-canonical K-major images [W | b] (forward) and W^T (dgrad)
 //   upd_layer0_kernel    h1 = relu(x W0^T + b0)                              CUDA cores (K = F <= 8)
-//   upd_gemm_kernel<0>   h_{l+1} = relu([h_l,1] Wb^T) (+ head logit)         tcgen05 kind::tf32, A and B from smem
+//   upd_gemm_kernel<0>   h_{l+1} = relu([h_l,1] Wb^T) (+ head logit)         tcgen05 kind::tf32 x 3 (hi/lo), A and B from smem
 //   upd_loss_kernel      per episode: log-softmax, logp(a), entropy, clipped surrogate, dlogits
 //   upd_dz4_kernel       dZ4 = dlogit (x) w4 . [h4 > 0]  (+ partial sums of dw4, db4)
-//   upd_gemm_kernel<1>   dZ_l = (dZ_{l+1} W_l) . [h_l > 0] (ReLU bit words)   tcgen05 kind::tf32
+//   upd_gemm_kernel<1> / upd_dgrad_persist_kernel   dZ_l = (dZ_{l+1} W_l) . [h_l > 0]   tcgen05 kind::tf32
 //   upd_wgrad_kernel     dWb_l = dZ_{l+1}^T [h_l,1]  split-K over CTAs        tcgen05 kind::tf32, both operands MN-major
 //   upd_wgrad0_kernel    dW0 = (dH1 . [h1 > 0])^T x, db0                      CUDA cores
 //   upd_reduce_kernel    fixed-order sum of the split-K partials -> dW, db    (deterministic, no atomics)
@@ -25,6 +26,7 @@
 // chunk where the no-swizzle UMMA canonical layout wants it (K-major for forward / dgrad, MN-major for wgrad where
 // K = rows), completion is signalled with cp.async.mbarrier.arrive.noinc, the weight images arrive by one
 // cp.async.bulk per stage.  All GEMMs here are HBM-bound (50 FLOP/B at TF32), not tensor-bound.
+// Also here: the value net (v_* kernels, fp32 CUDA cores), Adam, minibatch gather / advantage normalisation, loss sums.
 #include <stdlib.h>
 #include "common.cuh"
 #include "tmem_ldst.cuh"
@@ -165,8 +167,7 @@ struct Ws {          // workspace carve-up (device pointers)
   float* img_fwl[3];  // lo parts
   float* img_dgr[3];  // W^T, KT stages
   float* img_dgp[3];  // W^T, 32 K values per stage (persistent dgrad)
-  float* Hs[4];      // h1..h4 (tf32-rounded "hi" parts)
-  float* Hl[3];      // lo parts of h1..h3 (3xTF32 forward)
+  float* Hs[4];      // h1..h4, plain fp32
   uint32_t* hbits[2]; // ReLU decisions of h2, h3: [R][8] words, bit q of word c = (h[row][32 c + q] > 0)
   float* dZ[4];      // dZ1..dZ4
   float* logits;
@@ -190,7 +191,6 @@ static size_t carve(int E, int M, unsigned char* base, Ws* w) {
   for (int l = 0; l < 3; ++l) t.img_dgr[l] = (float*)take((size_t)IMG_FLOATS * 4);
   for (int l = 0; l < 3; ++l) t.img_dgp[l] = (float*)take((size_t)IMG_FLOATS * 4);
   for (int l = 0; l < 4; ++l) t.Hs[l] = (float*)take(Rp * HP * 4);
-  for (int l = 0; l < 3; ++l) t.Hl[l] = (float*)take(Rp * HP * 4);
   for (int l = 0; l < 2; ++l) t.hbits[l] = (uint32_t*)take(Rp * 8 * 4);
   for (int l = 0; l < 4; ++l) t.dZ[l] = (float*)take(Rp * HP * 4);
   t.logits = (float*)take(Rp * 4);
@@ -235,7 +235,7 @@ __global__ void upd_pack_kernel(Net net, Ws ws) {
 
 // ---- layer 0 on CUDA cores ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(THIN_THREADS) upd_layer0_kernel(Net net, const float* __restrict__ states, int R,
-                                                                   float* __restrict__ H1, float* __restrict__ H1lo) {
+                                                                   float* __restrict__ H1) {
   const int cg = threadIdx.x % 52, rsub = threadIdx.x / 52;
   const int F = net.F, H = net.H;
   float w[4][MAXF], bias[4];
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(THIN_THREADS) upd_layer0_kernel(Net net, const
     float x[MAXF];
 #pragma unroll
     for (int f = 0; f < MAXF; ++f) x[f] = f < F ? __ldg(states + (size_t)r * net.F_state + net.col[f]) : 0.f;
-    float o[4], ol[4];
+    float o[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       // torch's Linear on the CPU accumulates the dot product first and adds the bias last
@@ -261,22 +261,18 @@ __global__ void __launch_bounds__(THIN_THREADS) upd_layer0_kernel(Net net, const
       for (int f = 0; f < MAXF; ++f) acc = fmaf(x[f], w[e][f], acc);
       const int j = cg * 4 + e;
       acc = fmaxf(acc + bias[e], 0.f);
-      o[e] = j < H ? (H1lo ? tf32_rn(acc) : acc) : (j == H ? 1.f : 0.f);
-      ol[e] = j < H ? tf32_rn(acc - o[e]) : 0.f;
+      o[e] = j < H ? acc : (j == H ? 1.f : 0.f);
     }
     *(float4*)(H1 + (size_t)r * HP + cg * 4) = make_float4(o[0], o[1], o[2], o[3]);
-    if (H1lo) *(float4*)(H1lo + (size_t)r * HP + cg * 4) = make_float4(ol[0], ol[1], ol[2], ol[3]);
   }
 }
 
 // ---- forward / dgrad GEMM -----------------------------------------------------------------------------------------
 struct GemmArgs {
-  const float* A;        // [R, HP] rows of this GEMM (h_l hi part for forward, dZ_{l+1} for dgrad)
-  const float* Alo;      // forward: lo part of h_l
+  const float* A;        // [R, HP] rows of this GEMM (h_l for the forward, dZ_{l+1} for the dgrad), plain fp32
   const float* Bimg;     // weight image (forward: hi parts)
   const float* Bimg_lo;  // forward: lo parts
-  float* Out;            // [R, HP] (forward: hi part of h_{l+1})
-  float* OutLo;          // forward: lo part of h_{l+1}, or nullptr (h4 feeds only the head and the wgrad)
+  float* Out;            // [R, HP]: h_{l+1} (fp32, unrounded) or dZ_l (rounded to tf32)
   const uint32_t* bits_in;   // dgrad: ReLU decisions of h_l (nullptr: no mask, the consumer applies it)
   uint32_t* bits_out;        // forward: ReLU decisions of h_{l+1} for the dgrad, or nullptr
   const float* w4;       // forward of the last hidden layer: head weights [H], else nullptr
@@ -284,7 +280,6 @@ struct GemmArgs {
   float* logits;         // [R]
   int R, H;
   int dbg;               // timing experiments (MBO_UPD_DBG): 1 no epilogue, 2 no MMAs, 4 no A loads, 8 no weight loads
-  int onchip_lo;         // forward: A is plain fp32 in HBM, its tf32 hi / lo split is made in shared memory by the loaders
 };
 
 // EPI 0: forward, 3xTF32 (stage = 16 K values x {hi, lo} of both operands, 3 MMAs per K = 8 step), epilogue ReLU +
@@ -331,7 +326,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) upd_gemm_kernel(GemmArgs a, i
     // ---- A loaders: lane -> (16-byte chunk quarter cq, row-in-group r8): the 8 lanes of one cq write 128 contiguous
     // bytes of one core-matrix column (conflict-free) and read 64 B per row ----
     const int r8 = lane & 7, cq = lane >> 3;
-    if (X3 && a.onchip_lo) {
+    if (X3) {
       // ---- forward, activations stored once as plain fp32: every thread copies 2 chunks (16 B) per stage and, two
       // stages later, splits exactly those chunks in place into tf32 hi (written back) and lo (second half of the
       // stage) -- only its own cp.async groups have to be complete, no cross-thread hand-off ----
@@ -383,14 +378,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) upd_gemm_kernel(GemmArgs a, i
           const int grow = brow0 + j * 8 + r8;               // j = 8-row group
           const bool ok = grow < a.R;
           if (a.dbg & 4) continue;
-          if (X3) {
-            const int arr = cq >> 1, c = cq & 1;               // lanes 0-15: hi part, 16-31: lo part; 2 chunks = the K tile
-            const float* src = (arr ? a.Alo : a.A) + (size_t)(ok ? grow : 0) * HP + kt * KT_ + c * 4;
-            cp_async16(dstA + arr * (TM * KT3 * 4) + c * (TM * 16) + j * 128 + r8 * 16, src, ok);
-          } else {
-            const float* src = a.A + (size_t)(ok ? grow : 0) * HP + kt * KT_ + cq * 4;
-            cp_async16(dstA + cq * (TM * 16) + j * 128 + r8 * 16, src, ok);
-          }
+          const float* src = a.A + (size_t)(ok ? grow : 0) * HP + kt * KT_ + cq * 4;
+          cp_async16(dstA + cq * (TM * 16) + j * 128 + r8 * 16, src, ok);
         }
       }
       cp_async_arrive(FULL(s));
@@ -443,8 +432,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) upd_gemm_kernel(GemmArgs a, i
 #pragma unroll
         for (int q = 0; q < 32; ++q) x[q] = (q < nc && ((word >> q) & 1u)) ? tf32_rn(__uint_as_float(v[q])) : 0.f;
       }
-#pragma unroll 1
-      for (int part = 0; part < (EPI == 0 && a.OutLo && !a.onchip_lo ? 2 : 1); ++part) {
+      {
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           if (q * 4 < nc) {
@@ -452,18 +440,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) upd_gemm_kernel(GemmArgs a, i
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               float t = x[q * 4 + e];
-              if (EPI == 0) {
-                const int col = c0 + q * 4 + e;
-                const float hi = col == a.H ? 1.f : (a.onchip_lo ? t : tf32_rn(t));   // columns above H are 0 (zero weight rows)
-                t = part == 0 ? hi : (col == a.H ? 0.f : tf32_rn(t - hi));
-              }
+              if (EPI == 0 && c0 + q * 4 + e == a.H) t = 1.f;          // ones column; columns above H are 0 (zero weight rows)
               o[e] = t;
             }
             *(float4*)(stg + lane * STG_PITCH + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
           }
         }
         __syncwarp();
-        float* outp = part == 0 ? a.Out : a.OutLo;
+        float* outp = a.Out;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r = i * 4 + cr, grow = wrow0 + r;
@@ -518,11 +502,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) upd_gemm_kernel(GemmArgs a, i
     // The pipeline reads 32 (forward) or 64 bytes per row and stage, i.e. every DRAM page of the tile 26 / 13 times
     // over; without this the kernel ran at ~1.3 TB/s of DRAM reads ----
     {
-      const int piece = lane & 7, arr = lane >> 3;                 // arr 0: A, 1: Alo (forward only)
-      const int r_lo = row0 + piece * 16 * GEMM_MB;
+      const int r_lo = row0 + lane * 16 * GEMM_MB;
       const int nrow = min(16 * GEMM_MB, a.R - r_lo);
-      if (nrow > 0 && (arr == 0 || (X3 && arr == 1)))
-        bulk_prefetch_l2((arr ? a.Alo : a.A) + (size_t)r_lo * HP, (uint32_t)nrow * HP * 4);
+      if (lane < 8 && nrow > 0) bulk_prefetch_l2(a.A + (size_t)r_lo * HP, (uint32_t)nrow * HP * 4);
     }
     // ---- weight stages: bulk copies of the packed images ----
     if (lane == 0) {
@@ -552,42 +534,35 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) upd_gemm_kernel(GemmArgs a, i
   }
 }
 
-// ---- persistent variant of the forward / dgrad GEMM ----------------------------------------------------------------
+// ---- persistent dgrad GEMM -----------------------------------------------------------------------------------------
 // One CTA per SM over a contiguous range of rows (R / grid, rounded up to 8), 128-row tiles inside it; two accumulators
-// in TMEM (2 x 256 columns) so that the epilogue warps drain tile i while the loaders / MMA warp already run tile i + 1;
-// 8 pipeline stages (7 in flight).  Warps 0-3: epilogue, 4-7: A loaders, 8: MMA issue, 9: weight stages.
-constexpr int PG_STAGES = 8;
+// in TMEM (2 x 256 columns) so that the epilogue warps drain tile i while the loaders / MMA warp already run tile i + 1.
+// Warps 0-3: epilogue, 4-7: A loaders, 8: MMA issue, 9: weight stages.  4 stages of 32 K values: every row gives a whole
+// 128-byte line per stage (lane -> (row of 4, chunk of 8)); the 16-byte chunk planes are padded by 16 B so that those
+// cp.async stores stay conflict-free.  Same MMA sequence per tile as upd_gemm_kernel<1>: bitwise identical results.
+constexpr int PG_STAGES = 4;
+constexpr int PG_KT = 32, PG_NKT = 7;
+constexpr int PG_LBO_A = TM * 16 + 16;
+constexpr int PG_A_STAGE = 8 * PG_LBO_A;                 // 16 512
+constexpr int PG_B_STAGE = HP * PG_KT * 4;               // 26 624
 constexpr int PG_THREADS = 320;
-constexpr int PG_STG_BYTES = 4 * 32 * STG_PITCH * 4;                                     // 18 432
-constexpr int PG_SMEM = PG_STAGES * (A_STAGE + B_STAGE) + 1024 + PG_STG_BYTES + 256;
+constexpr int PG_STG_BYTES = 4 * 32 * STG_PITCH * 4;     // 18 432
+constexpr int PG_SMEM = PG_STAGES * (PG_A_STAGE + PG_B_STAGE) + PG_STG_BYTES + 256;
 
-template <int EPI>
-__global__ void __launch_bounds__(PG_THREADS, 1) upd_gemm_persist_kernel(GemmArgs a, int* __restrict__ err) {
-  constexpr bool X3 = EPI == 0;
-  // forward: 8 stages of 8 K values (hi + lo of both operands); dgrad: 4 stages of 32 K values, so that every row gives a
-  // whole 128-byte line per stage (LDGSTS costs per line touched: 8 rows x 64 B per instruction ran at ~80 cycles per
-  // instruction, 4 rows x 128 B at ~28) -- chunk planes padded by 16 B to keep those stores conflict-free
-  constexpr int NKT_ = X3 ? NKT3 : 7;
-  constexpr int KT_ = X3 ? KT3 : 32;
-  constexpr int NST = X3 ? PG_STAGES : 4;
-  constexpr int LBO_A = X3 ? TM * 16 : TM * 16 + 16;
-  constexpr int A_ST = X3 ? A_STAGE : 8 * LBO_A;
-  constexpr int B_ST = X3 ? B_STAGE : HP * 32 * 4;
-  static_assert(NST * (A_ST + B_ST) <= PG_STAGES * (A_STAGE + B_STAGE) + 1024, "stage budget");
+__global__ void __launch_bounds__(PG_THREADS, 1) upd_dgrad_persist_kernel(GemmArgs a, int* __restrict__ err) {
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* sA = smem;
-  unsigned char* sB = smem + NST * A_ST;
-  float* s_stg = (float*)(smem + PG_STAGES * (A_STAGE + B_STAGE) + 1024);
-  uint64_t* bars = (uint64_t*)(smem + PG_STAGES * (A_STAGE + B_STAGE) + 1024 + PG_STG_BYTES);
+  unsigned char* sB = smem + PG_STAGES * PG_A_STAGE;
+  float* s_stg = (float*)(smem + PG_STAGES * (PG_A_STAGE + PG_B_STAGE));
+  uint64_t* bars = (uint64_t*)(smem + PG_STAGES * (PG_A_STAGE + PG_B_STAGE) + PG_STG_BYTES);
   uint32_t* s_tmem = (uint32_t*)(bars + 2 * PG_STAGES + 4);
   volatile int* s_abort = (volatile int*)(s_tmem + 1);
-  __shared__ float s_w4[HP];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar0 = smem_u32(bars);
   auto FULL = [&](int s) { return bar0 + 8u * s; };
-  auto EMPTY = [&](int s) { return bar0 + 8u * (NST + s); };
-  auto ACCF = [&](int i) { return bar0 + 8u * (2 * NST + i); };
-  auto ACCE = [&](int i) { return bar0 + 8u * (2 * NST + 2 + i); };
+  auto EMPTY = [&](int s) { return bar0 + 8u * (PG_STAGES + s); };
+  auto ACCF = [&](int i) { return bar0 + 8u * (2 * PG_STAGES + i); };
+  auto ACCE = [&](int i) { return bar0 + 8u * (2 * PG_STAGES + 2 + i); };
   // this CTA's rows
   const int rpc = (((a.R + (int)gridDim.x - 1) / (int)gridDim.x) + 7) & ~7;
   const int r_begin = min(a.R, (int)blockIdx.x * rpc), r_end = min(a.R, r_begin + rpc);
@@ -595,11 +570,10 @@ __global__ void __launch_bounds__(PG_THREADS, 1) upd_gemm_persist_kernel(GemmArg
 
   if (tid == 0) {
     *s_abort = 0;
-    for (int s = 0; s < NST; ++s) { mbar_init(FULL(s), 128 + 1); mbar_init(EMPTY(s), 1); }
+    for (int s = 0; s < PG_STAGES; ++s) { mbar_init(FULL(s), 128 + 1); mbar_init(EMPTY(s), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(ACCF(i), 1); mbar_init(ACCE(i), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (EPI == 0 && a.w4) for (int i = tid; i < HP; i += PG_THREADS) s_w4[i] = i < a.H ? a.w4[i] : 0.f;
   if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -617,7 +591,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) upd_gemm_persist_kernel(GemmArg
       const int slot = t & 1;
       const int wrow0 = r_begin + t * TM + warp * 32;
       uint32_t mbits[8];
-      if (EPI == 1) {
+      {                                                      // the row's ReLU words, fetched before the accumulator is ready
         const int row = wrow0 + lane;
         uint4 w0 = make_uint4(~0u, ~0u, ~0u, ~0u), w1 = w0;
         if (a.bits_in && row < r_end) {
@@ -631,7 +605,6 @@ __global__ void __launch_bounds__(PG_THREADS, 1) upd_gemm_persist_kernel(GemmArg
       tc_fence_after();
       const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16) + slot * 256;
       const bool live = wrow0 < r_end;                       // warp-uniform
-      float head = 0.f;
 #pragma unroll 1
       for (int c0 = 0; c0 < HP; c0 += 32) {
         uint32_t v[32];
@@ -641,90 +614,49 @@ __global__ void __launch_bounds__(PG_THREADS, 1) upd_gemm_persist_kernel(GemmArg
         if (c0 + 32 >= HP) {                                 // the accumulator is in registers: hand the slot back
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ACCE(slot)) : "memory");
+          if (lane == 0) mbar_arrive(ACCE(slot));
         }
         if (!live || (a.dbg & 1)) continue;
-        float x[32];
-        if (EPI == 0) {
-          uint32_t word = 0;
+        const uint32_t word = mbits[c0 >> 5];
 #pragma unroll
-          for (int q = 0; q < 32; ++q) {
-            x[q] = fmaxf(__uint_as_float(v[q]), 0.f);
-            if (q < nc) {
-              if (a.w4) head = fmaf(x[q], s_w4[c0 + q], head);
-              word |= (x[q] > 0.f ? 1u : 0u) << q;
-            }
+        for (int q = 0; q < 8; ++q) {
+          if (q * 4 < nc) {
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              o[e] = ((word >> (q * 4 + e)) & 1u) ? tf32_rn(__uint_as_float(v[q * 4 + e])) : 0.f;
+            *(float4*)(stg + lane * STG_PITCH + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
           }
-          if (a.bits_out && wrow0 + lane < r_end) a.bits_out[(size_t)(wrow0 + lane) * 8 + (c0 >> 5)] = word;
-        } else {
-          const uint32_t word = mbits[c0 >> 5];
-#pragma unroll
-          for (int q = 0; q < 32; ++q) x[q] = (q < nc && ((word >> q) & 1u)) ? tf32_rn(__uint_as_float(v[q])) : 0.f;
         }
-#pragma unroll 1
-        for (int part = 0; part < (EPI == 0 && a.OutLo ? 2 : 1); ++part) {
+        __syncwarp();
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            if (q * 4 < nc) {
-              float o[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float tt = x[q * 4 + e];
-                if (EPI == 0) {
-                  const int col = c0 + q * 4 + e;
-                  const float hi = col == a.H ? 1.f : tf32_rn(tt);
-                  tt = part == 0 ? hi : (col == a.H ? 0.f : tf32_rn(tt - hi));
-                }
-                o[e] = tt;
-              }
-              *(float4*)(stg + lane * STG_PITCH + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
-            }
-          }
-          __syncwarp();
-          float* outp = part == 0 ? a.Out : a.OutLo;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = i * 4 + cr, grow = wrow0 + r;
-            if (grow < r_end && cc * 4 < nc)
-              *(float4*)(outp + (size_t)grow * HP + c0 + cc * 4) = *(const float4*)(stg + r * STG_PITCH + cc * 4);
-          }
-          __syncwarp();
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + cr, grow = wrow0 + r;
+          if (grow < r_end && cc * 4 < nc)
+            *(float4*)(a.Out + (size_t)grow * HP + c0 + cc * 4) = *(const float4*)(stg + r * STG_PITCH + cc * 4);
         }
+        __syncwarp();
       }
-      if (EPI == 0 && a.w4 && wrow0 + lane < r_end) a.logits[wrow0 + lane] = head + a.b4[0];
     }
   } else if (warp < 8) {
-    // ---- A loaders ----
+    // ---- A loaders: one instruction = 4 whole 128-byte lines ----
     const int lw = warp - 4;
-    const int r8 = lane & 7, cq = lane >> 3;
+    const int lr = lane >> 3, c = lane & 7;
     int g = 0;
     for (int t = 0; t < n_tiles; ++t) {
       const int row0 = r_begin + t * TM;
-      for (int kt = 0; kt < NKT_; ++kt, ++g) {
-        const int s = g % NST, u = g / NST;
+      for (int kt = 0; kt < PG_NKT; ++kt, ++g) {
+        const int s = g % PG_STAGES, u = g / PG_STAGES;
         if (u > 0) mbar_wait(EMPTY(s), (u - 1) & 1, s_abort);
-        const uint32_t dstA = smem_u32(sA + s * A_ST);
-        if (a.dbg & 4) {
-        } else if (X3) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int j = lw * 4 + i;
-            const int grow = row0 + j * 8 + r8;
-            const bool ok = grow < r_end;
-            const int arr = cq >> 1, c = cq & 1;
-            const float* src = (arr ? a.Alo : a.A) + (size_t)(ok ? grow : 0) * HP + kt * KT_ + c * 4;
-            cp_async16(dstA + arr * (TM * KT3 * 4) + c * (TM * 16) + j * 128 + r8 * 16, src, ok);
-          }
-        } else {
-          // lane -> (row of 4, chunk of 8): one instruction = 4 whole 128-byte lines
-          const int lr = lane >> 3, c = lane & 7;
+        const uint32_t dstA = smem_u32(sA + s * PG_A_STAGE);
+        if (!(a.dbg & 4)) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int row = (lw * 8 + i) * 4 + lr;
             const int grow = row0 + row;
-            const bool ok = grow < r_end && kt * KT_ + c * 4 < HP;
-            const float* src = a.A + (size_t)(ok ? grow : 0) * HP + (ok ? kt * KT_ + c * 4 : 0);
-            cp_async16(dstA + c * LBO_A + (row >> 3) * 128 + (row & 7) * 16, src, ok);
+            const bool ok = grow < r_end && kt * PG_KT + c * 4 < HP;
+            const float* src = a.A + (size_t)(ok ? grow : 0) * HP + (ok ? kt * PG_KT + c * 4 : 0);
+            cp_async16(dstA + c * PG_LBO_A + (row >> 3) * 128 + (row & 7) * 16, src, ok);
           }
         }
         cp_async_arrive(FULL(s));
@@ -738,27 +670,16 @@ __global__ void __launch_bounds__(PG_THREADS, 1) upd_gemm_persist_kernel(GemmArg
         const int slot = t & 1;
         if (t >= 2) { mbar_wait(ACCE(slot), ((t >> 1) - 1) & 1, s_abort); tc_fence_after(); }
         const uint32_t d = tmem + slot * 256;
-        for (int kt = 0; kt < NKT_; ++kt, ++g) {
-          const int s = g % NST, u = g / NST;
+        for (int kt = 0; kt < PG_NKT; ++kt, ++g) {
+          const int s = g % PG_STAGES, u = g / PG_STAGES;
           mbar_wait(FULL(s), u & 1, s_abort);
           tc_fence_after();
-          const uint32_t aS = smem_u32(sA + s * A_ST), bS = smem_u32(sB + s * B_ST);
-          if (a.dbg & 2) {
-          } else if (X3) {
-            const uint64_t bh = make_desc(bS, HP * 16, 128);
-            const uint64_t bl = make_desc(bS + HP * KT3 * 4, HP * 16, 128);
-            const uint64_t ah = make_desc(aS, TM * 16, 128);
-            const uint64_t al = make_desc(aS + TM * KT3 * 4, TM * 16, 128);
-            mma_ss_tf32(d, al, bh, IDESC_K, kt != 0);        // small terms first
-            mma_ss_tf32(d, ah, bl, IDESC_K, 1);
-            mma_ss_tf32(d, ah, bh, IDESC_K, 1);
-          } else {
-            const int nks = kt == NKT_ - 1 ? 2 : 4;            // the last stage holds K 192..207
-            for (int ks = 0; ks < nks; ++ks) {
-              const uint64_t bd = make_desc(bS + ks * 2 * (HP * 16), HP * 16, 128);
-              const uint64_t ad = make_desc(aS + ks * 2 * LBO_A, LBO_A, 128);
-              mma_ss_tf32(d, ad, bd, IDESC_K, (kt | ks) != 0);
-            }
+          const uint32_t aS = smem_u32(sA + s * PG_A_STAGE), bS = smem_u32(sB + s * PG_B_STAGE);
+          const int nks = (a.dbg & 2) ? 0 : (kt == PG_NKT - 1 ? 2 : 4);       // the last stage holds K 192..207
+          for (int ks = 0; ks < nks; ++ks) {
+            const uint64_t bd = make_desc(bS + ks * 2 * (HP * 16), HP * 16, 128);
+            const uint64_t ad = make_desc(aS + ks * 2 * PG_LBO_A, PG_LBO_A, 128);
+            mma_ss_tf32(d, ad, bd, IDESC_K, (kt | ks) != 0);
           }
           tc_commit(EMPTY(s));
         }
@@ -771,20 +692,12 @@ __global__ void __launch_bounds__(PG_THREADS, 1) upd_gemm_persist_kernel(GemmArg
     if (lane == 0) {
       int g = 0;
       for (int t = 0; t < n_tiles; ++t) {
-        for (int kt = 0; kt < NKT_; ++kt, ++g) {
-          const int s = g % NST, u = g / NST;
+        for (int kt = 0; kt < PG_NKT; ++kt, ++g) {
+          const int s = g % PG_STAGES, u = g / PG_STAGES;
           if (u > 0) mbar_wait(EMPTY(s), (u - 1) & 1, s_abort);
-          if (a.dbg & 8) {
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(FULL(s)) : "memory");
-            continue;
-          }
-          mbar_expect_tx(FULL(s), B_ST);
-          if (X3) {
-            bulk_g2s(smem_u32(sB + s * B_ST), a.Bimg + (size_t)kt * (HP * KT3), HP * KT3 * 4, FULL(s));
-            bulk_g2s(smem_u32(sB + s * B_ST) + HP * KT3 * 4, a.Bimg_lo + (size_t)kt * (HP * KT3), HP * KT3 * 4, FULL(s));
-          } else {
-            bulk_g2s(smem_u32(sB + s * B_ST), a.Bimg + (size_t)kt * (HP * 32), B_ST, FULL(s));
-          }
+          if (a.dbg & 8) { mbar_arrive(FULL(s)); continue; }
+          mbar_expect_tx(FULL(s), PG_B_STAGE);
+          bulk_g2s(smem_u32(sB + s * PG_B_STAGE), a.Bimg + (size_t)kt * (HP * PG_KT), PG_B_STAGE, FULL(s));
         }
       }
     }
@@ -1185,8 +1098,7 @@ static int set_attrs() {
   MBO_CUDA(cudaFuncSetAttribute(upd_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
   MBO_CUDA(cudaFuncSetAttribute(upd_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
   MBO_CUDA(cudaFuncSetAttribute(upd_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
-  MBO_CUDA(cudaFuncSetAttribute(upd_gemm_persist_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM));
-  MBO_CUDA(cudaFuncSetAttribute(upd_gemm_persist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM));
+  MBO_CUDA(cudaFuncSetAttribute(upd_dgrad_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM));
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev); }
   g_attr_done = true;
   return MBO_OK;
@@ -1255,23 +1167,20 @@ extern "C" int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32
   const char* w0_env = getenv("MBO_WG0_CTAS");
   const int l0_ctas = l0_env ? atoi(l0_env) : 4 * THIN_CTAS;
   const int wg0_ctas = w0_env ? (atoi(w0_env) < THIN_CTAS ? atoi(w0_env) : THIN_CTAS) : WG0_CTAS;
-  const char* ol_env = getenv("MBO_UPD_ONCHIP_LO");
-  const int onchip_lo = ol_env ? atoi(ol_env) != 0 : 1;
-  const char* pf_env = getenv("MBO_UPD_PERSIST_FWD");
+  // which dgrad kernel runs (both are kept and tested bitwise against each other): on the C3 minibatch the persistent
+  // double-buffered kernel takes 33.5 us, the one-tile-per-CTA kernel 38 us
   const char* pd_env = getenv("MBO_UPD_PERSIST_DGRAD");
-  const bool persist_fwd = (pf_env ? atoi(pf_env) != 0 : false) && !onchip_lo;
   const bool persist = pd_env ? atoi(pd_env) != 0 : true;
   const int pg_grid = g_num_sms < tiles ? g_num_sms : tiles;
 
   upd_pack_kernel<<<(9 * IMG_FLOATS + 255) / 256, 256, 0, st>>>(net, ws);
-  upd_layer0_kernel<<<l0_ctas, THIN_THREADS, 0, st>>>(net, states, R, ws.Hs[0], onchip_lo ? nullptr : ws.Hl[0]);
+  upd_layer0_kernel<<<l0_ctas, THIN_THREADS, 0, st>>>(net, states, R, ws.Hs[0]);
   for (int l = 0; l < 3; ++l) {
     GemmArgs g{};
-    g.A = ws.Hs[l]; g.Alo = ws.Hl[l]; g.Bimg = ws.img_fwd[l]; g.Bimg_lo = ws.img_fwl[l]; g.Out = ws.Hs[l + 1];
-    g.OutLo = l < 2 ? ws.Hl[l + 1] : nullptr; g.bits_out = l < 2 ? ws.hbits[l] : nullptr; g.R = R; g.H = H; g.dbg = dbg; g.onchip_lo = onchip_lo;
+    g.A = ws.Hs[l]; g.Bimg = ws.img_fwd[l]; g.Bimg_lo = ws.img_fwl[l]; g.Out = ws.Hs[l + 1];
+    g.bits_out = l < 2 ? ws.hbits[l] : nullptr; g.R = R; g.H = H; g.dbg = dbg;
     if (l == 2) { g.w4 = W[4]; g.b4 = b[4]; g.logits = ws.logits; }
-    if (persist_fwd) upd_gemm_persist_kernel<0><<<pg_grid, PG_THREADS, PG_SMEM, st>>>(g, ws.err);
-    else upd_gemm_kernel<0><<<tiles, GEMM_THREADS, GEMM_SMEM, st>>>(g, ws.err);
+    upd_gemm_kernel<0><<<tiles, GEMM_THREADS, GEMM_SMEM, st>>>(g, ws.err);
   }
   upd_loss_kernel<<<E, 256, 0, st>>>(M, ws.logits, actions, advs, logp_old, epsilon, ent_coeff, inv_n_global, ws.dl,
                                       ws.terms);
@@ -1285,7 +1194,7 @@ extern "C" int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32
     GemmArgs g{};
     g.A = ws.dZ[l + 1]; g.Bimg = persist ? ws.img_dgp[l] : ws.img_dgr[l]; g.Out = ws.dZ[l]; g.bits_in = l > 0 ? ws.hbits[l - 1] : nullptr;   // l = 0: dH1, masked in wgrad0
     g.R = R; g.H = H; g.dbg = dbg;
-    if (persist) upd_gemm_persist_kernel<1><<<pg_grid, PG_THREADS, PG_SMEM, st>>>(g, ws.err);
+    if (persist) upd_dgrad_persist_kernel<<<pg_grid, PG_THREADS, PG_SMEM, st>>>(g, ws.err);
     else upd_gemm_kernel<1><<<tiles, GEMM_THREADS, GEMM_SMEM, st>>>(g, ws.err);
   }
   WgradArgs wa{};
