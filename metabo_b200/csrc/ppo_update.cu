@@ -53,6 +53,9 @@ constexpr int GEMM_STAGES = 4;
 constexpr int GEMM_THREADS = 192;   // warps 0-3: A loaders then epilogue; warp 4: MMA issue; warp 5: weight stages
 constexpr int GEMM_A_STAGE = GEMM_MB * A_STAGE;
 constexpr int GEMM_SMEM = GEMM_STAGES * (GEMM_A_STAGE + B_STAGE) + 256;
+constexpr int FWD_LAND = 6;         // forward: landing slots of the raw fp32 A chunks (5 K tiles of loads in flight per thread)
+constexpr int FWD_LAND_BYTES = TM * KT3 * 4;                                // 4 096
+constexpr int FWD_SMEM = GEMM_SMEM + FWD_LAND * FWD_LAND_BYTES;
 constexpr int WG_STAGES = 3;
 constexpr int WG_A_STAGE = 8 * 4096;          // 8 blocks of 32 columns (256 = two M blocks) x 32 K rows x 128 B
 constexpr int WG_B_STAGE = 7 * 4096;          // 7 blocks (224 >= 208 columns)
@@ -296,6 +299,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) upd_gemm_kernel(GemmArgs a, i
   unsigned char* sA = smem;
   unsigned char* sB = smem + GEMM_STAGES * GEMM_A_STAGE;
   uint64_t* bars = (uint64_t*)(smem + GEMM_STAGES * (GEMM_A_STAGE + B_STAGE));
+  unsigned char* sLand = smem + GEMM_STAGES * (GEMM_A_STAGE + B_STAGE) + 256;       // forward only
   uint32_t* s_tmem = (uint32_t*)(bars + 2 * GEMM_STAGES + 2);
   volatile int* s_abort = (volatile int*)(s_tmem + 1);
   __shared__ float s_w4[HP];
@@ -327,43 +331,51 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) upd_gemm_kernel(GemmArgs a, i
     // bytes of one core-matrix column (conflict-free) and read 64 B per row ----
     const int r8 = lane & 7, cq = lane >> 3;
     if (X3) {
-      // ---- forward, activations stored once as plain fp32: every thread copies 2 chunks (16 B) per stage and, two
-      // stages later, splits exactly those chunks in place into tf32 hi (written back) and lo (second half of the
-      // stage) -- only its own cp.async groups have to be complete, no cross-thread hand-off ----
-      auto chunk_addr = [&](int kt, int i) {
-        const int j = warp * 4 + i * 2 + (cq >> 1);
-        return smem_u32(sA + (kt % GEMM_STAGES) * GEMM_A_STAGE) + (cq & 1) * (TM * 16) + j * 128 + r8 * 16;
-      };
-      auto split_stage = [&](int kt) {
+      // ---- forward, activations stored once as plain fp32: every thread copies 2 chunks (16 B) per K tile into a ring
+      // of FWD_LAND landing slots, 5 tiles ahead of their use (the ring is private per thread: a slot is reused only after
+      // this thread has split its own chunks out of it, so no barrier is involved and the loads run ahead of the MMAs),
+      // then splits exactly those chunks into tf32 hi and lo inside the operand stage -- only its own cp.async groups
+      // have to be complete.  (With the loads issued into the 4 operand stages, 2 tiles ahead, the kernel waited for
+      // DRAM on every tile: 34 of its 54 us.) ----
+      constexpr int D = FWD_LAND - 1;
+      const int j0 = warp * 4 + (cq >> 1);                               // 8-row group of chunk i = 0 (i = 1: + 2)
+      const uint32_t coff = (cq & 1) * (TM * 16) + r8 * 16;
+      auto issue = [&](int kt) {
+        if (kt < NKT_) {
+          const uint32_t land = smem_u32(sLand + (kt % FWD_LAND) * FWD_LAND_BYTES);
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const uint32_t ad = chunk_addr(kt, i);
-          float4 v;
-          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ad) : "memory");
-          const float4 hi = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
-          const float4 lo = make_float4(tf32_rn(v.x - hi.x), tf32_rn(v.y - hi.y), tf32_rn(v.z - hi.z), tf32_rn(v.w - hi.w));
-          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(ad), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
-          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(ad + TM * KT3 * 4), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
+          for (int i = 0; i < 2; ++i) {
+            const int j = j0 + i * 2;
+            const int grow = row0 + j * 8 + r8;
+            const bool ok = grow < a.R;
+            const float* src = a.A + (size_t)(ok ? grow : 0) * HP + kt * KT_ + (cq & 1) * 4;
+            cp_async16(land + coff + j * 128, src, ok);
+          }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(FULL(kt % GEMM_STAGES));
+        cp_async_commit();                                                // one group per K tile, also past the end
       };
+      for (int kt = 0; kt < D; ++kt) issue(kt);
       for (int kt = 0; kt < NKT_; ++kt) {
         const int s = kt % GEMM_STAGES, u = kt / GEMM_STAGES;
+        cp_async_wait<D - 1>();                                           // tile kt has landed (this thread's chunks)
         if (u > 0) mbar_wait(EMPTY(s), (u - 1) & 1, s_abort);
+        const uint32_t land = smem_u32(sLand + (kt % FWD_LAND) * FWD_LAND_BYTES);
+        const uint32_t opnd = smem_u32(sA + s * GEMM_A_STAGE);
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-          const int j = warp * 4 + i * 2 + (cq >> 1);
-          const int grow = row0 + j * 8 + r8;
-          const bool ok = grow < a.R;
-          const float* src = a.A + (size_t)(ok ? grow : 0) * HP + kt * KT_ + (cq & 1) * 4;
-          cp_async16(chunk_addr(kt, i), src, ok);
+          const uint32_t off = coff + (j0 + i * 2) * 128;
+          float4 v;
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(land + off) : "memory");
+          const float4 hi = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+          const float4 lo = make_float4(tf32_rn(v.x - hi.x), tf32_rn(v.y - hi.y), tf32_rn(v.z - hi.z), tf32_rn(v.w - hi.w));
+          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(opnd + off), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(opnd + off + TM * KT3 * 4), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
         }
-        cp_async_commit();
-        if (kt >= 2) { cp_async_wait<2>(); split_stage(kt - 2); }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(FULL(s));
+        issue(kt + D);                                                    // into the slot of tile kt - 1, already split
       }
-      cp_async_wait<1>(); split_stage(NKT_ - 2);
-      cp_async_wait<0>(); split_stage(NKT_ - 1);
+      cp_async_wait<0>();
     } else
     for (int kt = 0; kt < NKT_; ++kt) {
       const int s = kt % GEMM_STAGES, u = kt / GEMM_STAGES;
@@ -1095,7 +1107,7 @@ static bool g_attr_done = false;
 static int g_num_sms = 148;
 static int set_attrs() {
   if (g_attr_done) return MBO_OK;
-  MBO_CUDA(cudaFuncSetAttribute(upd_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+  MBO_CUDA(cudaFuncSetAttribute(upd_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
   MBO_CUDA(cudaFuncSetAttribute(upd_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
   MBO_CUDA(cudaFuncSetAttribute(upd_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
   MBO_CUDA(cudaFuncSetAttribute(upd_dgrad_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM));
@@ -1180,7 +1192,7 @@ extern "C" int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32
     g.A = ws.Hs[l]; g.Bimg = ws.img_fwd[l]; g.Bimg_lo = ws.img_fwl[l]; g.Out = ws.Hs[l + 1];
     g.bits_out = l < 2 ? ws.hbits[l] : nullptr; g.R = R; g.H = H; g.dbg = dbg;
     if (l == 2) { g.w4 = W[4]; g.b4 = b[4]; g.logits = ws.logits; }
-    upd_gemm_kernel<0><<<tiles, GEMM_THREADS, GEMM_SMEM, st>>>(g, ws.err);
+    upd_gemm_kernel<0><<<tiles, GEMM_THREADS, FWD_SMEM, st>>>(g, ws.err);
   }
   upd_loss_kernel<<<E, 256, 0, st>>>(M, ws.logits, actions, advs, logp_old, epsilon, ent_coeff, inv_n_global, ws.dl,
                                       ws.terms);
