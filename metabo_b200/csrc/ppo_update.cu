@@ -68,10 +68,11 @@ constexpr int MAXF = 8;
 
 // ---- PTX wrappers (own namespace: neural_af_tc.cu has same-named helpers with other constants) -----------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// round to nearest tf32 (ties away from zero, = cvt.rna.tf32.f32 for finite values) with two full-rate integer
+// instructions: cvt.rna runs on the conversion unit and made the forward loader's hi / lo split the slowest link of the
+// pipeline (~270 cycles per 16-byte chunk, tools/upd_trace.py)
 __device__ __forceinline__ float tf32_rn(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -270,6 +271,14 @@ __global__ void __launch_bounds__(THIN_THREADS) upd_layer0_kernel(Net net, const
   }
 }
 
+#ifdef MBO_UPD_TRACE
+// debug build (tools/build_trace_lib.sh): clock64 stamps of one CTA's pipeline roles, read back by tools/upd_trace.py
+__device__ long long g_upd_trace[4096];
+#define UPD_TRACE(role, idx) do { if (blockIdx.x == gridDim.x / 3) g_upd_trace[(role) * 512 + (idx)] = clock64(); } while (0)
+#else
+#define UPD_TRACE(role, idx) do { } while (0)
+#endif
+
 // ---- forward / dgrad GEMM -----------------------------------------------------------------------------------------
 struct GemmArgs {
   const float* A;        // [R, HP] rows of this GEMM (h_l for the forward, dZ_{l+1} for the dgrad), plain fp32
@@ -312,7 +321,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) upd_gemm_kernel(GemmArgs a, i
 
   if (tid == 0) {
     *s_abort = 0;
-    for (int s = 0; s < GEMM_STAGES; ++s) { mbar_init(FULL(s), 128 + 1); mbar_init(EMPTY(s), 1); }
+    for (int s = 0; s < GEMM_STAGES; ++s) { mbar_init(FULL(s), (X3 ? 64 : 128) + 1); mbar_init(EMPTY(s), 1); }
     mbar_init(ACCF, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -337,14 +346,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) upd_gemm_kernel(GemmArgs a, i
       // then splits exactly those chunks into tf32 hi and lo inside the operand stage -- only its own cp.async groups
       // have to be complete.  (With the loads issued into the 4 operand stages, 2 tiles ahead, the kernel waited for
       // DRAM on every tile: 34 of its 54 us.) ----
-      constexpr int D = FWD_LAND - 1;
-      const int j0 = warp * 4 + (cq >> 1);                               // 8-row group of chunk i = 0 (i = 1: + 2)
+      // The split + fence.proxy.async + arrive chain of one K tile takes a thread ~700 cycles (tools/upd_trace.py), more
+      // than the 3 MMAs of the tile: the four loader warps therefore work as two groups on alternate K tiles (64
+      // threads x 4 chunks each), so that two tiles are in that chain at any time.
+      constexpr int D = 2;                                               // own tiles in flight beyond the current one (6 slots / 2 groups - 1)
+      const int grp = warp >> 1;                                         // K tiles kt = grp, grp + 2, ...
+      const int j0 = (warp & 1) * 8 + (cq >> 1);                          // 8-row group of chunk i = 0 (i: + 2 i)
       const uint32_t coff = (cq & 1) * (TM * 16) + r8 * 16;
       auto issue = [&](int kt) {
         if (kt < NKT_) {
           const uint32_t land = smem_u32(sLand + (kt % FWD_LAND) * FWD_LAND_BYTES);
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
+          for (int i = 0; i < 4; ++i) {
             const int j = j0 + i * 2;
             const int grow = row0 + j * 8 + r8;
             const bool ok = grow < a.R;
@@ -352,28 +365,34 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) upd_gemm_kernel(GemmArgs a, i
             cp_async16(land + coff + j * 128, src, ok);
           }
         }
-        cp_async_commit();                                                // one group per K tile, also past the end
+        cp_async_commit();                                                // one group per own K tile, also past the end
       };
-      for (int kt = 0; kt < D; ++kt) issue(kt);
-      for (int kt = 0; kt < NKT_; ++kt) {
+      for (int n = 0; n < D; ++n) issue(grp + 2 * n);
+      for (int kt = grp; kt < NKT_; kt += 2) {
         const int s = kt % GEMM_STAGES, u = kt / GEMM_STAGES;
+        if (tid == 0) UPD_TRACE(0, 4 * kt + 0);
         cp_async_wait<D - 1>();                                           // tile kt has landed (this thread's chunks)
+        if (tid == 0) UPD_TRACE(0, 4 * kt + 1);
         if (u > 0) mbar_wait(EMPTY(s), (u - 1) & 1, s_abort);
+        if (tid == 0) UPD_TRACE(0, 4 * kt + 2);
         const uint32_t land = smem_u32(sLand + (kt % FWD_LAND) * FWD_LAND_BYTES);
         const uint32_t opnd = smem_u32(sA + s * GEMM_A_STAGE);
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 4; ++i) {
           const uint32_t off = coff + (j0 + i * 2) * 128;
           float4 v;
           asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(land + off) : "memory");
           const float4 hi = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
-          const float4 lo = make_float4(tf32_rn(v.x - hi.x), tf32_rn(v.y - hi.y), tf32_rn(v.z - hi.z), tf32_rn(v.w - hi.w));
+          const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);    // exact; the MMA drops bits below 2^-22 |v|
           asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(opnd + off), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
           asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(opnd + off + TM * KT3 * 4), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
         }
+        if (tid == 0) UPD_TRACE(4, 2 * kt + 0);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (tid == 0) UPD_TRACE(4, 2 * kt + 1);
         mbar_arrive(FULL(s));
-        issue(kt + D);                                                    // into the slot of tile kt - 1, already split
+        if (tid == 0) UPD_TRACE(0, 4 * kt + 3);
+        issue(kt + 2 * D);                                                // into the slot of tile kt - 2: this group's previous tile
       }
       cp_async_wait<0>();
     } else
@@ -411,8 +430,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) upd_gemm_kernel(GemmArgs a, i
         mbits[mb][4] = w1.x; mbits[mb][5] = w1.y; mbits[mb][6] = w1.z; mbits[mb][7] = w1.w;
       }
     }
+    if (tid == 0) UPD_TRACE(3, 0);
     mbar_wait(ACCF, 0, s_abort);
     tc_fence_after();
+    if (tid == 0) UPD_TRACE(3, 1);
     float* stg = (float*)smem + warp * (32 * STG_PITCH);            // per-warp staging tile [32 rows][36 floats]
     const int cr = lane >> 3, cc = lane & 7;                         // coalesced side: 4 rows x 8 chunks per instruction
 #pragma unroll 1
@@ -471,14 +492,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) upd_gemm_kernel(GemmArgs a, i
     }
     if (EPI == 0 && a.w4 && wrow0 + lane < a.R) a.logits[wrow0 + lane] = head + a.b4[0];
     }
+    if (tid == 0) UPD_TRACE(3, 2);
     tc_fence_before();
   } else if (warp == 4) {
     // ---- MMA issue ----
     if (lane == 0) {
       for (int kt = 0; kt < NKT_; ++kt) {
         const int s = kt % GEMM_STAGES, u = kt / GEMM_STAGES;
+        UPD_TRACE(1, 3 * kt + 0);
         mbar_wait(FULL(s), u & 1, s_abort);
         tc_fence_after();
+        UPD_TRACE(1, 3 * kt + 1);
         const uint32_t aS0 = smem_u32(sA + s * GEMM_A_STAGE), bS = smem_u32(sB + s * B_STAGE);
         if (a.dbg & 2) {
         } else if (X3) {
@@ -505,6 +529,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) upd_gemm_kernel(GemmArgs a, i
           }
         }
         tc_commit(EMPTY(s));
+        UPD_TRACE(1, 3 * kt + 2);
       }
       tc_commit(ACCF);
     }
@@ -522,6 +547,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) upd_gemm_kernel(GemmArgs a, i
     if (lane == 0) {
       for (int kt = 0; kt < NKT_; ++kt) {
         const int s = kt % GEMM_STAGES, u = kt / GEMM_STAGES;
+        UPD_TRACE(2, 2 * kt + 0);
         if (u > 0) mbar_wait(EMPTY(s), (u - 1) & 1, s_abort);
         if (a.dbg & 8) {
           asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(FULL(s)) : "memory");
@@ -534,6 +560,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) upd_gemm_kernel(GemmArgs a, i
         } else {
           bulk_g2s(smem_u32(sB + s * B_STAGE), a.Bimg + (size_t)kt * (HP * KT), B_STAGE, FULL(s));
         }
+        UPD_TRACE(2, 2 * kt + 1);
       }
     }
     __syncwarp();
@@ -1497,3 +1524,9 @@ extern "C" int mbo_ppo_loss_sums(int E, const float* terms, const float* vterms,
   MBO_LAUNCH_CHECK();
   return MBO_OK;
 }
+
+#ifdef MBO_UPD_TRACE
+extern "C" int mbo_upd_trace_read(long long* host_out /*[4096]*/) {
+  return cudaMemcpyFromSymbol(host_out, mbo::upd::g_upd_trace, sizeof(long long) * 4096) == cudaSuccess ? 0 : -2;
+}
+#endif
