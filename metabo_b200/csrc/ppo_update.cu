@@ -145,6 +145,14 @@ __device__ __forceinline__ void mma_ss_tf32(uint32_t d, uint64_t adesc, uint64_t
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]^T: the A operand (128 rows x 8 tf32 columns) read from tensor memory
+__device__ __forceinline__ void mma_ts_tf32(uint32_t d, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // cute::UMMA::SmemDescriptor, no swizzle, version 1.  K-major: LBO = distance of the two 16-byte K chunks of one
 // MMA, SBO = distance of 8-row groups.  MN-major: SBO = distance of 16-byte chunks along M/N, LBO = distance of
 // 8-row K groups (mma_sm100_desc.hpp make_umma_desc<Major::MN>, INTERLEAVE).
@@ -570,6 +578,178 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) upd_gemm_kernel(GemmArgs a, i
   if (warp == 4) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u * GEMM_MB) : "memory");
+  }
+}
+
+// ---- forward GEMM with the A operand in tensor memory (TS form) ---------------------------------------------------------
+// The SS-form forward is bound by the shared-memory pipe (its three MMAs per K tile read A hi twice, A lo, B hi twice,
+// B lo, and the loaders write the split operands): here the activations never touch shared memory.  Thread = row: each
+// loader thread reads its row straight from global memory (one 128-byte line = 4 K tiles at a time, one line ahead in
+// registers), splits in registers into tf32 hi / lo and writes them with tcgen05.st into a 3-slot ring of 16 TMEM columns
+// next to the 208 accumulator columns (256-column allocation, 2 CTAs per SM).  Only the weight stages (8 x 13 KB, bulk
+// copies) live in shared memory.  Warps 0-3: A producers, then epilogue; warp 4: MMA issue; warp 5: weight stages.
+constexpr int TS_BSTAGES = 8;
+constexpr int TS_ASLOTS = 3;
+constexpr int TS_ACOL = HP;                              // first TMEM column of the A ring
+constexpr int TS_SMEM = TS_BSTAGES * B_STAGE + 512;      // 107 008: two CTAs per SM; the epilogue's staging tile aliases the idle weight stages
+
+__global__ void __launch_bounds__(GEMM_THREADS, 2) upd_fwd_ts_kernel(GemmArgs a, int* __restrict__ err) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* sB = smem;
+  float* s_stg = (float*)smem;                            // used after ACCF: every weight stage has been consumed by then
+  uint64_t* bars = (uint64_t*)(smem + TS_BSTAGES * B_STAGE);
+  uint32_t* s_tmem = (uint32_t*)(bars + 2 * TS_BSTAGES + 2 * TS_ASLOTS + 2);
+  volatile int* s_abort = (volatile int*)(s_tmem + 1);
+  __shared__ float s_w4[HP];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row0 = blockIdx.x * TM;
+  const uint32_t bar0 = smem_u32(bars);
+  auto BFULL = [&](int s) { return bar0 + 8u * s; };
+  auto BEMPTY = [&](int s) { return bar0 + 8u * (TS_BSTAGES + s); };
+  auto AFULL = [&](int s) { return bar0 + 8u * (2 * TS_BSTAGES + s); };
+  auto AEMPTY = [&](int s) { return bar0 + 8u * (2 * TS_BSTAGES + TS_ASLOTS + s); };
+  const uint32_t ACCF = bar0 + 8u * (2 * TS_BSTAGES + 2 * TS_ASLOTS);
+
+  if (tid == 0) {
+    *s_abort = 0;
+    for (int s = 0; s < TS_BSTAGES; ++s) { mbar_init(BFULL(s), 1); mbar_init(BEMPTY(s), 1); }
+    for (int s = 0; s < TS_ASLOTS; ++s) { mbar_init(AFULL(s), 128); mbar_init(AEMPTY(s), 1); }
+    mbar_init(ACCF, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (a.w4) for (int i = tid; i < HP; i += GEMM_THREADS) s_w4[i] = i < a.H ? a.w4[i] : 0.f;
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+
+  if (warp < 4) {
+    // ---- A producers: thread = row (TMEM lane) ----
+    const int row = row0 + warp * 32 + lane;
+    const bool ok = row < a.R;
+    const float4* src = (const float4*)(a.A + (size_t)(ok ? row : 0) * HP);
+    const uint32_t tA = tmem + ((uint32_t)(warp * 32) << 16) + TS_ACOL;
+    constexpr int NLINE = (HP + 31) / 32;                 // 7 lines of 32 columns (the last one half)
+    float4 cur[8], nxt[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) cur[q] = ok ? src[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+    for (int ln = 0; ln < NLINE; ++ln) {
+      const int nq = ln + 1 < NLINE ? (HP - (ln + 1) * 32 >= 32 ? 8 : (HP - (ln + 1) * 32) / 4) : 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) nxt[q] = (ok && q < nq) ? src[(ln + 1) * 8 + q] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const int ntile = ln + 1 < NLINE ? 4 : (HP - ln * 32) / 8;        // K tiles in this line (4, last line 2)
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        if (t < ntile) {
+          const int kt = ln * 4 + t, slot = kt % TS_ASLOTS, u = kt / TS_ASLOTS;
+          const float v[8] = {cur[2 * t].x, cur[2 * t].y, cur[2 * t].z, cur[2 * t].w,
+                              cur[2 * t + 1].x, cur[2 * t + 1].y, cur[2 * t + 1].z, cur[2 * t + 1].w};
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float h = tf32_rn(v[e]);
+            hi[e] = __float_as_uint(h);
+            lo[e] = __float_as_uint(v[e] - h);             // exact; the MMA drops bits below 2^-22 |v|
+          }
+          if (u > 0) { mbar_wait(AEMPTY(slot), (u - 1) & 1, s_abort); tc_fence_after(); }
+          tmem_st8(tA + slot * 16, hi);
+          tmem_st8(tA + slot * 16 + 8, lo);
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(AFULL(slot));
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) cur[q] = nxt[q];
+    }
+    // ---- epilogue: ReLU, ones column, head logit, ReLU bit words; whole 128-byte lines through a staging tile ----
+    mbar_wait(ACCF, 0, s_abort);
+    tc_fence_after();
+    float* stg = s_stg + warp * (32 * STG_PITCH);
+    const int cr = lane >> 3, cc = lane & 7;
+    const int wrow0 = row0 + warp * 32;
+    if (wrow0 < a.R) {
+      const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16);
+      float head = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < HP; c0 += 32) {
+        uint32_t v[32];
+        const int nc = HP - c0 >= 32 ? 32 : 16;
+        if (nc == 32) tmem_ld32(tbase + c0, v); else tmem_ld16(tbase + c0, v);
+        tmem_wait_ld();
+        uint32_t word = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (q * 4 < nc) {
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int col = c0 + q * 4 + e;
+              const float x = fmaxf(__uint_as_float(v[q * 4 + e]), 0.f);
+              if (a.w4) head = fmaf(x, s_w4[col], head);
+              word |= (x > 0.f ? 1u : 0u) << (q * 4 + e);
+              o[e] = col == a.H ? 1.f : x;                  // ones column; columns above H are 0 (zero weight rows)
+            }
+            *(float4*)(stg + lane * STG_PITCH + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
+          }
+        }
+        if (a.bits_out && wrow0 + lane < a.R) a.bits_out[(size_t)(wrow0 + lane) * 8 + (c0 >> 5)] = word;
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + cr, grow = wrow0 + r;
+          if (grow < a.R && cc * 4 < nc)
+            *(float4*)(a.Out + (size_t)grow * HP + c0 + cc * 4) = *(const float4*)(stg + r * STG_PITCH + cc * 4);
+        }
+        __syncwarp();
+      }
+      if (a.w4 && wrow0 + lane < a.R) a.logits[wrow0 + lane] = head + a.b4[0];
+    }
+    tc_fence_before();
+  } else if (warp == 4) {
+    // ---- MMA issue: per K tile lo*hi + hi*lo + hi*hi ----
+    if (lane == 0) {
+      for (int kt = 0; kt < NKT3; ++kt) {
+        const int sb = kt % TS_BSTAGES, ub = kt / TS_BSTAGES, sa = kt % TS_ASLOTS, ua = kt / TS_ASLOTS;
+        mbar_wait(BFULL(sb), ub & 1, s_abort);
+        mbar_wait(AFULL(sa), ua & 1, s_abort);
+        tc_fence_after();
+        const uint32_t bS = smem_u32(sB + sb * B_STAGE);
+        const uint64_t bh = make_desc(bS, HP * 16, 128);
+        const uint64_t bl = make_desc(bS + HP * KT3 * 4, HP * 16, 128);
+        const uint32_t ah = tmem + TS_ACOL + sa * 16, al = ah + 8;
+        mma_ts_tf32(tmem, al, bh, IDESC_K, kt != 0);         // small terms first
+        mma_ts_tf32(tmem, ah, bl, IDESC_K, 1);
+        mma_ts_tf32(tmem, ah, bh, IDESC_K, 1);
+        tc_commit(BEMPTY(sb));
+        tc_commit(AEMPTY(sa));
+      }
+      tc_commit(ACCF);
+    }
+    __syncwarp();
+  } else {
+    // ---- weight stages: hi and lo image of one K tile per stage ----
+    if (lane == 0) {
+      for (int kt = 0; kt < NKT3; ++kt) {
+        const int s = kt % TS_BSTAGES, u = kt / TS_BSTAGES;
+        if (u > 0) mbar_wait(BEMPTY(s), (u - 1) & 1, s_abort);
+        mbar_expect_tx(BFULL(s), B_STAGE);
+        bulk_g2s(smem_u32(sB + s * B_STAGE), a.Bimg + (size_t)kt * (HP * KT3), HP * KT3 * 4, BFULL(s));
+        bulk_g2s(smem_u32(sB + s * B_STAGE) + HP * KT3 * 4, a.Bimg_lo + (size_t)kt * (HP * KT3), HP * KT3 * 4, BFULL(s));
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (tid == 0 && *s_abort) atomicOr(err, 1);
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
   }
 }
 
@@ -1138,6 +1318,7 @@ static int set_attrs() {
   MBO_CUDA(cudaFuncSetAttribute(upd_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
   MBO_CUDA(cudaFuncSetAttribute(upd_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
   MBO_CUDA(cudaFuncSetAttribute(upd_dgrad_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM));
+  MBO_CUDA(cudaFuncSetAttribute(upd_fwd_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev); }
   g_attr_done = true;
   return MBO_OK;
@@ -1208,6 +1389,8 @@ extern "C" int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32
   const int wg0_ctas = w0_env ? (atoi(w0_env) < THIN_CTAS ? atoi(w0_env) : THIN_CTAS) : WG0_CTAS;
   // which dgrad kernel runs (both are kept and tested bitwise against each other): on the C3 minibatch the persistent
   // double-buffered kernel takes 33.5 us, the one-tile-per-CTA kernel 38 us
+  const char* ts_env = getenv("MBO_UPD_FWD_TS");
+  const bool fwd_ts = ts_env ? atoi(ts_env) != 0 : true;      // A operand in TMEM (default) or in shared memory (SS form)
   const char* pd_env = getenv("MBO_UPD_PERSIST_DGRAD");
   const bool persist = pd_env ? atoi(pd_env) != 0 : true;
   const int pg_grid = g_num_sms < tiles ? g_num_sms : tiles;
@@ -1219,7 +1402,8 @@ extern "C" int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32
     g.A = ws.Hs[l]; g.Bimg = ws.img_fwd[l]; g.Bimg_lo = ws.img_fwl[l]; g.Out = ws.Hs[l + 1];
     g.bits_out = l < 2 ? ws.hbits[l] : nullptr; g.R = R; g.H = H; g.dbg = dbg;
     if (l == 2) { g.w4 = W[4]; g.b4 = b[4]; g.logits = ws.logits; }
-    upd_gemm_kernel<0><<<tiles, GEMM_THREADS, FWD_SMEM, st>>>(g, ws.err);
+    if (fwd_ts) upd_fwd_ts_kernel<<<tiles, GEMM_THREADS, TS_SMEM, st>>>(g, ws.err);
+    else upd_gemm_kernel<0><<<tiles, GEMM_THREADS, FWD_SMEM, st>>>(g, ws.err);
   }
   upd_loss_kernel<<<E, 256, 0, st>>>(M, ws.logits, actions, advs, logp_old, epsilon, ent_coeff, inv_n_global, ws.dl,
                                       ws.terms);

@@ -274,13 +274,15 @@ def test_value_net_grad_matches_autograd(E, Hv):
 
 
 def test_gemm_kernel_variants_agree_bitwise(monkeypatch):
-    """The persistent double-buffered dgrad kernel (default) and the one-tile-per-CTA kernel issue the same MMA sequence per
-    output tile: every dZ and gradient is bitwise identical whichever variant runs, on a ragged row count that gives the
-    persistent CTAs partial and empty tiles."""
+    """The persistent double-buffered dgrad kernel (default) and the one-tile-per-CTA kernel, the TS-form forward (A operand
+    in tensor memory, default) and the SS-form forward (A split in shared memory) issue the same MMA sequence per output
+    tile: every activation, dZ and gradient is bitwise identical whichever variants run, on a ragged row count that gives
+    the persistent CTAs partial and empty tiles."""
     layers, states, actions, advs, logp_old = _random_case(11, 9, 517, 6, list(range(6)), 200)
     outs = []
-    for dgr in ("1", "0", "1"):
+    for dgr, ts in (("1", "1"), ("0", "0"), ("1", "0"), ("0", "1")):
         monkeypatch.setenv("MBO_UPD_PERSIST_DGRAD", dgr)
+        monkeypatch.setenv("MBO_UPD_FWD_TS", ts)            # forward: A operand in TMEM (TS form) or in shared memory
         terms, v, dW, db = _run_case(9, 517, 6, list(range(6)), 200, layers, states, actions, advs, logp_old)
         outs.append((terms, v, dW, db))
     t0, v0, dW0, db0 = outs[0]

@@ -44,8 +44,8 @@ for it in range(iters):
     pg = ops.PPOPolicyGrad(E, M, Fs, cols, H, dev)
     Wd, bd = [w.detach().contiguous() for w in W], [x.detach().contiguous() for x in b]
     outs = []
-    for dgr in ("1", "0", "1"):
-        os.environ["MBO_UPD_PERSIST_DGRAD"] = dgr
+    for dgr, ts in (("1", "1"), ("0", "0"), ("1", "1")):
+        os.environ["MBO_UPD_PERSIST_DGRAD"], os.environ["MBO_UPD_FWD_TS"] = dgr, ts
         dW, db = [torch.full_like(w, 9.0) for w in Wd], [torch.full_like(x, 9.0) for x in bd]
         terms = pg(st, Wd, bd, ac.to(torch.int32), adv, lpo, 0.15, 0.01, E, dW, db).clone()
         torch.cuda.synchronize(); pg.check()
