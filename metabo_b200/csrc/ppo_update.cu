@@ -14,7 +14,8 @@
 // Kernels
 //   upd_pack_kernel      W1..W3 -> UMMA-canonical K-major images [W | b] (forward) and W^T (dgrad)
 //   upd_layer0_kernel    h1 = relu(x W0^T + b0)                              CUDA cores (K = F <= 8)
-//   upd_gemm_kernel<0>   h_{l+1} = relu([h_l,1] Wb^T) (+ head logit)         tcgen05 kind::tf32 x 3 (hi/lo), A and B from smem
+//   upd_ts_kernel<0>     h_{l+1} = relu([h_l,1] Wb^T) (+ head logit)         tcgen05 kind::tf32 x 3 (hi/lo), A from TMEM, B from smem
+//   upd_gemm_kernel<0>   the same with A split in shared memory (SS form)    kept as a bitwise-equal variant
 //   upd_loss_kernel      per episode: log-softmax, logp(a), entropy, clipped surrogate, dlogits
 //   upd_dz4_kernel       dZ4 = dlogit (x) w4 . [h4 > 0]  (+ partial sums of dw4, db4)
 //   upd_gemm_kernel<1> / upd_dgrad_persist_kernel   dZ_l = (dZ_{l+1} W_l) . [h_l > 0]   tcgen05 kind::tf32
@@ -593,7 +594,11 @@ constexpr int TS_ASLOTS = 3;
 constexpr int TS_ACOL = HP;                              // first TMEM column of the A ring
 constexpr int TS_SMEM = TS_BSTAGES * B_STAGE + 512;      // 107 008: two CTAs per SM; the epilogue's staging tile aliases the idle weight stages
 
-__global__ void __launch_bounds__(GEMM_THREADS, 2) upd_fwd_ts_kernel(GemmArgs a, int* __restrict__ err) {
+// EPI 0: forward (3xTF32, 26 K tiles of 8: hi and lo halves of a 16-column slot); EPI 1: dgrad (13 K tiles of 16: dZ is
+// already rounded to tf32, one 16-column slot = two K = 8 MMAs), epilogue masked by the ReLU bit words.
+template <int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 2) upd_ts_kernel(GemmArgs a, int* __restrict__ err) {
+  constexpr int NKT_ = EPI == 0 ? NKT3 : NKT;
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* sB = smem;
   float* s_stg = (float*)smem;                            // used after ACCF: every weight stage has been consumed by then
@@ -617,7 +622,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) upd_fwd_ts_kernel(GemmArgs a,
     mbar_init(ACCF, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (a.w4) for (int i = tid; i < HP; i += GEMM_THREADS) s_w4[i] = i < a.H ? a.w4[i] : 0.f;
+  if (EPI == 0 && a.w4) for (int i = tid; i < HP; i += GEMM_THREADS) s_w4[i] = i < a.H ? a.w4[i] : 0.f;
   if (warp == 4) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(256u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -642,32 +647,64 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) upd_fwd_ts_kernel(GemmArgs a,
       const int nq = ln + 1 < NLINE ? (HP - (ln + 1) * 32 >= 32 ? 8 : (HP - (ln + 1) * 32) / 4) : 0;
 #pragma unroll
       for (int q = 0; q < 8; ++q) nxt[q] = (ok && q < nq) ? src[(ln + 1) * 8 + q] : make_float4(0.f, 0.f, 0.f, 0.f);
-      const int ntile = ln + 1 < NLINE ? 4 : (HP - ln * 32) / 8;        // K tiles in this line (4, last line 2)
+      if (EPI == 0) {
+        const int ntile = ln + 1 < NLINE ? 4 : (HP - ln * 32) / 8;        // K tiles in this line (4, last line 2)
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        if (t < ntile) {
-          const int kt = ln * 4 + t, slot = kt % TS_ASLOTS, u = kt / TS_ASLOTS;
-          const float v[8] = {cur[2 * t].x, cur[2 * t].y, cur[2 * t].z, cur[2 * t].w,
-                              cur[2 * t + 1].x, cur[2 * t + 1].y, cur[2 * t + 1].z, cur[2 * t + 1].w};
-          uint32_t hi[8], lo[8];
+        for (int t = 0; t < 4; ++t) {
+          if (t < ntile) {
+            const int kt = ln * 4 + t, slot = kt % TS_ASLOTS, u = kt / TS_ASLOTS;
+            const float v[8] = {cur[2 * t].x, cur[2 * t].y, cur[2 * t].z, cur[2 * t].w,
+                                cur[2 * t + 1].x, cur[2 * t + 1].y, cur[2 * t + 1].z, cur[2 * t + 1].w};
+            uint32_t hi[8], lo[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float h = tf32_rn(v[e]);
-            hi[e] = __float_as_uint(h);
-            lo[e] = __float_as_uint(v[e] - h);             // exact; the MMA drops bits below 2^-22 |v|
+            for (int e = 0; e < 8; ++e) {
+              const float h = tf32_rn(v[e]);
+              hi[e] = __float_as_uint(h);
+              lo[e] = __float_as_uint(v[e] - h);             // exact; the MMA drops bits below 2^-22 |v|
+            }
+            if (u > 0) { mbar_wait(AEMPTY(slot), (u - 1) & 1, s_abort); tc_fence_after(); }
+            tmem_st8(tA + slot * 16, hi);
+            tmem_st8(tA + slot * 16 + 8, lo);
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(AFULL(slot));
           }
-          if (u > 0) { mbar_wait(AEMPTY(slot), (u - 1) & 1, s_abort); tc_fence_after(); }
-          tmem_st8(tA + slot * 16, hi);
-          tmem_st8(tA + slot * 16 + 8, lo);
-          tmem_wait_st();
-          tc_fence_before();
-          mbar_arrive(AFULL(slot));
+        }
+      } else {
+        const int ntile = ln + 1 < NLINE ? 2 : (HP - ln * 32) / 16;       // K tiles of 16 in this line (2, last line 1)
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (t < ntile) {
+            const int kt = ln * 2 + t, slot = kt % TS_ASLOTS, u = kt / TS_ASLOTS;
+            uint32_t w[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              w[4 * q + 0] = __float_as_uint(cur[4 * t + q].x); w[4 * q + 1] = __float_as_uint(cur[4 * t + q].y);
+              w[4 * q + 2] = __float_as_uint(cur[4 * t + q].z); w[4 * q + 3] = __float_as_uint(cur[4 * t + q].w);
+            }
+            if (u > 0) { mbar_wait(AEMPTY(slot), (u - 1) & 1, s_abort); tc_fence_after(); }
+            tmem_st16(tA + slot * 16, w);
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(AFULL(slot));
+          }
         }
       }
 #pragma unroll
       for (int q = 0; q < 8; ++q) cur[q] = nxt[q];
     }
-    // ---- epilogue: ReLU, ones column, head logit, ReLU bit words; whole 128-byte lines through a staging tile ----
+    // ---- epilogue: (forward) ReLU, ones column, head logit, ReLU bit words / (dgrad) ReLU mask from the bit words;
+    // whole 128-byte lines through a staging tile ----
+    uint32_t mbits[8];
+    if (EPI == 1) {
+      uint4 w0 = make_uint4(~0u, ~0u, ~0u, ~0u), w1 = w0;
+      if (a.bits_in && ok) {
+        w0 = *(const uint4*)(a.bits_in + (size_t)row * 8);
+        w1 = *(const uint4*)(a.bits_in + (size_t)row * 8 + 4);
+      }
+      mbits[0] = w0.x; mbits[1] = w0.y; mbits[2] = w0.z; mbits[3] = w0.w;
+      mbits[4] = w1.x; mbits[5] = w1.y; mbits[6] = w1.z; mbits[7] = w1.w;
+    }
     mbar_wait(ACCF, 0, s_abort);
     tc_fence_after();
     float* stg = s_stg + warp * (32 * STG_PITCH);
@@ -690,15 +727,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) upd_fwd_ts_kernel(GemmArgs a,
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int col = c0 + q * 4 + e;
-              const float x = fmaxf(__uint_as_float(v[q * 4 + e]), 0.f);
-              if (a.w4) head = fmaf(x, s_w4[col], head);
-              word |= (x > 0.f ? 1u : 0u) << (q * 4 + e);
-              o[e] = col == a.H ? 1.f : x;                  // ones column; columns above H are 0 (zero weight rows)
+              if (EPI == 0) {
+                const float x = fmaxf(__uint_as_float(v[q * 4 + e]), 0.f);
+                if (a.w4) head = fmaf(x, s_w4[col], head);
+                word |= (x > 0.f ? 1u : 0u) << (q * 4 + e);
+                o[e] = col == a.H ? 1.f : x;                  // ones column; columns above H are 0 (zero weight rows)
+              } else {
+                o[e] = ((mbits[c0 >> 5] >> (q * 4 + e)) & 1u) ? tf32_rn(__uint_as_float(v[q * 4 + e])) : 0.f;
+              }
             }
             *(float4*)(stg + lane * STG_PITCH + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
           }
         }
-        if (a.bits_out && wrow0 + lane < a.R) a.bits_out[(size_t)(wrow0 + lane) * 8 + (c0 >> 5)] = word;
+        if (EPI == 0 && a.bits_out && wrow0 + lane < a.R) a.bits_out[(size_t)(wrow0 + lane) * 8 + (c0 >> 5)] = word;
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -708,24 +749,29 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) upd_fwd_ts_kernel(GemmArgs a,
         }
         __syncwarp();
       }
-      if (a.w4 && wrow0 + lane < a.R) a.logits[wrow0 + lane] = head + a.b4[0];
+      if (EPI == 0 && a.w4 && wrow0 + lane < a.R) a.logits[wrow0 + lane] = head + a.b4[0];
     }
     tc_fence_before();
   } else if (warp == 4) {
     // ---- MMA issue: per K tile lo*hi + hi*lo + hi*hi ----
     if (lane == 0) {
-      for (int kt = 0; kt < NKT3; ++kt) {
+      for (int kt = 0; kt < NKT_; ++kt) {
         const int sb = kt % TS_BSTAGES, ub = kt / TS_BSTAGES, sa = kt % TS_ASLOTS, ua = kt / TS_ASLOTS;
         mbar_wait(BFULL(sb), ub & 1, s_abort);
         mbar_wait(AFULL(sa), ua & 1, s_abort);
         tc_fence_after();
         const uint32_t bS = smem_u32(sB + sb * B_STAGE);
-        const uint64_t bh = make_desc(bS, HP * 16, 128);
-        const uint64_t bl = make_desc(bS + HP * KT3 * 4, HP * 16, 128);
-        const uint32_t ah = tmem + TS_ACOL + sa * 16, al = ah + 8;
-        mma_ts_tf32(tmem, al, bh, IDESC_K, kt != 0);         // small terms first
-        mma_ts_tf32(tmem, ah, bl, IDESC_K, 1);
-        mma_ts_tf32(tmem, ah, bh, IDESC_K, 1);
+        const uint64_t b0 = make_desc(bS, HP * 16, 128);                       // forward: hi image; dgrad: K 0..7
+        const uint64_t b1 = make_desc(bS + HP * KT3 * 4, HP * 16, 128);        // forward: lo image; dgrad: K 8..15
+        const uint32_t a0 = tmem + TS_ACOL + sa * 16, a1 = a0 + 8;             // forward: hi / lo; dgrad: K 0..7 / 8..15
+        if (EPI == 0) {
+          mma_ts_tf32(tmem, a1, b0, IDESC_K, kt != 0);       // lo * hi: small terms first
+          mma_ts_tf32(tmem, a0, b1, IDESC_K, 1);
+          mma_ts_tf32(tmem, a0, b0, IDESC_K, 1);
+        } else {
+          mma_ts_tf32(tmem, a0, b0, IDESC_K, kt != 0);
+          mma_ts_tf32(tmem, a1, b1, IDESC_K, 1);
+        }
         tc_commit(BEMPTY(sb));
         tc_commit(AEMPTY(sa));
       }
@@ -735,12 +781,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) upd_fwd_ts_kernel(GemmArgs a,
   } else {
     // ---- weight stages: hi and lo image of one K tile per stage ----
     if (lane == 0) {
-      for (int kt = 0; kt < NKT3; ++kt) {
+      for (int kt = 0; kt < NKT_; ++kt) {
         const int s = kt % TS_BSTAGES, u = kt / TS_BSTAGES;
         if (u > 0) mbar_wait(BEMPTY(s), (u - 1) & 1, s_abort);
         mbar_expect_tx(BFULL(s), B_STAGE);
-        bulk_g2s(smem_u32(sB + s * B_STAGE), a.Bimg + (size_t)kt * (HP * KT3), HP * KT3 * 4, BFULL(s));
-        bulk_g2s(smem_u32(sB + s * B_STAGE) + HP * KT3 * 4, a.Bimg_lo + (size_t)kt * (HP * KT3), HP * KT3 * 4, BFULL(s));
+        if (EPI == 0) {
+          bulk_g2s(smem_u32(sB + s * B_STAGE), a.Bimg + (size_t)kt * (HP * KT3), HP * KT3 * 4, BFULL(s));
+          bulk_g2s(smem_u32(sB + s * B_STAGE) + HP * KT3 * 4, a.Bimg_lo + (size_t)kt * (HP * KT3), HP * KT3 * 4, BFULL(s));
+        } else {
+          bulk_g2s(smem_u32(sB + s * B_STAGE), a.Bimg + (size_t)kt * (HP * KT), B_STAGE, BFULL(s));
+        }
       }
     }
     __syncwarp();
@@ -1318,7 +1368,8 @@ static int set_attrs() {
   MBO_CUDA(cudaFuncSetAttribute(upd_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
   MBO_CUDA(cudaFuncSetAttribute(upd_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
   MBO_CUDA(cudaFuncSetAttribute(upd_dgrad_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM));
-  MBO_CUDA(cudaFuncSetAttribute(upd_fwd_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
+  MBO_CUDA(cudaFuncSetAttribute(upd_ts_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
+  MBO_CUDA(cudaFuncSetAttribute(upd_ts_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev); }
   g_attr_done = true;
   return MBO_OK;
@@ -1393,6 +1444,8 @@ extern "C" int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32
   const bool fwd_ts = ts_env ? atoi(ts_env) != 0 : true;      // A operand in TMEM (default) or in shared memory (SS form)
   const char* pd_env = getenv("MBO_UPD_PERSIST_DGRAD");
   const bool persist = pd_env ? atoi(pd_env) != 0 : true;
+  const char* dt_env = getenv("MBO_UPD_DGRAD_TS");
+  const bool dgrad_ts = dt_env ? atoi(dt_env) != 0 : false;
   const int pg_grid = g_num_sms < tiles ? g_num_sms : tiles;
 
   upd_pack_kernel<<<(9 * IMG_FLOATS + 255) / 256, 256, 0, st>>>(net, ws);
@@ -1402,7 +1455,7 @@ extern "C" int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32
     g.A = ws.Hs[l]; g.Bimg = ws.img_fwd[l]; g.Bimg_lo = ws.img_fwl[l]; g.Out = ws.Hs[l + 1];
     g.bits_out = l < 2 ? ws.hbits[l] : nullptr; g.R = R; g.H = H; g.dbg = dbg;
     if (l == 2) { g.w4 = W[4]; g.b4 = b[4]; g.logits = ws.logits; }
-    if (fwd_ts) upd_fwd_ts_kernel<<<tiles, GEMM_THREADS, TS_SMEM, st>>>(g, ws.err);
+    if (fwd_ts) upd_ts_kernel<0><<<tiles, GEMM_THREADS, TS_SMEM, st>>>(g, ws.err);
     else upd_gemm_kernel<0><<<tiles, GEMM_THREADS, FWD_SMEM, st>>>(g, ws.err);
   }
   upd_loss_kernel<<<E, 256, 0, st>>>(M, ws.logits, actions, advs, logp_old, epsilon, ent_coeff, inv_n_global, ws.dl,
@@ -1415,9 +1468,10 @@ extern "C" int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32
   upd_dz4_kernel<<<THIN_CTAS, THIN_THREADS, 0, st>>>(R, H, ws.Hs[3], ws.dl, W[4], ws.dZ[3], ws.part_head);
   for (int l = 2; l >= 0; --l) {      // dZ_{l+1} = (dZ_{l+2} W_{l+1}) . [h_{l+1} > 0]
     GemmArgs g{};
-    g.A = ws.dZ[l + 1]; g.Bimg = persist ? ws.img_dgp[l] : ws.img_dgr[l]; g.Out = ws.dZ[l]; g.bits_in = l > 0 ? ws.hbits[l - 1] : nullptr;   // l = 0: dH1, masked in wgrad0
+    g.A = ws.dZ[l + 1]; g.Bimg = (persist && !dgrad_ts) ? ws.img_dgp[l] : ws.img_dgr[l]; g.Out = ws.dZ[l]; g.bits_in = l > 0 ? ws.hbits[l - 1] : nullptr;   // l = 0: dH1, masked in wgrad0
     g.R = R; g.H = H; g.dbg = dbg;
-    if (persist) upd_dgrad_persist_kernel<<<pg_grid, PG_THREADS, PG_SMEM, st>>>(g, ws.err);
+    if (dgrad_ts) upd_ts_kernel<1><<<tiles, GEMM_THREADS, TS_SMEM, st>>>(g, ws.err);
+    else if (persist) upd_dgrad_persist_kernel<<<pg_grid, PG_THREADS, PG_SMEM, st>>>(g, ws.err);
     else upd_gemm_kernel<1><<<tiles, GEMM_THREADS, GEMM_SMEM, st>>>(g, ws.err);
   }
   WgradArgs wa{};

@@ -280,9 +280,10 @@ def test_gemm_kernel_variants_agree_bitwise(monkeypatch):
     the persistent CTAs partial and empty tiles."""
     layers, states, actions, advs, logp_old = _random_case(11, 9, 517, 6, list(range(6)), 200)
     outs = []
-    for dgr, ts in (("1", "1"), ("0", "0"), ("1", "0"), ("0", "1")):
+    for dgr, ts, dts in (("1", "1", "0"), ("0", "0", "0"), ("1", "0", "1"), ("0", "1", "1")):
         monkeypatch.setenv("MBO_UPD_PERSIST_DGRAD", dgr)
         monkeypatch.setenv("MBO_UPD_FWD_TS", ts)            # forward: A operand in TMEM (TS form) or in shared memory
+        monkeypatch.setenv("MBO_UPD_DGRAD_TS", dts)         # dgrad: TS form instead of the persistent / one-tile SS kernels
         terms, v, dW, db = _run_case(9, 517, 6, list(range(6)), 200, layers, states, actions, advs, logp_old)
         outs.append((terms, v, dW, db))
     t0, v0, dW0, db0 = outs[0]
