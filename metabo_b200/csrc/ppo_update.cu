@@ -181,7 +181,7 @@ struct Ws {          // workspace carve-up (device pointers)
   float* img_dgr[3];  // W^T, KT stages
   float* img_dgp[3];  // W^T, 32 K values per stage (persistent dgrad)
   float* Hs[4];      // h1..h4, plain fp32
-  uint32_t* hbits[2]; // ReLU decisions of h2, h3: [R][8] words, bit q of word c = (h[row][32 c + q] > 0)
+  uint32_t* hbits[3]; // ReLU decisions of h1, h2, h3: [R][8] words, bit q of word c = (h[row][32 c + q] > 0)
   float* dZ[4];      // dZ1..dZ4
   float* logits;
   float* dl;
@@ -204,7 +204,7 @@ static size_t carve(int E, int M, unsigned char* base, Ws* w) {
   for (int l = 0; l < 3; ++l) t.img_dgr[l] = (float*)take((size_t)IMG_FLOATS * 4);
   for (int l = 0; l < 3; ++l) t.img_dgp[l] = (float*)take((size_t)IMG_FLOATS * 4);
   for (int l = 0; l < 4; ++l) t.Hs[l] = (float*)take(Rp * HP * 4);
-  for (int l = 0; l < 2; ++l) t.hbits[l] = (uint32_t*)take(Rp * 8 * 4);
+  for (int l = 0; l < 3; ++l) t.hbits[l] = (uint32_t*)take(Rp * 8 * 4);
   for (int l = 0; l < 4; ++l) t.dZ[l] = (float*)take(Rp * HP * 4);
   t.logits = (float*)take(Rp * 4);
   t.dl = (float*)take(Rp * 4);
@@ -296,6 +296,7 @@ struct GemmArgs {
   float* Out;            // [R, HP]: h_{l+1} (fp32, unrounded) or dZ_l (rounded to tf32)
   const uint32_t* bits_in;   // dgrad: ReLU decisions of h_l (nullptr: no mask, the consumer applies it)
   uint32_t* bits_out;        // forward: ReLU decisions of h_{l+1} for the dgrad, or nullptr
+  uint32_t* bits_a;          // TS forward: ReLU decisions of its INPUT h_l, built by the producer threads (thread = row), or nullptr
   const float* w4;       // forward of the last hidden layer: head weights [H], else nullptr
   const float* b4;
   float* logits;         // [R]
@@ -647,6 +648,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) upd_ts_kernel(GemmArgs a, int
       const int nq = ln + 1 < NLINE ? (HP - (ln + 1) * 32 >= 32 ? 8 : (HP - (ln + 1) * 32) / 4) : 0;
 #pragma unroll
       for (int q = 0; q < 8; ++q) nxt[q] = (ok && q < nq) ? src[(ln + 1) * 8 + q] : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (EPI == 0 && a.bits_a && ok) {                                   // ReLU word of this 32-column line of the input
+        uint32_t word = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          word |= (cur[q].x > 0.f ? 1u : 0u) << (4 * q) | (cur[q].y > 0.f ? 1u : 0u) << (4 * q + 1) |
+                  (cur[q].z > 0.f ? 1u : 0u) << (4 * q + 2) | (cur[q].w > 0.f ? 1u : 0u) << (4 * q + 3);
+        }
+        if (ln * 32 <= a.H && a.H < ln * 32 + 32) word &= ~(1u << (a.H - ln * 32));      // the ones column is not a unit
+        a.bits_a[(size_t)row * 8 + ln] = word;
+      }
       if (EPI == 0) {
         const int ntile = ln + 1 < NLINE ? 4 : (HP - ln * 32) / 8;        // K tiles in this line (4, last line 2)
 #pragma unroll
@@ -1102,11 +1113,13 @@ __global__ void __launch_bounds__(THIN_THREADS) upd_wgrad0_kernel(Net net, const
       const int r = r0 + 4 * u;
       const bool ok = r < r_end;
       d[u] = ok ? *(const float4*)(dH1 + (size_t)r * HP + cg * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 h = ok ? *(const float4*)(H1 + (size_t)r * HP + cg * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      d[u].x = h.x > 0.f ? d[u].x : 0.f;          // dZ1 = dH1 . [h1 > 0] (the ones column has a zero dH1)
-      d[u].y = h.y > 0.f ? d[u].y : 0.f;
-      d[u].z = h.z > 0.f ? d[u].z : 0.f;
-      d[u].w = h.w > 0.f ? d[u].w : 0.f;
+      if (H1) {                                    // SS-forward variant: the dgrad stored dH1, dZ1 = dH1 . [h1 > 0] here
+        const float4 h = ok ? *(const float4*)(H1 + (size_t)r * HP + cg * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        d[u].x = h.x > 0.f ? d[u].x : 0.f;
+        d[u].y = h.y > 0.f ? d[u].y : 0.f;
+        d[u].z = h.z > 0.f ? d[u].z : 0.f;
+        d[u].w = h.w > 0.f ? d[u].w : 0.f;
+      }
 #pragma unroll
       for (int f = 0; f < MAXF; ++f) x[u][f] = (ok && f < F) ? __ldg(states + (size_t)r * net.F_state + net.col[f]) : 0.f;
       x[u][MAXF] = 1.f;
@@ -1453,7 +1466,8 @@ extern "C" int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32
   for (int l = 0; l < 3; ++l) {
     GemmArgs g{};
     g.A = ws.Hs[l]; g.Bimg = ws.img_fwd[l]; g.Bimg_lo = ws.img_fwl[l]; g.Out = ws.Hs[l + 1];
-    g.bits_out = l < 2 ? ws.hbits[l] : nullptr; g.R = R; g.H = H; g.dbg = dbg;
+    g.bits_out = l < 2 ? ws.hbits[l + 1] : nullptr; g.bits_a = (fwd_ts && l == 0) ? ws.hbits[0] : nullptr;
+    g.R = R; g.H = H; g.dbg = dbg;
     if (l == 2) { g.w4 = W[4]; g.b4 = b[4]; g.logits = ws.logits; }
     if (fwd_ts) upd_ts_kernel<0><<<tiles, GEMM_THREADS, TS_SMEM, st>>>(g, ws.err);
     else upd_gemm_kernel<0><<<tiles, GEMM_THREADS, FWD_SMEM, st>>>(g, ws.err);
@@ -1468,7 +1482,7 @@ extern "C" int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32
   upd_dz4_kernel<<<THIN_CTAS, THIN_THREADS, 0, st>>>(R, H, ws.Hs[3], ws.dl, W[4], ws.dZ[3], ws.part_head);
   for (int l = 2; l >= 0; --l) {      // dZ_{l+1} = (dZ_{l+2} W_{l+1}) . [h_{l+1} > 0]
     GemmArgs g{};
-    g.A = ws.dZ[l + 1]; g.Bimg = (persist && !dgrad_ts) ? ws.img_dgp[l] : ws.img_dgr[l]; g.Out = ws.dZ[l]; g.bits_in = l > 0 ? ws.hbits[l - 1] : nullptr;   // l = 0: dH1, masked in wgrad0
+    g.A = ws.dZ[l + 1]; g.Bimg = (persist && !dgrad_ts) ? ws.img_dgp[l] : ws.img_dgr[l]; g.Out = ws.dZ[l]; g.bits_in = (l > 0 || fwd_ts) ? ws.hbits[l] : nullptr;   // SS forward: no h1 words, l = 0 stores dH1, masked in wgrad0
     g.R = R; g.H = H; g.dbg = dbg;
     if (dgrad_ts) upd_ts_kernel<1><<<tiles, GEMM_THREADS, TS_SMEM, st>>>(g, ws.err);
     else if (persist) upd_dgrad_persist_kernel<<<pg_grid, PG_THREADS, PG_SMEM, st>>>(g, ws.err);
@@ -1479,7 +1493,7 @@ extern "C" int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32
   wa.part = ws.part_big; wa.R = R; wa.H = H;
 
   upd_wgrad_kernel<<<dim3(WG_SPLIT, 3), GEMM_THREADS, WG_SMEM, st>>>(wa, ws.err);
-  upd_wgrad0_kernel<<<wg0_ctas, THIN_THREADS, 0, st>>>(net, states, R, ws.dZ[0], ws.Hs[0], ws.part_l0);
+  upd_wgrad0_kernel<<<wg0_ctas, THIN_THREADS, 0, st>>>(net, states, R, ws.dZ[0], fwd_ts ? nullptr : ws.Hs[0], ws.part_l0);
   const int nblkA = (3 * H * (H + 1) + 255) / 256, nblkT = ((H + 1) + H * (F + 1) + 7) / 8;
   upd_reduce_kernel<<<nblkA + nblkT, 256, 0, st>>>(net, ws, THIN_CTAS, wg0_ctas, nblkA);
   MBO_CUDA(cudaMemcpyAsync(terms, ws.terms, (size_t)E * 16, cudaMemcpyDeviceToDevice, st));

@@ -289,8 +289,10 @@ def test_gemm_kernel_variants_agree_bitwise(monkeypatch):
     t0, v0, dW0, db0 = outs[0]
     for terms, v, dW, db in outs[1:]:
         assert torch.equal(terms, t0)
-        for k in ("h1", "h2", "h3", "h4", "dz1", "dz2", "dz3", "dz4", "logits", "dlogits"):
+        for k in ("h1", "h2", "h3", "h4", "dz2", "dz3", "dz4", "logits", "dlogits"):
             assert torch.equal(v[k], v0[k]), k
+        # the SS forward has no ReLU words of h1: its last dgrad stores dH1 and the layer-0 wgrad applies the mask
+        assert torch.equal(v["dz1"] * (v["h1"] > 0), v0["dz1"] * (v0["h1"] > 0))
         assert all(torch.equal(a, b) for a, b in zip(dW + db, dW0 + db0))
 
 
