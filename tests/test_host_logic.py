@@ -201,3 +201,37 @@ def test_function_draws_follow_reference_rng_order():
             y = torch.stack([fb.eval(torch.as_tensor(x[i:i + 1])) for i in range(6)])[:, 0].numpy()
             np.testing.assert_allclose(y, y_ref, rtol=1e-12, atol=1e-12)
             assert abs(float(fb.y_max[0]) - float(np.asarray(ref.y_max).reshape(-1)[0])) < 1e-12
+
+
+def test_ppo_update_abi_argument_checks_and_workspace_layout():
+    """mbo_ppo_* entry points without a GPU: size queries, the debug layout and the argument checks that
+    fire before any CUDA call (status code + mbo_last_error, no exception across the boundary)."""
+    import ctypes as C
+    from metabo_b200 import _lib as L
+    lib = L.lib()
+    n60 = lib.mbo_ppo_workspace_bytes(60, 966)
+    assert lib.mbo_ppo_workspace_bytes(0, 966) == 0 and lib.mbo_ppo_workspace_bytes(61, 966) > n60 > 60 * 966 * 208 * 4 * 8
+    off = (C.c_size_t * 12)()
+    assert lib.mbo_ppo_debug_offsets(60, 966, off) == 0
+    rows = ((60 * 966 + 127) // 128) * 128
+    o = list(off)
+    assert all(o[i + 1] - o[i] == rows * 208 * 4 for i in range(3))            # h1..h4 are consecutive [R_pad, 208] fp32 arrays
+    assert all(o[i + 1] - o[i] >= rows * 208 * 4 for i in range(4, 7)) and max(o) < n60
+    assert lib.mbo_ppo_debug_offsets(0, 966, off) == L.lib().mbo_ppo_debug_offsets(60, 966, None) < 0
+    null = C.c_void_p(0)
+    cols = (C.c_int32 * 6)(*range(6))
+    arr = (C.c_void_p * 5)()
+    rc = lib.mbo_ppo_policy_grad(0, 966, 6, 6, cols, 200, null, arr, arr, null, null, null, 0.15, 0.01, 1.0, arr, arr, null, null, 0, null)
+    assert rc == -1 and b"E, M must be > 0" in lib.mbo_last_error()
+    rc = lib.mbo_ppo_policy_grad(4, 10, 6, 6, cols, 300, null, arr, arr, null, null, null, 0.15, 0.01, 1.0, arr, arr, null, null, 0, null)
+    assert rc == -1 and b"hidden width" in lib.mbo_last_error()
+    rc = lib.mbo_ppo_policy_grad(4, 10, 6, 9, cols, 200, null, arr, arr, null, null, null, 0.15, 0.01, 1.0, arr, arr, null, null, 0, null)
+    assert rc == -1 and b"policy features" in lib.mbo_last_error()
+    assert lib.mbo_ppo_value_workspace_bytes(60, 200) >= 6 * 60 * 200 * 4 and lib.mbo_ppo_value_workspace_bytes(0, 200) == 0
+    rc = lib.mbo_ppo_value_grad(4, 60, 4, 5, 300, null, arr, arr, null, 0.1, arr, arr, null, null, null, 0, null)
+    assert rc == -1 and b"hidden width" in lib.mbo_last_error()
+    sizes = (C.c_int64 * 1)(4)
+    rc = lib.mbo_adam_step(0, arr, arr, arr, arr, sizes, arr, 1e-3, 0.9, 0.999, 1e-8, null)
+    assert rc == -1 and b"tensors per call" in lib.mbo_last_error()
+    assert lib.mbo_ppo_loss_sums(0, null, null, 1.0, 1.0, 0.01, null, null) == -1
+    assert lib.mbo_ppo_prepare_minibatch(0, 10, null, null, null, null, null, null, 1, null, null, null, null, null, null) == -1
