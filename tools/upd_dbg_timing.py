@@ -1,5 +1,7 @@
-"""Timing experiments on the update GEMMs: MBO_UPD_DBG bit mask (1 no epilogue, 2 no MMAs, 4 no A loads, 8 no weight
-loads); results are garbage, only the time of the whole call is of interest."""
+"""Timing experiments on the SS-form update GEMMs: MBO_UPD_DBG bit mask (1 no epilogue, 2 no MMAs, 4 no A loads, 8 no weight
+loads); results are garbage, only the time of the whole call is of interest.  The hooks live in upd_gemm_kernel (run with
+MBO_UPD_FWD_TS=0 to time the SS forward; bit 4 applies to its dgrad instantiation only) and in upd_dgrad_persist_kernel; the
+TS-form kernels (defaults for the forward) have none.  Tables of the round: profiles/r01c_update_launches.md."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
