@@ -127,6 +127,7 @@ class PPO:
             self.params.get("update_graph", True)
         self._upd = None        # (static inputs, CUDAGraph, static outputs) of one captured optimiser step
         self._ep = None         # native backend: one captured EPOCH (all minibatch steps) over static copies of the batch
+        self._ep_stale = True
         backend = self.params.get("update_backend", "native")
         if backend not in ("native", "autograd"):
             raise ValueError("update_backend must be 'native' or 'autograd'")
@@ -372,12 +373,13 @@ class PPO:
                         sums = sums + self._update_step_native(mbuf, prepared=True)
                     else:
                         sums = sums + self._update_step({k: v.index_select(0, sel) for k, v in static.items()})
-            self._ep = dict(sig=sig, static=static, perm=perm, graph=g, sums=sums, bounds=bounds, src=None)
+            self._ep = dict(sig=sig, static=static, perm=perm, graph=g, sums=sums, bounds=bounds)
+            self._ep_stale = True
         ep = self._ep
-        if ep["src"] is not buf["states"]:                 # a new batch: refresh the static copies once per iteration
+        if self._ep_stale:                                  # first epoch of this optimize_on_batch: refresh the static copies
             for k, v in flat.items():
                 ep["static"][k].copy_(v)
-            ep["src"] = buf["states"]
+            self._ep_stale = False
         ep["perm"].copy_(torch.as_tensor(order, dtype=torch.int64), non_blocking=False)
         ep["graph"].replay()
         return ep["sums"].clone(), len(ep["bounds"])
@@ -391,6 +393,7 @@ class PPO:
         local_mb = self.params["minibatch_size"] // self.world
         buf = self.batch_recorder.buf
         buf.pop("logprobs_old", None)
+        self._ep_stale = True             # the epoch graph reads static copies of the batch: refresh them once per call
         if self.update_backend == "native":
             # theta_old is frozen for the whole call: its log-probs (recomputed per minibatch in ppo.py:146-147) are
             # computed once per transition here and travel with the minibatches
