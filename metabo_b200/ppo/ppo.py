@@ -142,6 +142,7 @@ class PPO:
         self._pg_grads = None   # persistent gradient buffers of the policy net (written by the kernels)
         self._vg = None         # ops.PPOValueGrad
         self._vg_grads = None
+        self._flat_grads = None
         self._loss4 = None
         self._mbufs = {}        # minibatch buffers of mbo_ppo_prepare_minibatch, by minibatch size
 
@@ -195,6 +196,22 @@ class PPO:
         a = pi.value_net.arch_spec
         return pi.activation == "relu" and len(a) == 4 and len(set(a)) == 1 and 1 <= a[0] <= 256
 
+    def _alloc_native_grads(self):
+        """Persistent gradient buffers of the native backend, all views of ONE flat fp32 tensor: the kernels write into
+        them, and under torch.distributed the gradient all-reduce is a single call on the flat buffer."""
+        pi = self.pi
+        layers = list(pi.policy_net.fc) + (list(pi.value_net.fc) if pi.use_value_network else [])
+        n = sum(l.weight.numel() + l.bias.numel() for l in layers)
+        self._flat_grads = torch.zeros(n, dtype=torch.float32, device=self.device)
+        off, views = 0, []
+        for l in layers:
+            w = self._flat_grads[off:off + l.weight.numel()].view_as(l.weight); off += l.weight.numel()
+            b = self._flat_grads[off:off + l.bias.numel()].view_as(l.bias); off += l.bias.numel()
+            views.append((w, b))
+        k = len(pi.policy_net.fc)
+        self._pg_grads = ([w for w, _ in views[:k]], [b for _, b in views[:k]])
+        self._vg_grads = ([w for w, _ in views[k:]], [b for _, b in views[k:]])
+
     def _policy_grad_op(self, E, M, Fs):
         pg = self._pg
         if pg is None or pg.E < E or (pg.M, pg.F_state) != (M, Fs):
@@ -228,7 +245,7 @@ class PPO:
         if logprobs_old is None:
             logprobs_old = self._old_logprobs(states, actions)
         if self._pg_grads is None:
-            self._pg_grads = ([torch.zeros_like(l.weight) for l in fcs], [torch.zeros_like(l.bias) for l in fcs])
+            self._alloc_native_grads()
         dW, db = self._pg_grads
         self.optimizer.zero_grad(set_to_none=True)
         terms = self._pg(states.contiguous(), [l.weight.data for l in fcs], [l.bias.data for l in fcs],
@@ -241,8 +258,6 @@ class PPO:
             vfc = list(pi.value_net.fc)
             if self._vg is None or self._vg.E < E:
                 self._vg = ops.PPOValueGrad(E, pi.value_net.arch_spec[0], states.device)
-            if self._vg_grads is None:
-                self._vg_grads = ([torch.zeros_like(l.weight) for l in vfc], [torch.zeros_like(l.bias) for l in vfc])
             vW, vb = self._vg_grads
             _, vterms = self._vg(states.contiguous(), pi.t_idx, pi.T_idx, [l.weight.data for l in vfc],
                                  [l.bias.data for l in vfc], tdlamrets.to(torch.float32).contiguous(),
@@ -264,7 +279,10 @@ class PPO:
             l_val = l_val.detach()
         else:
             l_val = torch.sum(tdlamrets ** 2) / n_global       # the reference's value head is the constant 0
-        allreduce_gradients(list(self.pi.parameters()), self.world)
+        if self.world > 1 and self._flat_grads is not None and pi.use_value_network and self.native_value_supported(pi):
+            dist.all_reduce(self._flat_grads, op=dist.ReduceOp.SUM)      # every gradient is a view of this one buffer
+        else:
+            allreduce_gradients(list(self.pi.parameters()), self.world)
         self.optimizer.step()
         l_ppo = terms[:, 2].sum()
         l_ent = -terms[:, 1].sum() / n_global
