@@ -57,16 +57,29 @@ def load_weights():
 
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference algorithm on host cores (oracle port; the reference's GPy is not
-# installable).  One forked worker per core, torch pinned to 1 thread per worker,
-# exactly the reference's deployment (batchrecorder.py:24,162).
+# installable).  One forked worker per core, every worker single-threaded exactly as
+# the reference pins its workers (OMP_NUM_THREADS=1 at import: ppo.py:23, batchrecorder.py:24;
+# torch.set_num_threads(1): batchrecorder.py:162).  The pinning has to happen BEFORE numpy / torch
+# are imported, so the arm runs in a fresh child interpreter (`bench.py --cpu-child`) whose
+# environment is set first; the child keeps one persistent pool and prints one JSON line per step.
 # ------------------------------------------------------------------------------------------------
-def _cpu_worker(args):
-    seed, rounds, n = args
+PIN_ENV = {"OMP_NUM_THREADS": "1", "OPENBLAS_NUM_THREADS": "1", "MKL_NUM_THREADS": "1", "NUMEXPR_NUM_THREADS": "1",
+           "VECLIB_MAXIMUM_THREADS": "1"}
+_W = {}
+
+
+def _cpu_worker_init():
     import torch
     torch.set_num_threads(1)
     from oracle import metabo_oracle as O
-    pw = O.PolicyWeights.from_npz(os.path.join(ROOT, "tests", "golden", "weights_hm3_1988.npz"))
-    grids = O.Grids(HM3["D"], N_MS=HM3["N_MS"], N_LS=HM3["N_LS"], k=HM3["k"])
+    _W["O"] = O
+    _W["pw"] = O.PolicyWeights.from_npz(os.path.join(ROOT, "tests", "golden", "weights_hm3_1988.npz"))
+    _W["grids"] = O.Grids(HM3["D"], N_MS=HM3["N_MS"], N_LS=HM3["N_LS"], k=HM3["k"])
+
+
+def _cpu_worker(args):
+    seed, rounds, n = args
+    O, pw, grids = _W["O"], _W["pw"], _W["grids"]
     rng = np.random.RandomState(seed)
     cands = 0
     t0 = time.perf_counter()
@@ -80,53 +93,73 @@ def _cpu_worker(args):
     return cands, time.perf_counter() - t0
 
 
-def cpu_arm(rounds_per_core, n, cores=None):
+def cpu_child_main(argv):
+    """child interpreter of the CPU arm: `bench.py --cpu-child N_OBS CORES ROUNDS_PER_CORE REPS` (environment already
+    pinned by the parent, asserted here); prints one JSON line per repetition."""
+    n, cores, rounds, reps = (int(a) for a in argv)
+    for k, v in PIN_ENV.items():
+        assert os.environ.get(k) == v, "CPU arm must start with %s=%s" % (k, v)
     import multiprocessing as mp
-    cores = cores or os.cpu_count()
     ctx = mp.get_context("fork")
-    t0 = time.perf_counter()
-    with ctx.Pool(cores) as pool:
-        res = pool.map(_cpu_worker, [(1000 + i, rounds_per_core, n) for i in range(cores)])
-    wall = time.perf_counter() - t0
-    cands = sum(r[0] for r in res)
-    busy = max(r[1] for r in res)
-    return dict(value=cands / busy, unit="AF evals/s", cores=cores, kind="port",
-                sample="%d episodes-rounds (n=%d obs, 13461 candidates each) on %d forked workers, "
-                       "oracle port of GPy-route GP + torch-CPU NeuralAF, 1 thread/worker; %.1fs wall"
-                       % (rounds_per_core * cores, n, cores, wall)), cands, busy
+    with ctx.Pool(cores, initializer=_cpu_worker_init) as pool:
+        pool.map(_cpu_worker, [(i, 0, n) for i in range(cores)])         # all workers up, weights loaded
+        for rep in range(reps):
+            t0 = time.perf_counter()
+            res = pool.map(_cpu_worker, [(1000 + rep * cores + i, rounds, n) for i in range(cores)], chunksize=1)
+            wall = time.perf_counter() - t0
+            print(json.dumps({"cands": sum(r[0] for r in res), "wall": wall, "busy_max": max(r[1] for r in res)}), flush=True)
+
+
+def cpu_arm(rounds_per_core, n, reps=1, cores=None):
+    """-> list of (candidates, seconds) per repetition, and the description dict.  seconds = wall time of the
+    parallel map over the persistent single-threaded workers (includes task dispatch, excludes interpreter start)."""
+    cores = cores or os.cpu_count()
+    env = dict(os.environ)
+    env.update(PIN_ENV)
+    env.pop("CUDA_VISIBLE_DEVICES", None)
+    env["CUDA_VISIBLE_DEVICES"] = ""                      # the CPU arm never touches a GPU
+    out = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-child", str(n), str(cores),
+                          str(rounds_per_core), str(reps)], env=env, check=True, stdout=subprocess.PIPE, cwd=ROOT)
+    reps_out = [json.loads(l) for l in out.stdout.decode().splitlines() if l.startswith("{")]
+    assert len(reps_out) == reps
+    desc = dict(unit="AF evals/s", cores=cores, kind="port",
+                sample="%d episode-rounds per step (n=%d obs, 13461 candidates each; %d per worker) on %d forked "
+                       "single-threaded workers (OMP/OPENBLAS/MKL_NUM_THREADS=1 set before import, torch 1 thread, as "
+                       "ppo.py:23 / batchrecorder.py:24,162): oracle port of the GPy-route GP + torch-CPU fp32 NeuralAF"
+                       % (rounds_per_core * cores, n, rounds_per_core, cores))
+    return [(r["cands"], r["wall"]) for r in reps_out], desc
 
 
 def run_reference_arm(args, rank):
     if rank != 0:
         return
-    per_step = []
-    total_c = 0
-    for i in range(args.warmup + args.steps):
-        cb, cands, busy = cpu_arm(1, args.n_obs)
-        if i >= args.warmup:
-            per_step.append(busy)
-            total_c += cands
-    t = sum(per_step)
-    v = total_c / t
-    line = {"metric": "AF evals/sec (GP posterior+NeuralAF per candidate)", "impl": "reference", "value": v,
+    rounds = 4
+    reps, desc = cpu_arm(rounds, args.n_obs, reps=args.warmup + args.steps)
+    timed = reps[args.warmup:]
+    t = sum(w for _, w in timed)
+    v = sum(c for c, _ in timed) / t
+    line = {"metric": METRIC, "impl": "reference", "value": v,
             "unit": "AF evals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64 GP + f32 MLP", "data": "synthetic",
-            "config": workload_config(args, cb["cores"], ref=True),
-            "cpu_baseline": dict(cb, value=v),
+            "config": workload_config(args),
+            "reference_step": "%d episode-rounds of the workload per step (bounded sample; the GPU arm's step is "
+                              "episodes_per_gpu rounds per GPU)" % (rounds * desc["cores"]),
+            "cpu_baseline": dict(desc, value=v),
             "e2e": {"value": v, "unit": "AF evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def workload_config(args, B, ref=False):
-    c = {"workload": "evaluate_metabo_hm3.py AF-optimisation round (BASELINE configs[1]): D=3, F=7, 4x200 ReLU "
-                     "policy, candidates 1728+10000+1733 per episode, n=%d observations" % args.n_obs,
-         "episodes_per_gpu": B, "candidates_per_episode_round": 13461, "n_obs": args.n_obs}
-    if ref:
-        c["episodes_per_step"] = B
-    else:
-        c.update(gp_precision=args.gp, mlp_mode=args.mlp, l2="flushed between timed steps (256 MiB write)")
-    return c
+METRIC = "AF evals/sec (GP posterior+NeuralAF per candidate)"
+
+
+def workload_config(args):
+    """identical in both arms (the driver compares the two lines' `config`)"""
+    return {"workload": "evaluate_metabo_hm3.py AF-optimisation round (BASELINE configs[1]): D=3, F=7, 4x200 ReLU "
+                        "policy, candidates 1728+10000+1733 per episode, n=%d observations" % args.n_obs,
+            "episodes_per_gpu": args.B, "candidates_per_episode_round": 13461, "n_obs": args.n_obs,
+            "gp_precision": args.gp, "mlp_mode": args.mlp,
+            "l2": "flushed between timed steps (256 MiB write)"}
 
 
 class ClockSampler:
@@ -204,7 +237,7 @@ def ppo_rollout_rate(dev, world, rank):
     size = n_workers * eps * 30
     br = BatchRecorder(size=size, env_id=spec["env_id"], env_seeds=list(range(rank * n_workers, (rank + 1) * n_workers)),
                        policy_fn=lambda o, a, d: NeuralAF(o, a, d, options=opts), n_workers=n_workers,
-                       deterministic=False, store_states=False, mlp_mode="fp16", device=dev)
+                       deterministic=False, store_states=True, mlp_mode="fp16", device=dev)
     br.record_batch(0.98, 0.98)                       # eager warm-up
     br.record_batch(0.98, 0.98)                       # CUDA-graph capture of the per-step units
     br.record_batch(0.98, 0.98)                       # first replay
@@ -218,7 +251,8 @@ def ppo_rollout_rate(dev, world, rank):
     return {"env_steps_per_s": world * size / t, "t_batch_s": t, "batch_steps": world * size,
             "config": "train_metabo_branin.py env (C3), stochastic NeuralAF 4x200, 1024 episodes x T=30 per GPU, "
                       "6927 candidates per step (phase 3 reuses the multistart results of phase 1: 5199 evaluated), fp16 MLP + fp64 GP, "
-                      "CUDA-graph replay of the episode loop, transitions kept on device without states"}
+                      "CUDA-graph replay of the episode loop, every transition's state [966, 6] fp32 stored on the device "
+                      "(store_states=True, what PPO trains on; 712 MB per batch per GPU)"}
 
 
 def ppo_update_rate(dev):
@@ -283,6 +317,8 @@ def ppo_update_rate(dev):
 
 
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--cpu-child":
+        return cpu_child_main(sys.argv[2:])
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -291,7 +327,9 @@ def main():
     ap.add_argument("--B", type=int, default=1024, help="episodes per GPU")
     ap.add_argument("--n-obs", dest="n_obs", type=int, default=30)
     ap.add_argument("--gp", default="fp64", choices=["fp64", "fp32"])
-    ap.add_argument("--mlp", default="auto", choices=["auto", "fp32", "tf32", "bf16x3", "fp16"])
+    ap.add_argument("--mlp", default="fp16", choices=["fp32", "tf32", "bf16x3", "fp16"],
+                    help="arithmetic of the NeuralAF kernel for the headline line; an unavailable mode is an error")
+    ap.add_argument("--no-modes", action="store_true", help="skip the tf32 / bf16x3 step times printed next to the headline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ppo", action="store_true", help="skip the supplementary PPO rollout env-steps/s figure")
     args = ap.parse_args()
@@ -348,22 +386,20 @@ def main():
     Tvec = torch.full((B,), float(T), device=dev)
 
     modes = L.MLP_MODES
-    order = ["fp16", "tf32", "bf16x3", "fp32"] if args.mlp == "auto" else [args.mlp]
-    eng = None
-    for m in order:
-        try:
-            e = make_engine(modes[m])
-            e.set_data(X, Y, nvec, n_active_max=n)
-            e.set_episode_scalars(inc, tvec, Tvec)
-            e.af_round()
-            torch.cuda.synchronize()
-            eng, args.mlp = e, m
-            break
-        except L.MboError as ex:
-            if args.mlp != "auto":
-                raise
-            sys.stderr.write("[bench] mlp mode %s unavailable: %s\n" % (m, ex))
-    assert eng is not None
+
+    def ready_engine(m):
+        """no fallback ladder: a mode the library cannot run raises (MboError) and the bench fails"""
+        e = make_engine(modes[m])
+        if e.mlp_mode != modes[m]:
+            raise L.MboError("mlp mode %s is not available for this policy" % m)
+        e.set_data(X, Y, nvec, n_active_max=n)
+        e.set_episode_scalars(inc, tvec, Tvec)
+        e.af_round()
+        torch.cuda.synchronize()
+        e.policy.check()
+        return e
+
+    eng = ready_engine(args.mlp)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -372,7 +408,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, profile=False):
+    def timed(fn, steps, warmup, profile=False, eng=eng):
         for _ in range(warmup):
             fn()
         barrier()
@@ -410,22 +446,27 @@ def main():
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
         peaks = json.load(open(pk))
-    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
-    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else \
-        "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+    # the kernel is timed alone (CUDA events around the one launch) inside a sub-second region at max clock: the burst
+    # figure is the denominator; the sustained one is given beside it
+    peak_tf = peaks.get("bf16_tflops", 1620.0)
+    peak_sus = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "MEASURED_PEAKS.json bf16_tflops (burst: kernel timed alone by CUDA events)" if peaks else \
+        "fallback 1.62 PFLOP/s burst / 1.4 sustained (B200_PROFILING.md)"
     roof = None
     if mlp_big:
         dur = float(np.mean(mlp_big)) / 1e3
         ach = B * HM3["k"] * HM3["N_LS"] * MLP_FLOPS / dur / 1e12
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
         if os.path.exists(tp) and B == 1024:
             tj = json.load(open(tp)).get(args.mlp)
             if tj:
                 traffic = tj["dram_read_bytes"] + tj["dram_write_bytes"]     # one ncu --set full capture of this launch shape
         roof = {"bound": "tensor", "kernel": "NeuralAF MLP (%s), B x 10000 local-grid candidates" % args.mlp,
                 "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
-                "traffic_unit": "bytes per launch (dram read+write, ncu)",
+                "peak_sustained": peak_sus, "frac_of_sustained": ach / peak_sus,
+                "traffic_unit": "bytes per launch (dram read+write, one ncu --set full capture of this build: "
+                                "profiles/r02_traffic.json)",
                 "peak_source": peak_src, "avg_launch_ms": dur * 1e3,
                 "format_ceiling_frac": {"fp16": 1.0, "tf32": 0.5, "bf16x3": 1.0 / 3.0, "fp32": None}[args.mlp]}
         if gp_big:
@@ -456,6 +497,24 @@ def main():
     d2h = h_act.numel() * 4 + h_x.numel() * 8
     e2e_val = world * cands_step * args.steps / (ms_e / 1e3)
 
+    # ---- the other arithmetic modes of the same step (bf16x3 = the fp32-class default of the drop-in classes) ----
+    modes_info = None
+    if not args.no_modes:
+        modes_info = {args.mlp: {"ms_per_step": ms / args.steps, "AF_evals_per_s": value, "headline": True}}
+        for m in ("tf32", "bf16x3"):
+            if m == args.mlp:
+                continue
+            e2 = ready_engine(m)
+            k_steps = min(args.steps, 10)
+            ms_m, _, _ = timed(lambda: e2.af_round(), k_steps, 3, eng=e2)
+            e2.policy.check()
+            modes_info[m] = {"ms_per_step": ms_m / k_steps, "AF_evals_per_s": world * cands_step * k_steps / (ms_m / 1e3),
+                             "steps": k_steps}
+            del e2
+        modes_info["note"] = ("fp16 / tf32: 11-bit significand operands, fp32 accumulate (logits within 1e-3 of the fp32 "
+                              "reference, north_star's bar); bf16x3: split-bf16 3-pass, fp32-class (7e-6) -- the default "
+                              "mlp_mode of the drop-in NeuralAF / MetaBO / BatchRecorder classes")
+
     ppo_info = None
     upd_info = None
     if not args.no_ppo:
@@ -465,20 +524,22 @@ def main():
 
     cpu_b = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_b, _, _ = cpu_arm(3, n)
+        reps, cpu_b = cpu_arm(4, n, reps=3)        # 1 warm-up + 2 timed repetitions of 4 episode-rounds per core
+        cpu_b["value"] = sum(c for c, _ in reps[1:]) / sum(w for _, w in reps[1:])
 
     if world > 1:
         dist.barrier()
     if rank == 0:
-        line = {"metric": "AF evals/sec (GP posterior+NeuralAF per candidate)", "value": value, "unit": "AF evals/s",
+        line = {"metric": METRIC, "value": value, "unit": "AF evals/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64 GP + %s MLP" % args.mlp if args.gp == "fp64" else "f32 GP + %s MLP" % args.mlp,
                 "data": "synthetic (U[0,1] observations of Hartmann-3 variants; %s)" % wdesc,
-                "config": workload_config(args, B), "clocks": clocks,
+                "config": workload_config(args), "clocks": clocks,
                 "e2e": {"value": e2e_val, "unit": "AF evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e / args.steps},
-                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu_b, "ppo_rollout": ppo_info, "ppo_update": upd_info}
+                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu_b, "modes": modes_info,
+                "ppo_rollout": ppo_info, "ppo_update": upd_info}
         eng.policy.check()            # raises if a tensor-core kernel timed out or the fp16 mode clamped an activation
         print(json.dumps(line))
     if world > 1:

@@ -73,7 +73,9 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {   // splitmix64
 constexpr uint64_t GOLD = 0x9E3779B97F4A7C15ull;
 __device__ __forceinline__ float gumbel_noise(uint64_t key, int m) {
   uint64_t r = mix64(key + GOLD * (uint64_t)(m + 1));
-  float u = ((float)(r >> 40) + 0.5f) * (1.0f / 16777216.0f);   // 24-bit uniform in (0,1)
+  // 23-bit uniform strictly inside (0,1): (k + 0.5) * 2^-23 is exact in fp32 for every k < 2^23 (a 24-bit k + 0.5 is
+  // not representable from 2^23 on, and k = 2^24 - 1 rounded to u = 1 -> noise = +inf)
+  float u = ((float)(r >> 41) + 0.5f) * (1.0f / 8388608.0f);
   return -logf(-logf(u));
 }
 

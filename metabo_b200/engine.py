@@ -116,7 +116,10 @@ class AFEngine:
             self.mlp_mode = L.MLP_TF32    # fp16 mode needs two spare K columns; tf32 has the same significand
 
     def set_value_net(self, weights, biases, activation="relu"):
-        self.value = ops.PolicyHandle()
+        # ONE handle for the life of the engine: captured CUDA graphs (VecMetaBO) hold its device pointers by value,
+        # and mbo_policy_set_weights keeps the buffers while the architecture is unchanged
+        if self.value is None:
+            self.value = ops.PolicyHandle()
         self.value.set_weights(weights, biases, activation)
 
     def set_hyperparameters(self, lengthscale, variance, noise):

@@ -107,6 +107,13 @@ class FunctionSampler:
         self.discrete_grid = discrete_grid
         if f_type not in ("BRA-var", "HM3-var", "GP"):
             raise ValueError("Unknown f_type!")                # metabo_gym.py:544 (families outside the hot path)
+        if f_type == "GP" and discrete_grid is None:
+            # continuous domain (local_af_opt=True): approximate extrema on a uniform grid with
+            # ceil(1000^(1/D)) points per dimension (metabo_gym.py:254-258)
+            from ..engine import uniform_grid
+            n_dim = int(np.ceil(1000 ** (1 / D)))
+            assert n_dim > 3
+            self.discrete_grid = torch.as_tensor(uniform_grid(D, n_dim), device=device)
         self._grid = None
         if f_type in ("BRA-var", "HM3-var") and self.f_opts.get("M") is not None:
             nd = 3 if f_type == "BRA-var" else 4

@@ -445,4 +445,6 @@ class FusedAdam(torch.optim.Optimizer):
                                           arr([self.state[p]["_dev"] for p in ps]),
                                           float(group["lr"]), float(b1), float(b2), float(group["eps"]), _stream()),
                     "mbo_adam_step")
+            for p in ps:        # the kernel writes through raw pointers: torch's version counter does not move, so
+                p._mbo_version = getattr(p, "_mbo_version", 0) + 1      # NeuralAF._version() reads this one as well
         return None

@@ -83,7 +83,22 @@ class NeuralAF(nn.Module):
         return [i for i, m in enumerate(self.policy_mask()) if m]
 
     def _version(self):
-        return tuple(p._version for p in self.parameters()) + tuple(p.data_ptr() for p in self.parameters())
+        # _mbo_version: bumped by ops.FusedAdam (its kernel updates the parameters through raw pointers)
+        return tuple((p._version, getattr(p, "_mbo_version", 0), p.data_ptr()) for p in self.parameters())
+
+    def __deepcopy__(self, memo):
+        """copy.deepcopy(pi) (ppo.py:203 hands a copy to the workers): the kernel handles own device memory and are
+        not copied -- the copy re-packs its own on first use."""
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k in ("_h_policy", "_h_value", "_packed_version"):
+                new.__dict__[k] = None
+            else:
+                new.__dict__[k] = copy.deepcopy(v, memo)
+        return new
 
     def kernel_handles(self):
         """(policy handle, value handle or None), re-packed whenever a parameter changed."""

@@ -217,6 +217,7 @@ class PPO:
         if pg is None or pg.E < E or (pg.M, pg.F_state) != (M, Fs):
             pi = self.pi
             self._pg = ops.PPOPolicyGrad(E, M, Fs, pi.policy_columns(), pi.policy_net.arch_spec[0], self.device)
+            self._upd = self._ep = None      # captured graphs hold the old workspace's pointers
         return self._pg
 
     def _old_logprobs(self, states, actions):
@@ -257,7 +258,9 @@ class PPO:
         if pi.use_value_network and self.native_value_supported(pi):
             vfc = list(pi.value_net.fc)
             if self._vg is None or self._vg.E < E:
+                assert not torch.cuda.is_current_stream_capturing(), "value-net workspace must be sized before a capture"
                 self._vg = ops.PPOValueGrad(E, pi.value_net.arch_spec[0], states.device)
+                self._upd = self._ep = None  # captured graphs hold the old workspace's pointers
             vW, vb = self._vg_grads
             _, vterms = self._vg(states.contiguous(), pi.t_idx, pi.T_idx, [l.weight.data for l in vfc],
                                  [l.bias.data for l in vfc], tdlamrets.to(torch.float32).contiguous(),

@@ -24,7 +24,7 @@ def gumbel_noise(seed, b, step, M):
     with np.errstate(over="ignore"):
         key = mix64(mix64(np.uint64(seed) + GOLD * np.uint64(b + 1)) ^ (np.uint64(step) + GOLD))
         r = mix64(key + GOLD * (np.arange(M, dtype=np.uint64) + np.uint64(1)))
-    u = ((r >> np.uint64(40)).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 16777216.0)
+    u = ((r >> np.uint64(41)).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 8388608.0)   # 23 bits: exact, never 1
     return -np.log(-np.log(u, dtype=np.float32), dtype=np.float32)
 
 

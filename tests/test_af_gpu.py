@@ -73,12 +73,12 @@ def test_logits_on_reference_states(golden_dir, name, wfile, mode_name, mode, to
         got, ref = lg[0].cpu().numpy(), ep[p + "logits"]
         scale = np.max(np.abs(ref))
         assert np.max(np.abs(got - ref)) <= tol * scale + 1e-6, (name, int(t), mode_name)
-        if mode == 0:
-            # deterministic-eval action: identical unless the reference's top two are within tolerance
-            a_ref = int(ep[p + "action"])
-            a, _ = ops.logits_argmax(lg)
-            a = int(a[0])
-            assert a == a_ref or abs(ref[a] - ref[a_ref]) <= 2 * tol * scale
+        # deterministic-eval action (north_star): identical to the reference's unless the reference's own top two
+        # logits are within the mode's tolerance of each other -- asserted for EVERY arithmetic mode
+        a_ref = int(ep[p + "action"])
+        a, _ = ops.logits_argmax(lg)
+        a = int(a[0])
+        assert a == a_ref or abs(ref[a] - ref[a_ref]) <= 2 * tol * scale, (name, int(t), mode_name, a, a_ref)
 
 
 def test_value_net_matches_reference(golden_dir):
@@ -270,7 +270,13 @@ def test_sampler_is_invariant_under_sharding():
     full = ops.logits_sample(lg, seed=5, step=3).cpu().numpy()
     part = ops.logits_sample(lg[7:].contiguous(), seed=5, step=3, episode_offset=7).cpu().numpy()
     assert np.array_equal(full[7:], part)
-    assert np.array_equal(S.sample(lg.cpu().numpy(), 5, 3), full) or True   # oracle noise differs by <= 1 ulp of logf
+    # the oracle restates the noise bit for bit up to libm-vs-CUDA logf (<= 2 ulp): the sampled action may only differ
+    # where the top two perturbed logits are that close
+    ref = S.sample(lg.cpu().numpy(), 5, 3)
+    pert = lg.cpu().numpy() + np.stack([S.gumbel_noise(5, b, 3, lg.shape[1]) for b in range(lg.shape[0])])
+    for b in range(lg.shape[0]):
+        assert ref[b] == full[b] or abs(pert[b, ref[b]] - pert[b, full[b]]) <= 1e-5 * np.abs(pert[b]).max(), b
+    assert (ref == full).mean() >= 0.9
 
 
 @pytest.mark.parametrize("D", [4, 6])
@@ -344,16 +350,23 @@ def test_full_size_properties_hartmann3_batch(golden_dir):
     assert torch.equal(sd1, sd2) and torch.equal(sd1, sd3)                                        # (d)
     assert float((m3 - (2.0 * m1 - 0.5 * m2)).abs().max()) < 1e-8 * max(1.0, float(m1.abs().max()))
     mean, std = m1.float(), sd1.float()
-    lg = {m: ops.af_logits(pol, codes, cs, mean, std, epi, B, mode=m) for m in (0, 1, 2)}
+    lg = {m: ops.af_logits(pol, codes, cs, mean, std, epi, B, mode=m) for m in (0, 1, 2, 3)}
     torch.cuda.synchronize(); pol.check()
     scale = float(lg[0].abs().max())
     assert float((lg[1] - lg[0]).abs().max()) <= 1e-3 * scale                                     # (b)
     assert float((lg[2] - lg[0]).abs().max()) <= 2e-5 * scale
+    assert float((lg[3] - lg[0]).abs().max()) <= 1e-3 * scale          # fp16 = the mode bench.py times
+    # deterministic argmax per episode: every mode picks the fp32 kernel's action or one within its tolerance of it
+    a0, v0 = ops.logits_argmax(lg[0])
+    for m, tol in ((1, 1e-3), (2, 2e-5), (3, 1e-3)):
+        am, _ = ops.logits_argmax(lg[m])
+        picked = lg[0].gather(1, am.long()[:, None])[:, 0]
+        assert bool(((am == a0) | ((v0 - picked) <= 2 * tol * scale)).all()), m
     for b in (0, 517, 1023):                                                                      # (a)
         csb = ops.CandidateSet(D, tail=table, cubes=cubes[b:b + 1].contiguous())
         mb, sb = ops.gp_posterior(st1[b:b + 1].contiguous(), T, csb, 1)
         assert torch.equal(mb[0], m1[b]) and torch.equal(sb[0], sd1[b])
-        for m in (1, 2):
+        for m in (1, 2, 3):
             one = ops.af_logits(pol, codes, csb, mean[b:b + 1].contiguous(), std[b:b + 1].contiguous(),
                                 epi[b:b + 1].contiguous(), 1, mode=m)
             assert torch.equal(one[0], lg[m][b])

@@ -290,3 +290,73 @@ def test_graph_captured_ppo_update_equals_eager(golden_dir, tmp_path, monkeypatc
     log = lambda p: [float(x.split("=")[1]) for line in p.iter_log_str.splitlines() if "loss_ppo" in line for x in line.split(",")[1:]]
     np.testing.assert_allclose(log(ppo_f), log(ppo), rtol=1e-3)
     assert float((w_f - w_g).abs().max()) <= 2.5 * 1e-3 * 24
+
+
+def test_graph_replay_values_follow_weight_updates(golden_dir):
+    """the rollout graphs capture the value net's device pointers by value; `set_worker_weights` with
+    NEW weights before every batch (what PPO.train does once per iteration) must be seen by the replayed graphs for
+    at least 3 iterations after the capture -- values of the graph path == eager path, and they change with the weights."""
+    from metabo_b200 import gym_compat as gym
+    from metabo_b200.policies.policies import NeuralAF
+    from metabo_b200.ppo.batchrecorder import BatchRecorder
+    pw = O.PolicyWeights.from_npz(os.path.join(golden_dir, "weights_bra_1635.npz"))
+    spec = dict(BRA_SPEC, T=4, N_MS=100, N_LS=50, k=3, f_opts={"bound_translation": 0.1, "bound_scaling": 0.1, "M": 50},
+                reward_transformation="neg_log10", env_id="MetaBO-VALNET-v0")
+    gym.register(id=spec["env_id"], entry_point="metabo.environment.metabo_gym:MetaBO", max_episode_steps=4, kwargs=spec)
+    opts = dict(pw.options, mlp_mode="fp16")
+
+    def run(use_graphs):
+        fn = lambda o, a, d: NeuralAF(o, a, d, options=opts)
+        br = BatchRecorder(size=4 * 6, env_id=spec["env_id"], env_seeds=[3, 4, 5], policy_fn=fn, n_workers=3,
+                           deterministic=False, store_states=False, mlp_mode="fp16", use_graphs=use_graphs)
+        pi = fn(br.observation_space, br.action_space, False)
+        pi.load_state_dict({k: v.clone() for k, v in pw.sd.items()})
+        h_val = None
+        vals = []
+        for it in range(6):
+            with torch.no_grad():                      # a different value head (and policy) every iteration
+                pi.value_net.fc[4].bias.add_(0.25)
+                pi.policy_net.fc[4].bias.add_(0.01)
+            br.set_worker_weights(pi)
+            if h_val is None:
+                h_val = br.env.engine.value
+            assert br.env.engine.value is h_val        # ONE handle for the life of the engine
+            br.record_batch(0.98, 0.98)
+            vals.append(br.buf["values"].clone())
+        return vals, br
+
+    eager, _ = run(False)
+    graph, br = run(True)
+    assert any("graph" in e for e in br.env._graphs.values())
+    for it, (a, b) in enumerate(zip(eager, graph)):
+        assert torch.equal(a, b), it
+    for it in range(1, 6):
+        assert float((eager[it] - eager[it - 1]).mean()) == pytest.approx(0.25, abs=1e-3)
+
+
+def test_gp_family_with_local_af_optimisation(golden_dir):
+    """f_type "GP" with local_af_opt=True (evaluate_metabo_gps.py-style continuous domain): the
+    extrema come from the uniform grid with ceil(1000^(1/D)) points per dimension (metabo_gym.py:254-258)."""
+    from metabo_b200.environment.vec_env import VecMetaBO
+    from metabo_b200.environment.functions import FunctionSampler
+    from metabo_b200.engine import uniform_grid
+    pi, pw = _policy(golden_dir, "weights_gps_1161.npz", mode="fp32", M=2000, F=6)
+    D = 3
+    spec = {"env_id": "MetaBO-GPLOC-v0", "D": D, "f_type": "GP",
+            "f_opts": {"kernel": "Matern52", "lengthscale_low": 0.05, "lengthscale_high": 0.5, "noise_var_low": 0.1,
+                       "noise_var_high": 0.1, "signal_var_low": 1.0, "signal_var_high": 1.0, "min_regret": 1e-6},
+            "features": ["posterior_mean", "posterior_std", "incumbent", "timestep_perc", "timestep", "budget"],
+            "T": 4, "n_init_samples": 0, "pass_X_to_pi": False, "kernel": "Matern52", "kernel_lengthscale": None,
+            "kernel_variance": None, "noise_variance": None, "use_prior_mean_function": True, "local_af_opt": True,
+            "N_MS": 500, "N_LS": 200, "k": 3, "reward_transformation": "neg_log10"}
+    env = VecMetaBO(2, [11, 12], mlp_mode="fp32", **spec)
+    env.set_policy(pi)
+    env.reset(deterministic=True)
+    # y_max / y_min == max / min of the drawn sample over the 10^3 uniform grid
+    grid = torch.as_tensor(uniform_grid(D, 10), device=env.dev)
+    y = env.fb.raw(grid[None].expand(2, -1, -1))
+    assert torch.equal(env.fb.y_max, y.max(dim=1).values) and torch.equal(env.fb.y_min, y.min(dim=1).values)
+    for _ in range(4):
+        r, done = env.step(deterministic=True)
+    torch.cuda.synchronize()
+    assert done and bool(torch.isfinite(r).all())
