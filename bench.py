@@ -255,6 +255,76 @@ def ppo_rollout_rate(dev, world, rank):
                       "(store_states=True, what PPO trains on; 712 MB per batch per GPU)"}
 
 
+def ppo_train_rate(dev, world, rank, episodes_per_gpu, n_epochs, label):
+    """BASELINE configs[2] (train_metabo_branin.py:34-113) end to end under world = N: PPO iterations = weight sync +
+    rollouts sharded over the ranks (record_batch) + optimize_on_batch with every minibatch of the reference's size
+    (60) sharded over the ranks and the gradient exchanged inside the Adam kernel over NVLink peer memory.  Two warm
+    iterations (eager, graph capture), then two timed ones; times are the max over ranks."""
+    import copy
+    import shutil
+    import torch
+    import torch.distributed as dist
+    from metabo_b200 import gym_compat as gym
+    from metabo_b200.policies.policies import NeuralAF
+    from metabo_b200.ppo.ppo import PPO
+    T = 30
+    spec = {"env_id": "MetaBO-BRA-train-%s-v0" % episodes_per_gpu, "D": 2, "f_type": "BRA-var",
+            "f_opts": {"bound_translation": 0.1, "bound_scaling": 0.1, "M": 50},
+            "features": ["posterior_mean", "posterior_std", "timestep", "budget", "x"], "T": T, "n_init_samples": 0,
+            "pass_X_to_pi": False, "kernel_lengthscale": [0.235, 0.578], "kernel_variance": 2.0,
+            "noise_variance": 8.9e-16, "use_prior_mean_function": False, "local_af_opt": True, "N_MS": 1000,
+            "N_LS": 1000, "k": 5, "reward_transformation": "neg_log10"}
+    gym.register(id=spec["env_id"], entry_point="metabo.environment.metabo_gym:MetaBO", max_episode_steps=T, kwargs=spec)
+    if episodes_per_gpu is None:            # the reference batch: 1200 transitions = 40 episodes in total
+        n_workers, batch = 40, 1200
+    else:
+        n_workers, batch = 64 * world, episodes_per_gpu * T * world
+    params = {"batch_size": batch, "max_steps": 10 ** 12, "minibatch_size": 60, "n_epochs": n_epochs, "lr": 1e-4,
+              "epsilon": 0.15, "value_coeff": 1.0, "ent_coeff": 0.01, "gamma": 0.98, "lambda": 0.98,
+              "loss_type": "GAElam", "normalize_advs": True, "n_workers": n_workers, "env_id": spec["env_id"], "seed": 0,
+              "env_seeds": list(range(n_workers)), "mlp_mode": "fp16",
+              "policy_options": {"activations": "relu", "arch_spec": [200] * 4, "use_value_network": True, "t_idx": -2,
+                                 "T_idx": -1, "arch_spec_value": [200] * 4, "mlp_mode": "fp16"}}
+    logdir = os.path.join(tempfile.gettempdir(), "mbo_bench_ppo_%d_%s" % (os.getpid() if world == 1 else int(os.environ.get("MASTER_PORT", "0")), label))
+    if rank == 0:
+        shutil.rmtree(logdir, ignore_errors=True)
+    if world > 1:
+        dist.barrier()
+    ppo = PPO(policy_fn=lambda o, a, d: NeuralAF(o, a, d, options=params["policy_options"]), params=params,
+              logpath=os.path.join(logdir, "log"), save_interval=10 ** 9, verbose=True)
+    br = ppo.batch_recorder
+    times = []
+    for it in range(4):
+        ppo.iter_log_str = ""
+        if world > 1:
+            dist.barrier()
+        tw = br.set_worker_weights(copy.deepcopy(ppo.pi))
+        tb = br.record_batch(gamma=params["gamma"], lam=params["lambda"])
+        to = ppo.optimize_on_batch()
+        tt = torch.tensor([tw, tb, to], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        times.append(tt.tolist())
+    flat = torch.cat([p.detach().reshape(-1) for p in ppo.pi.parameters()])
+    same = True
+    if world > 1:
+        gathered = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(gathered, flat)
+        same = all(torch.equal(gathered[0], g) for g in gathered)
+    tw, tb, to = [float(np.mean([t[i] for t in times[2:]])) for i in range(3)]
+    n_steps = n_epochs * len(ppo._ep["bounds"]) if ppo._ep is not None else None
+    if rank == 0:
+        shutil.rmtree(logdir, ignore_errors=True)
+    return {"config": label, "global_batch_steps": batch, "minibatch_size": 60, "n_epochs": n_epochs,
+            "optimizer_steps_per_iteration": n_steps, "t_weights_s": tw, "t_batch_s": tb, "t_optim_s": to,
+            "rollout_env_steps_per_s": batch / tb, "end_to_end_env_steps_per_s": batch / (tw + tb + to),
+            "ms_per_optimizer_step": 1e3 * to / n_steps if n_steps else None,
+            "gradient_exchange": ("none (1 rank)" if world == 1 else
+                                  "mbo_comm_allreduce_adam: one-shot pull over NVLink peer memory fused into the Adam kernel, "
+                                  "inside the captured epoch graph" if ppo.comm is not None else "NCCL all_reduce, eager"),
+            "weights_identical_on_all_ranks": bool(same)}
+
+
 def ppo_update_rate(dev):
     """Supplementary: one PPO optimiser step's policy-net forward + backward on a train_metabo_branin.py minibatch
     (60 transitions x 966 candidates, 4x200 ReLU policy): the hand-written kernels behind mbo_ppo_policy_grad
@@ -517,10 +587,15 @@ def main():
 
     ppo_info = None
     upd_info = None
+    train_info = None
     if not args.no_ppo:
         ppo_info = ppo_rollout_rate(dev, world, rank)
         if rank == 0:
             upd_info = ppo_update_rate(dev)
+        train_info = [ppo_train_rate(dev, world, rank, None, 4, "C3 reference batch: train_metabo_branin.py (1200 steps = 40 "
+                                     "episodes over all ranks, minibatch 60, 4 epochs)"),
+                      ppo_train_rate(dev, world, rank, 1024, 1, "C3 at 1024 episodes per GPU (weak scaling of the batch, "
+                                     "minibatch 60, 1 epoch per iteration to bound the bench time)")]
 
     cpu_b = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -539,7 +614,7 @@ def main():
                 "e2e": {"value": e2e_val, "unit": "AF evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e / args.steps},
                 "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu_b, "modes": modes_info,
-                "ppo_rollout": ppo_info, "ppo_update": upd_info}
+                "ppo_rollout": ppo_info, "ppo_update": upd_info, "ppo_train": train_info}
         eng.policy.check()            # raises if a tensor-core kernel timed out or the fp16 mode clamped an activation
         print(json.dumps(line))
     if world > 1:

@@ -261,11 +261,17 @@ int mbo_ppo_value_grad(int E, size_t state_stride, int t_col, int T_col, int Hv,
 /* Minibatch gather + advantage normalisation of one optimiser step (ppo.py:129-144; batchrecorder.py:318-333 yields the
  * shuffled minibatches): transitions sel[0..E) (device int64 indices into the flattened batch) are gathered from the
  * batch arrays; advantages become (adv - mean) / std with the biased std of the minibatch (left alone if std is 0 / NaN).
- * row_floats = M * F floats per state.  logp_old_all may be NULL (zeros are written). */
+ * row_floats = M * F floats per state.  logp_old_all may be NULL (zeros are written).  adv_stats (device, 3 doubles
+ * {sum, sum of squares, count}, may be NULL): moments of the GLOBAL minibatch when it is sharded over ranks (NULL: the
+ * moments of these E transitions). */
 int mbo_ppo_prepare_minibatch(int E, size_t row_floats, const int64_t* sel, const float* states_all,
                               const int32_t* actions_all, const float* advs_all, const float* tdlamrets_all,
-                              const float* logp_old_all, int normalize_advs, float* states, int32_t* actions,
-                              float* advs, float* tdlamrets, float* logp_old, void* stream);
+                              const float* logp_old_all, int normalize_advs, const double* adv_stats, float* states,
+                              int32_t* actions, float* advs, float* tdlamrets, float* logp_old, void* stream);
+/* out[j] = {sum, sum of squares, count} (doubles) of advs_all[sel[bounds[j] .. bounds[j+1])] for the n_steps local
+ * minibatch shards of one epoch (bounds: device int32 [n_steps + 1]); the ranks sum the table with mbo_comm_allreduce. */
+int mbo_ppo_adv_stats(int n_steps, const int32_t* bounds, const int64_t* sel, const float* advs_all, double* out,
+                      void* stream);
 /* out4 = {loss_ppo, loss_value, loss_ent, loss} (ppo.py:158-168) from mbo_ppo_policy_grad's terms [E,4] and
  * mbo_ppo_value_grad's vterms [E] (NULL: no value net). */
 int mbo_ppo_loss_sums(int E, const float* terms, const float* vterms, float inv_n_global, float value_coeff,
@@ -280,6 +286,39 @@ int mbo_ppo_loss_sums(int E, const float* terms, const float* vterms, float inv_
 int mbo_adam_step(int n, float* const* p, const float* const* g, float* const* m, float* const* v,
                   const int64_t* sizes, int64_t* const* state, float lr, float beta1, float beta2, float eps,
                   void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Peer-memory exchange for the data-parallel PPO update (one process per GPU; the reference's learner is a single
+ * process -- ppo.py:170-172 `loss.backward(); optimizer.step()` -- so the flat gradient all-reduce is the only collective
+ * of the path).  An `mbo_comm` owns one cudaMalloc'ed region per rank, exported as a CUDA IPC handle; the
+ * ranks exchange the MBO_COMM_HANDLE_BYTES-byte handles on the host (e.g. torch.distributed.all_gather_object) and map
+ * each other's regions over NVLink / NVSwitch.  All calls below except create / export / connect / destroy / status
+ * only enqueue kernels (capturable in CUDA graphs); every rank must enqueue the same sequence of calls.  Sums are formed
+ * in rank order 0..world-1 on every rank: results are bit-identical across ranks.  Waits on peers are bounded (10 s): a
+ * time-out sets a sticky error bit (later waits return at once) that mbo_comm_status reports; nothing hangs. */
+typedef struct mbo_comm mbo_comm;
+#define MBO_COMM_HANDLE_BYTES 64
+#define MBO_COMM_MAX_RANKS 16
+#define MBO_COMM_F32 0
+#define MBO_COMM_F64 1
+/* slot_bytes: largest payload of one call (e.g. 4 x number of parameters).  Allocates 2 slots + 2.3 KB of flags. */
+int mbo_comm_create(int rank, int world, size_t slot_bytes, mbo_comm** out);
+int mbo_comm_export(mbo_comm* c, void* handle_out /* HOST, MBO_COMM_HANDLE_BYTES */);
+int mbo_comm_connect(mbo_comm* c, const void* handles /* HOST, world x MBO_COMM_HANDLE_BYTES, rank order */);
+void mbo_comm_destroy(mbo_comm* c);
+/* dst[i] = sum over ranks of src[i] (count elements of fp32 / fp64, device pointers; src == dst allowed). */
+int mbo_comm_allreduce(mbo_comm* c, int dtype, const void* src, void* dst, size_t count, void* stream);
+/* The optimiser step of ppo.py:170-172 under data parallelism as ONE kernel: all-reduce (sum) of the flat fp32
+ * gradient `grad` (the concatenation of the n tensors' gradients in the order of p / m / v / sizes / state, as written
+ * by mbo_ppo_policy_grad / mbo_ppo_value_grad into views of one buffer) pulled from every rank's slot over NVLink,
+ * consumed on the fly by the Adam update of mbo_adam_step (same arguments, same arithmetic).  grad_out (optional,
+ * device, count floats): the reduced gradient.  Weights stay replicated: every rank applies the identical update. */
+int mbo_comm_allreduce_adam(mbo_comm* c, const float* grad, float* grad_out, int n, float* const* p, float* const* m,
+                            float* const* v, const int64_t* sizes, int64_t* const* state, float lr, float beta1,
+                            float beta2, float eps, void* stream);
+/* Synchronises `stream`; *epoch_out = completed calls, *err_out = sticky error bits (bit 0: a peer wait timed out),
+ * cleared by the call. */
+int mbo_comm_status(mbo_comm* c, unsigned long long* epoch_out, unsigned int* err_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -61,12 +61,22 @@ SYMBOLS = [
     ("mbo_ppo_value_workspace_bytes", _sz, [_i, _i]),
     ("mbo_ppo_value_grad", _i, [_i, _sz, _i, _i, _i, _vp, C.POINTER(_vp), C.POINTER(_vp), _vp, C.c_float, C.POINTER(_vp),
                                 C.POINTER(_vp), _vp, _vp, _vp, _sz, _vp]),
-    ("mbo_ppo_prepare_minibatch", _i, [_i, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    ("mbo_ppo_prepare_minibatch", _i, [_i, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    ("mbo_ppo_adv_stats", _i, [_i, _vp, _vp, _vp, _vp, _vp]),
     ("mbo_ppo_loss_sums", _i, [_i, _vp, _vp, C.c_float, C.c_float, C.c_float, _vp, _vp]),
     ("mbo_adam_step", _i, [_i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_int64),
                            C.POINTER(_vp),
                            C.c_float, C.c_float, C.c_float, C.c_float, _vp]),
+    ("mbo_comm_create", _i, [_i, _i, _sz, C.POINTER(_vp)]),
+    ("mbo_comm_export", _i, [_vp, _vp]),
+    ("mbo_comm_connect", _i, [_vp, _vp]),
+    ("mbo_comm_destroy", None, [_vp]),
+    ("mbo_comm_allreduce", _i, [_vp, _i, _vp, _vp, _sz, _vp]),
+    ("mbo_comm_allreduce_adam", _i, [_vp, _vp, _vp, _i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp),
+                                     C.POINTER(C.c_int64), C.POINTER(_vp), C.c_float, C.c_float, C.c_float, C.c_float, _vp]),
+    ("mbo_comm_status", _i, [_vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_uint), _vp]),
 ]
+COMM_HANDLE_BYTES = 64
 
 
 def lib():

@@ -30,6 +30,7 @@
 // Also here: the value net (v_* kernels, fp32 CUDA cores), Adam, minibatch gather / advantage normalisation, loss sums.
 #include <stdlib.h>
 #include "common.cuh"
+#include "ppo_loss.cuh"
 #include "tmem_ldst.cuh"
 
 namespace mbo {
@@ -992,63 +993,6 @@ __global__ void __launch_bounds__(PG_THREADS, 1) upd_dgrad_persist_kernel(GemmAr
   }
 }
 
-// ---- loss terms and dlogits, one CTA per episode (policies.py:150-161, ppo.py:148-168) -----------------------------
-__device__ __forceinline__ double block_sum(double v, double* s_red) {
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  __syncthreads();
-  if (lane == 0) s_red[warp] = v;
-  __syncthreads();
-  double t = 0.0;
-  for (int i = 0; i < nw; ++i) t += s_red[i];      // same order in every thread
-  return t;
-}
-__global__ void __launch_bounds__(256) upd_loss_kernel(int M, const float* __restrict__ logits,
-                                                        const int32_t* __restrict__ actions, const float* __restrict__ advs,
-                                                        const float* __restrict__ logp_old, float eps, float ent_coeff,
-                                                        float inv_n, float* __restrict__ dl, float* __restrict__ terms) {
-  __shared__ double s_red[8];
-  __shared__ float s_max[8];
-  const int e = blockIdx.x, tid = threadIdx.x;
-  const float* l = logits + (size_t)e * M;
-  float mx = -INFINITY;
-  for (int i = tid; i < M; i += 256) mx = fmaxf(mx, l[i]);
-  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  if ((tid & 31) == 0) s_max[tid >> 5] = mx;
-  __syncthreads();
-  mx = s_max[0];
-  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, s_max[i]);
-  double se = 0.0;
-  for (int i = tid; i < M; i += 256) se += (double)expf(l[i] - mx);
-  se = block_sum(se, s_red);
-  const float lse = mx + (float)log(se);
-  double pe = 0.0;                                  // sum p log p
-  for (int i = tid; i < M; i += 256) { const float lp = l[i] - lse; pe += (double)(expf(lp) * lp); }
-  pe = block_sum(pe, s_red);
-  const float ent = (float)(-pe);
-  int act = actions[e];
-  act = act < 0 ? 0 : (act >= M ? M - 1 : act);
-  const float lpa = l[act] - lse;
-  const float adv = advs ? advs[e] : 0.f;
-  const float ratio = expf(lpa - (logp_old ? logp_old[e] : lpa));
-  const float clipped = fminf(fmaxf(ratio, 1.f - eps), 1.f + eps);
-  const float s1 = ratio * adv, s2 = clipped * adv;
-  // d(-min(s1, s2) / n) / d ratio: torch.min splits a tie evenly and clamp passes the gradient inside its range, so
-  // the unclipped and the tie case both give -adv / n; when the clipped branch is the smaller one the gradient is 0
-  const float g_lp = (s1 <= s2 ? -adv * inv_n : 0.f) * ratio;
-  const float g_ent = -ent_coeff * inv_n;
-  for (int i = tid; i < M; i += 256) {
-    const float lp = l[i] - lse, p = expf(lp);
-    dl[(size_t)e * M + i] = g_lp * ((i == act ? 1.f : 0.f) - p) - g_ent * p * (lp + ent);
-  }
-  if (tid == 0) {
-    terms[e * 4 + 0] = lpa;
-    terms[e * 4 + 1] = ent;
-    terms[e * 4 + 2] = -fminf(s1, s2) * inv_n;
-    terms[e * 4 + 3] = ratio;
-  }
-}
-
 // ---- dZ4 and the head's weight gradient -------------------------------------------------------------------------------
 __global__ void __launch_bounds__(THIN_THREADS) upd_dz4_kernel(int R, int H, const float* __restrict__ H4,
                                                                 const float* __restrict__ dl, const float* __restrict__ w4,
@@ -1696,16 +1640,21 @@ __global__ void __launch_bounds__(256) prep_kernel(int E, size_t row_floats, con
                                                     const float* __restrict__ states_all, const int32_t* __restrict__ actions_all,
                                                     const float* __restrict__ advs_all, const float* __restrict__ ret_all,
                                                     const float* __restrict__ lpo_all, int normalize,
+                                                    const double* __restrict__ adv_stats,
                                                     float* __restrict__ states, int32_t* __restrict__ actions,
                                                     float* __restrict__ advs, float* __restrict__ ret, float* __restrict__ lpo) {
   if (blockIdx.x == 0) {
     __shared__ double s_red[8];
-    double s = 0.0, s2 = 0.0;
-    for (int e = threadIdx.x; e < E; e += 256) { const double a = (double)advs_all[sel[e]]; s += a; s2 += a * a; }
-    s = block_sum(s, s_red);
-    s2 = block_sum(s2, s_red);
-    const double mean = s / E;
-    const double var = fmax(s2 / E - mean * mean, 0.0);
+    double s = 0.0, s2 = 0.0, cnt = (double)E;
+    if (adv_stats) {        // data-parallel update: {sum, sum of squares, count} over the GLOBAL minibatch (all ranks)
+      s = adv_stats[0]; s2 = adv_stats[1]; cnt = adv_stats[2];
+    } else {
+      for (int e = threadIdx.x; e < E; e += 256) { const double a = (double)advs_all[sel[e]]; s += a; s2 += a * a; }
+      s = block_sum(s, s_red);
+      s2 = block_sum(s2, s_red);
+    }
+    const double mean = s / cnt;
+    const double var = fmax(s2 / cnt - mean * mean, 0.0);
     const double sd = sqrt(var);
     const bool ok = normalize && sd > 0.0 && !isnan(sd);
     for (int e = threadIdx.x; e < E; e += 256) {
@@ -1729,6 +1678,19 @@ __global__ void __launch_bounds__(256) prep_kernel(int E, size_t row_floats, con
       for (size_t i = threadIdx.x; i < row_floats; i += 256) dst[i] = src[i];
     }
   }
+}
+
+// local {sum, sum of squares, count} of the advantages of every minibatch of an epoch (one CTA per minibatch): the
+// ranks all-reduce the [n_steps, 3] table once per epoch, prep_kernel then normalises with the global moments
+__global__ void __launch_bounds__(256) adv_stats_kernel(const int32_t* __restrict__ bounds, const long long* __restrict__ sel,
+                                                         const float* __restrict__ advs_all, double* __restrict__ out) {
+  __shared__ double s_red[8];
+  const int a = bounds[blockIdx.x], b = bounds[blockIdx.x + 1];
+  double s = 0.0, s2 = 0.0;
+  for (int e = a + threadIdx.x; e < b; e += 256) { const double x = (double)advs_all[sel[e]]; s += x; s2 += x * x; }
+  s = block_sum(s, s_red);
+  s2 = block_sum(s2, s_red);
+  if (threadIdx.x == 0) { out[blockIdx.x * 3] = s; out[blockIdx.x * 3 + 1] = s2; out[blockIdx.x * 3 + 2] = (double)(b - a); }
 }
 
 // out = {loss_ppo, loss_value, loss_ent, loss} of ppo.py:158-168 from the per-transition terms
@@ -1756,15 +1718,24 @@ __global__ void __launch_bounds__(256) loss_sums_kernel(int E, const float* __re
 
 extern "C" int mbo_ppo_prepare_minibatch(int E, size_t row_floats, const int64_t* sel, const float* states_all,
                                          const int32_t* actions_all, const float* advs_all, const float* tdlamrets_all,
-                                         const float* logp_old_all, int normalize_advs, float* states, int32_t* actions,
-                                         float* advs, float* tdlamrets, float* logp_old, void* stream) {
+                                         const float* logp_old_all, int normalize_advs, const double* adv_stats,
+                                         float* states, int32_t* actions, float* advs, float* tdlamrets, float* logp_old,
+                                         void* stream) {
   MBO_CHECK_ARG(E > 0 && row_floats > 0, "mbo_ppo_prepare_minibatch: E, row_floats must be > 0");
   MBO_CHECK_ARG(sel && states_all && actions_all && advs_all && tdlamrets_all && states && actions && advs && tdlamrets &&
                 logp_old, "mbo_ppo_prepare_minibatch: null pointer");
   const int nb = 1 + (E < 296 ? E : 296);
   mbo::upd::prep_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(E, row_floats, (const long long*)sel, states_all, actions_all,
-                                                              advs_all, tdlamrets_all, logp_old_all, normalize_advs, states,
-                                                              actions, advs, tdlamrets, logp_old);
+                                                              advs_all, tdlamrets_all, logp_old_all, normalize_advs, adv_stats,
+                                                              states, actions, advs, tdlamrets, logp_old);
+  MBO_LAUNCH_CHECK();
+  return MBO_OK;
+}
+
+extern "C" int mbo_ppo_adv_stats(int n_steps, const int32_t* bounds, const int64_t* sel, const float* advs_all, double* out,
+                                 void* stream) {
+  MBO_CHECK_ARG(n_steps > 0 && bounds && sel && advs_all && out, "mbo_ppo_adv_stats: bad arguments");
+  mbo::upd::adv_stats_kernel<<<n_steps, 256, 0, (cudaStream_t)stream>>>(bounds, (const long long*)sel, advs_all, out);
   MBO_LAUNCH_CHECK();
   return MBO_OK;
 }

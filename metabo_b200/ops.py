@@ -365,19 +365,98 @@ class PPOPolicyGrad:
         return v
 
 
-def ppo_prepare_minibatch(sel, flat, normalize, out):
+def ppo_prepare_minibatch(sel, flat, normalize, out, adv_stats=None):
     """Gathers the transitions `sel` (int64 device indices) of the flattened batch `flat` (dict: states [n,M,F] f32,
     actions [n] i32, advs / tdlamrets / logprobs_old [n] f32) into the preallocated minibatch tensors `out` and
-    normalises the advantages (ppo.py:141-144)."""
-    _chk(sel, torch.int64, "sel")
+    normalises the advantages (ppo.py:141-144); `adv_stats` (3 doubles on the device): moments of the GLOBAL minibatch
+    when it is sharded over ranks."""
+    _chk(sel, torch.int64, "sel"); _chk(adv_stats, torch.float64, "adv_stats")
     E = sel.shape[0]
     st = flat["states"]
     lpo = flat.get("logprobs_old")
     L.check(L.lib().mbo_ppo_prepare_minibatch(E, st.shape[1] * st.shape[2], _p(sel), _p(st), _p(flat["actions"]),
                                               _p(flat["advs"]), _p(flat["tdlamrets"]), _p(lpo), int(bool(normalize)),
-                                              _p(out["states"]), _p(out["actions"]), _p(out["advs"]), _p(out["tdlamrets"]),
-                                              _p(out["logprobs_old"]), _stream()), "mbo_ppo_prepare_minibatch")
+                                              _p(adv_stats), _p(out["states"]), _p(out["actions"]), _p(out["advs"]),
+                                              _p(out["tdlamrets"]), _p(out["logprobs_old"]), _stream()),
+            "mbo_ppo_prepare_minibatch")
     return out
+
+
+def ppo_adv_stats(bounds, sel, advs_all, out):
+    """out [n_steps, 3] f64 = {sum, sum of squares, count} of advs_all[sel[bounds[j]:bounds[j+1]]] (local shard of every
+    minibatch of an epoch)."""
+    _chk(bounds, torch.int32, "bounds"); _chk(sel, torch.int64, "sel"); _chk(advs_all, torch.float32, "advs_all")
+    _chk(out, torch.float64, "out")
+    n_steps = bounds.numel() - 1
+    assert out.numel() >= 3 * n_steps
+    L.check(L.lib().mbo_ppo_adv_stats(n_steps, _p(bounds), _p(sel), _p(advs_all), _p(out), _stream()), "mbo_ppo_adv_stats")
+    return out
+
+
+class Comm:
+    """Peer-memory exchange of the data-parallel PPO update (`mbo_comm`, csrc/comm.cu): one region per rank, mapped into
+    every process through CUDA IPC handles that travel over the torch.distributed process group on the host."""
+
+    def __init__(self, rank, world, slot_bytes, device=None):
+        self.rank, self.world, self.slot_bytes = int(rank), int(world), int(slot_bytes)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            L.check(L.lib().mbo_comm_create(self.rank, self.world, self.slot_bytes, C.byref(h)), "mbo_comm_create")
+        self.h = h
+
+    def export(self):
+        buf = C.create_string_buffer(L.COMM_HANDLE_BYTES)
+        L.check(L.lib().mbo_comm_export(self.h, buf), "mbo_comm_export")
+        return bytes(buf.raw)
+
+    def connect(self, handles):
+        assert len(handles) == self.world and all(len(x) == L.COMM_HANDLE_BYTES for x in handles)
+        blob = C.create_string_buffer(b"".join(handles), L.COMM_HANDLE_BYTES * self.world)
+        with torch.cuda.device(self.device):
+            L.check(L.lib().mbo_comm_connect(self.h, blob), "mbo_comm_connect")
+
+    @classmethod
+    def from_process_group(cls, slot_bytes, device=None, group=None):
+        """collective: every rank of the (initialised) process group calls this"""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        c = cls(rank, world, slot_bytes, device)
+        if world > 1:
+            handles = [None] * world
+            dist.all_gather_object(handles, c.export(), group=group)
+            c.connect(handles)
+            dist.barrier(group)
+        return c
+
+    def allreduce(self, src, dst=None):
+        """dst = sum over ranks of src (fp32 / fp64 contiguous CUDA tensors); in place when dst is None"""
+        dst = src if dst is None else dst
+        assert src.is_cuda and src.is_contiguous() and dst.is_contiguous() and src.dtype == dst.dtype
+        assert src.numel() == dst.numel()
+        dt = {torch.float32: 0, torch.float64: 1}[src.dtype]
+        L.check(L.lib().mbo_comm_allreduce(self.h, dt, _p(src), _p(dst), src.numel(), _stream()), "mbo_comm_allreduce")
+        return dst
+
+    def status(self):
+        ep, err = C.c_ulonglong(0), C.c_uint(0)
+        L.check(L.lib().mbo_comm_status(self.h, C.byref(ep), C.byref(err), _stream()), "mbo_comm_status")
+        return int(ep.value), int(err.value)
+
+    def check(self):
+        ep, err = self.status()
+        if err:
+            raise L.MboError("mbo_comm: a wait on a peer rank timed out (rank %d, %d completed calls): the ranks did not "
+                             "enqueue the same sequence of exchange calls" % (self.rank, ep))
+        return ep
+
+    def __del__(self):
+        try:
+            if self.h:
+                L.lib().mbo_comm_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
 
 
 def ppo_loss_sums(terms, vterms, n_global, value_coeff, ent_coeff, out):
@@ -419,6 +498,12 @@ class FusedAdam(torch.optim.Optimizer):
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        self.comm = None          # ops.Comm: the step all-reduces the flat gradient over the ranks inside the Adam kernel
+        self.flat_grad = None     # the ONE fp32 buffer all .grad tensors are views of (in parameter order)
+
+    def set_comm(self, comm, flat_grad):
+        """data-parallel mode: `flat_grad` is the concatenation of every parameter's gradient in param_groups order"""
+        self.comm, self.flat_grad = comm, flat_grad
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -439,6 +524,21 @@ class FusedAdam(torch.optim.Optimizer):
             arr = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])
             sizes = (C.c_int64 * n)(*[p.numel() for p in ps])
             b1, b2 = group["betas"]
+            if self.comm is not None and self.comm.world > 1:
+                off = 0
+                for p in ps:        # the gradients must tile the flat buffer in order (PPO._alloc_native_grads)
+                    assert p.grad.data_ptr() == self.flat_grad.data_ptr() + 4 * off, "gradients are not views of flat_grad"
+                    off += p.numel()
+                assert off == self.flat_grad.numel() and len(self.param_groups) == 1
+                L.check(L.lib().mbo_comm_allreduce_adam(self.comm.h, _p(self.flat_grad), None, n, arr([p.data for p in ps]),
+                                                        arr([self.state[p]["exp_avg"] for p in ps]),
+                                                        arr([self.state[p]["exp_avg_sq"] for p in ps]), sizes,
+                                                        arr([self.state[p]["_dev"] for p in ps]),
+                                                        float(group["lr"]), float(b1), float(b2), float(group["eps"]),
+                                                        _stream()), "mbo_comm_allreduce_adam")
+                for p in ps:
+                    p._mbo_version = getattr(p, "_mbo_version", 0) + 1
+                continue
             L.check(L.lib().mbo_adam_step(n, arr([p.data for p in ps]), arr([p.grad for p in ps]),
                                           arr([self.state[p]["exp_avg"] for p in ps]),
                                           arr([self.state[p]["exp_avg_sq"] for p in ps]), sizes,

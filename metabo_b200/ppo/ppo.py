@@ -72,6 +72,26 @@ def ppo_minibatch_loss(pi, states, actions, advs, tdlamrets, logprobs_old, param
     return loss, loss_ppo, loss_value, loss_ent
 
 
+def minibatch_bounds(n, minibatch_size):
+    """batchrecorder.py:326-330: consecutive minibatches, the remainder joins the last one"""
+    pos, out = 0, []
+    while pos < n:
+        cur = n - pos if pos + 2 * minibatch_size > n else minibatch_size
+        out.append((pos, pos + cur))
+        pos += cur
+    return out
+
+
+def shard_bounds(n_local, minibatch_size, rank, world):
+    """Data-parallel minibatches: every optimiser step works on a GLOBAL minibatch of the reference's size, of which
+    rank r holds the share [c_r(a), c_r(b)) of its own (locally shuffled) n_local transitions, c_r(x) = (x + r) // world.
+    By Hermite's identity the shares of all ranks add up to b - a for every step, and to n_local per rank over the
+    epoch, for ANY world size (60 = 8+7+8+7+... on 8 ranks).  Returns (local bounds, global minibatch sizes)."""
+    gb = minibatch_bounds(n_local * world, minibatch_size)
+    c = lambda x: (x + rank) // world
+    return [(c(a), c(b)) for a, b in gb], [b - a for a, b in gb]
+
+
 def allreduce_gradients(parameters, world):
     """one flat fp32 all-reduce (sum) per optimiser step (~0.97 MB for the 4x200 nets)"""
     if world == 1:
@@ -108,8 +128,10 @@ class PPO:
 
         # rollout lanes: workers are sharded contiguously over ranks, seeds keep their meaning
         nw, bs = self.params["n_workers"], self.params["batch_size"]
-        if nw % self.world or bs % self.world or self.params["minibatch_size"] % self.world:
-            raise ValueError("n_workers, batch_size and minibatch_size must be divisible by the number of ranks")
+        if nw % self.world or bs % self.world:
+            raise ValueError("n_workers and batch_size must be divisible by the number of ranks")
+        if self.params["minibatch_size"] < self.world:
+            raise ValueError("minibatch_size must be at least the number of ranks")
         lw = nw // self.world
         seeds = list(self.params["env_seeds"])[self.rank * lw:(self.rank + 1) * lw]
         self.batch_recorder = BatchRecorder(size=bs // self.world, env_id=self.params["env_id"], env_seeds=seeds,
@@ -123,8 +145,8 @@ class PPO:
                 dist.broadcast(p.data, src=0)
         # autograd GEMMs of the update: "highest" = fp32 (reference numerics), "high" = TF32 tensor cores
         torch.set_float32_matmul_precision(self.params.get("update_matmul_precision", "highest"))
-        self.use_update_graph = self.world == 1 and os.environ.get("MBO_NO_GRAPHS") is None and \
-            self.params.get("update_graph", True)
+        self.use_update_graph = os.environ.get("MBO_NO_GRAPHS") is None and self.params.get("update_graph", True)
+        self.comm = None        # ops.Comm (peer-memory gradient exchange), created with the gradient buffers when world > 1
         self._upd = None        # (static inputs, CUDAGraph, static outputs) of one captured optimiser step
         self._ep = None         # native backend: one captured EPOCH (all minibatch steps) over static copies of the batch
         self._ep_stale = True
@@ -134,6 +156,8 @@ class PPO:
         if backend == "native" and not self.native_update_supported(self.pi):
             backend = "autograd"          # e.g. the 2 x 20 GP-sample policy: too small for the tensor-core path
         self.update_backend = backend
+        if self.world > 1 and not self.dp_native() and self.params["minibatch_size"] % self.world:
+            raise ValueError("minibatch_size must be divisible by the number of ranks (NCCL exchange path)")
         if backend == "native":       # same update rule, one launch per step (mbo_adam_step)
             self.optimizer = ops.FusedAdam(self.pi.parameters(), lr=self.params["lr"])
         else:
@@ -211,6 +235,17 @@ class PPO:
         k = len(pi.policy_net.fc)
         self._pg_grads = ([w for w, _ in views[:k]], [b for _, b in views[:k]])
         self._vg_grads = ([w for w, _ in views[k:]], [b for _, b in views[k:]])
+        if self.world > 1 and self.dp_native():
+            # the ONE collective of the path: the flat gradient is pulled from every rank's slot over NVLink inside the
+            # Adam kernel (mbo_comm_allreduce_adam); collective call (every rank gets here in its first optimiser step)
+            self.comm = ops.Comm.from_process_group(4 * max(n, 1024), self.device)
+            self.optimizer.set_comm(self.comm, self._flat_grads)
+
+    def dp_native(self):
+        """data-parallel update entirely on the library's kernels (policy + value nets native, fused exchange)"""
+        pi = self.pi
+        return (self.update_backend == "native" and (not pi.use_value_network or self.native_value_supported(pi))
+                and self.params.get("dp_exchange", "peer") == "peer")
 
     def _policy_grad_op(self, E, M, Fs):
         pg = self._pg
@@ -229,14 +264,14 @@ class PPO:
                                 actions.to(torch.int32).contiguous())
         return lp
 
-    def _update_step_native(self, mb, prepared=False):
+    def _update_step_native(self, mb, prepared=False, n_global=None):
         """ppo.py:129-178 on the hand-written kernels: policy net (mbo_ppo_policy_grad), value net (mbo_ppo_value_grad),
         Adam (mbo_adam_step).  prepared=True: `mb` comes from mbo_ppo_prepare_minibatch (gathered, advantages already
         normalised, int32 actions) and the logged loss sums are one more kernel -- no torch op is left in the step."""
         states, actions, tdlamrets = mb["states"], mb["actions"], mb["tdlamrets"]
         advs = mb["advs"] if (prepared or self.params["loss_type"] == "GAElam") else mb["tdlamrets"]
         E, M, Fs = states.shape
-        n_global = E * self.world
+        n_global = E * self.world if n_global is None else n_global
         if self.params["normalize_advs"] and not prepared:
             advs = normalize_advantages(advs, self.world)
         pi = self.pi
@@ -267,8 +302,8 @@ class PPO:
                                  self.params["value_coeff"] / n_global, vW, vb)
             for l, gw, gb in zip(vfc, vW, vb):
                 l.weight.grad, l.bias.grad = gw, gb
-            if prepared and self.world == 1:
-                self.optimizer.step()
+            if prepared and (self.world == 1 or self.comm is not None):
+                self.optimizer.step()          # world > 1: gradient exchange + Adam in one kernel (FusedAdam.set_comm)
                 if self._loss4 is None:
                     self._loss4 = torch.zeros(4, device=self.device)
                 return ops.ppo_loss_sums(terms, vterms, n_global, self.params["value_coeff"], self.params["ent_coeff"],
@@ -282,7 +317,14 @@ class PPO:
             l_val = l_val.detach()
         else:
             l_val = torch.sum(tdlamrets ** 2) / n_global       # the reference's value head is the constant 0
-        if self.world > 1 and self._flat_grads is not None and pi.use_value_network and self.native_value_supported(pi):
+        if prepared and self.comm is not None:     # no value net: policy gradients only
+            self.optimizer.step()
+            if self._loss4 is None:
+                self._loss4 = torch.zeros(4, device=self.device)
+            return ops.ppo_loss_sums(terms, None, n_global, self.params["value_coeff"], self.params["ent_coeff"], self._loss4)
+        if self.comm is not None:
+            pass                                   # the exchange happens inside optimizer.step()
+        elif self.world > 1 and self._flat_grads is not None and pi.use_value_network and self.native_value_supported(pi):
             dist.all_reduce(self._flat_grads, op=dist.ReduceOp.SUM)      # every gradient is a view of this one buffer
         else:
             allreduce_gradients(list(self.pi.parameters()), self.world)
@@ -405,13 +447,85 @@ class PPO:
         ep["graph"].replay()
         return ep["sums"].clone(), len(ep["bounds"])
 
+    def _dp_epoch(self, order):
+        """One epoch of optimiser steps under data parallelism (world > 1, native kernels): every rank shuffles ITS
+        transitions (`order`), step j works on the global minibatch whose local share is perm[a_j:b_j] (shard_bounds),
+        the advantage moments of all steps are exchanged once per epoch, each step is
+            mbo_ppo_prepare_minibatch -> mbo_ppo_policy_grad -> mbo_ppo_value_grad -> mbo_comm_allreduce_adam -> mbo_ppo_loss_sums
+        and the logged loss sums are exchanged at the end -- kernels only, no NCCL call, so the whole epoch is ONE
+        captured CUDA graph per rank (eager on the first call, which allocates the optimiser state).  Every rank
+        enqueues the same sequence of exchange calls; the peer waits inside the kernels are bounded."""
+        br = self.batch_recorder
+        buf = br.buf
+        n = br.B * br.T
+        flat = {k: buf[k].reshape((n,) + tuple(buf[k].shape[2:])) for k in self._MB_KEYS}
+        sig = tuple((k, tuple(v.shape), v.dtype) for k, v in flat.items())
+        if self._ep is None or self._ep["sig"] != sig:
+            static = {k: v.clone().contiguous() for k, v in flat.items()}
+            assert static["actions"].dtype == torch.int32
+            perm = torch.zeros(n, dtype=torch.int64, device=self.device)
+            bounds, n_globals = shard_bounds(n, self.params["minibatch_size"], self.rank, self.world)
+            E_max = max(b - a for a, b in bounds)
+            self._policy_grad_op(E_max, *flat["states"].shape[1:])          # size the workspaces before any capture
+            if self.pi.use_value_network and (self._vg is None or self._vg.E < E_max):
+                self._vg = ops.PPOValueGrad(E_max, self.pi.value_net.arch_spec[0], self.device)
+            if self._pg_grads is None:
+                self._alloc_native_grads()                                   # collective: creates the comm
+            for a, b in bounds:
+                self._minibatch_buffers(b - a, static["states"])
+            if self._loss4 is None:
+                self._loss4 = torch.zeros(4, device=self.device)
+            src = dict(static)
+            if self.params["loss_type"] != "GAElam":
+                src["advs"] = static["tdlamrets"]
+            bounds_dev = torch.tensor([bounds[0][0]] + [b for _, b in bounds], dtype=torch.int32, device=self.device)
+            stats = torch.zeros((len(bounds), 3), dtype=torch.float64, device=self.device)
+            self._ep = dict(sig=sig, static=static, perm=perm, graph=None, sums=None, bounds=bounds, n_globals=n_globals,
+                            src=src, bounds_dev=bounds_dev, stats=stats, runs=0)
+            self._ep_stale = True
+        ep = self._ep
+        if self._ep_stale:
+            for k, v in flat.items():
+                ep["static"][k].copy_(v)
+            self._ep_stale = False
+        ep["perm"].copy_(torch.as_tensor(order, dtype=torch.int64), non_blocking=False)
+        norm = bool(self.params["normalize_advs"])
+
+        def body():
+            sums = torch.zeros(4, device=self.device)
+            if norm:        # global per-minibatch advantage moments (ppo.py:141-144), one exchange per epoch
+                ops.ppo_adv_stats(ep["bounds_dev"], ep["perm"], ep["src"]["advs"], ep["stats"])
+                self.comm.allreduce(ep["stats"])
+            for j, (a, b) in enumerate(ep["bounds"]):
+                mbuf = ops.ppo_prepare_minibatch(ep["perm"][a:b], ep["src"], norm, self._minibatch_buffers(b - a, ep["static"]["states"]),
+                                                 adv_stats=ep["stats"][j] if norm else None)
+                sums = sums + self._update_step_native(mbuf, prepared=True, n_global=ep["n_globals"][j])
+            self.comm.allreduce(sums)
+            return sums
+
+        use_graph = self.use_update_graph and self.params.get("epoch_graph", True)
+        if not use_graph or ep["runs"] == 0:
+            sums = body()
+        else:
+            if ep["graph"] is None:
+                torch.cuda.synchronize(self.device)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    ep["sums"] = body()
+                ep["graph"] = g
+            ep["graph"].replay()
+            sums = ep["sums"]
+        ep["runs"] += 1
+        return sums.clone(), len(ep["bounds"])
+
     def optimize_on_batch(self):
         now = time.time()
         self.iter_log_str += " OPTIMIZING...\n"
         self.old_pi.load_state_dict(self.pi.state_dict())
         self.old_pi.set_requires_grad(False)
         self.old_pi.kernel_handles()      # re-pack the frozen policy's kernel weights NOW: a replayed graph cannot do it
-        local_mb = self.params["minibatch_size"] // self.world
+        local_mb = -(-self.params["minibatch_size"] // self.world)       # largest local share of a minibatch
+        dp = self.world > 1 and self.dp_native()
         buf = self.batch_recorder.buf
         buf.pop("logprobs_old", None)
         self._ep_stale = True             # the epoch graph reads static copies of the batch: refresh them once per call
@@ -427,23 +541,29 @@ class PPO:
         for ep in range(self.params["n_epochs"]):
             sums = torch.zeros(4, device=self.device)
             n_minibatches = 0
-            if (self.update_backend == "native" and self.use_update_graph and self.stats["n_optsteps"] > 0
+            if dp:
+                sums, n_minibatches = self._dp_epoch(self.batch_recorder._order(True))       # sums are already global
+                self.stats["n_optsteps"] += n_minibatches
+            elif (self.update_backend == "native" and self.use_update_graph and self.world == 1 and self.stats["n_optsteps"] > 0
                     and self.params.get("epoch_graph", True)):
                 sums, n_minibatches = self._graphed_epoch(self.batch_recorder._order(True), local_mb)
                 self.stats["n_optsteps"] += n_minibatches
             for mb in (() if n_minibatches else self.batch_recorder.iterate_device(local_mb, shuffle=True)):
                 mb = {k: v for k, v in mb.items() if k in ("states", "actions", "tdlamrets", "advs", "logprobs_old")}
-                graphable = self.use_update_graph and mb["states"].shape[0] == local_mb and self.stats["n_optsteps"] > 0
+                graphable = (self.use_update_graph and self.world == 1 and mb["states"].shape[0] == local_mb
+                             and self.stats["n_optsteps"] > 0)
                 sums += self._graphed_update(mb) if graphable else self._update_step(mb)
                 self.stats["n_optsteps"] += 1
                 n_minibatches += 1
-            if self.world > 1:
+            if self.world > 1 and not dp:
                 dist.all_reduce(sums, op=dist.ReduceOp.SUM)
             avg = (sums / n_minibatches).tolist()
             self.iter_log_str += "   loss_ppo = {: .4g}, loss_value = {: .4g}, loss_ent = {: .4g}, loss = {: .4g}\n".format(*avg)
         torch.cuda.synchronize(self.device)
         if self._pg is not None:
             self._pg.check()              # sticky error word of the update kernels (bounded pipeline waits)
+        if self.comm is not None:
+            self.comm.check()             # a peer wait of the gradient exchange timed out
         t_optim = time.time() - now
         self.iter_log_str += "  Took {:.2f}s".format(t_optim)
         return t_optim

@@ -234,4 +234,43 @@ def test_ppo_update_abi_argument_checks_and_workspace_layout():
     rc = lib.mbo_adam_step(0, arr, arr, arr, arr, sizes, arr, 1e-3, 0.9, 0.999, 1e-8, null)
     assert rc == -1 and b"tensors per call" in lib.mbo_last_error()
     assert lib.mbo_ppo_loss_sums(0, null, null, 1.0, 1.0, 0.01, null, null) == -1
-    assert lib.mbo_ppo_prepare_minibatch(0, 10, null, null, null, null, null, null, 1, null, null, null, null, null, null) == -1
+    assert lib.mbo_ppo_prepare_minibatch(0, 10, null, null, null, null, null, null, 1, null, null, null, null, null, null, null) == -1
+    assert lib.mbo_ppo_adv_stats(0, null, null, null, null, null) == -1
+
+
+def test_comm_abi_argument_checks():
+    """mbo_comm_* (peer-memory gradient exchange): argument checks that fire before any CUDA call."""
+    import ctypes as C
+    from metabo_b200 import _lib as L
+    lib = L.lib()
+    h = C.c_void_p()
+    assert lib.mbo_comm_create(2, 2, 1024, C.byref(h)) == -1 and b"rank 2 / world 2" in lib.mbo_last_error()
+    assert lib.mbo_comm_create(0, 17, 1024, C.byref(h)) == -1
+    assert lib.mbo_comm_create(0, 1, 0, C.byref(h)) == -1 and b"slot_bytes" in lib.mbo_last_error()
+    assert lib.mbo_comm_export(None, None) == -1 and lib.mbo_comm_connect(None, None) == -1
+    assert lib.mbo_comm_allreduce(None, 0, None, None, 0, None) == -1
+    arr = (C.c_void_p * 1)()
+    sizes = (C.c_int64 * 1)(4)
+    assert lib.mbo_comm_allreduce_adam(None, None, None, 1, arr, arr, arr, sizes, arr, 1e-3, 0.9, 0.999, 1e-8, None) == -1
+    assert lib.mbo_comm_status(None, None, None, None) == -1
+    lib.mbo_comm_destroy(None)                      # no-op
+
+
+def test_shard_bounds_partition_every_minibatch_exactly():
+    """Data-parallel minibatches (ppo.py:127-178 sharded over ranks): for every world size the local shares of a step
+    add up to the reference's global minibatch (batchrecorder.py:326-330 incl. the merged remainder) and every rank
+    consumes exactly its n_local transitions per epoch."""
+    from metabo_b200.ppo.ppo import minibatch_bounds, shard_bounds
+    assert minibatch_bounds(1200, 60) == [(60 * i, 60 * (i + 1)) for i in range(20)]
+    assert minibatch_bounds(130, 60) == [(0, 60), (60, 130)]                 # remainder joins the last minibatch
+    for world in (1, 2, 3, 4, 8):
+        for n_local, mb in ((150, 60), (1200 // world if 1200 % world == 0 else 120, 60), (30720, 60), (130, 64), (96, 8)):
+            per_rank = [shard_bounds(n_local, mb, r, world) for r in range(world)]
+            gb = minibatch_bounds(n_local * world, mb)
+            for r, (loc, ng) in enumerate(per_rank):
+                assert ng == [b - a for a, b in gb]
+                assert loc[0][0] == 0 and loc[-1][1] == n_local
+                assert all(loc[i][1] == loc[i + 1][0] for i in range(len(loc) - 1))
+                assert all(b - a >= mb // world for a, b in loc) and all(b - a <= -(-max(ng) // world) for a, b in loc)
+            for j, (a, b) in enumerate(gb):
+                assert sum(per_rank[r][0][j][1] - per_rank[r][0][j][0] for r in range(world)) == b - a

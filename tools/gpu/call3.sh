@@ -1,0 +1,6 @@
+#!/bin/bash
+set -x
+O=gpurun_out/r2c3; mkdir -p $O
+timeout 900 python -m pytest tests -m gpu -q > $O/tests.log 2>&1; echo "tests rc=$?" >> $O/tests.log
+timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-modes > $O/bench.json 2> $O/bench.err; echo "bench rc=$?" >> $O/bench.err
+grep -n "^FAILED\|passed\|failed" $O/tests.log | tail; tail -3 $O/bench.err
