@@ -287,6 +287,23 @@ int mbo_adam_step(int n, float* const* p, const float* const* g, float* const* m
                   const int64_t* sizes, int64_t* const* state, float lr, float beta1, float beta2, float eps,
                   void* stream);
 
+/* PPO optimiser step for every network shape the tensor-core path (mbo_ppo_policy_grad / mbo_ppo_value_grad) does not
+ * cover: any MLP of mlp.py:25-61 with n_layers <= 8 linear layers of width <= 512, ReLU or tanh (policies.py:69-74),
+ * d_out = 1 -- e.g. train_metabo_gps.py:62-94's 4 -> 20 -> 20 -> 1 policy and 2 -> 20 -> 20 -> 1 value net -- in fp32 on
+ * CUDA cores (csrc/ppo_update_simt.cu).  widths: HOST array of n_layers + 1 ints {inputs, hidden..., 1}; W / b / dW /
+ * db: HOST arrays of n_layers device pointers in torch layouts.  Same semantics, terms and scaling as the calls
+ * above (dW == NULL: forward only).  Workspace: mbo_ppo_simt_workspace_bytes(rows = E * M or E, n_layers, widths, E). */
+size_t mbo_ppo_simt_workspace_bytes(long long rows, int n_layers, const int32_t* widths, int E);
+int mbo_ppo_policy_grad_simt(int E, int M, int F_state, int n_layers, const int32_t* widths, const int32_t* feat_col,
+                             int act, const float* states, const float* const* W, const float* const* b,
+                             const int32_t* actions, const float* advs, const float* logp_old, float epsilon,
+                             float ent_coeff, float inv_n_global, float* const* dW, float* const* db, float* terms,
+                             void* workspace, size_t workspace_bytes, void* stream);
+int mbo_ppo_value_grad_simt(int E, size_t state_stride, int t_col, int T_col, int n_layers, const int32_t* widths,
+                            int act, const float* states, const float* const* W, const float* const* b,
+                            const float* tdlamrets, float coeff, float* const* dW, float* const* db, float* values,
+                            float* vterms, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------------
  * Peer-memory exchange for the data-parallel PPO update (one process per GPU; the reference's learner is a single
  * process -- ppo.py:170-172 `loss.backward(); optimizer.step()` -- so the flat gradient all-reduce is the only collective

@@ -67,6 +67,12 @@ SYMBOLS = [
     ("mbo_adam_step", _i, [_i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_int64),
                            C.POINTER(_vp),
                            C.c_float, C.c_float, C.c_float, C.c_float, _vp]),
+    ("mbo_ppo_simt_workspace_bytes", _sz, [C.c_longlong, _i, C.POINTER(C.c_int32), _i]),
+    ("mbo_ppo_policy_grad_simt", _i, [_i, _i, _i, _i, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _i, _vp, C.POINTER(_vp),
+                                      C.POINTER(_vp), _vp, _vp, _vp, C.c_float, C.c_float, C.c_float, C.POINTER(_vp),
+                                      C.POINTER(_vp), _vp, _vp, _sz, _vp]),
+    ("mbo_ppo_value_grad_simt", _i, [_i, _sz, _i, _i, _i, C.POINTER(C.c_int32), _i, _vp, C.POINTER(_vp), C.POINTER(_vp), _vp,
+                                     C.c_float, C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _vp, _sz, _vp]),
     ("mbo_comm_create", _i, [_i, _i, _sz, C.POINTER(_vp)]),
     ("mbo_comm_export", _i, [_vp, _vp]),
     ("mbo_comm_connect", _i, [_vp, _vp]),

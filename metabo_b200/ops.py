@@ -365,6 +365,104 @@ class PPOPolicyGrad:
         return v
 
 
+class PPOPolicyGradSimt:
+    """`mbo_ppo_policy_grad_simt`: the same call as PPOPolicyGrad for any MLP shape / activation (fp32 CUDA cores)."""
+
+    def __init__(self, E, M, F_state, cols, widths, act, device):
+        self.E, self.M, self.F_state, self.cols = int(E), int(M), int(F_state), list(cols)
+        self.widths, self.act = [int(w) for w in widths], act
+        assert self.widths[0] == len(self.cols) and self.widths[-1] == 1
+        self.L = len(self.widths) - 1
+        self._w = (C.c_int32 * (self.L + 1))(*self.widths)
+        self._cols = (C.c_int32 * len(self.cols))(*self.cols)
+        self.nbytes = int(L.lib().mbo_ppo_simt_workspace_bytes(self.E * self.M, self.L, self._w, self.E))
+        if self.nbytes == 0:
+            raise L.MboError("mbo_ppo_policy_grad_simt does not support this network: %s" % (self.widths,))
+        self.ws = torch.zeros(self.nbytes // 4 + 64, dtype=torch.int32, device=device)
+        self.terms = torch.empty((self.E, 4), dtype=torch.float32, device=device)
+
+    def _call(self, states, weights, biases, actions, advs, logp_old, epsilon, ent_coeff, inv_n, dW, db):
+        _chk(states, torch.float32, "states"); _chk(actions, torch.int32, "actions")
+        _chk(advs, torch.float32, "advs"); _chk(logp_old, torch.float32, "logp_old")
+        E = states.shape[0]
+        assert E <= self.E and tuple(states.shape[1:]) == (self.M, self.F_state), states.shape
+        assert len(weights) == len(biases) == self.L
+        for t in list(weights) + list(biases) + list(dW or []) + list(db or []):
+            _chk(t, torch.float32, "parameter / gradient")
+        arr = lambda ts: None if ts is None else (C.c_void_p * self.L)(*[t.data_ptr() for t in ts])
+        L.check(L.lib().mbo_ppo_policy_grad_simt(E, self.M, self.F_state, self.L, self._w, self._cols, L.ACT[self.act],
+                                                 _p(states), arr(weights), arr(biases), _p(actions), _p(advs), _p(logp_old),
+                                                 float(epsilon), float(ent_coeff), float(inv_n), arr(dW), arr(db),
+                                                 _p(self.terms), _p(self.ws), self.nbytes, _stream()),
+                "mbo_ppo_policy_grad_simt")
+        return self.terms[:E]
+
+    def __call__(self, states, weights, biases, actions, advs, logp_old, epsilon, ent_coeff, n_global, dW, db):
+        assert len(dW) == len(db) == self.L
+        return self._call(states, weights, biases, actions, advs, logp_old, epsilon, ent_coeff, 1.0 / float(n_global), dW, db)
+
+    def logp_entropy(self, states, weights, biases, actions):
+        t = self._call(states, weights, biases, actions, None, None, 0.0, 0.0, 1.0, None, None)
+        return t[:, 0].clone(), t[:, 1].clone()
+
+    def check(self):
+        pass                        # no asynchronous pipeline in the CUDA-core kernels: nothing can time out
+
+
+class PPOValueGradSimt:
+    """`mbo_ppo_value_grad_simt`: value-net forward + backward for any MLP shape / activation (fp32 CUDA cores)."""
+
+    def __init__(self, E, widths, act, device):
+        self.E, self.widths, self.act = int(E), [int(w) for w in widths], act
+        assert self.widths[0] == 2 and self.widths[-1] == 1
+        self.L = len(self.widths) - 1
+        self._w = (C.c_int32 * (self.L + 1))(*self.widths)
+        self.nbytes = int(L.lib().mbo_ppo_simt_workspace_bytes(self.E, self.L, self._w, self.E))
+        if self.nbytes == 0:
+            raise L.MboError("mbo_ppo_value_grad_simt does not support this network: %s" % (self.widths,))
+        self.ws = torch.zeros(self.nbytes // 4 + 64, dtype=torch.int32, device=device)
+        self.values = torch.empty(self.E, dtype=torch.float32, device=device)
+        self.vterms = torch.empty(self.E, dtype=torch.float32, device=device)
+
+    def __call__(self, states, t_col, T_col, weights, biases, tdlamrets, coeff, dW, db):
+        _chk(states, torch.float32, "states"); _chk(tdlamrets, torch.float32, "tdlamrets")
+        E, M, F = states.shape
+        assert E <= self.E and len(weights) == len(biases) == len(dW) == len(db) == self.L
+        for t in list(weights) + list(biases) + list(dW) + list(db):
+            _chk(t, torch.float32, "parameter / gradient")
+        arr = lambda ts: (C.c_void_p * self.L)(*[t.data_ptr() for t in ts])
+        L.check(L.lib().mbo_ppo_value_grad_simt(E, M * F, int(t_col) % F, int(T_col) % F, self.L, self._w, L.ACT[self.act],
+                                                _p(states), arr(weights), arr(biases), _p(tdlamrets), float(coeff), arr(dW),
+                                                arr(db), _p(self.values), _p(self.vterms), _p(self.ws), self.nbytes, _stream()),
+                "mbo_ppo_value_grad_simt")
+        return self.values[:E], self.vterms[:E]
+
+
+def tensor_core_policy_update_ok(widths, act):
+    """shape served by the tcgen05 update kernels (mbo_ppo_policy_grad): F -> H -> H -> H -> H -> 1 ReLU, 8 <= H <= 207, F <= 8"""
+    w = list(widths)
+    return act == "relu" and len(w) == 6 and len(set(w[1:5])) == 1 and 8 <= w[1] <= 207 and 1 <= w[0] <= 8 and w[5] == 1
+
+
+def tensor_value_update_ok(widths, act):
+    w = list(widths)
+    return act == "relu" and len(w) == 6 and len(set(w[1:5])) == 1 and 1 <= w[1] <= 256 and w[0] == 2 and w[5] == 1
+
+
+def make_policy_grad(E, M, F_state, cols, widths, act, device):
+    """the library's kernel set for this policy-net shape: tcgen05 (3xTF32 forward / TF32 backward) for the shipped
+    4 x H ReLU nets, fp32 CUDA cores for every other MLP -- both behind the same call"""
+    if tensor_core_policy_update_ok(widths, act):
+        return PPOPolicyGrad(E, M, F_state, cols, widths[1], device)
+    return PPOPolicyGradSimt(E, M, F_state, cols, widths, act, device)
+
+
+def make_value_grad(E, widths, act, device):
+    if tensor_value_update_ok(widths, act):
+        return PPOValueGrad(E, widths[1], device)
+    return PPOValueGradSimt(E, widths, act, device)
+
+
 def ppo_prepare_minibatch(sel, flat, normalize, out, adv_stats=None):
     """Gathers the transitions `sel` (int64 device indices) of the flattened batch `flat` (dict: states [n,M,F] f32,
     actions [n] i32, advs / tdlamrets / logprobs_old [n] f32) into the preallocated minibatch tensors `out` and

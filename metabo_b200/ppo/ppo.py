@@ -10,11 +10,12 @@ every minibatch are sharded across ranks and the policy update all-reduces
 
 and every rank applies the identical Adam step (weights stay replicated, no broadcast).
 
-Update backends (`params["update_backend"]`): "native" (default when the policy net is the shipped
-F -> H -> H -> H -> H -> 1 ReLU shape) computes the policy-net forward + backward of every optimiser step
-with the hand-written tcgen05 kernels behind `mbo_ppo_policy_grad` (csrc/ppo_update.cu), the small value net
-(2 inputs x minibatch rows) with `mbo_ppo_value_grad` (fp32 CUDA cores) and Adam with `mbo_adam_step`.
-"autograd" is the all-torch fp32 path.
+The optimiser step runs entirely on the library's kernels, for every network NeuralAF can build: the shipped
+F -> H -> H -> H -> H -> 1 ReLU policies on the tcgen05 kernels behind `mbo_ppo_policy_grad` (csrc/ppo_update.cu), every
+other shape / tanh (e.g. train_metabo_gps.py's 4 -> 20 -> 20 -> 1) on the fp32 CUDA-core kernels of
+`mbo_ppo_policy_grad_simt` (csrc/ppo_update_simt.cu), value nets likewise (`mbo_ppo_value_grad[_simt]`), Adam with
+`mbo_adam_step` / `mbo_comm_allreduce_adam`.  There is no torch-autograd update path in the product (tests keep one as
+the comparison implementation, tests/autograd_ppo.py).
 """
 import collections
 import copy
@@ -143,25 +144,18 @@ class PPO:
         if self.world > 1:   # identical initial weights on every rank
             for p in self.pi.parameters():
                 dist.broadcast(p.data, src=0)
-        # autograd GEMMs of the update: "highest" = fp32 (reference numerics), "high" = TF32 tensor cores
-        torch.set_float32_matmul_precision(self.params.get("update_matmul_precision", "highest"))
         self.use_update_graph = os.environ.get("MBO_NO_GRAPHS") is None and self.params.get("update_graph", True)
         self.comm = None        # ops.Comm (peer-memory gradient exchange), created with the gradient buffers when world > 1
         self._upd = None        # (static inputs, CUDAGraph, static outputs) of one captured optimiser step
         self._ep = None         # native backend: one captured EPOCH (all minibatch steps) over static copies of the batch
         self._ep_stale = True
         backend = self.params.get("update_backend", "native")
-        if backend not in ("native", "autograd"):
-            raise ValueError("update_backend must be 'native' or 'autograd'")
-        if backend == "native" and not self.native_update_supported(self.pi):
-            backend = "autograd"          # e.g. the 2 x 20 GP-sample policy: too small for the tensor-core path
+        if backend != "native":
+            raise ValueError("update_backend must be 'native': the optimiser step runs on the library's kernels only")
         self.update_backend = backend
         if self.world > 1 and not self.dp_native() and self.params["minibatch_size"] % self.world:
             raise ValueError("minibatch_size must be divisible by the number of ranks (NCCL exchange path)")
-        if backend == "native":       # same update rule, one launch per step (mbo_adam_step)
-            self.optimizer = ops.FusedAdam(self.pi.parameters(), lr=self.params["lr"])
-        else:
-            self.optimizer = torch.optim.Adam(self.pi.parameters(), lr=self.params["lr"], capturable=True)
+        self.optimizer = self._make_optimizer()
         self._pg = None         # ops.PPOPolicyGrad for the current minibatch shape
         self._pg_grads = None   # persistent gradient buffers of the policy net (written by the kernels)
         self._vg = None         # ops.PPOValueGrad
@@ -209,16 +203,17 @@ class PPO:
         if not self.verbose:
             print(s)
 
-    @staticmethod
-    def native_update_supported(pi):
-        a = pi.policy_net.arch_spec
-        return (pi.activation == "relu" and len(a) == 4 and len(set(a)) == 1 and 8 <= a[0] <= 207
-                and 1 <= pi.N_features_policy <= 8)
+    def _make_optimizer(self):
+        """torch.optim.Adam(lr) semantics (ppo.py:93), one launch per step (mbo_adam_step)"""
+        return ops.FusedAdam(self.pi.parameters(), lr=self.params["lr"])
 
     @staticmethod
-    def native_value_supported(pi):
-        a = pi.value_net.arch_spec
-        return pi.activation == "relu" and len(a) == 4 and len(set(a)) == 1 and 1 <= a[0] <= 256
+    def policy_widths(pi):
+        return [pi.N_features_policy] + list(pi.policy_net.arch_spec) + [1]
+
+    @staticmethod
+    def value_widths(pi):
+        return [2] + list(pi.value_net.arch_spec) + [1]
 
     def _alloc_native_grads(self):
         """Persistent gradient buffers of the native backend, all views of ONE flat fp32 tensor: the kernels write into
@@ -242,16 +237,22 @@ class PPO:
             self.optimizer.set_comm(self.comm, self._flat_grads)
 
     def dp_native(self):
-        """data-parallel update entirely on the library's kernels (policy + value nets native, fused exchange)"""
-        pi = self.pi
-        return (self.update_backend == "native" and (not pi.use_value_network or self.native_value_supported(pi))
-                and self.params.get("dp_exchange", "peer") == "peer")
+        """gradient exchange inside the Adam kernel over NVLink peer memory (default) instead of an eager NCCL call"""
+        return self.params.get("dp_exchange", "peer") == "peer"
+
+    def _value_grad_op(self, E):
+        if self._vg is None or self._vg.E < E:
+            assert not torch.cuda.is_current_stream_capturing(), "value-net workspace must be sized before a capture"
+            pi = self.pi
+            self._vg = ops.make_value_grad(E, self.value_widths(pi), pi.activation, self.device)
+            self._upd = self._ep = None      # captured graphs hold the old workspace's pointers
+        return self._vg
 
     def _policy_grad_op(self, E, M, Fs):
         pg = self._pg
         if pg is None or pg.E < E or (pg.M, pg.F_state) != (M, Fs):
             pi = self.pi
-            self._pg = ops.PPOPolicyGrad(E, M, Fs, pi.policy_columns(), pi.policy_net.arch_spec[0], self.device)
+            self._pg = ops.make_policy_grad(E, M, Fs, pi.policy_columns(), self.policy_widths(pi), pi.activation, self.device)
             self._upd = self._ep = None      # captured graphs hold the old workspace's pointers
         return self._pg
 
@@ -290,44 +291,28 @@ class PPO:
                          n_global, dW, db)
         for l, gw, gb in zip(fcs, dW, db):
             l.weight.grad, l.bias.grad = gw, gb
-        if pi.use_value_network and self.native_value_supported(pi):
+        if pi.use_value_network:
             vfc = list(pi.value_net.fc)
-            if self._vg is None or self._vg.E < E:
-                assert not torch.cuda.is_current_stream_capturing(), "value-net workspace must be sized before a capture"
-                self._vg = ops.PPOValueGrad(E, pi.value_net.arch_spec[0], states.device)
-                self._upd = self._ep = None  # captured graphs hold the old workspace's pointers
+            self._value_grad_op(E)
             vW, vb = self._vg_grads
             _, vterms = self._vg(states.contiguous(), pi.t_idx, pi.T_idx, [l.weight.data for l in vfc],
                                  [l.bias.data for l in vfc], tdlamrets.to(torch.float32).contiguous(),
                                  self.params["value_coeff"] / n_global, vW, vb)
             for l, gw, gb in zip(vfc, vW, vb):
                 l.weight.grad, l.bias.grad = gw, gb
-            if prepared and (self.world == 1 or self.comm is not None):
-                self.optimizer.step()          # world > 1: gradient exchange + Adam in one kernel (FusedAdam.set_comm)
-                if self._loss4 is None:
-                    self._loss4 = torch.zeros(4, device=self.device)
-                return ops.ppo_loss_sums(terms, vterms, n_global, self.params["value_coeff"], self.params["ent_coeff"],
-                                         self._loss4)
-            l_val = vterms.sum() / n_global
-        elif pi.use_value_network:
-            tT = torch.stack([states[:, 0, pi.t_idx], states[:, 0, pi.T_idx]], dim=1)
-            vpreds = pi.value_net.forward(tT).squeeze(1)
-            l_val = torch.sum((vpreds - tdlamrets) ** 2) / n_global
-            (self.params["value_coeff"] * l_val).backward()
-            l_val = l_val.detach()
         else:
-            l_val = torch.sum(tdlamrets ** 2) / n_global       # the reference's value head is the constant 0
-        if prepared and self.comm is not None:     # no value net: policy gradients only
-            self.optimizer.step()
+            vterms = tdlamrets.to(torch.float32) ** 2          # the reference's value head is then the constant 0
+        if prepared and (self.world == 1 or self.comm is not None):
+            self.optimizer.step()              # world > 1: gradient exchange + Adam in one kernel (FusedAdam.set_comm)
             if self._loss4 is None:
                 self._loss4 = torch.zeros(4, device=self.device)
-            return ops.ppo_loss_sums(terms, None, n_global, self.params["value_coeff"], self.params["ent_coeff"], self._loss4)
+            return ops.ppo_loss_sums(terms, vterms.contiguous(), n_global, self.params["value_coeff"], self.params["ent_coeff"],
+                                     self._loss4)
+        l_val = vterms.sum() / n_global
         if self.comm is not None:
             pass                                   # the exchange happens inside optimizer.step()
-        elif self.world > 1 and self._flat_grads is not None and pi.use_value_network and self.native_value_supported(pi):
+        elif self.world > 1:
             dist.all_reduce(self._flat_grads, op=dist.ReduceOp.SUM)      # every gradient is a view of this one buffer
-        else:
-            allreduce_gradients(list(self.pi.parameters()), self.world)
         self.optimizer.step()
         l_ppo = terms[:, 2].sum()
         l_ent = -terms[:, 1].sum() / n_global
@@ -336,26 +321,11 @@ class PPO:
 
     def _update_step(self, mb):
         """one optimiser step on the (local shard of a) minibatch `mb` (dict of device tensors), ppo.py:129-178"""
-        if self.update_backend == "native":
-            return self._update_step_native(mb)
-        states, actions, tdlamrets = mb["states"], mb["actions"], mb["tdlamrets"]
-        advs = mb["advs"] if self.params["loss_type"] == "GAElam" else mb["tdlamrets"]
-        n_global = states.shape[0] * self.world
-        if self.params["normalize_advs"]:
-            advs = normalize_advantages(advs, self.world)
-        with torch.no_grad():
-            _, logprobs_old, _ = self.old_pi.predict_vals_logps_ents(states=states, actions=actions)
-        loss, l_ppo, l_val, l_ent = ppo_minibatch_loss(self.pi, states, actions, advs, tdlamrets, logprobs_old,
-                                                       self.params, n_global)
-        self.optimizer.zero_grad(set_to_none=True)
-        loss.backward()
-        allreduce_gradients(list(self.pi.parameters()), self.world)
-        self.optimizer.step()
-        return torch.stack([l_ppo, l_val, l_ent, loss]).detach()
+        return self._update_step_native(mb)
 
     def _graphed_update(self, mb):
-        """The optimiser step is ~100 small kernels (autograd MLP on 60 x 966 rows, Categorical terms, Adam): it is
-        launch-bound, so it is captured once in a CUDA graph (static input buffers) and replayed per minibatch."""
+        """One optimiser step (~35 small kernels) captured once in a CUDA graph (static input buffers) and replayed per
+        minibatch (`epoch_graph=False`; the default captures a whole epoch, `_graphed_epoch`)."""
         n = mb["states"].shape[0]
         if self._upd is None or self._upd[0]["states"].shape != mb["states"].shape:
             static = {k: torch.empty_like(v) for k, v in mb.items() if v is not None}
@@ -413,8 +383,8 @@ class PPO:
             bounds = br._minibatch_bounds(local_mb)
             E_max = max(b - a for a, b in bounds)
             self._policy_grad_op(E_max, *flat["states"].shape[1:])          # size the workspaces before the capture
-            if self.pi.use_value_network and self.native_value_supported(self.pi) and (self._vg is None or self._vg.E < E_max):
-                self._vg = ops.PPOValueGrad(E_max, self.pi.value_net.arch_spec[0], self.device)
+            if self.pi.use_value_network:
+                self._value_grad_op(E_max)
             src = dict(static)
             if self.params["loss_type"] != "GAElam":
                 src["advs"] = static["tdlamrets"]
@@ -467,8 +437,8 @@ class PPO:
             bounds, n_globals = shard_bounds(n, self.params["minibatch_size"], self.rank, self.world)
             E_max = max(b - a for a, b in bounds)
             self._policy_grad_op(E_max, *flat["states"].shape[1:])          # size the workspaces before any capture
-            if self.pi.use_value_network and (self._vg is None or self._vg.E < E_max):
-                self._vg = ops.PPOValueGrad(E_max, self.pi.value_net.arch_spec[0], self.device)
+            if self.pi.use_value_network:
+                self._value_grad_op(E_max)
             if self._pg_grads is None:
                 self._alloc_native_grads()                                   # collective: creates the comm
             for a, b in bounds:
@@ -518,6 +488,16 @@ class PPO:
         ep["runs"] += 1
         return sums.clone(), len(ep["bounds"])
 
+    def _batch_old_logprobs(self, buf, chunk):
+        """theta_old is frozen for the whole optimize_on_batch call: its log-probs (recomputed per minibatch in
+        ppo.py:146-147) are computed once per transition here and travel with the minibatches"""
+        B, T = buf["actions"].shape[:2]
+        st = buf["states"].reshape((B * T,) + tuple(buf["states"].shape[2:]))
+        ac = buf["actions"].reshape(B * T)
+        with torch.no_grad():
+            lp = [self._old_logprobs(st[i:i + chunk], ac[i:i + chunk]) for i in range(0, B * T, chunk)]
+        buf["logprobs_old"] = torch.cat(lp).reshape(B, T)
+
     def optimize_on_batch(self):
         now = time.time()
         self.iter_log_str += " OPTIMIZING...\n"
@@ -529,22 +509,14 @@ class PPO:
         buf = self.batch_recorder.buf
         buf.pop("logprobs_old", None)
         self._ep_stale = True             # the epoch graph reads static copies of the batch: refresh them once per call
-        if self.update_backend == "native":
-            # theta_old is frozen for the whole call: its log-probs (recomputed per minibatch in ppo.py:146-147) are
-            # computed once per transition here and travel with the minibatches
-            B, T = buf["actions"].shape[:2]
-            st = buf["states"].reshape((B * T,) + tuple(buf["states"].shape[2:]))
-            ac = buf["actions"].reshape(B * T)
-            with torch.no_grad():
-                lp = [self._old_logprobs(st[i:i + local_mb], ac[i:i + local_mb]) for i in range(0, B * T, local_mb)]
-            buf["logprobs_old"] = torch.cat(lp).reshape(B, T)
+        self._batch_old_logprobs(buf, local_mb)
         for ep in range(self.params["n_epochs"]):
             sums = torch.zeros(4, device=self.device)
             n_minibatches = 0
             if dp:
                 sums, n_minibatches = self._dp_epoch(self.batch_recorder._order(True))       # sums are already global
                 self.stats["n_optsteps"] += n_minibatches
-            elif (self.update_backend == "native" and self.use_update_graph and self.world == 1 and self.stats["n_optsteps"] > 0
+            elif (self.use_update_graph and self.world == 1 and self.stats["n_optsteps"] > 0
                     and self.params.get("epoch_graph", True)):
                 sums, n_minibatches = self._graphed_epoch(self.batch_recorder._order(True), local_mb)
                 self.stats["n_optsteps"] += n_minibatches

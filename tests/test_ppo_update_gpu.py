@@ -162,6 +162,7 @@ def test_ppo_native_update_follows_autograd_update(tmp_path):
     from metabo_b200 import gym_compat as gym
     from metabo_b200.policies.policies import NeuralAF
     from metabo_b200.ppo.ppo import PPO
+    from autograd_ppo import AutogradPPO
     from test_dropin_gpu import BRA_SPEC
     spec = dict(BRA_SPEC, T=5, N_MS=100, N_LS=50, k=3, reward_transformation="neg_log10", env_id="MetaBO-NATIVE-v0",
                 f_opts={"bound_translation": 0.1, "bound_scaling": 0.1, "M": 50})
@@ -171,10 +172,10 @@ def test_ppo_native_update_follows_autograd_update(tmp_path):
         params = {"batch_size": 80, "max_steps": 80, "minibatch_size": 20, "n_epochs": 2, "lr": 1e-4, "epsilon": 0.15,
                   "value_coeff": 1.0, "ent_coeff": 0.01, "gamma": 0.98, "lambda": 0.98, "loss_type": "GAElam",
                   "normalize_advs": True, "n_workers": 4, "env_id": spec["env_id"], "seed": 0, "env_seeds": [0, 1, 2, 3],
-                  "update_backend": backend,
                   "policy_options": {"activations": "relu", "arch_spec": [200] * 4, "use_value_network": True, "t_idx": -2,
                                      "T_idx": -1, "arch_spec_value": [200] * 4}}
-        ppo = PPO(policy_fn=lambda o, a, d: NeuralAF(o, a, d, options=params["policy_options"]), params=params,
+        cls = AutogradPPO if backend == "autograd" else PPO
+        ppo = cls(policy_fn=lambda o, a, d: NeuralAF(o, a, d, options=params["policy_options"]), params=params,
                   logpath=str(tmp_path / name), save_interval=10, verbose=True)
         w0 = torch.cat([p.detach().reshape(-1).clone() for p in ppo.pi.parameters()])
         ppo.train()
@@ -184,7 +185,7 @@ def test_ppo_native_update_follows_autograd_update(tmp_path):
 
     pa, w0a, w1a, la = run("autograd", "autograd")
     pn, w0n, w1n, ln = run("native", "native")
-    assert pn.update_backend == "native" and pn._pg is not None and pa._pg is None
+    assert pn._pg is not None and pa._pg is None
     assert torch.equal(w0a, w0n)
     assert la.shape == ln.shape == (2, 4)
     np.testing.assert_allclose(ln, la, rtol=2e-2, atol=2e-4)
