@@ -165,7 +165,8 @@ template <> __device__ __forceinline__ double t_exp<double>(double x) { return e
 // NV exp_nonpos evaluations with the NV dependent chains interleaved step by step: one fp64 warp has to cover the
 // DFMA latency with instruction-level parallelism.  Bitwise identical to exp_nonpos per element.  `tab` may point
 // to a shared-memory copy of MBO_EXP2_TAB.
-template <int NV>
+// TS: stride (in doubles) between consecutive table entries (32: the per-lane replicated shared-memory copy of the tensor kernel)
+template <int NV, int TS = 1>
 __device__ __forceinline__ void exp_nonpos_xn(const double* xin, double* out, const double* tab = MBO_EXP2_TAB) {
   const double MAGIC = 6755399441055744.0;
   double x[NV], kf[NV], r[NV], p[NV], tv[NV];
@@ -175,7 +176,7 @@ __device__ __forceinline__ void exp_nonpos_xn(const double* xin, double* out, co
 #pragma unroll
   for (int u = 0; u < NV; ++u) { const double t = fma(x[u], MBO_EXP_INV, MAGIC); k[u] = __double2loint(t); kf[u] = t - MAGIC; }
 #pragma unroll
-  for (int u = 0; u < NV; ++u) tv[u] = tab[k[u] & 63];
+  for (int u = 0; u < NV; ++u) tv[u] = tab[(k[u] & 63) * TS];
 #pragma unroll
   for (int u = 0; u < NV; ++u) r[u] = fma(kf[u], -MBO_EXP_HI, x[u]);
 #pragma unroll
@@ -197,7 +198,7 @@ __device__ __forceinline__ void exp_nonpos_xn(const double* xin, double* out, co
 __device__ __forceinline__ void exp_nonpos_x4(const double* xin, double* out) { exp_nonpos_xn<4>(xin, out); }
 
 // k(r2) for NV scaled squared distances at once (fp64), same values as kernel_of_r2<double>
-template <int NV>
+template <int NV, int TS = 1>
 __device__ __forceinline__ void kernel_of_r2_xn(int kid, double var, const double* r2, double* out,
                                                 const double* tab = MBO_EXP2_TAB) {
   double arg[NV], pre[NV], e[NV];
@@ -213,7 +214,7 @@ __device__ __forceinline__ void kernel_of_r2_xn(int kid, double var, const doubl
 #pragma unroll
     for (int u = 0; u < NV; ++u) { const double r = sqrt(r2[u]); arg[u] = -s5 * r; pre[u] = var * (1.0 + s5 * r + (5.0 / 3.0) * r2[u]); }
   }
-  exp_nonpos_xn<NV>(arg, e, tab);
+  exp_nonpos_xn<NV, TS>(arg, e, tab);
 #pragma unroll
   for (int u = 0; u < NV; ++u) out[u] = pre[u] * e[u];
 }

@@ -339,6 +339,236 @@ gp_posterior_kernel(int nmax, int kid_rt, const double* __restrict__ gp_state, m
   }   // tile loop (each thread only touches its own shared-memory column: no barrier between tiles)
 }
 
+// ------------------------------------------------------------------------------------------------
+// K1m: fp64 posterior with the blocked triangular mat-vec v = Linv k* on fp64 TENSOR instructions
+// (mma.sync.m8n8k4.f64, SASS DMMA.8x8x4).  A warp works on 8 candidates per pass:
+//   A fragment (8 x 4, row)  = Linv[8 rb + g][4 kb + t]  straight from the blob's 8-row blocks (conflict-free LDS.64),
+//   B fragment (4 x 8, col)  = k*[4 kb + t] of candidate g -- the lane that needs the value is the lane that computes
+//                              it (obs j = 4 kb + t, candidate g; g = lane >> 2, t = lane & 3), so k* is a per-lane
+//                              spill area [NKB][32] in shared memory: no cross-lane traffic, no barrier,
+//   C fragment (8 x 8)       = v[8 rb + g] of candidates 2t, 2t + 1; mean += v beta, q += v^2 per lane, summed over the
+//                              8 row lanes (g) with three shuffle steps.
+// Measured on B200 (tools/micro/dmma_bw.cu): DMMA and DFMA share the fp64 pipe (36.7 vs ~37 TFLOP/s, no gain from
+// mixing) -- the win is issue slots and latency tolerance: 20 DMMA + 40 LDS.64 per pass replace 640 DFMA + 240 LDS, the
+// per-thread k* column ([NP][128 TC] doubles, 65-106 KB per CTA) shrinks to 8-27 KB, so 8 CTAs (n = 30) or 16 warps
+// (n = 100) are resident instead of 3 CTAs / 4 warps.  Same values as gp_posterior_kernel<double> up to the order of
+// the fp64 additions (~1e-15 relative; tests/test_gp_gpu.py).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// NRB_T > 0: n <= 8 NRB_T observations, every loop over row / k blocks unrolled and k* kept in REGISTERS (2 NRB_T doubles
+// per lane); NRB_T == 0: any n, dynamic loops, k* in a per-lane shared-memory spill area.
+// Shared-memory traffic is what bounded both this kernel's first version and the CUDA-core kernel (LSU data-pipe
+// wavefronts at 80 % of peak in ncu): so (i) Linv is re-laid-out into mma fragment order while the blob is copied in
+// (tile (rb, kb) = 32 consecutive doubles in lane order: every A load is a conflict-free LDS.64), (ii) the 64-entry
+// exp table is replicated per lane ([64][32] doubles: a lane-varying index costs the minimum two wavefronts instead
+// of ~8), (iii) candidates are prepared once per lane (load + X / lengthscale) and handed to the pass that needs
+// them by shuffles, (iv) the per-candidate epilogue (clip, sqrt, store) runs once per lane after the four passes.
+template <int DT, int KID, int NRB_T>
+__global__ void __launch_bounds__(256)
+gp_posterior_mma_kernel(int nmax, const double* __restrict__ gp_state, mbo_candidates cand, int tiles_per_episode,
+                        int ctas_per_episode, void* __restrict__ mean_out, void* __restrict__ std_out, int out_is_f32) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int D = DT ? DT : cand.D;
+  constexpr int DU = DT ? DT : MBO_MAX_D;
+  const int b = blockIdx.x / ctas_per_episode;
+  const int cta = blockIdx.x - b * ctas_per_episode;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const size_t stride = gp_state_doubles(nmax, D);
+  const double* st = gp_state + (size_t)b * stride;
+  const int NPmax = gp_np(nmax);
+  const int n = (int)st[0];
+  // NRB_T > 0: the unrolled loops cover 8 NRB_T rows whatever this episode's n is; the blob is zero beyond n (the fit
+  // clears it), so the extra rows / k blocks of a shorter episode contribute exact zeros
+  const int NP = NRB_T ? 8 * NRB_T : gp_np(n);
+  const int NKB = NP >> 2, NRB = NRB_T ? NRB_T : (NP >> 3);
+  const double m = st[1];
+  const double var = st[2];
+
+  constexpr int TS = NRB_T ? 32 : 1;          // the generic kernel (large blobs) keeps one 512-byte copy: shared memory decides its occupancy
+  double* sTab = (double*)smraw;              // [64][TS] exp table (TS = 32: one copy per lane)
+  double* sXs = sTab + 64 * TS;               // [NP][D]
+  double* sBeta = sXs + NP * D;               // [NP]
+  double* sA = sBeta + NP;                    // Linv in mma A-fragment order
+  const int lcount = gp_linv_doubles(NP);
+  double* sOut = sA + lcount + (size_t)warp * 64;                              // [2][32] q / mu of the warp's 32 candidates
+  double* sK = sA + lcount + (size_t)nwarps * 64 + (size_t)warp * NKB * 32;    // NRB_T == 0: this warp's k* spill area [NKB][32]
+  for (int i = tid; i < 64 * TS; i += blockDim.x) sTab[i] = MBO_EXP2_TAB[i / TS];
+  for (int i = tid; i < NP * D; i += blockDim.x) sXs[i] = st[gp_off_xs() + i];
+  for (int i = tid; i < NP; i += blockDim.x) sBeta[i] = st[gp_off_beta(NPmax, D) + i];
+  {
+    const double* lb = st + gp_off_linv(NPmax, D);
+    for (int rb = 0; rb < (NP >> 3); ++rb) {
+      const int off = gp_linv_block_off(8 * rb), cnt = (8 * rb + 8) * 8;
+      for (int e = tid; e < cnt; e += blockDim.x) {          // blob: (j, r) -> j * 8 + r;  fragment order: tile j / 4, lane 4 r + j % 4
+        const int j = e >> 3, r = e & 7;
+        sA[off + (j >> 2) * 32 + r * 4 + (j & 3)] = lb[off + e];
+      }
+    }
+  }
+  double ls[DU];
+#pragma unroll
+  for (int d = 0; d < DU; ++d) ls[d] = d < D ? st[4 + d] : 1.0;
+  __syncthreads();
+  const double* tab = sTab + (NRB_T ? lane : 0);   // entry j of this lane's copy: tab[j * TS]
+
+  const int TILE = nwarps * 32;
+  for (int tile = cta; tile < tiles_per_episode; tile += ctas_per_episode) {
+    const int w0 = tile * TILE + warp * 32;
+    // this lane's own candidate, scaled like the fit scales the observations (a candidate equal to an observation has r == 0)
+    double own[DU];
+    {
+      double x[MBO_MAX_D];
+#pragma unroll
+      for (int d = 0; d < MBO_MAX_D; ++d) x[d] = 0.0;
+      if (w0 + lane < cand.M) load_candidate_compact(cand, b, w0 + lane, x);
+#pragma unroll
+      for (int d = 0; d < DU; ++d) own[d] = d < D ? x[d] / ls[d] : 0.0;
+    }
+#pragma unroll 1
+    for (int pass = 0; pass < 4; ++pass) {
+      double xs[DU];
+#pragma unroll
+      for (int d = 0; d < DU; ++d) xs[d] = __shfl_sync(0xffffffffu, own[d], pass * 8 + g);
+      // ---- k*: lane (g, t) evaluates observation j = 4 kb + t for candidate g ----
+      double K[NRB_T ? 2 * NRB_T : 1];
+      constexpr int NKB_U = NRB_T ? 2 * NRB_T : 0;
+      if (NRB_T) {
+#pragma unroll
+        for (int kb0 = 0; kb0 < NKB_U; kb0 += 2) {          // two kernel values at a time (interleaved exp chains)
+          double r2v[2], kv[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int jj = max(min(4 * (kb0 + u) + t, n - 1), 0);
+            double r2 = 0.0;
+#pragma unroll
+            for (int d = 0; d < DU; ++d)
+              if (DT || d < D) { const double dd = xs[d] - sXs[jj * D + d]; r2 = fma(dd, dd, r2); }
+            r2v[u] = r2;
+          }
+          kernel_of_r2_xn<2, TS>(KID, var, r2v, kv, tab);
+#pragma unroll
+          for (int u = 0; u < 2; ++u) K[kb0 + u] = (4 * (kb0 + u) + t < n) ? kv[u] : 0.0;
+        }
+      } else {
+        for (int kb0 = 0; kb0 < NKB; kb0 += 2) {
+          double r2v[2], kv[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int jj = max(min(4 * (kb0 + u) + t, n - 1), 0);
+            double r2 = 0.0;
+#pragma unroll
+            for (int d = 0; d < DU; ++d)
+              if (DT || d < D) { const double dd = xs[d] - sXs[jj * D + d]; r2 = fma(dd, dd, r2); }
+            r2v[u] = r2;
+          }
+          kernel_of_r2_xn<2, TS>(KID, var, r2v, kv, tab);
+#pragma unroll
+          for (int u = 0; u < 2; ++u) sK[(kb0 + u) * 32 + lane] = (4 * (kb0 + u) + t < n) ? kv[u] : 0.0;     // NKB is even
+        }
+      }
+      // ---- v = Linv k* by row blocks (DMMA), mean / q accumulation ----
+      double q0 = 0.0, q1 = 0.0, mu0 = 0.0, mu1 = 0.0;
+      if (NRB_T) {
+#pragma unroll
+        for (int rb = 0; rb < (NRB_T ? NRB_T : 1); ++rb) {
+          double c0 = 0.0, c1 = 0.0;
+          const double* blk = sA + 32 * rb * (rb + 1) + lane;      // gp_linv_block_off(8 rb)
+#pragma unroll
+          for (int kb = 0; kb < 2 * rb + 2; ++kb) dmma_884(c0, c1, blk[kb * 32], K[kb]);
+          const double be = sBeta[8 * rb + g];
+          q0 = fma(c0, c0, q0); q1 = fma(c1, c1, q1);
+          mu0 = fma(c0, be, mu0); mu1 = fma(c1, be, mu1);
+        }
+      } else {
+        for (int rb = 0; rb < NRB; ++rb) {
+          double c0 = 0.0, c1 = 0.0;
+          const double* blk = sA + gp_linv_block_off(8 * rb) + lane;
+          const int nk = 2 * rb + 2;
+#pragma unroll 2
+          for (int kb = 0; kb < nk; ++kb) dmma_884(c0, c1, blk[kb * 32], sK[kb * 32 + lane]);
+          const double be = sBeta[8 * rb + g];
+          q0 = fma(c0, c0, q0); q1 = fma(c1, c1, q1);
+          mu0 = fma(c0, be, mu0); mu1 = fma(c1, be, mu1);
+        }
+      }
+      // ---- sum over the 8 row lanes (g): exchange-and-halve butterfly, 4 double shuffles instead of 12 ----
+      const bool hi4 = lane & 16, hi3 = lane & 8;
+      const double r0 = __shfl_xor_sync(0xffffffffu, hi4 ? q0 : mu0, 16), r1 = __shfl_xor_sync(0xffffffffu, hi4 ? q1 : mu1, 16);
+      const double a0 = (hi4 ? mu0 : q0) + r0, a1 = (hi4 ? mu1 : q1) + r1;       // bit 4 set: the mu pair, else the q pair
+      const double r2x = __shfl_xor_sync(0xffffffffu, hi3 ? a0 : a1, 8);
+      double a = (hi3 ? a1 : a0) + r2x;                                            // bit 3 set: candidate 2t + 1, else 2t
+      a += __shfl_xor_sync(0xffffffffu, a, 4);
+      if (!(lane & 4)) sOut[(hi4 ? 32 : 0) + pass * 8 + 2 * t + (hi3 ? 1 : 0)] = a;
+    }
+    __syncwarp();
+    const int mo = w0 + lane;
+    if (mo < cand.M) {
+      double mean_v, var_v;
+      if (n == 0) { mean_v = 0.0; var_v = var; }               // metabo_gym.py:737: zero, not the prior mean
+      else {
+        mean_v = sOut[32 + lane] + m;
+        var_v = var - sOut[lane];
+        var_v = var_v < 1e-15 ? 1e-15 : var_v;                // GPy clip
+      }
+      const double sd = sqrt(var_v);
+      const size_t o = (size_t)b * cand.M + mo;
+      if (out_is_f32) { ((float*)mean_out)[o] = (float)mean_v; ((float*)std_out)[o] = (float)sd; }
+      else { ((double*)mean_out)[o] = mean_v; ((double*)std_out)[o] = sd; }
+    }
+    __syncwarp();
+  }
+}
+
+static size_t posterior_mma_smem_bytes(int ns, int D, int warps, bool k_in_smem) {
+  const int NP = gp_np(ns);
+  return sizeof(double) * ((size_t)64 * (k_in_smem ? 1 : 32) + (size_t)NP * D + NP + gp_linv_doubles(NP) + (size_t)warps * 64 +
+                           (k_in_smem ? (size_t)warps * (NP >> 2) * 32 : 0));
+}
+
+template <int DT, int KID>
+static int launch_posterior_mma_dk(int B, int nmax, int ns, const double* gp_state, const mbo_candidates& cand, void* mean, void* std_,
+                                   int out_is_f32, cudaStream_t s) {
+  const int NP = gp_np(ns);
+  const int nrb = NP >> 3;
+  // small blobs: 4-warp CTAs (many resident CTAs); large blobs (n ~ 100: 50 KB): 8 warps share one copy
+  const int warps = sizeof(double) * ((size_t)NP * cand.D + NP + gp_linv_doubles(NP)) > 20 * 1024 ? 8 : 4;
+  const bool reg_k = nrb >= 1 && nrb <= 4;
+  const size_t smem = posterior_mma_smem_bytes(ns, cand.D, warps, !reg_k);
+  auto kern = gp_posterior_mma_kernel<DT, KID, 0>;
+  if (nrb == 1) kern = gp_posterior_mma_kernel<DT, KID, 1>;
+  else if (nrb == 2) kern = gp_posterior_mma_kernel<DT, KID, 2>;
+  else if (nrb == 3) kern = gp_posterior_mma_kernel<DT, KID, 3>;
+  else if (nrb == 4) kern = gp_posterior_mma_kernel<DT, KID, 4>;
+  MBO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int TILE = warps * 32;
+  const int tiles = (cand.M + TILE - 1) / TILE;
+  int ctas = tiles;
+  if ((long long)B * tiles > 4096) { ctas = (tiles + 3) / 4; if (ctas < 1) ctas = 1; }
+  kern<<<B * ctas, warps * 32, smem, s>>>(nmax, gp_state, cand, tiles, ctas, mean, std_, out_is_f32);
+  MBO_LAUNCH_CHECK();
+  return MBO_OK;
+}
+
+template <int KID>
+static int launch_posterior_mma_k(int B, int nmax, int ns, const double* gp_state, const mbo_candidates& cand, void* mean, void* std_,
+                                  int out_is_f32, cudaStream_t s) {
+  // the dimensions of the shipped experiments (Branin 2, Hartmann-3 / GP samples 3) get their own instantiation
+  if (cand.D == 2) return launch_posterior_mma_dk<2, KID>(B, nmax, ns, gp_state, cand, mean, std_, out_is_f32, s);
+  if (cand.D == 3) return launch_posterior_mma_dk<3, KID>(B, nmax, ns, gp_state, cand, mean, std_, out_is_f32, s);
+  return launch_posterior_mma_dk<0, KID>(B, nmax, ns, gp_state, cand, mean, std_, out_is_f32, s);
+}
+
+static int launch_posterior_mma(int B, int nmax, int ns, int kid, const double* gp_state, const mbo_candidates& cand,
+                                void* mean, void* std_, int out_is_f32, cudaStream_t s) {
+  if (kid == MBO_KERNEL_RBF) return launch_posterior_mma_k<MBO_KERNEL_RBF>(B, nmax, ns, gp_state, cand, mean, std_, out_is_f32, s);
+  if (kid == MBO_KERNEL_MATERN32) return launch_posterior_mma_k<MBO_KERNEL_MATERN32>(B, nmax, ns, gp_state, cand, mean, std_, out_is_f32, s);
+  return launch_posterior_mma_k<MBO_KERNEL_MATERN52>(B, nmax, ns, gp_state, cand, mean, std_, out_is_f32, s);
+}
+
 template <typename T, int TC>
 static size_t posterior_smem_bytes(int nmax, int D) {
   int NP = gp_np(nmax);
@@ -410,6 +640,9 @@ extern "C" int mbo_gp_posterior(int B, int nmax, int n_active_max, int kernel_id
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   if (precision == MBO_GP_FP64) {
+    const char* simt_env = getenv("MBO_GP_SIMT");            // 1: the CUDA-core (DFMA) kernel, kept as the A/B and parity reference
+    const int simt = simt_env ? atoi(simt_env) : 0;
+    if (!simt) return launch_posterior_mma(B, nmax, ns, kernel_id, gp_state, *cand, mean, std_, out_is_f32, s);
     static const int force_tc1 = getenv("MBO_GP_TC1") ? 1 : 0;     // tuning switch
     if (!force_tc1 && posterior_smem_bytes<double, 2>(ns, cand->D) <= 100 * 1024)
       return launch_posterior<double, 2>(B, nmax, ns, kernel_id, gp_state, *cand, mean, std_, out_is_f32, s);

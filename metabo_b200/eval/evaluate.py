@@ -1,7 +1,9 @@
 """eval_experiment drop-in for the MetaBO policy (metabo/eval/evaluate.py:59-167): loads a trained
 NeuralAF from the reference's checkpoint files (params_N / weights_N / stats_N, shipped iclr2020
 runs included), plays T * n_episodes steps through the GPU BatchRecorder and stores the same
-`Result` pickle.  The baseline AFs (EI, TAF, ...) are outside the hot path and raise."""
+`Result` pickle.  Baselines: EI / GP-UCB / PI run as closed-form epilogues of the same GPU AF rounds, TAF-ME / TAF-RANKING
+(policies.py:310-468) through the host-driven env with their 50 source GPs on the batched GP kernel; the data-file
+baselines EPS-GREEDY / GMM-UCB and Random are outside the scope and raise."""
 import os
 import pickle as pkl
 from collections import namedtuple
@@ -12,6 +14,7 @@ import torch
 
 from .. import gym_compat as gym
 from ..policies.policies import NeuralAF, EI, PI, UCB
+from ..policies.taf import TAF
 from ..ppo.batchrecorder import BatchRecorder
 
 Result = namedtuple("Result",
@@ -33,8 +36,8 @@ def load_metabo_policy(logpath, load_iter, env, device, deterministic):
 def eval_experiment(eval_spec):
     env_id = eval_spec["env_id"]
     policy = eval_spec["policy"]
-    if policy not in ("MetaBO", "EI", "GP-UCB", "PI"):
-        raise ValueError("Unknown policy!" if policy not in ("TAF-ME", "TAF-RANKING", "EPS-GREEDY", "GMM-UCB", "Random")
+    if policy not in ("MetaBO", "EI", "GP-UCB", "PI", "TAF-ME", "TAF-RANKING"):
+        raise ValueError("Unknown policy!" if policy not in ("EPS-GREEDY", "GMM-UCB", "Random")
                          else "baseline '%s' is outside the GPU hot path" % policy)
     logpath, savepath = eval_spec["logpath"], eval_spec["savepath"]
     n_workers, n_episodes, T = eval_spec["n_workers"], eval_spec["n_episodes"], eval_spec["T"]
@@ -54,7 +57,11 @@ def eval_experiment(eval_spec):
     else:
         # closed-form baselines on the same GP kernels (evaluate.py:102-118)
         policy_specs = eval_spec["policy_specs"]
-        if policy == "EI":
+        if policy == "TAF-ME":
+            policy_fn = lambda *_: TAF(datafile=policy_specs["TAF_datafile"], mode="me")               # evaluate.py:112-113
+        elif policy == "TAF-RANKING":
+            policy_fn = lambda *_: TAF(datafile=policy_specs["TAF_datafile"], mode="ranking", rho=1.0)  # :114-115
+        elif policy == "EI":
             policy_fn = lambda *_: EI(feature_order=feature_order)
         elif policy == "PI":
             policy_fn = lambda *_: PI(feature_order=feature_order, xi=policy_specs["xi"])

@@ -106,6 +106,13 @@ class BatchRecorder:
         self.action_space = gym.spaces.Discrete(self.env.cardinality_xi_t)
         self.pi = policy_fn(self.observation_space, self.action_space, self.deterministic)
         self.pi.set_requires_grad(False)
+        from ..policies.policies import NeuralAF
+        # a foreign policy (TAF, ...: no kernel form) plays its episodes one at a time through the single-episode MetaBO
+        # env and the reference's host-side AF gridding, like one EnvRunner per worker (batchrecorder.py:38-113)
+        self.host_policy = not isinstance(self.pi, NeuralAF) and not hasattr(self.pi, "engine_spec")
+        self._host_envs = None
+        if self.host_policy:
+            return
         if hasattr(self.pi, "engine_spec"):
             self.deterministic = True          # closed-form baselines act by argmax (policies.py:191-199)
         self.env.set_policy(self.pi)
@@ -128,11 +135,59 @@ class BatchRecorder:
 
     def set_worker_weights(self, pi):
         now = time.time()
-        self.pi.load_state_dict(pi.state_dict())
-        self.env.sync_policy()
+        if not self.host_policy:
+            self.pi.load_state_dict(pi.state_dict())
+            self.env.sync_policy()
+        return time.time() - now
+
+    def _record_batch_host(self, gamma, lam):
+        """foreign policies: sequential episodes per worker on the host-driven MetaBO env (GP still on the kernels)"""
+        from ..environment.metabo_gym import MetaBO
+        now = time.time()
+        self.clear()
+        B, T, dev = self.B, self.T, self.env.dev
+        if self._host_envs is None:
+            self._host_envs = []
+            for seed in self.env_seeds:
+                e = MetaBO(**self._kwargs)
+                e.set_af_functions(self.pi.af)
+                e.seed(int(seed))
+                self._host_envs.append(e)
+        actions = torch.zeros((B, T), dtype=torch.int32)
+        rewards = torch.zeros((B, T), dtype=torch.float64)
+        values = torch.zeros((B, T), dtype=torch.float32)
+        states = torch.zeros((B, T, self.env.cardinality_xi_t, self.env.n_features), dtype=torch.float32) if self.store_states else None
+        lane = 0
+        for w, env in enumerate(self._host_envs):
+            for _ in range(self.episodes_per_worker):
+                self.pi.reset()
+                state = env.reset()
+                for t in range(T):
+                    st = torch.from_numpy(state.astype(np.float32))
+                    with torch.no_grad():
+                        a, v = self.pi.act(st, env.X, env.gp) if env.pass_X_to_pi else self.pi.act(st)   # :165-170
+                    if states is not None:
+                        states[lane, t] = st
+                    actions[lane, t], values[lane, t] = int(a), float(v)
+                    state, r, done, _ = env.step(int(a))
+                    rewards[lane, t] = r
+                assert done
+                lane += 1
+        adv, tdlamret = gae_device(rewards, values.double(), gamma, lam)
+        self.buf = dict(states=None if states is None else states.to(dev), actions=actions.to(dev), rewards=rewards.to(dev),
+                        values=values.to(dev), advs=adv.float().to(dev), tdlamrets=tdlamret.float().to(dev))
+        r_host = rewards.numpy()
+        self.reward_sum = float(r_host.sum())
+        self.n_new = B
+        self.worker_sizes = list(self.worker_batch_sizes)
+        self.worker_n_news = [self.episodes_per_worker] * self.n_workers
+        self.initial_rewards = list(r_host[:, 0])
+        self.terminal_rewards = list(r_host[:, -1])
         return time.time() - now
 
     def record_batch(self, gamma, lam):
+        if self.host_policy:
+            return self._record_batch_host(gamma, lam)
         now = time.time()
         self.clear()
         env, B, T = self.env, self.B, self.T

@@ -17,6 +17,22 @@ class GPRegression:
         self.X, self.Y = X, Y
         self._route = None
 
+    # GPy exposes the kernel as an attribute named after it (policies.py:372-373 `gp.rbf.lengthscale = ...`)
+    @property
+    def rbf(self):
+        assert self.kern.kind == "RBF"
+        return self.kern
+
+    @property
+    def Mat32(self):
+        assert self.kern.kind == "Matern32"
+        return self.kern
+
+    @property
+    def Mat52(self):
+        assert self.kern.kind == "Matern52"
+        return self.kern
+
     def set_XY(self, X, Y):
         self.X, self.Y = X, Y
         k = self.kern

@@ -1,0 +1,120 @@
+"""GPU tests of the foreign-AF boundary of the drop-in env (`MetaBO.set_af_functions` with an arbitrary numpy
+callback, `get_state`, metabo_gym.py:168-174, 615-677, 706-721) and of TAF (policies.py:310-468) on the batched GP kernel,
+against the reference's own TAF class (tests/golden/taf_bra.npz, minted by oracle/make_golden_taf.py) and the oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import metabo_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TAF_SPEC = {"env_id": "MetaBO-BRA-TAF-v0", "D": 2, "f_type": "BRA-var", "f_opts": {"bound_translation": 0.1, "bound_scaling": 0.1},
+            "features": ["posterior_mean", "posterior_std", "x", "incumbent", "timestep"], "T": 6, "n_init_samples": 0,
+            "pass_X_to_pi": True, "kernel_lengthscale": [0.235, 0.578], "kernel_variance": 2.0, "noise_variance": 8.9e-16,
+            "use_prior_mean_function": False, "local_af_opt": True, "N_MS": 200, "N_LS": 100, "k": 3,
+            "reward_transformation": "none"}
+
+
+class _TargetGP:
+    """model_target for TAF.af: predict_noiseless on the CUDA kernels"""
+
+    def __init__(self, X, Y):
+        from metabo_b200 import ops
+        dev = torch.device("cuda:0")
+        n = X.shape[0]
+        t = lambda a, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)
+        self.state, _ = ops.gp_fit(t(np.array([n]), torch.int32), t(X[None]), t(Y[None]), t(np.array([[0.235, 0.578]])),
+                                   t(np.array([2.0])), t(np.array([8.9e-16])))
+        self.n, self.dev = n, dev
+
+    def predict_noiseless(self, Xs):
+        from metabo_b200 import ops
+        cs = ops.CandidateSet(2, tail=torch.as_tensor(np.ascontiguousarray(Xs, dtype=np.float64), device=self.dev))
+        m, s = ops.gp_posterior(self.state, self.n, cs, 1)
+        return m[0].cpu().numpy().reshape(-1, 1), (s[0].cpu().numpy() ** 2).reshape(-1, 1)
+
+
+def test_taf_matches_reference_class(golden_dir):
+    from metabo_b200.policies.taf import TAF, generate_taf_data_branin
+    g = np.load(os.path.join(golden_dir, "taf_bra.npz"))
+    data = generate_taf_data_branin(50, 100)
+    assert np.array_equal(np.asarray(data["X"][0]), g["source_X"])                     # same Sobol inputs
+    Y = np.stack([y[:, 0] for y in data["Y"]])
+    np.testing.assert_allclose(Y, g["source_Y"], rtol=1e-12, atol=1e-12)               # same source tasks
+    for mode, key, kw in (("me", "taf_me", {}), ("ranking", "taf_ranking", {"rho": 1.0})):
+        taf = TAF(datafile=data, mode=mode, **kw)
+        for t in (0, 2, 7):
+            p = "t%02d_" % t
+            Xt = g[p + "X_target"]
+            model = _TargetGP(Xt, g[p + "Y_target"]) if t else None
+            got = taf.af(g[p + "state"], Xt if t else None, model)
+            ref = g[p + key]
+            # the source GPs (100 Sobol points, smooth RBF, noise 8.9e-16 + GPy's 1e-8 jitter) have cond(Ky) ~ 1e10: the
+            # reference's explicit-inverse route and the kernel's triangular route differ by ~1e-5 in the source
+            # sigmas, which TAF-ME turns into sigma^-2 weights -> 1e-3 of max|TAF| (measured 2.7e-4)
+            assert np.max(np.abs(got - ref)) <= 1e-3 * max(np.max(np.abs(ref)), 1e-6), (mode, t, np.max(np.abs(got - ref)))
+            assert int(np.argmax(got)) == int(np.argmax(ref)) or abs(ref[np.argmax(got)] - ref.max()) <= 1e-3 * abs(ref.max())
+
+
+def test_foreign_numpy_af_drives_the_env_like_the_oracle(golden_dir):
+    """A plain numpy AF (UCB on the state columns) through set_af_functions: every step's state is get_state(xi_t) with
+    xi_t = [af maxima; multistart grid] found by the reference's host-side gridding; checked against the oracle's
+    get_af_maxima on the same data."""
+    from metabo_b200.environment.metabo_gym import MetaBO
+    spec = dict(TAF_SPEC, pass_X_to_pi=False, env_id="MetaBO-BRA-FOREIGN-v0")
+    env = MetaBO(**spec)
+    calls = []
+
+    def my_af(state):
+        calls.append(state.shape)
+        return state[:, 0] + 2.0 * state[:, 1]
+
+    env.set_af_functions(my_af)
+    env.seed(5)
+    state = env.reset()
+    assert state.shape == (env.cardinality_xi_t, 6) and state.dtype == np.float32
+    assert calls[:2] == [(env.N_MS, 6), (env.k * env.N_LS, 6)]
+    grids = O.Grids(2, N_MS=spec["N_MS"], N_LS=spec["N_LS"], k=spec["k"])
+    for t in range(spec["T"]):
+        a = int(np.argmax(my_af(state)))
+        state, r, done, _ = env.step(a)
+        assert env.X.shape == (t + 1, 2)
+        # oracle round on the same data with the same AF
+        gp = O.EpisodeGP(2, "RBF", 2.0, [0.235, 0.578], 8.9e-16, y_min=env.y_min, route="truth")
+        gp.set_data(env.X, env.Y[:, 0])
+        s_ms = O.get_state(gp, grids.multistart_grid, spec["features"], t + 1, spec["T"])
+        top = np.argsort(-(s_ms[:, 0] + 2.0 * s_ms[:, 1]), kind="stable")[:spec["k"]]
+        local = grids.local_grids(grids.multistart_grid[top])
+        assert np.array_equal(env.af_opt_startpoints_t, grids.multistart_grid[top]) or t > 2     # later steps: near-ties
+        s_ref = O.get_state(gp, env.xi_t, spec["features"], t + 1, spec["T"])
+        assert np.max(np.abs(state - s_ref)) <= 1e-5 * max(1.0, np.abs(s_ref).max())
+        assert np.array_equal(env.xi_t[spec["k"]:], grids.multistart_grid)
+    assert done and env.is_terminal()
+    # get_state at arbitrary points is public (metabo_gym.py:624-677)
+    Xq = np.random.RandomState(0).rand(17, 2)
+    sq = env.get_state(Xq)
+    m, s = env.eval_gp(Xq)
+    assert sq.shape == (17, 6) and np.allclose(sq[:, 0], m.astype(np.float32)) and np.allclose(sq[:, 2:4], Xq.astype(np.float32))
+
+
+def test_taf_episode_and_eval_experiment(tmp_path):
+    """TAF-ME through eval_experiment (evaluate.py:112-113, pass_X_to_pi env): sequential host-driven episodes with the
+    GP on the kernels; regret is non-increasing and improves."""
+    import pickle as pkl
+    from metabo_b200 import gym_compat as gym
+    from metabo_b200.eval.evaluate import eval_experiment
+    from metabo_b200.policies.taf import generate_taf_data_branin
+    datafile = str(tmp_path / "taf_branin_M_20_N_40.pkl")
+    generate_taf_data_branin(20, 40, datafile)
+    assert set(pkl.load(open(datafile, "rb"))) >= {"D", "M", "X", "Y", "kernel_lengthscale"}
+    gym.register(id=TAF_SPEC["env_id"], entry_point="metabo.environment.metabo_gym:MetaBO", max_episode_steps=6, kwargs=TAF_SPEC)
+    res = eval_experiment({"env_id": TAF_SPEC["env_id"], "env_seed_offset": 100, "policy": "TAF-ME", "logpath": None,
+                           "load_iter": None, "deterministic": True, "policy_specs": {"TAF_datafile": datafile},
+                           "savepath": str(tmp_path / "eval"), "n_workers": 2, "n_episodes": 4, "T": 6})
+    r = np.array(res.rewards).reshape(4, 6)
+    assert np.all(np.diff(r, axis=1) <= 1e-12) and np.all(r[:, -1] <= r[:, 0])
+    assert os.path.exists(tmp_path / "eval" / "result_TAF-ME")

@@ -155,3 +155,42 @@ def test_fit_larger_n_and_linearity():
     np.testing.assert_allclose(s1, s2, rtol=0, atol=0)          # std does not depend on Y
     m_o, s_o = G.gpy_route_posterior(*args, X, Y1, cand)
     assert _rel(m1[0], m_o, 1e-2) < 1e-5 and _rel(s1[0], s_o, 1e-2) < 1e-5
+
+
+@pytest.mark.parametrize("kernel,D,n,M", [("RBF", 3, 30, 10000), ("RBF", 2, 30, 966), ("Matern52", 3, 100, 2000), ("Matern32", 5, 17, 333),
+                                          ("RBF", 6, 64, 1000), ("RBF", 3, 1, 77), ("RBF", 3, 0, 50)])
+def test_tensor_posterior_kernel_equals_cuda_core_kernel(monkeypatch, kernel, D, n, M):
+    """The default fp64 posterior (blocked triangular mat-vec on fp64 tensor instructions, DMMA.8x8x4) against the
+    CUDA-core DFMA kernel it replaces (MBO_GP_SIMT=1): same blob, same k*, only the order of the fp64 additions
+    differs -> 1e-12 relative on mean and std (std relative to sqrt(variance): it is a difference of O(variance) terms)
+    and identical fp32 outputs except for isolated last-bit roundings; ragged n per episode, candidate counts that do not fill a
+    tile, head + tail + cube candidate descriptors."""
+    from metabo_b200 import ops
+    dev = _dev()
+    rng = np.random.RandomState(n * 7 + D)
+    B, T = 5, max(n, 1)
+    ns = np.array([n, max(n - 1, 0), max(n // 2, 0), n, min(n, 3)], dtype=np.int32)
+    X = rng.rand(B, T, D); Y = rng.randn(B, T)
+    t = lambda a, dt=torch.float64: torch.as_tensor(a, dtype=dt, device=dev).contiguous()
+    ls = rng.uniform(0.2, 0.7, (B, D))
+    state, status = ops.gp_fit(t(ns, torch.int32), t(X), t(Y), t(ls), t(np.full(B, 0.83)), t(np.full(B, 1e-6)), kernel=kernel,
+                               use_prior_mean=True)
+    k = 3
+    head = t(rng.rand(B, k, D))
+    tail = t(rng.rand(M - k, D))
+    cs = ops.CandidateSet(D, head=head, tail=tail)
+    outs = {}
+    for simt in ("1", "0"):
+        monkeypatch.setenv("MBO_GP_SIMT", simt)
+        m64, s64 = ops.gp_posterior(state, T, cs, B, kernel=kernel, n_active_max=n)
+        m32, s32 = ops.gp_posterior(state, T, cs, B, kernel=kernel, out_dtype=torch.float32, n_active_max=n)
+        torch.cuda.synchronize()
+        outs[simt] = (m64.cpu().numpy(), s64.cpu().numpy(), m32.cpu().numpy(), s32.cpu().numpy())
+    a, b_ = outs["1"], outs["0"]
+    scale_m = max(1.0, np.abs(a[0]).max())
+    assert np.max(np.abs(a[0] - b_[0])) <= 1e-12 * scale_m
+    # var = variance - |v|^2 cancels: compare variances at 1e-12 of the prior variance
+    assert np.max(np.abs(a[1] ** 2 - b_[1] ** 2)) <= 1e-12 * 0.83
+    assert (a[2] != b_[2]).mean() <= 1e-3 and np.max(np.abs(a[2] - b_[2])) <= 2e-7 * scale_m
+    sd_close = np.abs(a[3] - b_[3]) <= 2e-7 * np.maximum(np.abs(a[3]), 1e-3)
+    assert sd_close.mean() >= 0.999

@@ -71,7 +71,11 @@ def test_simt_policy_grad_matches_fp64_autograd(act, widths, cols, F_state, E, M
     assert torch.equal(terms[:, 0], lp_k) and torch.equal(terms[:, 1], ent_k)      # forward-only == gradient call
     for l in range(L):
         assert _rel(dW[l], Wr[l].grad) <= 1e-4, ("dW", l, _rel(dW[l], Wr[l].grad))
-        assert _rel(db[l], br[l].grad) <= 1e-4, ("db", l)
+        if l < L - 1:
+            assert _rel(db[l], br[l].grad) <= 1e-4, ("db", l)
+    # the logit bias shifts every logit of an episode alike: its gradient is analytically 0 (softmax invariance) and
+    # the kernels' value is the fp32 round-off of a sum of R cancelling dlogits
+    assert float(db[L - 1].abs().max()) <= 1e-5 * float(dW[L - 1].abs().max()) + 1e-7
     # bitwise reproducible (fixed-order partial sums, no atomics)
     dW2, db2 = [torch.zeros_like(w) for w in Wd], [torch.zeros_like(x) for x in bd]
     pg(states.to(dev), Wd, bd, a32, advs.to(dev), lpo.float().to(dev), eps, entc, n_global, dW2, db2)
