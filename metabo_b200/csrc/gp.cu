@@ -366,7 +366,7 @@ __device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, doubl
 // exp table is replicated per lane ([64][32] doubles: a lane-varying index costs the minimum two wavefronts instead
 // of ~8), (iii) candidates are prepared once per lane (load + X / lengthscale) and handed to the pass that needs
 // them by shuffles, (iv) the per-candidate epilogue (clip, sqrt, store) runs once per lane after the four passes.
-template <int DT, int KID, int NRB_T>
+template <int DT, int KID, int NRB_T, int TSV = 32>
 __global__ void __launch_bounds__(256)
 gp_posterior_mma_kernel(int nmax, const double* __restrict__ gp_state, mbo_candidates cand, int tiles_per_episode,
                         int ctas_per_episode, void* __restrict__ mean_out, void* __restrict__ std_out, int out_is_f32) {
@@ -388,7 +388,9 @@ gp_posterior_mma_kernel(int nmax, const double* __restrict__ gp_state, mbo_candi
   const double m = st[1];
   const double var = st[2];
 
-  constexpr int TS = NRB_T ? 32 : 1;          // the generic kernel (large blobs) keeps one 512-byte copy: shared memory decides its occupancy
+  // TS copies of the exp table: 32 = one per lane (16 KB), 8 = 4 KB (a CTA then needs 12 KB at n = 30 and fits beside the
+  // resident tensor-core MLP CTA of another stream); the generic kernel (large blobs) keeps a single 512-byte copy
+  constexpr int TS = NRB_T ? TSV : 1;
   double* sTab = (double*)smraw;              // [64][TS] exp table (TS = 32: one copy per lane)
   double* sXs = sTab + 64 * TS;               // [NP][D]
   double* sBeta = sXs + NP * D;               // [NP]
@@ -413,7 +415,7 @@ gp_posterior_mma_kernel(int nmax, const double* __restrict__ gp_state, mbo_candi
 #pragma unroll
   for (int d = 0; d < DU; ++d) ls[d] = d < D ? st[4 + d] : 1.0;
   __syncthreads();
-  const double* tab = sTab + (NRB_T ? lane : 0);   // entry j of this lane's copy: tab[j * TS]
+  const double* tab = sTab + (lane & (TS - 1));    // entry j of this lane's copy: tab[j * TS]
 
   const int TILE = nwarps * 32;
   for (int tile = cta; tile < tiles_per_episode; tile += ctas_per_episode) {
@@ -523,9 +525,9 @@ gp_posterior_mma_kernel(int nmax, const double* __restrict__ gp_state, mbo_candi
   }
 }
 
-static size_t posterior_mma_smem_bytes(int ns, int D, int warps, bool k_in_smem) {
+static size_t posterior_mma_smem_bytes(int ns, int D, int warps, bool k_in_smem, int ts) {
   const int NP = gp_np(ns);
-  return sizeof(double) * ((size_t)64 * (k_in_smem ? 1 : 32) + (size_t)NP * D + NP + gp_linv_doubles(NP) + (size_t)warps * 64 +
+  return sizeof(double) * ((size_t)64 * (k_in_smem ? 1 : ts) + (size_t)NP * D + NP + gp_linv_doubles(NP) + (size_t)warps * 64 +
                            (k_in_smem ? (size_t)warps * (NP >> 2) * 32 : 0));
 }
 
@@ -537,13 +539,25 @@ static int launch_posterior_mma_dk(int B, int nmax, int ns, const double* gp_sta
   // small blobs: 4-warp CTAs (many resident CTAs); large blobs (n ~ 100: 50 KB): 8 warps share one copy
   const int warps = sizeof(double) * ((size_t)NP * cand.D + NP + gp_linv_doubles(NP)) > 20 * 1024 ? 8 : 4;
   const bool reg_k = nrb >= 1 && nrb <= 4;
-  const size_t smem = posterior_mma_smem_bytes(ns, cand.D, warps, !reg_k);
+  const char* ts_env = getenv("MBO_GP_TS");
+  const int ts = ts_env && atoi(ts_env) == 32 ? 32 : 8;      // 8 measured as fast as 32 (n = 30: 1.71 vs 1.73 ms) at a quarter of the table
+  const size_t smem = posterior_mma_smem_bytes(ns, cand.D, warps, !reg_k, ts);
   auto kern = gp_posterior_mma_kernel<DT, KID, 0>;
-  if (nrb == 1) kern = gp_posterior_mma_kernel<DT, KID, 1>;
-  else if (nrb == 2) kern = gp_posterior_mma_kernel<DT, KID, 2>;
-  else if (nrb == 3) kern = gp_posterior_mma_kernel<DT, KID, 3>;
-  else if (nrb == 4) kern = gp_posterior_mma_kernel<DT, KID, 4>;
+  if (ts == 32) {
+    if (nrb == 1) kern = gp_posterior_mma_kernel<DT, KID, 1, 32>;
+    else if (nrb == 2) kern = gp_posterior_mma_kernel<DT, KID, 2, 32>;
+    else if (nrb == 3) kern = gp_posterior_mma_kernel<DT, KID, 3, 32>;
+    else if (nrb == 4) kern = gp_posterior_mma_kernel<DT, KID, 4, 32>;
+  } else {
+    if (nrb == 1) kern = gp_posterior_mma_kernel<DT, KID, 1, 8>;
+    else if (nrb == 2) kern = gp_posterior_mma_kernel<DT, KID, 2, 8>;
+    else if (nrb == 3) kern = gp_posterior_mma_kernel<DT, KID, 3, 8>;
+    else if (nrb == 4) kern = gp_posterior_mma_kernel<DT, KID, 4, 8>;
+  }
   MBO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // same shared-memory carve-out as the tensor-core MLP kernel (maximum): an SM has ONE L1 / shared split at a time, so
+  // a kernel that prefers another split cannot start on an SM where an MLP CTA of another stream is resident
+  MBO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
   const int TILE = warps * 32;
   const int tiles = (cand.M + TILE - 1) / TILE;
   int ctas = tiles;

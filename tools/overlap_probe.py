@@ -22,7 +22,8 @@ mA = torch.randn((B, M), device=dev); sA = torch.rand((B, M), device=dev); lgA =
 mB = torch.empty((B, M), device=dev); sB = torch.empty((B, M), device=dev)
 codes = [0, 1, 2, 3, 4, 12, 13]
 s1, s2 = torch.cuda.Stream(), torch.cuda.Stream(priority=-1)
-def mlp(): ops.af_logits(pol, codes, cs, mA, sA, epi, B, mode=1, logits=lgA)
+MODE = {"tf32": 1, "bf16x3": 2, "fp16": 3}[sys.argv[1] if len(sys.argv) > 1 else "fp16"]
+def mlp(): ops.af_logits(pol, codes, cs, mA, sA, epi, B, mode=MODE, logits=lgA)
 def gp(): ops.gp_posterior(st, T, cs, B, out_dtype=torch.float32, n_active_max=n, mean=mB, std=sB)
 def timed(fn, reps=5):
     fn(); torch.cuda.synchronize()
@@ -39,5 +40,14 @@ def both():
     e1, e2 = torch.cuda.Event(), torch.cuda.Event()
     e1.record(s1); e2.record(s2)
     torch.cuda.current_stream().wait_event(e1); torch.cuda.current_stream().wait_event(e2)
-print("mlp alone %.3f ms, gp alone %.3f ms, both concurrently %.3f ms" % (timed(mlp), timed(gp), timed(both)))
+def both_gp_first():
+    ev = torch.cuda.Event(); ev.record()
+    s1.wait_event(ev); s2.wait_event(ev)
+    with torch.cuda.stream(s1): gp()
+    with torch.cuda.stream(s2): mlp()
+    e1, e2 = torch.cuda.Event(), torch.cuda.Event()
+    e1.record(s1); e2.record(s2)
+    torch.cuda.current_stream().wait_event(e1); torch.cuda.current_stream().wait_event(e2)
+print("MBO_GP_TS=%s mode %d: mlp alone %.3f ms, gp alone %.3f ms, both (mlp first) %.3f ms, both (gp first) %.3f ms" %
+      (os.environ.get("MBO_GP_TS"), MODE, timed(mlp), timed(gp), timed(both), timed(both_gp_first)))
 pol.check()
