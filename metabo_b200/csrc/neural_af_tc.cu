@@ -623,7 +623,11 @@ struct TcTopk {
 };
 
 template <int MODE, bool FUSE, int K0S>     // K0S: K = 8 slices of layer 0 (1: F + 1 <= 8, 2: F + 1 <= 16)
-__global__ void __launch_bounds__(FUSE ? TC_THREADS_FUSED : TC_THREADS, 1)
+// 104 registers (no spills): the register file is partitioned per SM sub-partition (4 x 16 384); this CTA puts 4 warps on
+// two of them, and at 118 registers (15 104 of 16 384) no warp of another kernel fits there -- which is why the fp64 GP
+// kernel of another stream never co-resided with it (tools/micro/coresidency.cu).  At 104 a GP warp (80 registers) fits
+// on every sub-partition, next to the 219 KB of shared memory this CTA holds.
+__global__ void __maxnreg__(FUSE ? 112 : 104)
 neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candidates cand, int B,
                     int tiles_per_episode, const float* __restrict__ mean, const float* __restrict__ std_,
                     const float* __restrict__ epi, float* __restrict__ logits, int* __restrict__ err_flag, int debug_noload,

@@ -21,7 +21,7 @@ st, _ = ops.gp_fit(torch.full((B,), n, dtype=torch.int32, device=dev), X, Y, tor
 mA = torch.randn((B, M), device=dev); sA = torch.rand((B, M), device=dev); lgA = torch.empty((B, M), device=dev)
 mB = torch.empty((B, M), device=dev); sB = torch.empty((B, M), device=dev)
 codes = [0, 1, 2, 3, 4, 12, 13]
-s1, s2 = torch.cuda.Stream(), torch.cuda.Stream(priority=-1)
+s1, s2 = torch.cuda.Stream(), (torch.cuda.Stream(priority=-1) if os.environ.get('PROBE_PRIO', '1') == '1' else torch.cuda.Stream())
 MODE = {"tf32": 1, "bf16x3": 2, "fp16": 3}[sys.argv[1] if len(sys.argv) > 1 else "fp16"]
 def mlp(): ops.af_logits(pol, codes, cs, mA, sA, epi, B, mode=MODE, logits=lgA)
 def gp(): ops.gp_posterior(st, T, cs, B, out_dtype=torch.float32, n_active_max=n, mean=mB, std=sB)
@@ -51,3 +51,26 @@ def both_gp_first():
 print("MBO_GP_TS=%s mode %d: mlp alone %.3f ms, gp alone %.3f ms, both (mlp first) %.3f ms, both (gp first) %.3f ms" %
       (os.environ.get("MBO_GP_TS"), MODE, timed(mlp), timed(gp), timed(both), timed(both_gp_first)))
 pol.check()
+
+
+def detail(first):
+    """per-stream end times of one concurrent run (ms after the common start)"""
+    torch.cuda.synchronize()
+    ev = torch.cuda.Event(enable_timing=True); ev.record()
+    s1.wait_event(ev); s2.wait_event(ev)
+    em, eg = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    def run_mlp():
+        with torch.cuda.stream(s2):
+            mlp(); em.record(s2)
+    def run_gp():
+        with torch.cuda.stream(s1):
+            gp(); eg.record(s1)
+    (run_mlp(), run_gp()) if first == "mlp" else (run_gp(), run_mlp())
+    torch.cuda.synchronize()
+    return ev.elapsed_time(em), ev.elapsed_time(eg)
+
+
+for first in ("mlp", "gp"):
+    for _ in range(2):
+        a, b_ = detail(first)
+    print("%s launched first: mlp ends at %.3f ms, gp ends at %.3f ms" % (first, a, b_))

@@ -79,28 +79,38 @@ def main():
         run_eval("C4 T=100 observations, M=2000, 1000 episodes", g100, "weights_gps_1161.npz", 10, 1000, "fp32", 2000)
         g16k = dict(GPS, T=100, cardinality_domain=16000)
         run_eval("C4 T=100, M=16000, 200 episodes", g16k, "weights_gps_1161.npz", 10, 200, "fp32", 16000)
-    for backend, prec in ((("native", "highest"), ("autograd", "highest"), ("autograd", "high")) if "C3" in which else ()):
-        spec = dict(BRA, f_opts={"bound_translation": 0.1, "bound_scaling": 0.1, "M": 50}, reward_transformation="neg_log10")
+    for cfg in ((["C3"] if "C3" in which else []) + (["C4train"] if "C4" in which else [])):
+        import tempfile
+        if cfg == "C3":
+            spec = dict(BRA, f_opts={"bound_translation": 0.1, "bound_scaling": 0.1, "M": 50}, reward_transformation="neg_log10")
+            popts = {"activations": "relu", "arch_spec": [200] * 4, "use_value_network": True, "t_idx": -2, "T_idx": -1,
+                     "arch_spec_value": [200] * 4, "mlp_mode": "fp16"}
+            desc = ("C3 train_metabo_branin: 6 PPO iterations (batch 1200 = 40 episodes, 80 optimiser steps each, minibatch 60x966 "
+                    "candidates; policy / value / Adam on the tcgen05 update kernels)")
+            ref = {"rollout_sps": 151.1, "t_optim_s": 2.05, "e2e_steps_per_s": 78.4, "source": "stats_1635"}
+        else:
+            spec = dict(GPS, env_id="MetaBO-GP-train-v0")
+            popts = {"activations": "relu", "arch_spec": [20, 20], "use_value_network": True, "arch_spec_value": [20, 20],
+                     "exclude_t_from_policy": True, "exclude_T_from_policy": True, "t_idx": -2, "T_idx": -1, "mlp_mode": "fp32"}
+            desc = ("C4 train_metabo_gps: 6 PPO iterations (batch 1200, minibatch 60x2000 candidates, 4->20->20->1 policy and "
+                    "2->20->20->1 value net on the CUDA-core update kernels mbo_ppo_*_simt)")
+            ref = {"rollout_sps": 397.5, "t_optim_s": 4.33, "e2e_steps_per_s": 149.7, "source": "stats_1161"}
         gym.register(id=spec["env_id"], entry_point="metabo.environment.metabo_gym:MetaBO", max_episode_steps=30, kwargs=spec)
         params = {"batch_size": 1200, "max_steps": 6 * 1200, "minibatch_size": 60, "n_epochs": 4, "lr": 1e-4, "epsilon": 0.15,
                   "value_coeff": 1.0, "ent_coeff": 0.01, "gamma": 0.98, "lambda": 0.98, "loss_type": "GAElam", "normalize_advs": True,
-                  "n_workers": 10, "env_id": spec["env_id"], "seed": 0, "env_seeds": list(range(10)), "mlp_mode": "fp16", "update_matmul_precision": prec, "update_backend": backend,
-                  "policy_options": {"activations": "relu", "arch_spec": [200] * 4, "use_value_network": True, "t_idx": -2, "T_idx": -1,
-                                     "arch_spec_value": [200] * 4, "mlp_mode": "fp16"}}
-        import tempfile
+                  "n_workers": 10, "env_id": spec["env_id"], "seed": 0, "env_seeds": list(range(10)), "mlp_mode": popts["mlp_mode"],
+                  "policy_options": popts}
         lp = os.path.join(tempfile.mkdtemp(), "log")
         ppo = PPO(policy_fn=lambda o, a, d: NeuralAF(o, a, d, options=params["policy_options"]), params=params, logpath=lp,
                   save_interval=10, verbose=True)
         t0 = time.time(); ppo.train(); wall = time.time() - t0
         st = ppo.stats
-        print(json.dumps({"update_backend": ppo.update_backend, "update_matmul_precision": prec, "steady_state_e2e_steps_per_s": 1200 / (st["batch_stats"]["t_batch"] + st["t_optim"]),
-                          "config": "C3 train_metabo_branin: 6 PPO iterations (batch 1200 = 40 episodes, 80 optimiser steps each, "
-                          "minibatch 60x966 candidates; update_backend native = hand-written policy / value / Adam kernels, autograd = torch, "
-                          "update_matmul_precision applies to autograd only)", "wall_s": wall, "t_batch_s": st["batch_stats"]["t_batch"],
+        print(json.dumps({"config": desc, "update_kernels": type(ppo._pg).__name__,
+                          "steady_state_e2e_steps_per_s": 1200 / (st["batch_stats"]["t_batch"] + st["t_optim"]),
+                          "wall_s": wall, "t_batch_s": st["batch_stats"]["t_batch"],
                           "rollout_sps": st["batch_stats"]["sps"], "t_optim_s": st["t_optim"],
                           "e2e_steps_per_s": st["n_timesteps"] / st["t_train"], "avg_step_rews": list(map(float, st["avg_step_rews"])),
-                          "reference_stats_1635": {"rollout_sps": 151.1, "t_optim_s": 2.05, "e2e_steps_per_s": 78.4}}), flush=True)
-
+                          "reference_shipped_stats": ref}), flush=True)
 
 if __name__ == "__main__":
     main()
