@@ -541,8 +541,13 @@ def main():
                 "format_ceiling_frac": {"fp16": 1.0, "tf32": 0.5, "bf16x3": 1.0 / 3.0, "fp32": None}[args.mlp]}
         if gp_big:
             gdur = float(np.mean(gp_big)) / 1e3
-            roof["gp_posterior"] = {"avg_launch_ms": gdur * 1e3, "precision": args.gp,
-                                    "achieved_tflops": B * HM3["k"] * HM3["N_LS"] * gp_flops(n, D) / gdur / 1e12}
+            g_ach = B * HM3["k"] * HM3["N_LS"] * gp_flops(n, D) / gdur / 1e12
+            fp64_peak = 148 * 64 * 2 * (peaks.get("sm_max_mhz", 1965.0) * 1e6) / 1e12      # derived: not in MEASURED_PEAKS
+            roof["gp_posterior"] = {"kernel": "GP posterior (fp64, DMMA triangular mat-vec), B x 10000 local-grid candidates",
+                                    "avg_launch_ms": gdur * 1e3, "precision": args.gp, "achieved_tflops": g_ach,
+                                    "bound": "fp64 pipe (DFMA and DMMA share it: tools/micro/dmma_bw.cu)",
+                                    "peak_tflops_derived": fp64_peak, "frac": g_ach / fp64_peak,
+                                    "algorithmic_flops_per_candidate": gp_flops(n, D)}
 
     # ---- e2e arm: host buffers -> engine -> host actions ----
     hX = X.cpu().pin_memory(); hY = Y.cpu().pin_memory(); hn = nvec.cpu().pin_memory()

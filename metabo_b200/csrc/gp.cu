@@ -570,9 +570,12 @@ static int launch_posterior_mma_dk(int B, int nmax, int ns, const double* gp_sta
 template <int KID>
 static int launch_posterior_mma_k(int B, int nmax, int ns, const double* gp_state, const mbo_candidates& cand, void* mean, void* std_,
                                   int out_is_f32, cudaStream_t s) {
-  // the dimensions of the shipped experiments (Branin 2, Hartmann-3 / GP samples 3) get their own instantiation
+  // the dimensions of the shipped experiments (Branin 2, Hartmann-3 / GP samples 3) and of the sweep (4, 6) get their
+  // own instantiation; everything else runs the generic one (distance loops predicated to MBO_MAX_D)
   if (cand.D == 2) return launch_posterior_mma_dk<2, KID>(B, nmax, ns, gp_state, cand, mean, std_, out_is_f32, s);
   if (cand.D == 3) return launch_posterior_mma_dk<3, KID>(B, nmax, ns, gp_state, cand, mean, std_, out_is_f32, s);
+  if (cand.D == 4) return launch_posterior_mma_dk<4, KID>(B, nmax, ns, gp_state, cand, mean, std_, out_is_f32, s);
+  if (cand.D == 6) return launch_posterior_mma_dk<6, KID>(B, nmax, ns, gp_state, cand, mean, std_, out_is_f32, s);
   return launch_posterior_mma_dk<0, KID>(B, nmax, ns, gp_state, cand, mean, std_, out_is_f32, s);
 }
 
