@@ -439,11 +439,12 @@ gp_posterior_mma_kernel(int nmax, const double* __restrict__ gp_state, mbo_candi
       double K[NRB_T ? 2 * NRB_T : 1];
       constexpr int NKB_U = NRB_T ? 2 * NRB_T : 0;
       if (NRB_T) {
+        constexpr int GX = (NKB_U % 4 == 0) ? 4 : 2;           // kernel values per step (interleaved exp chains)
 #pragma unroll
-        for (int kb0 = 0; kb0 < NKB_U; kb0 += 2) {          // two kernel values at a time (interleaved exp chains)
-          double r2v[2], kv[2];
+        for (int kb0 = 0; kb0 < NKB_U; kb0 += GX) {
+          double r2v[GX], kv[GX];
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
+          for (int u = 0; u < GX; ++u) {
             const int jj = max(min(4 * (kb0 + u) + t, n - 1), 0);
             double r2 = 0.0;
 #pragma unroll
@@ -451,9 +452,9 @@ gp_posterior_mma_kernel(int nmax, const double* __restrict__ gp_state, mbo_candi
               if (DT || d < D) { const double dd = xs[d] - sXs[jj * D + d]; r2 = fma(dd, dd, r2); }
             r2v[u] = r2;
           }
-          kernel_of_r2_xn<2, TS>(KID, var, r2v, kv, tab);
+          kernel_of_r2_xn<GX, TS>(KID, var, r2v, kv, tab);
 #pragma unroll
-          for (int u = 0; u < 2; ++u) K[kb0 + u] = (4 * (kb0 + u) + t < n) ? kv[u] : 0.0;
+          for (int u = 0; u < GX; ++u) K[kb0 + u] = (4 * (kb0 + u) + t < n) ? kv[u] : 0.0;
         }
       } else {
         for (int kb0 = 0; kb0 < NKB; kb0 += 2) {

@@ -231,9 +231,17 @@ class PPO:
         self._pg_grads = ([w for w, _ in views[:k]], [b for _, b in views[:k]])
         self._vg_grads = ([w for w, _ in views[k:]], [b for _, b in views[k:]])
         if self.world > 1 and self.dp_native():
-            # the ONE collective of the path: the flat gradient is pulled from every rank's slot over NVLink inside the
-            # Adam kernel (mbo_comm_allreduce_adam); collective call (every rank gets here in its first optimiser step)
-            self.comm = ops.Comm.from_process_group(4 * max(n, 1024), self.device)
+            self._ensure_comm(4 * n)
+
+    def _ensure_comm(self, nbytes):
+        """The ONE collective of the path: the flat gradient is pulled from every rank's slot over NVLink inside the Adam
+        kernel (mbo_comm_allreduce_adam).  Creating the exchange object is itself collective (every rank gets here at the
+        same point of its first optimiser step / epoch); the slot also carries the per-epoch advantage moments."""
+        need = max(int(nbytes), 4096)
+        if self.comm is None or self.comm.slot_bytes < need:
+            self.comm = ops.Comm.from_process_group(need, self.device)
+            self._ep = None                    # captured graphs hold the old regions' pointers
+        if self._flat_grads is not None:
             self.optimizer.set_comm(self.comm, self._flat_grads)
 
     def dp_native(self):
@@ -441,6 +449,7 @@ class PPO:
                 self._value_grad_op(E_max)
             if self._pg_grads is None:
                 self._alloc_native_grads()                                   # collective: creates the comm
+            self._ensure_comm(max(4 * self._flat_grads.numel(), 24 * len(bounds)))    # the slot also carries [n_steps, 3] fp64 moments
             for a, b in bounds:
                 self._minibatch_buffers(b - a, static["states"])
             if self._loss4 is None:
