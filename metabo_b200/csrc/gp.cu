@@ -367,7 +367,7 @@ __device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, doubl
 // of ~8), (iii) candidates are prepared once per lane (load + X / lengthscale) and handed to the pass that needs
 // them by shuffles, (iv) the per-candidate epilogue (clip, sqrt, store) runs once per lane after the four passes.
 template <int DT, int KID, int NRB_T, int TSV = 32>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(NRB_T ? 128 : 256, NRB_T ? 8 : 1)      // NRB_T: 64 registers (no spills) -> 8 CTAs / SM
 gp_posterior_mma_kernel(int nmax, const double* __restrict__ gp_state, mbo_candidates cand, int tiles_per_episode,
                         int ctas_per_episode, void* __restrict__ mean_out, void* __restrict__ std_out, int out_is_f32) {
   extern __shared__ __align__(16) unsigned char smraw[];

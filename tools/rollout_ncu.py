@@ -18,7 +18,7 @@ opts = {"activations": "relu", "arch_spec": [200] * 4, "use_value_network": True
 nb = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 br = BatchRecorder(size=64 * 16 * 30, env_id=spec["env_id"], env_seeds=list(range(64)),
                    policy_fn=lambda o, a, d: NeuralAF(o, a, d, options=opts), n_workers=64,
-                   deterministic=False, store_states=False, mlp_mode="fp16", device=torch.device("cuda:0"))
+                   deterministic=False, store_states=True, mlp_mode="fp16", device=torch.device("cuda:0"))
 for i in range(nb):
     t = br.record_batch(0.98, 0.98)
     print("batch", i, "t_batch %.4f s  %.0f env-steps/s" % (t, 30720 / t), flush=True)
