@@ -214,6 +214,36 @@ class MetaBO(gym.Env):
         self.optimize_AF()
         return self.get_state(self.xi_t), reward, bool(done), {}
 
+    def get_random_sampling_reward(self):
+        """metabo_gym.py:754-773: one episode of uniformly random queries (the "Random" baseline of evaluate.py:154-160),
+        drawn from the env's own RandomState in the reference's order; objective evaluated on the device."""
+        v = self._vec
+        v.t = 0
+        fb, hyper = v.sampler.draw(v.rngs)
+        if v.fb is None:
+            v.fb = fb
+        else:
+            v.fb.copy_from(fb)
+        v.engine.n.zero_()
+        v.engine.n_active_max = 0
+        v.best.fill_(-float("inf"))
+        rewards = []
+        for t in range(v.T):
+            if self.do_local_af_opt:
+                x = self.rng.rand(1, self.D)
+            else:
+                xi = v.engine.xi_table
+                x = xi[int(self.rng.choice(np.arange(self.cardinality_xi_t)))].cpu().numpy().reshape(1, -1)
+            cs = ops.CandidateSet(self.D, tail=torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64), device=v.dev))
+            n_init, v.n_init_samples = v.n_init_samples, 0           # random queries replace the initial design too
+            out = v._step_device(t, True, False, {"cand": cs}, [0])
+            v.n_init_samples = n_init
+            v.t = t + 1
+            rewards.append(float(out["reward"][0]))
+        self._host_views()
+        assert self.is_terminal()
+        return rewards
+
     def optimize_AF(self):
         """metabo_gym.py:615-622"""
         if self.do_local_af_opt:

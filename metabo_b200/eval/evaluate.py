@@ -2,8 +2,9 @@
 NeuralAF from the reference's checkpoint files (params_N / weights_N / stats_N, shipped iclr2020
 runs included), plays T * n_episodes steps through the GPU BatchRecorder and stores the same
 `Result` pickle.  Baselines: EI / GP-UCB / PI run as closed-form epilogues of the same GPU AF rounds, TAF-ME / TAF-RANKING
-(policies.py:310-468) through the host-driven env with their 50 source GPs on the batched GP kernel; the data-file
-baselines EPS-GREEDY / GMM-UCB and Random are outside the scope and raise."""
+(policies.py:310-468) through the host-driven env with their 50 source GPs on the batched GP kernel; "Random" is
+`MetaBO.get_random_sampling_reward` (evaluate.py:154-160); the data-file baselines EPS-GREEDY / GMM-UCB need the authors'
+data files, are outside the scope and raise."""
 import os
 import pickle as pkl
 from collections import namedtuple
@@ -36,9 +37,9 @@ def load_metabo_policy(logpath, load_iter, env, device, deterministic):
 def eval_experiment(eval_spec):
     env_id = eval_spec["env_id"]
     policy = eval_spec["policy"]
-    if policy not in ("MetaBO", "EI", "GP-UCB", "PI", "TAF-ME", "TAF-RANKING"):
-        raise ValueError("Unknown policy!" if policy not in ("EPS-GREEDY", "GMM-UCB", "Random")
-                         else "baseline '%s' is outside the GPU hot path" % policy)
+    if policy not in ("MetaBO", "EI", "GP-UCB", "PI", "TAF-ME", "TAF-RANKING", "Random"):
+        raise ValueError("Unknown policy!" if policy not in ("EPS-GREEDY", "GMM-UCB")
+                         else "baseline '%s' needs the authors' data files and is outside the scope" % policy)
     logpath, savepath = eval_spec["logpath"], eval_spec["savepath"]
     n_workers, n_episodes, T = eval_spec["n_workers"], eval_spec["n_episodes"], eval_spec["T"]
     assert n_episodes % n_workers == 0
@@ -56,7 +57,8 @@ def eval_experiment(eval_spec):
                             options=policy_specs["policy_options"])
     else:
         # closed-form baselines on the same GP kernels (evaluate.py:102-118)
-        policy_specs = eval_spec["policy_specs"]
+        policy_specs = eval_spec.get("policy_specs", {})
+        policy_fn = None
         if policy == "TAF-ME":
             policy_fn = lambda *_: TAF(datafile=policy_specs["TAF_datafile"], mode="me")               # evaluate.py:112-113
         elif policy == "TAF-RANKING":
@@ -65,18 +67,27 @@ def eval_experiment(eval_spec):
             policy_fn = lambda *_: EI(feature_order=feature_order)
         elif policy == "PI":
             policy_fn = lambda *_: PI(feature_order=feature_order, xi=policy_specs["xi"])
-        else:
+        elif policy == "GP-UCB":
             policy_fn = lambda *_: UCB(feature_order=feature_order, kappa=policy_specs["kappa"], D=env_specs["D"],
                                        delta=policy_specs["delta"])
 
-    br = BatchRecorder(size=T * n_episodes, env_id=env_id, env_seeds=list(env_seeds), policy_fn=policy_fn,
-                       n_workers=n_workers, deterministic=deterministic, store_states=False)
-    if policy == "MetaBO":
-        pi, _, _ = load_metabo_policy(logpath, load_iter, br, "cpu", deterministic)
-        br.set_worker_weights(pi=pi)
-    br.record_batch(gamma=1.0, lam=1.0)
-    rewards = tuple(t.reward for t in br.memory)
-    br.cleanup()
+    if policy == "Random":                       # evaluate.py:154-160
+        env = gym.make(env_id)
+        env.seed(eval_spec["env_seed_offset"])
+        rewards = []
+        for _ in range(n_episodes):
+            rewards = rewards + env.unwrapped.get_random_sampling_reward()
+        env.close()
+        rewards = tuple(rewards)
+    else:
+        br = BatchRecorder(size=T * n_episodes, env_id=env_id, env_seeds=list(env_seeds), policy_fn=policy_fn,
+                           n_workers=n_workers, deterministic=deterministic, store_states=False)
+        if policy == "MetaBO":
+            pi, _, _ = load_metabo_policy(logpath, load_iter, br, "cpu", deterministic)
+            br.set_worker_weights(pi=pi)
+        br.record_batch(gamma=1.0, lam=1.0)
+        rewards = tuple(t.reward for t in br.memory)
+        br.cleanup()
     with open(os.path.join(savepath, "000_eval_overview_{}.txt".format(policy)), "w") as f:
         print("Evaluation timestamp: {}\nEnvironment-ID: {}\nEnvironment-seeds:\n{}".format(
             datetime.strftime(datetime.now(), "%Y-%m-%d-%H-%M-%S"), env_id, env_seeds), file=f)

@@ -118,3 +118,28 @@ def test_taf_episode_and_eval_experiment(tmp_path):
     r = np.array(res.rewards).reshape(4, 6)
     assert np.all(np.diff(r, axis=1) <= 1e-12) and np.all(r[:, -1] <= r[:, 0])
     assert os.path.exists(tmp_path / "eval" / "result_TAF-ME")
+
+
+def test_random_baseline_matches_reference_rng_order(tmp_path):
+    """"Random" policy (evaluate.py:154-160, metabo_gym.py:754-773): per episode the env RandomState is consumed for the
+    objective draw and then for T uniform queries; the simple regret of every step equals the oracle's on the same
+    numpy stream."""
+    from metabo_b200 import gym_compat as gym
+    from metabo_b200.eval.evaluate import eval_experiment
+    spec = dict(TAF_SPEC, pass_X_to_pi=False, env_id="MetaBO-BRA-RANDOM-v0", T=7)
+    gym.register(id=spec["env_id"], entry_point="metabo.environment.metabo_gym:MetaBO", max_episode_steps=7, kwargs=spec)
+    res = eval_experiment({"env_id": spec["env_id"], "env_seed_offset": 100, "policy": "Random", "logpath": None,
+                           "load_iter": None, "deterministic": True, "savepath": str(tmp_path / "eval"),
+                           "n_workers": 1, "n_episodes": 3, "T": 7})
+    r = np.array(res.rewards).reshape(3, 7)
+    rng = np.random.RandomState(); rng.seed(100)
+    for ep in range(3):
+        t = rng.uniform(low=-0.1, high=0.1, size=(1, 2))
+        s = rng.uniform(low=0.9, high=1.1)
+        y_max = float(O.bra_max(t[0], s)[0]) if hasattr(O, "bra_max") else None
+        best = -np.inf
+        for k in range(7):
+            x = rng.rand(1, 2)
+            best = max(best, float(O.bra_var(x, t[0], s)[0, 0]))
+            assert abs(r[ep, k] - (y_max - best)) <= 1e-9 * max(1.0, abs(y_max)), (ep, k)
+    assert os.path.exists(tmp_path / "eval" / "result_Random")
