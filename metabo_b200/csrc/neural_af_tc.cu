@@ -327,11 +327,14 @@ __device__ __forceinline__ float f16_bits_to_float(uint32_t h) {
   return __half2float(__ushort_as_half((unsigned short)h));
 }
 
-__global__ void tc_pack_kernel(PackArgs a, unsigned char* __restrict__ out) {
+// bf16x3_only: pack just what the bf16x3 mode reads (layer 0, the bf16 hi / lo hidden stages, the fp32 tail) -- the PPO
+// update re-packs the current weights on every optimiser step and needs neither the tf32 nor the fp16 images
+__global__ void tc_pack_kernel(PackArgs a, unsigned char* __restrict__ out, int bf16x3_only) {
   const PackLayout pl = pack_layout();
   const size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // 32-bit word index
   const size_t byte = w * 4;
   if (byte >= pl.total) return;
+  if (bf16x3_only && ((byte >= pl.off_tf32 && byte < pl.off_bf16) || byte >= pl.off_w0h)) return;
   uint32_t* dst = (uint32_t*)(out + byte);
   const int F = a.F, H = a.H;
   if (byte < pl.off_tf32) {
@@ -474,7 +477,7 @@ int tc_pack_weights(mbo_policy* p, cudaStream_t s) {
   size_t words = pl.total / 4;
   tc_scale_kernel<<<1, 256, 0, s>>>(a, (int*)((unsigned char*)p->d_tc + pl.off_scale));
   MBO_LAUNCH_CHECK();
-  tc_pack_kernel<<<(unsigned)((words + 255) / 256), 256, 0, s>>>(a, (unsigned char*)p->d_tc);
+  tc_pack_kernel<<<(unsigned)((words + 255) / 256), 256, 0, s>>>(a, (unsigned char*)p->d_tc, 0);
   MBO_LAUNCH_CHECK();
   p->tc_ready = 1;
   p->tc_f16 = H + 2 <= TC_N;     // two spare K columns for the bias
@@ -502,14 +505,15 @@ struct TcFeat {
 // that is hot anyway.  The chip-wide L2 -> SM rate (~6 300 B/clk, 43 B/clk per SM) is what bounds a kernel that
 // re-streams all weights for every 128-candidate tile (tf32 mode: 520 KB per tile = 12 200 clk); and a dedicated
 // producer warp whose loop body runs once per ~900 cycles pays an instruction-cache miss on every pass.
-template <int MODE, bool FUSE = false, int K0S = 2>
+constexpr int STG_LD = 36;   // STORE staging tile: 32 fp32 columns per row + 4 of padding (float4 rows stay conflict-free)
+template <int MODE, bool FUSE = false, int K0S = 2, bool STORE = false>
 struct TcSmem {
   using C = ModeCfg<MODE>;
   static constexpr bool RES = MODE == MBO_MLP_FP16 && !FUSE;
   static constexpr int NRES1 = K0S == 1 ? 2 : 1;                      // resident leading stages of layers 1 and 3
   static constexpr int NSLOT = C::STAGES_PER_LAYER - NRES1;           // time-shared slots (the last one is half a stage)
   static constexpr int NA = NSLOT - 3;                                // slots [0, NA) arrive with the first refill copy, the rest with the second
-  static constexpr int NS = RES ? NSLOT : (FUSE ? C::NSTAGE_FUSED : C::NSTAGE);
+  static constexpr int NS = RES ? NSLOT : ((FUSE || STORE) ? C::NSTAGE_FUSED : C::NSTAGE);   // STORE trades three stages for its staging tiles
   static constexpr size_t SLOT_BYTES = RES ? (size_t)(NSLOT - 1) * C::STAGE_BYTES + C::STAGE_BYTES / 2 : 0;
   static constexpr size_t L2_BYTES = (size_t)6 * C::STAGE_BYTES + C::STAGE_BYTES / 2;
   static constexpr size_t RES_BYTES = RES ? (size_t)2 * NRES1 * C::STAGE_BYTES + L2_BYTES : 0;   // [L1 | L2 | L3]
@@ -525,7 +529,8 @@ struct TcSmem {
   static constexpr size_t off_gp = off_part + sizeof(float) * TC_M;             // fused GP: episode blob + mu/sd hand-off
   static constexpr size_t off_musd = off_gp + (FUSE ? sizeof(double) * GPB_DOUBLES : 0);
   static constexpr size_t off_ks = off_musd + (FUSE ? sizeof(float) * 4 * TC_M : 0);        // k* scratch [32][128] fp64
-  static constexpr size_t total = off_ks + (FUSE ? sizeof(double) * GP_NP * TC_M : 0);
+  static constexpr size_t off_stg = off_ks + (FUSE ? sizeof(double) * GP_NP * TC_M : 0);   // STORE: [8 warps][32 rows][STG_LD] fp32
+  static constexpr size_t total = off_stg + (STORE ? sizeof(float) * 8 * 32 * STG_LD : 0);
 };
 
 // per-mode conversion of one accumulator chunk into the next layer's A operand (in registers)
@@ -622,7 +627,16 @@ struct TcTopk {
   int32_t* part_idx;
 };
 
-template <int MODE, bool FUSE, int K0S>     // K0S: K = 8 slices of layer 0 (1: F + 1 <= 8, 2: F + 1 <= 16)
+// STORE (PPO update forward, ppo.py:146-156): besides the logits the kernel writes what the backward needs -- the four
+// post-ReLU activations as plain fp32 rows [rows][208] (row = episode * M + candidate; column H is a ones column: the
+// wgrad GEMMs take their bias gradient from it) and the ReLU decisions of h1..h3 as bit words [rows][8].
+struct TcStore {
+  float* h[4];
+  uint32_t* bits[3];
+  int H;
+};
+
+template <int MODE, bool FUSE, int K0S, bool STORE = false>     // K0S: K = 8 slices of layer 0 (1: F + 1 <= 8, 2: F + 1 <= 16)
 // Register budget: the SM's register file is four 16 K sub-partition files and this CTA puts 4 of its 14 warps on two of
 // them, so above 104 registers no warp of another kernel can co-reside (tools/micro/coresidency.cu).  Co-residency with
 // the fp64 GP kernel was measured at 104 registers and does not pay (both kernels live on the shared-memory data path,
@@ -631,9 +645,10 @@ __global__ void __launch_bounds__(FUSE ? TC_THREADS_FUSED : TC_THREADS, 1)
 neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candidates cand, int B,
                     int tiles_per_episode, const float* __restrict__ mean, const float* __restrict__ std_,
                     const float* __restrict__ epi, float* __restrict__ logits, int* __restrict__ err_flag, int debug_noload,
-                    GpFuse gp, TcTopk tk) {
+                    GpFuse gp, TcTopk tk, TcStore st) {
+  static_assert(!STORE || (MODE == MBO_MLP_BF16X3 && !FUSE), "STORE: bf16x3 (fp32-class) forward of the PPO update only");
   using C = ModeCfg<MODE>;
-  using SM = TcSmem<MODE, FUSE, K0S>;
+  using SM = TcSmem<MODE, FUSE, K0S, STORE>;
   constexpr int NTHREADS = FUSE ? TC_THREADS_FUSED : TC_THREADS;
   constexpr int NS = SM::NS;                      // ring depth
   constexpr bool RES = SM::RES;                   // fp16: even weight stages resident, odd ones streamed
@@ -1057,6 +1072,46 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
     // (loads double-buffered, loop rolled over pairs of chunks); every finished chunk is handed to the MMA warp
     // through its own mbarrier.
     constexpr int MAXI = (C::NCHUNK + 1) / 2;
+    // STORE: a finished block of <= 32 activation columns goes through this warp's staging tile so that global memory
+    // sees whole 128-byte row segments (thread = row on the TMEM side, 8 lanes = one row segment on the HBM side; a
+    // thread storing its own row would touch 32 different lines per instruction: measured 150 instead of 53 us per call)
+    float* const stg = (float*)(smem + SM::off_stg) + (STORE ? warp * 32 * STG_LD : 0);
+    float* st_base = nullptr;           // first row of this warp's 32 rows in the activation being stored
+    uint32_t* st_bits = nullptr;        // this thread's row of ReLU bit words (null: padding row / no words for this layer)
+    int st_nrows = 0;                   // rows of this warp that exist (ragged last tile of an episode)
+    auto st_tile = [&](int t, float* h, uint32_t* bits) {
+      const int tile_s = (int)blockIdx.x + t * (int)gridDim.x;
+      const int b_s = tile_s / tiles_per_episode;
+      const int m0 = (tile_s - b_s * tiles_per_episode) * TC_M + quad * 32;
+      const size_t r0 = (size_t)b_s * cand.M + m0;
+      st_nrows = min(max(cand.M - m0, 0), 32);
+      st_base = h + r0 * TC_N;
+      st_bits = (bits && lane < st_nrows) ? bits + (r0 + lane) * 8 : nullptr;
+    };
+    auto st_block = [&](auto&& get, int n4, int gcol) {      // get(j) = columns gcol + 4 j .. of this thread's row
+      float4* srow = reinterpret_cast<float4*>(stg + lane * STG_LD);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (j < n4) {
+          float4 v = get(j);
+          const int col0 = gcol + 4 * j;
+          const int d = st.H - col0;                                            // the ones column
+          v.x = d == 0 ? 1.0f : v.x; v.y = d == 1 ? 1.0f : v.y; v.z = d == 2 ? 1.0f : v.z; v.w = d == 3 ? 1.0f : v.w;
+          srow[j] = v;
+        }
+      }
+      __syncwarp();
+      const int ch = lane & 7, rr = lane >> 3;
+      if (ch < n4) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = 4 * i + rr;
+          if (r < st_nrows)
+            *reinterpret_cast<float4*>(st_base + (size_t)r * TC_N + gcol + 4 * ch) = *reinterpret_cast<const float4*>(stg + r * STG_LD + 4 * ch);
+        }
+      }
+      __syncwarp();
+    };
     auto convert_chunks = [&](auto rolled, uint32_t col, const float* bias, int c0, int step, int cend, int tt, int trace_slot) {
       uint32_t va[C::CHUNK_COLS], vb[C::CHUNK_COLS];
       auto ncols_of = [&](int c) { return (MODE == MBO_MLP_TF32) ? 40 : (c == C::NCHUNK - 1 ? 16 : 32); };
@@ -1070,6 +1125,23 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
         __syncwarp();
         if (lane == 0) mbar_arrive(BAR_AREADY(c));
         if (quad == 0) TC_TRACE_T(tt, trace_slot + i);
+        if constexpr (STORE) {
+          // after the hand-off (off the MMA's critical path): relu(D + b) of this chunk as fp32 + its ReLU bit word
+          const int nc = ncols_of(c);
+          const float* bb = bias + c * C::CHUNK_COLS;
+          uint32_t word = 0u;
+          st_block([&](int j) {
+            float4 o;
+            o.x = fmaxf(__uint_as_float(cur[4 * j + 0]) + bb[4 * j + 0], 0.f);
+            o.y = fmaxf(__uint_as_float(cur[4 * j + 1]) + bb[4 * j + 1], 0.f);
+            o.z = fmaxf(__uint_as_float(cur[4 * j + 2]) + bb[4 * j + 2], 0.f);
+            o.w = fmaxf(__uint_as_float(cur[4 * j + 3]) + bb[4 * j + 3], 0.f);
+            word |= (o.x > 0.f ? 1u : 0u) << (4 * j) | (o.y > 0.f ? 1u : 0u) << (4 * j + 1) |
+                    (o.z > 0.f ? 1u : 0u) << (4 * j + 2) | (o.w > 0.f ? 1u : 0u) << (4 * j + 3);
+            return o;
+          }, nc / 4, c * C::CHUNK_COLS);
+          if (st_bits) st_bits[c] = word;
+        }
       };
       if (c0 < cend) ChunkOps<MODE>::load(tlane + col + c0 * C::CHUNK_COLS, va, ncols_of(c0));
       if constexpr (decltype(rolled)::value) {
@@ -1124,6 +1196,7 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
         tc_fence_after();
         if (quad == 0) TC_TRACE(100 + 100 * half + 20 * l);
         const float* bias = s_tail + l * TC_N;
+        if constexpr (STORE) st_tile(t, st.h[l], st.bits[l]);
         convert_chunks(std::false_type{}, col, bias, half, 2, C::NCHUNK, t, 100 + 100 * half + 20 * l + 1);
         // Layer 1 is complete (this warp saw d_full): the shared slots take layer 3's stages.  Issuing a bulk copy
         // costs the thread ~160 cycles, so this sits after the chunk conversions, on the half with fewer chunks;
@@ -1158,6 +1231,7 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
         const float* b3 = s_tail + 3 * TC_N + cb;
         const float* w4 = s_w4 + cb;
         uint32_t v0[32], v1[32];
+        if constexpr (STORE) st_tile(t, st.h[3], nullptr);
         auto dot = [&](const uint32_t* v, int j0, int n4) {     // columns j0 .. j0 + 4 n4 of this thread's range
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -1165,11 +1239,20 @@ neural_af_tc_kernel(const unsigned char* __restrict__ pack, TcFeat fs, mbo_candi
               const float4 w = reinterpret_cast<const float4*>(w4 + j0)[j];
               float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
               if constexpr (!F16) b = reinterpret_cast<const float4*>(b3 + j0)[j];   // fp16 mode: b3 is in the accumulator
-              acc = fmaf(fmaxf(__uint_as_float(v[4 * j + 0]) + b.x, 0.f), w.x, acc);
-              acc2 = fmaf(fmaxf(__uint_as_float(v[4 * j + 1]) + b.y, 0.f), w.y, acc2);
-              acc = fmaf(fmaxf(__uint_as_float(v[4 * j + 2]) + b.z, 0.f), w.z, acc);
-              acc2 = fmaf(fmaxf(__uint_as_float(v[4 * j + 3]) + b.w, 0.f), w.w, acc2);
+              const float x0 = fmaxf(__uint_as_float(v[4 * j + 0]) + b.x, 0.f), x1 = fmaxf(__uint_as_float(v[4 * j + 1]) + b.y, 0.f);
+              const float x2 = fmaxf(__uint_as_float(v[4 * j + 2]) + b.z, 0.f), x3 = fmaxf(__uint_as_float(v[4 * j + 3]) + b.w, 0.f);
+              acc = fmaf(x0, w.x, acc);
+              acc2 = fmaf(x1, w.y, acc2);
+              acc = fmaf(x2, w.z, acc);
+              acc2 = fmaf(x3, w.w, acc2);
             }
+          }
+          if constexpr (STORE) {
+            st_block([&](int j) {
+              float4 b = reinterpret_cast<const float4*>(b3 + j0)[j];
+              return make_float4(fmaxf(__uint_as_float(v[4 * j + 0]) + b.x, 0.f), fmaxf(__uint_as_float(v[4 * j + 1]) + b.y, 0.f),
+                                 fmaxf(__uint_as_float(v[4 * j + 2]) + b.z, 0.f), fmaxf(__uint_as_float(v[4 * j + 3]) + b.w, 0.f));
+            }, n4, cb + j0);
           }
         };
         // R1 is what the next tile's layer 1 waits for (r1_free): get D3 into registers with two load round trips instead
@@ -1438,12 +1521,26 @@ static bool tc_standard_layout(int F, const int32_t* src, int D) {
   return true;
 }
 
+template <int MODE, bool FUSE, int K0S, bool STORE = false>
+static int launch_tc_pack(const unsigned char* pack, int B, const TcFeat& fs, const mbo_candidates& cand, const float* mean,
+                          const float* std_, const float* epi, float* logits, int* err_flag, cudaStream_t s,
+                          const GpFuse& gp, const TcTopk& tk, const TcStore& st);
+
 template <int MODE, bool FUSE, int K0S>
 static int launch_tc_k(const mbo_policy* p, int B, const TcFeat& fs, const mbo_candidates& cand, const float* mean,
                      const float* std_, const float* epi, float* logits, int* err_flag, cudaStream_t s,
                      const GpFuse& gp, const TcTopk& tk) {
-  using SM = TcSmem<MODE, FUSE, K0S>;
-  auto kern = neural_af_tc_kernel<MODE, FUSE, K0S>;
+  TcStore st;
+  memset(&st, 0, sizeof(st));
+  return launch_tc_pack<MODE, FUSE, K0S, false>((const unsigned char*)p->d_tc, B, fs, cand, mean, std_, epi, logits, err_flag, s, gp, tk, st);
+}
+
+template <int MODE, bool FUSE, int K0S, bool STORE>
+static int launch_tc_pack(const unsigned char* pack, int B, const TcFeat& fs, const mbo_candidates& cand, const float* mean,
+                          const float* std_, const float* epi, float* logits, int* err_flag, cudaStream_t s,
+                          const GpFuse& gp, const TcTopk& tk, const TcStore& st) {
+  using SM = TcSmem<MODE, FUSE, K0S, STORE>;
+  auto kern = neural_af_tc_kernel<MODE, FUSE, K0S, STORE>;
   MBO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::total));
   if (g_num_sms == 0) {
     int dev = 0;
@@ -1454,8 +1551,8 @@ static int launch_tc_k(const mbo_policy* p, int B, const TcFeat& fs, const mbo_c
   const int total = B * tiles_per_episode;
   const int grid = total < g_num_sms ? total : g_num_sms;
   kern<<<grid, FUSE ? TC_THREADS_FUSED : TC_THREADS, SM::total, s>>>(
-      (const unsigned char*)p->d_tc, fs, cand, B, tiles_per_episode, mean, std_, epi, logits, err_flag,
-      getenv("MBO_TC_DEBUG_NOLOAD") ? 1 : 0, gp, tk);
+      pack, fs, cand, B, tiles_per_episode, mean, std_, epi, logits, err_flag,
+      getenv("MBO_TC_DEBUG_NOLOAD") ? 1 : 0, gp, tk, st);
   MBO_LAUNCH_CHECK();
   return MBO_OK;
 }
@@ -1512,6 +1609,56 @@ int tc_forward(const mbo_policy* p, int mode, int B, int F, const int32_t* feat_
   topk_merge_kernel<<<B, 128, 0, s>>>(tiles * 4, topk, tk.part_val, tk.part_idx, topk_idx, topk_val);
   MBO_LAUNCH_CHECK();
   return MBO_OK;
+}
+
+// ---- entry points of the PPO update (ppo_update.cu): the current raw weights, packed for the bf16x3 mode on every
+// optimiser step, and the policy forward on materialised states with optional activation / ReLU-bit stores ----------
+size_t tc_pack_bytes() { return pack_layout().total; }
+
+int tc_pack_raw_bf16x3(const float* const* W, const float* const* b, int F, int H, void* pack, cudaStream_t s) {
+  MBO_CHECK_ARG(F + 1 <= TC_K0 && H >= 8 && H <= TC_N, "tc_pack_raw_bf16x3: unsupported shape F=%d H=%d", F, H);
+  PackArgs a;
+  for (int l = 0; l < 5; ++l) { a.W[l] = W[l]; a.b[l] = b[l]; }
+  a.F = F; a.H = H;
+  const size_t words = pack_layout().total / 4;
+  tc_pack_kernel<<<(unsigned)((words + 255) / 256), 256, 0, s>>>(a, (unsigned char*)pack, 1);
+  MBO_LAUNCH_CHECK();
+  return MBO_OK;
+}
+
+int tc_forward_dense_bf16x3(const void* pack, int E, int M, int F_state, int F, const int32_t* cols, const float* states,
+                            float* logits, int* err_flag, float* const* h_out, uint32_t* const* bits_out, int H,
+                            cudaStream_t s) {
+  TcFeat fs;
+  fs.F = F;
+  fs.dense = states;
+  fs.dense_F = F_state;
+  fs.k0_slices = (F + 1 <= 8) ? 1 : 2;
+  for (int i = 0; i < TC_K0; ++i) fs.src[i] = i < F ? cols[i] : 0;
+  fs.standard = 0;
+  mbo_candidates c;
+  memset(&c, 0, sizeof(c));
+  c.M = M;
+  c.D = 1;
+  GpFuse gp;
+  memset(&gp, 0, sizeof(gp));
+  TcTopk tk;
+  memset(&tk, 0, sizeof(tk));
+  TcStore st;
+  memset(&st, 0, sizeof(st));
+  const bool store = h_out != nullptr;
+  if (store) {
+    for (int l = 0; l < 4; ++l) st.h[l] = h_out[l];
+    for (int l = 0; l < 3; ++l) st.bits[l] = bits_out[l];
+    st.H = H;
+  }
+  const unsigned char* pk = (const unsigned char*)pack;
+  if (store) {
+    if (fs.k0_slices == 1) return launch_tc_pack<MBO_MLP_BF16X3, false, 1, true>(pk, E, fs, c, nullptr, nullptr, nullptr, logits, err_flag, s, gp, tk, st);
+    return launch_tc_pack<MBO_MLP_BF16X3, false, 2, true>(pk, E, fs, c, nullptr, nullptr, nullptr, logits, err_flag, s, gp, tk, st);
+  }
+  if (fs.k0_slices == 1) return launch_tc_pack<MBO_MLP_BF16X3, false, 1, false>(pk, E, fs, c, nullptr, nullptr, nullptr, logits, err_flag, s, gp, tk, st);
+  return launch_tc_pack<MBO_MLP_BF16X3, false, 2, false>(pk, E, fs, c, nullptr, nullptr, nullptr, logits, err_flag, s, gp, tk, st);
 }
 
 size_t tc_workspace_bytes(int B, int M) {

@@ -18,3 +18,12 @@ struct mbo_policy {
   int tc_f16 = 0;         // 1 when additionally H <= 206 (MBO_MLP_FP16 folds the bias into two spare K columns)
   int tc_H = 0, tc_F = 0;
 };
+
+namespace mbo {
+// neural_af_tc.cu: the tcgen05 policy forward on raw weights, used by the PPO update (ppo_update.cu)
+size_t tc_pack_bytes();
+int tc_pack_raw_bf16x3(const float* const* W, const float* const* b, int F, int H, void* pack, cudaStream_t s);
+int tc_forward_dense_bf16x3(const void* pack, int E, int M, int F_state, int F, const int32_t* cols, const float* states,
+                            float* logits, int* err_flag, float* const* h_out, uint32_t* const* bits_out, int H,
+                            cudaStream_t s);
+}  // namespace mbo

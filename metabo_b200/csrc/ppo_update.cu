@@ -31,6 +31,7 @@
 #include <stdlib.h>
 #include "common.cuh"
 #include "ppo_loss.cuh"
+#include "policy.cuh"
 #include "tmem_ldst.cuh"
 
 namespace mbo {
@@ -190,6 +191,7 @@ struct Ws {          // workspace carve-up (device pointers)
   float* part_big;   // [WG_SPLIT][3][HP][HP]
   float* part_head;  // [THIN_CTAS][HP]
   float* part_l0;    // [THIN_CTAS][HP][MAXF + 1]
+  void* tcpack;      // the current weights packed for the tcgen05 policy kernel (bf16x3 images), re-packed every call
 };
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -213,6 +215,7 @@ static size_t carve(int E, int M, unsigned char* base, Ws* w) {
   t.part_big = (float*)take((size_t)WG_SPLIT * 3 * HP * HP * 4);
   t.part_head = (float*)take((size_t)THIN_CTAS * HP * 4);
   t.part_l0 = (float*)take((size_t)THIN_CTAS * HP * (MAXF + 1) * 4);
+  t.tcpack = (void*)take(tc_pack_bytes());
   if (w) *w = t;
   return off;
 }
@@ -1319,8 +1322,16 @@ __global__ void __launch_bounds__(256) adam_step_kernel(AdamArgs a, float lr, fl
 
 static bool g_attr_done = false;
 static int g_num_sms = 148;
+// second stream of a policy-gradient call: the CUDA-core layer-0 wgrad runs beside the tensor-core wgrad of the hidden
+// layers (fork / join by events; inside a stream capture the two become parallel branches of the graph).  Created on the
+// first call, which must not be a captured one (PPO runs its first optimiser steps eagerly).
+static cudaStream_t g_side = nullptr;
+static cudaEvent_t g_ev_fork = nullptr, g_ev_join = nullptr;
 static int set_attrs() {
   if (g_attr_done) return MBO_OK;
+  MBO_CUDA(cudaStreamCreateWithFlags(&g_side, cudaStreamNonBlocking));
+  MBO_CUDA(cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming));
+  MBO_CUDA(cudaEventCreateWithFlags(&g_ev_join, cudaEventDisableTiming));
   MBO_CUDA(cudaFuncSetAttribute(upd_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
   MBO_CUDA(cudaFuncSetAttribute(upd_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
   MBO_CUDA(cudaFuncSetAttribute(upd_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
@@ -1405,7 +1416,21 @@ extern "C" int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32
   const bool dgrad_ts = dt_env ? atoi(dt_env) != 0 : false;
   const int pg_grid = g_num_sms < tiles ? g_num_sms : tiles;
 
+  // Forward (policies.py:104-125 on the minibatch).  Default: ONE launch of the tcgen05 policy kernel of the rollouts
+  // (neural_af_tc.cu, bf16x3 = fp32-class arithmetic, all four layers with the activations resident in tensor memory)
+  // on the current weights, which also writes the fp32 activations h1..h4 and the ReLU bit words the backward reads --
+  // instead of layer 0 + three GEMM launches whose activations made an HBM round trip each.  MBO_UPD_FWD_K2=0 selects
+  // the GEMM-per-layer forward (3xTF32), kept as the A/B reference.
+  const char* k2_env = getenv("MBO_UPD_FWD_K2");
+  const bool fwd_k2 = k2_env ? atoi(k2_env) != 0 : true;
   upd_pack_kernel<<<(9 * IMG_FLOATS + 255) / 256, 256, 0, st>>>(net, ws);
+  if (fwd_k2) {
+    int rc = tc_pack_raw_bf16x3(W, b, F, H, ws.tcpack, st);
+    if (rc != MBO_OK) return rc;
+    rc = tc_forward_dense_bf16x3(ws.tcpack, E, M, F_state, F, feat_col, states, ws.logits, ws.err, fwd_only ? nullptr : ws.Hs,
+                                 ws.hbits, H, st);
+    if (rc != MBO_OK) return rc;
+  } else {
   upd_layer0_kernel<<<l0_ctas, THIN_THREADS, 0, st>>>(net, states, R, ws.Hs[0]);
   for (int l = 0; l < 3; ++l) {
     GemmArgs g{};
@@ -1415,6 +1440,7 @@ extern "C" int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32
     if (l == 2) { g.w4 = W[4]; g.b4 = b[4]; g.logits = ws.logits; }
     if (fwd_ts) upd_ts_kernel<0><<<tiles, GEMM_THREADS, TS_SMEM, st>>>(g, ws.err);
     else upd_gemm_kernel<0><<<tiles, GEMM_THREADS, FWD_SMEM, st>>>(g, ws.err);
+  }
   }
   upd_loss_kernel<<<E, 256, 0, st>>>(M, ws.logits, actions, advs, logp_old, epsilon, ent_coeff, inv_n_global, ws.dl,
                                       ws.terms);
@@ -1426,7 +1452,7 @@ extern "C" int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32
   upd_dz4_kernel<<<THIN_CTAS, THIN_THREADS, 0, st>>>(R, H, ws.Hs[3], ws.dl, W[4], ws.dZ[3], ws.part_head);
   for (int l = 2; l >= 0; --l) {      // dZ_{l+1} = (dZ_{l+2} W_{l+1}) . [h_{l+1} > 0]
     GemmArgs g{};
-    g.A = ws.dZ[l + 1]; g.Bimg = (persist && !dgrad_ts) ? ws.img_dgp[l] : ws.img_dgr[l]; g.Out = ws.dZ[l]; g.bits_in = (l > 0 || fwd_ts) ? ws.hbits[l] : nullptr;   // SS forward: no h1 words, l = 0 stores dH1, masked in wgrad0
+    g.A = ws.dZ[l + 1]; g.Bimg = (persist && !dgrad_ts) ? ws.img_dgp[l] : ws.img_dgr[l]; g.Out = ws.dZ[l]; g.bits_in = (l > 0 || fwd_ts || fwd_k2) ? ws.hbits[l] : nullptr;   // SS forward: no h1 words, l = 0 stores dH1, masked in wgrad0
     g.R = R; g.H = H; g.dbg = dbg;
     if (dgrad_ts) upd_ts_kernel<1><<<tiles, GEMM_THREADS, TS_SMEM, st>>>(g, ws.err);
     else if (persist) upd_dgrad_persist_kernel<<<pg_grid, PG_THREADS, PG_SMEM, st>>>(g, ws.err);
@@ -1436,8 +1462,20 @@ extern "C" int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32
   for (int l = 0; l < 3; ++l) { wa.dZ[l] = ws.dZ[l + 1]; wa.Hin[l] = ws.Hs[l]; }
   wa.part = ws.part_big; wa.R = R; wa.H = H;
 
+  const char* fk_env = getenv("MBO_UPD_FORK");
+  const bool fork = fk_env ? atoi(fk_env) != 0 : true;
+  cudaStream_t st0 = st;                    // stream of the layer-0 wgrad
+  if (fork) {
+    MBO_CUDA(cudaEventRecord(g_ev_fork, st));
+    MBO_CUDA(cudaStreamWaitEvent(g_side, g_ev_fork, 0));
+    st0 = g_side;
+  }
   upd_wgrad_kernel<<<dim3(WG_SPLIT, 3), GEMM_THREADS, WG_SMEM, st>>>(wa, ws.err);
-  upd_wgrad0_kernel<<<wg0_ctas, THIN_THREADS, 0, st>>>(net, states, R, ws.dZ[0], fwd_ts ? nullptr : ws.Hs[0], ws.part_l0);
+  upd_wgrad0_kernel<<<wg0_ctas, THIN_THREADS, 0, st0>>>(net, states, R, ws.dZ[0], (fwd_ts || fwd_k2) ? nullptr : ws.Hs[0], ws.part_l0);
+  if (fork) {
+    MBO_CUDA(cudaEventRecord(g_ev_join, g_side));
+    MBO_CUDA(cudaStreamWaitEvent(st, g_ev_join, 0));
+  }
   const int nblkA = (3 * H * (H + 1) + 255) / 256, nblkT = ((H + 1) + H * (F + 1) + 7) / 8;
   upd_reduce_kernel<<<nblkA + nblkT, 256, 0, st>>>(net, ws, THIN_CTAS, wg0_ctas, nblkA);
   MBO_CUDA(cudaMemcpyAsync(terms, ws.terms, (size_t)E * 16, cudaMemcpyDeviceToDevice, st));

@@ -162,6 +162,7 @@ class PPO:
         self._vg_grads = None
         self._flat_grads = None
         self._loss4 = None
+        self._side = None       # second stream: the value-net branch of an optimiser step
         self._mbufs = {}        # minibatch buffers of mbo_ppo_prepare_minibatch, by minibatch size
 
         self.stats = dict()
@@ -264,6 +265,11 @@ class PPO:
             self._upd = self._ep = None      # captured graphs hold the old workspace's pointers
         return self._pg
 
+    def _side_stream(self):
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
+
     def _old_logprobs(self, states, actions):
         """ppo.py:146-147 `logprobs_old` of the frozen old policy, by the update kernels' own forward (same
         arithmetic as the new policy's log-probs: the ratio is exactly 1 while theta == theta_old)."""
@@ -293,23 +299,33 @@ class PPO:
             self._alloc_native_grads()
         dW, db = self._pg_grads
         self.optimizer.zero_grad(set_to_none=True)
+        # The value net's ~15 small kernels (60 rows) depend only on the minibatch: they run on a second stream beside
+        # the policy-net kernels and join before Adam (inside a captured graph this is a fork / join of two branches).
+        side = None
+        if pi.use_value_network:
+            vfc = list(pi.value_net.fc)
+            self._value_grad_op(E)
+            vW, vb = self._vg_grads
+            cur = torch.cuda.current_stream()
+            side = self._side_stream() if self.params.get("value_branch", True) else None
+            if side is not None:
+                side.wait_stream(cur)
+            with torch.cuda.stream(side if side is not None else cur):
+                _, vterms = self._vg(states.contiguous(), pi.t_idx, pi.T_idx, [l.weight.data for l in vfc],
+                                     [l.bias.data for l in vfc], tdlamrets.to(torch.float32).contiguous(),
+                                     self.params["value_coeff"] / n_global, vW, vb)
+            for l, gw, gb in zip(vfc, vW, vb):
+                l.weight.grad, l.bias.grad = gw, gb
+        else:
+            vterms = tdlamrets.to(torch.float32) ** 2          # the reference's value head is then the constant 0
         terms = self._pg(states.contiguous(), [l.weight.data for l in fcs], [l.bias.data for l in fcs],
                          actions.to(torch.int32).contiguous(), advs.to(torch.float32).contiguous(),
                          logprobs_old.to(torch.float32).contiguous(), self.params["epsilon"], self.params["ent_coeff"],
                          n_global, dW, db)
         for l, gw, gb in zip(fcs, dW, db):
             l.weight.grad, l.bias.grad = gw, gb
-        if pi.use_value_network:
-            vfc = list(pi.value_net.fc)
-            self._value_grad_op(E)
-            vW, vb = self._vg_grads
-            _, vterms = self._vg(states.contiguous(), pi.t_idx, pi.T_idx, [l.weight.data for l in vfc],
-                                 [l.bias.data for l in vfc], tdlamrets.to(torch.float32).contiguous(),
-                                 self.params["value_coeff"] / n_global, vW, vb)
-            for l, gw, gb in zip(vfc, vW, vb):
-                l.weight.grad, l.bias.grad = gw, gb
-        else:
-            vterms = tdlamrets.to(torch.float32) ** 2          # the reference's value head is then the constant 0
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
         if prepared and (self.world == 1 or self.comm is not None):
             self.optimizer.step()              # world > 1: gradient exchange + Adam in one kernel (FusedAdam.set_comm)
             if self._loss4 is None:

@@ -280,6 +280,7 @@ def test_gemm_kernel_variants_agree_bitwise(monkeypatch):
     tile: every activation, dZ and gradient is bitwise identical whichever variants run, on a ragged row count that gives
     the persistent CTAs partial and empty tiles."""
     layers, states, actions, advs, logp_old = _random_case(11, 9, 517, 6, list(range(6)), 200)
+    monkeypatch.setenv("MBO_UPD_FWD_K2", "0")               # the GEMM-per-layer forward (the default is the fused tcgen05 policy kernel)
     outs = []
     for dgr, ts, dts in (("1", "1", "0"), ("0", "0", "0"), ("1", "0", "1"), ("0", "1", "1")):
         monkeypatch.setenv("MBO_UPD_PERSIST_DGRAD", dgr)
@@ -329,3 +330,29 @@ def test_prepare_minibatch_and_loss_sums_match_torch():
     l_ppo, l_val, l_ent = terms[:, 2].sum(), vterms.sum() / (2 * E), -terms[:, 1].sum() / (2 * E)
     ref4 = torch.stack([l_ppo, l_val, l_ent, l_ppo + 0.7 * l_val + 0.01 * l_ent])
     assert float((out4 - ref4).abs().max()) <= 1e-5 * float(ref4.abs().max())
+
+
+def test_fused_policy_forward_agrees_with_gemm_forward(monkeypatch):
+    """Default forward of the update = ONE launch of the tcgen05 policy kernel (bf16x3, activations resident in tensor
+    memory, h1..h4 + ReLU bit words written for the backward) vs the GEMM-per-layer 3xTF32 forward (MBO_UPD_FWD_K2=0):
+    both are fp32-class -- logits within 2e-5 of max|logit|, stored activations within 2e-5 of max|h|, ReLU decisions
+    identical except at pre-activations within rounding of 0, gradients pointing the same way (cosine > 0.9999) and the
+    ones column / zero padding of every stored activation in place."""
+    layers, states, actions, advs, logp_old = _random_case(21, 7, 966, 6, list(range(6)), 200)
+    outs = {}
+    for k2 in ("0", "1"):
+        monkeypatch.setenv("MBO_UPD_FWD_K2", k2)
+        outs[k2] = _run_case(7, 966, 6, list(range(6)), 200, layers, states, actions, advs, logp_old)
+    (t0, v0, dW0, db0), (t1, v1, dW1, db1) = outs["0"], outs["1"]
+    R = 7 * 966
+    scale = float(v0["logits"][:R].abs().max())
+    assert float((v0["logits"][:R] - v1["logits"][:R]).abs().max()) <= 2e-5 * scale
+    for k in ("h1", "h2", "h3", "h4"):
+        a, b = v0[k][:R], v1[k][:R]
+        assert float((a - b).abs().max()) <= 2e-5 * float(a.abs().max()), k
+        assert bool((b[:, 200] == 1.0).all()) and float(b[:, 201:].abs().max()) == 0.0, k
+        assert float(((a > 0) != (b > 0)).float().mean()) < 1e-4, k
+    np.testing.assert_allclose(t1[:, 0].cpu().numpy(), t0[:, 0].cpu().numpy(), atol=2e-5 * scale)       # log-probs
+    g0 = torch.cat([x.reshape(-1) for x in dW0 + db0]).double()
+    g1 = torch.cat([x.reshape(-1) for x in dW1 + db1]).double()
+    assert float(torch.nn.functional.cosine_similarity(g0, g1, dim=0)) > 0.9999
