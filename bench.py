@@ -381,9 +381,10 @@ def ppo_update_rate(dev):
     pg.check()
     flops = 3 * 2 * E * M * (F * H + 3 * H * H + H)
     return {"policy_grad_ms": t_nat, "algorithmic_tflops": flops / t_nat / 1e9, "torch_fp32_autograd_ms": t_ref,
-            "launches_per_step": 13,
-            "config": "train_metabo_branin.py minibatch (C3): 60 x 966 candidates, F=6, 4x200 ReLU policy; forward 3xTF32 "
-                      "(fp32-level logits), backward single-pass TF32, deterministic split-K"}
+            "launches_per_step": 12,
+            "config": "train_metabo_branin.py minibatch (C3): 60 x 966 candidates, F=6, 4x200 ReLU policy; forward = one launch "
+                      "of the tcgen05 policy kernel in bf16x3 (fp32-level logits; activations + ReLU words stored for the "
+                      "backward), backward single-pass TF32, deterministic split-K"}
 
 
 def main():
@@ -464,7 +465,7 @@ def main():
             raise L.MboError("mlp mode %s is not available for this policy" % m)
         e.set_data(X, Y, nvec, n_active_max=n)
         e.set_episode_scalars(inc, tvec, Tvec)
-        e.af_round()
+        e.af_round(want_logits=False)
         torch.cuda.synchronize()
         e.policy.check()
         return e
@@ -503,7 +504,7 @@ def main():
 
     # ---- resident arm ----
     eng.kernel_events = []          # (tag, start, end) around the MLP launches, see engine.evaluate
-    ms, clocks, launches = timed(lambda: eng.af_round(), args.steps, args.warmup, profile=True)
+    ms, clocks, launches = timed(lambda: eng.af_round(want_logits=False), args.steps, args.warmup, profile=True)
     kev = eng.kernel_events
     eng.kernel_events = None
     cands_step = B * 13461
@@ -562,7 +563,7 @@ def main():
         ds.copy_(hs, non_blocking=True)
         eng.set_data(dX, dY, dn, n_active_max=n)
         eng.set_episode_scalars(ds[0], ds[1], ds[2])
-        out = eng.af_round()
+        out = eng.af_round(want_logits=False)
         h_act.copy_(out["action"], non_blocking=True)
         h_x.copy_(out["x_action"], non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -581,7 +582,7 @@ def main():
                 continue
             e2 = ready_engine(m)
             k_steps = min(args.steps, 10)
-            ms_m, _, _ = timed(lambda: e2.af_round(), k_steps, 3, eng=e2)
+            ms_m, _, _ = timed(lambda: e2.af_round(want_logits=False), k_steps, 3, eng=e2)
             e2.policy.check()
             modes_info[m] = {"ms_per_step": ms_m / k_steps, "AF_evals_per_s": world * cands_step * k_steps / (ms_m / 1e3),
                              "steps": k_steps}

@@ -14,6 +14,8 @@ GP state lives in one fp64 blob per episode, and every step is enqueued on the c
 without host synchronisation.  Discrete domains (`local_af_opt=False`, e.g. train_metabo_gps.py)
 skip phases 1-2.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -99,7 +101,9 @@ class AFEngine:
         self.reuse_multistart = False   # phase 3 reuses the phase-1 results of the multistart grid (VecMetaBO turns it on)
         self.evals_skipped = 0
         self.episode_offset = 0         # global index of lane 0 (keys the sampler under sharding)
-        self.fuse_topk = False          # opt-in: top-k selection in the tensor-core kernel epilogue (mbo_af_topk); measured slower, see profiles/r01_notes.md
+        # top-k / argmax selection in the tensor-core kernel's epilogue (mbo_af_topk): the logits of the search phases never
+        # reach HBM.  Default since r2 (fp16: step 4.28 -> 4.23 ms, tf32 / bf16x3 +1.5 %; MBO_FUSE_TOPK=0: logits -> topk_kernel)
+        self.fuse_topk = os.environ.get("MBO_FUSE_TOPK", "1") != "0"
         self.keep_phase_logits = False  # also materialise the phase-1/2 logits (parity tests, smoke)
         self.fuse_gp = False         # opt-in: mbo_af_eval_fused (correct, but slower than the two-kernel path so far, see profiles/r01_notes.md)
         self.tc_ok = False           # set by set_policy: architecture supported by the tensor-core kernel
@@ -228,10 +232,12 @@ class AFEngine:
                 and self.n_active_max <= ops.FUSED_MAX_N and self.tc_ok)
 
     def af_round(self, deterministic=True, seed=0, step=0, refit=True, want_stats=False, want_posterior=False,
-                 step_dev=None):
+                 step_dev=None, want_logits=True):
         """One AF-optimisation round for all B episodes.  Returns a dict of device tensors:
         action [B] i32, x_action [B,D] f64, xi_t candidate set, logits [B,M] (phase 3), and with
-        want_stats also logp / entropy [B]."""
+        want_stats also logp / entropy [B].  want_logits=False (greedy evaluation, policies.py:127-136 only needs the
+        argmax): phase 3 takes the action from the kernel's selection epilogue (k = 1: first-index ties like
+        torch.argmax) and no logit of the round is written to HBM."""
         if refit:
             self.fit()
         out = {}
@@ -257,9 +263,14 @@ class AFEngine:
             mean = torch.cat([mh, mean1], dim=1) if (want_posterior and mean1 is not None) else None
             std = torch.cat([sh, std1], dim=1) if (want_posterior and std1 is not None) else None
             self.evals_skipped += self.B * self.N_MS
+        elif deterministic and not want_logits and not want_stats:
+            mean, std, lg3, top3 = self.evaluate_topk(cs, 1)
+            action = top3[:, 0].contiguous() if lg3 is None else None
         else:
             mean, std, lg3 = self.evaluate(cs, want_posterior=want_posterior)
-        if deterministic:
+        if deterministic and lg3 is None:
+            pass                                     # the action came out of the selection epilogue
+        elif deterministic:
             action, _ = ops.logits_argmax(lg3)
         else:
             action = ops.logits_sample(lg3, seed, step, episode_offset=self.episode_offset, step_dev=step_dev)

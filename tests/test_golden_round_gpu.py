@@ -169,6 +169,44 @@ def test_af_round_on_golden_episode_states(golden_dir, name, mode_name, mode, to
         assert full_chain >= 2, (name, mode_name, full_chain)
 
 
+@pytest.mark.parametrize("name", ["bra", "hm3"])
+@pytest.mark.parametrize("mode_name,mode,tol", MODES)
+def test_round_without_logits_equals_round_with_logits(golden_dir, name, mode_name, mode, tol, monkeypatch):
+    """`af_round(want_logits=False)` -- what bench.py times: selections of all three phases in the tensor-core kernel's
+    epilogue, no logit written to HBM -- returns the top-k starts, maxima, action and x_action of the round that
+    materialises every logit and selects with topk_kernel / argmax_kernel (MBO_FUSE_TOPK=0), bit for bit, on the
+    reference's own episode states (first-index ties like torch.argmax; the fp32 CUDA-core mode has no selection
+    epilogue and takes the same path both times)."""
+    ep = np.load(os.path.join(golden_dir, "episode_%s.npz" % name))
+    spec = json.loads(str(ep["__env_spec__"]))
+    pw = O.PolicyWeights.from_npz(os.path.join(golden_dir, WEIGHTS[name]))
+    keep = [int(t) for t in ep["keep"]]
+    B, D, T = len(keep), spec["D"], spec["T"]
+    outs = []
+    for fuse, want in (("0", True), ("1", False)):
+        monkeypatch.setenv("MBO_FUSE_TOPK", fuse)
+        eng = _engine_for(ep, spec, pw, mode, B)
+        dev = eng.dev
+        X = np.zeros((B, T, D)); Y = np.zeros((B, T)); inc = np.zeros(B)
+        for b, t in enumerate(keep):
+            p = "t%02d_" % t
+            X[b, :t], Y[b, :t] = ep[p + "X"], ep[p + "Y"]
+            inc[b] = float(ep[p + "incumbent"])
+        eng.set_data(torch.as_tensor(X, device=dev), torch.as_tensor(Y, device=dev),
+                     torch.as_tensor(np.array(keep, dtype=np.int32), device=dev))
+        eng.set_episode_scalars(inc, np.array(keep, dtype=np.float32), np.full(B, T, dtype=np.float32))
+        out = eng.af_round(deterministic=True, want_logits=want)
+        torch.cuda.synchronize()
+        eng.policy.check()
+        outs.append(out)
+    a, b = outs
+    assert a["logits"] is not None
+    if mode != 0:
+        assert b["logits"] is None and b["af_ms"] is None and b["af_ls"] is None
+    for key in ("top_ms", "top_ls", "af_maxima", "action", "x_action"):
+        assert torch.equal(a[key], b[key]), (name, mode_name, key)
+
+
 @pytest.mark.parametrize("mode_name", ["fp32"])
 def test_gps_discrete_round_on_golden_states(golden_dir, mode_name):
     """C4 (train_metabo_gps.py: Matern-5/2, prior mean = mean(Y), discrete Sobol domain, 2x20 policy with t / T masked
