@@ -224,11 +224,12 @@ static size_t carve(int E, int M, unsigned char* base, Ws* w) {
 // K-major canonical, one stage per KT (dgrad) / KT3 (forward) K values: [kt][16-byte K chunk c][n (208)][4 floats]
 // (4 chunks per dgrad stage, 2 per forward stage).
 // Forward: [W | b] split into tf32 hi and lo parts (3xTF32: hi*hi + lo*hi + hi*lo, fp32-level logits); dgrad: W^T.
-__global__ void upd_pack_kernel(Net net, Ws ws) {
+__global__ void upd_pack_kernel(Net net, Ws ws, int kinds) {      // kinds: bit k set = image kind k is needed by this call
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= 9 * IMG_FLOATS) return;
   const int img = idx / IMG_FLOATS, o = idx - img * IMG_FLOATS;
   const int kind = img / 3, l = img - kind * 3;     // kind 0: forward hi / lo, 1: dgrad (KT), 2: dgrad (32 per stage); layer l + 1
+  if (!((kinds >> kind) & 1)) return;
   const int kt_len = kind == 0 ? KT3 : (kind == 1 ? KT : 32);
   const int kt = o / (HP * kt_len), r = o - kt * (HP * kt_len);
   const int c = r / (HP * 4), r2 = r - c * (HP * 4);
@@ -1326,12 +1327,14 @@ static int g_num_sms = 148;
 // layers (fork / join by events; inside a stream capture the two become parallel branches of the graph).  Created on the
 // first call, which must not be a captured one (PPO runs its first optimiser steps eagerly).
 static cudaStream_t g_side = nullptr;
-static cudaEvent_t g_ev_fork = nullptr, g_ev_join = nullptr;
+static cudaEvent_t g_ev_fork = nullptr, g_ev_join = nullptr, g_ev_fork0 = nullptr, g_ev_pack = nullptr;
 static int set_attrs() {
   if (g_attr_done) return MBO_OK;
   MBO_CUDA(cudaStreamCreateWithFlags(&g_side, cudaStreamNonBlocking));
   MBO_CUDA(cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming));
   MBO_CUDA(cudaEventCreateWithFlags(&g_ev_join, cudaEventDisableTiming));
+  MBO_CUDA(cudaEventCreateWithFlags(&g_ev_fork0, cudaEventDisableTiming));
+  MBO_CUDA(cudaEventCreateWithFlags(&g_ev_pack, cudaEventDisableTiming));
   MBO_CUDA(cudaFuncSetAttribute(upd_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
   MBO_CUDA(cudaFuncSetAttribute(upd_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
   MBO_CUDA(cudaFuncSetAttribute(upd_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
@@ -1423,7 +1426,20 @@ extern "C" int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32
   // the GEMM-per-layer forward (3xTF32), kept as the A/B reference.
   const char* k2_env = getenv("MBO_UPD_FWD_K2");
   const bool fwd_k2 = k2_env ? atoi(k2_env) != 0 : true;
-  upd_pack_kernel<<<(9 * IMG_FLOATS + 255) / 256, 256, 0, st>>>(net, ws);
+  const char* fk_env = getenv("MBO_UPD_FORK");
+  const bool fork = fk_env ? atoi(fk_env) != 0 : true;
+  // weight images of the backward GEMMs (W^T, tf32): needed by the first dgrad only -- packed on the second stream while
+  // the forward runs; the GEMM-per-layer forward also needs the [W | b] hi / lo images, up front
+  const int pack_kinds = (fwd_k2 ? 0 : 1) | (fwd_only ? 0 : ((persist && !dgrad_ts) ? 4 : 2));
+  const bool pack_aside = fork && fwd_k2 && !fwd_only;
+  if (pack_aside) {
+    MBO_CUDA(cudaEventRecord(g_ev_fork0, st));
+    MBO_CUDA(cudaStreamWaitEvent(g_side, g_ev_fork0, 0));
+    upd_pack_kernel<<<(9 * IMG_FLOATS + 255) / 256, 256, 0, g_side>>>(net, ws, pack_kinds);
+    MBO_CUDA(cudaEventRecord(g_ev_pack, g_side));
+  } else if (pack_kinds) {
+    upd_pack_kernel<<<(9 * IMG_FLOATS + 255) / 256, 256, 0, st>>>(net, ws, pack_kinds);
+  }
   if (fwd_k2) {
     int rc = tc_pack_raw_bf16x3(W, b, F, H, ws.tcpack, st);
     if (rc != MBO_OK) return rc;
@@ -1450,6 +1466,7 @@ extern "C" int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32
     return MBO_OK;
   }
   upd_dz4_kernel<<<THIN_CTAS, THIN_THREADS, 0, st>>>(R, H, ws.Hs[3], ws.dl, W[4], ws.dZ[3], ws.part_head);
+  if (pack_aside) MBO_CUDA(cudaStreamWaitEvent(st, g_ev_pack, 0));
   for (int l = 2; l >= 0; --l) {      // dZ_{l+1} = (dZ_{l+2} W_{l+1}) . [h_{l+1} > 0]
     GemmArgs g{};
     g.A = ws.dZ[l + 1]; g.Bimg = (persist && !dgrad_ts) ? ws.img_dgp[l] : ws.img_dgr[l]; g.Out = ws.dZ[l]; g.bits_in = (l > 0 || fwd_ts || fwd_k2) ? ws.hbits[l] : nullptr;   // SS forward: no h1 words, l = 0 stores dH1, masked in wgrad0
@@ -1462,8 +1479,6 @@ extern "C" int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32
   for (int l = 0; l < 3; ++l) { wa.dZ[l] = ws.dZ[l + 1]; wa.Hin[l] = ws.Hs[l]; }
   wa.part = ws.part_big; wa.R = R; wa.H = H;
 
-  const char* fk_env = getenv("MBO_UPD_FORK");
-  const bool fork = fk_env ? atoi(fk_env) != 0 : true;
   cudaStream_t st0 = st;                    // stream of the layer-0 wgrad
   if (fork) {
     MBO_CUDA(cudaEventRecord(g_ev_fork, st));
