@@ -997,6 +997,221 @@ __global__ void __launch_bounds__(PG_THREADS, 1) upd_dgrad_persist_kernel(GemmAr
   }
 }
 
+
+// ---- fused dgrad chain: dZ4 -> dZ3 -> dZ2 -> dZ1 in ONE persistent kernel ----------------------------------------------
+// The three dgrad GEMMs of a 128-row tile run back to back in one CTA: the masked, tf32-rounded output of GEMM i leaves
+// through the staging tile to HBM (the wgrad needs it) AND is written by the same epilogue threads straight into the
+// NEXT GEMM's A operand in shared memory (the whole K extent of the tile, 7 K stages in the K-major canonical layout), so
+// dZ3 and dZ2 are never read back from HBM: 2 of the 3 A streams (96 MB each at C3) and two launches disappear, and the
+// next GEMM's MMAs start on K stage 0 while the epilogue is still converting stage 1.  Same MMA sequence, same masks and
+// roundings per tile as upd_dgrad_persist_kernel: bitwise identical results (tested).
+// Warps 0-7: epilogue (the accumulator's column blocks alternate between warps 0-3 and 4-7: the kernel is bound by the
+// epilogue's latency chain, not by the tensor pipe or HBM); warps 4-7 also load dZ4; 8: MMA issue; 9: weight stages (3 images
+// per tile through a 3-stage ring).
+struct ChainArgs {
+  const float* A;              // dZ4 [R, HP]
+  const float* Bimg[3];        // W^T images of hidden layers 3, 2, 1 (32 K values per stage)
+  float* Out[3];               // dZ3, dZ2, dZ1
+  const uint32_t* bits[3];     // ReLU words of h3, h2, h1
+  int R, H;
+};
+constexpr int CH_BSTAGES = 3;
+constexpr int CH_A_BYTES = (PG_NKT - 1) * PG_A_STAGE + 4 * PG_LBO_A;        // the last K stage holds K 192..207: 4 chunk planes
+constexpr int CH_STG_BYTES = 8 * 32 * STG_PITCH * 4;                         // one staging tile per epilogue warp (8)
+constexpr int CH_SMEM = CH_A_BYTES + CH_BSTAGES * PG_B_STAGE + CH_STG_BYTES + 256;      // 224 320
+
+__global__ void __launch_bounds__(PG_THREADS, 1) upd_dgrad_chain_kernel(ChainArgs a, int* __restrict__ err) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* sA = smem;                                   // [7 K stages] the tile's A operand (dZ4, then dZ3, then dZ2)
+  unsigned char* sB = smem + CH_A_BYTES;
+  float* s_stg = (float*)(sB + CH_BSTAGES * PG_B_STAGE);
+  uint64_t* bars = (uint64_t*)((unsigned char*)s_stg + CH_STG_BYTES);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar0 = smem_u32(bars);
+  auto AL = [&](int k) { return bar0 + 8u * k; };                      // K stage k of dZ4 has landed (128 loader threads)
+  auto AE = [&](int k) { return bar0 + 8u * (PG_NKT + k); };           // K stage k written by the epilogue (4 warps)
+  auto BFULL = [&](int s) { return bar0 + 8u * (2 * PG_NKT + s); };
+  auto BEMPTY = [&](int s) { return bar0 + 8u * (2 * PG_NKT + CH_BSTAGES + s); };
+  auto ACCF = [&](int i) { return bar0 + 8u * (2 * PG_NKT + 2 * CH_BSTAGES + i); };
+  auto ACCE = [&](int i) { return bar0 + 8u * (2 * PG_NKT + 2 * CH_BSTAGES + 2 + i); };
+  const uint32_t AFREE = bar0 + 8u * (2 * PG_NKT + 2 * CH_BSTAGES + 4);   // the tile's last GEMM has read the A operand
+  uint32_t* s_tmem = (uint32_t*)(bars + 2 * PG_NKT + 2 * CH_BSTAGES + 5);
+  volatile int* s_abort = (volatile int*)(s_tmem + 1);
+  const int rpc = (((a.R + (int)gridDim.x - 1) / (int)gridDim.x) + 7) & ~7;
+  const int r_begin = min(a.R, (int)blockIdx.x * rpc), r_end = min(a.R, r_begin + rpc);
+  const int n_tiles = (r_end - r_begin + TM - 1) / TM;
+
+  if (tid == 0) {
+    *s_abort = 0;
+    for (int k = 0; k < PG_NKT; ++k) { mbar_init(AL(k), 128); mbar_init(AE(k), 4); }
+    for (int s = 0; s < CH_BSTAGES; ++s) { mbar_init(BFULL(s), 1); mbar_init(BEMPTY(s), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(ACCF(i), 1); mbar_init(ACCE(i), 8); }
+    mbar_init(AFREE, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+
+  if (warp < 8) {
+    // ---- warps 0-7: epilogue (TMEM lane quarter warp & 3; warps 0-3 take the column blocks 0, 2, 4, 6, warps 4-7 the blocks
+    // 1, 3, 5); warps 4-7 are also the loaders of dZ4 ----
+    const int quad = warp & 3, half = warp >> 2;
+    float* stg = s_stg + warp * (32 * STG_PITCH);
+    const int cr = lane >> 3, cc = lane & 7;
+    const int trow = quad * 32 + lane;                                  // this thread's row of the tile
+    const uint32_t a_row = smem_u32(sA) + (trow >> 3) * 128 + (trow & 7) * 16;
+    // GEMM g = 3 t + i produces dZ_{3-i}
+    auto epilogue = [&](int t, int i) {
+      const int g = 3 * t + i, slot = g & 1;
+      const int wrow0 = r_begin + t * TM + quad * 32;
+      const bool live = wrow0 < r_end;                       // warp-uniform
+      uint32_t mbits[8];
+      {                                                      // the row's ReLU words, fetched before the accumulator is ready
+        const int row = wrow0 + lane;
+        uint4 w0 = make_uint4(0u, 0u, 0u, 0u), w1 = w0;      // rows beyond the range: zeros into the next A operand
+        if (row < r_end) {
+          w0 = *(const uint4*)(a.bits[i] + (size_t)row * 8);
+          w1 = *(const uint4*)(a.bits[i] + (size_t)row * 8 + 4);
+        }
+        mbits[0] = w0.x; mbits[1] = w0.y; mbits[2] = w0.z; mbits[3] = w0.w;
+        mbits[4] = w1.x; mbits[5] = w1.y; mbits[6] = w1.z; mbits[7] = w1.w;
+      }
+      mbar_wait(ACCF(slot), (g >> 1) & 1, s_abort);
+      tc_fence_after();
+      const uint32_t tbase = tmem + ((uint32_t)(quad * 32) << 16) + slot * 256;
+      float* out = a.Out[i];
+#pragma unroll 1
+      for (int c0 = 32 * half; c0 < HP; c0 += 64) {
+        uint32_t v[32];
+        const int nc = HP - c0 >= 32 ? 32 : 16;
+        if (nc == 32) tmem_ld32(tbase + c0, v); else tmem_ld16(tbase + c0, v);
+        tmem_wait_ld();
+        if (c0 + 64 >= HP) {                                 // this warp's last block is in registers: hand the slot back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(ACCE(slot));
+        }
+        const uint32_t word = mbits[c0 >> 5];
+        const uint32_t a_stage = a_row + (c0 >> 5) * PG_A_STAGE;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (q * 4 < nc) {
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              o[e] = ((word >> (q * 4 + e)) & 1u) ? tf32_rn(__uint_as_float(v[q * 4 + e])) : 0.f;
+            *(float4*)(stg + lane * STG_PITCH + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
+            if (i < 2)                                       // K chunk q of stage c0 / 32 of the next GEMM's A operand
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_stage + q * PG_LBO_A), "f"(o[0]), "f"(o[1]),
+                           "f"(o[2]), "f"(o[3]) : "memory");
+          }
+        }
+        if (i < 2) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // read by the tensor core (async proxy)
+        __syncwarp();
+        if (i < 2 && lane == 0) mbar_arrive(AE(c0 >> 5));
+        if (live) {
+#pragma unroll
+          for (int r8 = 0; r8 < 8; ++r8) {
+            const int r = r8 * 4 + cr, grow = wrow0 + r;
+            if (grow < r_end && cc * 4 < nc)
+              *(float4*)(out + (size_t)grow * HP + c0 + cc * 4) = *(const float4*)(stg + r * STG_PITCH + cc * 4);
+          }
+        }
+        __syncwarp();
+      }
+    };
+    // dZ4 of tile t: the whole K extent, one barrier per K stage
+    auto load_tile = [&](int t) {
+      const int lr = lane >> 3, c = lane & 7;
+      const int row0 = r_begin + t * TM;
+      for (int kt = 0; kt < PG_NKT; ++kt) {
+        const uint32_t dstA = smem_u32(sA + kt * PG_A_STAGE);
+        if (kt < PG_NKT - 1 || c < 4) {                      // the last stage has 4 chunk planes
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = (quad * 8 + i) * 4 + lr;
+            const int grow = row0 + row;
+            const bool ok = grow < r_end;
+            const float* src = a.A + (size_t)(ok ? grow : 0) * HP + kt * PG_KT + c * 4;
+            cp_async16(dstA + c * PG_LBO_A + (row >> 3) * 128 + (row & 7) * 16, src, ok);
+          }
+        }
+        cp_async_arrive(AL(kt));
+      }
+    };
+    if (half == 1 && n_tiles > 0) load_tile(0);
+    for (int t = 0; t < n_tiles; ++t) {
+      epilogue(t, 0);
+      epilogue(t, 1);
+      if (half == 1 && t + 1 < n_tiles) {
+        mbar_wait(AFREE, t & 1, s_abort);                    // this tile's last GEMM is done with sA
+        load_tile(t + 1);
+      }
+      epilogue(t, 2);
+    }
+  } else if (warp == 8) {
+    // ---- MMA issue ----
+    if (lane == 0) {
+      int g = 0, gb = 0;
+      for (int t = 0; t < n_tiles; ++t) {
+        for (int i = 0; i < 3; ++i, ++g) {
+          const int slot = g & 1;
+          if (g >= 2) { mbar_wait(ACCE(slot), ((g >> 1) - 1) & 1, s_abort); tc_fence_after(); }
+          const uint32_t d = tmem + slot * 256;
+          for (int kt = 0; kt < PG_NKT; ++kt, ++gb) {
+            const int s = gb % CH_BSTAGES, u = gb / CH_BSTAGES;
+            // A stage kt: the loaders' (GEMM 0 of the tile, once per tile) or the previous epilogue's (twice per tile)
+            if (i == 0) mbar_wait(AL(kt), t & 1, s_abort);
+            else mbar_wait(AE(kt), (i - 1) & 1, s_abort);
+            mbar_wait(BFULL(s), u & 1, s_abort);
+            tc_fence_after();
+            const uint32_t aS = smem_u32(sA + kt * PG_A_STAGE), bS = smem_u32(sB + s * PG_B_STAGE);
+            const int nks = kt == PG_NKT - 1 ? 2 : 4;       // the last stage holds K 192..207
+            for (int ks = 0; ks < nks; ++ks) {
+              const uint64_t bd = make_desc(bS + ks * 2 * (HP * 16), HP * 16, 128);
+              const uint64_t ad = make_desc(aS + ks * 2 * PG_LBO_A, PG_LBO_A, 128);
+              mma_ss_tf32(d, ad, bd, IDESC_K, (kt | ks) != 0);
+            }
+            tc_commit(BEMPTY(s));
+          }
+          tc_commit(ACCF(slot));
+          if (i == 2) tc_commit(AFREE);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---- weight stages: the three W^T images per tile ----
+    if (lane == 0) {
+      int gb = 0;
+      for (int t = 0; t < n_tiles; ++t) {
+        for (int i = 0; i < 3; ++i) {
+          for (int kt = 0; kt < PG_NKT; ++kt, ++gb) {
+            const int s = gb % CH_BSTAGES, u = gb / CH_BSTAGES;
+            if (u > 0) mbar_wait(BEMPTY(s), (u - 1) & 1, s_abort);
+            mbar_expect_tx(BFULL(s), PG_B_STAGE);
+            bulk_g2s(smem_u32(sB + s * PG_B_STAGE), a.Bimg[i] + (size_t)kt * (HP * PG_KT), PG_B_STAGE, BFULL(s));
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0 && *s_abort) atomicOr(err, 1);
+  if (warp == 8) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
 // ---- dZ4 and the head's weight gradient -------------------------------------------------------------------------------
 __global__ void __launch_bounds__(THIN_THREADS) upd_dz4_kernel(int R, int H, const float* __restrict__ H4,
                                                                 const float* __restrict__ dl, const float* __restrict__ w4,
@@ -1339,6 +1554,7 @@ static int set_attrs() {
   MBO_CUDA(cudaFuncSetAttribute(upd_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
   MBO_CUDA(cudaFuncSetAttribute(upd_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
   MBO_CUDA(cudaFuncSetAttribute(upd_dgrad_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM));
+  MBO_CUDA(cudaFuncSetAttribute(upd_dgrad_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM));
   MBO_CUDA(cudaFuncSetAttribute(upd_ts_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
   MBO_CUDA(cudaFuncSetAttribute(upd_ts_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev); }
@@ -1467,7 +1683,18 @@ extern "C" int mbo_ppo_policy_grad(int E, int M, int F_state, int F, const int32
   }
   upd_dz4_kernel<<<THIN_CTAS, THIN_THREADS, 0, st>>>(R, H, ws.Hs[3], ws.dl, W[4], ws.dZ[3], ws.part_head);
   if (pack_aside) MBO_CUDA(cudaStreamWaitEvent(st, g_ev_pack, 0));
-  for (int l = 2; l >= 0; --l) {      // dZ_{l+1} = (dZ_{l+2} W_{l+1}) . [h_{l+1} > 0]
+  // Default: the three dgrad GEMMs as ONE persistent kernel (dZ3 / dZ2 go from the epilogue straight into the next GEMM's
+  // shared-memory operand); MBO_UPD_DGRAD_CHAIN=0: one launch per layer (kept: bitwise equal, the A/B reference)
+  const char* ch_env = getenv("MBO_UPD_DGRAD_CHAIN");
+  const bool chain = (ch_env ? atoi(ch_env) != 0 : true) && persist && !dgrad_ts && (fwd_ts || fwd_k2);
+  if (chain) {
+    ChainArgs c{};
+    c.A = ws.dZ[3];
+    for (int i = 0; i < 3; ++i) { c.Bimg[i] = ws.img_dgp[2 - i]; c.Out[i] = ws.dZ[2 - i]; c.bits[i] = ws.hbits[2 - i]; }
+    c.R = R; c.H = H;
+    upd_dgrad_chain_kernel<<<pg_grid, PG_THREADS, CH_SMEM, st>>>(c, ws.err);
+  }
+  for (int l = chain ? -1 : 2; l >= 0; --l) {      // dZ_{l+1} = (dZ_{l+2} W_{l+1}) . [h_{l+1} > 0]
     GemmArgs g{};
     g.A = ws.dZ[l + 1]; g.Bimg = (persist && !dgrad_ts) ? ws.img_dgp[l] : ws.img_dgr[l]; g.Out = ws.dZ[l]; g.bits_in = (l > 0 || fwd_ts || fwd_k2) ? ws.hbits[l] : nullptr;   // SS forward: no h1 words, l = 0 stores dH1, masked in wgrad0
     g.R = R; g.H = H; g.dbg = dbg;
