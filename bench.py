@@ -381,7 +381,7 @@ def ppo_update_rate(dev):
     pg.check()
     flops = 3 * 2 * E * M * (F * H + 3 * H * H + H)
     return {"policy_grad_ms": t_nat, "algorithmic_tflops": flops / t_nat / 1e9, "torch_fp32_autograd_ms": t_ref,
-            "launches_per_step": 12,
+            "launches_per_step": 9,
             "config": "train_metabo_branin.py minibatch (C3): 60 x 966 candidates, F=6, 4x200 ReLU policy; forward = one launch "
                       "of the tcgen05 policy kernel in bf16x3 (fp32-level logits; activations + ReLU words stored for the "
                       "backward), backward single-pass TF32, deterministic split-K"}

@@ -220,8 +220,12 @@ int mbo_cubes_around(int B, int k, int D, const double* x /*[B,k,D]*/, double di
  * The policy-net half of one PPO optimiser step on one (shard of a) minibatch: replaces the autograd
  * forward + backward of ppo.py:129-178 (clipped surrogate + entropy bonus), policies.py:150-161
  * (Categorical(logits).log_prob / entropy) and mlp.py:25-61 for the F -> H -> H -> H -> H -> 1 ReLU
- * policy net (H <= 207, F <= 8).  TF32 tensor-core GEMMs with fp32 accumulation, deterministic
- * (fixed-order split-K reduction, no atomics).
+ * policy net (H <= 207, F <= 8).  Forward: one launch of the tcgen05 policy kernel in its fp32-class
+ * bf16x3 mode (activations + ReLU words stored for the backward); backward: TF32 tensor-core GEMMs with fp32
+ * accumulation; deterministic (fixed-order split-K reduction, no atomics).  The call enqueues on `stream` and
+ * on one library-internal stream forked from it and joined before the call returns (legal inside a stream
+ * capture: the forks become parallel graph branches); the FIRST call of a process creates that stream and
+ * must not be made under capture.
  *   states      [E, M, F_state] fp32 (the PPO buffer's states); feat_col[F] = state column of policy
  *               feature f (policies.py:109-114 feature mask), HOST array
  *   W, b        HOST arrays of 5 device pointers, torch layout W_l [out][in], b_l [out]

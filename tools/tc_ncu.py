@@ -15,8 +15,12 @@ g = torch.Generator(device=dev); g.manual_seed(0)
 cs = ops.CandidateSet(3, tail=torch.rand((M, 3), generator=g, dtype=torch.float64, device=dev))
 mean = torch.randn((B, M), generator=g, device=dev); std = torch.rand((B, M), generator=g, device=dev)
 epi = torch.zeros(B, 4, device=dev); epi[:, 2] = 15; epi[:, 3] = 30
+topk = len(sys.argv) > 4 and sys.argv[4] == "topk"      # the AF round's search phases: selection in the epilogue, no logits written
 lg = None
 for _ in range(3):
-    lg = ops.af_logits(pol, [0, 1, 2, 3, 4, 12, 13], cs, mean, std, epi, B, mode=mode, logits=lg)
+    if topk:
+        idx, val = ops.af_topk(pol, [0, 1, 2, 3, 4, 12, 13], cs, mean, std, epi, B, 5, mode=mode)
+    else:
+        lg = ops.af_logits(pol, [0, 1, 2, 3, 4, 12, 13], cs, mean, std, epi, B, mode=mode, logits=lg)
 torch.cuda.synchronize(); pol.check()
-print("ok", float(lg.abs().max()))
+print("ok", float(val.abs().max()) if topk else float(lg.abs().max()))
