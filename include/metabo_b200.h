@@ -216,6 +216,31 @@ int mbo_candidates_gather(int B, const mbo_candidates* cand, int k, const int32_
 int mbo_cubes_around(int B, int k, int D, const double* x /*[B,k,D]*/, double diam,
                      double* cubes /*[B,k,2,D]*/, void* stream);
 
+/* ---- device-resident environment step ----------------------------------------------
+ * One BO step of B lock-step episodes on the analytic objective families: replaces, for every lane b,
+ *   y = s_b f(x_b - clip(t_b))            metabo/environment/objectives.py:26-80 (Branin), :165-219 (Hartmann-3)
+ *   X[b, t_idx] = x_b, Y[b, t_idx] = y    metabo_gym.py:195-217 (step -> add_data), n[b] = t_idx + 1
+ *   best[b] = max(best[b], y); reward[b]  metabo_gym.py:679-704 (simple regret y_max - best, transformed)
+ *   epi[b] = {incumbent, t_next / T_budget, timestep, budget} of the NEXT state (metabo_gym.py:642-671, 723-730;
+ *            T_training >= 0: timestep = min(t_next, T_training), budget = T_training); epi may be NULL
+ * fp64, one rounding per operation in the order of the reference's expressions.  trans [B, D], scale / y_max /
+ * y_min / best / reward [B] fp64, x [B, D] fp64, X [B, T, D], Y [B, T], n [B] int32, epi [B, 4] fp32. */
+#define MBO_ENV_BRANIN 0
+#define MBO_ENV_HARTMANN3 1
+#define MBO_REWARD_NONE 0
+#define MBO_REWARD_NEG_LINEAR 1
+#define MBO_REWARD_NEG_LOG10 2
+int mbo_env_step(int family, int B, int T, int D, int t_idx, const double* x, const double* trans,
+                 const double* scale, const double* y_max, const double* y_min, double* X, double* Y,
+                 int32_t* n, double* best, int reward_kind, double* reward, float* epi, float t_next,
+                 float T_budget, float T_training, void* stream);
+
+/* get_state (metabo_gym.py:624-677) materialised for the PPO buffer: state[b, m, f] = column feat_src[f] (MBO_FEAT_*,
+ * any of the ten columns, HOST array of F <= 16 codes) of {mean, std, x, incumbent, timestep_perc, timestep, budget} as
+ * fp32; mean / std [B, M] fp32, epi [B, 4] fp32, state [B, M, F] fp32. */
+int mbo_state_pack(int B, const mbo_candidates* cand, int F, const int32_t* feat_src, const float* mean,
+                   const float* std_, const float* epi, float* state /*[B,M,F]*/, void* stream);
+
 /* ---- PPO policy update ------------------------------------------------------------
  * The policy-net half of one PPO optimiser step on one (shard of a) minibatch: replaces the autograd
  * forward + backward of ppo.py:129-178 (clipped surrogate + entropy bonus), policies.py:150-161

@@ -10,6 +10,8 @@ GP_FP64, GP_FP32 = 0, 1
 MLP_FP32, MLP_TF32, MLP_BF16X3, MLP_FP16 = 0, 1, 2, 3
 AF_EI, AF_UCB, AF_PI = 0, 1, 2
 MLP_MODES = {"fp32": MLP_FP32, "tf32": MLP_TF32, "bf16x3": MLP_BF16X3, "fp16": MLP_FP16}
+ENV_BRANIN, ENV_HARTMANN3 = 0, 1
+REWARDS = {"none": 0, "neg_linear": 1, "neg_log10": 2}
 ACT = {"relu": 0, "tanh": 1}
 FEAT_MEAN, FEAT_STD, FEAT_X0, FEAT_INCUMBENT, FEAT_TPERC, FEAT_TIMESTEP, FEAT_BUDGET = 0, 1, 2, 10, 11, 12, 13
 
@@ -54,6 +56,9 @@ SYMBOLS = [
     ("mbo_logits_logp_entropy", _i, [_i, _i, _vp, _vp, _vp, _vp, _vp]),
     ("mbo_candidates_gather", _i, [_i, C.POINTER(Candidates), _i, _vp, _vp, _vp]),
     ("mbo_cubes_around", _i, [_i, _i, _i, _vp, _d, _vp, _vp]),
+    ("mbo_state_pack", _i, [_i, C.POINTER(Candidates), _i, C.POINTER(C.c_int32), _vp, _vp, _vp, _vp, _vp]),
+    ("mbo_env_step", _i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, C.c_float, C.c_float,
+                          C.c_float, _vp]),
     ("mbo_ppo_workspace_bytes", _sz, [_i, _i]),
     ("mbo_ppo_debug_offsets", _i, [_i, _i, C.POINTER(_sz)]),
     ("mbo_ppo_policy_grad", _i, [_i, _i, _i, _i, C.POINTER(C.c_int32), _i, _vp, C.POINTER(_vp), C.POINTER(_vp), _vp, _vp,

@@ -120,7 +120,7 @@ constexpr int TAIL_FLOATS = 5 * TC_N + 4;                    // zeros(b0 is fold
 // packed-weight buffer layout (bytes):
 //   [W0][tf32 hidden x3][bf16 hidden x3][tail floats] | fp16 mode: [W0h][fp16 hidden x3][tail floats][scale exponents]
 struct PackLayout {
-  size_t off_w0, off_tf32, off_bf16, off_tail, off_w0h, off_f16, off_tailh, off_scale, total;
+  size_t off_w0, off_tf32, off_bf16, off_tail, off_w0h, off_f16, off_tailh, off_scale, off_ssq, total;
 };
 __host__ __device__ inline PackLayout pack_layout() {
   PackLayout p;
@@ -132,7 +132,8 @@ __host__ __device__ inline PackLayout pack_layout() {
   p.off_f16 = p.off_w0h + W0_BYTES;
   p.off_tailh = p.off_f16 + (size_t)3 * ModeCfg<MBO_MLP_FP16>::STAGES_PER_LAYER * ModeCfg<MBO_MLP_FP16>::STAGE_BYTES;
   p.off_scale = p.off_tailh + sizeof(float) * TAIL_FLOATS;
-  p.total = p.off_scale + 32;
+  p.off_ssq = p.off_scale + 32;          // tc_scale_kernel scratch: 8 sums of squares (fp64) + a block counter
+  p.total = p.off_ssq + 96;
   return p;
 }
 
@@ -280,12 +281,15 @@ struct PackArgs {
 // the activations handed to layer l+1 to O(1); layer l is packed as 2^(E_l - E_{l-1}) W_l with bias 2^E_l b_l and
 // the head as 2^-E_3 w4 -- the same function in exact arithmetic because relu(c x) = c relu(x) for c > 0.
 // exps[0..3] = per-layer exponents, exps[4] = sticky "a packed value left fp16's range" flag (set by the pack).
-__global__ void tc_scale_kernel(PackArgs a, int* __restrict__ exps) {
+// Eight CTAs, one per sum (q < 4: sum W_q^2, q >= 4: sum b_{q-4}^2); the last CTA to finish derives the exponents
+// (one CTA doing the eight sums in sequence took 220 us per weight sync).  `scratch`: 8 doubles + a counter that the
+// last CTA resets, zero-initialised once when the pack buffer is allocated.
+__global__ void tc_scale_kernel(PackArgs a, int* __restrict__ exps, double* __restrict__ scratch) {
   __shared__ double sh[256];
-  __shared__ double ssq[8];
+  __shared__ bool last;
   const int F = a.F, H = a.H;
-  for (int q = 0; q < 8; ++q) {              // q < 4: sum W_q^2, q >= 4: sum b_{q-4}^2
-    const int l = q & 3;
+  const int q = blockIdx.x, l = q & 3;
+  {
     const int cnt = q < 4 ? H * (l == 0 ? F : H) : H;
     const float* src = q < 4 ? a.W[l] : a.b[l];
     double acc = 0.0;
@@ -296,14 +300,23 @@ __global__ void tc_scale_kernel(PackArgs a, int* __restrict__ exps) {
       if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
       __syncthreads();
     }
-    if (threadIdx.x == 0) ssq[q] = sh[0];
-    __syncthreads();
   }
+  unsigned int* counter = (unsigned int*)(scratch + 8);
   if (threadIdx.x == 0) {
+    scratch[q] = sh[0];
+    __threadfence();
+    last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    volatile double* ssq = scratch;
+    *counter = 0u;
     double est2 = 1.0;
     int Eprev = 0;
-    for (int l = 0; l < 4; ++l) {
-      est2 = ssq[l] / H * est2 + ssq[4 + l] / H;
+    for (int l2 = 0; l2 < 4; ++l2) {
+      est2 = ssq[l2] / H * est2 + ssq[4 + l2] / H;
       int E = Eprev;
       if (est2 > 0.0 && est2 < 1e300) {       // zero, inf or NaN parameters: keep the previous scale
         E = -(int)rint(0.5 * log2(est2));
@@ -311,7 +324,7 @@ __global__ void tc_scale_kernel(PackArgs a, int* __restrict__ exps) {
         E = E > Eprev + 20 ? Eprev + 20 : (E < Eprev - 20 ? Eprev - 20 : E);
         E = E > 60 ? 60 : (E < -60 ? -60 : E);
       }
-      exps[l] = E - Eprev;
+      exps[l2] = E - Eprev;
       Eprev = E;
     }
     exps[4] = 0;
@@ -469,13 +482,14 @@ int tc_pack_weights(mbo_policy* p, cudaStream_t s) {
     if (p->d_tc) cudaFree(p->d_tc);
     p->d_tc = nullptr;
     MBO_CUDA(cudaMalloc(&p->d_tc, pl.total));
+    MBO_CUDA(cudaMemsetAsync((unsigned char*)p->d_tc + pl.off_ssq, 0, 96, s));     // tc_scale_kernel's block counter
     p->tc_bytes = pl.total;
   }
   PackArgs a;
   for (int l = 0; l < 5; ++l) { a.W[l] = p->d_W_raw + p->raw_off[l]; a.b[l] = p->d_b[l]; }
   a.F = F; a.H = H;
   size_t words = pl.total / 4;
-  tc_scale_kernel<<<1, 256, 0, s>>>(a, (int*)((unsigned char*)p->d_tc + pl.off_scale));
+  tc_scale_kernel<<<8, 256, 0, s>>>(a, (int*)((unsigned char*)p->d_tc + pl.off_scale), (double*)((unsigned char*)p->d_tc + pl.off_ssq));
   MBO_LAUNCH_CHECK();
   tc_pack_kernel<<<(unsigned)((words + 255) / 256), 256, 0, s>>>(a, (unsigned char*)p->d_tc, 0);
   MBO_LAUNCH_CHECK();

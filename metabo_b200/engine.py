@@ -283,18 +283,5 @@ class AFEngine:
         return out
 
     def state_tensor(self, cand, mean, std):
-        """Materialise state [B,M,F] fp32 exactly as get_state packs it (for the PPO buffer)."""
-        B, M = mean.shape
-        idx = torch.arange(M, dtype=torch.int32, device=self.dev)[None].expand(B, M).contiguous()
-        x = ops.candidates_gather(cand, idx, B).float()
-        cols = []
-        for c in self.codes_all:
-            if c == L.FEAT_MEAN:
-                cols.append(mean[..., None])
-            elif c == L.FEAT_STD:
-                cols.append(std[..., None])
-            elif L.FEAT_X0 <= c < L.FEAT_X0 + self.D:
-                cols.append(x[..., c - L.FEAT_X0:c - L.FEAT_X0 + 1])
-            else:
-                cols.append(self.epi[:, c - L.FEAT_INCUMBENT].reshape(B, 1, 1).expand(B, M, 1))
-        return torch.cat(cols, dim=2).contiguous()
+        """Materialise state [B,M,F] fp32 exactly as get_state packs it (for the PPO buffer): one kernel."""
+        return ops.state_pack(cand, list(self.codes_all), mean.contiguous(), std.contiguous(), self.epi, mean.shape[0])

@@ -11,6 +11,7 @@ import math
 import numpy as np
 import torch
 
+from .. import _lib as L
 from .. import objectives as obj
 from ..sobol import i4_sobol_generate
 
@@ -35,6 +36,7 @@ class FunctionBatch:
 
 class BraninBatch(FunctionBatch):
     D = 2
+    family = L.ENV_BRANIN           # analytic family of mbo_env_step (the fused device-resident step)
     _tensors = ("t", "s", "y_max", "x_max", "y_min")
 
     def __init__(self, t, s, device):
@@ -50,6 +52,7 @@ class BraninBatch(FunctionBatch):
 
 class Hartmann3Batch(FunctionBatch):
     D = 3
+    family = L.ENV_HARTMANN3
     _tensors = ("t", "s", "y_max", "x_max", "y_min")
 
     def __init__(self, t, s, device):

@@ -11,6 +11,8 @@ Per episode step (MetaBO.step, metabo_gym.py:195-217) for all lanes at once:
 The AF round whose state is never acted on (after the T-th step, metabo_gym.py:211-214) is skipped.
 Only fixed horizons (T_min == T_max) are supported in lock-step mode.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -160,11 +162,12 @@ class VecMetaBO:
         self.best.fill_(-float("inf"))
         return self._round(0, deterministic)
 
-    def _round(self, t, deterministic):
+    def _round(self, t, deterministic, scalars_set=False):
         eng = self.engine
-        inc = torch.where(torch.isinf(self.best), self.fb.y_min, self.best)      # metabo_gym.py:723-730
-        eng.set_episode_scalars(inc.float(), torch.full((self.B,), float(t), device=self.dev),
-                                torch.full((self.B,), float(self.T), device=self.dev))
+        if not scalars_set:              # (the fused environment step has already written them)
+            inc = torch.where(torch.isinf(self.best), self.fb.y_min, self.best)      # metabo_gym.py:723-730
+            eng.set_episode_scalars(inc.float(), torch.full((self.B,), float(t), device=self.dev),
+                                    torch.full((self.B,), float(self.T), device=self.dev))
         cur = eng.af_round(deterministic=deterministic, seed=self.sample_seed, step=0, step_dev=self.step_dev,
                            want_stats=False, want_posterior=self.want_states)
         self.step_dev += 1
@@ -188,9 +191,10 @@ class VecMetaBO:
         tT = torch.stack([epi[:, cols[0]], epi[:, cols[1]]], dim=1).contiguous()
         w = self.engine.value.widths
         if (self.policy.activation == "relu" and len(w) == 6 and len(set(w[1:5])) == 1 and 8 <= w[1] <= 208 and w[5] == 1
-                and self.B >= 64):
+                and self.B >= int(os.environ.get("MBO_VALUE_TC_MIN_B", "1"))):
             # the B lanes as the candidate rows of ONE dense "episode" on the tensor-core kernel (bf16x3: fp32-class):
-            # 8 tiles at B = 1024 instead of 130 us of the CUDA-core kernel per step (6 % of a rollout)
+            # 8 tiles at B = 1024 instead of 130 us of the CUDA-core kernel per step (6 % of a rollout); also for few lanes
+            # (40 episodes: one tile, ~20 us instead of 42 us of mlp_rows_kernel)
             return ops.af_logits_dense(self.engine.value, [0, 1], tT.view(1, self.B, 2), mode=L.MLP_BF16X3)[0]
         return ops.value_net(self.engine.value, tT)
 
@@ -230,6 +234,20 @@ class VecMetaBO:
             from .. import ops
             a = torch.as_tensor(actions, dtype=torch.int32, device=self.dev).reshape(self.B, 1).contiguous()
             x = ops.candidates_gather(prev["cand"], a, self.B)[:, 0]
+        fused = (getattr(self.fb, "family", None) is not None and self.reward_transformation in L.REWARDS
+                 and os.environ.get("MBO_ENV_TORCH") is None)
+        if fused:
+            # ONE kernel: evaluate, append, incumbent, reward and the next state's per-episode scalars (mbo_env_step)
+            from .. import ops
+            reward = ops.env_step(self.fb.family, t, x.contiguous(), self.fb.t, self.fb.s, self.fb.y_max, self.fb.y_min, eng.X, eng.Y,
+                                  eng.n, self.best, L.REWARDS[self.reward_transformation],
+                                  torch.empty(self.B, dtype=torch.float64, device=self.dev),
+                                  epi=eng.epi if do_round else None, t_next=t + 1, T_budget=self.T, T_training=eng.T_training)
+            eng.n_active_max = t + 1
+            out = {"reward": reward, "cur": None}
+            if do_round:
+                out["cur"] = self._round(t + 1, deterministic, scalars_set=True)
+            return out
         y = self.fb.eval(x)
         eng.X[:, t] = x
         eng.Y[:, t] = y

@@ -297,6 +297,32 @@ def cubes_around(x, diam, cubes=None):
     return cubes
 
 
+def state_pack(cand, feat_src, mean, std, epi, B, out=None):
+    """state [B, M, F] fp32 as get_state packs it (`mbo_state_pack`, one launch)."""
+    _chk(mean, torch.float32, "mean"); _chk(std, torch.float32, "std"); _chk(epi, torch.float32, "epi")
+    F = len(feat_src)
+    if out is None:
+        out = torch.empty((B, cand.M, F), dtype=torch.float32, device=mean.device)
+    fs = (C.c_int32 * F)(*feat_src)
+    L.check(L.lib().mbo_state_pack(B, cand.ref(), F, fs, _p(mean), _p(std), _p(epi), _p(out), _stream()), "mbo_state_pack")
+    return out
+
+
+def env_step(family, t_idx, x, trans, scale, y_max, y_min, X, Y, n, best, reward_kind, reward, epi=None, t_next=0.0,
+             T_budget=1.0, T_training=None):
+    """One BO step of all lanes on an analytic objective family (`mbo_env_step`): evaluate, append, incumbent, reward and
+    the per-episode scalars of the next state in ONE launch."""
+    for t_, nm in ((x, "x"), (trans, "trans"), (scale, "scale"), (y_max, "y_max"), (y_min, "y_min"), (X, "X"), (Y, "Y"),
+                   (best, "best"), (reward, "reward")):
+        _chk(t_, torch.float64, nm)
+    _chk(n, torch.int32, "n"); _chk(epi, torch.float32, "epi")
+    B, T, D = X.shape
+    L.check(L.lib().mbo_env_step(int(family), B, T, D, int(t_idx), _p(x), _p(trans), _p(scale), _p(y_max), _p(y_min), _p(X), _p(Y),
+                                 _p(n), _p(best), int(reward_kind), _p(reward), _p(epi), float(t_next), float(T_budget),
+                                 -1.0 if T_training is None else float(T_training), _stream()), "mbo_env_step")
+    return reward
+
+
 class PPOPolicyGrad:
     """Workspace + call wrapper of `mbo_ppo_policy_grad` (the policy-net forward + backward of one PPO optimiser
     step, ppo.py:129-178) for a fixed minibatch shape [E, M, F_state]."""

@@ -360,3 +360,46 @@ def test_gp_family_with_local_af_optimisation(golden_dir):
         r, done = env.step(deterministic=True)
     torch.cuda.synchronize()
     assert done and bool(torch.isfinite(r).all())
+
+
+@pytest.mark.parametrize("family,D", [("bra", 2), ("hm3", 3)])
+@pytest.mark.parametrize("reward", ["none", "neg_linear", "neg_log10"])
+def test_fused_env_step_matches_torch_objectives(family, D, reward):
+    """`mbo_env_step` (one launch: objective value, append, incumbent, reward, next state's scalars) against the torch
+    expressions it replaces (metabo_b200/objectives.py = objectives.py:26-80 / :165-219, metabo_gym.py:679-704, 723-730):
+    the objective value to a few 1e-16 (one rounding per operation in the same order; only the libm calls and the order of two short
+    sums can differ), everything derived from it likewise."""
+    from metabo_b200 import ops, objectives as obj, _lib as L
+    dev = torch.device("cuda:0")
+    B, T, t_idx = 333, 30, 7
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(B, D, generator=g, dtype=torch.float64).to(dev)
+    trans = ((torch.rand(B, D, generator=g, dtype=torch.float64) - 0.5) * 2.2).to(dev)      # beyond the clip ranges too
+    scale = (0.9 + 0.2 * torch.rand(B, generator=g, dtype=torch.float64)).to(dev)
+    fvar, fmax = (obj.bra_var, obj.bra_max) if family == "bra" else (obj.hm3_var, obj.hm3_max)
+    y_ref = fvar(x, trans, scale)
+    y_max, _ = fmax(trans, scale)
+    y_min = y_max - 5.0
+    best0 = torch.full((B,), -float("inf"), dtype=torch.float64, device=dev)
+    best0[::3] = y_ref[::3] + 0.01                      # lanes whose incumbent stays
+    X = torch.zeros(B, T, D, dtype=torch.float64, device=dev); Y = torch.zeros(B, T, dtype=torch.float64, device=dev)
+    n = torch.zeros(B, dtype=torch.int32, device=dev)
+    best = best0.clone()
+    epi = torch.zeros(B, 4, dtype=torch.float32, device=dev)
+    rew = torch.empty(B, dtype=torch.float64, device=dev)
+    ops.env_step(L.ENV_BRANIN if family == "bra" else L.ENV_HARTMANN3, t_idx, x, trans, scale, y_max.contiguous(), y_min.contiguous(),
+                 X, Y, n, best, L.REWARDS[reward], rew, epi=epi, t_next=t_idx + 1, T_budget=T, T_training=None)
+    torch.cuda.synchronize()
+    y = Y[:, t_idx]
+    assert float(((y - y_ref).abs() / y_ref.abs().clamp(min=1.0)).max()) < 1e-15      # values are O(1) sums of O(1) terms
+    others = torch.ones(T, dtype=torch.bool, device=dev); others[t_idx] = False
+    assert torch.equal(X[:, t_idx], x) and float(X[:, others].abs().max()) == 0.0 and float(Y[:, others].abs().max()) == 0.0
+    assert torch.equal(n, torch.full_like(n, t_idx + 1))
+    best_ref = torch.maximum(best0, y)
+    assert torch.equal(best, best_ref)
+    regret = y_max - best_ref
+    rew_ref = {"none": regret, "neg_linear": -regret, "neg_log10": -torch.log10(torch.clamp(regret, min=1e-20))}[reward]
+    assert float((rew - rew_ref).abs().max()) <= 1e-14 * float(rew_ref.abs().max())
+    assert torch.equal(epi[:, 0], best_ref.float())
+    assert torch.equal(epi[:, 1], torch.full((B,), float(t_idx + 1), device=dev) / torch.full((B,), float(T), device=dev))
+    assert float((epi[:, 2] - (t_idx + 1)).abs().max()) == 0.0 and float((epi[:, 3] - T).abs().max()) == 0.0

@@ -3,7 +3,7 @@
 set -e
 cd "$(dirname "$0")/../metabo_b200/csrc"
 mkdir -p ../_build_trace
-for f in api gp mlp_simt reduce neural_af_tc ppo_update ppo_update_simt comm; do
+for f in api gp mlp_simt reduce neural_af_tc ppo_update ppo_update_simt comm env; do
   /usr/local/cuda/bin/nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC \
     --expt-relaxed-constexpr -DMBO_TC_TRACE -DMBO_UPD_TRACE -c $f.cu -o ../_build_trace/$f.o &
 done

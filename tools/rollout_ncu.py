@@ -16,9 +16,11 @@ gym.register(id=spec["env_id"], entry_point="metabo.environment.metabo_gym:MetaB
 opts = {"activations": "relu", "arch_spec": [200] * 4, "use_value_network": True, "t_idx": -2, "T_idx": -1,
         "arch_spec_value": [200] * 4, "mlp_mode": "fp16"}
 nb = int(sys.argv[1]) if len(sys.argv) > 1 else 1
-br = BatchRecorder(size=64 * 16 * 30, env_id=spec["env_id"], env_seeds=list(range(64)),
-                   policy_fn=lambda o, a, d: NeuralAF(o, a, d, options=opts), n_workers=64,
+n_ep = int(sys.argv[2]) if len(sys.argv) > 2 else 1024          # episodes per batch (40 = train_metabo_branin.py's batch of 1200)
+n_w = 64 if n_ep % 64 == 0 else n_ep
+br = BatchRecorder(size=n_ep * 30, env_id=spec["env_id"], env_seeds=list(range(n_w)),
+                   policy_fn=lambda o, a, d: NeuralAF(o, a, d, options=opts), n_workers=n_w,
                    deterministic=False, store_states=True, mlp_mode="fp16", device=torch.device("cuda:0"))
 for i in range(nb):
     t = br.record_batch(0.98, 0.98)
-    print("batch", i, "t_batch %.4f s  %.0f env-steps/s" % (t, 30720 / t), flush=True)
+    print("batch", i, "t_batch %.4f s  %.0f env-steps/s" % (t, n_ep * 30 / t), flush=True)
