@@ -274,3 +274,19 @@ def test_shard_bounds_partition_every_minibatch_exactly():
                 assert all(b - a >= mb // world for a, b in loc) and all(b - a <= -(-max(ng) // world) for a, b in loc)
             for j, (a, b) in enumerate(gb):
                 assert sum(per_rank[r][0][j][1] - per_rank[r][0][j][0] for r in range(world)) == b - a
+
+
+def test_env_step_abi_argument_checks():
+    """mbo_env_step / mbo_state_pack reject bad arguments before any CUDA call (status code + mbo_last_error)."""
+    import ctypes as C
+    from metabo_b200 import _lib
+    lib = _lib.lib()
+    p = C.c_void_p(256)                      # never dereferenced: the checks fire first
+    args = lambda family, B, T, D, t_idx, reward: (family, B, T, D, t_idx, p, p, p, p, p, p, p, p, p, reward, p, None,
+                                                   C.c_float(1.0), C.c_float(30.0), C.c_float(-1.0), None)
+    assert lib.mbo_env_step(*args(7, 4, 30, 2, 0, 2)) == -1 and b"unknown objective family" in lib.mbo_last_error()
+    assert lib.mbo_env_step(*args(_lib.ENV_BRANIN, 4, 30, 3, 0, 2)) == -1 and b"dimensional domain" in lib.mbo_last_error()
+    assert lib.mbo_env_step(*args(_lib.ENV_HARTMANN3, 4, 30, 3, 30, 2)) == -1 and b"t_idx" in lib.mbo_last_error()
+    assert lib.mbo_env_step(*args(_lib.ENV_HARTMANN3, 4, 30, 3, 0, 5)) == -1 and b"reward transformation" in lib.mbo_last_error()
+    assert lib.mbo_state_pack(4, None, 6, None, p, p, p, p, None) == -1 and b"mbo_state_pack" in lib.mbo_last_error()
+    assert set(_lib.REWARDS) == {"none", "neg_linear", "neg_log10"}          # metabo_gym.py:679-704
