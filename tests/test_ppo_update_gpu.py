@@ -105,6 +105,7 @@ def _random_case(seed, E, M, F_state, cols, H):
     (3, 50, 6, [0, 1, 2, 3], 64),              # masked features (exclude_t / exclude_T, policies.py:109-114), narrow net
     (1, 1, 7, [0, 1, 2, 3, 4, 5, 6], 200),     # a single candidate: softmax over one logit, dlogits = 0
     (16, 966, 6, [0, 1, 2, 3, 4, 5], 200),     # Branin minibatch rows (16 x 966)
+    (5, 130, 8, [0, 1, 2, 3, 4, 5, 6, 7], 200),  # all eight state columns at D = 2: layer 0 takes two K = 8 slices (K0S = 2)
 ])
 def test_policy_grad_kernels_against_oracle(E, M, F_state, cols, H):
     layers, states, actions, advs, logp_old = _random_case(E * 1000 + M, E, M, F_state, cols, H)
