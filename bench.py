@@ -255,7 +255,7 @@ def ppo_rollout_rate(dev, world, rank):
                       "(store_states=True, what PPO trains on; 712 MB per batch per GPU)"}
 
 
-def ppo_train_rate(dev, world, rank, episodes_per_gpu, n_epochs, label):
+def ppo_train_rate(dev, world, rank, episodes_per_gpu, n_epochs, label, minibatch=60):
     """BASELINE configs[2] (train_metabo_branin.py:34-113) end to end under world = N: PPO iterations = weight sync +
     rollouts sharded over the ranks (record_batch) + optimize_on_batch with every minibatch of the reference's size
     (60) sharded over the ranks and the gradient exchanged inside the Adam kernel over NVLink peer memory.  Two warm
@@ -279,7 +279,7 @@ def ppo_train_rate(dev, world, rank, episodes_per_gpu, n_epochs, label):
         n_workers, batch = 40, 1200
     else:
         n_workers, batch = 64 * world, episodes_per_gpu * T * world
-    params = {"batch_size": batch, "max_steps": 10 ** 12, "minibatch_size": 60, "n_epochs": n_epochs, "lr": 1e-4,
+    params = {"batch_size": batch, "max_steps": 10 ** 12, "minibatch_size": minibatch, "n_epochs": n_epochs, "lr": 1e-4,
               "epsilon": 0.15, "value_coeff": 1.0, "ent_coeff": 0.01, "gamma": 0.98, "lambda": 0.98,
               "loss_type": "GAElam", "normalize_advs": True, "n_workers": n_workers, "env_id": spec["env_id"], "seed": 0,
               "env_seeds": list(range(n_workers)), "mlp_mode": "fp16",
@@ -315,7 +315,7 @@ def ppo_train_rate(dev, world, rank, episodes_per_gpu, n_epochs, label):
     n_steps = n_epochs * len(ppo._ep["bounds"]) if ppo._ep is not None else None
     if rank == 0:
         shutil.rmtree(logdir, ignore_errors=True)
-    return {"config": label, "global_batch_steps": batch, "minibatch_size": 60, "n_epochs": n_epochs,
+    return {"config": label, "global_batch_steps": batch, "minibatch_size": minibatch, "n_epochs": n_epochs,
             "optimizer_steps_per_iteration": n_steps, "t_weights_s": tw, "t_batch_s": tb, "t_optim_s": to,
             "rollout_env_steps_per_s": batch / tb, "end_to_end_env_steps_per_s": batch / (tw + tb + to),
             "ms_per_optimizer_step": 1e3 * to / n_steps if n_steps else None,
@@ -602,6 +602,10 @@ def main():
                                      "episodes over all ranks, minibatch 60, 4 epochs)"),
                       ppo_train_rate(dev, world, rank, 1024, 1, "C3 at 1024 episodes per GPU (weak scaling of the batch, "
                                      "minibatch 60, 1 epoch per iteration to bound the bench time)")]
+        if world > 1:       # data-parallel weak scaling proper: the global minibatch grows with the ranks, every rank keeps 60 transitions per step
+            train_info.append(ppo_train_rate(dev, world, rank, 1024, 1, "C3 at 1024 episodes per GPU, minibatch 60 PER GPU (global "
+                                             "minibatch %d: weak scaling of batch and minibatch), 1 epoch per iteration" % (60 * world),
+                                             minibatch=60 * world))
 
     cpu_b = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
