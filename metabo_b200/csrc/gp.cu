@@ -367,7 +367,7 @@ __device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, doubl
 // of ~8), (iii) candidates are prepared once per lane (load + X / lengthscale) and handed to the pass that needs
 // them by shuffles, (iv) the per-candidate epilogue (clip, sqrt, store) runs once per lane after the four passes.
 template <int DT, int KID, int NRB_T, int TSV = 32>
-__global__ void __launch_bounds__(NRB_T ? 128 : 256, NRB_T ? 8 : 1)      // NRB_T: 64 registers (no spills) -> 8 CTAs / SM
+__global__ void __launch_bounds__(NRB_T ? 128 : 256, NRB_T ? (NRB_T <= 4 ? 8 : 4) : 1)      // NRB_T <= 4: 64 registers (no spills) -> 8 CTAs / SM; 6, 8 (n <= 48, 64): 128
 gp_posterior_mma_kernel(int nmax, const double* __restrict__ gp_state, mbo_candidates cand, int tiles_per_episode,
                         int ctas_per_episode, void* __restrict__ mean_out, void* __restrict__ std_out, int out_is_f32) {
   extern __shared__ __align__(16) unsigned char smraw[];
@@ -538,11 +538,17 @@ static int launch_posterior_mma_dk(int B, int nmax, int ns, const double* gp_sta
   const int NP = gp_np(ns);
   const int nrb = NP >> 3;
   // small blobs: 4-warp CTAs (many resident CTAs); large blobs (n ~ 100: 50 KB): 8 warps share one copy
-  const int warps = sizeof(double) * ((size_t)NP * cand.D + NP + gp_linv_doubles(NP)) > 20 * 1024 ? 8 : 4;
-  const bool reg_k = nrb >= 1 && nrb <= 4;
+  int warps = sizeof(double) * ((size_t)NP * cand.D + NP + gp_linv_doubles(NP)) > 20 * 1024 ? 8 : 4;
+  // k* in registers: n <= 32 exactly (NRB_T = 1..4), n <= 48 / 64 on the NRB_T = 6 / 8 instantiations (a shorter episode's
+  // extra row / k blocks are zeros) as long as the blob of this call has that many rows
+  const int npmax_rb = gp_np(nmax) >> 3;
   const char* ts_env = getenv("MBO_GP_TS");
   const int ts = ts_env && atoi(ts_env) == 32 ? 32 : 8;      // 8 measured as fast as 32 (n = 30: 1.71 vs 1.73 ms) at a quarter of the table
-  const size_t smem = posterior_mma_smem_bytes(ns, cand.D, warps, !reg_k, ts);
+  int nrb_t = nrb <= 4 ? nrb : (nrb <= 6 && npmax_rb >= 6 ? 6 : (nrb <= 8 && npmax_rb >= 8 ? 8 : 0));
+  if (nrb_t > 4 && (ts == 32 || getenv("MBO_GP_NO_WIDE_REG"))) nrb_t = 0;      // (A/B: the shared-memory k* kernel)
+  const bool reg_k = nrb_t >= 1;
+  if (reg_k) warps = 4;                                        // the register kernels are 4-warp CTAs
+  const size_t smem = posterior_mma_smem_bytes(reg_k ? 8 * nrb_t : ns, cand.D, warps, !reg_k, ts);
   auto kern = gp_posterior_mma_kernel<DT, KID, 0>;
   if (ts == 32) {
     if (nrb == 1) kern = gp_posterior_mma_kernel<DT, KID, 1, 32>;
@@ -554,6 +560,8 @@ static int launch_posterior_mma_dk(int B, int nmax, int ns, const double* gp_sta
     else if (nrb == 2) kern = gp_posterior_mma_kernel<DT, KID, 2, 8>;
     else if (nrb == 3) kern = gp_posterior_mma_kernel<DT, KID, 3, 8>;
     else if (nrb == 4) kern = gp_posterior_mma_kernel<DT, KID, 4, 8>;
+    else if (nrb_t == 6) kern = gp_posterior_mma_kernel<DT, KID, 6, 8>;
+    else if (nrb_t == 8) kern = gp_posterior_mma_kernel<DT, KID, 8, 8>;
   }
   MBO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // same shared-memory carve-out as the tensor-core MLP kernel (maximum): an SM has ONE L1 / shared split at a time, so
