@@ -6,6 +6,7 @@
 // ~1e-6 relative (summation order differs).  The throughput path is neural_af_tc.cu.
 #include "common.cuh"
 #include "policy.cuh"
+#include <stdlib.h>
 
 namespace mbo {
 
@@ -212,6 +213,106 @@ mlp_rows_kernel(SimtNet net, const float* __restrict__ direct, int R, int hmax, 
   }
 }
 
+
+// ---- narrow nets (every width <= 32: train_metabo_gps.py's 4 -> 20 -> 20 -> 1 policy, policies.py:69-74) ----------------
+// mlp_simt_kernel maps a thread to an OUTPUT unit: with 20-wide layers 20 of its 256 threads work (measured: 885 us per
+// 2 M candidates, 37 % of a C4 rollout step).  Here a thread owns a candidate row, its activations live in registers, and the
+// weights -- staged once per CTA, rows padded to a multiple of four outputs -- are warp-broadcast LDS.128: four fma per
+// load.  Same arithmetic per output as mlp_simt_kernel's wide branch (bias first, k ascending, one fma per term).
+constexpr int NW_MAX = 32;          // widest layer / most policy features
+constexpr int NW_THREADS = 256;
+
+__global__ void __launch_bounds__(NW_THREADS)
+mlp_narrow_kernel(SimtNet net, FeatSpec fs, mbo_candidates cand, const float* __restrict__ mean, const float* __restrict__ std_,
+                  const float* __restrict__ epi, const float* __restrict__ direct, long long R, float* __restrict__ out) {
+  extern __shared__ __align__(16) float sw[];      // per layer: W^T [K][N4] then bias [N4]
+  const int tid = threadIdx.x;
+  {
+    int off = 0;
+    for (int l = 0; l < net.n_layers; ++l) {
+      const int K = net.widths[l], N = net.widths[l + 1], N4 = (N + 3) & ~3;
+      for (int e = tid; e < K * N4; e += NW_THREADS) {
+        const int k = e / N4, o = e - k * N4;
+        sw[off + e] = o < N ? net.Wt[l][(size_t)k * N + o] : 0.f;
+      }
+      for (int o = tid; o < N4; o += NW_THREADS) sw[off + K * N4 + o] = o < N ? net.b[l][o] : 0.f;
+      off += (K + 1) * N4;
+    }
+  }
+  __syncthreads();
+  const long long row = (long long)blockIdx.x * NW_THREADS + tid;
+  if (row >= R) return;
+  const int F = net.widths[0];
+  float h[NW_MAX];
+#pragma unroll
+  for (int i = 0; i < NW_MAX; ++i) h[i] = 0.f;
+  if (direct) {
+#pragma unroll
+    for (int f = 0; f < NW_MAX; ++f) if (f < F) h[f] = direct[(size_t)row * F + f];
+  } else {
+    const int b = (int)(row / cand.M), m = (int)(row - (long long)b * cand.M);
+    double x[MBO_MAX_D];
+#pragma unroll
+    for (int d = 0; d < MBO_MAX_D; ++d) x[d] = 0.0;
+    float mu = 0.f, sd = 0.f;
+    if (!fs.dense) {
+      load_candidate(cand, b, m, x);
+      mu = mean[row];
+      sd = std_[row];
+    }
+#pragma unroll
+    for (int f = 0; f < NW_MAX; ++f) {
+      if (f < F) {
+        const int sidx = fs.src[f];
+        float v;
+        if (fs.dense) v = fs.dense[(size_t)row * fs.dense_F + sidx];
+        else if (sidx == MBO_FEAT_MEAN) v = mu;
+        else if (sidx == MBO_FEAT_STD) v = sd;
+        else if (sidx >= MBO_FEAT_X0 && sidx < MBO_FEAT_X0 + MBO_MAX_D) {
+          v = 0.f;
+#pragma unroll
+          for (int d = 0; d < MBO_MAX_D; ++d) if (sidx - MBO_FEAT_X0 == d) v = (float)x[d];
+        } else v = epi[b * 4 + (sidx - MBO_FEAT_INCUMBENT)];
+        h[f] = v;
+      }
+    }
+  }
+  int off = 0;
+  for (int l = 0; l < net.n_layers; ++l) {
+    const int K = net.widths[l], N = net.widths[l + 1], N4 = (N + 3) & ~3;
+    const float4* W4 = reinterpret_cast<const float4*>(sw + off);
+    const float4* B4 = reinterpret_cast<const float4*>(sw + off + K * N4);
+    const bool last = l == net.n_layers - 1;
+    float o_[NW_MAX];
+#pragma unroll
+    for (int o4 = 0; o4 < NW_MAX / 4; ++o4) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (4 * o4 < N) {
+        acc = B4[o4];
+#pragma unroll
+        for (int k = 0; k < NW_MAX; ++k) {
+          if (k < K) {
+            const float4 w = W4[k * (N4 >> 2) + o4];
+            acc.x = fmaf(w.x, h[k], acc.x); acc.y = fmaf(w.y, h[k], acc.y);
+            acc.z = fmaf(w.z, h[k], acc.z); acc.w = fmaf(w.w, h[k], acc.w);
+          }
+        }
+        if (!last) {
+          acc.x = act_fn(net.activation, acc.x); acc.y = act_fn(net.activation, acc.y);
+          acc.z = act_fn(net.activation, acc.z); acc.w = act_fn(net.activation, acc.w);
+        }
+      }
+      o_[4 * o4 + 0] = acc.x; o_[4 * o4 + 1] = acc.y; o_[4 * o4 + 2] = acc.z; o_[4 * o4 + 3] = acc.w;
+    }
+#pragma unroll
+    for (int i = 0; i < NW_MAX; ++i) h[i] = i < N ? o_[i] : 0.f;
+    off += (K + 1) * N4;
+  }
+  const int NO = net.widths[net.n_layers];
+#pragma unroll
+  for (int o = 0; o < NW_MAX; ++o) if (o < NO) out[(size_t)row * NO + o] = h[o];
+}
+
 int simt_forward(const mbo_policy* p, int B, int F, const int32_t* feat_src, const mbo_candidates* cand,
                  const float* mean, const float* std_, const float* epi, const float* direct, int R,
                  float* out, cudaStream_t s, const float* dense = nullptr, int dense_F = 0) {
@@ -228,6 +329,20 @@ int simt_forward(const mbo_policy* p, int B, int F, const int32_t* feat_src, con
   mbo_candidates c0;
   memset(&c0, 0, sizeof(c0));
   int grid, tiles = 1;
+  // narrow nets with many rows: thread = row (mlp_narrow_kernel)
+  bool narrow = hmax <= NW_MAX && getenv("MBO_MLP_NO_NARROW") == nullptr;
+  const long long rows = direct ? (long long)R : (long long)B * cand->M;
+  if (narrow && rows >= 4096) {
+    size_t smem_w = 0;
+    for (int l = 0; l < p->n_layers; ++l) smem_w += sizeof(float) * (size_t)(p->widths[l] + 1) * ((p->widths[l + 1] + 3) & ~3);
+    if (!direct) {
+      for (int f = 0; f < F; ++f) fs.src[f] = feat_src[f];
+      c0 = *cand;
+    }
+    mlp_narrow_kernel<<<(unsigned)((rows + NW_THREADS - 1) / NW_THREADS), NW_THREADS, smem_w, s>>>(net, fs, c0, mean, std_, epi, direct, rows, out);
+    MBO_LAUNCH_CHECK();
+    return MBO_OK;
+  }
   if (direct) {
     // few dense rows: weights staged in shared memory when the widest layer fits
     int wmax = 0;
